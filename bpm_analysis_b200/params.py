@@ -1,0 +1,81 @@
+"""The params contract of the hot path.
+
+The reference passes one flat dict (``config.py:3-108`` ``DEFAULT_PARAMS``) to
+every function.  This package consumes that dict unchanged; the table below
+only lists the 12 keys the data-parallel front end reads with
+the reference's default values, so the package is usable standalone.  Callers
+that already hold the reference's ``DEFAULT_PARAMS`` just pass it through.
+
+Optional keys this package adds (absent => reference behaviour):
+
+``filter_mode``   ``"parity"`` (default): stride-decimate, then band-pass at the
+                  envelope rate -- what ``bpm_analysis.py:1031-1045`` does.
+                  ``"fullrate"``: band-pass at the original rate (the order
+                  ``README.md:6`` documents), then take every ds-th sample.
+``lowcut_hz`` / ``highcut_hz``   band edges, hard-coded 20/150 in
+                  ``bpm_analysis.py:1018``; exposed for the C5 sweep.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+HOT_PATH_DEFAULTS: Dict[str, object] = {
+    "downsample_factor": 300,
+    "save_filtered_wav": True,
+    "min_peak_distance_sec": 0.05,
+    "peak_prominence_quantile": 0.1,
+    "trough_prominence_quantile": 0.1,
+    "noise_floor_quantile": 0.20,
+    "noise_window_sec": 10,
+    "trough_rejection_multiplier": 4.0,
+    "deviation_smoothing_factor": 0.05,
+    "output_smoothing_window_sec": 5,
+    "hrv_window_size_beats": 40,
+    "hrv_step_size_beats": 5,
+}
+
+# constants the reference hard-codes on the hot path (file:line in bpm_analysis.py)
+LOWCUT_HZ = 20.0            # :1018
+HIGHCUT_HZ = 150.0          # :1018
+FILTER_ORDER = 2            # :1044
+MIN_TROUGHS_FOR_DYNAMIC = 5  # :1073
+ROLLING_MIN_PERIODS = 3     # :1085
+MIN_SANITIZED_TROUGHS = 2   # :1102  (strictly more than)
+FALLBACK_QUANTILE = 0.1     # :1114
+STRENGTH_EPS = 1e-9         # :96
+MIN_DEV_WINDOW = 5          # :99
+MIN_TIME_DIFF = 1e-6        # :1468
+SLOPE_WINDOW_SEC = 20       # :1552, :1576
+HR_PROMINENCE = 5           # :1496
+HR_MIN_DURATION_SEC = 10    # :1486
+HR_MIN_CHANGE_BPM = 15      # :1486
+
+
+def default_params() -> Dict[str, object]:
+    """A fresh copy of the hot-path defaults."""
+    return dict(HOT_PATH_DEFAULTS)
+
+
+def band_edges(params: Dict) -> tuple:
+    return float(params.get("lowcut_hz", LOWCUT_HZ)), float(params.get("highcut_hz", HIGHCUT_HZ))
+
+
+def filter_mode(params: Dict) -> str:
+    mode = params.get("filter_mode", "parity")
+    if mode not in ("parity", "fullrate"):
+        raise ValueError(f"filter_mode must be 'parity' or 'fullrate', got {mode!r}")
+    return mode
+
+
+def effective_decimation(sample_rate: int, params: Dict):
+    """``(ds, new_rate, clamped)`` as ``bpm_analysis.py:1021-1036`` computes them."""
+    ds = params["downsample_factor"]
+    _, highcut = band_edges(params)
+    max_safe = int((sample_rate / (highcut * 2)) - 1)
+    clamped = False
+    if ds > max_safe:
+        ds = max(1, max_safe)
+        clamped = True
+    if ds > 1:
+        return int(ds), int(sample_rate // ds), clamped
+    return 1, int(sample_rate), clamped
