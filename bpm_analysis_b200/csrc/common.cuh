@@ -1,0 +1,131 @@
+// Shared helpers for libbpm_b200 (sm_100a).  See include/bpm_b200.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <math.h>
+#include "../../include/bpm_b200.h"
+
+namespace bpm {
+
+constexpr int PADLEN = 15;            // scipy filtfilt default pad for this filter (Appendix A.1)
+constexpr int SCAN_CHUNK = 8;         // == design.py SCAN_CHUNK
+constexpr int SCAN_THREADS = 256;     // == design.py SCAN_THREADS
+constexpr int SCAN_TILE = SCAN_CHUNK * SCAN_THREADS;
+constexpr int N_POW = 16;
+
+extern int64_t g_launches;            // counted by LAUNCH_OK
+
+#define BPM_LAUNCH_OK()                                          \
+  do {                                                           \
+    ++::bpm::g_launches;                                         \
+    if (cudaGetLastError() != cudaSuccess) return BPM_ERR_CUDA;  \
+  } while (0)
+
+#define BPM_TRY(expr)                 \
+  do {                                \
+    int _rc = (expr);                 \
+    if (_rc != BPM_OK) return _rc;    \
+  } while (0)
+
+// ---------------------------------------------------------------- workspace
+// Bump allocator over the caller's workspace.  With base == nullptr it only
+// measures, so *_workspace_bytes() and the real call share one code path.
+struct Workspace {
+  char* base;
+  size_t cap;
+  size_t used = 0;
+  bool overflow = false;
+  Workspace(void* b, size_t c) : base(static_cast<char*>(b)), cap(c) {}
+  template <class T>
+  T* take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    size_t at = used;
+    used += bytes;
+    if (base == nullptr) return reinterpret_cast<T*>(uintptr_t(256));  // measuring
+    if (used > cap) { overflow = true; return nullptr; }
+    return reinterpret_cast<T*>(base + at);
+  }
+  bool measuring() const { return base == nullptr; }
+};
+
+struct BatchShape {
+  int n_items = 0;
+  int64_t total_m = 0;   // sum of m  (assumes items are packed back to back)
+  int64_t max_m = 0;
+  int64_t max_n_in = 0;
+};
+
+inline BatchShape batch_shape(const BpmItem* items_host, int n_items) {
+  BatchShape s;
+  s.n_items = n_items;
+  for (int i = 0; i < n_items; ++i) {
+    if (items_host[i].m > s.max_m) s.max_m = items_host[i].m;
+    if (items_host[i].n_in > s.max_n_in) s.max_n_in = items_host[i].n_in;
+    int64_t end = items_host[i].m_off + items_host[i].m;
+    if (end > s.total_m) s.total_m = end;
+  }
+  return s;
+}
+
+inline unsigned cdiv(int64_t a, int64_t b) { return static_cast<unsigned>((a + b - 1) / b); }
+
+// ------------------------------------------------------------- device helpers
+// total order on doubles as unsigned keys (negative values flipped)
+__host__ __device__ __forceinline__ unsigned long long f64_key(double v) {
+#ifdef __CUDA_ARCH__
+  unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+#else
+  unsigned long long b;
+  memcpy(&b, &v, 8);
+#endif
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_f64(unsigned long long k) {
+  unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double(static_cast<long long>(b));
+}
+
+__device__ __forceinline__ double shfl_up_f64(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double shfl_f64(double v, int l) { return __shfl_sync(0xffffffffu, v, l); }
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// exclusive prefix of `v` across the block (blockDim.x <= 1024); total in *total
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* smem /* >= 33 ints */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) smem[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+    int x = lane < nw ? smem[lane] : 0;
+    int xi = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, xi, o);
+      if (lane >= o) xi += t;
+    }
+    smem[lane] = xi - x;
+    if (lane == 31) smem[32] = xi;
+  }
+  __syncthreads();
+  int res = smem[w] + inc - v;
+  *total = smem[32];
+  __syncthreads();
+  return res;
+}
+
+// x' = sign * x with sign in {+1, -1} (exact)
+__device__ __forceinline__ double signed_val(double v, int sign) { return sign < 0 ? -v : v; }
+
+}  // namespace bpm

@@ -1,0 +1,641 @@
+// K0 + K1 + K2 (+K2b): pcm -> zero-phase band-pass at the kept samples -> envelope.
+//
+// Replaces, on the device, what preprocess_audio does with numpy/scipy/pandas
+// (bpm_analysis.py:1015-1054): stereo mean, x[::ds], butter(2,'band') + filtfilt,
+// abs, centred rolling mean.  The mathematics of the blocked forward-backward
+// evaluation is in bpm_analysis_b200/design.py; a serial numpy model of exactly
+// these kernels is oracle/kernel_models.py::blocked_filtfilt.
+//
+//   k_contract_*   per kept sample j:  uf[j] = sum_l wf[l] x[E_j+l]   (4-vector)
+//                                      ub0[j] = sum_l q[l] x[E_j+l]   (4-vector)
+//                  HBM-bound when block == ds (filter at the original rate).
+//   k_filter_init  s_f[E_0] from the 15 padded samples and the steady state zi*x[0].
+//   k_scan<FWD>    s_f[j+1] = Ad s_f[j] + uf[j]              (chunked scan, warp-shuffle carries)
+//   k_filter_tail  serial forward over the last block + right padding, then backward
+//                  down to E_{m-1}, seeded with zi*y_f[last] (scipy's second pass).
+//   k_scan<BWD>    s_b[j] = Ad s_b[j+1] + P s_f[j] + ub0[j];  y[j] = C s_b[j] + D y_f[j]
+//   k_envelope     |y| -> centred rolling mean (pandas FixedWindowIndexer semantics).
+#include "common.cuh"
+
+namespace bpm {
+
+int64_t g_launches = 0;
+
+// ------------------------------------------------------------------ design view
+struct DesignView {
+  const double* w;
+  __device__ __forceinline__ int block() const { return static_cast<int>(w[0]); }
+  __device__ __forceinline__ int lookback() const {
+    double v = w[1];
+    return v > 1.0e9 ? 1000000000 : static_cast<int>(v);
+  }
+  __device__ __forceinline__ double D() const { return w[2]; }
+  __device__ __forceinline__ const double* sos() const { return w + 4; }
+  __device__ __forceinline__ const double* zi() const { return w + 16; }
+  __device__ __forceinline__ const double* C() const { return w + 20; }
+  __device__ __forceinline__ const double* Ad() const { return w + 24; }
+  __device__ __forceinline__ const double* P() const { return w + 40; }
+  __device__ __forceinline__ const double* pw(int k) const { return w + 56 + 16 * k; }
+  __device__ __forceinline__ const double* wf() const { return w + BPM_DESIGN_HEADER_WORDS; }
+  __device__ __forceinline__ const double* q() const { return w + BPM_DESIGN_HEADER_WORDS + 4 * block(); }
+};
+
+// ------------------------------------------------------------------ pcm access
+struct PcmView {
+  const void* base;
+  int dtype;
+  int channels;
+};
+
+// one frame as float64; multi-channel frames are averaged the way np.mean(axis=1) does
+// (bpm_analysis.py:1016): integer sums are exact, float32 accumulates in float32.
+__device__ __forceinline__ double pcm_frame(const PcmView& p, int64_t f) {
+  const int ch = p.channels;
+  switch (p.dtype) {
+    case BPM_PCM_I16: {
+      const int16_t* b = static_cast<const int16_t*>(p.base);
+      if (ch == 1) return static_cast<double>(b[f]);
+      long long s = 0;
+      for (int c = 0; c < ch; ++c) s += b[f * ch + c];
+      return static_cast<double>(s) / static_cast<double>(ch);
+    }
+    case BPM_PCM_I32: {
+      const int32_t* b = static_cast<const int32_t*>(p.base);
+      if (ch == 1) return static_cast<double>(b[f]);
+      long long s = 0;
+      for (int c = 0; c < ch; ++c) s += b[f * ch + c];
+      return static_cast<double>(s) / static_cast<double>(ch);
+    }
+    case BPM_PCM_U8: {
+      const uint8_t* b = static_cast<const uint8_t*>(p.base);
+      if (ch == 1) return static_cast<double>(b[f]);
+      long long s = 0;
+      for (int c = 0; c < ch; ++c) s += b[f * ch + c];
+      return static_cast<double>(s) / static_cast<double>(ch);
+    }
+    case BPM_PCM_F32: {
+      const float* b = static_cast<const float*>(p.base);
+      if (ch == 1) return static_cast<double>(b[f]);
+      float s = b[f * ch];
+      for (int c = 1; c < ch; ++c) s = __fadd_rn(s, b[f * ch + c]);
+      return static_cast<double>(__fdiv_rn(s, static_cast<float>(ch)));
+    }
+    default: {
+      const double* b = static_cast<const double*>(p.base);
+      if (ch == 1) return b[f];
+      double s = b[f * ch];
+      for (int c = 1; c < ch; ++c) s = __dadd_rn(s, b[f * ch + c]);
+      return __ddiv_rn(s, static_cast<double>(ch));
+    }
+  }
+}
+
+// the filter's input with scipy's odd extension (Appendix A.1): e in [0, n_dec + 30)
+struct ExtSignal {
+  PcmView pcm;
+  int64_t in_off, n_dec, stride;
+  __device__ __forceinline__ double s(int64_t i) const { return pcm_frame(pcm, in_off + i * stride); }
+  __device__ __forceinline__ double at(int64_t e) const {
+    int64_t i = e - PADLEN;
+    if (i < 0) return __dsub_rn(__dmul_rn(2.0, s(0)), s(-i));
+    if (i >= n_dec) return __dsub_rn(__dmul_rn(2.0, s(n_dec - 1)), s(2 * (n_dec - 1) - i));
+    return s(i);
+  }
+};
+
+__device__ __forceinline__ ExtSignal make_ext(const PcmView& pcm, const BpmItem& it, int64_t stride) {
+  ExtSignal x;
+  x.pcm = pcm;
+  x.in_off = it.in_off;
+  x.stride = stride;
+  x.n_dec = (it.n_in + stride - 1) / stride;
+  return x;
+}
+
+// one sample through the two-section cascade, direct form II transposed
+__device__ __forceinline__ double df2t_step(const double* __restrict__ sos, double s[4], double x) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const double b0 = sos[6 * k], b1 = sos[6 * k + 1], b2 = sos[6 * k + 2];
+    const double a1 = sos[6 * k + 4], a2 = sos[6 * k + 5];
+    const double y = b0 * x + s[2 * k];
+    s[2 * k] = b1 * x - a1 * y + s[2 * k + 1];
+    s[2 * k + 1] = b2 * x - a2 * y;
+    x = y;
+  }
+  return x;
+}
+
+__device__ __forceinline__ void matvec4(const double* __restrict__ M, const double v[4], double out[4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    out[r] = M[4 * r] * v[0] + M[4 * r + 1] * v[1] + M[4 * r + 2] * v[2] + M[4 * r + 3] * v[3];
+}
+// v = M v + add
+__device__ __forceinline__ void affine4(const double* __restrict__ M, double v[4], const double add[4]) {
+  double t[4];
+  matvec4(M, v, t);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) v[r] = t[r] + add[r];
+}
+
+// ------------------------------------------------------------ contraction (generic)
+// Any dtype / channel count / stride / block.  One thread per kept sample.
+__global__ void __launch_bounds__(256) k_contract_generic(PcmView pcm, const BpmItem* __restrict__ items,
+                                                          int64_t stride, const double* __restrict__ design,
+                                                          double* __restrict__ uf, double* __restrict__ ub0,
+                                                          double* __restrict__ xe) {
+  const BpmItem it = items[blockIdx.y];
+  const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j >= it.m) return;
+  const DesignView d{design};
+  const int blk = d.block();
+  const ExtSignal x = make_ext(pcm, it, stride);
+  const int64_t E = PADLEN + j * blk;
+  const double x0 = x.at(E);
+  xe[it.m_off + j] = x0;
+  if (j >= it.m - 1) return;
+  const double* __restrict__ wf = d.wf();
+  const double* __restrict__ q = d.q();
+  double f[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+  double v = x0;
+  for (int l = 0; l < blk; ++l) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      f[c] += wf[4 * l + c] * v;
+      b[c] += q[4 * l + c] * v;
+    }
+    v = x.at(E + l + 1);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) b[c] += q[4 * blk + c] * v;
+  double* pf = uf + 4 * (it.m_off + j);
+  double* pb = ub0 + 4 * (it.m_off + j);
+  reinterpret_cast<double2*>(pf)[0] = make_double2(f[0], f[1]);
+  reinterpret_cast<double2*>(pf)[1] = make_double2(f[2], f[3]);
+  reinterpret_cast<double2*>(pb)[0] = make_double2(b[0], b[1]);
+  reinterpret_cast<double2*>(pb)[1] = make_double2(b[2], b[3]);
+}
+
+// ------------------------------------------------------ contraction (int16, full rate)
+// The HBM-bound kernel: mono int16 at the original rate (stride 1), block = ds.
+// A CTA stages CT_BLOCKS consecutive blocks (+1 sample) of PCM in shared memory with
+// 128-bit coalesced loads (raw int16, converted at use), then each thread owns one block
+// and accumulates its 8 dot products; the weight rows are read as warp-wide broadcasts.
+// The first / last CTA of a recording (odd-extension samples) take the direct path.
+constexpr int CT_THREADS = 128;
+constexpr int CT_BLOCKS = 128;     // kept samples per CTA
+
+__global__ void __launch_bounds__(CT_THREADS) k_contract_i16(const int16_t* __restrict__ pcm,
+                                                             const BpmItem* __restrict__ items,
+                                                             const double* __restrict__ design,
+                                                             double* __restrict__ uf, double* __restrict__ ub0,
+                                                             double* __restrict__ xe) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const BpmItem it = items[blockIdx.y];
+  const int64_t j0 = static_cast<int64_t>(blockIdx.x) * CT_BLOCKS;
+  if (j0 >= it.m) return;
+  const DesignView d{design};
+  const int blk = d.block();
+  const int64_t n = it.n_in;                               // stride 1: n_dec == n_in
+  const int nb = static_cast<int>(min(static_cast<int64_t>(CT_BLOCKS), it.m - j0));
+  const int span = nb * blk + 1;                           // samples E_j0 .. E_j0 + nb*blk
+  // shared layout: weights [(blk+1)][8] (wf row | q row), then raw PCM as 16-byte vectors
+  double* s_w = reinterpret_cast<double*>(smem_raw);
+  int4* s_v = reinterpret_cast<int4*>(s_w + 8 * (blk + 1));
+  const double* __restrict__ wf = d.wf();
+  const double* __restrict__ q = d.q();
+  for (int t = threadIdx.x; t < 4 * (blk + 1); t += CT_THREADS) {
+    const int l = t >> 2, c = t & 3;
+    s_w[8 * l + c] = (l < blk) ? wf[4 * l + c] : 0.0;
+    s_w[8 * l + 4 + c] = q[4 * l + c];
+  }
+  const int64_t i0 = j0 * blk;                              // data index of the first staged sample
+  const int16_t* __restrict__ src = pcm + it.in_off;
+  const bool interior = (i0 >= 8) && (i0 + span + 8 <= n);
+  int head = 0;
+  if (interior) {
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(src + i0);
+    head = static_cast<int>((addr & 15) >> 1);             // samples before i0 in its 16-byte word
+    const int4* __restrict__ v = reinterpret_cast<const int4*>(src + i0 - head);
+    const int nvec = (head + span + 7) >> 3;
+    for (int t = threadIdx.x; t < nvec; t += CT_THREADS) s_v[t] = __ldg(v + t);
+  }
+  __syncthreads();
+  const int jl = threadIdx.x;
+  if (jl >= nb) return;
+  const int64_t j = j0 + jl;
+  double f0 = 0, f1 = 0, f2 = 0, f3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+  double x0;
+  const bool bulk = (j < it.m - 1);
+  if (interior) {
+    const int16_t* __restrict__ xs = reinterpret_cast<const int16_t*>(s_v) + head + jl * blk;
+    x0 = static_cast<double>(xs[0]);
+    if (bulk) {
+#pragma unroll 4
+      for (int l = 0; l <= blk; ++l) {
+        const double v = static_cast<double>(xs[l]);
+        const double2 w0 = *reinterpret_cast<const double2*>(s_w + 8 * l);
+        const double2 w1 = *reinterpret_cast<const double2*>(s_w + 8 * l + 2);
+        const double2 w2 = *reinterpret_cast<const double2*>(s_w + 8 * l + 4);
+        const double2 w3 = *reinterpret_cast<const double2*>(s_w + 8 * l + 6);
+        f0 += w0.x * v; f1 += w0.y * v; f2 += w1.x * v; f3 += w1.y * v;
+        b0 += w2.x * v; b1 += w2.y * v; b2 += w3.x * v; b3 += w3.y * v;
+      }
+    }
+  } else {
+    PcmView pv{pcm, BPM_PCM_I16, 1};
+    const ExtSignal x = make_ext(pv, it, 1);
+    const int64_t E = PADLEN + j * blk;
+    x0 = x.at(E);
+    if (bulk) {
+      for (int l = 0; l <= blk; ++l) {
+        const double v = x.at(E + l);
+        const double* w = s_w + 8 * l;
+        f0 += w[0] * v; f1 += w[1] * v; f2 += w[2] * v; f3 += w[3] * v;
+        b0 += w[4] * v; b1 += w[5] * v; b2 += w[6] * v; b3 += w[7] * v;
+      }
+    }
+  }
+  xe[it.m_off + j] = x0;
+  if (!bulk) return;
+  double* pf = uf + 4 * (it.m_off + j);
+  double* pb = ub0 + 4 * (it.m_off + j);
+  reinterpret_cast<double2*>(pf)[0] = make_double2(f0, f1);
+  reinterpret_cast<double2*>(pf)[1] = make_double2(f2, f3);
+  reinterpret_cast<double2*>(pb)[0] = make_double2(b0, b1);
+  reinterpret_cast<double2*>(pb)[1] = make_double2(b2, b3);
+}
+
+// ------------------------------------------------------------------ init / tail
+__global__ void k_filter_init(PcmView pcm, const BpmItem* __restrict__ items, int n_items, int64_t stride,
+                              const double* __restrict__ design, double* __restrict__ s0) {
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= n_items) return;
+  const BpmItem it = items[item];
+  const DesignView d{design};
+  const ExtSignal x = make_ext(pcm, it, stride);
+  double s[4];
+  const double x0 = x.at(0);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) s[c] = d.zi()[c] * x0;
+  for (int e = 0; e < PADLEN; ++e) df2t_step(d.sos(), s, x.at(e));
+#pragma unroll
+  for (int c = 0; c < 4; ++c) s0[4 * item + c] = s[c];
+}
+
+__global__ void k_filter_tail(PcmView pcm, const BpmItem* __restrict__ items, int n_items, int64_t stride,
+                              const double* __restrict__ design, const double* __restrict__ sf,
+                              double* __restrict__ tail_buf, int tail_cap, double* __restrict__ sb_last) {
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= n_items) return;
+  const BpmItem it = items[item];
+  const DesignView d{design};
+  const ExtSignal x = make_ext(pcm, it, stride);
+  const int blk = d.block();
+  const int64_t le = x.n_dec + 2 * PADLEN;
+  const int64_t e_last = PADLEN + (it.m - 1) * blk;
+  const int lt = static_cast<int>(le - e_last);
+  double* yf = tail_buf + static_cast<size_t>(item) * tail_cap;
+  double s[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) s[c] = sf[4 * (it.m_off + it.m - 1) + c];
+  for (int k = 0; k < lt; ++k) yf[k] = df2t_step(d.sos(), s, x.at(e_last + k));
+  const double ylast = yf[lt - 1];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) s[c] = d.zi()[c] * ylast;
+  for (int k = lt - 1; k >= 1; --k) df2t_step(d.sos(), s, yf[k]);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) sb_last[4 * item + c] = s[c];
+}
+
+// ------------------------------------------------------------------ low-rate scans
+struct ScanParams {
+  const BpmItem* items;
+  const double* design;
+  const double* u;        // FWD: uf       BWD: ub0
+  double* sf;             // FWD: out      BWD: in
+  const double* xe;       // BWD only
+  const double* s_init;   // FWD: s0[item] BWD: sb_last[item]
+  double* agg;            // tile aggregates [tile_slot][4]
+  double* y;              // BWD apply: filtered signal out
+  unsigned long long* absmax_bits;  // BWD apply: max |y| per item (bit pattern of a non-negative double)
+};
+
+__device__ __forceinline__ int64_t tile_slot0(const BpmItem& it, int item) {
+  return it.m_off / SCAN_TILE + item;
+}
+
+template <int DIR /*0 fwd, 1 bwd*/, bool APPLY>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(ScanParams p) {
+  __shared__ double sm_pow[9 * 16];      // Ad^(CHUNK*2^k), k = 0..8
+  __shared__ double sm_Ad[16], sm_P[16], sm_C[4];
+  __shared__ double sm_tot[SCAN_THREADS / 32][4];
+  __shared__ double sm_pre[SCAN_THREADS / 32][4];
+
+  const int item = blockIdx.y;
+  const BpmItem it = p.items[item];
+  const DesignView d{p.design};
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t ns = it.m - 1;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * SCAN_TILE;
+  const double Dd = d.D();
+
+  if (APPLY && blockIdx.x == 0 && tid == 0) {
+    // the state that needs no step: s_f[0], or y[m-1] from s_b[m-1]
+    const double* si = p.s_init + 4 * item;
+    if (DIR == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) p.sf[4 * it.m_off + c] = si[c];
+    } else {
+      const double* sfl = p.sf + 4 * (it.m_off + it.m - 1);
+      double yf = Dd * p.xe[it.m_off + it.m - 1], yb = 0.0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { yf += d.C()[c] * sfl[c]; yb += d.C()[c] * si[c]; }
+      const double yy = yb + Dd * yf;
+      p.y[it.m_off + it.m - 1] = yy;
+      atomicMax(p.absmax_bits + item, static_cast<unsigned long long>(__double_as_longlong(fabs(yy))));
+    }
+  }
+  if (r0 >= ns) return;
+
+  for (int t = tid; t < 9 * 16; t += SCAN_THREADS) sm_pow[t] = d.pw(0)[t];
+  if (tid < 16) { sm_Ad[tid] = d.Ad()[tid]; sm_P[tid] = d.P()[tid]; }
+  if (tid < 4) sm_C[tid] = d.C()[tid];
+  __syncthreads();
+
+  const int64_t rbeg = r0 + static_cast<int64_t>(tid) * SCAN_CHUNK;
+  double u[SCAN_CHUNK][4];
+  double yfv[SCAN_CHUNK];
+  double z[4] = {0, 0, 0, 0};
+  double start[4] = {0, 0, 0, 0};
+
+  if (APPLY && tid == 0) {
+    // look back over the preceding tiles' aggregates (contraction makes older ones vanish)
+    const int64_t b = blockIdx.x;
+    const int64_t K = d.lookback();
+    const int64_t k0 = (b > K) ? b - K : 0;
+    const double* si = p.s_init + 4 * item;
+    if (k0 == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) start[c] = si[c];
+    }
+    const double* ag = p.agg + 4 * tile_slot0(it, item);
+    for (int64_t t = k0; t < b; ++t) affine4(sm_pow + 8 * 16, start, ag + 4 * t);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) z[c] = start[c];
+  }
+
+#pragma unroll
+  for (int c = 0; c < SCAN_CHUNK; ++c) {
+    const int64_t r = rbeg + c;
+    if (r < ns) {
+      const int64_t j = (DIR == 0) ? r : (it.m - 2 - r);
+      const double2* pu = reinterpret_cast<const double2*>(p.u + 4 * (it.m_off + j));
+      const double2 a = pu[0], bb = pu[1];
+      u[c][0] = a.x; u[c][1] = a.y; u[c][2] = bb.x; u[c][3] = bb.y;
+      if (DIR == 1) {
+        const double2* ps = reinterpret_cast<const double2*>(p.sf + 4 * (it.m_off + j));
+        const double2 s01 = ps[0], s23 = ps[1];
+        const double sv[4] = {s01.x, s01.y, s23.x, s23.y};
+        double t4[4];
+        matvec4(sm_P, sv, t4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[c][k] += t4[k];
+        if (APPLY)
+          yfv[c] = sm_C[0] * sv[0] + sm_C[1] * sv[1] + sm_C[2] * sv[2] + sm_C[3] * sv[3] + Dd * p.xe[it.m_off + j];
+      }
+      affine4(sm_Ad, z, u[c]);
+    }
+  }
+
+  // inclusive scan of chunk aggregates across the warp
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int o = 1 << k;
+    double zo[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) zo[c] = shfl_up_f64(z[c], o);
+    if (lane >= o) {
+      double t4[4];
+      matvec4(sm_pow + 16 * k, zo, t4);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) z[c] += t4[c];
+    }
+  }
+  if (lane == 31) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) sm_tot[warp][c] = z[c];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // exclusive prefix per warp (and the tile aggregate), 8 serial steps with Ad^(32*CHUNK)
+    double a[4] = {0, 0, 0, 0};
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) sm_pre[w][c] = a[c];
+      affine4(sm_pow + 16 * 5, a, sm_tot[w]);
+    }
+    if (!APPLY) {
+      double* ag = p.agg + 4 * (tile_slot0(it, item) + blockIdx.x);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ag[c] = a[c];
+    }
+  }
+  if (!APPLY) return;
+  __syncthreads();
+
+  // state before this thread's chunk = Ad^(CHUNK*lane) * warp_prefix + (inclusive state of lane-1)
+  double st[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const double prev = shfl_up_f64(z[c], 1);
+    st[c] = (lane == 0) ? 0.0 : prev;
+  }
+  if (warp > 0) {
+    double pre[4] = {sm_pre[warp][0], sm_pre[warp][1], sm_pre[warp][2], sm_pre[warp][3]};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      if (lane & (1 << k)) {
+        double t4[4];
+        matvec4(sm_pow + 16 * k, pre, t4);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) pre[c] = t4[c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) st[c] += pre[c];
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) st[c] = start[c];
+  }
+
+  double amax = 0.0;
+#pragma unroll
+  for (int c = 0; c < SCAN_CHUNK; ++c) {
+    const int64_t r = rbeg + c;
+    if (r < ns) {
+      affine4(sm_Ad, st, u[c]);
+      if (DIR == 0) {
+        double2* po = reinterpret_cast<double2*>(p.sf + 4 * (it.m_off + r + 1));
+        po[0] = make_double2(st[0], st[1]);
+        po[1] = make_double2(st[2], st[3]);
+      } else {
+        const int64_t j = it.m - 2 - r;
+        const double yb = sm_C[0] * st[0] + sm_C[1] * st[1] + sm_C[2] * st[2] + sm_C[3] * st[3];
+        const double yy = yb + Dd * yfv[c];
+        p.y[it.m_off + j] = yy;
+        amax = fmax(amax, fabs(yy));
+      }
+    }
+  }
+  if (DIR == 1) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0) atomicMax(p.absmax_bits + item, static_cast<unsigned long long>(__double_as_longlong(amax)));
+  }
+}
+
+// ------------------------------------------------------------------ envelope (K2)
+// pandas rolling(window=w, min_periods=1, center=True).mean() of |y|
+// (bpm_analysis.py:1052-1054): window [i+1+off-w, i+off] clipped, off=(w-1)//2.
+constexpr int ENV_THREADS = 256;
+constexpr int ENV_MAX_W = 1024;
+
+__global__ void __launch_bounds__(ENV_THREADS) k_envelope(const double* __restrict__ y,
+                                                          const BpmItem* __restrict__ items, int w,
+                                                          double* __restrict__ env) {
+  extern __shared__ double s_abs[];          // ENV_THREADS + w
+  const BpmItem it = items[blockIdx.y];
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * ENV_THREADS;
+  if (i0 >= it.m) return;
+  const int off = (w - 1) / 2;
+  const int left = w - 1 - off;
+  const int64_t lo = i0 - left;
+  const int n = ENV_THREADS + w - 1;
+  for (int t = threadIdx.x; t < n; t += ENV_THREADS) {
+    const int64_t k = lo + t;
+    s_abs[t] = (k >= 0 && k < it.m) ? fabs(y[it.m_off + k]) : 0.0;
+  }
+  __syncthreads();
+  const int64_t i = i0 + threadIdx.x;
+  if (i >= it.m) return;
+  const int64_t a = max(static_cast<int64_t>(0), i - left), b = min(it.m - 1, i + off);
+  double s = 0.0;
+  const int ta = static_cast<int>(a - lo), tb = static_cast<int>(b - lo);
+  for (int t = ta; t <= tb; ++t) s = __dadd_rn(s, s_abs[t]);
+  env[it.m_off + i] = __ddiv_rn(s, static_cast<double>(b - a + 1));
+}
+
+// K2b: np.int16(y / max|y| * 32767)
+__global__ void k_debug_wav(const double* __restrict__ y, const double* __restrict__ absmax,
+                            const BpmItem* __restrict__ items, int16_t* __restrict__ out) {
+  const BpmItem it = items[blockIdx.y];
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= it.m) return;
+  const double v = __dmul_rn(__ddiv_rn(y[it.m_off + i], absmax[blockIdx.y]), 32767.0);
+  out[it.m_off + i] = static_cast<int16_t>(static_cast<int>(v));
+}
+
+// ------------------------------------------------------------------ host side
+struct FrontendBuffers {
+  double *uf, *ub0, *xe, *sf, *agg, *s0, *sb_last, *tail;
+  int tail_cap;
+};
+
+static int carve_frontend(Workspace& ws, int64_t total_m, int n_items, int block, FrontendBuffers* b) {
+  const int64_t tiles = total_m / SCAN_TILE + n_items + 1;
+  b->uf = ws.take<double>(4 * total_m);
+  b->ub0 = ws.take<double>(4 * total_m);
+  b->xe = ws.take<double>(total_m);
+  b->sf = ws.take<double>(4 * total_m);
+  b->agg = ws.take<double>(4 * tiles);
+  b->s0 = ws.take<double>(4 * n_items);
+  b->sb_last = ws.take<double>(4 * n_items);
+  b->tail_cap = block + PADLEN + 1;
+  b->tail = ws.take<double>(static_cast<size_t>(n_items) * b->tail_cap);
+  return ws.overflow ? BPM_ERR_WORKSPACE : BPM_OK;
+}
+
+// worst-case block for workspace sizing (the tail scratch is the only part that depends on it)
+constexpr int MAX_BLOCK = 8192;
+
+size_t frontend_workspace_bytes(int64_t total_m, int n_items) {
+  Workspace ws(nullptr, 0);
+  FrontendBuffers b;
+  carve_frontend(ws, total_m, n_items, MAX_BLOCK, &b);
+  return ws.used;
+}
+
+int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* items,
+                 const BpmItem* items_host, int n_items, int64_t stride, const double* design,
+                 int64_t design_words, int block, int env_window, double* filtered, double* envelope,
+                 double* absmax, Workspace& ws, cudaStream_t st) {
+  if (!pcm || !items || !items_host || !design || !filtered || !envelope || !absmax) return BPM_ERR_ARG;
+  if (n_items <= 0 || stride < 1 || channels < 1 || pcm_dtype < 0 || pcm_dtype > BPM_PCM_F64) return BPM_ERR_ARG;
+  if (block < 1 || block > MAX_BLOCK || design_words < BPM_DESIGN_HEADER_WORDS + 4 * (2 * block + 1)) return BPM_ERR_ARG;
+  if (env_window < 1 || env_window > ENV_MAX_W) return BPM_ERR_ARG;
+  const BatchShape sh = batch_shape(items_host, n_items);
+  for (int i = 0; i < n_items; ++i) {
+    const int64_t n_dec = (items_host[i].n_in + stride - 1) / stride;
+    if (n_dec <= PADLEN) return BPM_ERR_TOO_SHORT;           // scipy: len(x) must be > padlen
+    if (items_host[i].m != (n_dec + block - 1) / block) return BPM_ERR_ARG;
+  }
+  FrontendBuffers b;
+  BPM_TRY(carve_frontend(ws, sh.total_m, n_items, block, &b));
+  PcmView pv{pcm, pcm_dtype, channels};
+
+  if (cudaMemsetAsync(absmax, 0, sizeof(double) * n_items, st) != cudaSuccess) return BPM_ERR_CUDA;
+  const bool fast = (pcm_dtype == BPM_PCM_I16 && channels == 1 && stride == 1 && block >= 8);
+  if (fast) {
+    const size_t smem = sizeof(double) * 8 * (block + 1) + 2 * (static_cast<size_t>(CT_BLOCKS) * block + 1 + 16);
+    if (smem > 200 * 1024) {
+      k_contract_generic<<<dim3(cdiv(sh.max_m, 256), n_items), 256, 0, st>>>(pv, items, stride, design, b.uf, b.ub0, b.xe);
+    } else {
+      cudaFuncSetAttribute(k_contract_i16, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      k_contract_i16<<<dim3(cdiv(sh.max_m, CT_BLOCKS), n_items), CT_THREADS, smem, st>>>(
+          static_cast<const int16_t*>(pcm), items, design, b.uf, b.ub0, b.xe);
+    }
+  } else {
+    k_contract_generic<<<dim3(cdiv(sh.max_m, 256), n_items), 256, 0, st>>>(pv, items, stride, design, b.uf, b.ub0, b.xe);
+  }
+  BPM_LAUNCH_OK();
+  k_filter_init<<<cdiv(n_items, 64), 64, 0, st>>>(pv, items, n_items, stride, design, b.s0);
+  BPM_LAUNCH_OK();
+
+  const dim3 sgrid(cdiv(sh.max_m > 1 ? sh.max_m - 1 : 1, SCAN_TILE), n_items);
+  ScanParams sp{items, design, b.uf, b.sf, b.xe, b.s0, b.agg, filtered,
+                reinterpret_cast<unsigned long long*>(absmax)};
+  if (sgrid.x > 1) {
+    k_scan<0, false><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
+    BPM_LAUNCH_OK();
+  }
+  k_scan<0, true><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
+  BPM_LAUNCH_OK();
+  k_filter_tail<<<cdiv(n_items, 32), 32, 0, st>>>(pv, items, n_items, stride, design, b.sf, b.tail, b.tail_cap, b.sb_last);
+  BPM_LAUNCH_OK();
+  sp.u = b.ub0;
+  sp.s_init = b.sb_last;
+  if (sgrid.x > 1) {
+    k_scan<1, false><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
+    BPM_LAUNCH_OK();
+  }
+  k_scan<1, true><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
+  BPM_LAUNCH_OK();
+  k_envelope<<<dim3(cdiv(sh.max_m, ENV_THREADS), n_items), ENV_THREADS,
+               sizeof(double) * (ENV_THREADS + env_window), st>>>(filtered, items, env_window, envelope);
+  BPM_LAUNCH_OK();
+  return BPM_OK;
+}
+
+int debug_wav_run(const double* filtered, const double* absmax, const BpmItem* items,
+                  const BpmItem* items_host, int n_items, int16_t* out, cudaStream_t st) {
+  if (!filtered || !absmax || !items || !items_host || !out || n_items <= 0) return BPM_ERR_ARG;
+  const BatchShape sh = batch_shape(items_host, n_items);
+  k_debug_wav<<<dim3(cdiv(sh.max_m, 256), n_items), 256, 0, st>>>(filtered, absmax, items, out);
+  BPM_LAUNCH_OK();
+  return BPM_OK;
+}
+
+}  // namespace bpm

@@ -1,0 +1,351 @@
+// K4: scipy.signal.find_peaks(sign*x, height=, prominence=, distance=), conditions in
+// scipy's order (scipy/signal/_peak_finding.py:943-1010; internals restated in SURVEY.md
+// Appendix A.3):  plateau-aware local maxima -> height -> distance -> prominence.
+// Called by the reference at bpm_analysis.py:227 (peaks of the envelope above the noise
+// floor) and :1070 (troughs = peaks of -envelope).
+//
+//   k_localmax_flags   per sample: is it the midpoint of a strict local maximum plateau,
+//                      and (optionally) at or above its height threshold; per-tile counts.
+//   k_tile_scan        exclusive scan of tile counts per recording -> offsets, totals.
+//   k_scatter          ordered compaction of flagged positions (int64).
+//   k_distance_prom    greedy "highest first removes neighbours closer than d" resolved as a
+//                      fix-point on clusters of candidates (a cluster = run of candidates with
+//                      gaps < d; clusters never interact), then a warp-cooperative prominence
+//                      walk with ballot early exit for every survivor.
+// Equal-height candidates within `distance`: the later index wins (what a stable argsort
+// gives scipy); numpy's default sort is unstable, so the reference does not pin this case.
+#include "common.cuh"
+
+namespace bpm {
+
+constexpr int PK_THREADS = 256;
+constexpr int PK_PER = 8;
+constexpr int PK_TILE = PK_THREADS * PK_PER;     // domain elements per tile
+
+__device__ __forceinline__ int64_t pk_slot0(int64_t dom_off, int item) { return dom_off / PK_TILE + item; }
+
+__global__ void __launch_bounds__(PK_THREADS) k_localmax_flags(const double* __restrict__ x, int sign,
+                                                               const double* __restrict__ height,
+                                                               const BpmItem* __restrict__ items,
+                                                               unsigned char* __restrict__ flags,
+                                                               int* __restrict__ tile_counts) {
+  __shared__ int s_cnt[PK_THREADS / 32];
+  const int item = blockIdx.y;
+  const BpmItem it = items[item];
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * PK_TILE;
+  if (i0 >= it.m) return;
+  const double* __restrict__ xi = x + it.m_off;
+  const int64_t n = it.m;
+  int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < PK_PER; ++k) {
+    const int64_t i = i0 + k * PK_THREADS + threadIdx.x;
+    if (i >= n) continue;
+    bool pk = false;
+    if (i >= 1 && i <= n - 2) {
+      const double c = signed_val(xi[i], sign);
+      const double l = signed_val(xi[i - 1], sign), r = signed_val(xi[i + 1], sign);
+      if (l < c && r < c) {
+        pk = true;
+      } else if ((l == c || r == c) && l <= c && r <= c) {
+        // plateau member: locate its edges; peak iff both outer neighbours are lower and
+        // this is the midpoint (left + right) // 2.  Plateaus touching either end are not peaks.
+        int64_t L = i, R = i;
+        while (L - 1 >= 0 && signed_val(xi[L - 1], sign) == c) --L;
+        while (R + 1 <= n - 1 && signed_val(xi[R + 1], sign) == c) ++R;
+        if (L >= 1 && R <= n - 2 && signed_val(xi[L - 1], sign) < c && signed_val(xi[R + 1], sign) < c &&
+            i == (L + R) / 2)
+          pk = true;
+      }
+      if (pk && height != nullptr) pk = (height[it.m_off + i] <= c);
+    }
+    flags[it.m_off + i] = pk ? 1 : 0;
+    cnt += pk ? 1 : 0;
+  }
+  cnt = warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < PK_THREADS / 32; ++w) t += s_cnt[w];
+    tile_counts[pk_slot0(it.m_off, item) + blockIdx.x] = t;
+  }
+}
+
+// per recording: tile_counts -> exclusive offsets (in place), total -> totals[item]
+// dom_len == nullptr: the domain is the recording's m samples.
+__global__ void __launch_bounds__(256) k_tile_scan(const BpmItem* __restrict__ items,
+                                                   const int64_t* __restrict__ dom_len,
+                                                   int* __restrict__ tile_counts, int64_t* __restrict__ totals) {
+  __shared__ int s_scan[34];
+  __shared__ int s_carry;
+  const int item = blockIdx.x;
+  const BpmItem it = items[item];
+  const int64_t len = dom_len ? dom_len[item] : it.m;
+  const int64_t nt = (len + PK_TILE - 1) / PK_TILE;
+  int* tc = tile_counts + pk_slot0(it.m_off, item);
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < nt; base += blockDim.x) {
+    const int64_t t = base + threadIdx.x;
+    const int v = (t < nt) ? tc[t] : 0;
+    int total;
+    const int ex = block_exclusive_scan(v, &total, s_scan);
+    const int carry = s_carry;
+    if (t < nt) tc[t] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) totals[item] = s_carry;
+}
+
+// ordered compaction: out[m_off + rank] = value of every flagged domain element.
+// src == nullptr: the value is the element's own index; else value = src[m_off + index].
+__global__ void __launch_bounds__(PK_THREADS) k_scatter(const unsigned char* __restrict__ flags,
+                                                        const int64_t* __restrict__ src,
+                                                        const BpmItem* __restrict__ items,
+                                                        const int64_t* __restrict__ dom_len,
+                                                        const int* __restrict__ tile_offsets,
+                                                        int64_t* __restrict__ out) {
+  __shared__ unsigned char s_f[PK_TILE];
+  __shared__ int s_scan[34];
+  const int item = blockIdx.y;
+  const BpmItem it = items[item];
+  const int64_t len = dom_len ? dom_len[item] : it.m;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * PK_TILE;
+  if (i0 >= len) return;
+  for (int t = threadIdx.x; t < PK_TILE; t += PK_THREADS) {
+    const int64_t i = i0 + t;
+    s_f[t] = (i < len) ? flags[it.m_off + i] : 0;
+  }
+  __syncthreads();
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < PK_PER; ++k) c += s_f[threadIdx.x * PK_PER + k];
+  int total;
+  int ex = block_exclusive_scan(c, &total, s_scan);
+  int64_t o = it.m_off + tile_offsets[pk_slot0(it.m_off, item) + blockIdx.x] + ex;
+#pragma unroll
+  for (int k = 0; k < PK_PER; ++k) {
+    if (s_f[threadIdx.x * PK_PER + k]) {
+      const int64_t i = i0 + threadIdx.x * PK_PER + k;
+      out[o++] = src ? src[it.m_off + i] : i;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ distance + prominence
+__device__ __forceinline__ bool higher_priority(double va, int64_t ka, double vb, int64_t kb) {
+  return va > vb || (va == vb && ka > kb);
+}
+
+// does the prominence of the peak at p reach thr?  (scipy _peak_prominences, wlen=None)
+// warp-cooperative: every lane calls with the same arguments.
+__device__ bool warp_prominence_ok(const double* __restrict__ xi, int sign, int64_t n, int64_t p, double thr) {
+  const int lane = threadIdx.x & 31;
+  const double xp = signed_val(xi[p], sign);
+  if (__dsub_rn(xp, xp) >= thr) return true;            // the peak itself is the running minimum
+  bool side_ok[2];
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    bool ok = false;
+    int64_t base = (side == 0) ? p - 1 : p + 1;
+    while (true) {
+      const int64_t idx = (side == 0) ? base - lane : base + lane;
+      const bool valid = (idx >= 0 && idx < n);
+      const double v = valid ? signed_val(xi[idx], sign) : 0.0;
+      const bool stop = !valid || (v > xp);
+      const bool pass = valid && !(v > xp) && (__dsub_rn(xp, v) >= thr);
+      const unsigned bs = __ballot_sync(0xffffffffu, stop);
+      const unsigned bp = __ballot_sync(0xffffffffu, pass);
+      const int fs = bs ? __ffs(bs) : 33, fp = bp ? __ffs(bp) : 33;
+      if (fp < fs) { ok = true; break; }
+      if (bs) { ok = false; break; }
+      base += (side == 0) ? -32 : 32;
+    }
+    side_ok[side] = ok;
+    if (!ok) return false;
+  }
+  return side_ok[0] && side_ok[1];
+}
+
+constexpr int DP_THREADS = 256;
+constexpr int DP_TILE = 1024;      // nominal candidates per CTA
+
+__global__ void __launch_bounds__(DP_THREADS) k_distance_prom(const double* __restrict__ x, int sign,
+                                                              const BpmItem* __restrict__ items,
+                                                              const int64_t* __restrict__ cand,
+                                                              const int64_t* __restrict__ cand_count,
+                                                              int distance, const double* __restrict__ prominence,
+                                                              unsigned char* __restrict__ state /* per candidate */,
+                                                              int* __restrict__ tile_counts) {
+  __shared__ long long s_edge[2];
+  __shared__ int s_cnt;
+  const int item = blockIdx.y;
+  const BpmItem it = items[item];
+  const int64_t nc = cand_count[item];
+  const int64_t k0 = static_cast<int64_t>(blockIdx.x) * DP_TILE;
+  if (k0 >= nc) return;
+  const int64_t k1 = min(nc, k0 + DP_TILE);
+  const int64_t* __restrict__ pos = cand + it.m_off;
+  const double* __restrict__ xi = x + it.m_off;
+  volatile unsigned char* stt = state + it.m_off;
+  const int64_t d = distance;
+
+  // own the clusters whose head lies in [k0, k1): ks = first head >= k0, ke = first head >= k1
+  if (threadIdx.x < 2) s_edge[threadIdx.x] = nc;
+  __syncthreads();
+  for (int e = 0; e < 2; ++e) {
+    const int64_t from = e == 0 ? k0 : k1;
+    for (int64_t base = from; base < nc; base += DP_THREADS) {
+      const int64_t k = base + threadIdx.x;
+      const bool head = (k < nc) && (k == 0 || pos[k] - pos[k - 1] >= d);
+      if (head) atomicMin(reinterpret_cast<long long*>(&s_edge[e]), static_cast<long long>(k));
+      __syncthreads();
+      const bool found = s_edge[e] < nc;
+      __syncthreads();
+      if (found) break;
+    }
+  }
+  const int64_t ks = s_edge[0], ke = s_edge[1];
+  // zero the per-tile count for the nominal tile (a tile fully inside someone else's cluster
+  // still has to publish its count; the owner counts for it below)
+  for (int64_t k = ks + threadIdx.x; k < ke; k += DP_THREADS) stt[k] = 0;
+  __syncthreads();
+
+  if (distance > 1) {
+    while (true) {
+      int changed = 0;
+      for (int64_t k = ks + threadIdx.x; k < ke; k += DP_THREADS) {
+        if (stt[k] != 0) continue;
+        const int64_t pk = pos[k];
+        const double vk = signed_val(xi[pk], sign);
+        bool any_keep = false, any_open = false;
+        for (int64_t k2 = k - 1; k2 >= ks && pk - pos[k2] < d; --k2) {
+          if (higher_priority(signed_val(xi[pos[k2]], sign), k2, vk, k)) {
+            const unsigned char s2 = stt[k2];
+            any_keep |= (s2 == 1);
+            any_open |= (s2 == 0);
+          }
+        }
+        for (int64_t k2 = k + 1; k2 < ke && pos[k2] - pk < d; ++k2) {
+          if (higher_priority(signed_val(xi[pos[k2]], sign), k2, vk, k)) {
+            const unsigned char s2 = stt[k2];
+            any_keep |= (s2 == 1);
+            any_open |= (s2 == 0);
+          }
+        }
+        if (any_keep) { stt[k] = 2; changed = 1; }
+        else if (!any_open) { stt[k] = 1; changed = 1; }
+      }
+      if (!__syncthreads_or(changed)) break;
+    }
+  } else {
+    for (int64_t k = ks + threadIdx.x; k < ke; k += DP_THREADS) stt[k] = 1;
+    __syncthreads();
+  }
+
+  if (prominence != nullptr) {
+    const double thr = prominence[item];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t k = ks + warp; k < ke; k += DP_THREADS / 32) {
+      if (stt[k] != 1) continue;                       // warp-uniform
+      const bool ok = warp_prominence_ok(xi, sign, it.m, pos[k], thr);
+      if (lane == 0 && !ok) stt[k] = 2;
+    }
+  }
+  __syncthreads();
+  // normalise to 0/1 flags
+  for (int64_t k = ks + threadIdx.x; k < ke; k += DP_THREADS) stt[k] = (stt[k] == 1) ? 1 : 0;
+  (void)tile_counts;
+  (void)s_cnt;
+}
+
+// counts of set flags per PK_TILE of a (device-length) domain
+__global__ void __launch_bounds__(PK_THREADS) k_count_flags(const unsigned char* __restrict__ flags,
+                                                            const BpmItem* __restrict__ items,
+                                                            const int64_t* __restrict__ dom_len,
+                                                            int* __restrict__ tile_counts) {
+  __shared__ int s_cnt[PK_THREADS / 32];
+  const int item = blockIdx.y;
+  const BpmItem it = items[item];
+  const int64_t len = dom_len ? dom_len[item] : it.m;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * PK_TILE;
+  if (i0 >= len) return;
+  int cnt = 0;
+  for (int k = 0; k < PK_PER; ++k) {
+    const int64_t i = i0 + k * PK_THREADS + threadIdx.x;
+    if (i < len) cnt += flags[it.m_off + i];
+  }
+  cnt = warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < PK_THREADS / 32; ++w) t += s_cnt[w];
+    tile_counts[pk_slot0(it.m_off, item) + blockIdx.x] = t;
+  }
+}
+
+// ------------------------------------------------------------------ host side
+struct PeakBuffers {
+  unsigned char* flags;     // [total_m]  sample-domain flags, then candidate-domain flags
+  unsigned char* cstate;    // [total_m]
+  int* tile_counts;         // [total_m / PK_TILE + n_items + 1]
+  int64_t* cand;            // [total_m]
+  int64_t* cand_count;      // [n_items]
+};
+
+static int carve_peaks(Workspace& ws, int64_t total_m, int n_items, PeakBuffers* b) {
+  b->flags = ws.take<unsigned char>(total_m);
+  b->cstate = ws.take<unsigned char>(total_m);
+  b->tile_counts = ws.take<int>(total_m / PK_TILE + n_items + 1);
+  b->cand = ws.take<int64_t>(total_m);
+  b->cand_count = ws.take<int64_t>(n_items);
+  return ws.overflow ? BPM_ERR_WORKSPACE : BPM_OK;
+}
+
+size_t find_peaks_workspace_bytes(int64_t total_m, int n_items) {
+  Workspace ws(nullptr, 0);
+  PeakBuffers b;
+  carve_peaks(ws, total_m, n_items, &b);
+  return ws.used;
+}
+
+// compaction of a flag array over a domain (samples or a device-length list)
+int compact_run(const unsigned char* flags, const int64_t* src, const BpmItem* items, const BatchShape& sh,
+                const int64_t* dom_len, int64_t max_len, bool counts_ready, int* tile_counts,
+                int64_t* out, int64_t* out_count, cudaStream_t st) {
+  const dim3 grid(cdiv(max_len > 0 ? max_len : 1, PK_TILE), sh.n_items);
+  if (!counts_ready) {
+    k_count_flags<<<grid, PK_THREADS, 0, st>>>(flags, items, dom_len, tile_counts);
+    BPM_LAUNCH_OK();
+  }
+  k_tile_scan<<<sh.n_items, 256, 0, st>>>(items, dom_len, tile_counts, out_count);
+  BPM_LAUNCH_OK();
+  k_scatter<<<grid, PK_THREADS, 0, st>>>(flags, src, items, dom_len, tile_counts, out);
+  BPM_LAUNCH_OK();
+  return BPM_OK;
+}
+
+int find_peaks_run(const double* x, int sign, const double* height, const double* prominence, int distance,
+                   const BpmItem* items, const BatchShape& sh, int64_t* out_idx, int64_t* out_count,
+                   Workspace& ws, cudaStream_t st) {
+  if (!x || !items || !out_idx || !out_count || sh.n_items <= 0 || distance < 1) return BPM_ERR_ARG;
+  PeakBuffers b;
+  BPM_TRY(carve_peaks(ws, sh.total_m, sh.n_items, &b));
+  const dim3 grid(cdiv(sh.max_m, PK_TILE), sh.n_items);
+  k_localmax_flags<<<grid, PK_THREADS, 0, st>>>(x, sign, height, items, b.flags, b.tile_counts);
+  BPM_LAUNCH_OK();
+  BPM_TRY(compact_run(b.flags, nullptr, items, sh, nullptr, sh.max_m, true, b.tile_counts, b.cand, b.cand_count, st));
+  // a local maximum needs a lower neighbour on both sides: at most (m-1)/2 candidates
+  const int64_t max_c = sh.max_m / 2 + 1;
+  k_distance_prom<<<dim3(cdiv(max_c, DP_TILE), sh.n_items), DP_THREADS, 0, st>>>(
+      x, sign, items, b.cand, b.cand_count, distance, prominence, b.cstate, b.tile_counts);
+  BPM_LAUNCH_OK();
+  BPM_TRY(compact_run(b.cstate, b.cand, items, sh, b.cand_count, max_c, false, b.tile_counts, out_idx, out_count, st));
+  return BPM_OK;
+}
+
+}  // namespace bpm

@@ -1,0 +1,361 @@
+// extern "C" surface of libbpm_b200.so (include/bpm_b200.h) and the chained stages
+// a2 (_calculate_dynamic_noise_floor, bpm_analysis.py:1064-1117), a3 (_find_raw_peaks,
+// :223-229) and a1..a4 in one call.  All data-dependent fall-backs of the reference are
+// resolved by per-recording control words on the device, so a stage is enqueued without
+// any host synchronisation.
+#include "common.cuh"
+
+namespace bpm {
+
+// filter.cu
+size_t frontend_workspace_bytes(int64_t total_m, int n_items);
+int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* items, const BpmItem* items_host,
+                 int n_items, int64_t stride, const double* design, int64_t design_words, int block,
+                 int env_window, double* filtered, double* envelope, double* absmax, Workspace& ws, cudaStream_t st);
+int debug_wav_run(const double* filtered, const double* absmax, const BpmItem* items, const BpmItem* items_host,
+                  int n_items, int16_t* out, cudaStream_t st);
+// select.cu
+size_t quantile_workspace_bytes(int n_items);
+int quantile_run(const double* x, const BpmItem* items, const BatchShape& sh, double q, const int* cond,
+                 double* out, Workspace& ws, cudaStream_t st);
+// peaks.cu
+size_t find_peaks_workspace_bytes(int64_t total_m, int n_items);
+int find_peaks_run(const double* x, int sign, const double* height, const double* prominence, int distance,
+                   const BpmItem* items, const BatchShape& sh, int64_t* out_idx, int64_t* out_count,
+                   Workspace& ws, cudaStream_t st);
+int compact_run(const unsigned char* flags, const int64_t* src, const BpmItem* items, const BatchShape& sh,
+                const int64_t* dom_len, int64_t max_len, bool counts_ready, int* tile_counts, int64_t* out,
+                int64_t* out_count, cudaStream_t st);
+// floor.cu
+size_t rolling_floor_workspace_bytes(int64_t total_m, int n_items);
+int rolling_floor_run(const double* env, const int64_t* knots, const int64_t* knot_count, const BpmItem* items,
+                      const BatchShape& sh, int window, double q, const int* mode, const double* alt,
+                      const double* cval, const double* nan_fill, double* out, Workspace& ws, cudaStream_t st);
+__global__ void k_sanitize_flags(const double*, const double*, const int64_t*, const int64_t*, const int*,
+                                 const BpmItem*, double, unsigned char*);
+__global__ void k_floor_modes(const int64_t*, const int64_t*, int, int, int*, int*);
+// metrics.cu
+int peak_metrics_run(const double* env, const double* floor_, const int64_t* peaks, const int64_t* peak_count,
+                     const BpmItem* items, const BatchShape& sh, double factor, double* strength,
+                     double* deviation, double* smoothed, cudaStream_t st);
+int bpm_series_run(const int64_t* beats, const BpmItem* lists, const BatchShape& sh, int rate, int64_t window_us,
+                   double* inst, double* smoothed, double* times_sec, int64_t* stamp_us, int64_t* n_valid,
+                   cudaStream_t st);
+int steepest_run(const double* smoothed, const int64_t* stamp_us, const int64_t* n_valid, const BpmItem* lists,
+                 int n_lists, int sign, double window_sec, double* result, cudaStream_t st);
+int hrv_run(const int64_t* beats, const BpmItem* lists, const BatchShape& sh, int rate, int win, int step,
+            double* out, int64_t* rows, cudaStream_t st);
+
+// ------------------------------------------------------------------ a2
+struct NoiseFloorScratch {
+  double* q_tp;        // [n] trough prominence threshold
+  double* q_nf;        // [n] static floor for the "<5 troughs" path
+  double* q_fb;        // [n] q(0.1) for the all-NaN path (aliases q_tp when trough_prom_q == 0.1)
+  int64_t* all_troughs;
+  int64_t* n_all;
+  double* draft;
+  int* few;
+  int* mode;
+  unsigned char* keep;
+  int* tile_counts;
+};
+
+static int carve_noise_floor(Workspace& ws, int64_t total_m, int n, NoiseFloorScratch* s) {
+  s->q_tp = ws.take<double>(n);
+  s->q_nf = ws.take<double>(n);
+  s->q_fb = ws.take<double>(n);
+  s->all_troughs = ws.take<int64_t>(total_m);
+  s->n_all = ws.take<int64_t>(n);
+  s->draft = ws.take<double>(total_m);
+  s->few = ws.take<int>(n);
+  s->mode = ws.take<int>(n);
+  s->keep = ws.take<unsigned char>(total_m);
+  s->tile_counts = ws.take<int>(total_m / 2048 + n + 1);
+  return ws.overflow ? BPM_ERR_WORKSPACE : BPM_OK;
+}
+
+// Sub-steps run one after another on one stream, so their scratch can share memory: each
+// takes a nested Workspace over the same tail region.
+static Workspace sub_ws(Workspace& parent, size_t bytes) {
+  if (parent.measuring()) {
+    // account for the largest sub-step once
+    return Workspace(nullptr, 0);
+  }
+  char* p = parent.base ? parent.base + parent.used : nullptr;
+  size_t cap = parent.cap > parent.used ? parent.cap - parent.used : 0;
+  (void)bytes;
+  return Workspace(p, cap);
+}
+
+static size_t noise_floor_sub_bytes(int64_t total_m, int n) {
+  size_t a = quantile_workspace_bytes(n), b = find_peaks_workspace_bytes(total_m, n),
+         c = rolling_floor_workspace_bytes(total_m, n);
+  size_t mx = a > b ? a : b;
+  return mx > c ? mx : c;
+}
+
+size_t noise_floor_workspace_bytes(int64_t total_m, int n) {
+  Workspace ws(nullptr, 0);
+  NoiseFloorScratch s;
+  carve_noise_floor(ws, total_m, n, &s);
+  return ws.used + noise_floor_sub_bytes(total_m, n);
+}
+
+int noise_floor_run(const double* env, const BpmItem* items, const BatchShape& sh, int distance,
+                    double trough_prom_q, double floor_q, int window, double mult, double* floor_out,
+                    int64_t* troughs_out, int64_t* trough_count, double* q_tp_out /* optional [n] */,
+                    Workspace& ws, cudaStream_t st) {
+  if (!env || !items || !floor_out || !troughs_out || !trough_count) return BPM_ERR_ARG;
+  if (distance < 1 || window < MIN_PERIODS) return BPM_ERR_ARG;
+  const int n = sh.n_items;
+  NoiseFloorScratch s;
+  BPM_TRY(carve_noise_floor(ws, sh.total_m, n, &s));
+  double* q_tp = q_tp_out ? q_tp_out : s.q_tp;
+  {
+    Workspace w = sub_ws(ws, 0);
+    BPM_TRY(quantile_run(env, items, sh, trough_prom_q, nullptr, q_tp, w, st));                 // :1067
+  }
+  {
+    Workspace w = sub_ws(ws, 0);
+    BPM_TRY(find_peaks_run(env, -1, nullptr, q_tp, distance, items, sh, s.all_troughs, s.n_all, w, st));  // :1070
+  }
+  k_floor_modes<<<cdiv(n, 128), 128, 0, st>>>(s.n_all, nullptr, n, 0, s.few, s.mode);
+  BPM_LAUNCH_OK();
+  {
+    Workspace w = sub_ws(ws, 0);
+    BPM_TRY(quantile_run(env, items, sh, floor_q, s.few, s.q_nf, w, st));                          // :1075
+  }
+  const double* q_fb = q_tp;
+  if (trough_prom_q != 0.1) {
+    Workspace w = sub_ws(ws, 0);
+    BPM_TRY(quantile_run(env, items, sh, 0.1, nullptr, s.q_fb, w, st));                            // :1114
+    q_fb = s.q_fb;
+  }
+  {
+    // draft floor from all troughs (:1081-1086); skipped (constant, unused) on the "<5" path
+    Workspace w = sub_ws(ws, 0);
+    BPM_TRY(rolling_floor_run(env, s.all_troughs, s.n_all, items, sh, window, floor_q, s.mode, nullptr, s.q_nf,
+                              nullptr, s.draft, w, st));
+  }
+  k_sanitize_flags<<<dim3(cdiv(sh.max_m / 2 + 2, 256), n), 256, 0, st>>>(env, s.draft, s.all_troughs, s.n_all,
+                                                                        s.few, items, mult, s.keep);     // :1090-1097
+  BPM_LAUNCH_OK();
+  BPM_TRY(compact_run(s.keep, s.all_troughs, items, sh, s.n_all, sh.max_m / 2 + 2, false, s.tile_counts,
+                      troughs_out, trough_count, st));
+  k_floor_modes<<<cdiv(n, 128), 128, 0, st>>>(s.n_all, trough_count, n, 1, s.few, s.mode);
+  BPM_LAUNCH_OK();
+  {
+    // final floor from the kept troughs (:1102-1106), draft when <= 2 kept (:1107-1110),
+    // constant on the "<5" path (:1073-1077), q(0.1) when everything is NaN (:1113-1115)
+    Workspace w = sub_ws(ws, 0);
+    BPM_TRY(rolling_floor_run(env, troughs_out, trough_count, items, sh, window, floor_q, s.mode, s.draft,
+                              s.q_nf, q_fb, floor_out, w, st));
+  }
+  return BPM_OK;
+}
+
+// ------------------------------------------------------------------ a3
+size_t raw_peaks_workspace_bytes(int64_t total_m, int n) {
+  Workspace ws(nullptr, 0);
+  ws.take<double>(n);
+  size_t a = quantile_workspace_bytes(n), b = find_peaks_workspace_bytes(total_m, n);
+  return ws.used + (a > b ? a : b);
+}
+
+int raw_peaks_run(const double* env, const double* floor_, const BpmItem* items, const BatchShape& sh,
+                  int distance, double prom_q, const double* q_ready /* optional: already computed */,
+                  int64_t* peaks_out, int64_t* peak_count, Workspace& ws, cudaStream_t st) {
+  if (!env || !floor_ || !items || !peaks_out || !peak_count || distance < 1) return BPM_ERR_ARG;
+  double* q = ws.take<double>(sh.n_items);
+  if (ws.overflow) return BPM_ERR_WORKSPACE;
+  const double* thr = q_ready;
+  if (!thr) {
+    Workspace w = sub_ws(ws, 0);
+    BPM_TRY(quantile_run(env, items, sh, prom_q, nullptr, q, w, st));                             // :225
+    thr = q;
+  }
+  Workspace w = sub_ws(ws, 0);
+  return find_peaks_run(env, +1, floor_, thr, distance, items, sh, peaks_out, peak_count, w, st);   // :227
+}
+
+}  // namespace bpm
+
+// =========================================================================== C ABI
+using namespace bpm;
+
+extern "C" {
+
+int bpm_abi_version(void) { return BPM_ABI_VERSION; }
+
+const char* bpm_error_string(int code) {
+  switch (code) {
+    case BPM_OK: return "ok";
+    case BPM_ERR_ARG: return "invalid argument";
+    case BPM_ERR_WORKSPACE: return "workspace too small";
+    case BPM_ERR_CUDA: return "CUDA error";
+    case BPM_ERR_TOO_SHORT: return "recording not longer than the filter padding (15 samples)";
+    default: return "unknown error";
+  }
+}
+
+int64_t bpm_launch_count(void) { return g_launches; }
+
+size_t bpm_frontend_workspace_bytes(int64_t total_m, int n_items) { return frontend_workspace_bytes(total_m, n_items); }
+
+int bpm_frontend(const void* pcm, int pcm_dtype, int channels, const BpmItem* items, const BpmItem* items_host,
+                 int n_items, int64_t stride, const double* design, int64_t design_words, int env_window,
+                 double* filtered, double* envelope, double* absmax, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+  if (!workspace || n_items <= 0 || !items_host) return BPM_ERR_ARG;
+  // block length is word 0 of the design image; the caller states it through items' m
+  // (validated in frontend_run), so read it from the host-visible relation m = ceil(n_dec / block)
+  Workspace ws(workspace, workspace_bytes);
+  // block is passed implicitly: design_words = header + 4 * (2 * block + 1)
+  const int64_t rem = design_words - BPM_DESIGN_HEADER_WORDS;
+  if (rem < 12 || (rem - 4) % 8 != 0) return BPM_ERR_ARG;
+  const int block = static_cast<int>((rem - 4) / 8);
+  return frontend_run(pcm, pcm_dtype, channels, items, items_host, n_items, stride, design, design_words, block,
+                      env_window, filtered, envelope, absmax, ws, static_cast<cudaStream_t>(stream));
+}
+
+int bpm_debug_wav(const double* filtered, const double* absmax, const BpmItem* items, const BpmItem* items_host,
+                  int n_items, int16_t* out, void* stream) {
+  return debug_wav_run(filtered, absmax, items, items_host, n_items, out, static_cast<cudaStream_t>(stream));
+}
+
+size_t bpm_quantile_workspace_bytes(int n_items) { return quantile_workspace_bytes(n_items); }
+
+int bpm_quantile(const double* x, const BpmItem* items, const BpmItem* items_host, int n_items, double q,
+                 double* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!workspace || !items_host || n_items <= 0) return BPM_ERR_ARG;
+  Workspace ws(workspace, workspace_bytes);
+  return quantile_run(x, items, batch_shape(items_host, n_items), q, nullptr, out, ws, static_cast<cudaStream_t>(stream));
+}
+
+size_t bpm_find_peaks_workspace_bytes(int64_t total_m, int n_items) { return find_peaks_workspace_bytes(total_m, n_items); }
+
+int bpm_find_peaks(const double* x, int sign, const double* height, const double* prominence, int distance,
+                   const BpmItem* items, const BpmItem* items_host, int n_items, int64_t* out_idx,
+                   int64_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!workspace || !items_host || n_items <= 0 || (sign != 1 && sign != -1)) return BPM_ERR_ARG;
+  Workspace ws(workspace, workspace_bytes);
+  return find_peaks_run(x, sign, height, prominence, distance, items, batch_shape(items_host, n_items), out_idx,
+                        out_count, ws, static_cast<cudaStream_t>(stream));
+}
+
+size_t bpm_rolling_floor_workspace_bytes(int64_t total_m, int n_items) { return rolling_floor_workspace_bytes(total_m, n_items); }
+
+int bpm_rolling_floor(const double* envelope, const int64_t* knots, const int64_t* knot_count, const BpmItem* items,
+                      const BpmItem* items_host, int n_items, int window, double q, double* floor_out,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (!workspace || !items_host || n_items <= 0) return BPM_ERR_ARG;
+  Workspace ws(workspace, workspace_bytes);
+  return rolling_floor_run(envelope, knots, knot_count, items, batch_shape(items_host, n_items), window, q, nullptr,
+                           nullptr, nullptr, nullptr, floor_out, ws, static_cast<cudaStream_t>(stream));
+}
+
+size_t bpm_noise_floor_workspace_bytes(int64_t total_m, int n_items) { return noise_floor_workspace_bytes(total_m, n_items); }
+
+int bpm_noise_floor(const double* envelope, const BpmItem* items, const BpmItem* items_host, int n_items,
+                    int distance, double trough_prom_q, double floor_q, int window, double rejection_multiplier,
+                    double* floor_out, int64_t* troughs_out, int64_t* trough_count, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  if (!workspace || !items_host || n_items <= 0) return BPM_ERR_ARG;
+  Workspace ws(workspace, workspace_bytes);
+  return noise_floor_run(envelope, items, batch_shape(items_host, n_items), distance, trough_prom_q, floor_q, window,
+                         rejection_multiplier, floor_out, troughs_out, trough_count, nullptr, ws,
+                         static_cast<cudaStream_t>(stream));
+}
+
+size_t bpm_raw_peaks_workspace_bytes(int64_t total_m, int n_items) { return raw_peaks_workspace_bytes(total_m, n_items); }
+
+int bpm_raw_peaks(const double* envelope, const double* floor_, const BpmItem* items, const BpmItem* items_host,
+                  int n_items, int distance, double prom_q, int64_t* peaks_out, int64_t* peak_count,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+  if (!workspace || !items_host || n_items <= 0) return BPM_ERR_ARG;
+  Workspace ws(workspace, workspace_bytes);
+  return raw_peaks_run(envelope, floor_, items, batch_shape(items_host, n_items), distance, prom_q, nullptr, peaks_out,
+                       peak_count, ws, static_cast<cudaStream_t>(stream));
+}
+
+int bpm_peak_metrics(const double* envelope, const double* floor_, const int64_t* peaks, const int64_t* peak_count,
+                     const BpmItem* items, const BpmItem* items_host, int n_items, double smoothing_factor,
+                     double* strength, double* deviation, double* smoothed, void* stream) {
+  if (!items_host || n_items <= 0) return BPM_ERR_ARG;
+  return peak_metrics_run(envelope, floor_, peaks, peak_count, items, batch_shape(items_host, n_items),
+                          smoothing_factor, strength, deviation, smoothed, static_cast<cudaStream_t>(stream));
+}
+
+int bpm_bpm_series(const int64_t* beats, const BpmItem* lists, const BpmItem* lists_host, int n_lists, int rate,
+                   int64_t window_us, double* inst, double* smoothed, double* times_sec, int64_t* stamp_us,
+                   int64_t* n_valid, void* stream) {
+  if (!lists_host || n_lists <= 0 || window_us <= 0) return BPM_ERR_ARG;
+  return bpm_series_run(beats, lists, batch_shape(lists_host, n_lists), rate, window_us, inst, smoothed, times_sec,
+                        stamp_us, n_valid, static_cast<cudaStream_t>(stream));
+}
+
+size_t bpm_steepest_slope_workspace_bytes(int64_t total_beats, int n_lists) {
+  (void)total_beats; (void)n_lists;
+  return 256;
+}
+
+int bpm_steepest_slope(const double* smoothed, const int64_t* stamp_us, const int64_t* n_valid, const BpmItem* lists,
+                       const BpmItem* lists_host, int n_lists, int sign, double window_sec, double* result,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes; (void)lists_host;
+  return steepest_run(smoothed, stamp_us, n_valid, lists, n_lists, sign, window_sec, result,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int bpm_windowed_hrv(const int64_t* beats, const BpmItem* lists, const BpmItem* lists_host, int n_lists, int rate,
+                     int window_beats, int step_beats, double* out, int64_t* rows, void* stream) {
+  if (!lists_host || n_lists <= 0) return BPM_ERR_ARG;
+  return hrv_run(beats, lists, batch_shape(lists_host, n_lists), rate, window_beats, step_beats, out, rows,
+                 static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------ a1..a4 in one call
+size_t bpm_stage_a_workspace_bytes(int64_t total_m, int n_items) {
+  size_t a = frontend_workspace_bytes(total_m, n_items);
+  size_t b = noise_floor_workspace_bytes(total_m, n_items);
+  size_t c = raw_peaks_workspace_bytes(total_m, n_items);
+  size_t mx = a > b ? a : b;
+  mx = mx > c ? mx : c;
+  return mx + 256 * 4 + sizeof(double) * static_cast<size_t>(n_items);
+}
+
+int bpm_stage_a(const void* pcm, const BpmItem* items, const BpmItem* items_host, int n_items, const double* design,
+                int64_t design_words, const BpmStageAConfig* cfg, const BpmStageAOutputs* out, void* workspace,
+                size_t workspace_bytes, void* stream) {
+  if (!workspace || !items_host || !cfg || !out || n_items <= 0) return BPM_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const BatchShape sh = batch_shape(items_host, n_items);
+  Workspace top(workspace, workspace_bytes);
+  double* q_tp = top.take<double>(n_items);
+  if (top.overflow) return BPM_ERR_WORKSPACE;
+  {
+    Workspace ws(top.base + top.used, top.cap - top.used);
+    BPM_TRY(frontend_run(pcm, cfg->pcm_dtype, cfg->channels, items, items_host, n_items, cfg->stride, design,
+                         design_words, static_cast<int>(cfg->block), cfg->env_window, out->filtered, out->envelope,
+                         out->absmax, ws, st));
+  }
+  if (cfg->want_debug_wav && out->debug_wav)
+    BPM_TRY(debug_wav_run(out->filtered, out->absmax, items, items_host, n_items, out->debug_wav, st));
+  {
+    Workspace ws(top.base + top.used, top.cap - top.used);
+    BPM_TRY(noise_floor_run(out->envelope, items, sh, cfg->distance, cfg->trough_prom_q, cfg->floor_q,
+                            cfg->noise_window, cfg->rejection_multiplier, out->floor, out->troughs,
+                            out->trough_count, q_tp, ws, st));
+  }
+  {
+    Workspace ws(top.base + top.used, top.cap - top.used);
+    const double* ready = (cfg->peak_prom_q == cfg->trough_prom_q) ? q_tp : nullptr;   // same np.quantile call
+    BPM_TRY(raw_peaks_run(out->envelope, out->floor, items, sh, cfg->distance, cfg->peak_prom_q, ready, out->peaks,
+                          out->peak_count, ws, st));
+  }
+  BPM_TRY(peak_metrics_run(out->envelope, out->floor, out->peaks, out->peak_count, items, sh, cfg->smoothing_factor,
+                           out->strength, out->deviation, out->smoothed_dev, st));
+  return BPM_OK;
+}
+
+}  // extern "C"

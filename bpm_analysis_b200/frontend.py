@@ -1,0 +1,279 @@
+"""Drop-in mirror of the data-parallel front end of the reference's ``bpm_analysis.py``.
+
+Same names, signatures, return types and error behaviour as the reference
+functions (cited per function), so ``analyze_wav_file``, ``gui.py`` and the
+hugging-face-space app keep working when ``install()`` rebinds them.  Every
+numeric step runs in libbpm_b200.so on the GPU; this module only adapts host
+objects (WAV files, numpy arrays, pandas Series / DataFrame) at the boundary.
+There is no CPU fallback: without the library or a CUDA device these raise.
+"""
+from __future__ import annotations
+
+import datetime
+import logging
+import os
+import warnings
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import pandas as pd
+from scipy.io import wavfile
+
+from . import runtime
+from .params import (HR_MIN_CHANGE_BPM, HR_MIN_DURATION_SEC, HR_PROMINENCE, SLOPE_WINDOW_SEC, band_edges,
+                     effective_decimation)
+
+__all__ = ["preprocess_audio", "preprocess_pcm", "_calculate_dynamic_noise_floor", "_find_raw_peaks",
+           "_initialize_state", "calculate_bpm_series", "find_peak_recovery_rate", "find_peak_exertion_rate",
+           "find_major_hr_inclines", "find_major_hr_declines", "calculate_windowed_hrv", "find_peaks",
+           "install"]
+
+
+# --------------------------------------------------------------------------- a1
+def preprocess_pcm(audio_data: np.ndarray, sample_rate: int, params: Dict, want_debug: bool = False):
+    """Array-level body of ``preprocess_audio``: (envelope, rate, filtered, debug_int16 | None)."""
+    ds, rate, clamped = effective_decimation(sample_rate, params)
+    if clamped:                                                     # bpm_analysis.py:1023-1029
+        _, highcut = band_edges(params)
+        logging.warning(f"Original 'downsample_factor' of {params['downsample_factor']} is too high for a "
+                        f"{highcut:g}Hz filter with a {sample_rate}Hz sample rate.")
+        logging.warning(f"Adjusting 'downsample_factor' to a safe value of {ds}.")
+    return runtime.ops().frontend(np.asarray(audio_data), int(sample_rate), params, want_debug)
+
+
+def preprocess_audio(file_path: str, params: Dict, output_directory: str) -> Tuple[np.ndarray, int]:
+    """Reads, filters, and prepares the audio envelope.  Mirrors bpm_analysis.py:1007-1062."""
+    save_debug_file = params["save_filtered_wav"]
+    _ = params["downsample_factor"]                                 # KeyError like the reference
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sample_rate, audio_data = wavfile.read(file_path)
+    envelope, rate, _, debug = preprocess_pcm(audio_data, sample_rate, params, want_debug=bool(save_debug_file))
+    if save_debug_file:
+        # the reference writes the same int16 signal twice (:1047-1050 and :1056-1060)
+        wavfile.write(f"{os.path.splitext(file_path)[0]}_filtered_debug.wav", rate, debug)
+        base_name = os.path.basename(os.path.splitext(file_path)[0])
+        wavfile.write(os.path.join(output_directory, f"{base_name}_filtered_debug.wav"), rate, debug)
+    return envelope, rate
+
+
+# --------------------------------------------------------------------------- a2
+def _calculate_dynamic_noise_floor(audio_envelope: np.ndarray, sample_rate: int, params: Dict
+                                   ) -> Tuple[pd.Series, np.ndarray]:
+    """Dynamic noise floor from sanitised troughs.  Mirrors bpm_analysis.py:1064-1117."""
+    env = np.ascontiguousarray(audio_envelope, dtype=np.float64)
+    floor, troughs = runtime.ops().noise_floor(env, int(sample_rate), params)
+    logging.info(f"Trough Sanitization: Kept {len(troughs)} troughs.")
+    return pd.Series(floor, index=np.arange(len(env))), troughs
+
+
+# --------------------------------------------------------------------------- a3 / a4
+def _raw_peaks(envelope: np.ndarray, height_threshold: np.ndarray, sample_rate: int, params: Dict,
+               with_metrics: bool):
+    env = np.ascontiguousarray(envelope, dtype=np.float64)
+    height = np.ascontiguousarray(height_threshold, dtype=np.float64)
+    if height.shape != env.shape:                                   # what scipy's find_peaks raises
+        raise ValueError("array size of lower interval border must match x")
+    return runtime.ops().raw_peaks_and_metrics(env, height, int(sample_rate), params, with_metrics)
+
+
+def _find_raw_peaks(self, height_threshold: np.ndarray) -> np.ndarray:
+    """Replacement for ``PeakClassifier._find_raw_peaks`` (bpm_analysis.py:223-229)."""
+    peaks, _ = _raw_peaks(self.audio_envelope, height_threshold, self.sample_rate, self.params, False)
+    logging.info(f"Found {len(peaks)} raw peaks using dynamic height threshold.")
+    return peaks
+
+
+def _initialize_state(self, start_bpm_hint, precomputed_noise_floor, precomputed_troughs) -> Dict:
+    """Replacement for ``PeakClassifier._initialize_state`` (bpm_analysis.py:85-111)."""
+    state = {"analysis_data": {}}
+    state["dynamic_noise_floor"], state["trough_indices"] = precomputed_noise_floor, precomputed_troughs
+    peaks, met = _raw_peaks(self.audio_envelope, state["dynamic_noise_floor"].values, self.sample_rate,
+                            self.params, True)
+    logging.info(f"Found {len(peaks)} raw peaks using dynamic height threshold.")
+    state["all_peaks"] = peaks
+    state["analysis_data"]["dynamic_noise_floor_series"] = state["dynamic_noise_floor"]
+    state["analysis_data"]["trough_indices"] = state["trough_indices"]
+    deviation_times = (peaks[:-1] + peaks[1:]) / 2 / self.sample_rate
+    state["smoothed_dev_series"] = pd.Series(met["smoothed"], index=deviation_times)
+    state["analysis_data"]["deviation_series"] = state["smoothed_dev_series"]
+    state["long_term_bpm"] = float(start_bpm_hint) if start_bpm_hint else 80.0
+    state["candidate_beats"] = []
+    state["beat_debug_info"] = {}
+    state["long_term_bpm_history"] = []
+    state["sorted_troughs"] = sorted(state["trough_indices"])
+    state["consecutive_rr_rejections"] = 0
+    state["loop_idx"] = 0
+    return state
+
+
+def find_peaks(x, height=None, prominence=None, distance=None):
+    """scipy.signal.find_peaks-shaped operator (the subset the reference uses), on the GPU."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    if distance is not None and distance < 1:
+        raise ValueError("`distance` must be greater or equal to 1")
+    h = None
+    if height is not None:
+        h = np.broadcast_to(np.asarray(height, dtype=np.float64), x.shape).copy()
+    d = 1 if distance is None else int(np.ceil(distance))
+    if len(x) < 3:
+        return np.array([], dtype=np.int64), {}
+    return runtime.ops().find_peaks(x, h, None if prominence is None else float(prominence), d, 1), {}
+
+
+# --------------------------------------------------------------------------- a5
+def _epoch_us() -> int:
+    """datetime.fromtimestamp(0) -- the reference's series epoch (local time, :1472)."""
+    e = datetime.datetime.fromtimestamp(0)
+    return int((e - datetime.datetime(1970, 1, 1)) // datetime.timedelta(microseconds=1))
+
+
+def calculate_bpm_series(peaks: np.ndarray, sample_rate: int, params: Dict) -> Tuple[pd.Series, np.ndarray]:
+    """Smoothed BPM series from S1 peaks.  Mirrors bpm_analysis.py:1463-1484."""
+    if len(peaks) < 2:
+        return pd.Series(dtype=np.float64), np.array([])
+    window_sec = params["output_smoothing_window_sec"]
+    window_us = int(pd.Timedelta(f"{window_sec}s") // pd.Timedelta(microseconds=1))
+    inst, smoothed, times, us = runtime.ops().bpm_series(np.asarray(peaks, dtype=np.int64), int(sample_rate),
+                                                         window_us)
+    if len(inst) == 0:
+        return pd.Series(dtype=np.float64), np.array([])
+    index = pd.DatetimeIndex((us + _epoch_us()).astype("datetime64[us]"))
+    if not (np.median(inst) > 0):
+        return pd.Series(dtype=np.float64), times
+    return pd.Series(smoothed, index=index), times
+
+
+# --------------------------------------------------------------------------- a6
+def _series_arrays(series: pd.Series):
+    return np.ascontiguousarray(series.values, dtype=np.float64), series.index.as_unit("us").asi8
+
+
+def find_peak_recovery_rate(smoothed_bpm_series: pd.Series, window_sec: int = SLOPE_WINDOW_SEC) -> Optional[Dict]:
+    """Steepest HR decline after the peak BPM.  Mirrors bpm_analysis.py:1552-1574."""
+    if smoothed_bpm_series.empty or len(smoothed_bpm_series) < 2:
+        return None
+    vals, us = _series_arrays(smoothed_bpm_series)
+    hit = runtime.ops().steepest(vals, us, -1, float(window_sec))
+    if hit is None:
+        return None
+    i, j, slope = hit
+    start = int(np.argmax(vals))
+    dur = float((us[j] - us[start]) / 1e6 - (us[i] - us[start]) / 1e6)
+    ix = smoothed_bpm_series.index
+    return {"start_time": ix[i], "end_time": ix[j], "start_bpm": vals[i], "end_bpm": vals[j],
+            "slope_bpm_per_sec": slope, "duration_sec": dur}
+
+
+def find_peak_exertion_rate(smoothed_bpm_series: pd.Series, window_sec: int = SLOPE_WINDOW_SEC) -> Optional[Dict]:
+    """Steepest HR increase over the recording.  Mirrors bpm_analysis.py:1576-1595."""
+    if smoothed_bpm_series.empty or len(smoothed_bpm_series) < 2:
+        return None
+    vals, us = _series_arrays(smoothed_bpm_series)
+    hit = runtime.ops().steepest(vals, us, +1, float(window_sec))
+    if hit is None:
+        return None
+    i, j, slope = hit
+    dur = float((us[j] - us[0]) / 1e6 - (us[i] - us[0]) / 1e6)
+    ix = smoothed_bpm_series.index
+    return {"start_time": ix[i], "end_time": ix[j], "start_bpm": vals[i], "end_bpm": vals[j],
+            "slope_bpm_per_sec": slope, "duration_sec": dur}
+
+
+# --------------------------------------------------------------------------- a7
+def _hr_extrema(series: pd.Series, min_duration_sec: float):
+    vals, us = _series_arrays(series)
+    gaps = np.diff(us) / 1e6                                        # index.to_series().diff().dt.total_seconds()
+    # np.nanmean over [NaN, gaps...]: NaN -> 0, summed with it, divided by the non-NaN count
+    mean_gap = np.sum(np.concatenate([[0.0], gaps])) / len(gaps) if len(gaps) else np.nan
+    dist = 5 if np.isnan(mean_gap) or mean_gap == 0 else int((min_duration_sec / 2) / mean_gap)
+    if dist < 1:
+        raise ValueError("`distance` must be greater or equal to 1")
+    o = runtime.ops()
+    tops = o.find_peaks(vals, None, float(HR_PROMINENCE), dist, +1)
+    bottoms = o.find_peaks(vals, None, float(HR_PROMINENCE), dist, -1)
+    return vals, tops, bottoms
+
+
+def find_major_hr_inclines(smoothed_bpm_series: pd.Series, min_duration_sec: int = HR_MIN_DURATION_SEC,
+                           min_bpm_increase: int = HR_MIN_CHANGE_BPM) -> List[Dict]:
+    """Sustained HR increases.  Mirrors bpm_analysis.py:1486-1516."""
+    if smoothed_bpm_series.empty or len(smoothed_bpm_series) < 2:
+        return []
+    vals, tops, bottoms = _hr_extrema(smoothed_bpm_series, min_duration_sec)
+    if len(bottoms) == 0 or len(tops) == 0:
+        return []
+    ix = smoothed_bpm_series.index
+    out = []
+    for b in bottoms:
+        k = np.searchsorted(tops, b, side="right")
+        if k >= len(tops):
+            continue
+        p = tops[k]
+        dur = (ix[p] - ix[b]).total_seconds()
+        rise = vals[p] - vals[b]
+        if dur >= min_duration_sec and rise >= min_bpm_increase:
+            out.append({"start_time": ix[b], "end_time": ix[p], "start_bpm": vals[b], "end_bpm": vals[p],
+                        "duration_sec": dur, "bpm_increase": rise, "slope_bpm_per_sec": rise / dur})
+    out.sort(key=lambda d: d["slope_bpm_per_sec"], reverse=True)
+    return out
+
+
+def find_major_hr_declines(smoothed_bpm_series: pd.Series, min_duration_sec: int = HR_MIN_DURATION_SEC,
+                           min_bpm_decrease: int = HR_MIN_CHANGE_BPM) -> List[Dict]:
+    """Sustained HR decreases.  Mirrors bpm_analysis.py:1518-1550."""
+    if smoothed_bpm_series.empty or len(smoothed_bpm_series) < 2:
+        return []
+    vals, tops, bottoms = _hr_extrema(smoothed_bpm_series, min_duration_sec)
+    if len(bottoms) == 0 or len(tops) == 0:
+        return []
+    ix = smoothed_bpm_series.index
+    out = []
+    for p in tops:
+        k = np.searchsorted(bottoms, p, side="right")
+        if k >= len(bottoms):
+            continue
+        b = bottoms[k]
+        dur = (ix[b] - ix[p]).total_seconds()
+        drop = vals[p] - vals[b]
+        if dur >= min_duration_sec and drop >= min_bpm_decrease:
+            out.append({"start_time": ix[p], "end_time": ix[b], "start_bpm": vals[p], "end_bpm": vals[b],
+                        "duration_sec": dur, "bpm_decrease": drop, "slope_bpm_per_sec": (vals[b] - vals[p]) / dur})
+    out.sort(key=lambda d: d["slope_bpm_per_sec"])
+    return out
+
+
+# --------------------------------------------------------------------------- a8
+def calculate_windowed_hrv(s1_peaks: np.ndarray, sample_rate: int, params: Dict) -> pd.DataFrame:
+    """Sliding-window SDNN / RMSSDc.  Mirrors bpm_analysis.py:1414-1461."""
+    window_size_beats = params["hrv_window_size_beats"]
+    step_size_beats = params["hrv_step_size_beats"]
+    cols = ["time", "rmssdc", "sdnn", "bpm"]
+    if len(s1_peaks) < window_size_beats:
+        logging.warning(f"Not enough beats ({len(s1_peaks)}) to perform windowed HRV analysis with a window of "
+                        f"{window_size_beats} beats.")
+        return pd.DataFrame(columns=cols)
+    rows = runtime.ops().windowed_hrv(np.asarray(s1_peaks, dtype=np.int64), int(sample_rate),
+                                      int(window_size_beats), int(step_size_beats))
+    if len(rows) == 0:
+        logging.warning("Could not perform windowed HRV analysis. Recording may be too short or have too few beats.")
+        return pd.DataFrame(columns=cols)
+    logging.info(f"Beat-based windowed HRV analysis complete. Generated {len(rows)} data points.")
+    return pd.DataFrame(rows, columns=cols)
+
+
+# --------------------------------------------------------------------------- install
+def install(ref_module):
+    """Rebind the reference module's front-end names to this package.
+
+    ``ref_module`` is an imported reference ``bpm_analysis`` module.  Callers that did
+    ``from bpm_analysis import analyze_wav_file`` keep working because that function
+    resolves these names from the module's globals at call time.
+    """
+    for name in ("preprocess_audio", "_calculate_dynamic_noise_floor", "calculate_bpm_series",
+                 "find_peak_recovery_rate", "find_peak_exertion_rate", "find_major_hr_inclines",
+                 "find_major_hr_declines", "calculate_windowed_hrv"):
+        setattr(ref_module, name, globals()[name])
+    ref_module.PeakClassifier._find_raw_peaks = _find_raw_peaks
+    ref_module.PeakClassifier._initialize_state = _initialize_state
+    return ref_module

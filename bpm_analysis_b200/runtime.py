@@ -1,0 +1,414 @@
+"""Device-side plumbing: batches of recordings -> libbpm_b200 calls.
+
+PyTorch owns device memory, pinned staging buffers and streams; every numeric
+step is a call into the C ABI (``_native.py``).  Nothing here computes on
+samples with numpy -- the host only builds small descriptor arrays (offsets,
+lengths, filter design tables).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .design import PADLEN, design_block_filter
+from .params import band_edges, effective_decimation, filter_mode
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise nat.NativeLibraryError("no CUDA device visible: the front end runs on the GPU only "
+                                     "(there is no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _host_ptr(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+def make_items(n_in: Sequence[int], m: Sequence[int]) -> np.ndarray:
+    """Descriptor array (BpmItem) for recordings packed back to back."""
+    n_in = np.asarray(n_in, dtype=np.int64)
+    m = np.asarray(m, dtype=np.int64)
+    it = np.zeros(len(n_in), dtype=nat.ITEM_DTYPE)
+    it["n_in"], it["m"] = n_in, m
+    it["in_off"][1:] = np.cumsum(n_in)[:-1]
+    it["m_off"][1:] = np.cumsum(m)[:-1]
+    return it
+
+
+def to_device(a: np.ndarray) -> torch.Tensor:
+    require_cuda()
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda(non_blocking=False)
+
+
+@dataclass
+class FilterPlan:
+    """Where the band-pass runs and what it decimates to (bpm_analysis.py:1018-1045)."""
+    sample_rate: int
+    ds: int
+    rate: int            # envelope rate = sample_rate // ds
+    stride: int          # samples skipped before the filter (ds in 'parity', 1 in 'fullrate')
+    block: int           # filter outputs skipped (1 in 'parity', ds in 'fullrate')
+    clamped: bool
+    design: object       # BlockFilterDesign
+
+    def n_dec(self, n_in: int) -> int:
+        return (n_in + self.stride - 1) // self.stride
+
+    def m(self, n_in: int) -> int:
+        return (self.n_dec(n_in) + self.block - 1) // self.block
+
+
+def plan_filter(sample_rate: int, params: Dict) -> FilterPlan:
+    ds, rate, clamped = effective_decimation(sample_rate, params)
+    lowcut, highcut = band_edges(params)
+    mode = filter_mode(params)
+    if mode == "parity":
+        nyq = 0.5 * rate
+        lo, hi = lowcut / nyq, highcut / nyq
+        if hi >= 1.0:                                           # bpm_analysis.py:1041-1042
+            raise ValueError(f"Cannot create a {int(highcut) if float(highcut).is_integer() else highcut}Hz "
+                             f"filter. The effective sample rate of {rate}Hz is too low.")
+        return FilterPlan(sample_rate, ds, rate, ds, 1, clamped, design_block_filter(lo, hi, 1))
+    nyq = 0.5 * sample_rate
+    lo, hi = lowcut / nyq, highcut / nyq
+    if hi >= 1.0:
+        raise ValueError(f"Cannot create a {highcut}Hz filter. The sample rate of {sample_rate}Hz is too low.")
+    return FilterPlan(sample_rate, ds, rate, 1, ds, clamped, design_block_filter(lo, hi, ds))
+
+
+_design_cache: Dict[tuple, torch.Tensor] = {}
+
+
+def design_on_device(plan: FilterPlan) -> torch.Tensor:
+    key = (torch.cuda.current_device(), id(plan.design))
+    t = _design_cache.get(key)
+    if t is None:
+        t = to_device(plan.design.packed())
+        _design_cache[key] = t
+    return t
+
+
+def stage_a_config(plan: FilterPlan, params: Dict, pcm_dtype: int, channels: int, want_debug: bool
+                   ) -> nat.StageAConfig:
+    rate = plan.rate
+    noise_window = int(params["noise_window_sec"] * rate)                   # :1083
+    if noise_window < 3:
+        raise ValueError(f"min_periods 3 must be <= window {noise_window}")    # what pandas raises
+    distance = int(params["min_peak_distance_sec"] * rate)                  # :226, :1066
+    if distance < 1:
+        raise ValueError("`distance` must be greater or equal to 1")           # what scipy raises
+    return nat.StageAConfig(
+        stride=plan.stride, block=plan.block, pcm_dtype=pcm_dtype, channels=channels,
+        env_window=rate // 10, distance=distance, noise_window=noise_window,
+        want_debug_wav=1 if want_debug else 0,
+        trough_prom_q=float(params["trough_prominence_quantile"]),
+        peak_prom_q=float(params["peak_prominence_quantile"]),
+        floor_q=float(params["noise_floor_quantile"]),
+        rejection_multiplier=float(params.get("trough_rejection_multiplier", 4.0)),
+        smoothing_factor=float(params["deviation_smoothing_factor"]))
+
+
+class StageAResult:
+    """Device tensors of one stage-A call plus lazy host views per recording."""
+
+    def __init__(self, items: np.ndarray, rate: int, dev: Dict[str, torch.Tensor]):
+        self.items, self.rate, self.dev = items, rate, dev
+        self._host: Dict[str, np.ndarray] = {}
+
+    def host(self, name: str) -> np.ndarray:
+        if name not in self._host:
+            self._host[name] = self.dev[name].cpu().numpy()
+        return self._host[name]
+
+    def item(self, i: int) -> Dict[str, object]:
+        it = self.items[i]
+        o, m = int(it["m_off"]), int(it["m"])
+        nt, npk = int(self.host("trough_count")[i]), int(self.host("peak_count")[i])
+        out = {"rate": self.rate,
+               "filtered": self.host("filtered")[o:o + m], "envelope": self.host("envelope")[o:o + m],
+               "floor": self.host("floor")[o:o + m], "absmax": float(self.host("absmax")[i]),
+               "troughs": self.host("troughs")[o:o + nt].copy(), "peaks": self.host("peaks")[o:o + npk].copy(),
+               "strength": self.host("strength")[o:o + npk],
+               "deviation": self.host("deviation")[o:o + max(npk - 1, 0)],
+               "smoothed_dev": self.host("smoothed_dev")[o:o + max(npk - 1, 0)]}
+        if "debug_wav" in self.dev:
+            out["debug_wav"] = self.host("debug_wav")[o:o + m]
+        return out
+
+
+class StageARunner:
+    """a1..a4 for a batch of equal-format recordings in one C call (bpm_stage_a).
+
+    Buffers are allocated once for a given batch shape and reused, so repeated
+    calls (bench.py, servers) enqueue work without touching the allocator.
+    """
+
+    def __init__(self, n_in: Sequence[int], sample_rate: int, params: Dict, pcm_dtype=np.int16,
+                 channels: int = 1, want_debug: bool = False):
+        self.device = require_cuda()
+        self.lib = nat.load_library()
+        self.plan = plan_filter(sample_rate, params)
+        self.np_dtype = np.dtype(pcm_dtype)
+        if self.np_dtype not in nat.PCM_DTYPES:
+            raise TypeError(f"unsupported PCM dtype {self.np_dtype}")
+        self.channels = int(channels)
+        for n in n_in:
+            if self.plan.n_dec(int(n)) <= PADLEN:                     # scipy _validate_pad
+                raise ValueError("The length of the input vector x must be greater than padlen, which is 15.")
+        self.items = make_items(n_in, [self.plan.m(int(n)) for n in n_in])
+        self.n_items = len(self.items)
+        self.total_in = int(self.items["n_in"].sum())
+        self.total_m = int(self.items["m"].sum())
+        self.cfg = stage_a_config(self.plan, params, nat.PCM_DTYPES[self.np_dtype], self.channels, want_debug)
+        self.items_dev = torch.from_numpy(self.items.view(np.int64).reshape(-1, 4).copy()).to(self.device)
+        self.design_dev = design_on_device(self.plan)
+        self.design_words = int(self.design_dev.numel())
+        f64 = dict(dtype=torch.float64, device=self.device)
+        i64 = dict(dtype=torch.int64, device=self.device)
+        M, n = self.total_m, self.n_items
+        self.out = {"filtered": torch.empty(M, **f64), "envelope": torch.empty(M, **f64),
+                    "absmax": torch.empty(n, **f64), "floor": torch.empty(M, **f64),
+                    "troughs": torch.empty(M, **i64), "trough_count": torch.empty(n, **i64),
+                    "peaks": torch.empty(M, **i64), "peak_count": torch.empty(n, **i64),
+                    "strength": torch.empty(M, **f64), "deviation": torch.empty(M, **f64),
+                    "smoothed_dev": torch.empty(M, **f64)}
+        if want_debug:
+            self.out["debug_wav"] = torch.empty(M, dtype=torch.int16, device=self.device)
+        self.ws_bytes = int(self.lib.bpm_stage_a_workspace_bytes(M, n))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        self.pcm_dev = torch.empty(self.total_in * self.channels, dtype=_torch_dtype(self.np_dtype), device=self.device)
+        self.outs_struct = nat.StageAOutputs(**{k: self.out[k].data_ptr() if k in self.out else None
+                                                for k, _ in nat.StageAOutputs._fields_})
+
+    # -- input staging
+    def upload(self, pcms: Sequence[np.ndarray]) -> None:
+        """Pageable host arrays -> the device PCM buffer (one copy per recording)."""
+        off = 0
+        for a in pcms:
+            a = np.ascontiguousarray(a)
+            flat = torch.from_numpy(a.reshape(-1))
+            self.pcm_dev[off:off + flat.numel()].copy_(flat, non_blocking=False)
+            off += flat.numel()
+
+    def upload_pinned(self, pinned: torch.Tensor) -> None:
+        """One async H2D copy from a pinned host tensor holding the whole batch."""
+        self.pcm_dev.copy_(pinned, non_blocking=True)
+
+    # -- compute
+    def launch(self) -> None:
+        """Enqueue a1..a4 on the current stream (no host synchronisation)."""
+        rc = self.lib.bpm_stage_a(_ptr(self.pcm_dev), _ptr(self.items_dev), _host_ptr(self.items), self.n_items,
+                                  _ptr(self.design_dev), self.design_words, C.byref(self.cfg),
+                                  C.byref(self.outs_struct), _ptr(self.ws), self.ws_bytes, _stream_ptr())
+        nat.check(rc)
+
+    def result(self) -> StageAResult:
+        return StageAResult(self.items, self.plan.rate, self.out)
+
+
+def _torch_dtype(dt: np.dtype):
+    return {np.dtype(np.int16): torch.int16, np.dtype(np.int32): torch.int32, np.dtype(np.uint8): torch.uint8,
+            np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}[np.dtype(dt)]
+
+
+# ---------------------------------------------------------------------------- single ops
+class Ops:
+    """Thin per-operator wrappers (one recording or a batch) used by the drop-in functions."""
+
+    def __init__(self):
+        self.device = require_cuda()
+        self.lib = nat.load_library()
+
+    def _ws(self, nbytes: int) -> torch.Tensor:
+        return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+
+    def _items(self, lengths: Sequence[int]):
+        items = make_items(lengths, lengths)
+        dev = torch.from_numpy(items.view(np.int64).reshape(-1, 4).copy()).to(self.device)
+        return items, dev
+
+    def frontend(self, pcm: np.ndarray, sample_rate: int, params: Dict, want_debug: bool):
+        """K0+K1+K2(+K2b) for one recording -> (envelope, rate, filtered, debug_i16 or None)."""
+        plan = plan_filter(sample_rate, params)
+        channels = 1 if pcm.ndim == 1 else int(pcm.shape[1])
+        if pcm.dtype not in nat.PCM_DTYPES:
+            pcm = pcm.astype(np.float64)
+        n_in = int(pcm.shape[0])
+        if plan.n_dec(n_in) <= PADLEN:
+            raise ValueError("The length of the input vector x must be greater than padlen, which is 15.")
+        m = plan.m(n_in)
+        items = make_items([n_in], [m])
+        items_dev = torch.from_numpy(items.view(np.int64).reshape(-1, 4).copy()).to(self.device)
+        pcm_dev = to_device(pcm.reshape(-1))
+        design = design_on_device(plan)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        filt, env, amax = torch.empty(m, **f64), torch.empty(m, **f64), torch.empty(1, **f64)
+        nb = int(self.lib.bpm_frontend_workspace_bytes(m, 1))
+        ws = self._ws(nb)
+        nat.check(self.lib.bpm_frontend(_ptr(pcm_dev), nat.PCM_DTYPES[pcm.dtype], channels, _ptr(items_dev),
+                                        _host_ptr(items), 1, plan.stride, _ptr(design), int(design.numel()),
+                                        plan.rate // 10, _ptr(filt), _ptr(env), _ptr(amax), _ptr(ws), nb,
+                                        _stream_ptr()))
+        dbg = None
+        if want_debug:
+            dbg_dev = torch.empty(m, dtype=torch.int16, device=self.device)
+            nat.check(self.lib.bpm_debug_wav(_ptr(filt), _ptr(amax), _ptr(items_dev), _host_ptr(items), 1,
+                                             _ptr(dbg_dev), _stream_ptr()))
+            dbg = dbg_dev.cpu().numpy()
+        return env.cpu().numpy(), plan.rate, filt.cpu().numpy(), dbg
+
+    def quantile(self, x: np.ndarray, q: float) -> float:
+        items, items_dev = self._items([len(x)])
+        xd = to_device(np.asarray(x, dtype=np.float64))
+        out = torch.empty(1, dtype=torch.float64, device=self.device)
+        nb = int(self.lib.bpm_quantile_workspace_bytes(1))
+        ws = self._ws(nb)
+        nat.check(self.lib.bpm_quantile(_ptr(xd), _ptr(items_dev), _host_ptr(items), 1, float(q), _ptr(out),
+                                        _ptr(ws), nb, _stream_ptr()))
+        return float(out.cpu()[0])
+
+    def find_peaks(self, x: np.ndarray, height: Optional[np.ndarray] = None, prominence: Optional[float] = None,
+                   distance: int = 1, sign: int = 1) -> np.ndarray:
+        n = len(x)
+        items, items_dev = self._items([n])
+        xd = to_device(np.asarray(x, dtype=np.float64))
+        hd = to_device(np.asarray(height, dtype=np.float64)) if height is not None else None
+        pd_ = to_device(np.array([prominence], dtype=np.float64)) if prominence is not None else None
+        idx = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+        cnt = torch.empty(1, dtype=torch.int64, device=self.device)
+        nb = int(self.lib.bpm_find_peaks_workspace_bytes(n, 1))
+        ws = self._ws(nb)
+        nat.check(self.lib.bpm_find_peaks(_ptr(xd), int(sign), _ptr(hd), _ptr(pd_), int(distance), _ptr(items_dev),
+                                          _host_ptr(items), 1, _ptr(idx), _ptr(cnt), _ptr(ws), nb, _stream_ptr()))
+        c = int(cnt.cpu()[0])
+        return idx[:c].cpu().numpy()
+
+    def rolling_floor(self, env: np.ndarray, knots: np.ndarray, window: int, q: float) -> np.ndarray:
+        n = len(env)
+        items, items_dev = self._items([n])
+        ed = to_device(np.asarray(env, dtype=np.float64))
+        kbuf = torch.zeros(max(n, 1), dtype=torch.int64, device=self.device)
+        kbuf[:len(knots)] = to_device(np.asarray(knots, dtype=np.int64))
+        kc = to_device(np.array([len(knots)], dtype=np.int64))
+        out = torch.empty(n, dtype=torch.float64, device=self.device)
+        nb = int(self.lib.bpm_rolling_floor_workspace_bytes(n, 1))
+        ws = self._ws(nb)
+        nat.check(self.lib.bpm_rolling_floor(_ptr(ed), _ptr(kbuf), _ptr(kc), _ptr(items_dev), _host_ptr(items), 1,
+                                             int(window), float(q), _ptr(out), _ptr(ws), nb, _stream_ptr()))
+        return out.cpu().numpy()
+
+    def noise_floor(self, env: np.ndarray, rate: int, params: Dict):
+        n = len(env)
+        window = int(params["noise_window_sec"] * rate)
+        if window < 3:
+            raise ValueError(f"min_periods 3 must be <= window {window}")
+        distance = int(params["min_peak_distance_sec"] * rate)
+        if distance < 1:
+            raise ValueError("`distance` must be greater or equal to 1")
+        items, items_dev = self._items([n])
+        ed = to_device(np.asarray(env, dtype=np.float64))
+        floor = torch.empty(n, dtype=torch.float64, device=self.device)
+        tr = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+        cnt = torch.empty(1, dtype=torch.int64, device=self.device)
+        nb = int(self.lib.bpm_noise_floor_workspace_bytes(n, 1))
+        ws = self._ws(nb)
+        nat.check(self.lib.bpm_noise_floor(_ptr(ed), _ptr(items_dev), _host_ptr(items), 1, distance,
+                                           float(params["trough_prominence_quantile"]),
+                                           float(params["noise_floor_quantile"]), window,
+                                           float(params.get("trough_rejection_multiplier", 4.0)), _ptr(floor),
+                                           _ptr(tr), _ptr(cnt), _ptr(ws), nb, _stream_ptr()))
+        c = int(cnt.cpu()[0])
+        return floor.cpu().numpy(), tr[:c].cpu().numpy()
+
+    def raw_peaks_and_metrics(self, env: np.ndarray, floor: np.ndarray, rate: int, params: Dict,
+                              with_metrics: bool = True):
+        n = len(env)
+        distance = int(params["min_peak_distance_sec"] * rate)
+        if distance < 1:
+            raise ValueError("`distance` must be greater or equal to 1")
+        items, items_dev = self._items([n])
+        ed = to_device(np.asarray(env, dtype=np.float64))
+        fd = to_device(np.asarray(floor, dtype=np.float64))
+        pk = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+        cnt = torch.empty(1, dtype=torch.int64, device=self.device)
+        nb = int(self.lib.bpm_raw_peaks_workspace_bytes(n, 1))
+        ws = self._ws(nb)
+        nat.check(self.lib.bpm_raw_peaks(_ptr(ed), _ptr(fd), _ptr(items_dev), _host_ptr(items), 1, distance,
+                                         float(params["peak_prominence_quantile"]), _ptr(pk), _ptr(cnt), _ptr(ws),
+                                         nb, _stream_ptr()))
+        if not with_metrics:
+            c = int(cnt.cpu()[0])
+            return pk[:c].cpu().numpy(), None
+        f64 = dict(dtype=torch.float64, device=self.device)
+        st, dv, sm = torch.empty(n, **f64), torch.empty(n, **f64), torch.empty(n, **f64)
+        nat.check(self.lib.bpm_peak_metrics(_ptr(ed), _ptr(fd), _ptr(pk), _ptr(cnt), _ptr(items_dev),
+                                            _host_ptr(items), 1, float(params["deviation_smoothing_factor"]),
+                                            _ptr(st), _ptr(dv), _ptr(sm), _stream_ptr()))
+        c = int(cnt.cpu()[0])
+        d = max(c - 1, 0)
+        return pk[:c].cpu().numpy(), {"strength": st[:c].cpu().numpy(), "deviation": dv[:d].cpu().numpy(),
+                                      "smoothed": sm[:d].cpu().numpy()}
+
+    # ---- beat-list reductions
+    def bpm_series(self, beats: np.ndarray, rate: int, window_us: int):
+        b = len(beats)
+        items, items_dev = self._items([b])
+        bd = to_device(np.asarray(beats, dtype=np.int64))
+        f64 = dict(dtype=torch.float64, device=self.device)
+        inst, sm, ts = torch.empty(b, **f64), torch.empty(b, **f64), torch.empty(b, **f64)
+        us = torch.empty(b, dtype=torch.int64, device=self.device)
+        nv = torch.empty(1, dtype=torch.int64, device=self.device)
+        nat.check(self.lib.bpm_bpm_series(_ptr(bd), _ptr(items_dev), _host_ptr(items), 1, int(rate), int(window_us),
+                                          _ptr(inst), _ptr(sm), _ptr(ts), _ptr(us), _ptr(nv), _stream_ptr()))
+        n = int(nv.cpu()[0])
+        return inst[:n].cpu().numpy(), sm[:n].cpu().numpy(), ts[:n].cpu().numpy(), us[:n].cpu().numpy()
+
+    def steepest(self, values: np.ndarray, stamps_us: np.ndarray, sign: int, window_sec: float):
+        n = len(values)
+        items, items_dev = self._items([n])
+        vd = to_device(np.asarray(values, dtype=np.float64))
+        ud = to_device(np.asarray(stamps_us, dtype=np.int64))
+        nv = to_device(np.array([n], dtype=np.int64))
+        res = torch.empty(4, dtype=torch.float64, device=self.device)
+        ws = self._ws(256)
+        nat.check(self.lib.bpm_steepest_slope(_ptr(vd), _ptr(ud), _ptr(nv), _ptr(items_dev), _host_ptr(items), 1,
+                                              int(sign), float(window_sec), _ptr(res), _ptr(ws), 256, _stream_ptr()))
+        r = res.cpu().numpy()
+        if r[0] == 0.0:
+            return None
+        return int(r[1]), int(r[2]), float(r[3])
+
+    def windowed_hrv(self, beats: np.ndarray, rate: int, win: int, step: int) -> np.ndarray:
+        b = len(beats)
+        items, items_dev = self._items([b])
+        bd = to_device(np.asarray(beats, dtype=np.int64))
+        out = torch.empty((max(b, 1), 4), dtype=torch.float64, device=self.device)
+        rows = torch.empty(1, dtype=torch.int64, device=self.device)
+        nat.check(self.lib.bpm_windowed_hrv(_ptr(bd), _ptr(items_dev), _host_ptr(items), 1, int(rate), int(win),
+                                            int(step), _ptr(out), _ptr(rows), _stream_ptr()))
+        r = int(rows.cpu()[0])
+        return out[:r].cpu().numpy()
+
+
+_ops_singleton: Optional[Ops] = None
+
+
+def ops() -> Ops:
+    global _ops_singleton
+    if _ops_singleton is None:
+        _ops_singleton = Ops()
+    return _ops_singleton

@@ -1,0 +1,203 @@
+/*
+ * bpm_b200.h -- C ABI of libbpm_b200.so: the data-parallel numeric front end of
+ * pixeru/bpm_analysis, written for NVIDIA B200 (sm_100a).
+ *
+ * The reference has no FFI of its own: its hot path is Python calling
+ * numpy / scipy.signal / pandas (bpm_analysis.py:3-6).  Each entry point below
+ * replaces the library calls made at the cited reference lines; the Python
+ * mirror of the reference's functions (bpm_analysis_b200/frontend.py) binds
+ * them with ctypes.  INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - the library never allocates: callers pass a workspace sized by the
+ *     matching *_workspace_bytes() query; nothing is kept between calls;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*) and the call
+ *     returns without synchronising; results are valid after the stream drains;
+ *   - return value: 0 on success, a negative BPM_ERR_* code otherwise; never
+ *     throws, never exits;
+ *   - a call processes a ragged BATCH of recordings described by an array of
+ *     BpmItem; every per-sample buffer holds the recordings back to back at
+ *     `m_off`, every per-recording scalar / count is an array of n_items;
+ *   - variable-length results (trough / peak lists) are written as int64 at
+ *     `m_off` of the recording (capacity m) with the length in a per-recording
+ *     int64 count.
+ */
+#ifndef BPM_B200_H_
+#define BPM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPM_ABI_VERSION 1
+
+enum {
+  BPM_OK = 0,
+  BPM_ERR_ARG = -1,        /* bad argument (null pointer, negative size, unknown dtype) */
+  BPM_ERR_WORKSPACE = -2,  /* workspace too small */
+  BPM_ERR_CUDA = -3,       /* a CUDA runtime call or launch failed */
+  BPM_ERR_TOO_SHORT = -4   /* a recording is not longer than the 15-sample filter padding */
+};
+
+/* sample formats scipy.io.wavfile.read can hand to preprocess_audio (bpm_analysis.py:1014) */
+enum { BPM_PCM_I16 = 0, BPM_PCM_I32 = 1, BPM_PCM_U8 = 2, BPM_PCM_F32 = 3, BPM_PCM_F64 = 4 };
+
+typedef struct {
+  int64_t in_off;  /* first frame of this recording in the PCM buffer (frames, not bytes) */
+  int64_t n_in;    /* frames in this recording */
+  int64_t m_off;   /* first element of this recording in every envelope-rate buffer */
+  int64_t m;       /* envelope-rate samples: ceil(ceil(n_in / stride) / block) */
+} BpmItem;
+
+/* Layout (float64 words) of the filter design image built by
+ * bpm_analysis_b200/design.py::BlockFilterDesign.packed():
+ *   [0] block  [1] lookback_tiles  [2] D  [3] reserved
+ *   [4..16)  sos[2][6]      [16..20) zi[4]      [20..24) C[4]
+ *   [24..40) Ad[4][4]       [40..56) P[4][4]    [56..312) pow_chunk[16][4][4]
+ *   [312 .. 312+4*block)            wf[block][4]
+ *   [312+4*block .. 312+4*(2*block+1)) q[block+1][4]                              */
+#define BPM_DESIGN_HEADER_WORDS 312
+
+int bpm_abi_version(void);
+const char* bpm_error_string(int code);
+
+/* ---- K0+K1+K2(+K2b): preprocess_audio, bpm_analysis.py:1015-1054 -----------------
+ * pcm -> zero-phase Butterworth band-pass (scipy filtfilt semantics: odd padding 15,
+ * steady-state zi) evaluated at the kept samples -> |.| -> centred rolling mean.
+ *   stride/block: (ds, 1) = the reference's decimate-then-filter order;
+ *                 (1, ds) = filter at the original rate, keep every ds-th output.
+ *   filtered, envelope: out, float64[total_m];  absmax: out, float64[n_items] = max|filtered|. */
+size_t bpm_frontend_workspace_bytes(int64_t total_m, int n_items);
+int bpm_frontend(const void* pcm, int pcm_dtype, int channels,
+                 const BpmItem* items, const BpmItem* items_host, int n_items,
+                 int64_t stride, const double* design, int64_t design_words,
+                 int env_window, double* filtered, double* envelope, double* absmax,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* K2b: np.int16(y / max|y| * 32767), bpm_analysis.py:1049 (truncating cast). */
+int bpm_debug_wav(const double* filtered, const double* absmax, const BpmItem* items,
+                  const BpmItem* items_host, int n_items, int16_t* out, void* stream);
+
+/* ---- K3: np.quantile(x, q) (method 'linear'), bpm_analysis.py:225,1067,1075,1114 ---
+ * out[i] = quantile of recording i.  Exact order statistics (radix select on the
+ * float64 bit pattern) and numpy's two-branch lerp. */
+size_t bpm_quantile_workspace_bytes(int n_items);
+int bpm_quantile(const double* x, const BpmItem* items, const BpmItem* items_host, int n_items,
+                 double q, double* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K4: scipy.signal.find_peaks(sign*x, height=, prominence=, distance=) ----------
+ * bpm_analysis.py:227 (sign=+1, height = noise floor) and :1070 (sign=-1, no height).
+ * Order of conditions as scipy applies them: plateau-aware local maxima -> height ->
+ * distance (greedy, highest first) -> prominence (wlen=None).
+ *   height: float64[total_m] or NULL; prominence: float64[n_items] (device) or NULL;
+ *   distance: samples (>= 1); out_idx: int64[total_m] (list of recording i at m_off);
+ *   out_count: int64[n_items]. */
+size_t bpm_find_peaks_workspace_bytes(int64_t total_m, int n_items);
+int bpm_find_peaks(const double* x, int sign, const double* height, const double* prominence,
+                   int distance, const BpmItem* items, const BpmItem* items_host, int n_items,
+                   int64_t* out_idx, int64_t* out_count,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K5+K6: Series(idx->val).reindex(arange(m)).interpolate()
+ *             .rolling(window, min_periods=3, center=True).quantile(q).bfill().ffill()
+ * bpm_analysis.py:1081-1086 / :1103-1106.  The interpolated series is never
+ * materialised.  Output is all-NaN for a recording whose knot count is < 1. */
+size_t bpm_rolling_floor_workspace_bytes(int64_t total_m, int n_items);
+int bpm_rolling_floor(const double* envelope, const int64_t* knots, const int64_t* knot_count,
+                      const BpmItem* items, const BpmItem* items_host, int n_items,
+                      int window, double q, double* floor_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a2 whole: _calculate_dynamic_noise_floor, bpm_analysis.py:1064-1117 ------------
+ * K3 + K4(-env) + draft floor + K7 sanitisation + final floor, with the reference's
+ * fall-backs (<5 troughs: constant floor and ALL troughs returned; <=2 kept: draft
+ * floor; all-NaN: q(0.1)) resolved on the device.
+ *   floor_out: float64[total_m]; troughs_out: int64[total_m]; trough_count: int64[n_items]. */
+size_t bpm_noise_floor_workspace_bytes(int64_t total_m, int n_items);
+int bpm_noise_floor(const double* envelope, const BpmItem* items, const BpmItem* items_host,
+                    int n_items, int distance, double trough_prom_q, double floor_q, int window,
+                    double rejection_multiplier, double* floor_out, int64_t* troughs_out,
+                    int64_t* trough_count, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a3: PeakClassifier._find_raw_peaks, bpm_analysis.py:223-229 ------------------- */
+size_t bpm_raw_peaks_workspace_bytes(int64_t total_m, int n_items);
+int bpm_raw_peaks(const double* envelope, const double* floor, const BpmItem* items,
+                  const BpmItem* items_host, int n_items, int distance, double prom_q,
+                  int64_t* peaks_out, int64_t* peak_count,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K8: numeric part of PeakClassifier._initialize_state, bpm_analysis.py:93-100 ---
+ * strength[p] = max(0, env - floor) at peaks; deviation[p-1]; smoothed deviation
+ * (centred rolling mean, window max(5, int((P-1)*smoothing_factor)), min_periods=1).
+ * Outputs are laid out like the peak list (at m_off, length P resp. P-1). */
+int bpm_peak_metrics(const double* envelope, const double* floor, const int64_t* peaks,
+                     const int64_t* peak_count, const BpmItem* items, const BpmItem* items_host,
+                     int n_items, double smoothing_factor, double* strength, double* deviation,
+                     double* smoothed, void* stream);
+
+/* ---- beat-list reductions (K9, K10, K12).  A "beat list" is int64 indices at the
+ * envelope rate; lists of a batch are back to back, described by BpmItem with
+ * m = number of beats and m_off = first beat (in_off / n_in unused).            */
+
+/* K9 calculate_bpm_series, bpm_analysis.py:1463-1484.  Per beat list with B beats:
+ *   n_valid = number of intervals with dt > 1e-6; inst / smoothed / times_sec: float64,
+ *   stamp_us: int64 microseconds since the series epoch (what datetime.timedelta
+ *   quantises to); all four laid out at m_off, length n_valid.  window_us = smoothing
+ *   window in microseconds; the centred window is (t - w/2, t + w/2]. */
+int bpm_bpm_series(const int64_t* beats, const BpmItem* lists, const BpmItem* lists_host,
+                   int n_lists, int rate, int64_t window_us, double* inst, double* smoothed,
+                   double* times_sec, int64_t* stamp_us, int64_t* n_valid, void* stream);
+
+/* K10 find_peak_recovery_rate / find_peak_exertion_rate, bpm_analysis.py:1552-1595.
+ *   sign = -1: steepest decline searched from the series maximum onward (recovery);
+ *   sign = +1: steepest incline over the whole series (exertion).
+ *   result: float64[n_lists][4] = {found(0/1), start index, end index, slope}; indices
+ *   are positions in the series of that list. */
+int bpm_steepest_slope(const double* smoothed, const int64_t* stamp_us, const int64_t* n_valid,
+                       const BpmItem* lists, const BpmItem* lists_host, int n_lists, int sign,
+                       double window_sec, double* result, void* workspace, size_t workspace_bytes,
+                       void* stream);
+size_t bpm_steepest_slope_workspace_bytes(int64_t total_beats, int n_lists);
+
+/* K12 calculate_windowed_hrv, bpm_analysis.py:1414-1461.  rows[i] = number of windows
+ * of list i; out: float64[.][4] = {time, rmssdc, sdnn, bpm}, rows of list i start at
+ * row m_off (capacity m). */
+int bpm_windowed_hrv(const int64_t* beats, const BpmItem* lists, const BpmItem* lists_host,
+                     int n_lists, int rate, int window_beats, int step_beats,
+                     double* out, int64_t* rows, void* stream);
+
+/* ---- a1..a4 chained in one call (what analyze_wav_file does at :1731-1732 + :1635) --- */
+typedef struct {
+  int64_t stride, block;          /* filter placement, see bpm_frontend */
+  int32_t pcm_dtype, channels;
+  int32_t env_window;             /* rate // 10                 (:1053) */
+  int32_t distance;               /* int(min_peak_distance_sec * rate)  (:226, :1066) */
+  int32_t noise_window;           /* int(noise_window_sec * rate)       (:1083) */
+  int32_t want_debug_wav;
+  double trough_prom_q, peak_prom_q, floor_q, rejection_multiplier, smoothing_factor;
+} BpmStageAConfig;
+
+typedef struct {
+  double* filtered;   double* envelope;  double* absmax;   int16_t* debug_wav; /* may be NULL */
+  double* floor;      int64_t* troughs;  int64_t* trough_count;
+  int64_t* peaks;     int64_t* peak_count;
+  double* strength;   double* deviation; double* smoothed_dev;
+} BpmStageAOutputs;
+
+size_t bpm_stage_a_workspace_bytes(int64_t total_m, int n_items);
+int bpm_stage_a(const void* pcm, const BpmItem* items, const BpmItem* items_host, int n_items,
+                const double* design, int64_t design_words, const BpmStageAConfig* cfg_host,
+                const BpmStageAOutputs* out_host, void* workspace, size_t workspace_bytes,
+                void* stream);
+
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t bpm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPM_B200_H_ */

@@ -1,0 +1,107 @@
+"""CPU-side checks: the C-ABI library loads and exports what include/bpm_b200.h declares,
+the filter design matches scipy, the blocked formulation (numpy model of the kernels) matches
+scipy's filtfilt / sosfiltfilt, and host-side planning mirrors the reference's arithmetic."""
+import os
+import re
+
+import numpy as np
+import pytest
+from scipy.signal import butter, filtfilt, sosfiltfilt
+
+from bpm_analysis_b200 import _native, design, params as P, synth
+from oracle import kernel_models
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from bpm_analysis_b200.build import build_native
+    build_native()
+    return _native.load_library()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(REPO, "include", "bpm_b200.h")).read()
+    declared = set(re.findall(r"\b(bpm_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/bpm_b200.h but not exported"
+    assert declared == set(_native.EXPORTED_SYMBOLS)
+    assert lib.bpm_abi_version() == _native.ABI_VERSION
+    assert lib.bpm_error_string(-2) == b"workspace too small"
+
+
+def test_workspace_queries_are_monotone(lib):
+    a = lib.bpm_stage_a_workspace_bytes(100_000, 1)
+    b = lib.bpm_stage_a_workspace_bytes(1_000_000, 4)
+    assert 0 < a < b
+
+
+def test_missing_library_is_loud(tmp_path, monkeypatch):
+    monkeypatch.setattr(_native, "_lib", None)
+    with pytest.raises(_native.NativeLibraryError):
+        _native.load_library(str(tmp_path / "nope.so"))
+
+
+@pytest.mark.parametrize("sr,ds", [(44100, 146), (48000, 159), (4000, 12)])
+def test_butterworth_matches_scipy(sr, ds):
+    for rate in (sr // ds, sr):
+        lo, hi = 20 / (rate / 2), 150 / (rate / 2)
+        b, a = design.sos_to_ba(design.butter_bandpass_sos(lo, hi))
+        b0, a0 = butter(2, [lo, hi], btype="band")
+        assert np.max(np.abs(b - b0)) < 1e-12 * np.max(np.abs(b0)) + 1e-16
+        assert np.max(np.abs(a - a0)) < 1e-12
+
+
+def test_blocked_model_parity_mode_matches_filtfilt():
+    pcm, sr, _ = synth.config_c1(seed=3, duration_sec=6.0)
+    ds, rate, _ = P.effective_decimation(sr, P.default_params())
+    assert (ds, rate) == (146, 302)
+    lo, hi = 20 / (rate / 2), 150 / (rate / 2)
+    d = design.design_block_filter(lo, hi, 1)
+    y = kernel_models.blocked_filtfilt(pcm, d, stride=ds)
+    b, a = butter(2, [lo, hi], btype="band")
+    ref = filtfilt(b, a, pcm[::ds])
+    assert y.shape == ref.shape
+    assert np.max(np.abs(y - ref)) < 1e-11 * np.max(np.abs(ref))
+
+
+def test_blocked_model_fullrate_matches_sosfiltfilt():
+    pcm, sr, _ = synth.config_c1(seed=4, duration_sec=3.0)
+    ds = 146
+    lo, hi = 20 / (sr / 2), 150 / (sr / 2)
+    d = design.design_block_filter(lo, hi, ds)
+    y = kernel_models.blocked_filtfilt(pcm, d, stride=1)
+    sos = butter(2, [lo, hi], btype="band", output="sos")
+    ref = sosfiltfilt(sos, pcm.astype(np.float64), padlen=15)[::ds]
+    assert y.shape == ref.shape
+    assert np.max(np.abs(y - ref)) < 1e-9 * np.max(np.abs(ref))
+
+
+def test_design_image_layout():
+    d = design.design_block_filter(0.1, 0.9, 7)
+    img = d.packed()
+    assert img.shape[0] == _native.DESIGN_HEADER_WORDS + 4 * (2 * 7 + 1)
+    assert img[0] == 7 and img[2] == d.D
+    assert np.array_equal(img[24:40].reshape(4, 4), d.Ad)
+    assert np.array_equal(img[312:312 + 28].reshape(7, 4), d.wf)
+
+
+def test_decimation_plan_matches_reference_arithmetic():
+    p = P.default_params()
+    assert P.effective_decimation(44100, p) == (146, 302, True)
+    assert P.effective_decimation(48000, p) == (159, 301, True)
+    assert P.effective_decimation(4000, p) == (12, 333, True)
+    p2 = dict(p, downsample_factor=10)
+    assert P.effective_decimation(44100, p2) == (10, 4410, False)
+    p3 = dict(p, downsample_factor=1)
+    assert P.effective_decimation(44100, p3) == (1, 44100, False)
+
+
+def test_items_layout():
+    pytest.importorskip("torch")
+    from bpm_analysis_b200.runtime import make_items
+    it = make_items([100, 50, 70], [10, 5, 7])
+    assert it["in_off"].tolist() == [0, 100, 150] and it["m_off"].tolist() == [0, 10, 15]
+    assert it.view(np.int64).reshape(-1, 4)[1].tolist() == [100, 50, 10, 5]
