@@ -52,6 +52,8 @@ _SIGNATURES = {
     "bpm_abi_version": (C.c_int, []),
     "bpm_error_string": (C.c_char_p, [_I]),
     "bpm_launch_count": (_L, []),
+    "bpm_profile_begin": (_I, [_P]),
+    "bpm_profile_end": (_I, [C.c_char_p, _Z]),
     "bpm_frontend_workspace_bytes": (_Z, [_L, _I]),
     "bpm_frontend": (_I, [_P, _I, _I, _P, _P, _I, _L, _P, _L, _I, _P, _P, _P, _P, _Z, _P]),
     "bpm_debug_wav": (_I, [_P, _P, _P, _P, _I, _P, _P]),

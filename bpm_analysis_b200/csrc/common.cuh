@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <math.h>
+#include <string.h>
 #include "../../include/bpm_b200.h"
 
 namespace bpm {
@@ -14,12 +15,19 @@ constexpr int SCAN_THREADS = 256;     // == design.py SCAN_THREADS
 constexpr int SCAN_TILE = SCAN_CHUNK * SCAN_THREADS;
 constexpr int N_POW = 16;
 
-extern int64_t g_launches;            // counted by LAUNCH_OK
+extern int64_t g_launches;            // counted by BPM_LAUNCH_OK
+extern const char* g_cur_kernel;      // set by BPM_KERNEL just before a launch
+extern bool g_profiling;              // bpm_profile_begin / bpm_profile_end
+void profile_mark(const char* name, cudaStream_t st);
 
-#define BPM_LAUNCH_OK()                                          \
-  do {                                                           \
-    ++::bpm::g_launches;                                         \
-    if (cudaGetLastError() != cudaSuccess) return BPM_ERR_CUDA;  \
+// BPM_KERNEL(name); name<<<...>>>(...); BPM_LAUNCH_OK();   -- `st` is the stream in scope
+#define BPM_KERNEL(name) (::bpm::g_cur_kernel = #name)
+
+#define BPM_LAUNCH_OK()                                                   \
+  do {                                                                    \
+    ++::bpm::g_launches;                                                  \
+    if (cudaGetLastError() != cudaSuccess) return BPM_ERR_CUDA;           \
+    if (::bpm::g_profiling) ::bpm::profile_mark(::bpm::g_cur_kernel, st); \
   } while (0)
 
 #define BPM_TRY(expr)                 \

@@ -20,6 +20,8 @@
 namespace bpm {
 
 int64_t g_launches = 0;
+const char* g_cur_kernel = "?";
+bool g_profiling = false;
 
 // ------------------------------------------------------------------ design view
 struct DesignView {
@@ -591,16 +593,20 @@ int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
   if (fast) {
     const size_t smem = sizeof(double) * 8 * (block + 1) + 2 * (static_cast<size_t>(CT_BLOCKS) * block + 1 + 16);
     if (smem > 200 * 1024) {
+      BPM_KERNEL(k_contract_generic);
       k_contract_generic<<<dim3(cdiv(sh.max_m, 256), n_items), 256, 0, st>>>(pv, items, stride, design, b.uf, b.ub0, b.xe);
     } else {
       cudaFuncSetAttribute(k_contract_i16, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      BPM_KERNEL(k_contract_i16);
       k_contract_i16<<<dim3(cdiv(sh.max_m, CT_BLOCKS), n_items), CT_THREADS, smem, st>>>(
           static_cast<const int16_t*>(pcm), items, design, b.uf, b.ub0, b.xe);
     }
   } else {
+    BPM_KERNEL(k_contract_generic);
     k_contract_generic<<<dim3(cdiv(sh.max_m, 256), n_items), 256, 0, st>>>(pv, items, stride, design, b.uf, b.ub0, b.xe);
   }
   BPM_LAUNCH_OK();
+  BPM_KERNEL(k_filter_init);
   k_filter_init<<<cdiv(n_items, 64), 64, 0, st>>>(pv, items, n_items, stride, design, b.s0);
   BPM_LAUNCH_OK();
 
@@ -608,21 +614,27 @@ int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
   ScanParams sp{items, design, b.uf, b.sf, b.xe, b.s0, b.agg, filtered,
                 reinterpret_cast<unsigned long long*>(absmax)};
   if (sgrid.x > 1) {
+    BPM_KERNEL(k_scan);
     k_scan<0, false><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
     BPM_LAUNCH_OK();
   }
+  BPM_KERNEL(k_scan);
   k_scan<0, true><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
   BPM_LAUNCH_OK();
+  BPM_KERNEL(k_filter_tail);
   k_filter_tail<<<cdiv(n_items, 32), 32, 0, st>>>(pv, items, n_items, stride, design, b.sf, b.tail, b.tail_cap, b.sb_last);
   BPM_LAUNCH_OK();
   sp.u = b.ub0;
   sp.s_init = b.sb_last;
   if (sgrid.x > 1) {
+    BPM_KERNEL(k_scan);
     k_scan<1, false><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
     BPM_LAUNCH_OK();
   }
+  BPM_KERNEL(k_scan);
   k_scan<1, true><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
   BPM_LAUNCH_OK();
+  BPM_KERNEL(k_envelope);
   k_envelope<<<dim3(cdiv(sh.max_m, ENV_THREADS), n_items), ENV_THREADS,
                sizeof(double) * (ENV_THREADS + env_window), st>>>(filtered, items, env_window, envelope);
   BPM_LAUNCH_OK();
@@ -633,6 +645,7 @@ int debug_wav_run(const double* filtered, const double* absmax, const BpmItem* i
                   const BpmItem* items_host, int n_items, int16_t* out, cudaStream_t st) {
   if (!filtered || !absmax || !items || !items_host || !out || n_items <= 0) return BPM_ERR_ARG;
   const BatchShape sh = batch_shape(items_host, n_items);
+  BPM_KERNEL(k_debug_wav);
   k_debug_wav<<<dim3(cdiv(sh.max_m, 256), n_items), 256, 0, st>>>(filtered, absmax, items, out);
   BPM_LAUNCH_OK();
   return BPM_OK;

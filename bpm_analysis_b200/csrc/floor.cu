@@ -324,6 +324,7 @@ int rolling_floor_run(const double* env, const int64_t* knots, const int64_t* kn
   FloorBuffers b;
   BPM_TRY(carve_floor(ws, sh.total_m, sh.n_items, &b));
   const int64_t max_k = sh.max_m / 2 + 2;
+  BPM_KERNEL(k_knot_table);
   k_knot_table<<<dim3(cdiv(max_k, 256), sh.n_items), 256, 0, st>>>(env, knots, knot_count, items, window,
                                                                     b.kv, b.ks, b.kinv, b.meta);
   BPM_LAUNCH_OK();
@@ -332,6 +333,7 @@ int rolling_floor_run(const double* env, const int64_t* knots, const int64_t* kn
   if (run < 16) run = 16;
   if (run > 128) run = 128;
   KnotTable kt{knots, b.kv, b.ks, b.kinv};
+  BPM_KERNEL(k_rolling_floor);
   k_rolling_floor<<<dim3(cdiv(sh.max_m, RF_THREADS * run), sh.n_items), RF_THREADS, 0, st>>>(
       items, kt, b.meta, window, q, static_cast<int>(run), mode, alt, cval, nan_fill, out);
   BPM_LAUNCH_OK();

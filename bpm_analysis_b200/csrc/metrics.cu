@@ -54,10 +54,13 @@ int peak_metrics_run(const double* env, const double* floor_, const int64_t* pea
                      double* deviation, double* smoothed, cudaStream_t st) {
   if (!env || !floor_ || !peaks || !peak_count || !items || !strength || !deviation || !smoothed) return BPM_ERR_ARG;
   const dim3 grid(cdiv(sh.max_m / 2 + 2, 256), sh.n_items);
+  BPM_KERNEL(k_peak_strength);
   k_peak_strength<<<grid, 256, 0, st>>>(env, floor_, peaks, peak_count, items, strength);
   BPM_LAUNCH_OK();
+  BPM_KERNEL(k_peak_deviation);
   k_peak_deviation<<<grid, 256, 0, st>>>(strength, peak_count, items, deviation);
   BPM_LAUNCH_OK();
+  BPM_KERNEL(k_dev_smooth);
   k_dev_smooth<<<grid, 256, 0, st>>>(deviation, peak_count, items, factor, smoothed);
   BPM_LAUNCH_OK();
   return BPM_OK;
@@ -135,8 +138,10 @@ int bpm_series_run(const int64_t* beats, const BpmItem* lists, const BatchShape&
                    int64_t window_us, double* inst, double* smoothed, double* times_sec, int64_t* stamp_us,
                    int64_t* n_valid, cudaStream_t st) {
   if (!beats || !lists || !inst || !smoothed || !times_sec || !stamp_us || !n_valid || rate <= 0) return BPM_ERR_ARG;
+  BPM_KERNEL(k_bpm_instant);
   k_bpm_instant<<<sh.n_items, 1024, 0, st>>>(beats, lists, rate, inst, times_sec, stamp_us, n_valid);
   BPM_LAUNCH_OK();
+  BPM_KERNEL(k_bpm_smooth);
   k_bpm_smooth<<<dim3(cdiv(sh.max_m, 256), sh.n_items), 256, 0, st>>>(inst, stamp_us, n_valid, lists, window_us, smoothed);
   BPM_LAUNCH_OK();
   return BPM_OK;
@@ -244,6 +249,7 @@ int steepest_run(const double* smoothed, const int64_t* stamp_us, const int64_t*
                  int n_lists, int sign, double window_sec, double* result, cudaStream_t st) {
   if (!smoothed || !stamp_us || !n_valid || !lists || !result || n_lists <= 0 || (sign != 1 && sign != -1))
     return BPM_ERR_ARG;
+  BPM_KERNEL(k_steepest);
   k_steepest<<<n_lists, 1024, 0, st>>>(smoothed, stamp_us, n_valid, lists, sign, window_sec, result);
   BPM_LAUNCH_OK();
   return BPM_OK;
@@ -294,6 +300,7 @@ __global__ void k_hrv(const int64_t* __restrict__ beats, const BpmItem* __restri
 int hrv_run(const int64_t* beats, const BpmItem* lists, const BatchShape& sh, int rate, int win, int step,
             double* out, int64_t* rows, cudaStream_t st) {
   if (!beats || !lists || !out || !rows || rate <= 0 || win < 2 || step < 1) return BPM_ERR_ARG;
+  BPM_KERNEL(k_hrv);
   k_hrv<<<dim3(cdiv(sh.max_m / step + 1, 128), sh.n_items), 128, 0, st>>>(beats, lists, rate, win, step, out, rows);
   BPM_LAUNCH_OK();
   return BPM_OK;

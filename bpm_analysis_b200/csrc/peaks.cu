@@ -319,11 +319,14 @@ int compact_run(const unsigned char* flags, const int64_t* src, const BpmItem* i
                 int64_t* out, int64_t* out_count, cudaStream_t st) {
   const dim3 grid(cdiv(max_len > 0 ? max_len : 1, PK_TILE), sh.n_items);
   if (!counts_ready) {
+    BPM_KERNEL(k_count_flags);
     k_count_flags<<<grid, PK_THREADS, 0, st>>>(flags, items, dom_len, tile_counts);
     BPM_LAUNCH_OK();
   }
+  BPM_KERNEL(k_tile_scan);
   k_tile_scan<<<sh.n_items, 256, 0, st>>>(items, dom_len, tile_counts, out_count);
   BPM_LAUNCH_OK();
+  BPM_KERNEL(k_scatter);
   k_scatter<<<grid, PK_THREADS, 0, st>>>(flags, src, items, dom_len, tile_counts, out);
   BPM_LAUNCH_OK();
   return BPM_OK;
@@ -336,11 +339,13 @@ int find_peaks_run(const double* x, int sign, const double* height, const double
   PeakBuffers b;
   BPM_TRY(carve_peaks(ws, sh.total_m, sh.n_items, &b));
   const dim3 grid(cdiv(sh.max_m, PK_TILE), sh.n_items);
+  BPM_KERNEL(k_localmax_flags);
   k_localmax_flags<<<grid, PK_THREADS, 0, st>>>(x, sign, height, items, b.flags, b.tile_counts);
   BPM_LAUNCH_OK();
   BPM_TRY(compact_run(b.flags, nullptr, items, sh, nullptr, sh.max_m, true, b.tile_counts, b.cand, b.cand_count, st));
   // a local maximum needs a lower neighbour on both sides: at most (m-1)/2 candidates
   const int64_t max_c = sh.max_m / 2 + 1;
+  BPM_KERNEL(k_distance_prom);
   k_distance_prom<<<dim3(cdiv(max_c, DP_TILE), sh.n_items), DP_THREADS, 0, st>>>(
       x, sign, items, b.cand, b.cand_count, distance, prominence, b.cstate, b.tile_counts);
   BPM_LAUNCH_OK();

@@ -119,6 +119,7 @@ int noise_floor_run(const double* env, const BpmItem* items, const BatchShape& s
     Workspace w = sub_ws(ws, 0);
     BPM_TRY(find_peaks_run(env, -1, nullptr, q_tp, distance, items, sh, s.all_troughs, s.n_all, w, st));  // :1070
   }
+  BPM_KERNEL(k_floor_modes);
   k_floor_modes<<<cdiv(n, 128), 128, 0, st>>>(s.n_all, nullptr, n, 0, s.few, s.mode);
   BPM_LAUNCH_OK();
   {
@@ -137,11 +138,13 @@ int noise_floor_run(const double* env, const BpmItem* items, const BatchShape& s
     BPM_TRY(rolling_floor_run(env, s.all_troughs, s.n_all, items, sh, window, floor_q, s.mode, nullptr, s.q_nf,
                               nullptr, s.draft, w, st));
   }
+  BPM_KERNEL(k_sanitize_flags);
   k_sanitize_flags<<<dim3(cdiv(sh.max_m / 2 + 2, 256), n), 256, 0, st>>>(env, s.draft, s.all_troughs, s.n_all,
                                                                         s.few, items, mult, s.keep);     // :1090-1097
   BPM_LAUNCH_OK();
   BPM_TRY(compact_run(s.keep, s.all_troughs, items, sh, s.n_all, sh.max_m / 2 + 2, false, s.tile_counts,
                       troughs_out, trough_count, st));
+  BPM_KERNEL(k_floor_modes);
   k_floor_modes<<<cdiv(n, 128), 128, 0, st>>>(s.n_all, trough_count, n, 1, s.few, s.mode);
   BPM_LAUNCH_OK();
   {
@@ -180,6 +183,33 @@ int raw_peaks_run(const double* env, const double* floor_, const BpmItem* items,
 
 }  // namespace bpm
 
+// ------------------------------------------------------------------ per-kernel timing
+// Diagnostic used by bench.py for the roofline line: while profiling is on, an event is
+// recorded after every launch; on a serial stream consecutive events bracket one kernel.
+#include <map>
+#include <string>
+#include <vector>
+namespace bpm {
+static std::vector<cudaEvent_t> g_prof_pool;
+static std::vector<std::pair<const char*, int>> g_prof_marks;   // (kernel name, event index)
+static size_t g_prof_used = 0;
+
+static cudaEvent_t prof_event() {
+  if (g_prof_used == g_prof_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    g_prof_pool.push_back(e);
+  }
+  return g_prof_pool[g_prof_used++];
+}
+
+void profile_mark(const char* name, cudaStream_t st) {
+  const int idx = static_cast<int>(g_prof_used);
+  cudaEventRecord(prof_event(), st);
+  g_prof_marks.emplace_back(name, idx);
+}
+}  // namespace bpm
+
 // =========================================================================== C ABI
 using namespace bpm;
 
@@ -199,6 +229,35 @@ const char* bpm_error_string(int code) {
 }
 
 int64_t bpm_launch_count(void) { return g_launches; }
+
+int bpm_profile_begin(void* stream) {
+  g_prof_used = 0;
+  g_prof_marks.clear();
+  g_profiling = true;
+  profile_mark("<begin>", static_cast<cudaStream_t>(stream));
+  return BPM_OK;
+}
+
+// Writes "name count total_ms\n" lines (aggregated per kernel) into `text`.
+int bpm_profile_end(char* text, size_t cap) {
+  g_profiling = false;
+  if (!text || cap == 0) return BPM_ERR_ARG;
+  if (g_prof_marks.empty()) { text[0] = 0; return BPM_OK; }
+  if (cudaEventSynchronize(g_prof_pool[g_prof_marks.back().second]) != cudaSuccess) return BPM_ERR_CUDA;
+  std::map<std::string, std::pair<long, double>> agg;
+  for (size_t i = 1; i < g_prof_marks.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_prof_pool[g_prof_marks[i - 1].second], g_prof_pool[g_prof_marks[i].second]);
+    auto& a = agg[g_prof_marks[i].first];
+    a.first += 1;
+    a.second += ms;
+  }
+  std::string out;
+  for (auto& kv : agg) out += kv.first + " " + std::to_string(kv.second.first) + " " + std::to_string(kv.second.second) + "\n";
+  if (out.size() + 1 > cap) return BPM_ERR_WORKSPACE;
+  memcpy(text, out.c_str(), out.size() + 1);
+  return BPM_OK;
+}
 
 size_t bpm_frontend_workspace_bytes(int64_t total_m, int n_items) { return frontend_workspace_bytes(total_m, n_items); }
 

@@ -234,17 +234,22 @@ int quantile_run(const double* x, const BpmItem* items, const BatchShape& sh, do
   const int n = sh.n_items;
   if (cudaMemsetAsync(b.hist, 0, sizeof(unsigned int) * static_cast<size_t>(n) * SEL_PASSES * SEL_BINS, st) != cudaSuccess)
     return BPM_ERR_CUDA;
+  BPM_KERNEL(k_select_init);
   k_select_init<<<cdiv(n, 128), 128, 0, st>>>(items, n, q, cond, b.states);
   BPM_LAUNCH_OK();
+  BPM_KERNEL(k_select_preset);
   k_select_preset<<<cdiv(n, 128), 128, 0, st>>>(b.states + static_cast<size_t>(SEL_PASSES) * n, n);
   BPM_LAUNCH_OK();
   const dim3 grid(cdiv(sh.max_m, SEL_TILE), n);
   for (int p = 0; p < SEL_PASSES; ++p) {
+    BPM_KERNEL(k_select_pass);
     k_select_pass<<<grid, SEL_THREADS, 0, st>>>(x, items, p, b.states, b.hist, n);
     BPM_LAUNCH_OK();
   }
+  BPM_KERNEL(k_select_next);
   k_select_next<<<grid, SEL_THREADS, 0, st>>>(x, items, b.states, b.hist, n);
   BPM_LAUNCH_OK();
+  BPM_KERNEL(k_select_finish);
   k_select_finish<<<cdiv(n, 128), 128, 0, st>>>(b.states + static_cast<size_t>(SEL_PASSES) * n, n, out);
   BPM_LAUNCH_OK();
   return BPM_OK;

@@ -51,7 +51,10 @@ def make_items(n_in: Sequence[int], m: Sequence[int]) -> np.ndarray:
 
 def to_device(a: np.ndarray) -> torch.Tensor:
     require_cuda()
-    return torch.from_numpy(np.ascontiguousarray(a)).cuda(non_blocking=False)
+    a = np.ascontiguousarray(a)
+    if not a.flags.writeable:          # torch refuses read-only views (e.g. arrays out of np.load)
+        a = a.copy()
+    return torch.from_numpy(a).cuda(non_blocking=False)
 
 
 @dataclass

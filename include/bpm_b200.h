@@ -197,6 +197,12 @@ int bpm_stage_a(const void* pcm, const BpmItem* items, const BpmItem* items_host
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t bpm_launch_count(void);
 
+/* Diagnostic per-kernel timing (bench.py's roofline line).  Between begin and end an event
+ * is recorded after every launch on `stream`; end synchronises and writes one line per
+ * kernel, "name launches total_ms", into the HOST buffer `text_host`. */
+int bpm_profile_begin(void* stream);
+int bpm_profile_end(char* text_host, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif
