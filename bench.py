@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""Headline benchmark: audio-hours/s of the bpm_analysis front end on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--filter-mode parity|fullrate]
+
+Workload (BASELINE.json configs[1], "C2"): one synthetic 60-min 48 kHz mono int16
+heart-sound recording (60 -> 170 -> 80 BPM ramp) per GPU.  One step = one pass of the hot
+path over it: a1..a4 (band-pass + envelope, dynamic noise floor, raw peaks, per-peak
+metrics) on the audio, then a5..a8 (BPM series, steepest slopes, incline/decline extrema,
+windowed HRV) on the recording's beat list.  With N > 1 (torchrun) every rank processes its
+own recording of the same shape -- recordings are independent units, so there is no
+data-path collective ("weak" scaling); NCCL is only used for the barrier and the
+max-over-ranks of the device time.
+
+`value` is measured with the PCM already in HBM; `e2e` through the public runner objects
+with pinned HOST buffers (H2D of the PCM and beat list and D2H of every result inside the
+timed region).  `--impl reference` times the CPU oracle (oracle/ref_port.py: the reference's
+own numpy/scipy/pandas calls) on the host cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC, UNIT = "audio_hours_per_sec", "audio-hours/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--filter-mode", default="parity", choices=["parity", "fullrate"])
+    ap.add_argument("--duration-sec", type=float, default=3600.0)
+    ap.add_argument("--sample-rate", type=int, default=48000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--dump-kernels", default=None, help="write the per-kernel table to this JSON file")
+    return ap.parse_args()
+
+
+def workload_name(args) -> str:
+    return (f"C2: synthetic {args.duration_sec / 60:g}-min {args.sample_rate / 1000:g} kHz mono int16 heart-sound "
+            f"recording (60->170->80 BPM ramp), one per GPU")
+
+
+def make_recording(args, rank: int):
+    from bpm_analysis_b200 import synth
+    return synth.config_c2(seed=2 + rank, duration_sec=args.duration_sec, sample_rate=args.sample_rate)
+
+
+def bench_params(args):
+    from bpm_analysis_b200.params import default_params
+    p = default_params()
+    p["save_filtered_wav"] = False
+    p["filter_mode"] = args.filter_mode
+    return p
+
+
+def hr_extrema_distance(beat_idx: np.ndarray, rate: int) -> int:
+    """`distance` the reference derives for find_major_hr_* (bpm_analysis.py:1492-1494)."""
+    t = beat_idx[1:] / rate
+    ip = np.trunc(t)
+    us = ip.astype(np.int64) * 1000000 + np.rint((t - ip) * 1e6).astype(np.int64)
+    gaps = np.diff(us) / 1e6
+    mean_gap = np.sum(np.concatenate([[0.0], gaps])) / len(gaps)
+    return max(1, int((10 / 2) / mean_gap))
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- roofline
+def algorithmic_bytes(kernel: str, shp: dict) -> float:
+    """Compulsory bytes per launch of one kernel at its own interface:
+    every input element it needs read once + every output element written once."""
+    N, M, T, P, B = shp["N"], shp["M"], shp["T"], shp["P"], shp["B"]
+    s_in = 2
+    table = {
+        "k_contract_i16": N * s_in + 8 * M,            # N*s_in + 8*M
+        "k_contract_generic": M * s_in + 8 * M,        # parity: only the kept samples are needed
+        "k_scan": 80 * M,                              # 32 u + 32 s_f (+8 x) in, state / y out (avg of 4 launches)
+        "k_envelope": 16 * M,
+        "k_select_pass": 8 * M,
+        "k_select_next": 8 * M,
+        "k_localmax_flags": 9 * M,
+        "k_scatter": M + 8 * max(T, P),
+        "k_distance_prom": 24 * max(T, P),
+        "k_count_flags": max(T, P),
+        "k_knot_table": 40 * T,
+        "k_rolling_floor": 16 * T + 8 * M,             # SURVEY §8(d) K5+K6
+        "k_sanitize_flags": 24 * T,
+        "k_peak_strength": 32 * P, "k_peak_deviation": 16 * P, "k_dev_smooth": 16 * P,
+        "k_bpm_instant": 32 * B, "k_bpm_smooth": 24 * B, "k_steepest": 16 * B, "k_hrv": 8 * B + 32 * (B // 5),
+    }
+    return float(table.get(kernel, 0.0))
+
+
+def measured_peak_gbs():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel: str, mode: str):
+    """dram bytes per launch from the committed ncu --set full capture, if one exists."""
+    try:
+        with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as fh:
+            return json.load(fh).get(mode, {}).get(kernel)
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------- CPU side
+def _cpu_one(job):
+    pcm, sr, beat_idx, params = job
+    from oracle import ref_port
+    fe = ref_port.front_end(pcm, sr, params)
+    ref_port.beat_reductions(beat_idx, fe["rate"], params)
+    return len(fe["peaks"])
+
+
+_POOL_JOB = None
+
+
+def _cpu_pool_worker(_):
+    return _cpu_one(_POOL_JOB)
+
+
+def cpu_step(pcm, sr, beat_idx, params, workers: int):
+    """One CPU step: `workers` recordings, one per process (the reference is single-threaded)."""
+    global _POOL_JOB
+    if workers <= 1:
+        t0 = time.perf_counter()
+        _cpu_one((pcm, sr, beat_idx, params))
+        return time.perf_counter() - t0
+    import multiprocessing as mp
+    _POOL_JOB = (pcm, sr, beat_idx, params)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        pool.map(_cpu_pool_worker, range(workers))            # spin-up excluded
+        t0 = time.perf_counter()
+        pool.map(_cpu_pool_worker, range(workers))
+        return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    params = bench_params(args)
+    from bpm_analysis_b200 import synth
+    from bpm_analysis_b200.params import effective_decimation
+    pcm, sr, beats = make_recording(args, 0)
+    _, rate, _ = effective_decimation(sr, params)
+    cores = os.cpu_count() or 1
+    workers = min(cores, 64 if args.filter_mode == "parity" else 8)
+    # bounded sample: keep (steps + warmup) CPU steps inside ~3 minutes (~7 s per audio-hour per core)
+    budget = 170.0 / max(1, args.steps + args.warmup + 1)
+    sample_sec = float(min(args.duration_sec, max(120.0, budget / 8.0 * 3600.0)))
+    n = int(sample_sec * sr)
+    pcm_s = pcm[:n]
+    beat_idx = synth.beats_to_envelope_indices(beats[beats < sample_sec - 1.0], rate)
+    global _POOL_JOB
+    _POOL_JOB = (pcm_s, sr, beat_idx, params)
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(workers) as pool:
+        for _ in range(args.warmup):
+            pool.map(_cpu_pool_worker, range(workers))
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_pool_worker, range(workers))
+            times.append(time.perf_counter() - t0)
+    step = sum(times) / len(times)
+    value = workers * (sample_sec / 3600.0) / step
+    sample = (f"{workers} x first {sample_sec:g} s of the C2 recording per step, one process per recording "
+              f"(numpy/scipy/pandas are single-threaded on this path), a1..a8")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "filter_mode": args.filter_mode},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU side
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from bpm_analysis_b200 import _native, synth
+    from bpm_analysis_b200.runtime import BeatRunner, StageARunner, profile_kernels
+
+    lib = _native.load_library()
+    params = bench_params(args)
+    pcm, sr, beats = make_recording(args, rank)
+    A = StageARunner([len(pcm)], sr, params)
+    rate = A.plan.rate
+    beat_idx = synth.beats_to_envelope_indices(beats, rate)
+    Bn = BeatRunner(len(beat_idx), rate, params, hr_extrema_distance(beat_idx, rate))
+    pcm_pin = torch.from_numpy(pcm).pin_memory()
+    beats_pin = torch.from_numpy(beat_idx).pin_memory()
+    A.upload_pinned(pcm_pin)
+    Bn.upload(beats_pin)
+    torch.cuda.synchronize()
+    audio_hours = args.duration_sec / 3600.0
+
+    def step():
+        A.launch()
+        Bn.launch()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = lib.bpm_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = int(lib.bpm_launch_count() - l0)
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    value = world * audio_hours / (ms_step / 1e3)
+
+    # ---- end to end: pinned host in, pinned host out, every step
+    M = A.total_m
+    host = {k: torch.empty_like(A.out[k], device="cpu").pin_memory()
+            for k in ("envelope", "floor", "troughs", "peaks", "trough_count", "peak_count", "strength",
+                      "smoothed_dev")}
+    hostb = {k: torch.empty_like(v, device="cpu").pin_memory() for k, v in Bn.out.items()}
+
+    def e2e_step():
+        A.upload_pinned(pcm_pin)
+        Bn.upload(beats_pin)
+        A.launch()
+        Bn.launch()
+        for k in ("trough_count", "peak_count"):
+            host[k].copy_(A.out[k], non_blocking=True)
+        for k in ("n_tops", "n_bottoms", "hrv_rows", "slopes", "n_valid"):
+            hostb[k].copy_(Bn.out[k], non_blocking=True)
+        host["envelope"].copy_(A.out["envelope"], non_blocking=True)
+        host["floor"].copy_(A.out["floor"], non_blocking=True)
+        torch.cuda.synchronize()
+        nt, npk = int(host["trough_count"][0]), int(host["peak_count"][0])
+        host["troughs"][:nt].copy_(A.out["troughs"][:nt], non_blocking=True)
+        for k in ("peaks", "strength", "smoothed_dev"):
+            host[k][:npk].copy_(A.out[k][:npk], non_blocking=True)
+        nv, rows = int(hostb["n_valid"][0]), int(hostb["hrv_rows"][0])
+        for k in ("smoothed", "times", "stamps"):
+            hostb[k][:nv].copy_(Bn.out[k][:nv], non_blocking=True)
+        hostb["tops"][:int(hostb["n_tops"][0])].copy_(Bn.out["tops"][:int(hostb["n_tops"][0])], non_blocking=True)
+        hostb["bottoms"][:int(hostb["n_bottoms"][0])].copy_(Bn.out["bottoms"][:int(hostb["n_bottoms"][0])],
+                                                            non_blocking=True)
+        hostb["hrv"][:rows].copy_(Bn.out["hrv"][:rows], non_blocking=True)
+        torch.cuda.synchronize()
+        return nt, npk, nv, rows
+
+    for _ in range(max(1, args.warmup // 2)):
+        nt, npk, nv, rows = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    clocks = sampler.stop()
+    e2e_value = world * audio_hours / (e2e_ms / 1e3)
+    h2d = pcm_pin.numel() * pcm_pin.element_size() + beats_pin.numel() * 8
+    d2h = 2 * M * 8 + nt * 8 + npk * 24 + nv * 24 + rows * 32 + 8 * 8 + 7 * 8 + \
+        (int(hostb["n_tops"][0]) + int(hostb["n_bottoms"][0])) * 8
+
+    # ---- per-kernel event timing (separate pass: events between launches perturb the step)
+    roofline, kernels = None, {}
+    if not args.no_profile:
+        prof = profile_kernels(lambda: [step() for _ in range(args.steps)])
+        torch.cuda.synchronize()
+        shp = {"N": len(pcm), "M": M, "T": nt, "P": npk, "B": len(beat_idx)}
+        peak, peak_src = measured_peak_gbs()
+        total_ms = sum(v[1] for v in prof.values()) or 1.0
+        for name, (cnt, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+            avg_us = ms * 1e3 / cnt
+            ab = algorithmic_bytes(name, shp)
+            kernels[name] = {"launches_per_step": cnt / args.steps, "avg_us": round(avg_us, 3),
+                             "share": round(ms / total_ms, 4), "alg_bytes": ab,
+                             "gbs": round(ab / (avg_us * 1e-6) / 1e9, 2) if avg_us > 0 else None}
+        top = next(iter(kernels))
+        k = kernels[top]
+        roofline = {"kernel": top, "bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": round(k["gbs"] / peak, 5) if k["gbs"] else None,
+                    "traffic": ncu_traffic(top, args.filter_mode), "peak_source": peak_src,
+                    "share_of_step": k["share"], "avg_launch_us": k["avg_us"],
+                    "how": "CUDA events after every launch over a separate pass of `steps` steps"}
+        if args.dump_kernels and rank == 0:
+            with open(args.dump_kernels, "w") as fh:
+                json.dump({"filter_mode": args.filter_mode, "shape": shp, "ms_per_step": ms_step, "kernels": kernels},
+                          fh, indent=1)
+
+    # ---- CPU baseline beside it (rank 0, single GPU runs only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.environ.setdefault("OMP_NUM_THREADS", "1")
+        sample_sec = min(args.duration_sec, 3600.0)
+        n = int(sample_sec * sr)
+        bi = synth.beats_to_envelope_indices(beats[beats < sample_sec - 1.0], rate)
+        t = cpu_step(pcm[:n], sr, bi, params, 1)
+        cpu = {"value": (sample_sec / 3600.0) / t, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"1 x first {sample_sec:g} s of the same recording, a1..a8, one core "
+                         f"(the reference is single-threaded); {t:.2f} s"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(args), "filter_mode": args.filter_mode,
+                           "raw_samples": len(pcm), "envelope_samples": M, "beats": len(beat_idx),
+                           "l2": "inputs larger than L2 (PCM %.1f MB per step)" % (len(pcm) * 2 / 1e6),
+                           "parallelism": f"{world} x independent recordings, no collective"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

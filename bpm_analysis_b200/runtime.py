@@ -415,3 +415,75 @@ def ops() -> Ops:
     if _ops_singleton is None:
         _ops_singleton = Ops()
     return _ops_singleton
+
+
+class BeatRunner:
+    """a5..a8 for one beat list with preallocated device buffers (bpm_bpm_series,
+    bpm_steepest_slope x2, bpm_find_peaks x2 for the incline/decline extrema, bpm_windowed_hrv).
+
+    The beat list must be strictly increasing (every interval valid), which is what the
+    classifier and the synthetic generators produce; the series length is then B-1.
+    """
+
+    def __init__(self, n_beats: int, rate: int, params: Dict, hr_distance: int):
+        self.device = require_cuda()
+        self.lib = nat.load_library()
+        self.rate, self.B = int(rate), int(n_beats)
+        if self.B < 3:
+            raise ValueError("need at least 3 beats")
+        self.window_us = int(round(float(params["output_smoothing_window_sec"]) * 1e6))
+        self.win, self.step = int(params["hrv_window_size_beats"]), int(params["hrv_step_size_beats"])
+        self.hr_distance = int(hr_distance)
+        self.items = make_items([self.B], [self.B])
+        self.items_dev = torch.from_numpy(self.items.view(np.int64).reshape(-1, 4).copy()).to(self.device)
+        n = self.B - 1
+        self.series_items = make_items([n], [n])
+        self.series_items_dev = torch.from_numpy(self.series_items.view(np.int64).reshape(-1, 4).copy()).to(self.device)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        i64 = dict(dtype=torch.int64, device=self.device)
+        self.beats_dev = torch.empty(self.B, **i64)
+        self.out = {"inst": torch.empty(self.B, **f64), "smoothed": torch.empty(self.B, **f64),
+                    "times": torch.empty(self.B, **f64), "stamps": torch.empty(self.B, **i64),
+                    "n_valid": torch.empty(1, **i64), "slopes": torch.empty(8, **f64),
+                    "tops": torch.empty(self.B, **i64), "n_tops": torch.empty(1, **i64),
+                    "bottoms": torch.empty(self.B, **i64), "n_bottoms": torch.empty(1, **i64),
+                    "hrv": torch.empty((self.B, 4), **f64), "hrv_rows": torch.empty(1, **i64)}
+        self.prom = torch.full((1,), 5.0, **f64)
+        self.ws_bytes = int(self.lib.bpm_find_peaks_workspace_bytes(self.B, 1))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+
+    def upload(self, beats_host: torch.Tensor) -> None:
+        self.beats_dev.copy_(beats_host, non_blocking=True)
+
+    def launch(self) -> None:
+        L, o, st = self.lib, self.out, _stream_ptr()
+        nat.check(L.bpm_bpm_series(_ptr(self.beats_dev), _ptr(self.items_dev), _host_ptr(self.items), 1, self.rate,
+                                   self.window_us, _ptr(o["inst"]), _ptr(o["smoothed"]), _ptr(o["times"]),
+                                   _ptr(o["stamps"]), _ptr(o["n_valid"]), st))
+        for k, sign in enumerate((+1, -1)):
+            res = o["slopes"][4 * k:4 * k + 4]
+            nat.check(L.bpm_steepest_slope(_ptr(o["smoothed"]), _ptr(o["stamps"]), _ptr(o["n_valid"]),
+                                           _ptr(self.series_items_dev), _host_ptr(self.series_items), 1, sign, 20.0,
+                                           _ptr(res), _ptr(self.ws), self.ws_bytes, st))
+        for sign, idx, cnt in ((+1, o["tops"], o["n_tops"]), (-1, o["bottoms"], o["n_bottoms"])):
+            nat.check(L.bpm_find_peaks(_ptr(o["smoothed"]), sign, None, _ptr(self.prom), self.hr_distance,
+                                       _ptr(self.series_items_dev), _host_ptr(self.series_items), 1, _ptr(idx),
+                                       _ptr(cnt), _ptr(self.ws), self.ws_bytes, st))
+        nat.check(L.bpm_windowed_hrv(_ptr(self.beats_dev), _ptr(self.items_dev), _host_ptr(self.items), 1, self.rate,
+                                     self.win, self.step, _ptr(o["hrv"]), _ptr(o["hrv_rows"]), st))
+
+
+def profile_kernels(fn, stream_ptr: Optional[int] = None) -> Dict[str, tuple]:
+    """Run ``fn()`` with per-kernel event timing on; returns {kernel: (launches, total_ms)}."""
+    lib = nat.load_library()
+    nat.check(lib.bpm_profile_begin(stream_ptr if stream_ptr is not None else _stream_ptr()))
+    try:
+        fn()
+    finally:
+        buf = C.create_string_buffer(1 << 16)
+        nat.check(lib.bpm_profile_end(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        out[name] = (int(cnt), float(ms))
+    return out
