@@ -145,7 +145,7 @@ def algorithmic_bytes(kernel: str, shp: dict) -> float:
         "k_select_next": 8 * M,
         "k_localmax_flags": 9 * M,
         "k_scatter": M + 8 * max(T, P),
-        "k_distance_prom": 24 * max(T, P),
+        "k_distance": 17 * max(T, P), "k_prominence": 24 * max(T, P),
         "k_count_flags": max(T, P),
         "k_knot_table": 40 * T,
         "k_rolling_floor": 16 * T + 8 * M,             # SURVEY §8(d) K5+K6

@@ -181,19 +181,32 @@ __global__ void __launch_bounds__(256) k_contract_generic(PcmView pcm, const Bpm
 
 // ------------------------------------------------------ contraction (int16, full rate)
 // The HBM-bound kernel: mono int16 at the original rate (stride 1), block = ds.
-// A CTA stages CT_BLOCKS consecutive blocks (+1 sample) of PCM in shared memory with
-// 128-bit coalesced loads (raw int16, converted at use), then each thread owns one block
-// and accumulates its 8 dot products; the weight rows are read as warp-wide broadcasts.
-// The first / last CTA of a recording (odd-extension samples) take the direct path.
-constexpr int CT_THREADS = 128;
-constexpr int CT_BLOCKS = 128;     // kept samples per CTA
+//   * a CTA owns CT_BLOCKS consecutive blocks; one elected thread brings their PCM span into
+//     shared memory with a single TMA bulk copy (cp.async.bulk + mbarrier), 16-byte aligned;
+//   * each thread accumulates the 8 dot products of CT_J blocks; the weight row of sample l is
+//     the same for every thread, so it lives in constant memory and reaches the FP64 pipe as a
+//     uniform-register operand (LDCU + DFMA R,R,UR,R): no shared-memory traffic for weights;
+//   * the first / last CTA of a recording (odd-extension samples) read global memory directly.
+// 8 DFMA per input sample: at 64 FP64 lanes per SM that is about the time HBM needs to
+// deliver the 2 bytes, so the kernel sits where the FP64 and HBM rooflines meet.
+constexpr int CT_THREADS = 64;
+constexpr int CT_J = 2;
+constexpr int CT_BLOCKS = CT_THREADS * CT_J;   // kept samples per CTA
+constexpr int CW_MAX_BLOCK = 767;              // weight image limit: 8*(block+1) doubles of constant memory
+
+__constant__ double c_contract_w[8 * (CW_MAX_BLOCK + 1)];
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
 
 __global__ void __launch_bounds__(CT_THREADS) k_contract_i16(const int16_t* __restrict__ pcm,
                                                              const BpmItem* __restrict__ items,
                                                              const double* __restrict__ design,
                                                              double* __restrict__ uf, double* __restrict__ ub0,
                                                              double* __restrict__ xe) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long s_bar;
   const BpmItem it = items[blockIdx.y];
   const int64_t j0 = static_cast<int64_t>(blockIdx.x) * CT_BLOCKS;
   if (j0 >= it.m) return;
@@ -202,16 +215,6 @@ __global__ void __launch_bounds__(CT_THREADS) k_contract_i16(const int16_t* __re
   const int64_t n = it.n_in;                               // stride 1: n_dec == n_in
   const int nb = static_cast<int>(min(static_cast<int64_t>(CT_BLOCKS), it.m - j0));
   const int span = nb * blk + 1;                           // samples E_j0 .. E_j0 + nb*blk
-  // shared layout: weights [(blk+1)][8] (wf row | q row), then raw PCM as 16-byte vectors
-  double* s_w = reinterpret_cast<double*>(smem_raw);
-  int4* s_v = reinterpret_cast<int4*>(s_w + 8 * (blk + 1));
-  const double* __restrict__ wf = d.wf();
-  const double* __restrict__ q = d.q();
-  for (int t = threadIdx.x; t < 4 * (blk + 1); t += CT_THREADS) {
-    const int l = t >> 2, c = t & 3;
-    s_w[8 * l + c] = (l < blk) ? wf[4 * l + c] : 0.0;
-    s_w[8 * l + 4 + c] = q[4 * l + c];
-  }
   const int64_t i0 = j0 * blk;                              // data index of the first staged sample
   const int16_t* __restrict__ src = pcm + it.in_off;
   const bool interior = (i0 >= 8) && (i0 + span + 8 <= n);
@@ -219,54 +222,88 @@ __global__ void __launch_bounds__(CT_THREADS) k_contract_i16(const int16_t* __re
   if (interior) {
     const uintptr_t addr = reinterpret_cast<uintptr_t>(src + i0);
     head = static_cast<int>((addr & 15) >> 1);             // samples before i0 in its 16-byte word
-    const int4* __restrict__ v = reinterpret_cast<const int4*>(src + i0 - head);
-    const int nvec = (head + span + 7) >> 3;
-    for (int t = threadIdx.x; t < nvec; t += CT_THREADS) s_v[t] = __ldg(v + t);
+    const uint32_t bytes = static_cast<uint32_t>(((head + span + 7) >> 3) << 4);
+    const uint32_t bar = smem_u32(&s_bar);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              smem_u32(smem_raw)),
+          "l"(src + i0 - head), "r"(bytes), "r"(bar)
+          : "memory");
+    }
+    __syncthreads();                                       // barrier initialised before anyone polls it
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_TMA:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra DONE_TMA;\n"
+        "bra WAIT_TMA;\n"
+        "DONE_TMA:\n"
+        "}" ::"r"(bar)
+        : "memory");
   }
-  __syncthreads();
-  const int jl = threadIdx.x;
-  if (jl >= nb) return;
-  const int64_t j = j0 + jl;
-  double f0 = 0, f1 = 0, f2 = 0, f3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-  double x0;
-  const bool bulk = (j < it.m - 1);
+  const int tid = threadIdx.x;
+  double acc[CT_J][8];
+#pragma unroll
+  for (int jj = 0; jj < CT_J; ++jj)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[jj][c] = 0.0;
+  double x0[CT_J];
   if (interior) {
-    const int16_t* __restrict__ xs = reinterpret_cast<const int16_t*>(s_v) + head + jl * blk;
-    x0 = static_cast<double>(xs[0]);
-    if (bulk) {
-#pragma unroll 4
-      for (int l = 0; l <= blk; ++l) {
-        const double v = static_cast<double>(xs[l]);
-        const double2 w0 = *reinterpret_cast<const double2*>(s_w + 8 * l);
-        const double2 w1 = *reinterpret_cast<const double2*>(s_w + 8 * l + 2);
-        const double2 w2 = *reinterpret_cast<const double2*>(s_w + 8 * l + 4);
-        const double2 w3 = *reinterpret_cast<const double2*>(s_w + 8 * l + 6);
-        f0 += w0.x * v; f1 += w0.y * v; f2 += w1.x * v; f3 += w1.y * v;
-        b0 += w2.x * v; b1 += w2.y * v; b2 += w3.x * v; b3 += w3.y * v;
+    const int16_t* __restrict__ xs = reinterpret_cast<const int16_t*>(smem_raw) + head + tid * blk;
+    const int jstride = CT_THREADS * blk;
+    // blocks beyond nb (last CTA only) read staged-but-unused or stale shared memory; their
+    // results are discarded below, the reads stay inside the allocation
+#pragma unroll
+    for (int jj = 0; jj < CT_J; ++jj) x0[jj] = static_cast<double>(xs[jj * jstride]);
+#pragma unroll 2
+    for (int l = 0; l <= blk; ++l) {
+      double v[CT_J];
+#pragma unroll
+      for (int jj = 0; jj < CT_J; ++jj) v[jj] = static_cast<double>(xs[jj * jstride + l]);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const double w = c_contract_w[8 * l + c];
+#pragma unroll
+        for (int jj = 0; jj < CT_J; ++jj) acc[jj][c] += w * v[jj];
       }
     }
   } else {
     PcmView pv{pcm, BPM_PCM_I16, 1};
     const ExtSignal x = make_ext(pv, it, 1);
-    const int64_t E = PADLEN + j * blk;
-    x0 = x.at(E);
-    if (bulk) {
+#pragma unroll
+    for (int jj = 0; jj < CT_J; ++jj) {
+      const int jl = jj * CT_THREADS + tid;
+      x0[jj] = 0.0;
+      if (jl >= nb) continue;
+      const int64_t E = PADLEN + (j0 + jl) * blk;
+      x0[jj] = x.at(E);
+      if (j0 + jl >= it.m - 1) continue;
       for (int l = 0; l <= blk; ++l) {
         const double v = x.at(E + l);
-        const double* w = s_w + 8 * l;
-        f0 += w[0] * v; f1 += w[1] * v; f2 += w[2] * v; f3 += w[3] * v;
-        b0 += w[4] * v; b1 += w[5] * v; b2 += w[6] * v; b3 += w[7] * v;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[jj][c] += c_contract_w[8 * l + c] * v;
       }
     }
   }
-  xe[it.m_off + j] = x0;
-  if (!bulk) return;
-  double* pf = uf + 4 * (it.m_off + j);
-  double* pb = ub0 + 4 * (it.m_off + j);
-  reinterpret_cast<double2*>(pf)[0] = make_double2(f0, f1);
-  reinterpret_cast<double2*>(pf)[1] = make_double2(f2, f3);
-  reinterpret_cast<double2*>(pb)[0] = make_double2(b0, b1);
-  reinterpret_cast<double2*>(pb)[1] = make_double2(b2, b3);
+#pragma unroll
+  for (int jj = 0; jj < CT_J; ++jj) {
+    const int jl = jj * CT_THREADS + tid;
+    if (jl >= nb) continue;
+    const int64_t j = j0 + jl;
+    xe[it.m_off + j] = x0[jj];
+    if (j >= it.m - 1) continue;
+    double2* pf = reinterpret_cast<double2*>(uf + 4 * (it.m_off + j));
+    double2* pb = reinterpret_cast<double2*>(ub0 + 4 * (it.m_off + j));
+    pf[0] = make_double2(acc[jj][0], acc[jj][1]);
+    pf[1] = make_double2(acc[jj][2], acc[jj][3]);
+    pb[0] = make_double2(acc[jj][4], acc[jj][5]);
+    pb[1] = make_double2(acc[jj][6], acc[jj][7]);
+  }
 }
 
 // ------------------------------------------------------------------ init / tail
@@ -576,7 +613,7 @@ int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
                  double* absmax, Workspace& ws, cudaStream_t st) {
   if (!pcm || !items || !items_host || !design || !filtered || !envelope || !absmax) return BPM_ERR_ARG;
   if (n_items <= 0 || stride < 1 || channels < 1 || pcm_dtype < 0 || pcm_dtype > BPM_PCM_F64) return BPM_ERR_ARG;
-  if (block < 1 || block > MAX_BLOCK || design_words < BPM_DESIGN_HEADER_WORDS + 4 * (2 * block + 1)) return BPM_ERR_ARG;
+  if (block < 1 || block > MAX_BLOCK || design_words < BPM_DESIGN_HEADER_WORDS + 16 * block + 12) return BPM_ERR_ARG;
   if (env_window < 1 || env_window > ENV_MAX_W) return BPM_ERR_ARG;
   const BatchShape sh = batch_shape(items_host, n_items);
   for (int i = 0; i < n_items; ++i) {
@@ -589,18 +626,18 @@ int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
   PcmView pv{pcm, pcm_dtype, channels};
 
   if (cudaMemsetAsync(absmax, 0, sizeof(double) * n_items, st) != cudaSuccess) return BPM_ERR_CUDA;
-  const bool fast = (pcm_dtype == BPM_PCM_I16 && channels == 1 && stride == 1 && block >= 8);
+  const bool fast = (pcm_dtype == BPM_PCM_I16 && channels == 1 && stride == 1 && block >= 8 &&
+                     block <= CW_MAX_BLOCK && (reinterpret_cast<uintptr_t>(pcm) & 1) == 0);
   if (fast) {
-    const size_t smem = sizeof(double) * 8 * (block + 1) + 2 * (static_cast<size_t>(CT_BLOCKS) * block + 1 + 16);
-    if (smem > 200 * 1024) {
-      BPM_KERNEL(k_contract_generic);
-      k_contract_generic<<<dim3(cdiv(sh.max_m, 256), n_items), 256, 0, st>>>(pv, items, stride, design, b.uf, b.ub0, b.xe);
-    } else {
-      cudaFuncSetAttribute(k_contract_i16, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      BPM_KERNEL(k_contract_i16);
-      k_contract_i16<<<dim3(cdiv(sh.max_m, CT_BLOCKS), n_items), CT_THREADS, smem, st>>>(
-          static_cast<const int16_t*>(pcm), items, design, b.uf, b.ub0, b.xe);
-    }
+    // PCM span of a CTA, rounded up to whole 16-byte words on both sides
+    const size_t smem = 2 * (static_cast<size_t>(CT_BLOCKS) * block + 1 + 16) + 32;
+    if (cudaMemcpyToSymbolAsync(c_contract_w, design + BPM_DESIGN_HEADER_WORDS + 4 * (2 * block + 1),
+                                sizeof(double) * 8 * (block + 1), 0, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return BPM_ERR_CUDA;
+    cudaFuncSetAttribute(k_contract_i16, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    BPM_KERNEL(k_contract_i16);
+    k_contract_i16<<<dim3(cdiv(sh.max_m, CT_BLOCKS), n_items), CT_THREADS, smem, st>>>(
+        static_cast<const int16_t*>(pcm), items, design, b.uf, b.ub0, b.xe);
   } else {
     BPM_KERNEL(k_contract_generic);
     k_contract_generic<<<dim3(cdiv(sh.max_m, 256), n_items), 256, 0, st>>>(pv, items, stride, design, b.uf, b.ub0, b.xe);

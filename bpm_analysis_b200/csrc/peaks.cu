@@ -8,10 +8,11 @@
 //                      and (optionally) at or above its height threshold; per-tile counts.
 //   k_tile_scan        exclusive scan of tile counts per recording -> offsets, totals.
 //   k_scatter          ordered compaction of flagged positions (int64).
-//   k_distance_prom    greedy "highest first removes neighbours closer than d" resolved as a
+//   k_distance         greedy "highest first removes neighbours closer than d" resolved as a
 //                      fix-point on clusters of candidates (a cluster = run of candidates with
-//                      gaps < d; clusters never interact), then a warp-cooperative prominence
-//                      walk with ballot early exit for every survivor.
+//                      gaps < d; clusters never interact), staged in shared memory.
+//   k_prominence       warp-cooperative prominence walk (both sides at once, 32 samples per
+//                      step, ballot early exit) for every survivor.
 // Equal-height candidates within `distance`: the later index wins (what a stable argsort
 // gives scipy); numpy's default sort is unstable, so the reference does not pin this case.
 #include "common.cuh"
@@ -141,47 +142,56 @@ __device__ __forceinline__ bool higher_priority(double va, int64_t ka, double vb
 }
 
 // does the prominence of the peak at p reach thr?  (scipy _peak_prominences, wlen=None)
-// warp-cooperative: every lane calls with the same arguments.
+// Warp-cooperative, both sides walked together 32 samples at a time: a side passes as soon as
+// a sample low enough (x[p] - x[i] >= thr) is met before the walk would stop (a sample above
+// the peak, or the end of the signal); it fails when the walk stops first.
 __device__ bool warp_prominence_ok(const double* __restrict__ xi, int sign, int64_t n, int64_t p, double thr) {
   const int lane = threadIdx.x & 31;
   const double xp = signed_val(xi[p], sign);
   if (__dsub_rn(xp, xp) >= thr) return true;            // the peak itself is the running minimum
-  bool side_ok[2];
-#pragma unroll
-  for (int side = 0; side < 2; ++side) {
-    bool ok = false;
-    int64_t base = (side == 0) ? p - 1 : p + 1;
-    while (true) {
-      const int64_t idx = (side == 0) ? base - lane : base + lane;
-      const bool valid = (idx >= 0 && idx < n);
-      const double v = valid ? signed_val(xi[idx], sign) : 0.0;
-      const bool stop = !valid || (v > xp);
-      const bool pass = valid && !(v > xp) && (__dsub_rn(xp, v) >= thr);
-      const unsigned bs = __ballot_sync(0xffffffffu, stop);
-      const unsigned bp = __ballot_sync(0xffffffffu, pass);
+  int done_l = 0, done_r = 0;                             // 0 open, 1 passed
+  int64_t bl = p - 1, br = p + 1;
+  while (true) {
+    const int64_t il = bl - lane, ir = br + lane;
+    const bool vl = !done_l && il >= 0, vr = !done_r && ir < n;
+    const double xl = vl ? signed_val(xi[il], sign) : 0.0;
+    const double xr = vr ? signed_val(xi[ir], sign) : 0.0;
+    if (!done_l) {
+      const bool stop = !vl || (xl > xp);
+      const bool pass = vl && !(xl > xp) && (__dsub_rn(xp, xl) >= thr);
+      const unsigned bs = __ballot_sync(0xffffffffu, stop), bp = __ballot_sync(0xffffffffu, pass);
       const int fs = bs ? __ffs(bs) : 33, fp = bp ? __ffs(bp) : 33;
-      if (fp < fs) { ok = true; break; }
-      if (bs) { ok = false; break; }
-      base += (side == 0) ? -32 : 32;
+      if (fp < fs) done_l = 1;
+      else if (bs) return false;
+      else bl -= 32;
     }
-    side_ok[side] = ok;
-    if (!ok) return false;
+    if (!done_r) {
+      const bool stop = !vr || (xr > xp);
+      const bool pass = vr && !(xr > xp) && (__dsub_rn(xp, xr) >= thr);
+      const unsigned bs = __ballot_sync(0xffffffffu, stop), bp = __ballot_sync(0xffffffffu, pass);
+      const int fs = bs ? __ffs(bs) : 33, fp = bp ? __ffs(bp) : 33;
+      if (fp < fs) done_r = 1;
+      else if (bs) return false;
+      else br += 32;
+    }
+    if (done_l && done_r) return true;
   }
-  return side_ok[0] && side_ok[1];
 }
 
 constexpr int DP_THREADS = 256;
-constexpr int DP_TILE = 1024;      // nominal candidates per CTA
+constexpr int DP_TILE = 256;       // nominal candidates per CTA
+constexpr int DP_CAP = 1536;       // candidates a CTA can stage in shared memory
 
-__global__ void __launch_bounds__(DP_THREADS) k_distance_prom(const double* __restrict__ x, int sign,
-                                                              const BpmItem* __restrict__ items,
-                                                              const int64_t* __restrict__ cand,
-                                                              const int64_t* __restrict__ cand_count,
-                                                              int distance, const double* __restrict__ prominence,
-                                                              unsigned char* __restrict__ state /* per candidate */,
-                                                              int* __restrict__ tile_counts) {
+// Distance rule: state[k] = 1 kept / 0 removed for every candidate.
+__global__ void __launch_bounds__(DP_THREADS) k_distance(const double* __restrict__ x, int sign,
+                                                         const BpmItem* __restrict__ items,
+                                                         const int64_t* __restrict__ cand,
+                                                         const int64_t* __restrict__ cand_count, int distance,
+                                                         unsigned char* __restrict__ state) {
   __shared__ long long s_edge[2];
-  __shared__ int s_cnt;
+  __shared__ int s_pos[DP_CAP];
+  __shared__ double s_val[DP_CAP];
+  __shared__ unsigned char s_st[DP_CAP];
   const int item = blockIdx.y;
   const BpmItem it = items[item];
   const int64_t nc = cand_count[item];
@@ -190,10 +200,15 @@ __global__ void __launch_bounds__(DP_THREADS) k_distance_prom(const double* __re
   const int64_t k1 = min(nc, k0 + DP_TILE);
   const int64_t* __restrict__ pos = cand + it.m_off;
   const double* __restrict__ xi = x + it.m_off;
-  volatile unsigned char* stt = state + it.m_off;
+  unsigned char* st_out = state + it.m_off;
   const int64_t d = distance;
 
+  if (distance <= 1) {
+    for (int64_t k = k0 + threadIdx.x; k < k1; k += DP_THREADS) st_out[k] = 1;
+    return;
+  }
   // own the clusters whose head lies in [k0, k1): ks = first head >= k0, ke = first head >= k1
+  // (a cluster = run of candidates with gaps < d; a head is a candidate >= d after its predecessor)
   if (threadIdx.x < 2) s_edge[threadIdx.x] = nc;
   __syncthreads();
   for (int e = 0; e < 2; ++e) {
@@ -209,57 +224,104 @@ __global__ void __launch_bounds__(DP_THREADS) k_distance_prom(const double* __re
     }
   }
   const int64_t ks = s_edge[0], ke = s_edge[1];
-  // zero the per-tile count for the nominal tile (a tile fully inside someone else's cluster
-  // still has to publish its count; the owner counts for it below)
-  for (int64_t k = ks + threadIdx.x; k < ke; k += DP_THREADS) stt[k] = 0;
-  __syncthreads();
+  const int64_t len = ke - ks;
+  if (len <= 0) return;
 
-  if (distance > 1) {
+  if (len <= DP_CAP) {
+    const int L = static_cast<int>(len);
+    for (int t = threadIdx.x; t < L; t += DP_THREADS) {
+      const int64_t pp = pos[ks + t];
+      s_pos[t] = static_cast<int>(pp);
+      s_val[t] = signed_val(xi[pp], sign);
+      s_st[t] = 0;
+    }
+    __syncthreads();
+    const int di = distance;
     while (true) {
       int changed = 0;
-      for (int64_t k = ks + threadIdx.x; k < ke; k += DP_THREADS) {
-        if (stt[k] != 0) continue;
-        const int64_t pk = pos[k];
-        const double vk = signed_val(xi[pk], sign);
+      for (int k = threadIdx.x; k < L; k += DP_THREADS) {
+        if (s_st[k] != 0) continue;
+        const int pk = s_pos[k];
+        const double vk = s_val[k];
         bool any_keep = false, any_open = false;
-        for (int64_t k2 = k - 1; k2 >= ks && pk - pos[k2] < d; --k2) {
-          if (higher_priority(signed_val(xi[pos[k2]], sign), k2, vk, k)) {
-            const unsigned char s2 = stt[k2];
-            any_keep |= (s2 == 1);
-            any_open |= (s2 == 0);
+        for (int k2 = k - 1; k2 >= 0 && pk - s_pos[k2] < di; --k2) {
+          const double v2 = s_val[k2];
+          if (v2 > vk) {                                   // equal heights: the later index wins
+            const unsigned char s2 = s_st[k2];
+            any_keep |= (s2 == 1); any_open |= (s2 == 0);
           }
         }
-        for (int64_t k2 = k + 1; k2 < ke && pos[k2] - pk < d; ++k2) {
-          if (higher_priority(signed_val(xi[pos[k2]], sign), k2, vk, k)) {
-            const unsigned char s2 = stt[k2];
-            any_keep |= (s2 == 1);
-            any_open |= (s2 == 0);
+        for (int k2 = k + 1; k2 < L && s_pos[k2] - pk < di; ++k2) {
+          const double v2 = s_val[k2];
+          if (v2 >= vk) {
+            const unsigned char s2 = s_st[k2];
+            any_keep |= (s2 == 1); any_open |= (s2 == 0);
           }
         }
-        if (any_keep) { stt[k] = 2; changed = 1; }
-        else if (!any_open) { stt[k] = 1; changed = 1; }
+        if (any_keep) { s_st[k] = 2; changed = 1; }
+        else if (!any_open) { s_st[k] = 1; changed = 1; }
       }
       if (!__syncthreads_or(changed)) break;
     }
-  } else {
-    for (int64_t k = ks + threadIdx.x; k < ke; k += DP_THREADS) stt[k] = 1;
-    __syncthreads();
+    for (int t = threadIdx.x; t < L; t += DP_THREADS) st_out[ks + t] = (s_st[t] == 1) ? 1 : 0;
+    return;
   }
 
-  if (prominence != nullptr) {
-    const double thr = prominence[item];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int64_t k = ks + warp; k < ke; k += DP_THREADS / 32) {
-      if (stt[k] != 1) continue;                       // warp-uniform
-      const bool ok = warp_prominence_ok(xi, sign, it.m, pos[k], thr);
-      if (lane == 0 && !ok) stt[k] = 2;
-    }
-  }
+  // oversized cluster run: same fix-point straight on global memory
+  volatile unsigned char* stt = st_out;
+  for (int64_t k = ks + threadIdx.x; k < ke; k += DP_THREADS) stt[k] = 0;
   __syncthreads();
-  // normalise to 0/1 flags
+  while (true) {
+    int changed = 0;
+    for (int64_t k = ks + threadIdx.x; k < ke; k += DP_THREADS) {
+      if (stt[k] != 0) continue;
+      const int64_t pk = pos[k];
+      const double vk = signed_val(xi[pk], sign);
+      bool any_keep = false, any_open = false;
+      for (int64_t k2 = k - 1; k2 >= ks && pk - pos[k2] < d; --k2) {
+        if (higher_priority(signed_val(xi[pos[k2]], sign), k2, vk, k)) {
+          const unsigned char s2 = stt[k2];
+          any_keep |= (s2 == 1); any_open |= (s2 == 0);
+        }
+      }
+      for (int64_t k2 = k + 1; k2 < ke && pos[k2] - pk < d; ++k2) {
+        if (higher_priority(signed_val(xi[pos[k2]], sign), k2, vk, k)) {
+          const unsigned char s2 = stt[k2];
+          any_keep |= (s2 == 1); any_open |= (s2 == 0);
+        }
+      }
+      if (any_keep) { stt[k] = 2; changed = 1; }
+      else if (!any_open) { stt[k] = 1; changed = 1; }
+    }
+    if (!__syncthreads_or(changed)) break;
+  }
   for (int64_t k = ks + threadIdx.x; k < ke; k += DP_THREADS) stt[k] = (stt[k] == 1) ? 1 : 0;
-  (void)tile_counts;
-  (void)s_cnt;
+}
+
+// Prominence rule on the survivors of the distance rule: one warp per candidate, grid-stride.
+constexpr int PR_THREADS = 256;
+constexpr int PR_BLOCKS = 148 * 4;
+
+__global__ void __launch_bounds__(PR_THREADS) k_prominence(const double* __restrict__ x, int sign,
+                                                           const BpmItem* __restrict__ items,
+                                                           const int64_t* __restrict__ cand,
+                                                           const int64_t* __restrict__ cand_count,
+                                                           const double* __restrict__ prominence,
+                                                           unsigned char* __restrict__ state) {
+  const int item = blockIdx.y;
+  const BpmItem it = items[item];
+  const int64_t nc = cand_count[item];
+  const double thr = prominence[item];
+  const int64_t* __restrict__ pos = cand + it.m_off;
+  const double* __restrict__ xi = x + it.m_off;
+  unsigned char* stt = state + it.m_off;
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = static_cast<int64_t>(gridDim.x) * (PR_THREADS / 32);
+  for (int64_t k = static_cast<int64_t>(blockIdx.x) * (PR_THREADS / 32) + (threadIdx.x >> 5); k < nc; k += warps) {
+    if (stt[k] != 1) continue;                            // warp-uniform
+    const bool ok = warp_prominence_ok(xi, sign, it.m, pos[k], thr);
+    if (lane == 0 && !ok) stt[k] = 0;
+  }
 }
 
 // counts of set flags per PK_TILE of a (device-length) domain
@@ -345,10 +407,18 @@ int find_peaks_run(const double* x, int sign, const double* height, const double
   BPM_TRY(compact_run(b.flags, nullptr, items, sh, nullptr, sh.max_m, true, b.tile_counts, b.cand, b.cand_count, st));
   // a local maximum needs a lower neighbour on both sides: at most (m-1)/2 candidates
   const int64_t max_c = sh.max_m / 2 + 1;
-  BPM_KERNEL(k_distance_prom);
-  k_distance_prom<<<dim3(cdiv(max_c, DP_TILE), sh.n_items), DP_THREADS, 0, st>>>(
-      x, sign, items, b.cand, b.cand_count, distance, prominence, b.cstate, b.tile_counts);
+  BPM_KERNEL(k_distance);
+  k_distance<<<dim3(cdiv(max_c, DP_TILE), sh.n_items), DP_THREADS, 0, st>>>(x, sign, items, b.cand, b.cand_count,
+                                                                           distance, b.cstate);
   BPM_LAUNCH_OK();
+  if (prominence != nullptr) {
+    const int64_t want = (max_c + PR_THREADS / 32 - 1) / (PR_THREADS / 32);
+    const unsigned gx = static_cast<unsigned>(want < PR_BLOCKS ? (want > 0 ? want : 1) : PR_BLOCKS);
+    BPM_KERNEL(k_prominence);
+    k_prominence<<<dim3(gx, sh.n_items), PR_THREADS, 0, st>>>(x, sign, items, b.cand, b.cand_count, prominence,
+                                                              b.cstate);
+    BPM_LAUNCH_OK();
+  }
   BPM_TRY(compact_run(b.cstate, b.cand, items, sh, b.cand_count, max_c, false, b.tile_counts, out_idx, out_count, st));
   return BPM_OK;
 }

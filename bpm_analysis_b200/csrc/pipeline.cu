@@ -230,6 +230,15 @@ const char* bpm_error_string(int code) {
 
 int64_t bpm_launch_count(void) { return g_launches; }
 
+#ifdef BPM_DEBUG_COUNTERS
+int bpm_debug_counters(unsigned long long* out_host, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out_host, g_dbg, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_dbg, z, sizeof(z)); }
+  return 0;
+}
+#endif
+
 int bpm_profile_begin(void* stream) {
   g_prof_used = 0;
   g_prof_marks.clear();
@@ -271,8 +280,8 @@ int bpm_frontend(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
   Workspace ws(workspace, workspace_bytes);
   // block is passed implicitly: design_words = header + 4 * (2 * block + 1)
   const int64_t rem = design_words - BPM_DESIGN_HEADER_WORDS;
-  if (rem < 12 || (rem - 4) % 8 != 0) return BPM_ERR_ARG;
-  const int block = static_cast<int>((rem - 4) / 8);
+  if (rem < 28 || (rem - 12) % 16 != 0) return BPM_ERR_ARG;
+  const int block = static_cast<int>((rem - 12) / 16);
   return frontend_run(pcm, pcm_dtype, channels, items, items_host, n_items, stride, design, design_words, block,
                       env_window, filtered, envelope, absmax, ws, static_cast<cudaStream_t>(stream));
 }

@@ -125,9 +125,12 @@ class BlockFilterDesign:
     def packed(self) -> np.ndarray:
         """Flat float64 image in the layout ``BpmFilterDesign`` (include/bpm_b200.h) reads."""
         head = np.array([float(self.block), float(self.lookback_tiles), self.D, 0.0])
+        # wq8[l] = (wf[l] | q[l]) interleaved, wf padded with a zero row: the image the
+        # full-rate contraction kernel copies into constant memory
+        wq8 = np.concatenate([np.vstack([self.wf, np.zeros((1, 4))]), self.q], axis=1)
         return np.concatenate([head, self.sos.ravel(), self.zi, self.C, self.Ad.ravel(),
                                self.P.ravel(), self.pow_chunk.ravel(),
-                               self.wf.ravel(), self.q.ravel()]).astype(np.float64)
+                               self.wf.ravel(), self.q.ravel(), wq8.ravel()]).astype(np.float64)
 
 
 def _matpow(M, e: int):

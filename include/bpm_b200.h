@@ -58,8 +58,10 @@ typedef struct {
  *   [0] block  [1] lookback_tiles  [2] D  [3] reserved
  *   [4..16)  sos[2][6]      [16..20) zi[4]      [20..24) C[4]
  *   [24..40) Ad[4][4]       [40..56) P[4][4]    [56..312) pow_chunk[16][4][4]
- *   [312 .. 312+4*block)            wf[block][4]
- *   [312+4*block .. 312+4*(2*block+1)) q[block+1][4]                              */
+ *   [312 .. 312+4*block)               wf[block][4]
+ *   [312+4*block .. 312+4*(2*block+1))  q[block+1][4]
+ *   [312+4*(2*block+1) .. +8*(block+1)) wq8[block+1][8] = (wf[l] | q[l]), wf[block] = 0
+ * total words = 312 + 16*block + 12                                               */
 #define BPM_DESIGN_HEADER_WORDS 312
 
 int bpm_abi_version(void);

@@ -82,10 +82,12 @@ def test_blocked_model_fullrate_matches_sosfiltfilt():
 def test_design_image_layout():
     d = design.design_block_filter(0.1, 0.9, 7)
     img = d.packed()
-    assert img.shape[0] == _native.DESIGN_HEADER_WORDS + 4 * (2 * 7 + 1)
+    assert img.shape[0] == _native.DESIGN_HEADER_WORDS + 16 * 7 + 12
     assert img[0] == 7 and img[2] == d.D
     assert np.array_equal(img[24:40].reshape(4, 4), d.Ad)
     assert np.array_equal(img[312:312 + 28].reshape(7, 4), d.wf)
+    wq8 = img[312 + 4 * 15:].reshape(8, 8)
+    assert np.array_equal(wq8[:7, :4], d.wf) and np.all(wq8[7, :4] == 0) and np.array_equal(wq8[:, 4:], d.q)
 
 
 def test_decimation_plan_matches_reference_arithmetic():
