@@ -672,14 +672,14 @@ __global__ void __launch_bounds__(RF_THREADS) k_rolling_floor(
 // A CTA owns RB_THREADS * run consecutive outputs.  It materialises the interpolated samples its
 // windows touch (n = outputs + window - 1 <= RB_NCAP) in shared memory and SORTS them by value
 // (sample sort: RB_G - 1 splitters from a sorted strided sample, counting sort into buckets,
-// insertion sort inside each small bucket), keeping perm[] (sorted order -> sample index) and
+// then each sample counts the members of its small bucket that precede it), keeping perm[] (sorted order -> sample index) and
 // rank[] (sample index -> sorted position).  A coarse 2-D prefix table over (index chunk, rank
 // band) lets every thread place its first window's order statistic in O(log) steps.  After that
 // a thread slides over its run with a pointer p into the sorted order: the entering / leaving
 // sample changes the number of in-window entries before p by at most one each, and p walks a few
 // entries to the new order statistic.  Uniform O(1) work per output, all in shared memory, and
 // exact: the samples are the float64 np.interp values.
-constexpr int RB_THREADS = 128;
+constexpr int RB_THREADS = 256;
 constexpr int RB_NCAP = 6656;          // samples a CTA can stage
 constexpr int RB_G = 1024;             // sort buckets (RB_G - 1 splitters)
 constexpr int RB_NSUP = 32;            // rank bands of the coarse table
@@ -793,7 +793,7 @@ __global__ void __launch_bounds__(RB_THREADS) k_rolling_floor_blk(
   }
   __syncthreads();
   // ---- S3: exclusive scan of the histogram -> start[], scatter (hist becomes the cursor),
-  //          insertion sort inside every bucket, inverse permutation
+  //          order inside every bucket, inverse permutation
   {
     constexpr int PER = RB_G / RB_THREADS;
     unsigned int loc[PER];
@@ -816,19 +816,31 @@ __global__ void __launch_bounds__(RB_THREADS) k_rolling_floor_blk(
     sh.perm[pos] = static_cast<unsigned short>(j);
   }
   __syncthreads();
-  for (int g = tid; g < RB_G; g += RB_THREADS) {
-    const int e0 = sh.start[g], e1 = sh.start[g + 1];
-    for (int e = e0 + 1; e < e1; ++e) {
-      const unsigned short pj = sh.perm[e];
-      const double x = sh.d[pj];
-      int f = e - 1;
-      while (f >= e0 && sh.d[sh.perm[f]] > x) { sh.perm[f + 1] = sh.perm[f]; --f; }
-      sh.perm[f + 1] = pj;
+  // order inside the buckets by counting (load-balanced over samples, not buckets):
+  // final position = bucket start + #{bucket members that sort before this sample}
+  {
+    constexpr int MAXPER = (RB_NCAP + RB_THREADS - 1) / RB_THREADS;
+    unsigned short fin[MAXPER];
+#pragma unroll 1
+    for (int u2 = 0, j = tid; j < n; j += RB_THREADS, ++u2) {
+      const int g = sh.rank[j];
+      const int e0 = sh.start[g], e1 = sh.start[g + 1];
+      const double x = sh.d[j];
+      int before = 0;
+      for (int e = e0; e < e1; ++e) {
+        const int y = sh.perm[e];
+        const double dy = sh.d[y];
+        before += (dy < x || (dy == x && y < j)) ? 1 : 0;
+      }
+      fin[u2] = static_cast<unsigned short>(e0 + before);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int u2 = 0, j = tid; j < n; j += RB_THREADS, ++u2) {
+      sh.rank[j] = fin[u2];
+      sh.perm[fin[u2]] = static_cast<unsigned short>(j);
     }
   }
-  __syncthreads();
-  for (int e = tid; e < n; e += RB_THREADS) sh.rank[sh.perm[e]] = static_cast<unsigned short>(e);
-
   // ---- S4: coarse table over (index chunk, rank band)
   int ch = run > 32 ? run : 32;
   while ((n + ch - 1) / ch > RB_MAXCH) ch *= 2;
