@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--sample-rate", type=int, default=48000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--dump-kernels", default=None, help="write the per-kernel table to this JSON file")
     return ap.parse_args()
 
@@ -149,6 +150,8 @@ def algorithmic_bytes(kernel: str, shp: dict) -> float:
         "k_count_flags": max(T, P),
         "k_knot_table": 40 * T,
         "k_rolling_floor": 16 * T + 8 * M,             # SURVEY §8(d) K5+K6
+        "k_rolling_floor_blk": 16 * T + 8 * M,
+        "k_find_peaks_small": 16 * B,
         "k_sanitize_flags": 24 * T,
         "k_peak_strength": 32 * P, "k_peak_deviation": 16 * P, "k_dev_smooth": 16 * P,
         "k_bpm_instant": 32 * B, "k_bpm_smooth": 24 * B, "k_steepest": 16 * B, "k_hrv": 8 * B + 32 * (B // 5),
@@ -264,7 +267,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     from bpm_analysis_b200 import _native, synth
-    from bpm_analysis_b200.runtime import BeatRunner, StageARunner, profile_kernels
+    from bpm_analysis_b200.runtime import BeatRunner, GraphedStep, StageARunner, profile_kernels
 
     lib = _native.load_library()
     params = bench_params(args)
@@ -280,9 +283,12 @@ def run_b200(args):
     torch.cuda.synchronize()
     audio_hours = args.duration_sec / 3600.0
 
-    def step():
+    def step_eager():
         A.launch()
         Bn.launch()
+
+    graphed = None if args.no_graph else GraphedStep(A, Bn)
+    step = step_eager if graphed is None else graphed.launch
 
     def barrier():
         torch.cuda.synchronize()
@@ -296,6 +302,12 @@ def run_b200(args):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    # kernels per step (counted on an eager step; a graph replay launches the same kernels)
+    l_before = lib.bpm_launch_count()
+    step_eager()
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.bpm_launch_count() - l_before)
 
     # ---- device-resident timing
     for _ in range(args.warmup):
@@ -324,8 +336,7 @@ def run_b200(args):
     def e2e_step():
         A.upload_pinned(pcm_pin)
         Bn.upload(beats_pin)
-        A.launch()
-        Bn.launch()
+        step()
         for k in ("trough_count", "peak_count"):
             host[k].copy_(A.out[k], non_blocking=True)
         for k in ("n_tops", "n_bottoms", "hrv_rows", "slopes", "n_valid"):
@@ -364,7 +375,7 @@ def run_b200(args):
     # ---- per-kernel event timing (separate pass: events between launches perturb the step)
     roofline, kernels = None, {}
     if not args.no_profile:
-        prof = profile_kernels(lambda: [step() for _ in range(args.steps)])
+        prof = profile_kernels(lambda: [step_eager() for _ in range(args.steps)])
         torch.cuda.synchronize()
         shp = {"N": len(pcm), "M": M, "T": nt, "P": npk, "B": len(beat_idx)}
         peak, peak_src = measured_peak_gbs()
@@ -410,7 +421,8 @@ def run_b200(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h)},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
+                "gpu_launches": launches if graphed is None else launches_per_step * args.steps,
+                "launch_mode": "eager" if graphed is None else "cuda-graph replay", "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -16,6 +16,7 @@
 //   k_scan<BWD>    s_b[j] = Ad s_b[j+1] + P s_f[j] + ub0[j];  y[j] = C s_b[j] + D y_f[j]
 //   k_envelope     |y| -> centred rolling mean (pandas FixedWindowIndexer semantics).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace bpm {
 
@@ -189,9 +190,6 @@ __global__ void __launch_bounds__(256) k_contract_generic(PcmView pcm, const Bpm
 //   * the first / last CTA of a recording (odd-extension samples) read global memory directly.
 // 8 DFMA per input sample: at 64 FP64 lanes per SM that is about the time HBM needs to
 // deliver the 2 bytes, so the kernel sits where the FP64 and HBM rooflines meet.
-constexpr int CT_THREADS = 64;
-constexpr int CT_J = 2;
-constexpr int CT_BLOCKS = CT_THREADS * CT_J;   // kept samples per CTA
 constexpr int CW_MAX_BLOCK = 767;              // weight image limit: 8*(block+1) doubles of constant memory
 
 __constant__ double c_contract_w[8 * (CW_MAX_BLOCK + 1)];
@@ -200,133 +198,194 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// int16 -> float64 without the (slow) I2F.F64 conversion: 2^52 + 2^31 + x assembled from bits,
+// then one DADD
+__device__ __forceinline__ double i16_to_f64(int x) {
+  return __hiloint2double(0x43300000, x ^ 0x80000000) - 4503601774854144.0;
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_TMA:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_TMA;\n"
+      "bra WAIT_TMA;\n"
+      "DONE_TMA:\n"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+// one elected thread: arm the barrier with the byte count and start the bulk copy global -> shared
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// Persistent: a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... of its recording with a
+// two-stage TMA pipeline (the copy of tile k+2 is issued as soon as tile k's buffer is free), so
+// the FP64 pipe never waits for HBM after the first tile.
+template <int CT_THREADS, int CT_J>
 __global__ void __launch_bounds__(CT_THREADS) k_contract_i16(const int16_t* __restrict__ pcm,
                                                              const BpmItem* __restrict__ items,
                                                              const double* __restrict__ design,
                                                              double* __restrict__ uf, double* __restrict__ ub0,
-                                                             double* __restrict__ xe) {
+                                                             double* __restrict__ xe, int stage_bytes) {
+  constexpr int CT_BLOCKS = CT_THREADS * CT_J;             // kept samples per tile
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ __align__(8) unsigned long long s_bar[2];
   const BpmItem it = items[blockIdx.y];
-  const int64_t j0 = static_cast<int64_t>(blockIdx.x) * CT_BLOCKS;
-  if (j0 >= it.m) return;
   const DesignView d{design};
   const int blk = d.block();
   const int64_t n = it.n_in;                               // stride 1: n_dec == n_in
-  const int nb = static_cast<int>(min(static_cast<int64_t>(CT_BLOCKS), it.m - j0));
-  const int span = nb * blk + 1;                           // samples E_j0 .. E_j0 + nb*blk
-  const int64_t i0 = j0 * blk;                              // data index of the first staged sample
+  const int64_t num_tiles = (it.m + CT_BLOCKS - 1) / CT_BLOCKS;
   const int16_t* __restrict__ src = pcm + it.in_off;
-  const bool interior = (i0 >= 8) && (i0 + span + 8 <= n);
-  int head = 0;
-  if (interior) {
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(src + i0);
-    head = static_cast<int>((addr & 15) >> 1);             // samples before i0 in its 16-byte word
-    const uint32_t bytes = static_cast<uint32_t>(((head + span + 7) >> 3) << 4);
-    const uint32_t bar = smem_u32(&s_bar);
-    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-      asm volatile(
-          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-              smem_u32(smem_raw)),
-          "l"(src + i0 - head), "r"(bytes), "r"(bar)
-          : "memory");
-    }
-    __syncthreads();                                       // barrier initialised before anyone polls it
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_TMA:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
-        "@p bra DONE_TMA;\n"
-        "bra WAIT_TMA;\n"
-        "DONE_TMA:\n"
-        "}" ::"r"(bar)
-        : "memory");
-  }
   const int tid = threadIdx.x;
-  double acc[CT_J][8];
+  const uint32_t bar0 = smem_u32(&s_bar[0]), bar1 = smem_u32(&s_bar[1]);
+
+  // geometry of a tile: first staged data index, samples, whether TMA can fetch it whole
+  auto tile_geom = [&](int64_t tile, int64_t& i0, int& nb, int& span, bool& interior) {
+    const int64_t j0 = tile * CT_BLOCKS;
+    nb = static_cast<int>(min(static_cast<int64_t>(CT_BLOCKS), it.m - j0));
+    span = nb * blk + 1;                                   // samples E_j0 .. E_j0 + nb*blk
+    i0 = j0 * blk;
+    interior = (i0 >= 8) && (i0 + span + 8 <= n);
+  };
+  auto issue = [&](int64_t tile, int stage) {              // thread 0 only
+    int64_t i0; int nb, span; bool interior;
+    tile_geom(tile, i0, nb, span, interior);
+    if (!interior) return;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(src + i0);
+    const int head = static_cast<int>((addr & 15) >> 1);
+    const uint32_t bytes = static_cast<uint32_t>(((head + span + 7) >> 3) << 4);
+    tma_load_1d(smem_u32(smem_raw + static_cast<size_t>(stage) * stage_bytes), src + i0 - head, bytes,
+                stage ? bar1 : bar0);
+  };
+
+  if (tid == 0) {
+    mbar_init(bar0);
+    mbar_init(bar1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (blockIdx.x < num_tiles) issue(blockIdx.x, 0);
+    if (blockIdx.x + gridDim.x < num_tiles) issue(blockIdx.x + gridDim.x, 1);
+  }
+  __syncthreads();                                         // barriers initialised before anyone polls
+
+  uint32_t uses0 = 0, uses1 = 0;                           // completed TMA uses per stage -> wait parity
+  int k = 0;
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++k) {
+    const int stage = k & 1;
+    int64_t i0; int nb, span; bool interior;
+    tile_geom(tile, i0, nb, span, interior);
+    const int64_t j0 = tile * CT_BLOCKS;
+    double acc[CT_J][8];
 #pragma unroll
-  for (int jj = 0; jj < CT_J; ++jj)
+    for (int jj = 0; jj < CT_J; ++jj)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[jj][c] = 0.0;
-  double x0[CT_J];
-  if (interior) {
-    const int16_t* __restrict__ xs = reinterpret_cast<const int16_t*>(smem_raw) + head + tid * blk;
-    const int jstride = CT_THREADS * blk;
-    // blocks beyond nb (last CTA only) read staged-but-unused or stale shared memory; their
-    // results are discarded below, the reads stay inside the allocation
+      for (int c = 0; c < 8; ++c) acc[jj][c] = 0.0;
+    double x0[CT_J];
+    if (interior) {
+      if (stage) { mbar_wait(bar1, uses1 & 1); ++uses1; } else { mbar_wait(bar0, uses0 & 1); ++uses0; }
+      const uintptr_t addr = reinterpret_cast<uintptr_t>(src + i0);
+      const int head = static_cast<int>((addr & 15) >> 1);
+      const int16_t* __restrict__ xs =
+          reinterpret_cast<const int16_t*>(smem_raw + static_cast<size_t>(stage) * stage_bytes) + head + tid * blk;
+      const int jstride = CT_THREADS * blk;
+      // blocks beyond nb (last tile only) read staged-but-unused or stale shared memory; their
+      // results are discarded below, the reads stay inside the stage buffer
 #pragma unroll
-    for (int jj = 0; jj < CT_J; ++jj) x0[jj] = static_cast<double>(xs[jj * jstride]);
-#pragma unroll 2
-    for (int l = 0; l <= blk; ++l) {
-      double v[CT_J];
+      for (int jj = 0; jj < CT_J; ++jj) x0[jj] = static_cast<double>(xs[jj * jstride]);
+#pragma unroll 4
+      for (int l = 0; l <= blk; ++l) {
+        double v[CT_J];
 #pragma unroll
-      for (int jj = 0; jj < CT_J; ++jj) v[jj] = static_cast<double>(xs[jj * jstride + l]);
+        for (int jj = 0; jj < CT_J; ++jj) v[jj] = i16_to_f64(xs[jj * jstride + l]);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const double w = c_contract_w[8 * l + c];
+        for (int c = 0; c < 8; ++c) {
+          const double w = c_contract_w[8 * l + c];
 #pragma unroll
-        for (int jj = 0; jj < CT_J; ++jj) acc[jj][c] += w * v[jj];
+          for (int jj = 0; jj < CT_J; ++jj) acc[jj][c] += w * v[jj];
+        }
+      }
+    } else {
+      PcmView pv{pcm, BPM_PCM_I16, 1};
+      const ExtSignal x = make_ext(pv, it, 1);
+#pragma unroll
+      for (int jj = 0; jj < CT_J; ++jj) {
+        const int jl = jj * CT_THREADS + tid;
+        x0[jj] = 0.0;
+        if (jl >= nb) continue;
+        const int64_t E = PADLEN + (j0 + jl) * blk;
+        x0[jj] = x.at(E);
+        if (j0 + jl >= it.m - 1) continue;
+        for (int l = 0; l <= blk; ++l) {
+          const double v = x.at(E + l);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[jj][c] += c_contract_w[8 * l + c] * v;
+        }
       }
     }
-  } else {
-    PcmView pv{pcm, BPM_PCM_I16, 1};
-    const ExtSignal x = make_ext(pv, it, 1);
+    __syncthreads();                                       // everyone is done with this stage's buffer
+    if (tid == 0 && tile + 2 * static_cast<int64_t>(gridDim.x) < num_tiles)
+      issue(tile + 2 * static_cast<int64_t>(gridDim.x), stage);
 #pragma unroll
     for (int jj = 0; jj < CT_J; ++jj) {
       const int jl = jj * CT_THREADS + tid;
-      x0[jj] = 0.0;
       if (jl >= nb) continue;
-      const int64_t E = PADLEN + (j0 + jl) * blk;
-      x0[jj] = x.at(E);
-      if (j0 + jl >= it.m - 1) continue;
-      for (int l = 0; l <= blk; ++l) {
-        const double v = x.at(E + l);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[jj][c] += c_contract_w[8 * l + c] * v;
-      }
+      const int64_t j = j0 + jl;
+      xe[it.m_off + j] = x0[jj];
+      if (j >= it.m - 1) continue;
+      double2* pf = reinterpret_cast<double2*>(uf + 4 * (it.m_off + j));
+      double2* pb = reinterpret_cast<double2*>(ub0 + 4 * (it.m_off + j));
+      pf[0] = make_double2(acc[jj][0], acc[jj][1]);
+      pf[1] = make_double2(acc[jj][2], acc[jj][3]);
+      pb[0] = make_double2(acc[jj][4], acc[jj][5]);
+      pb[1] = make_double2(acc[jj][6], acc[jj][7]);
     }
-  }
-#pragma unroll
-  for (int jj = 0; jj < CT_J; ++jj) {
-    const int jl = jj * CT_THREADS + tid;
-    if (jl >= nb) continue;
-    const int64_t j = j0 + jl;
-    xe[it.m_off + j] = x0[jj];
-    if (j >= it.m - 1) continue;
-    double2* pf = reinterpret_cast<double2*>(uf + 4 * (it.m_off + j));
-    double2* pb = reinterpret_cast<double2*>(ub0 + 4 * (it.m_off + j));
-    pf[0] = make_double2(acc[jj][0], acc[jj][1]);
-    pf[1] = make_double2(acc[jj][2], acc[jj][3]);
-    pb[0] = make_double2(acc[jj][4], acc[jj][5]);
-    pb[1] = make_double2(acc[jj][6], acc[jj][7]);
   }
 }
 
 // ------------------------------------------------------------------ init / tail
-__global__ void k_filter_init(PcmView pcm, const BpmItem* __restrict__ items, int n_items, int64_t stride,
-                              const double* __restrict__ design, double* __restrict__ s0) {
-  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per recording: the lanes fetch the (strided, possibly reflected) samples with
+// independent loads into shared memory, then lane 0 runs the short serial recurrence from there.
+constexpr int FE_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * FE_WARPS) k_filter_init(PcmView pcm, const BpmItem* __restrict__ items,
+                                                              int n_items, int64_t stride,
+                                                              const double* __restrict__ design,
+                                                              double* __restrict__ s0) {
+  __shared__ double s_x[FE_WARPS][PADLEN + 1];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * FE_WARPS + w;
   if (item >= n_items) return;
   const BpmItem it = items[item];
   const DesignView d{design};
   const ExtSignal x = make_ext(pcm, it, stride);
+  if (lane < PADLEN) s_x[w][lane] = x.at(lane);
+  __syncwarp();
+  if (lane != 0) return;
   double s[4];
-  const double x0 = x.at(0);
+  const double x0 = s_x[w][0];
 #pragma unroll
   for (int c = 0; c < 4; ++c) s[c] = d.zi()[c] * x0;
-  for (int e = 0; e < PADLEN; ++e) df2t_step(d.sos(), s, x.at(e));
+  for (int e = 0; e < PADLEN; ++e) df2t_step(d.sos(), s, s_x[w][e]);
 #pragma unroll
   for (int c = 0; c < 4; ++c) s0[4 * item + c] = s[c];
 }
 
-__global__ void k_filter_tail(PcmView pcm, const BpmItem* __restrict__ items, int n_items, int64_t stride,
-                              const double* __restrict__ design, const double* __restrict__ sf,
-                              double* __restrict__ tail_buf, int tail_cap, double* __restrict__ sb_last) {
-  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32 * FE_WARPS) k_filter_tail(PcmView pcm, const BpmItem* __restrict__ items,
+                                                              int n_items, int64_t stride,
+                                                              const double* __restrict__ design,
+                                                              const double* __restrict__ sf, int tail_cap,
+                                                              double* __restrict__ sb_last) {
+  extern __shared__ double s_tail[];                       // [FE_WARPS][tail_cap]
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * FE_WARPS + w;
   if (item >= n_items) return;
   const BpmItem it = items[item];
   const DesignView d{design};
@@ -335,11 +394,14 @@ __global__ void k_filter_tail(PcmView pcm, const BpmItem* __restrict__ items, in
   const int64_t le = x.n_dec + 2 * PADLEN;
   const int64_t e_last = PADLEN + (it.m - 1) * blk;
   const int lt = static_cast<int>(le - e_last);
-  double* yf = tail_buf + static_cast<size_t>(item) * tail_cap;
+  double* yf = s_tail + static_cast<size_t>(w) * tail_cap;
+  for (int k = lane; k < lt; k += 32) yf[k] = x.at(e_last + k);
+  __syncwarp();
+  if (lane != 0) return;
   double s[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) s[c] = sf[4 * (it.m_off + it.m - 1) + c];
-  for (int k = 0; k < lt; ++k) yf[k] = df2t_step(d.sos(), s, x.at(e_last + k));
+  for (int k = 0; k < lt; ++k) yf[k] = df2t_step(d.sos(), s, yf[k]);
   const double ylast = yf[lt - 1];
 #pragma unroll
   for (int c = 0; c < 4; ++c) s[c] = d.zi()[c] * ylast;
@@ -598,7 +660,7 @@ static int carve_frontend(Workspace& ws, int64_t total_m, int n_items, int block
 }
 
 // worst-case block for workspace sizing (the tail scratch is the only part that depends on it)
-constexpr int MAX_BLOCK = 8192;
+constexpr int MAX_BLOCK = 4096;
 
 size_t frontend_workspace_bytes(int64_t total_m, int n_items) {
   Workspace ws(nullptr, 0);
@@ -629,22 +691,51 @@ int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
   const bool fast = (pcm_dtype == BPM_PCM_I16 && channels == 1 && stride == 1 && block >= 8 &&
                      block <= CW_MAX_BLOCK && (reinterpret_cast<uintptr_t>(pcm) & 1) == 0);
   if (fast) {
-    // PCM span of a CTA, rounded up to whole 16-byte words on both sides
-    const size_t smem = 2 * (static_cast<size_t>(CT_BLOCKS) * block + 1 + 16) + 32;
     if (cudaMemcpyToSymbolAsync(c_contract_w, design + BPM_DESIGN_HEADER_WORDS + 4 * (2 * block + 1),
                                 sizeof(double) * 8 * (block + 1), 0, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
       return BPM_ERR_CUDA;
-    cudaFuncSetAttribute(k_contract_i16, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    // tile shape: small CTAs for long blocks (more resident warps per SM measured fastest),
+    // wide CTAs for short blocks (keeps each bulk copy above a few KB)
+    static const int forced = getenv("BPM_CONTRACT_VARIANT") ? atoi(getenv("BPM_CONTRACT_VARIANT")) : -1;
+    const int variant = forced >= 0 ? forced : (block >= 96 ? 8 : 2);
     BPM_KERNEL(k_contract_i16);
-    k_contract_i16<<<dim3(cdiv(sh.max_m, CT_BLOCKS), n_items), CT_THREADS, smem, st>>>(
-        static_cast<const int16_t*>(pcm), items, design, b.uf, b.ub0, b.xe);
+    // PCM span of a CTA (threads * J blocks), rounded up to whole 16-byte words on both sides
+#define BPM_LAUNCH_CONTRACT(T, J, CTAS_PER_SM)                                                           \
+    do {                                                                                                 \
+      const size_t stage = ((2 * (static_cast<size_t>(T) * J * block + 1 + 16) + 32) + 127) & ~size_t(127); \
+      const int64_t tiles = (sh.max_m + T * J - 1) / (T * J);                                            \
+      int64_t gx = tiles;                                                                                \
+      size_t smem = stage;                    /* CTAS_PER_SM == 0: one tile per CTA, single buffer */    \
+      if (CTAS_PER_SM > 0) {                                                                             \
+        gx = (static_cast<int64_t>(148) * CTAS_PER_SM + n_items - 1) / n_items;                          \
+        if (gx > tiles) gx = tiles;                                                                      \
+        smem = 2 * stage;                                                                                \
+      }                                                                                                  \
+      if (gx < 1) gx = 1;                                                                                \
+      cudaFuncSetAttribute(k_contract_i16<T, J>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                           static_cast<int>(smem));                                                      \
+      k_contract_i16<T, J><<<dim3(static_cast<unsigned>(gx), n_items), T, smem, st>>>(                   \
+          static_cast<const int16_t*>(pcm), items, design, b.uf, b.ub0, b.xe, static_cast<int>(stage));  \
+    } while (0)
+    switch (variant) {
+      case 0: BPM_LAUNCH_CONTRACT(64, 2, 0); break;
+      case 2: BPM_LAUNCH_CONTRACT(128, 2, 0); break;
+      case 3: BPM_LAUNCH_CONTRACT(64, 1, 0); break;
+      case 4: BPM_LAUNCH_CONTRACT(64, 4, 0); break;
+      case 5: BPM_LAUNCH_CONTRACT(32, 4, 0); break;
+      case 6: BPM_LAUNCH_CONTRACT(32, 4, 3); break;
+      case 7: BPM_LAUNCH_CONTRACT(128, 2, 1); break;
+      case 8: BPM_LAUNCH_CONTRACT(32, 2, 0); break;
+      default: BPM_LAUNCH_CONTRACT(128, 1, 0); break;
+    }
+#undef BPM_LAUNCH_CONTRACT
   } else {
     BPM_KERNEL(k_contract_generic);
     k_contract_generic<<<dim3(cdiv(sh.max_m, 256), n_items), 256, 0, st>>>(pv, items, stride, design, b.uf, b.ub0, b.xe);
   }
   BPM_LAUNCH_OK();
   BPM_KERNEL(k_filter_init);
-  k_filter_init<<<cdiv(n_items, 64), 64, 0, st>>>(pv, items, n_items, stride, design, b.s0);
+  k_filter_init<<<cdiv(n_items, FE_WARPS), 32 * FE_WARPS, 0, st>>>(pv, items, n_items, stride, design, b.s0);
   BPM_LAUNCH_OK();
 
   const dim3 sgrid(cdiv(sh.max_m > 1 ? sh.max_m - 1 : 1, SCAN_TILE), n_items);
@@ -658,8 +749,13 @@ int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
   BPM_KERNEL(k_scan);
   k_scan<0, true><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
   BPM_LAUNCH_OK();
-  BPM_KERNEL(k_filter_tail);
-  k_filter_tail<<<cdiv(n_items, 32), 32, 0, st>>>(pv, items, n_items, stride, design, b.sf, b.tail, b.tail_cap, b.sb_last);
+  {
+    const size_t smem = sizeof(double) * FE_WARPS * b.tail_cap;
+    cudaFuncSetAttribute(k_filter_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    BPM_KERNEL(k_filter_tail);
+    k_filter_tail<<<cdiv(n_items, FE_WARPS), 32 * FE_WARPS, smem, st>>>(pv, items, n_items, stride, design, b.sf,
+                                                                        b.tail_cap, b.sb_last);
+  }
   BPM_LAUNCH_OK();
   sp.u = b.ub0;
   sp.s_init = b.sb_last;

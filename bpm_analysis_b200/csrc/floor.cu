@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(RF_THREADS) k_rolling_floor(
 // entries to the new order statistic.  Uniform O(1) work per output, all in shared memory, and
 // exact: the samples are the float64 np.interp values.
 constexpr int RB_THREADS = 256;
-constexpr int RB_NCAP = 6656;          // samples a CTA can stage
+constexpr int RB_NCAP = 6144;          // samples a CTA can stage
 constexpr int RB_G = 1024;             // sort buckets (RB_G - 1 splitters)
 constexpr int RB_NSUP = 32;            // rank bands of the coarse table
 constexpr int RB_MAXCH = 224;          // index chunks of the coarse table
@@ -695,6 +695,7 @@ struct RbShared {
     double piv[RB_G];                                     // sorted splitters, piv[RB_G-1] = +inf
     unsigned short pc[RB_MAXCH + 1][RB_NSUP];             // samples with index < c*ch and band <= s
   } u;
+  unsigned short ragged[RB_NSUP][RB_THREADS];   // per-thread band counts of a window's ragged ends
   double red[2 * (RB_THREADS / 32)];
   int scan_tmp[40];
 };
@@ -816,29 +817,36 @@ __global__ void __launch_bounds__(RB_THREADS) k_rolling_floor_blk(
     sh.perm[pos] = static_cast<unsigned short>(j);
   }
   __syncthreads();
-  // order inside the buckets by counting (load-balanced over samples, not buckets):
-  // final position = bucket start + #{bucket members that sort before this sample}
+  // order inside the buckets by counting: final position = bucket start + #{bucket members that
+  // sort before this sample}.  Work is dealt out in bucket order (thread <-> scattered position),
+  // so the lanes of a warp walk the same bucket: equal trip counts, broadcast shared-memory reads.
   {
     constexpr int MAXPER = (RB_NCAP + RB_THREADS - 1) / RB_THREADS;
     unsigned short fin[MAXPER];
 #pragma unroll 1
-    for (int u2 = 0, j = tid; j < n; j += RB_THREADS, ++u2) {
+    for (int u2 = 0, e = tid; e < n; e += RB_THREADS, ++u2) {
+      const int j = sh.perm[e];
       const int g = sh.rank[j];
       const int e0 = sh.start[g], e1 = sh.start[g + 1];
       const double x = sh.d[j];
       int before = 0;
-      for (int e = e0; e < e1; ++e) {
-        const int y = sh.perm[e];
+      for (int f = e0; f < e1; ++f) {
+        const int y = sh.perm[f];
         const double dy = sh.d[y];
         before += (dy < x || (dy == x && y < j)) ? 1 : 0;
       }
       fin[u2] = static_cast<unsigned short>(e0 + before);
     }
     __syncthreads();
+    // perm is rewritten in place: every thread first reads the sample ids it owns
+    unsigned short own[MAXPER];
 #pragma unroll 1
-    for (int u2 = 0, j = tid; j < n; j += RB_THREADS, ++u2) {
-      sh.rank[j] = fin[u2];
-      sh.perm[fin[u2]] = static_cast<unsigned short>(j);
+    for (int u2 = 0, e = tid; e < n; e += RB_THREADS, ++u2) own[u2] = sh.perm[e];
+    __syncthreads();
+#pragma unroll 1
+    for (int u2 = 0, e = tid; e < n; e += RB_THREADS, ++u2) {
+      sh.rank[own[u2]] = fin[u2];
+      sh.perm[fin[u2]] = own[u2];
     }
   }
   // ---- S4: coarse table over (index chunk, rank band)
@@ -890,19 +898,26 @@ __global__ void __launch_bounds__(RB_THREADS) k_rolling_floor_blk(
     const double frac = __dsub_rn(fq, static_cast<double>(idx));
     const int a = aa - x0, b = bb - x0;                        // local indices, inclusive
     if (!have || i != prev_i + 1) {
-      // #{window samples in rank bands <= s}: whole chunks from the table + the ragged ends
+      // #{window samples in rank bands <= s}: whole chunks from the table + the ragged ends.
+      // The ragged ends are counted once into a per-thread band histogram (cumulated in place).
       const int ca = (a + ch - 1) / ch;                        // first whole chunk
       const int cbk = (b + 1) / ch;                            // one past the last whole chunk
+      unsigned short* rg = &sh.ragged[0][0] + tid;                   // [RB_NSUP][RB_THREADS]
+      for (int s2 = 0; s2 < RB_NSUP; ++s2) rg[s2 * RB_THREADS] = 0;
+      if (cbk > ca) {
+        for (int j = a; j < ca * ch; ++j) rg[(sh.rank[j] >> bshift) * RB_THREADS] += 1;
+        for (int j = cbk * ch; j <= b; ++j) rg[(sh.rank[j] >> bshift) * RB_THREADS] += 1;
+      } else {
+        for (int j = a; j <= b; ++j) rg[(sh.rank[j] >> bshift) * RB_THREADS] += 1;
+      }
+      {
+        unsigned int acc = 0;
+        for (int s2 = 0; s2 < RB_NSUP; ++s2) { acc += rg[s2 * RB_THREADS]; rg[s2 * RB_THREADS] = static_cast<unsigned short>(acc); }
+      }
       auto cum = [&](int s_) -> int {
         if (s_ < 0) return 0;
-        int cs_ = 0;
-        if (cbk > ca) {
-          cs_ = static_cast<int>(sh.u.pc[cbk][s_]) - static_cast<int>(sh.u.pc[ca][s_]);
-          for (int j = a; j < ca * ch; ++j) cs_ += ((sh.rank[j] >> bshift) <= s_);
-          for (int j = cbk * ch; j <= b; ++j) cs_ += ((sh.rank[j] >> bshift) <= s_);
-        } else {
-          for (int j = a; j <= b; ++j) cs_ += ((sh.rank[j] >> bshift) <= s_);
-        }
+        int cs_ = rg[s_ * RB_THREADS];
+        if (cbk > ca) cs_ += static_cast<int>(sh.u.pc[cbk][s_]) - static_cast<int>(sh.u.pc[ca][s_]);
         return cs_;
       };
       int slo = 0, shi = RB_NSUP - 1;                          // smallest band with cum > idx

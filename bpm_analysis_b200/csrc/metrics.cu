@@ -11,49 +11,64 @@ __global__ void k_peak_strength(const double* __restrict__ env, const double* __
                                 const int64_t* __restrict__ peaks, const int64_t* __restrict__ peak_count,
                                 const BpmItem* __restrict__ items, double* __restrict__ strength) {
   const BpmItem it = items[blockIdx.y];
-  const long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (k >= peak_count[blockIdx.y]) return;
-  const int64_t p = peaks[it.m_off + k];
-  double s = __dsub_rn(env[it.m_off + p], floor_[it.m_off + p]);
-  if (s < 0.0) s = 0.0;
-  strength[it.m_off + k] = s;
+  const long long np = peak_count[blockIdx.y];
+  for (long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < np;
+       k += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int64_t p = peaks[it.m_off + k];
+    double s = __dsub_rn(env[it.m_off + p], floor_[it.m_off + p]);
+    if (s < 0.0) s = 0.0;
+    strength[it.m_off + k] = s;
+  }
 }
 
 // deviation[k] = |s[k+1]-s[k]| / (max(s[k], s[k+1]) + 1e-9)                       (:96)
 __global__ void k_peak_deviation(const double* __restrict__ strength, const int64_t* __restrict__ peak_count,
                                  const BpmItem* __restrict__ items, double* __restrict__ dev) {
   const BpmItem it = items[blockIdx.y];
-  const long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (k + 1 >= peak_count[blockIdx.y]) return;
-  const double a = strength[it.m_off + k], b = strength[it.m_off + k + 1];
-  const double mx = (isnan(a) || isnan(b)) ? __longlong_as_double(0x7ff8000000000000ll) : fmax(a, b);
-  dev[it.m_off + k] = __ddiv_rn(fabs(__dsub_rn(b, a)), __dadd_rn(mx, 1e-9));
+  const long long np = peak_count[blockIdx.y];
+  for (long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; k + 1 < np;
+       k += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const double a = strength[it.m_off + k], b = strength[it.m_off + k + 1];
+    const double mx = (isnan(a) || isnan(b)) ? __longlong_as_double(0x7ff8000000000000ll) : fmax(a, b);
+    dev[it.m_off + k] = __ddiv_rn(fabs(__dsub_rn(b, a)), __dadd_rn(mx, 1e-9));
+  }
 }
 
 // centred rolling mean, window max(5, int((P-1)*factor)), min_periods=1          (:99-100)
-__global__ void k_dev_smooth(const double* __restrict__ dev, const int64_t* __restrict__ peak_count,
-                             const BpmItem* __restrict__ items, double factor, double* __restrict__ out) {
+// one warp per output: lanes stride over the window, then a shuffle reduction
+__global__ void __launch_bounds__(256) k_dev_smooth(const double* __restrict__ dev,
+                                                    const int64_t* __restrict__ peak_count,
+                                                    const BpmItem* __restrict__ items, double factor,
+                                                    double* __restrict__ out) {
   const BpmItem it = items[blockIdx.y];
   const long long n = peak_count[blockIdx.y] - 1;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const int lane = threadIdx.x & 31;
   long long w = static_cast<long long>(__dmul_rn(static_cast<double>(n), factor));
   if (w < 5) w = 5;
   const long long off = (w - 1) / 2;
-  long long a = i + 1 + off - w, b = i + off;
-  if (a < 0) a = 0;
-  if (b > n - 1) b = n - 1;
   const double* d = dev + it.m_off;
-  double s = 0.0;
-  for (long long k = a; k <= b; ++k) s = __dadd_rn(s, d[k]);
-  out[it.m_off + i] = __ddiv_rn(s, static_cast<double>(b - a + 1));
+  const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long i = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+    long long a = i + 1 + off - w, b = i + off;
+    if (a < 0) a = 0;
+    if (b > n - 1) b = n - 1;
+    double s = 0.0;
+    for (long long k = a + lane; k <= b; k += 32) s += d[k];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[it.m_off + i] = __ddiv_rn(s, static_cast<double>(b - a + 1));
+  }
 }
 
 int peak_metrics_run(const double* env, const double* floor_, const int64_t* peaks, const int64_t* peak_count,
                      const BpmItem* items, const BatchShape& sh, double factor, double* strength,
                      double* deviation, double* smoothed, cudaStream_t st) {
   if (!env || !floor_ || !peaks || !peak_count || !items || !strength || !deviation || !smoothed) return BPM_ERR_ARG;
-  const dim3 grid(cdiv(sh.max_m / 2 + 2, 256), sh.n_items);
+  // peak counts live on the device: bounded grids, grid-stride loops
+  int64_t gx = (sh.max_m / 2 + 2 + 255) / 256;
+  const int64_t cap = (148 * 4 + sh.n_items - 1) / sh.n_items;
+  if (gx > cap) gx = cap;
+  const dim3 grid(static_cast<unsigned>(gx < 1 ? 1 : gx), sh.n_items);
   BPM_KERNEL(k_peak_strength);
   k_peak_strength<<<grid, 256, 0, st>>>(env, floor_, peaks, peak_count, items, strength);
   BPM_LAUNCH_OK();
@@ -156,16 +171,31 @@ __global__ void __launch_bounds__(1024) k_steepest(const double* __restrict__ sm
                                                    const int64_t* __restrict__ stamp_us,
                                                    const int64_t* __restrict__ n_valid,
                                                    const BpmItem* __restrict__ lists, int sign, double window_sec,
-                                                   double* __restrict__ result) {
+                                                   double* __restrict__ result, int stage_cap) {
+  extern __shared__ __align__(16) unsigned char st_raw[];   // optional staging: stamps then values
   __shared__ double s_val[32];
   __shared__ long long s_idx[32];
   __shared__ long long s_j[32];
   __shared__ long long s_start;
+  // sign == 0: blockIdx.y selects the direction (0: +1 exertion, 1: -1 recovery), results
+  // interleaved as [list][2][4]
+  const bool both = (sign == 0);
+  if (both) sign = blockIdx.y == 0 ? +1 : -1;
   const BpmItem it = lists[blockIdx.x];
   const long long n = n_valid[blockIdx.x];
   const double* v = smoothed + it.m_off;
   const int64_t* us = stamp_us + it.m_off;
-  double* res = result + 4 * blockIdx.x;
+  bool staged = false;
+  if (stage_cap > 0 && n <= stage_cap) {
+    int64_t* s_us = reinterpret_cast<int64_t*>(st_raw);
+    double* s_v = reinterpret_cast<double*>(st_raw) + stage_cap;
+    for (long long t = threadIdx.x; t < n; t += blockDim.x) { s_us[t] = us[t]; s_v[t] = v[t]; }
+    __syncthreads();
+    us = s_us;
+    v = s_v;
+    staged = true;
+  }
+  double* res = both ? result + 8 * blockIdx.x + 4 * blockIdx.y : result + 4 * blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   if (n < 2) {
     if (threadIdx.x == 0) { res[0] = 0; res[1] = 0; res[2] = 0; res[3] = 0; }
@@ -202,20 +232,28 @@ __global__ void __launch_bounds__(1024) k_steepest(const double* __restrict__ sm
     if (threadIdx.x == 0) { res[0] = 0; res[1] = 0; res[2] = 0; res[3] = 0; }
     return;
   }
+  // seconds since the sub-series start, total_seconds() = us / 1e6, tabulated once when staged
+  double* s_t = reinterpret_cast<double*>(st_raw) + 2 * static_cast<size_t>(stage_cap);
+  if (staged) {
+    __syncthreads();
+    for (long long t = start + threadIdx.x; t < n; t += blockDim.x)
+      s_t[t] = __ddiv_rn(static_cast<double>(us[t] - us0), 1.0e6);
+    __syncthreads();
+  }
   double best = 0.0; long long best_i = 0x7fffffffffffffffll, best_j = 0;
   for (long long ii = threadIdx.x; ii + 1 < len; ii += blockDim.x) {
     const long long i = start + ii;
-    const double ti = __ddiv_rn(static_cast<double>(us[i] - us0), 1.0e6);
+    const double ti = staged ? s_t[i] : __ddiv_rn(static_cast<double>(us[i] - us0), 1.0e6);
     const double target = __dadd_rn(ti, window_sec);
     // first j in [start, n) with t_j >= target (times are non-decreasing)
     long long lo = start, hi = n;
     while (lo < hi) {
       const long long mid = (lo + hi) >> 1;
-      const double tm = __ddiv_rn(static_cast<double>(us[mid] - us0), 1.0e6);
+      const double tm = staged ? s_t[mid] : __ddiv_rn(static_cast<double>(us[mid] - us0), 1.0e6);
       if (tm >= target) hi = mid; else lo = mid + 1;
     }
     if (lo >= n) continue;           // the reference breaks here; later i cannot succeed either
-    const double tj = __ddiv_rn(static_cast<double>(us[lo] - us0), 1.0e6);
+    const double tj = staged ? s_t[lo] : __ddiv_rn(static_cast<double>(us[lo] - us0), 1.0e6);
     const double dur = __dsub_rn(tj, ti);
     if (dur > 0.0) {
       const double slope = __ddiv_rn(__dsub_rn(v[lo], v[i]), dur);
@@ -246,11 +284,16 @@ __global__ void __launch_bounds__(1024) k_steepest(const double* __restrict__ sm
 }
 
 int steepest_run(const double* smoothed, const int64_t* stamp_us, const int64_t* n_valid, const BpmItem* lists,
-                 int n_lists, int sign, double window_sec, double* result, cudaStream_t st) {
-  if (!smoothed || !stamp_us || !n_valid || !lists || !result || n_lists <= 0 || (sign != 1 && sign != -1))
+                 int n_lists, int64_t max_len, int sign, double window_sec, double* result, cudaStream_t st) {
+  if (!smoothed || !stamp_us || !n_valid || !lists || !result || n_lists <= 0 || sign < -1 || sign > 1)
     return BPM_ERR_ARG;
+  // series up to 6144 points are staged in shared memory (the binary searches are latency-bound)
+  const int stage_cap = max_len <= 6144 ? 6144 : 0;
+  const size_t smem = static_cast<size_t>(stage_cap) * 24;
+  if (smem) cudaFuncSetAttribute(k_steepest, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   BPM_KERNEL(k_steepest);
-  k_steepest<<<n_lists, 1024, 0, st>>>(smoothed, stamp_us, n_valid, lists, sign, window_sec, result);
+  k_steepest<<<dim3(n_lists, sign == 0 ? 2 : 1), 1024, smem, st>>>(smoothed, stamp_us, n_valid, lists, sign,
+                                                                  window_sec, result, stage_cap);
   BPM_LAUNCH_OK();
   return BPM_OK;
 }

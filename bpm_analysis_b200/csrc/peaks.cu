@@ -195,17 +195,18 @@ __global__ void __launch_bounds__(DP_THREADS) k_distance(const double* __restric
   const int item = blockIdx.y;
   const BpmItem it = items[item];
   const int64_t nc = cand_count[item];
-  const int64_t k0 = static_cast<int64_t>(blockIdx.x) * DP_TILE;
-  if (k0 >= nc) return;
-  const int64_t k1 = min(nc, k0 + DP_TILE);
   const int64_t* __restrict__ pos = cand + it.m_off;
   const double* __restrict__ xi = x + it.m_off;
   unsigned char* st_out = state + it.m_off;
   const int64_t d = distance;
+  // the grid is bounded (the candidate count is only known on the device): tiles are block-strided
+  for (int64_t k0 = static_cast<int64_t>(blockIdx.x) * DP_TILE; k0 < nc; k0 += static_cast<int64_t>(gridDim.x) * DP_TILE) {
+  const int64_t k1 = min(nc, k0 + DP_TILE);
+  __syncthreads();
 
   if (distance <= 1) {
     for (int64_t k = k0 + threadIdx.x; k < k1; k += DP_THREADS) st_out[k] = 1;
-    return;
+    continue;
   }
   // own the clusters whose head lies in [k0, k1): ks = first head >= k0, ke = first head >= k1
   // (a cluster = run of candidates with gaps < d; a head is a candidate >= d after its predecessor)
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(DP_THREADS) k_distance(const double* __restric
   }
   const int64_t ks = s_edge[0], ke = s_edge[1];
   const int64_t len = ke - ks;
-  if (len <= 0) return;
+  if (len <= 0) continue;
 
   if (len <= DP_CAP) {
     const int L = static_cast<int>(len);
@@ -245,15 +246,13 @@ __global__ void __launch_bounds__(DP_THREADS) k_distance(const double* __restric
         const double vk = s_val[k];
         bool any_keep = false, any_open = false;
         for (int k2 = k - 1; k2 >= 0 && pk - s_pos[k2] < di; --k2) {
-          const double v2 = s_val[k2];
-          if (v2 > vk) {                                   // equal heights: the later index wins
+          if (s_val[k2] > vk) {                            // equal heights: the later index wins
             const unsigned char s2 = s_st[k2];
             any_keep |= (s2 == 1); any_open |= (s2 == 0);
           }
         }
         for (int k2 = k + 1; k2 < L && s_pos[k2] - pk < di; ++k2) {
-          const double v2 = s_val[k2];
-          if (v2 >= vk) {
+          if (s_val[k2] >= vk) {
             const unsigned char s2 = s_st[k2];
             any_keep |= (s2 == 1); any_open |= (s2 == 0);
           }
@@ -264,7 +263,7 @@ __global__ void __launch_bounds__(DP_THREADS) k_distance(const double* __restric
       if (!__syncthreads_or(changed)) break;
     }
     for (int t = threadIdx.x; t < L; t += DP_THREADS) st_out[ks + t] = (s_st[t] == 1) ? 1 : 0;
-    return;
+    continue;
   }
 
   // oversized cluster run: same fix-point straight on global memory
@@ -296,6 +295,7 @@ __global__ void __launch_bounds__(DP_THREADS) k_distance(const double* __restric
     if (!__syncthreads_or(changed)) break;
   }
   for (int64_t k = ks + threadIdx.x; k < ke; k += DP_THREADS) stt[k] = (stt[k] == 1) ? 1 : 0;
+  }  // tile loop
 }
 
 // Prominence rule on the survivors of the distance rule: one warp per candidate, grid-stride.
@@ -350,6 +350,167 @@ __global__ void __launch_bounds__(PK_THREADS) k_count_flags(const unsigned char*
   }
 }
 
+// Prominence test with per-32-sample block minima / maxima (shared memory): whole blocks that
+// contain neither a stop (a sample above the peak) nor a pass (a sample low enough) are skipped
+// 32 at a time.  Same decision as warp_prominence_ok.
+__device__ bool warp_prominence_ok_blocks(const double* __restrict__ xs, const double* __restrict__ bmin,
+                                          const double* __restrict__ bmax, int n, int p, double thr) {
+  const int lane = threadIdx.x & 31;
+  const double xp = xs[p];
+  if (__dsub_rn(xp, xp) >= thr) return true;
+  const int nblk = (n + 31) >> 5;
+#pragma unroll 1
+  for (int side = 0; side < 2; ++side) {
+    const int dir = side == 0 ? -1 : +1;
+    int pos = p + dir;                                     // next sample to examine
+    bool decided = false, ok = false;
+    while (!decided) {
+      if (pos < 0 || pos >= n) { ok = false; break; }      // ran off the signal: walk stops
+      // sample-wise over the rest of the current block (in walking direction)
+      const int blk = pos >> 5;
+      const int idx = pos + dir * lane;
+      const bool valid = idx >= 0 && idx < n && (idx >> 5) == blk;
+      const double v = valid ? xs[idx] : 0.0;
+      const bool stop = valid && (v > xp);
+      const bool pass = valid && !(v > xp) && (__dsub_rn(xp, v) >= thr);
+      const unsigned bs = __ballot_sync(0xffffffffu, stop), bp = __ballot_sync(0xffffffffu, pass);
+      const int fs = bs ? __ffs(bs) : 33, fp = bp ? __ffs(bp) : 33;
+      if (fp < fs) { ok = true; decided = true; break; }
+      if (bs) { ok = false; decided = true; break; }
+      // move to the edge of the next block and skip whole quiet blocks 32 at a time
+      int nb = blk + dir;
+      while (true) {
+        if (nb < 0 || nb >= nblk) { pos = dir < 0 ? -1 : n; break; }
+        const int b = nb + dir * lane;
+        const bool bvalid = b >= 0 && b < nblk;
+        const bool hot = bvalid && ((bmax[b] > xp) || (__dsub_rn(xp, bmin[b]) >= thr));
+        const unsigned bh = __ballot_sync(0xffffffffu, hot || !bvalid);
+        if (bh == 0) { nb += dir * 32; continue; }
+        const int first = __ffs(bh) - 1;                   // first hot (or out-of-range) block on the way
+        const int bsel = nb + dir * first;
+        if (bsel < 0 || bsel >= nblk) pos = dir < 0 ? -1 : n;
+        else pos = dir < 0 ? (bsel << 5) + 31 : (bsel << 5);
+        if (pos >= n) pos = n - 1;                          // ragged last block, walking left into it
+        break;
+      }
+    }
+    if (!ok) return false;
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------ one-CTA find_peaks
+// Short signals (the BPM series of the beat-list reductions, short recordings): the whole
+// pipeline -- local maxima, height, ordered compaction, distance fix-point, prominence,
+// final compaction -- in ONE launch, signal and candidate list staged in shared memory.
+constexpr int FPS_THREADS = 512;
+constexpr int FPS_MAXN = 8192;
+
+__global__ void __launch_bounds__(FPS_THREADS) k_find_peaks_small(const double* __restrict__ x, int sign,
+                                                                  const double* __restrict__ height,
+                                                                  const double* __restrict__ prominence, int distance,
+                                                                  const BpmItem* __restrict__ items,
+                                                                  int64_t* __restrict__ out_idx,
+                                                                  int64_t* __restrict__ out_count) {
+  extern __shared__ __align__(16) unsigned char fps_raw[];
+  double* xs = reinterpret_cast<double*>(fps_raw);                       // [FPS_MAXN]
+  int* cpos = reinterpret_cast<int*>(xs + FPS_MAXN);                     // [FPS_MAXN / 2 + 1]
+  unsigned char* cst = reinterpret_cast<unsigned char*>(cpos + FPS_MAXN / 2 + 1);
+  __shared__ double s_bmin[FPS_MAXN / 32], s_bmax[FPS_MAXN / 32];
+  __shared__ int s_scan[34];
+  __shared__ int s_base;
+  const int item = blockIdx.x;
+  const BpmItem it = items[item];
+  const int n = static_cast<int>(it.m);
+  const int tid = threadIdx.x;
+  const double* __restrict__ xi = x + it.m_off;
+  for (int i = tid; i < n; i += FPS_THREADS) xs[i] = signed_val(xi[i], sign);
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int b = tid; b < (n + 31) / 32; b += FPS_THREADS) {
+    double mn = INFINITY, mx = -INFINITY;
+    for (int i = b * 32; i < min(n, b * 32 + 32); ++i) { mn = fmin(mn, xs[i]); mx = fmax(mx, xs[i]); }
+    s_bmin[b] = mn; s_bmax[b] = mx;
+  }
+  // ---- local maxima (plateau midpoints) + height, ordered
+  for (int base = 0; base < n; base += FPS_THREADS) {
+    const int i = base + tid;
+    bool pk = false;
+    if (i >= 1 && i <= n - 2) {
+      const double c = xs[i], l = xs[i - 1], r = xs[i + 1];
+      if (l < c && r < c) {
+        pk = true;
+      } else if ((l == c || r == c) && l <= c && r <= c) {
+        int L = i, R = i;
+        while (L - 1 >= 0 && xs[L - 1] == c) --L;
+        while (R + 1 <= n - 1 && xs[R + 1] == c) ++R;
+        pk = (L >= 1 && R <= n - 2 && xs[L - 1] < c && xs[R + 1] < c && i == (L + R) / 2);
+      }
+      if (pk && height != nullptr) pk = (height[it.m_off + i] <= c);
+    }
+    int total;
+    const int ex = block_exclusive_scan(pk ? 1 : 0, &total, s_scan);
+    const int b0 = s_base;
+    if (pk) { cpos[b0 + ex] = i; cst[b0 + ex] = 0; }
+    __syncthreads();
+    if (tid == 0) s_base = b0 + total;
+    __syncthreads();
+  }
+  const int nc = s_base;
+  // ---- distance: fix-point of "kept iff no kept higher-priority candidate closer than d"
+  // (lock-step rounds; polling without barriers was measured slower)
+  if (distance > 1) {
+    while (true) {
+      int changed = 0;
+      for (int k = tid; k < nc; k += FPS_THREADS) {
+        if (cst[k] != 0) continue;
+        const int pk = cpos[k];
+        const double vk = xs[pk];
+        bool any_keep = false, any_open = false;
+        for (int k2 = k - 1; k2 >= 0 && pk - cpos[k2] < distance; --k2) {
+          if (xs[cpos[k2]] > vk) { const unsigned char s2 = cst[k2]; any_keep |= (s2 == 1); any_open |= (s2 == 0); }
+        }
+        for (int k2 = k + 1; k2 < nc && cpos[k2] - pk < distance; ++k2) {
+          if (xs[cpos[k2]] >= vk) { const unsigned char s2 = cst[k2]; any_keep |= (s2 == 1); any_open |= (s2 == 0); }
+        }
+        if (any_keep) { cst[k] = 2; changed = 1; }
+        else if (!any_open) { cst[k] = 1; changed = 1; }
+      }
+      if (!__syncthreads_or(changed)) break;
+    }
+  } else {
+    for (int k = tid; k < nc; k += FPS_THREADS) cst[k] = 1;
+    __syncthreads();
+  }
+  // ---- prominence: one warp per survivor
+  if (prominence != nullptr) {
+    const double thr = prominence[item];
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int k = warp; k < nc; k += FPS_THREADS / 32) {
+      if (cst[k] != 1) continue;
+      const bool ok = warp_prominence_ok_blocks(xs, s_bmin, s_bmax, n, cpos[k], thr);
+      if (lane == 0 && !ok) cst[k] = 2;
+    }
+    __syncthreads();
+  }
+  // ---- ordered output
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  int64_t* oi = out_idx + it.m_off;
+  for (int base = 0; base < nc; base += FPS_THREADS) {
+    const int k = base + tid;
+    const bool keep = (k < nc) && cst[k] == 1;
+    int total;
+    const int ex = block_exclusive_scan(keep ? 1 : 0, &total, s_scan);
+    const int b0 = s_base;
+    if (keep) oi[b0 + ex] = cpos[k];
+    __syncthreads();
+    if (tid == 0) s_base = b0 + total;
+    __syncthreads();
+  }
+  if (tid == 0) out_count[item] = s_base;
+}
+
 // ------------------------------------------------------------------ host side
 struct PeakBuffers {
   unsigned char* flags;     // [total_m]  sample-domain flags, then candidate-domain flags
@@ -398,6 +559,15 @@ int find_peaks_run(const double* x, int sign, const double* height, const double
                    const BpmItem* items, const BatchShape& sh, int64_t* out_idx, int64_t* out_count,
                    Workspace& ws, cudaStream_t st) {
   if (!x || !items || !out_idx || !out_count || sh.n_items <= 0 || distance < 1) return BPM_ERR_ARG;
+  if (sh.max_m <= FPS_MAXN) {
+    const size_t smem = sizeof(double) * FPS_MAXN + sizeof(int) * (FPS_MAXN / 2 + 1) + (FPS_MAXN / 2 + 1);
+    cudaFuncSetAttribute(k_find_peaks_small, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    BPM_KERNEL(k_find_peaks_small);
+    k_find_peaks_small<<<sh.n_items, FPS_THREADS, smem, st>>>(x, sign, height, prominence, distance, items, out_idx,
+                                                            out_count);
+    BPM_LAUNCH_OK();
+    return BPM_OK;
+  }
   PeakBuffers b;
   BPM_TRY(carve_peaks(ws, sh.total_m, sh.n_items, &b));
   const dim3 grid(cdiv(sh.max_m, PK_TILE), sh.n_items);
@@ -408,8 +578,14 @@ int find_peaks_run(const double* x, int sign, const double* height, const double
   // a local maximum needs a lower neighbour on both sides: at most (m-1)/2 candidates
   const int64_t max_c = sh.max_m / 2 + 1;
   BPM_KERNEL(k_distance);
-  k_distance<<<dim3(cdiv(max_c, DP_TILE), sh.n_items), DP_THREADS, 0, st>>>(x, sign, items, b.cand, b.cand_count,
-                                                                           distance, b.cstate);
+  {
+    int64_t gx = (max_c + DP_TILE - 1) / DP_TILE;
+    const int64_t cap = (148 * 8 + sh.n_items - 1) / sh.n_items;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    k_distance<<<dim3(static_cast<unsigned>(gx), sh.n_items), DP_THREADS, 0, st>>>(x, sign, items, b.cand,
+                                                                                  b.cand_count, distance, b.cstate);
+  }
   BPM_LAUNCH_OK();
   if (prominence != nullptr) {
     const int64_t want = (max_c + PR_THREADS / 32 - 1) / (PR_THREADS / 32);

@@ -42,7 +42,7 @@ int bpm_series_run(const int64_t* beats, const BpmItem* lists, const BatchShape&
                    double* inst, double* smoothed, double* times_sec, int64_t* stamp_us, int64_t* n_valid,
                    cudaStream_t st);
 int steepest_run(const double* smoothed, const int64_t* stamp_us, const int64_t* n_valid, const BpmItem* lists,
-                 int n_lists, int sign, double window_sec, double* result, cudaStream_t st);
+                 int n_lists, int64_t max_len, int sign, double window_sec, double* result, cudaStream_t st);
 int hrv_run(const int64_t* beats, const BpmItem* lists, const BatchShape& sh, int rate, int win, int step,
             double* out, int64_t* rows, cudaStream_t st);
 
@@ -370,9 +370,10 @@ size_t bpm_steepest_slope_workspace_bytes(int64_t total_beats, int n_lists) {
 int bpm_steepest_slope(const double* smoothed, const int64_t* stamp_us, const int64_t* n_valid, const BpmItem* lists,
                        const BpmItem* lists_host, int n_lists, int sign, double window_sec, double* result,
                        void* workspace, size_t workspace_bytes, void* stream) {
-  (void)workspace; (void)workspace_bytes; (void)lists_host;
-  return steepest_run(smoothed, stamp_us, n_valid, lists, n_lists, sign, window_sec, result,
-                      static_cast<cudaStream_t>(stream));
+  (void)workspace; (void)workspace_bytes;
+  if (!lists_host || n_lists <= 0) return BPM_ERR_ARG;
+  return steepest_run(smoothed, stamp_us, n_valid, lists, n_lists, batch_shape(lists_host, n_lists).max_m, sign,
+                      window_sec, result, static_cast<cudaStream_t>(stream));
 }
 
 int bpm_windowed_hrv(const int64_t* beats, const BpmItem* lists, const BpmItem* lists_host, int n_lists, int rate,

@@ -4,8 +4,11 @@
 // Exact order statistics by most-significant-digit radix select on the order-preserving
 // 64-bit image of each float64 (six passes: 11,11,11,11,11,9 bits), then the next larger
 // element, then numpy's two-branch lerp evaluated with unfused float64 operations so the
-// result is bit-identical to numpy's.  All items of the batch advance together; a pass
-// whose `cond` says the quantile is not needed for an item skips that item.
+// result is bit-identical to numpy's.  Up to SEL_MAXQ quantile levels of the same data are
+// resolved in the same passes (the noise-floor stage needs q(trough_prominence) always and
+// q(noise_floor_quantile) only for recordings with fewer than 5 troughs: `cond` switches a
+// level off per recording).  Histogram updates are warp-aggregated (envelope values share
+// their leading digits, so plain shared-memory atomics would serialise).
 #include "common.cuh"
 
 namespace bpm {
@@ -15,6 +18,7 @@ constexpr int SEL_BINS = 2048;
 constexpr int SEL_THREADS = 256;
 constexpr int SEL_PER_THREAD = 16;
 constexpr int SEL_TILE = SEL_THREADS * SEL_PER_THREAD;
+constexpr int SEL_MAXQ = 3;
 
 __host__ __device__ __forceinline__ int sel_shift(int p) { return p < 5 ? 53 - 11 * p : 0; }
 __host__ __device__ __forceinline__ int sel_bits(int p) { return p < 5 ? 11 : 9; }
@@ -30,12 +34,26 @@ struct SelState {
   long long active;            // 0: skipped for this item
 };
 
-// state after pass p-1 from the state after pass p-2 and hist[p-1]; every block computes it
-// redundantly, block 0 of the item stores it.
-__device__ void sel_advance(const SelState* __restrict__ prev, const unsigned int* __restrict__ hist, int bins,
-                            SelState* out_shared, int* scratch /* >= 34 ints */) {
-  // block-wide: find bucket b with cum[b] <= rank < cum[b+1]
-  __shared__ long long s_cum[SEL_THREADS + 1];
+struct SelLevels {
+  int nq;
+  double q[SEL_MAXQ];
+  const int* cond[SEL_MAXQ];   // per recording on/off (nullptr: always on)
+  double* out[SEL_MAXQ];       // per recording result
+};
+
+// index helpers: states[pass][level][item], hist[item][level][pass][bin]
+__device__ __forceinline__ size_t st_idx(int pass, int lvl, int item, int n_items) {
+  return (static_cast<size_t>(pass) * SEL_MAXQ + lvl) * n_items + item;
+}
+__device__ __forceinline__ size_t hist_idx(int item, int lvl, int pass) {
+  return ((static_cast<size_t>(item) * SEL_MAXQ + lvl) * SEL_PASSES + pass) * SEL_BINS;
+}
+
+// state after resolving one pass, from the state before it and that pass's histogram
+// (block-wide; every block computes it redundantly)
+__device__ void sel_advance(const SelState& prev, const unsigned int* __restrict__ hist, int bits, SelState* out_shared,
+                            long long* s_cum /* SEL_THREADS + 1 */) {
+  const int bins = 1 << bits;
   const int per = (bins + SEL_THREADS - 1) / SEL_THREADS;
   const int b0 = threadIdx.x * per;
   long long local = 0;
@@ -43,177 +61,250 @@ __device__ void sel_advance(const SelState* __restrict__ prev, const unsigned in
   s_cum[threadIdx.x + 1] = local;
   if (threadIdx.x == 0) s_cum[0] = 0;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int t = 1; t <= SEL_THREADS; ++t) s_cum[t] += s_cum[t - 1];
+  if (threadIdx.x < 32) {
+    // inclusive scan of SEL_THREADS partial sums by one warp, 8 per lane
+    constexpr int PW = SEL_THREADS / 32;
+    long long v[PW];
+    long long s = 0;
+#pragma unroll
+    for (int u = 0; u < PW; ++u) { s += s_cum[1 + threadIdx.x * PW + u]; v[u] = s; }
+    long long inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (threadIdx.x >= o) inc += t;
+    }
+    const long long base = inc - s;
+#pragma unroll
+    for (int u = 0; u < PW; ++u) s_cum[1 + threadIdx.x * PW + u] = base + v[u];
   }
   __syncthreads();
-  const long long rank = prev->rank;
+  const long long rank = prev.rank;
   const long long lo = s_cum[threadIdx.x], hi = s_cum[threadIdx.x + 1];
   if (rank >= lo && rank < hi) {
     long long c = lo;
     for (int b = b0; b < min(b0 + per, bins); ++b) {
       const long long h = hist[b];
       if (rank < c + h) {
-        out_shared->prefix = (prev->prefix << (bins == 512 ? 9 : 11)) | static_cast<unsigned long long>(b);
+        out_shared->prefix = (prev.prefix << bits) | static_cast<unsigned long long>(b);
         out_shared->rank = rank - c;
-        out_shared->below = prev->below + c;
+        out_shared->below = prev.below + c;
         out_shared->count = h;
         break;
       }
       c += h;
     }
-    out_shared->k = prev->k;
-    out_shared->gamma = prev->gamma;
-    out_shared->active = prev->active;
+    out_shared->k = prev.k;
+    out_shared->gamma = prev.gamma;
+    out_shared->active = prev.active;
     out_shared->next_key = ~0ull;
   }
   __syncthreads();
-  (void)scratch;
 }
 
-__global__ void k_select_init(const BpmItem* __restrict__ items, int n_items, double q,
-                              const int* __restrict__ cond, SelState* __restrict__ st) {
+__global__ void k_select_init(const BpmItem* __restrict__ items, int n_items, SelLevels lv,
+                              SelState* __restrict__ states) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_items) return;
   const long long n = items[i].m;
-  SelState s;
-  const double v = __dmul_rn(static_cast<double>(n - 1), q);   // (n - 1) * q
-  const double fl = floor(v);
-  s.prefix = 0;
-  s.k = static_cast<long long>(fl);
-  if (s.k > n - 1) s.k = n - 1;
-  if (s.k < 0) s.k = 0;
-  s.rank = s.k;
-  s.below = 0;
-  s.count = n;
-  s.gamma = __dsub_rn(v, fl);
-  s.next_key = ~0ull;
-  s.active = (n > 0 && (cond == nullptr || cond[i] != 0)) ? 1 : 0;
-  st[i] = s;
+  for (int l = 0; l < lv.nq; ++l) {
+    SelState s;
+    const double v = __dmul_rn(static_cast<double>(n - 1), lv.q[l]);   // (n - 1) * q
+    const double fl = floor(v);
+    s.prefix = 0;
+    s.k = static_cast<long long>(fl);
+    if (s.k > n - 1) s.k = n - 1;
+    if (s.k < 0) s.k = 0;
+    s.rank = s.k;
+    s.below = 0;
+    s.count = n;
+    s.gamma = __dsub_rn(v, fl);
+    s.next_key = ~0ull;
+    s.active = (n > 0 && (lv.cond[l] == nullptr || lv.cond[l][i] != 0)) ? 1 : 0;
+    states[st_idx(0, l, i, n_items)] = s;
+    SelState f = s;                       // final slot: next_key accumulates by atomicMin, active set by k_select_next
+    f.active = 0;
+    states[st_idx(SEL_PASSES, l, i, n_items)] = f;
+  }
 }
 
-// pass p: (p > 0) resolve pass p-1, then histogram digit p of the elements under the prefix
+// add 1 to s_hist[bin] for every lane with `on`, one shared-memory atomic per distinct bin per warp
+__device__ __forceinline__ void warp_hist_add(unsigned int* s_hist, bool on, unsigned int bin) {
+  const unsigned act = __ballot_sync(0xffffffffu, on);
+  if (!on) return;
+  const unsigned peers = __match_any_sync(act, bin);
+  if ((threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&s_hist[bin], static_cast<unsigned int>(__popc(peers)));
+}
+
+// pass p: (p > 0) resolve pass p-1, then histogram digit p of the elements under each level's prefix
 __global__ void __launch_bounds__(SEL_THREADS) k_select_pass(const double* __restrict__ x,
-                                                             const BpmItem* __restrict__ items, int p,
-                                                             SelState* __restrict__ states /* [SEL_PASSES+1][n_items] */,
-                                                             unsigned int* __restrict__ hist /* [n_items][SEL_PASSES][SEL_BINS] */,
-                                                             int n_items) {
-  __shared__ unsigned int s_hist[SEL_BINS];
-  __shared__ SelState s_cur;
+                                                             const BpmItem* __restrict__ items, int p, int nq,
+                                                             SelState* __restrict__ states,
+                                                             unsigned int* __restrict__ hist, int n_items) {
+  __shared__ unsigned int s_hist[SEL_MAXQ][SEL_BINS];
+  __shared__ SelState s_cur[SEL_MAXQ];
+  __shared__ long long s_cum[SEL_THREADS + 1];
   const int item = blockIdx.y;
   const BpmItem it = items[item];
-  const SelState* prev = states + static_cast<size_t>(p) * n_items + item;        // state before pass p-1 ... see below
-  // states[0] = initial; states[p] = after resolving pass p-1
-  if (prev[0].active == 0 && p == 0) return;
-  if (p > 0) {
-    const SelState* before = states + static_cast<size_t>(p - 1) * n_items + item;
-    if (before->active == 0) return;
-    sel_advance(before, hist + (static_cast<size_t>(item) * SEL_PASSES + (p - 1)) * SEL_BINS,
-                1 << sel_bits(p - 1), &s_cur, nullptr);
-    if (blockIdx.x == 0 && threadIdx.x == 0) states[static_cast<size_t>(p) * n_items + item] = s_cur;
-  } else {
-    if (threadIdx.x == 0) s_cur = prev[0];
-    __syncthreads();
+  bool any = false;
+  for (int l = 0; l < nq; ++l) {
+    if (p > 0) {
+      const SelState before = states[st_idx(p - 1, l, item, n_items)];
+      if (before.active == 0) {
+        if (threadIdx.x == 0) {
+          s_cur[l].active = 0;
+          if (blockIdx.x == 0) states[st_idx(p, l, item, n_items)].active = 0;   // keep the chain defined
+        }
+        __syncthreads();
+        continue;
+      }
+      sel_advance(before, hist + hist_idx(item, l, p - 1), sel_bits(p - 1), &s_cur[l], s_cum);
+      if (blockIdx.x == 0 && threadIdx.x == 0) states[st_idx(p, l, item, n_items)] = s_cur[l];
+    } else {
+      if (threadIdx.x == 0) s_cur[l] = states[st_idx(0, l, item, n_items)];
+      __syncthreads();
+    }
+    any = any || (s_cur[l].active != 0);
   }
   const int64_t i0 = static_cast<int64_t>(blockIdx.x) * SEL_TILE;
-  if (i0 >= it.m) return;
-  for (int t = threadIdx.x; t < SEL_BINS; t += SEL_THREADS) s_hist[t] = 0;
-  __syncthreads();
-  const unsigned long long prefix = s_cur.prefix;
+  if (!any || i0 >= it.m) return;
   const int sh = sel_shift(p), bits = sel_bits(p);
   const int up = sh + bits;                       // bits above this digit
   const unsigned int mask = (1u << bits) - 1u;
+  for (int l = 0; l < nq; ++l)
+    if (s_cur[l].active)
+      for (int t = threadIdx.x; t < (1 << bits); t += SEL_THREADS) s_hist[l][t] = 0;
+  __syncthreads();
   const double* __restrict__ xi = x + it.m_off;
 #pragma unroll 4
   for (int k = 0; k < SEL_PER_THREAD; ++k) {
     const int64_t i = i0 + k * SEL_THREADS + threadIdx.x;
-    if (i < it.m) {
-      const unsigned long long key = f64_key(xi[i]);
-      const bool match = (up >= 64) ? true : ((key >> up) == prefix);
-      if (match) atomicAdd(&s_hist[static_cast<unsigned int>(key >> sh) & mask], 1u);
+    const bool in = i < it.m;
+    const unsigned long long key = in ? f64_key(xi[i]) : 0ull;
+    const unsigned int bin = static_cast<unsigned int>(key >> sh) & mask;
+    for (int l = 0; l < nq; ++l) {
+      if (!s_cur[l].active) continue;
+      const bool match = in && ((up >= 64) ? true : ((key >> up) == s_cur[l].prefix));
+      warp_hist_add(s_hist[l], match, bin);
     }
   }
   __syncthreads();
-  unsigned int* gh = hist + (static_cast<size_t>(item) * SEL_PASSES + p) * SEL_BINS;
-  for (int t = threadIdx.x; t < (1 << bits); t += SEL_THREADS) {
-    const unsigned int c = s_hist[t];
-    if (c) atomicAdd(gh + t, c);
+  for (int l = 0; l < nq; ++l) {
+    if (!s_cur[l].active) continue;
+    unsigned int* gh = hist + hist_idx(item, l, p);
+    for (int t = threadIdx.x; t < (1 << bits); t += SEL_THREADS) {
+      const unsigned int c = s_hist[l][t];
+      if (c) atomicAdd(gh + t, c);
+    }
   }
 }
 
-// resolve the last pass, then find the smallest key above the selected one
+// resolve the last pass, find the smallest key above the selected one; the last block to
+// finish a recording evaluates numpy's lerp
 __global__ void __launch_bounds__(SEL_THREADS) k_select_next(const double* __restrict__ x,
-                                                             const BpmItem* __restrict__ items,
+                                                             const BpmItem* __restrict__ items, SelLevels lv,
                                                              SelState* __restrict__ states,
-                                                             const unsigned int* __restrict__ hist, int n_items) {
-  __shared__ SelState s_cur;
-  __shared__ unsigned long long s_min[SEL_THREADS / 32];
+                                                             const unsigned int* __restrict__ hist,
+                                                             unsigned int* __restrict__ done_count, int n_items) {
+  __shared__ SelState s_cur[SEL_MAXQ];
+  __shared__ long long s_cum[SEL_THREADS + 1];
+  __shared__ unsigned long long s_min[SEL_MAXQ][SEL_THREADS / 32];
+  __shared__ bool s_last;
   const int item = blockIdx.y;
   const BpmItem it = items[item];
-  const SelState* before = states + static_cast<size_t>(SEL_PASSES - 1) * n_items + item;
-  if (before->active == 0) return;
-  sel_advance(before, hist + (static_cast<size_t>(item) * SEL_PASSES + (SEL_PASSES - 1)) * SEL_BINS,
-              1 << sel_bits(SEL_PASSES - 1), &s_cur, nullptr);
-  SelState* fin = states + static_cast<size_t>(SEL_PASSES) * n_items + item;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    // next_key is accumulated with atomicMin by all blocks; it was preset to ~0 by the memset-free init below
-    fin->prefix = s_cur.prefix; fin->rank = s_cur.rank; fin->below = s_cur.below; fin->count = s_cur.count;
-    fin->k = s_cur.k; fin->gamma = s_cur.gamma; fin->active = 1;
-  }
-  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * SEL_TILE;
-  if (i0 >= it.m) return;
-  const unsigned long long sel = s_cur.prefix;
-  unsigned long long best = ~0ull;
-  const double* __restrict__ xi = x + it.m_off;
-  for (int k = 0; k < SEL_PER_THREAD; ++k) {
-    const int64_t i = i0 + k * SEL_THREADS + threadIdx.x;
-    if (i < it.m) {
-      const unsigned long long key = f64_key(xi[i]);
-      if (key > sel && key < best) best = key;
+  const int nq = lv.nq;
+  for (int l = 0; l < nq; ++l) {
+    const SelState before = states[st_idx(SEL_PASSES - 1, l, item, n_items)];
+    if (before.active == 0) {
+      if (threadIdx.x == 0) s_cur[l].active = 0;
+      __syncthreads();
+      continue;
+    }
+    sel_advance(before, hist + hist_idx(item, l, SEL_PASSES - 1), sel_bits(SEL_PASSES - 1), &s_cur[l], s_cum);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      SelState* fin = states + st_idx(SEL_PASSES, l, item, n_items);
+      fin->prefix = s_cur[l].prefix; fin->rank = s_cur[l].rank; fin->below = s_cur[l].below;
+      fin->count = s_cur[l].count; fin->k = s_cur[l].k; fin->gamma = s_cur[l].gamma; fin->active = 1;
     }
   }
+  bool any = false;
+  for (int l = 0; l < nq; ++l) any = any || (s_cur[l].active != 0);
+  if (!any) return;                                      // uniform for the whole row: nobody counts tickets
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * SEL_TILE;
+  if (i0 < it.m) {
+    unsigned long long best[SEL_MAXQ];
 #pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
-    best = t < best ? t : best;
+    for (int l = 0; l < SEL_MAXQ; ++l) best[l] = ~0ull;
+    const double* __restrict__ xi = x + it.m_off;
+    for (int k = 0; k < SEL_PER_THREAD; ++k) {
+      const int64_t i = i0 + k * SEL_THREADS + threadIdx.x;
+      if (i < it.m) {
+        const unsigned long long key = f64_key(xi[i]);
+#pragma unroll
+        for (int l = 0; l < SEL_MAXQ; ++l)
+          if (l < nq && s_cur[l].active && key > s_cur[l].prefix && key < best[l]) best[l] = key;
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < SEL_MAXQ; ++l) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, best[l], o);
+        best[l] = t < best[l] ? t : best[l];
+      }
+      if ((threadIdx.x & 31) == 0) s_min[l][threadIdx.x >> 5] = best[l];
+    }
+    __syncthreads();
+    if (threadIdx.x < nq && s_cur[threadIdx.x].active) {
+      const int l = threadIdx.x;
+      unsigned long long b = s_min[l][0];
+      for (int w = 1; w < SEL_THREADS / 32; ++w) b = s_min[l][w] < b ? s_min[l][w] : b;
+      if (b != ~0ull) atomicMin(&states[st_idx(SEL_PASSES, l, item, n_items)].next_key, b);
+    }
   }
-  if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = best;
+  // last block of this recording finishes
+  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < SEL_THREADS / 32; ++w) best = s_min[w] < best ? s_min[w] : best;
-    if (best != ~0ull) atomicMin(&fin->next_key, best);
+    const unsigned int tiles = static_cast<unsigned int>((it.m + SEL_TILE - 1) / SEL_TILE);
+    const unsigned int ticket = atomicAdd(done_count + item, 1u);
+    // blocks beyond the recording's last tile also pass here: every block of the row counts
+    s_last = (ticket == gridDim.x - 1);
+    (void)tiles;
   }
-}
-
-__global__ void k_select_finish(const SelState* __restrict__ fin, int n_items, double* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_items) return;
-  const SelState s = fin[i];
-  if (!s.active) return;
-  const double a = key_f64(s.prefix);
-  // element k+1: the same value when duplicates cover it, else the next larger element
-  double b = a;
-  if (s.below + s.count <= s.k + 1 && s.next_key != ~0ull) b = key_f64(s.next_key);
-  const double t = s.gamma;
-  const double diff = __dsub_rn(b, a);
-  double r = __dadd_rn(a, __dmul_rn(diff, t));
-  if (t >= 0.5) r = __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, t)));
-  out[i] = r;
-}
-
-__global__ void k_select_preset(SelState* __restrict__ fin, int n_items) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_items) { fin[i].next_key = ~0ull; fin[i].active = 0; }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < nq) {
+    const int l = threadIdx.x;
+    const volatile SelState* f = states + st_idx(SEL_PASSES, l, item, n_items);
+    if (f->active) {
+      const unsigned long long pk = f->prefix, nk = f->next_key;
+      const long long below = f->below, count = f->count, k = f->k;
+      const double a = key_f64(pk);
+      // element k+1: the same value when duplicates cover it, else the next larger element
+      double b = a;
+      if (below + count <= k + 1 && nk != ~0ull) b = key_f64(nk);
+      const double t = f->gamma;
+      const double diff = __dsub_rn(b, a);
+      double r = __dadd_rn(a, __dmul_rn(diff, t));
+      if (t >= 0.5) r = __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, t)));
+      lv.out[l][item] = r;
+    }
+  }
 }
 
 struct SelectBuffers {
   SelState* states;
   unsigned int* hist;
+  unsigned int* done;
 };
 
 static int carve_select(Workspace& ws, int n_items, SelectBuffers* b) {
-  b->states = ws.take<SelState>(static_cast<size_t>(SEL_PASSES + 1) * n_items);
-  b->hist = ws.take<unsigned int>(static_cast<size_t>(n_items) * SEL_PASSES * SEL_BINS);
+  b->states = ws.take<SelState>(static_cast<size_t>(SEL_PASSES + 1) * SEL_MAXQ * n_items);
+  // histograms and the per-recording completion counters are zeroed together
+  b->hist = ws.take<unsigned int>(static_cast<size_t>(n_items) * SEL_MAXQ * SEL_PASSES * SEL_BINS + n_items);
+  b->done = b->hist + static_cast<size_t>(n_items) * SEL_MAXQ * SEL_PASSES * SEL_BINS;
   return ws.overflow ? BPM_ERR_WORKSPACE : BPM_OK;
 }
 
@@ -224,35 +315,45 @@ size_t quantile_workspace_bytes(int n_items) {
   return ws.used;
 }
 
-// out[i] = np.quantile(x_i, q) for every item with cond[i] != 0 (cond may be null: all items);
-// out[i] is left untouched for skipped items.
-int quantile_run(const double* x, const BpmItem* items, const BatchShape& sh, double q, const int* cond,
-                 double* out, Workspace& ws, cudaStream_t st) {
-  if (!x || !items || !out || sh.n_items <= 0 || !(q >= 0.0 && q <= 1.0)) return BPM_ERR_ARG;
+// out[l][i] = np.quantile(x_i, q[l]) for every recording i with cond[l][i] != 0 (cond[l] may be
+// null: all recordings); skipped entries are left untouched.
+int quantile_multi_run(const double* x, const BpmItem* items, const BatchShape& sh, int nq, const double* q,
+                       const int* const* cond, double* const* out, Workspace& ws, cudaStream_t st) {
+  if (!x || !items || sh.n_items <= 0 || nq < 1 || nq > SEL_MAXQ) return BPM_ERR_ARG;
+  SelLevels lv;
+  lv.nq = nq;
+  for (int l = 0; l < SEL_MAXQ; ++l) { lv.q[l] = 0.0; lv.cond[l] = nullptr; lv.out[l] = nullptr; }
+  for (int l = 0; l < nq; ++l) {
+    if (!(q[l] >= 0.0 && q[l] <= 1.0) || !out[l]) return BPM_ERR_ARG;
+    lv.q[l] = q[l];
+    lv.cond[l] = cond ? cond[l] : nullptr;
+    lv.out[l] = out[l];
+  }
   SelectBuffers b;
   BPM_TRY(carve_select(ws, sh.n_items, &b));
   const int n = sh.n_items;
-  if (cudaMemsetAsync(b.hist, 0, sizeof(unsigned int) * static_cast<size_t>(n) * SEL_PASSES * SEL_BINS, st) != cudaSuccess)
-    return BPM_ERR_CUDA;
+  const size_t zero_words = static_cast<size_t>(n) * SEL_MAXQ * SEL_PASSES * SEL_BINS + n;
+  if (cudaMemsetAsync(b.hist, 0, sizeof(unsigned int) * zero_words, st) != cudaSuccess) return BPM_ERR_CUDA;
   BPM_KERNEL(k_select_init);
-  k_select_init<<<cdiv(n, 128), 128, 0, st>>>(items, n, q, cond, b.states);
-  BPM_LAUNCH_OK();
-  BPM_KERNEL(k_select_preset);
-  k_select_preset<<<cdiv(n, 128), 128, 0, st>>>(b.states + static_cast<size_t>(SEL_PASSES) * n, n);
+  k_select_init<<<cdiv(n, 128), 128, 0, st>>>(items, n, lv, b.states);
   BPM_LAUNCH_OK();
   const dim3 grid(cdiv(sh.max_m, SEL_TILE), n);
   for (int p = 0; p < SEL_PASSES; ++p) {
     BPM_KERNEL(k_select_pass);
-    k_select_pass<<<grid, SEL_THREADS, 0, st>>>(x, items, p, b.states, b.hist, n);
+    k_select_pass<<<grid, SEL_THREADS, 0, st>>>(x, items, p, nq, b.states, b.hist, n);
     BPM_LAUNCH_OK();
   }
   BPM_KERNEL(k_select_next);
-  k_select_next<<<grid, SEL_THREADS, 0, st>>>(x, items, b.states, b.hist, n);
-  BPM_LAUNCH_OK();
-  BPM_KERNEL(k_select_finish);
-  k_select_finish<<<cdiv(n, 128), 128, 0, st>>>(b.states + static_cast<size_t>(SEL_PASSES) * n, n, out);
+  k_select_next<<<grid, SEL_THREADS, 0, st>>>(x, items, lv, b.states, b.hist, b.done, n);
   BPM_LAUNCH_OK();
   return BPM_OK;
+}
+
+int quantile_run(const double* x, const BpmItem* items, const BatchShape& sh, double q, const int* cond,
+                 double* out, Workspace& ws, cudaStream_t st) {
+  const int* conds[1] = {cond};
+  double* outs[1] = {out};
+  return quantile_multi_run(x, items, sh, 1, &q, conds, outs, ws, st);
 }
 
 }  // namespace bpm

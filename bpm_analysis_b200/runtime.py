@@ -460,17 +460,56 @@ class BeatRunner:
         nat.check(L.bpm_bpm_series(_ptr(self.beats_dev), _ptr(self.items_dev), _host_ptr(self.items), 1, self.rate,
                                    self.window_us, _ptr(o["inst"]), _ptr(o["smoothed"]), _ptr(o["times"]),
                                    _ptr(o["stamps"]), _ptr(o["n_valid"]), st))
-        for k, sign in enumerate((+1, -1)):
-            res = o["slopes"][4 * k:4 * k + 4]
-            nat.check(L.bpm_steepest_slope(_ptr(o["smoothed"]), _ptr(o["stamps"]), _ptr(o["n_valid"]),
-                                           _ptr(self.series_items_dev), _host_ptr(self.series_items), 1, sign, 20.0,
-                                           _ptr(res), _ptr(self.ws), self.ws_bytes, st))
+        # slopes[0:4] = exertion (+1), slopes[4:8] = recovery (-1): one launch for both directions
+        nat.check(L.bpm_steepest_slope(_ptr(o["smoothed"]), _ptr(o["stamps"]), _ptr(o["n_valid"]),
+                                       _ptr(self.series_items_dev), _host_ptr(self.series_items), 1, 0, 20.0,
+                                       _ptr(o["slopes"]), _ptr(self.ws), self.ws_bytes, st))
         for sign, idx, cnt in ((+1, o["tops"], o["n_tops"]), (-1, o["bottoms"], o["n_bottoms"])):
             nat.check(L.bpm_find_peaks(_ptr(o["smoothed"]), sign, None, _ptr(self.prom), self.hr_distance,
                                        _ptr(self.series_items_dev), _host_ptr(self.series_items), 1, _ptr(idx),
                                        _ptr(cnt), _ptr(self.ws), self.ws_bytes, st))
         nat.check(L.bpm_windowed_hrv(_ptr(self.beats_dev), _ptr(self.items_dev), _host_ptr(self.items), 1, self.rate,
                                      self.win, self.step, _ptr(o["hrv"]), _ptr(o["hrv_rows"]), st))
+
+
+class GraphedStep:
+    """Captures runner launches into one CUDA graph and replays it.
+
+    The runners' buffers are allocated once and the library never allocates or synchronises,
+    so a whole step is capturable; replay removes the per-launch CPU / driver overhead of the
+    ~60 small kernels of a step.  Runners that do not depend on each other (a1..a4 on the audio,
+    a5..a8 on the beat list) are captured on forked streams, so their latency-bound kernels
+    overlap on the device.
+    """
+
+    def __init__(self, *runners, concurrent: bool = True):
+        require_cuda()
+        self.runners = runners
+        main = torch.cuda.Stream()
+        main.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(main):                      # warm-up outside capture (lazy module load etc.)
+            for r in runners:
+                r.launch()
+        torch.cuda.current_stream().wait_stream(main)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        sides = [torch.cuda.Stream() for _ in runners[1:]] if concurrent else []
+        with torch.cuda.graph(self.graph):
+            cur = torch.cuda.current_stream()
+            if concurrent:
+                for side, r in zip(sides, runners[1:]):
+                    side.wait_stream(cur)                  # fork
+                    with torch.cuda.stream(side):
+                        r.launch()
+                runners[0].launch()
+                for side in sides:
+                    cur.wait_stream(side)                  # join
+            else:
+                for r in runners:
+                    r.launch()
+
+    def launch(self) -> None:
+        self.graph.replay()
 
 
 def profile_kernels(fn, stream_ptr: Optional[int] = None) -> Dict[str, tuple]:

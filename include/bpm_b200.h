@@ -157,6 +157,7 @@ int bpm_bpm_series(const int64_t* beats, const BpmItem* lists, const BpmItem* li
 /* K10 find_peak_recovery_rate / find_peak_exertion_rate, bpm_analysis.py:1552-1595.
  *   sign = -1: steepest decline searched from the series maximum onward (recovery);
  *   sign = +1: steepest incline over the whole series (exertion).
+ *   sign =  0: both in one launch, result float64[n_lists][2][4] = {exertion, recovery}.
  *   result: float64[n_lists][4] = {found(0/1), start index, end index, slope}; indices
  *   are positions in the series of that list. */
 int bpm_steepest_slope(const double* smoothed, const int64_t* stamp_us, const int64_t* n_valid,
