@@ -180,6 +180,38 @@ __global__ void __launch_bounds__(256) k_contract_generic(PcmView pcm, const Bpm
   reinterpret_cast<double2*>(pb)[1] = make_double2(b[2], b[3]);
 }
 
+// ------------------------------------------------------------ contraction (block == 1)
+// The reference's decimate-then-filter order: each kept sample is one strided PCM frame, so
+// uf[j] = wf[0] x_j and ub0[j] = q[0] x_j + q[1] x_{j+1}.  Every thread loads ONE frame and
+// gets its right neighbour's by shuffle -- the PCM buffer may be mapped pinned HOST memory
+// (zero-copy ingest: only the sectors holding kept frames cross PCIe).
+__global__ void __launch_bounds__(256) k_contract_b1(PcmView pcm, const BpmItem* __restrict__ items, int64_t stride,
+                                                     const double* __restrict__ design, double* __restrict__ uf,
+                                                     double* __restrict__ ub0, double* __restrict__ xe) {
+  const BpmItem it = items[blockIdx.y];
+  // a warp covers 31 outputs + 1 shared neighbour so that every interior frame is loaded once
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t j = warp_global * 31 + lane;
+  if (warp_global * 31 >= it.m) return;
+  const DesignView d{design};
+  const ExtSignal x = make_ext(pcm, it, stride);
+  const bool valid = j < it.m;
+  const double v = valid ? x.at(PADLEN + j) : 0.0;
+  const double vn = __shfl_down_sync(0xffffffffu, v, 1);
+  if (!valid || lane == 31) return;
+  xe[it.m_off + j] = v;
+  if (j >= it.m - 1) return;
+  const double* __restrict__ wf = d.wf();
+  const double* __restrict__ q = d.q();
+  double2* pf = reinterpret_cast<double2*>(uf + 4 * (it.m_off + j));
+  double2* pb = reinterpret_cast<double2*>(ub0 + 4 * (it.m_off + j));
+  pf[0] = make_double2(wf[0] * v, wf[1] * v);
+  pf[1] = make_double2(wf[2] * v, wf[3] * v);
+  pb[0] = make_double2(q[0] * v + q[4] * vn, q[1] * v + q[5] * vn);
+  pb[1] = make_double2(q[2] * v + q[6] * vn, q[3] * v + q[7] * vn);
+}
+
 // ------------------------------------------------------ contraction (int16, full rate)
 // The HBM-bound kernel: mono int16 at the original rate (stride 1), block = ds.
 //   * a CTA owns CT_BLOCKS consecutive blocks; one elected thread brings their PCM span into
@@ -729,6 +761,9 @@ int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
       default: BPM_LAUNCH_CONTRACT(128, 1, 0); break;
     }
 #undef BPM_LAUNCH_CONTRACT
+  } else if (block == 1) {
+    BPM_KERNEL(k_contract_b1);
+    k_contract_b1<<<dim3(cdiv(sh.max_m, 8 * 31), n_items), 256, 0, st>>>(pv, items, stride, design, b.uf, b.ub0, b.xe);
   } else {
     BPM_KERNEL(k_contract_generic);
     k_contract_generic<<<dim3(cdiv(sh.max_m, 256), n_items), 256, 0, st>>>(pv, items, stride, design, b.uf, b.ub0, b.xe);

@@ -194,6 +194,7 @@ class StageARunner:
         self.ws_bytes = int(self.lib.bpm_stage_a_workspace_bytes(M, n))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
         self.pcm_dev = torch.empty(self.total_in * self.channels, dtype=_torch_dtype(self.np_dtype), device=self.device)
+        self._pcm_src = self.pcm_dev          # what the kernels read: the device copy, or mapped pinned host memory
         self.outs_struct = nat.StageAOutputs(**{k: self.out[k].data_ptr() if k in self.out else None
                                                 for k, _ in nat.StageAOutputs._fields_})
 
@@ -210,11 +211,23 @@ class StageARunner:
     def upload_pinned(self, pinned: torch.Tensor) -> None:
         """One async H2D copy from a pinned host tensor holding the whole batch."""
         self.pcm_dev.copy_(pinned, non_blocking=True)
+        self._pcm_src = self.pcm_dev
+
+    def read_from_host(self, pinned: torch.Tensor) -> None:
+        """Zero-copy ingest: the kernels read the batch straight out of PINNED host memory.
+
+        Worth it in the reference's decimate-then-filter order, where only every ds-th frame is
+        ever touched: the sectors holding kept frames cross PCIe, not the whole recording.  The
+        tensor must stay alive (and unchanged) until the step has run.
+        """
+        if not pinned.is_pinned() or pinned.numel() != self.pcm_dev.numel() or pinned.dtype != self.pcm_dev.dtype:
+            raise ValueError("need a pinned host tensor with the batch's dtype and size")
+        self._pcm_src = pinned
 
     # -- compute
     def launch(self) -> None:
         """Enqueue a1..a4 on the current stream (no host synchronisation)."""
-        rc = self.lib.bpm_stage_a(_ptr(self.pcm_dev), _ptr(self.items_dev), _host_ptr(self.items), self.n_items,
+        rc = self.lib.bpm_stage_a(_ptr(self._pcm_src), _ptr(self.items_dev), _host_ptr(self.items), self.n_items,
                                   _ptr(self.design_dev), self.design_words, C.byref(self.cfg),
                                   C.byref(self.outs_struct), _ptr(self.ws), self.ws_bytes, _stream_ptr())
         nat.check(rc)
