@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--no-zero-copy", action="store_true", help="e2e: copy the whole recording to the device first")
     ap.add_argument("--dump-kernels", default=None, help="write the per-kernel table to this JSON file")
+    ap.add_argument("--workload", default="recordings", choices=["recordings", "stream"],
+                    help="recordings: one C2 recording per GPU (weak scaling, the headline). stream: ONE C2 "
+                         "recording split into halo-overlapped time chunks over the GPUs (strong scaling)")
     return ap.parse_args()
 
 
@@ -449,10 +452,107 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_stream(args):
+    """BASELINE configs[1] as it is worded: ONE 60-min stream, halo-chunked over the GPUs
+    (bpm_analysis_b200/stream.py).  Strong scaling: total work is fixed, every rank uploads
+    only the PCM frames of its chunk + halo; NCCL all-gathers the envelope chunks, the kept
+    trough lists and the floor chunks.  a1..a4 only (the beat-list reductions are replicated
+    work of a few hundred microseconds)."""
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from bpm_analysis_b200 import _native, stream
+    lib = _native.load_library()
+    params = bench_params(args)
+    pcm, sr, _ = make_recording(args, 0)                       # every rank: the SAME recording
+    comm = stream.DistComm()
+    eng = stream.DeviceEngine()
+    fe = stream.ChunkedFrontEnd(len(pcm), sr, params, comm, eng)
+    f0, f1 = fe.frames()
+    pcm_pin = torch.from_numpy(pcm[f0:f1].copy()).pin_memory()
+    pcm_dev = pcm_pin.to(dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    out = None
+    for _ in range(args.warmup):
+        out = fe.run(pcm_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = lib.bpm_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = fe.run(pcm_dev)
+    e1.record()
+    barrier()
+    launches = int(lib.bpm_launch_count() - l0)
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    audio_hours = args.duration_sec / 3600.0
+    value = audio_hours / (ms_step / 1e3)
+    # end to end: this rank's frames from pinned host memory, the full result back on every rank
+    host = {k: torch.empty_like(v, device="cpu").pin_memory() for k, v in out.items()}
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pcm_dev.copy_(pcm_pin, non_blocking=True)
+        out = fe.run(pcm_dev)
+        for k, v in out.items():
+            if host[k].numel() != v.numel():
+                host[k] = torch.empty_like(v, device="cpu").pin_memory()
+            host[k].copy_(v, non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    clocks = sampler.stop()
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "C2 as ONE stream: synthetic 60-min 48 kHz mono int16 recording, "
+                                       f"halo-chunked over {world} GPU(s)",
+                           "filter_mode": args.filter_mode, "raw_samples": len(pcm), "envelope_samples": fe.chunks.m,
+                           "halo_envelope_samples": fe.chunks.halo, "frames_this_rank": int(f1 - f0),
+                           "l2": "every step re-reads its PCM slice (%.1f MB)" % ((f1 - f0) * 2 / 1e6),
+                           "parallelism": f"time chunks over {world} ranks; all_gather(envelope, kept troughs, floor)"},
+                "clocks": clocks,
+                "e2e": {"value": audio_hours / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": int((f1 - f0) * 2),
+                        "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in out.values()))},
+                "gpu_launches": launches, "launch_mode": "eager (host reads list lengths between stages)",
+                "roofline": None, "cpu_baseline": None,
+                "result": {"troughs": int(out["troughs"].numel()), "peaks": int(out["peaks"].numel())}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "stream":
+        run_stream(args)
     else:
         run_b200(args)
 

@@ -65,6 +65,8 @@ _SIGNATURES = {
     "bpm_rolling_floor": (_I, [_P, _P, _P, _P, _P, _I, _I, _D, _P, _P, _Z, _P]),
     "bpm_noise_floor_workspace_bytes": (_Z, [_L, _I]),
     "bpm_noise_floor": (_I, [_P, _P, _P, _I, _I, _D, _D, _I, _D, _P, _P, _P, _P, _Z, _P]),
+    "bpm_sanitize_troughs_workspace_bytes": (_Z, [_L, _I]),
+    "bpm_sanitize_troughs": (_I, [_P, _P, _P, _P, _P, _P, _I, _D, _P, _P, _P, _Z, _P]),
     "bpm_raw_peaks_workspace_bytes": (_Z, [_L, _I]),
     "bpm_raw_peaks": (_I, [_P, _P, _P, _P, _I, _I, _D, _P, _P, _P, _Z, _P]),
     "bpm_peak_metrics": (_I, [_P, _P, _P, _P, _P, _P, _I, _D, _P, _P, _P, _P]),

@@ -157,6 +157,31 @@ int noise_floor_run(const double* env, const BpmItem* items, const BatchShape& s
   return BPM_OK;
 }
 
+// ------------------------------------------------------------------ K7 on its own
+// Used when a long recording is processed as halo-overlapped time chunks (stream.py): the draft
+// floor of a chunk exists only on the rank that owns it, so that rank sanitises its troughs.
+size_t sanitize_workspace_bytes(int64_t total_m, int n) {
+  Workspace ws(nullptr, 0);
+  ws.take<unsigned char>(total_m);
+  ws.take<int>(total_m / 2048 + n + 1);
+  return ws.used;
+}
+
+int sanitize_run(const double* env, const double* draft, const int64_t* troughs, const int64_t* trough_count,
+                 const BpmItem* items, const BatchShape& sh, double mult, int64_t* kept_out, int64_t* kept_count,
+                 Workspace& ws, cudaStream_t st) {
+  if (!env || !draft || !troughs || !trough_count || !items || !kept_out || !kept_count) return BPM_ERR_ARG;
+  unsigned char* keep = ws.take<unsigned char>(sh.total_m);
+  int* tile_counts = ws.take<int>(sh.total_m / 2048 + sh.n_items + 1);
+  if (ws.overflow) return BPM_ERR_WORKSPACE;
+  BPM_KERNEL(k_sanitize_flags);
+  k_sanitize_flags<<<dim3(cdiv(sh.max_m / 2 + 2, 256), sh.n_items), 256, 0, st>>>(env, draft, troughs, trough_count,
+                                                                                 nullptr, items, mult, keep);
+  BPM_LAUNCH_OK();
+  return compact_run(keep, troughs, items, sh, trough_count, sh.max_m / 2 + 2, false, tile_counts, kept_out,
+                     kept_count, st);
+}
+
 // ------------------------------------------------------------------ a3
 size_t raw_peaks_workspace_bytes(int64_t total_m, int n) {
   Workspace ws(nullptr, 0);
@@ -333,6 +358,18 @@ int bpm_noise_floor(const double* envelope, const BpmItem* items, const BpmItem*
   return noise_floor_run(envelope, items, batch_shape(items_host, n_items), distance, trough_prom_q, floor_q, window,
                          rejection_multiplier, floor_out, troughs_out, trough_count, nullptr, ws,
                          static_cast<cudaStream_t>(stream));
+}
+
+size_t bpm_sanitize_troughs_workspace_bytes(int64_t total_m, int n_items) { return sanitize_workspace_bytes(total_m, n_items); }
+
+int bpm_sanitize_troughs(const double* envelope, const double* draft_floor, const int64_t* troughs,
+                         const int64_t* trough_count, const BpmItem* items, const BpmItem* items_host, int n_items,
+                         double rejection_multiplier, int64_t* kept_out, int64_t* kept_count, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  if (!workspace || !items_host || n_items <= 0) return BPM_ERR_ARG;
+  Workspace ws(workspace, workspace_bytes);
+  return sanitize_run(envelope, draft_floor, troughs, trough_count, items, batch_shape(items_host, n_items),
+                      rejection_multiplier, kept_out, kept_count, ws, static_cast<cudaStream_t>(stream));
 }
 
 size_t bpm_raw_peaks_workspace_bytes(int64_t total_m, int n_items) { return raw_peaks_workspace_bytes(total_m, n_items); }

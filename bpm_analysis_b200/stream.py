@@ -1,0 +1,409 @@
+"""One long recording as halo-overlapped time chunks, one chunk per GPU.
+
+BASELINE configs[1] / [3]: a 60-min or 24-h stream is split into ``world`` contiguous time
+chunks.  Every stage of the front end has bounded support except two global scalars, so a
+rank needs its chunk plus a halo, and the ranks exchange three small things:
+
+  stage                       sharded?   needs from outside the chunk            exchange
+  --------------------------- ---------- --------------------------------------- ---------------------
+  a1 band-pass + envelope      yes        filter transient: ``halo`` kept samples  all_gather(envelope)
+     (bpm_analysis.py:1031-1054)          each side (rho^halo < 1e-22) + w/2
+  np.quantile (:1067, :225)    replicated whole envelope (8.7 MB at C2)            --
+  find_peaks(-env) (:1070)     replicated prominence walks are unbounded           --
+  draft floor (:1081-1086)     yes        the troughs around the chunk            --
+  sanitisation (:1090-1097)    yes        --                                      all_gather(kept troughs)
+  final floor (:1103-1106)     yes        the kept troughs around the chunk       all_gather(floor)
+  find_peaks(env, height=floor) replicated --                                      --
+  peak metrics (:93-100)       replicated window = f(total peak count)            --
+
+Exactness of the sharded rolling quantile: the floor of a chunk is computed on the sub-range
+[a0, a1) of the stream that starts AT a trough at least ``left + 1`` samples before the chunk
+and ends AT a trough at least ``off + 1`` samples after it (or at the stream's own ends).
+Inside such a range the interpolated trough series equals the global one sample for sample
+(np.interp between the same knots), and every window of the chunk's outputs lies inside it,
+so the chunk's floor is bit-identical to the unchunked computation, including the reference's
+NaN / bfill / ffill behaviour at the true ends of the stream.
+
+The numeric work is done by an *engine* (``DeviceEngine``: libbpm_b200 on CUDA tensors) and
+the exchange by a *communicator* (``DistComm``: torch.distributed, NCCL on GPUs;
+``ThreadComm``: ranks as threads of one process sharing one GPU, used by the tests).  The CPU
+tests drive the same planner with the oracle as the engine under gloo, world size 2.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import threading
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .dist import shard_range
+
+MIN_TROUGHS = 5          # bpm_analysis.py:1073
+MIN_KEPT = 2             # bpm_analysis.py:1102  (len > 2)
+FALLBACK_Q = 0.1         # bpm_analysis.py:1114
+
+
+# --------------------------------------------------------------------------- planning
+def filter_halo(spectral_radius: float, block: int, env_window: int, tol: float = 1e-22) -> int:
+    """Kept samples after which the transient of a chunk edge has decayed below ``tol``.
+
+    ``spectral_radius`` is per filter input sample and ``block`` the number of filter steps
+    per kept sample.  The forward-backward pass convolves two decays (k * rho^k), hence the
+    extra log term; the envelope's centred mean adds half its window.
+    """
+    rho = float(spectral_radius) ** int(block)
+    if not (0.0 < rho < 1.0):
+        return env_window + 16
+    k = math.log(tol) / math.log(rho)
+    k += math.log(max(k, 2.0)) / -math.log(rho)
+    return int(math.ceil(k)) + env_window + 16
+
+
+@dataclass(frozen=True)
+class ChunkPlan:
+    """Chunk geometry in envelope samples (kept samples) and PCM frames."""
+    n_frames: int        # N
+    m: int               # M = kept samples of the whole stream
+    frames_per_sample: int   # stride * block = ds
+    halo: int
+    world: int
+
+    def core(self, rank: int) -> Tuple[int, int]:
+        return shard_range(self.m, self.world, rank)
+
+    def ext(self, rank: int) -> Tuple[int, int]:
+        c0, c1 = self.core(rank)
+        return max(0, c0 - self.halo), min(self.m, c1 + self.halo)
+
+    def frames(self, rank: int) -> Tuple[int, int]:
+        """PCM frames rank ``rank`` has to supply: [f0, f1)."""
+        e0, e1 = self.ext(rank)
+        return e0 * self.frames_per_sample, min(self.n_frames, e1 * self.frames_per_sample)
+
+    def core_sizes(self) -> List[int]:
+        return [self.core(r)[1] - self.core(r)[0] for r in range(self.world)]
+
+
+def floor_item_range(knots: np.ndarray, c0: int, c1: int, window: int, m: int) -> Tuple[int, int]:
+    """Sub-range [a0, a1) of the stream on which the rolling quantile of outputs [c0, c1) is
+    bit-identical to the global computation (see module docstring).  ``knots`` ascending."""
+    off = (window - 1) // 2
+    left = window - 1 - off
+    a0, a1 = 0, m
+    if len(knots):
+        i = int(np.searchsorted(knots, c0 - left - 1, side="right")) - 1     # last knot <= c0-left-1
+        if i >= 0:
+            a0 = int(knots[i])
+        j = int(np.searchsorted(knots, c1 - 1 + off + 1, side="left"))        # first knot >= c1+off
+        if j < len(knots):
+            a1 = int(knots[j]) + 1
+    return a0, a1
+
+
+# --------------------------------------------------------------------------- communicators
+class DistComm:
+    """torch.distributed (NCCL on CUDA tensors, gloo on CPU tensors)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self._dist, self.group = dist, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def all_gather(self, t: torch.Tensor, sizes: Optional[Sequence[int]] = None) -> List[torch.Tensor]:
+        """Ragged all-gather of 1-D tensors: padded to the longest, sliced back by ``sizes``
+        (exchanged first when the caller does not know them)."""
+        if self.world == 1:
+            return [t]
+        dist = self._dist
+        if sizes is None:
+            n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+            ns = [torch.zeros_like(n) for _ in range(self.world)]
+            dist.all_gather(ns, n, group=self.group)
+            sizes = [int(x.item()) for x in ns]
+        cap = max(max(sizes), 1)
+        buf = torch.zeros(cap, dtype=t.dtype, device=t.device)
+        buf[:t.numel()] = t
+        out = torch.empty(self.world * cap, dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, buf, group=self.group)
+        return [out[r * cap:r * cap + s] for r, s in enumerate(sizes)]
+
+
+class ThreadComm:
+    """``world`` ranks as threads of one process (all on the current device): the exchange is
+    a barrier plus a shared slot list.  For tests and for trying a chunking on one GPU."""
+
+    class _Shared:
+        def __init__(self, world: int):
+            self.barrier = threading.Barrier(world)
+            self.slots: List[Optional[torch.Tensor]] = [None] * world
+
+    def __init__(self, shared: "ThreadComm._Shared", rank: int):
+        self.shared, self.rank, self.world = shared, rank, len(shared.slots)
+
+    @classmethod
+    def make_world(cls, world: int) -> List["ThreadComm"]:
+        sh = cls._Shared(world)
+        return [cls(sh, r) for r in range(world)]
+
+    def all_gather(self, t: torch.Tensor, sizes: Optional[Sequence[int]] = None) -> List[torch.Tensor]:
+        if t.is_cuda:
+            torch.cuda.current_stream().synchronize()
+        self.shared.slots[self.rank] = t
+        self.shared.barrier.wait()
+        out = [x.clone() for x in self.shared.slots]
+        self.shared.barrier.wait()
+        return out
+
+
+def run_thread_world(world: int, fn):
+    """Run ``fn(comm)`` on ``world`` threads; returns the per-rank results (re-raises errors)."""
+    comms = ThreadComm.make_world(world)
+    res: List[object] = [None] * world
+    errs: List[BaseException] = []
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else None
+
+    def body(r):
+        try:
+            if dev is not None:
+                torch.cuda.set_device(dev)
+            res[r] = fn(comms[r])
+        except BaseException as e:          # noqa: BLE001 - reported to the caller below
+            errs.append(e)
+            comms[r].shared.barrier.abort()
+
+    ts = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if errs:
+        raise errs[0]
+    return res
+
+
+# --------------------------------------------------------------------------- engine (CUDA)
+class DeviceEngine:
+    """The per-chunk numeric steps as libbpm_b200 calls on CUDA tensors (no numpy round trips)."""
+
+    def __init__(self):
+        from . import _native as nat
+        from . import runtime
+        self.nat, self.rt = nat, runtime
+        self.device = runtime.require_cuda()
+        self.lib = nat.load_library()
+
+    # helpers
+    def _ws(self, nbytes: int) -> torch.Tensor:
+        return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+
+    def _items(self, n_in: int, m: int):
+        items = self.rt.make_items([n_in], [m])
+        dev = torch.from_numpy(items.view(np.int64).reshape(-1, 4).copy()).to(self.device)
+        return items, dev
+
+    def tensor(self, a: np.ndarray) -> torch.Tensor:
+        return self.rt.to_device(np.asarray(a))
+
+    def full(self, n: int, value) -> torch.Tensor:
+        return torch.full((n,), float(value), dtype=torch.float64, device=self.device)
+
+    # a1 on a slice of the stream
+    def frontend(self, pcm: torch.Tensor, n_in: int, plan, channels: int, np_dtype) -> Tuple[torch.Tensor, torch.Tensor]:
+        rt, nat, L = self.rt, self.nat, self.lib
+        m = plan.m(n_in)
+        items, items_dev = self._items(n_in, m)
+        design = rt.design_on_device(plan)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        filt, env, amax = torch.empty(m, **f64), torch.empty(m, **f64), torch.empty(1, **f64)
+        nb = int(L.bpm_frontend_workspace_bytes(m, 1))
+        ws = self._ws(nb)
+        nat.check(L.bpm_frontend(rt._ptr(pcm), nat.PCM_DTYPES[np.dtype(np_dtype)], channels, rt._ptr(items_dev),
+                                 rt._host_ptr(items), 1, plan.stride, rt._ptr(design), int(design.numel()),
+                                 plan.rate // 10, rt._ptr(filt), rt._ptr(env), rt._ptr(amax), rt._ptr(ws), nb,
+                                 rt._stream_ptr()))
+        self._keep = (ws, items_dev)
+        return filt, env
+
+    def quantile(self, x: torch.Tensor, q: float) -> torch.Tensor:
+        rt, L = self.rt, self.lib
+        items, items_dev = self._items(x.numel(), x.numel())
+        out = torch.empty(1, dtype=torch.float64, device=self.device)
+        nb = int(L.bpm_quantile_workspace_bytes(1))
+        ws = self._ws(nb)
+        self.nat.check(L.bpm_quantile(rt._ptr(x), rt._ptr(items_dev), rt._host_ptr(items), 1, float(q), rt._ptr(out),
+                                      rt._ptr(ws), nb, rt._stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+        return out
+
+    def find_peaks(self, x: torch.Tensor, sign: int, height: Optional[torch.Tensor],
+                   prominence: Optional[torch.Tensor], distance: int) -> torch.Tensor:
+        rt, L = self.rt, self.lib
+        n = x.numel()
+        items, items_dev = self._items(n, n)
+        idx = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+        cnt = torch.empty(1, dtype=torch.int64, device=self.device)
+        nb = int(L.bpm_find_peaks_workspace_bytes(n, 1))
+        ws = self._ws(nb)
+        self.nat.check(L.bpm_find_peaks(rt._ptr(x), int(sign), rt._ptr(height), rt._ptr(prominence), int(distance),
+                                        rt._ptr(items_dev), rt._host_ptr(items), 1, rt._ptr(idx), rt._ptr(cnt),
+                                        rt._ptr(ws), nb, rt._stream_ptr()))
+        return idx[:int(cnt.cpu()[0])].clone()
+
+    def rolling_floor(self, env: torch.Tensor, knots: torch.Tensor, window: int, q: float) -> torch.Tensor:
+        rt, L = self.rt, self.lib
+        n = env.numel()
+        items, items_dev = self._items(n, n)
+        kbuf = torch.zeros(max(n, 1), dtype=torch.int64, device=self.device)
+        kbuf[:knots.numel()] = knots
+        kc = torch.tensor([knots.numel()], dtype=torch.int64, device=self.device)
+        out = torch.empty(n, dtype=torch.float64, device=self.device)
+        nb = int(L.bpm_rolling_floor_workspace_bytes(n, 1))
+        ws = self._ws(nb)
+        self.nat.check(L.bpm_rolling_floor(rt._ptr(env), rt._ptr(kbuf), rt._ptr(kc), rt._ptr(items_dev),
+                                           rt._host_ptr(items), 1, int(window), float(q), rt._ptr(out), rt._ptr(ws),
+                                           nb, rt._stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+        return out
+
+    def sanitize(self, env: torch.Tensor, draft: torch.Tensor, troughs: torch.Tensor, mult: float) -> torch.Tensor:
+        rt, L = self.rt, self.lib
+        n = env.numel()
+        items, items_dev = self._items(n, n)
+        tb = torch.zeros(max(n, 1), dtype=torch.int64, device=self.device)
+        tb[:troughs.numel()] = troughs
+        tc = torch.tensor([troughs.numel()], dtype=torch.int64, device=self.device)
+        kept = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+        kc = torch.empty(1, dtype=torch.int64, device=self.device)
+        nb = int(L.bpm_sanitize_troughs_workspace_bytes(n, 1))
+        ws = self._ws(nb)
+        self.nat.check(L.bpm_sanitize_troughs(rt._ptr(env), rt._ptr(draft), rt._ptr(tb), rt._ptr(tc),
+                                              rt._ptr(items_dev), rt._host_ptr(items), 1, float(mult), rt._ptr(kept),
+                                              rt._ptr(kc), rt._ptr(ws), nb, rt._stream_ptr()))
+        return kept[:int(kc.cpu()[0])].clone()
+
+    def peak_metrics(self, env: torch.Tensor, floor: torch.Tensor, peaks: torch.Tensor, factor: float):
+        rt, L = self.rt, self.lib
+        n = env.numel()
+        items, items_dev = self._items(n, n)
+        pk = torch.zeros(max(n, 1), dtype=torch.int64, device=self.device)
+        pk[:peaks.numel()] = peaks
+        cnt = torch.tensor([peaks.numel()], dtype=torch.int64, device=self.device)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        st, dv, sm = torch.empty(n, **f64), torch.empty(n, **f64), torch.empty(n, **f64)
+        self.nat.check(L.bpm_peak_metrics(rt._ptr(env), rt._ptr(floor), rt._ptr(pk), rt._ptr(cnt), rt._ptr(items_dev),
+                                          rt._host_ptr(items), 1, float(factor), rt._ptr(st), rt._ptr(dv), rt._ptr(sm),
+                                          rt._stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+        c = peaks.numel()
+        d = max(c - 1, 0)
+        return st[:c], dv[:d], sm[:d]
+
+
+# --------------------------------------------------------------------------- the chunked front end
+class ChunkedFrontEnd:
+    """a1..a4 of ONE recording, time-chunked over ``comm.world`` ranks.
+
+    Every rank constructs it with the same arguments, feeds the PCM frames ``frames()`` asks
+    for, and receives the full result (every rank ends up with the whole envelope, floor and
+    lists, which is what the sequential classifier that follows needs).
+    """
+
+    def __init__(self, n_frames: int, sample_rate: int, params: Dict, comm, engine, plan=None,
+                 pcm_dtype=np.int16, channels: int = 1):
+        if plan is None:
+            from .runtime import plan_filter
+            plan = plan_filter(sample_rate, params)
+        self.plan = plan
+        self.np_dtype, self.channels = np.dtype(pcm_dtype), int(channels)
+        self._common(plan.rate, params, comm, engine)
+        m = plan.m(int(n_frames))
+        halo = filter_halo(plan.design.spectral_radius, plan.block, plan.rate // 10)
+        self.chunks = ChunkPlan(int(n_frames), m, plan.stride * plan.block, halo, comm.world)
+        c0, c1 = self.chunks.core(comm.rank)
+        if c1 - c0 < 1:
+            raise ValueError("more ranks than envelope samples")
+
+    @classmethod
+    def for_envelope(cls, m: int, rate: int, params: Dict, comm, engine) -> "ChunkedFrontEnd":
+        """Only the analysis stages (``analyse``) on an envelope every rank already holds."""
+        self = cls.__new__(cls)
+        self.plan = None
+        self._common(int(rate), params, comm, engine)
+        self.chunks = ChunkPlan(int(m), int(m), 1, 0, comm.world)
+        return self
+
+    def _common(self, rate: int, params: Dict, comm, engine) -> None:
+        self.params, self.comm, self.engine, self.rate = params, comm, engine, rate
+        self.window = int(params["noise_window_sec"] * rate)                       # :1083
+        if self.window < 3:
+            raise ValueError(f"min_periods 3 must be <= window {self.window}")
+        self.distance = int(params["min_peak_distance_sec"] * rate)               # :226, :1066
+        if self.distance < 1:
+            raise ValueError("`distance` must be greater or equal to 1")
+
+    def frames(self) -> Tuple[int, int]:
+        return self.chunks.frames(self.comm.rank)
+
+    # -- a1
+    def envelope(self, pcm_slice) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Filter + envelope of this rank's frames -> (full envelope, this rank's filtered core)."""
+        ch, r = self.chunks, self.comm.rank
+        f0, f1 = ch.frames(r)
+        (c0, c1), (e0, _) = ch.core(r), ch.ext(r)
+        filt, env = self.engine.frontend(pcm_slice, f1 - f0, self.plan, self.channels, self.np_dtype)
+        core_env = env[c0 - e0:c1 - e0].contiguous()
+        parts = self.comm.all_gather(core_env, ch.core_sizes())
+        return torch.cat(parts), filt[c0 - e0:c1 - e0]
+
+    # -- a2 + a3 + a4 on a full envelope every rank holds
+    def _chunk_floor(self, env: torch.Tensor, knots_host: np.ndarray) -> Tuple[torch.Tensor, int, int]:
+        c0, c1 = self.chunks.core(self.comm.rank)
+        a0, a1 = floor_item_range(knots_host, c0, c1, self.window, self.chunks.m)
+        lo, hi = np.searchsorted(knots_host, [a0, a1])
+        local = self.engine.tensor(knots_host[lo:hi] - a0)
+        item = self.engine.rolling_floor(env[a0:a1], local, self.window, float(self.params["noise_floor_quantile"]))
+        return item, a0, a1
+
+    def analyse(self, env: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """_calculate_dynamic_noise_floor + _find_raw_peaks + metrics (bpm_analysis.py:1064-1117,
+        :223-229, :93-100) with the two rolling quantiles and the sanitisation sharded by chunk."""
+        E, P, ch, comm = self.engine, self.params, self.chunks, self.comm
+        c0, c1 = ch.core(comm.rank)
+        sizes = ch.core_sizes()
+        q_tp = E.quantile(env, float(P["trough_prominence_quantile"]))                            # :1067
+        all_troughs = E.find_peaks(env, -1, None, q_tp, self.distance)                            # :1070
+        if all_troughs.numel() < MIN_TROUGHS:                                                     # :1073-1077
+            floor = E.full(ch.m, float(E.quantile(env, float(P["noise_floor_quantile"]))[0]))
+            troughs = all_troughs
+        else:
+            knots = all_troughs.cpu().numpy()
+            draft_item, a0, a1 = self._chunk_floor(env, knots)                                    # :1081-1086
+            lo, hi = np.searchsorted(knots, [c0, c1])
+            mine = E.tensor(knots[lo:hi] - a0)
+            kept_local = E.sanitize(env[a0:a1], draft_item, mine,
+                                    float(P.get("trough_rejection_multiplier", 4.0)))             # :1090-1097
+            troughs = torch.cat(comm.all_gather(kept_local + a0))
+            if troughs.numel() > MIN_KEPT:                                                        # :1102-1106
+                floor_item, a0, a1 = self._chunk_floor(env, troughs.cpu().numpy())
+            else:                                                                                 # :1107-1110
+                floor_item = draft_item
+            floor = torch.cat(comm.all_gather(floor_item[c0 - a0:c1 - a0].contiguous(), sizes))
+            if bool(torch.isnan(floor).all()):                                                    # :1113-1115
+                floor = E.full(ch.m, float(E.quantile(env, FALLBACK_Q)[0]))
+        q_pp = q_tp if P["peak_prominence_quantile"] == P["trough_prominence_quantile"] else \
+            E.quantile(env, float(P["peak_prominence_quantile"]))                                 # :225
+        peaks = E.find_peaks(env, +1, floor, q_pp, self.distance)                                 # :227
+        strength, deviation, smoothed = E.peak_metrics(env, floor, peaks, float(P["deviation_smoothing_factor"]))
+        return {"envelope": env, "floor": floor, "troughs": troughs, "peaks": peaks, "strength": strength,
+                "deviation": deviation, "smoothed_dev": smoothed}
+
+    def run(self, pcm_slice) -> Dict[str, torch.Tensor]:
+        env, filt_core = self.envelope(pcm_slice)
+        out = self.analyse(env)
+        out["filtered_core"] = filt_core
+        return out

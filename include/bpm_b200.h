@@ -125,6 +125,17 @@ int bpm_noise_floor(const double* envelope, const BpmItem* items, const BpmItem*
                     double rejection_multiplier, double* floor_out, int64_t* troughs_out,
                     int64_t* trough_count, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- K7 on its own: trough sanitisation, bpm_analysis.py:1090-1097 -------------------
+ * kept = [t for t in troughs if not isnan(draft[t]) and envelope[t] <= mult * draft[t]].
+ * Needed separately when a long recording is split into halo-overlapped time chunks and
+ * the draft floor of a chunk lives on the rank that owns it (bpm_analysis_b200/stream.py).
+ *   troughs / kept_out: int64 lists at m_off; trough_count / kept_count: int64[n_items]. */
+size_t bpm_sanitize_troughs_workspace_bytes(int64_t total_m, int n_items);
+int bpm_sanitize_troughs(const double* envelope, const double* draft_floor, const int64_t* troughs,
+                         const int64_t* trough_count, const BpmItem* items, const BpmItem* items_host,
+                         int n_items, double rejection_multiplier, int64_t* kept_out,
+                         int64_t* kept_count, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a3: PeakClassifier._find_raw_peaks, bpm_analysis.py:223-229 ------------------- */
 size_t bpm_raw_peaks_workspace_bytes(int64_t total_m, int n_items);
 int bpm_raw_peaks(const double* envelope, const double* floor, const BpmItem* items,
