@@ -13,7 +13,7 @@ import threading
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbpm_b200.so")
+LIB_PATH = os.environ.get("BPM_B200_LIB") or os.path.join(HERE, "libbpm_b200.so")   # override: diagnostic builds
 ABI_VERSION = 1
 DESIGN_HEADER_WORDS = 312
 

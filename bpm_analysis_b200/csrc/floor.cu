@@ -669,49 +669,87 @@ __global__ void __launch_bounds__(RF_THREADS) k_rolling_floor(
 #undef RF_C
 
 // ---- block-cooperative path -----------------------------------------------------------------
-// A CTA owns RB_THREADS * run consecutive outputs.  It materialises the interpolated samples its
-// windows touch (n = outputs + window - 1 <= RB_NCAP) in shared memory and SORTS them by value
-// (sample sort: RB_G - 1 splitters from a sorted strided sample, counting sort into buckets,
-// then each sample counts the members of its small bucket that precede it), keeping perm[] (sorted order -> sample index) and
-// rank[] (sample index -> sorted position).  A coarse 2-D prefix table over (index chunk, rank
-// band) lets every thread place its first window's order statistic in O(log) steps.  After that
-// a thread slides over its run with a pointer p into the sorted order: the entering / leaving
-// sample changes the number of in-window entries before p by at most one each, and p walks a few
-// entries to the new order statistic.  Uniform O(1) work per output, all in shared memory, and
-// exact: the samples are the float64 np.interp values.
-constexpr int RB_THREADS = 256;
-constexpr int RB_NCAP = 6144;          // samples a CTA can stage
-constexpr int RB_G = 1024;             // sort buckets (RB_G - 1 splitters)
+// One CTA per SM (RB_THREADS threads, ~215 KB of shared memory) owns `outs` consecutive outputs;
+// the host sizes `outs` so that the grid is a whole number of waves of 148 CTAs.  The CTA
+//   S1  materialises the n = outs + window - 1 interpolated samples its windows touch in shared
+//       memory (float64 np.interp values, never written to HBM);
+//   S1b estimates a PIVOT value from 16 probe windows (128 strided samples each, the element of
+//       rank (q + margin) * 128): order statistic idx (and idx + 1) of every window of the tile
+//       is expected at or below it, so only the samples <= pivot ("kept", ~1/3 for q = 0.2) have
+//       to be sorted -- the others can never be the answer and only ever count as "above";
+//   S2/S3 sample-sorts the kept samples: splitters = the part of a sorted 2048-sample below the
+//       pivot, counting sort into buckets, exact order inside each (small) bucket by counting;
+//       keeps perm[] (sorted position -> sample) and rank[] (sample -> sorted position, 0xFFFF
+//       for samples above the pivot);
+//   S4  builds a coarse (index chunk x rank band) prefix table so that a thread can place the
+//       order statistic of its first window in O(log) steps;
+//   S5  every thread slides over its run of outputs with a pointer p into the sorted order: the
+//       entering / leaving sample changes the number of in-window entries before p by at most
+//       one each, and p walks a few entries to the new order statistic.
+// The pivot is validated lazily: if any walk runs off the end of the kept set (a window with
+// fewer than idx + 2 kept samples) the CTA repeats S2..S5 with pivot = +inf, i.e. sorts
+// everything.  Results are exact either way: the samples are the float64 np.interp values and
+// pandas' interpolation between the two order statistics is evaluated unfused.
+#ifndef BPM_RB_THREADS
+#define BPM_RB_THREADS 1024
+#endif
+constexpr int RB_THREADS = BPM_RB_THREADS;
+constexpr int RB_NCAP = RB_THREADS == 1024 ? 13312 : 14336;   // samples a CTA can stage (shared-memory budget)
+constexpr int RB_S = 2048;             // sorted sample the splitters come from (power of two)
 constexpr int RB_NSUP = 32;            // rank bands of the coarse table
-constexpr int RB_MAXCH = 224;          // index chunks of the coarse table
+constexpr int RB_CH = 32;              // samples per index chunk of the coarse table
+constexpr int RB_MAXCH = RB_NCAP / RB_CH;
+constexpr int RB_NPROBE = RB_THREADS / 32;
+constexpr int RB_CW = RB_S / 2 / (RB_THREADS / 32);   // bitonic compare-exchanges per warp and step
+constexpr int RB_PROBE_N = 64;         // samples per probe window (2 per lane)
+constexpr unsigned short RB_ABOVE = 0xFFFFu;
 
+struct RbSortPhase {
+  double piv[RB_S];                    // sorted splitter candidates, piv[RB_S-1] = +inf
+  unsigned int hist[RB_S];
+  unsigned short start[RB_S + 1];
+};
+struct RbSlidePhase {
+  unsigned short pc[RB_MAXCH + 1][RB_NSUP];       // kept samples with index < c*ch and band <= s
+  unsigned char ragged[RB_NSUP][RB_THREADS];      // per-thread band counts of a window's ragged ends (< 2 RB_CH)
+};
 struct RbShared {
   double d[RB_NCAP];
   unsigned short rank[RB_NCAP];        // bucket id while sorting, then position in sorted order
-  unsigned short perm[RB_NCAP];
-  unsigned short start[RB_G + 1];
-  unsigned int hist[RB_G];
+  unsigned short perm[RB_NCAP + 8];    // 8-byte aligned; [nk, nk+4) padded with RB_ABOVE for the 4-entry loads
   union {
-    double piv[RB_G];                                     // sorted splitters, piv[RB_G-1] = +inf
-    unsigned short pc[RB_MAXCH + 1][RB_NSUP];             // samples with index < c*ch and band <= s
+    RbSortPhase sort;
+    RbSlidePhase slide;
   } u;
-  unsigned short ragged[RB_NSUP][RB_THREADS];   // per-thread band counts of a window's ragged ends
-  double red[2 * (RB_THREADS / 32)];
+  unsigned long long pivot_key;        // max over the probes (order-preserving key of a double)
   int scan_tmp[40];
+  int fail;
+  int probes_ok;
+  int k_lo, k_hi;                      // knots around the tile's first / last sample
 };
 
-__global__ void __launch_bounds__(RB_THREADS) k_rolling_floor_blk(
+// in-window test on a perm entry: j in [a, a + span]  (RB_ABOVE never is: 65535 - a > span)
+__device__ __forceinline__ bool rb_in(unsigned int j, int a, unsigned int span) {
+  return (j - static_cast<unsigned int>(a)) <= span;
+}
+#ifdef BPM_DEBUG_COUNTERS
+#define RB_TICK(i) do { __syncthreads(); if (threadIdx.x == 0) { long long t_ = clock64(); atomicAdd(&g_dbg[i], (unsigned long long)(t_ - t_phase)); t_phase = t_; } } while (0)
+#else
+#define RB_TICK(i)
+#endif
+
+__global__ void __launch_bounds__(RB_THREADS, 1) k_rolling_floor_blk(
     const BpmItem* __restrict__ items, KnotTable kt, const FloorMeta* __restrict__ meta, int window, double q,
-    int run, const int* __restrict__ mode, const double* __restrict__ alt, const double* __restrict__ cval,
+    int outs, const int* __restrict__ mode, const double* __restrict__ alt, const double* __restrict__ cval,
     const double* __restrict__ nan_fill, double* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char rb_raw[];
   RbShared& sh = *reinterpret_cast<RbShared*>(rb_raw);
   const int item = blockIdx.y;
   const BpmItem it = items[item];
   const long long m = it.m;
-  const long long blk_first = static_cast<long long>(blockIdx.x) * RB_THREADS * run;
+  const long long blk_first = static_cast<long long>(blockIdx.x) * outs;
   if (blk_first >= m) return;
-  const long long blk_last = min(m, blk_first + static_cast<long long>(RB_THREADS) * run);   // exclusive
+  const long long blk_last = min(m, blk_first + static_cast<long long>(outs));   // exclusive
   double* o = out + it.m_off;
   const int tid = threadIdx.x;
   const int md = mode ? mode[item] : 0;
@@ -731,6 +769,9 @@ __global__ void __launch_bounds__(RB_THREADS) k_rolling_floor_blk(
     for (long long i = blk_first + tid; i < blk_last; i += RB_THREADS) o[i] = nanv;
     return;
   }
+#ifdef BPM_DEBUG_COUNTERS
+  long long t_phase = clock64();
+#endif
   WinCtx c;
   c.t = kt.t + it.m_off; c.v = kt.v + it.m_off; c.s = kt.slope + it.m_off; c.inv = kt.inv + it.m_off;
   c.e = kt.end + it.m_off;
@@ -750,11 +791,22 @@ __global__ void __launch_bounds__(RB_THREADS) k_rolling_floor_blk(
   const int n = x1 - x0 + 1;                                  // <= RB_NCAP (host guarantees)
 
   // ---- S1: interpolated samples -> shared memory
+  if (tid == 0) sh.k_lo = knot_at_or_before(c, x0);
+  if (tid == 32) sh.k_hi = knot_at_or_before(c, x1);
+  __syncthreads();
   {
     const int per = (n + RB_THREADS - 1) / RB_THREADS;
     const int j0 = tid * per, j1 = min(n, j0 + per);
     if (j0 < j1) {
-      int k = knot_at_or_before(c, x0 + j0);
+      int k = sh.k_lo;
+      {
+        int hi = sh.k_hi;                                     // last knot <= x0 + j0, searched inside the tile's knots
+        const int xi = x0 + j0;
+        while (k < hi) {
+          const int mid = (k + hi + 1) >> 1;
+          if (c.t[mid] <= xi) k = mid; else hi = mid - 1;
+        }
+      }
       for (int j = j0; j < j1; ++j) {
         const int x = x0 + j;
         while (k + 1 < c.T && c.t[k + 1] <= x) ++k;
@@ -762,72 +814,159 @@ __global__ void __launch_bounds__(RB_THREADS) k_rolling_floor_blk(
       }
     }
   }
-  for (int t = tid; t < RB_G; t += RB_THREADS) sh.hist[t] = 0;
+  if (tid == 0) { sh.pivot_key = 0ull; sh.fail = 0; sh.probes_ok = 1; }
   __syncthreads();
+  RB_TICK(0);
 
-  // ---- S2: splitters = sorted strided sample of the staged values; bucket ids; histogram
-  for (int t = tid; t < RB_G; t += RB_THREADS)
-    sh.u.piv[t] = (t < RB_G - 1) ? sh.d[static_cast<int>((static_cast<long long>(t) * (n - 1)) / (RB_G - 2))] : INFINITY;
-  __syncthreads();
-  for (int k2 = 2; k2 <= RB_G; k2 <<= 1) {                    // bitonic sort, RB_G / 2 compare-exchanges per step
-    for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-      for (int t = tid; t < RB_G / 2; t += RB_THREADS) {
-        const int lo_i = ((t / j2) * 2 * j2) + (t % j2);
-        const int hi_i = lo_i + j2;
-        const bool up = ((lo_i & k2) == 0);
-        const double x = sh.u.piv[lo_i], y = sh.u.piv[hi_i];
-        if ((x > y) == up) { sh.u.piv[lo_i] = y; sh.u.piv[hi_i] = x; }
+  // ---- S1b: pivot estimate.  Warp w probes the window of output ie0 + (2w+1)(ie1-ie0)/(2 NPROBE).
+  const double keep_frac = q + 0.15;
+  bool use_pivot = keep_frac < 0.8;
+  if (use_pivot) {
+    const int w = tid >> 5, lane = tid & 31;
+    const int ip = ie0 + static_cast<int>((static_cast<long long>(2 * w + 1) * (ie1 - ie0)) / (2 * RB_NPROBE));
+    int pb = ip + off; if (pb > mi - 1) pb = mi - 1;
+    int pa = ip - left; if (pa < 0) pa = 0; if (pa < t0) pa = t0;
+    const int nwp = pb - pa + 1;
+    if (nwp < 4 * RB_PROBE_N) {
+      if (lane == 0) sh.probes_ok = 0;                          // tiny windows: not worth a pivot
+    } else {
+      // ranks are taken on the high 32 bits of the order-preserving key (integer compares; an
+      // estimate does not need the low mantissa bits), ties broken by sample number
+      double mine[2];
+      unsigned int hk[2];
+      int below[2];
+#pragma unroll
+      for (int u2 = 0; u2 < 2; ++u2) {
+        const int k2 = lane * 2 + u2;
+        mine[u2] = sh.d[(pa - x0) + static_cast<int>((static_cast<long long>(k2) * (nwp - 1)) / (RB_PROBE_N - 1))];
+        hk[u2] = static_cast<unsigned int>(f64_key(mine[u2]) >> 32);
+        below[u2] = 0;
       }
-      __syncthreads();
-    }
-  }
-  for (int j = tid; j < n; j += RB_THREADS) {
-    // bucket = number of splitters strictly below the value (equal values share a bucket)
-    const double x = sh.d[j];
-    int lo_i = 0, hi_i = RB_G - 1;
-    while (lo_i < hi_i) {
-      const int mid = (lo_i + hi_i) >> 1;
-      if (sh.u.piv[mid] < x) lo_i = mid + 1; else hi_i = mid;
-    }
-    sh.rank[j] = static_cast<unsigned short>(lo_i);
-    atomicAdd(&sh.hist[lo_i], 1u);
-  }
-  __syncthreads();
-  // ---- S3: exclusive scan of the histogram -> start[], scatter (hist becomes the cursor),
-  //          order inside every bucket, inverse permutation
-  {
-    constexpr int PER = RB_G / RB_THREADS;
-    unsigned int loc[PER];
-    int sum = 0;
+      for (int src = 0; src < 32; ++src) {
 #pragma unroll
-    for (int u2 = 0; u2 < PER; ++u2) { loc[u2] = sh.hist[tid * PER + u2]; sum += loc[u2]; }
-    int total;
-    int ex = block_exclusive_scan(sum, &total, sh.scan_tmp);
+        for (int v2 = 0; v2 < 2; ++v2) {
+          const unsigned int y = __shfl_sync(0xffffffffu, hk[v2], src);
+          const int ky = src * 2 + v2;
 #pragma unroll
-    for (int u2 = 0; u2 < PER; ++u2) {
-      sh.start[tid * PER + u2] = static_cast<unsigned short>(ex);
-      sh.hist[tid * PER + u2] = ex;
-      ex += loc[u2];
+          for (int u2 = 0; u2 < 2; ++u2) {
+            const int k2 = lane * 2 + u2;
+            below[u2] += (y < hk[u2] || (y == hk[u2] && ky < k2)) ? 1 : 0;
+          }
+        }
+      }
+      int target = static_cast<int>(ceil(keep_frac * RB_PROBE_N));
+      if (target > RB_PROBE_N - 1) target = RB_PROBE_N - 1;
+#pragma unroll
+      for (int u2 = 0; u2 < 2; ++u2)
+        if (below[u2] == target) atomicMax(&sh.pivot_key, f64_key(mine[u2]));
     }
-    if (tid == RB_THREADS - 1) sh.start[RB_G] = static_cast<unsigned short>(ex);
   }
   __syncthreads();
-  for (int j = tid; j < n; j += RB_THREADS) {
-    const unsigned int pos = atomicAdd(&sh.hist[sh.rank[j]], 1u);
-    sh.perm[pos] = static_cast<unsigned short>(j);
-  }
-  __syncthreads();
-  // order inside the buckets by counting: final position = bucket start + #{bucket members that
-  // sort before this sample}.  Work is dealt out in bucket order (thread <-> scattered position),
-  // so the lanes of a warp walk the same bucket: equal trip counts, broadcast shared-memory reads.
-  {
-    constexpr int MAXPER = (RB_NCAP + RB_THREADS - 1) / RB_THREADS;
-    unsigned short fin[MAXPER];
-#pragma unroll 1
-    for (int u2 = 0, e = tid; e < n; e += RB_THREADS, ++u2) {
+  double pivot = INFINITY;
+  if (use_pivot && sh.probes_ok) pivot = key_f64(sh.pivot_key);
+  RB_TICK(1);
+
+  const int outs_here = static_cast<int>(blk_last - blk_first);
+  const int run = (outs_here + RB_THREADS - 1) / RB_THREADS;
+  const long long first = blk_first + static_cast<long long>(tid) * run;
+  const long long last = min(blk_last, first + run);
+
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    RbSortPhase& so = sh.u.sort;
+    // ---- S2: sorted sample of the staged values -> splitters below the pivot; bucket ids; histogram
+    for (int t = tid; t < RB_S; t += RB_THREADS) {
+      so.piv[t] = (t < RB_S - 1) ? sh.d[static_cast<int>((static_cast<long long>(t) * (n - 1)) / (RB_S - 2))] : INFINITY;
+      so.hist[t] = 0;
+    }
+    __syncthreads();
+    // bitonic sort; compare-exchange c of a step touches elements inside the (2 RB_CW)-element block
+    // of c / RB_CW whenever j2 <= RB_CW, so warp w owns CEs [RB_CW w, RB_CW (w+1)) and those steps
+    // only need __syncwarp
+    for (int k2 = 2; k2 <= RB_S; k2 <<= 1) {
+      for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+#pragma unroll
+        for (int h = 0; h < RB_S / 2 / RB_THREADS; ++h) {
+          const int t = (tid >> 5) * RB_CW + h * 32 + (tid & 31);
+          const int lo_i = ((t & ~(j2 - 1)) << 1) | (t & (j2 - 1));      // j2 is a power of two
+          const int hi_i = lo_i + j2;
+          const bool up = ((lo_i & k2) == 0);
+          const double x = so.piv[lo_i], y = so.piv[hi_i];
+          if ((x > y) == up) { so.piv[lo_i] = y; so.piv[hi_i] = x; }
+        }
+        if (j2 > RB_CW || (j2 == 1 && k2 > RB_CW)) __syncthreads(); else __syncwarp();
+      }
+    }
+    __syncthreads();
+    // usable splitters: piv[0 .. nsplit) are <= pivot (the +inf sentinel is never usable)
+    int nsplit;
+    {
+      int lo_i = 0, hi_i = RB_S - 1;
+      while (lo_i < hi_i) {
+        const int mid = (lo_i + hi_i) >> 1;
+        if (so.piv[mid] <= pivot) lo_i = mid + 1; else hi_i = mid;
+      }
+      nsplit = lo_i;                                           // in [0, RB_S - 1]
+    }
+    const int nbuckets = nsplit + 1;
+    RB_TICK(2);
+    for (int j = tid; j < n; j += RB_THREADS) {
+      const double x = sh.d[j];
+      unsigned short bk = RB_ABOVE;
+      if (x <= pivot) {
+        // bucket = number of usable splitters strictly below the value (equal values share a bucket)
+        int lo_i = 0, hi_i = nsplit;
+        while (lo_i < hi_i) {
+          const int mid = (lo_i + hi_i) >> 1;
+          if (so.piv[mid] < x) lo_i = mid + 1; else hi_i = mid;
+        }
+        bk = static_cast<unsigned short>(lo_i);
+        atomicAdd(&so.hist[lo_i], 1u);
+      }
+      sh.rank[j] = bk;
+    }
+    __syncthreads();
+    RB_TICK(3);
+    // ---- S3: exclusive scan of the histogram -> start[], scatter (hist becomes the cursor),
+    //          exact order inside every bucket, inverse permutation
+    int nk;
+    {
+      constexpr int PER = RB_S / RB_THREADS;
+      unsigned int loc[PER];
+      int sum = 0;
+#pragma unroll
+      for (int u2 = 0; u2 < PER; ++u2) {
+        const int b2 = tid * PER + u2;
+        loc[u2] = (b2 < nbuckets) ? so.hist[b2] : 0u;
+        sum += loc[u2];
+      }
+      int ex = block_exclusive_scan(sum, &nk, sh.scan_tmp);
+#pragma unroll
+      for (int u2 = 0; u2 < PER; ++u2) {
+        const int b2 = tid * PER + u2;
+        so.start[b2] = static_cast<unsigned short>(ex);
+        so.hist[b2] = ex;
+        ex += loc[u2];
+      }
+      if (tid == RB_THREADS - 1) so.start[RB_S] = static_cast<unsigned short>(ex);
+    }
+    __syncthreads();
+    for (int j = tid; j < n; j += RB_THREADS) {
+      const unsigned short bk = sh.rank[j];
+      if (bk != RB_ABOVE) {
+        const unsigned int pos = atomicAdd(&so.hist[bk], 1u);
+        sh.perm[pos] = static_cast<unsigned short>(j);
+      }
+    }
+    __syncthreads();
+    RB_TICK(4);
+    // order inside the buckets by counting: final position = bucket start + #{bucket members that
+    // sort before this sample}.  Work is dealt out in bucket order (thread <-> scattered position),
+    // so the lanes of a warp walk the same bucket: equal trip counts, broadcast shared-memory reads.
+    // Only the owner of sample j reads rank[j] (its bucket), so it can be overwritten in place.
+    for (int e = tid; e < nk; e += RB_THREADS) {
       const int j = sh.perm[e];
       const int g = sh.rank[j];
-      const int e0 = sh.start[g], e1 = sh.start[g + 1];
+      const int e0 = so.start[g], e1 = so.start[g + 1];
       const double x = sh.d[j];
       int before = 0;
       for (int f = e0; f < e1; ++f) {
@@ -835,130 +974,146 @@ __global__ void __launch_bounds__(RB_THREADS) k_rolling_floor_blk(
         const double dy = sh.d[y];
         before += (dy < x || (dy == x && y < j)) ? 1 : 0;
       }
-      fin[u2] = static_cast<unsigned short>(e0 + before);
+      sh.rank[j] = static_cast<unsigned short>(e0 + before);
     }
     __syncthreads();
-    // perm is rewritten in place: every thread first reads the sample ids it owns
-    unsigned short own[MAXPER];
-#pragma unroll 1
-    for (int u2 = 0, e = tid; e < n; e += RB_THREADS, ++u2) own[u2] = sh.perm[e];
-    __syncthreads();
-#pragma unroll 1
-    for (int u2 = 0, e = tid; e < n; e += RB_THREADS, ++u2) {
-      sh.rank[own[u2]] = fin[u2];
-      sh.perm[fin[u2]] = own[u2];
+    for (int j = tid; j < n; j += RB_THREADS) {
+      const unsigned short r2 = sh.rank[j];
+      if (r2 != RB_ABOVE) sh.perm[r2] = static_cast<unsigned short>(j);
     }
-  }
-  // ---- S4: coarse table over (index chunk, rank band)
-  int ch = run > 32 ? run : 32;
-  while ((n + ch - 1) / ch > RB_MAXCH) ch *= 2;
-  const int nch = (n + ch - 1) / ch;
-  int bshift = 0;
-  while (((n - 1) >> bshift) >= RB_NSUP) ++bshift;            // band = rank >> bshift  in [0, RB_NSUP)
-  for (int t = tid; t < (nch + 1) * RB_NSUP; t += RB_THREADS) (&sh.u.pc[0][0])[t] = 0;
-  __syncthreads();
-  for (int j = tid; j < n; j += RB_THREADS) {
-    // counts land one row down so that an inclusive column scan yields the exclusive prefix
-    unsigned short* cell = &sh.u.pc[j / ch + 1][sh.rank[j] >> bshift];
-    // 16-bit shared atomics do not exist: add into the containing 32-bit word
-    unsigned int* word = reinterpret_cast<unsigned int*>(reinterpret_cast<uintptr_t>(cell) & ~uintptr_t(3));
-    const unsigned int add = (reinterpret_cast<uintptr_t>(cell) & 2) ? (1u << 16) : 1u;
-    atomicAdd(word, add);
-  }
-  __syncthreads();
-  if (tid < RB_NSUP) {
-    unsigned int acc = 0;
-    for (int r2 = 0; r2 <= nch; ++r2) { acc += sh.u.pc[r2][tid]; sh.u.pc[r2][tid] = static_cast<unsigned short>(acc); }
-  }
-  __syncthreads();
-  for (int r2 = tid; r2 <= nch; r2 += RB_THREADS) {
-    unsigned int acc = 0;
-    for (int s2 = 0; s2 < RB_NSUP; ++s2) { acc += sh.u.pc[r2][s2]; sh.u.pc[r2][s2] = static_cast<unsigned short>(acc); }
-  }
-  __syncthreads();
+    if (tid < 8) sh.perm[nk + tid] = RB_ABOVE;
+    __syncthreads();                                           // sort phase of the union is dead from here
+    RB_TICK(5);
 
-  // ---- S5 / S6: every thread slides over its run
-  const long long first = blk_first + static_cast<long long>(tid) * run;
-  if (first >= blk_last) return;
-  const long long last = min(blk_last, first + run);
-  bool have = false;
-  int p = 0, cb = 0;            // position in sorted order; in-window entries at positions < p
-  double prev_out = 0.0;
-  int prev_i = -2, a_prev = 0, b_prev = 0;
-  for (long long io = first; io < last; ++io) {
-    int i = static_cast<int>(io);
-    if (i < mt.iv0) i = static_cast<int>(mt.iv0);
-    if (i > mt.iv1) i = static_cast<int>(mt.iv1);
-    if (i == prev_i) { o[io] = prev_out; continue; }
-    int bb = i + off; if (bb > mi - 1) bb = mi - 1;
-    int aa = i - left; if (aa < 0) aa = 0; if (aa < t0) aa = t0;
-    const int nw = bb - aa + 1;
-    const double fq = __dmul_rn(q, static_cast<double>(nw - 1));      // pandas: q * (nobs - 1)
-    const int idx = static_cast<int>(fq);
-    const double frac = __dsub_rn(fq, static_cast<double>(idx));
-    const int a = aa - x0, b = bb - x0;                        // local indices, inclusive
-    if (!have || i != prev_i + 1) {
-      // #{window samples in rank bands <= s}: whole chunks from the table + the ragged ends.
-      // The ragged ends are counted once into a per-thread band histogram (cumulated in place).
-      const int ca = (a + ch - 1) / ch;                        // first whole chunk
-      const int cbk = (b + 1) / ch;                            // one past the last whole chunk
-      unsigned short* rg = &sh.ragged[0][0] + tid;                   // [RB_NSUP][RB_THREADS]
-      for (int s2 = 0; s2 < RB_NSUP; ++s2) rg[s2 * RB_THREADS] = 0;
-      if (cbk > ca) {
-        for (int j = a; j < ca * ch; ++j) rg[(sh.rank[j] >> bshift) * RB_THREADS] += 1;
-        for (int j = cbk * ch; j <= b; ++j) rg[(sh.rank[j] >> bshift) * RB_THREADS] += 1;
-      } else {
-        for (int j = a; j <= b; ++j) rg[(sh.rank[j] >> bshift) * RB_THREADS] += 1;
-      }
-      {
-        unsigned int acc = 0;
-        for (int s2 = 0; s2 < RB_NSUP; ++s2) { acc += rg[s2 * RB_THREADS]; rg[s2 * RB_THREADS] = static_cast<unsigned short>(acc); }
-      }
-      auto cum = [&](int s_) -> int {
-        if (s_ < 0) return 0;
-        int cs_ = rg[s_ * RB_THREADS];
-        if (cbk > ca) cs_ += static_cast<int>(sh.u.pc[cbk][s_]) - static_cast<int>(sh.u.pc[ca][s_]);
-        return cs_;
-      };
-      int slo = 0, shi = RB_NSUP - 1;                          // smallest band with cum > idx
-      while (slo < shi) {
-        const int mid = (slo + shi) >> 1;
-        if (cum(mid) > idx) shi = mid; else slo = mid + 1;
-      }
-      p = slo << bshift;
-      cb = cum(slo - 1);
-      have = true;
-    } else {
-      if (b > b_prev) cb += (sh.rank[b] < p) ? 1 : 0;
-      if (a > a_prev) cb -= (sh.rank[a_prev] < p) ? 1 : 0;
+    // ---- S4: coarse table over (index chunk, rank band) of the kept samples
+    RbSlidePhase& sl = sh.u.slide;
+    constexpr int ch = RB_CH;
+    const int nch = (n + ch - 1) / ch;
+    int bshift = 0;
+    while (((nk > 0 ? nk - 1 : 0) >> bshift) >= RB_NSUP) ++bshift;   // band = rank >> bshift  in [0, RB_NSUP)
+    for (int t = tid; t < (nch + 1) * RB_NSUP; t += RB_THREADS) (&sl.pc[0][0])[t] = 0;
+    __syncthreads();
+    for (int j = tid; j < n; j += RB_THREADS) {
+      const unsigned short r2 = sh.rank[j];
+      if (r2 == RB_ABOVE) continue;
+      // counts land one row down so that an inclusive column scan yields the exclusive prefix
+      unsigned short* cell = &sl.pc[j / ch + 1][r2 >> bshift];
+      // 16-bit shared atomics do not exist: add into the containing 32-bit word
+      unsigned int* word = reinterpret_cast<unsigned int*>(reinterpret_cast<uintptr_t>(cell) & ~uintptr_t(3));
+      const unsigned int add = (reinterpret_cast<uintptr_t>(cell) & 2) ? (1u << 16) : 1u;
+      atomicAdd(word, add);
     }
-    // walk p to the in-window entry that has exactly idx in-window entries before it
-    while (cb > idx) {
-      --p;
-      const int j = sh.perm[p];
-      if (j >= a && j <= b) --cb;
+    __syncthreads();
+    if (tid < RB_NSUP) {
+      unsigned int acc = 0;
+      for (int r2 = 0; r2 <= nch; ++r2) { acc += sl.pc[r2][tid]; sl.pc[r2][tid] = static_cast<unsigned short>(acc); }
     }
-    while (true) {
-      const int j = sh.perm[p];
-      const bool in = (j >= a && j <= b);
-      if (in && cb == idx) break;
-      if (in) ++cb;
-      ++p;
+    __syncthreads();
+    for (int r2 = tid; r2 <= nch; r2 += RB_THREADS) {
+      unsigned int acc = 0;
+      for (int s2 = 0; s2 < RB_NSUP; ++s2) { acc += sl.pc[r2][s2]; sl.pc[r2][s2] = static_cast<unsigned short>(acc); }
     }
-    const double vlow = sh.d[sh.perm[p]];
-    double res = vlow;
-    if (fq != static_cast<double>(idx)) {
-      int p2 = p + 1;
-      while (true) {                                           // next in-window entry (idx + 1 < nw here)
-        const int j = sh.perm[p2];
-        if (j >= a && j <= b) break;
-        ++p2;
+    __syncthreads();
+    RB_TICK(6);
+
+    // ---- S5: every thread slides over its run
+    bool failed = false;
+    if (first < blk_last) {
+      bool have = false;
+      int p = 0, cb = 0;            // position in sorted order; in-window entries at positions < p
+      double prev_out = 0.0;
+      int prev_i = -2, a_prev = 0, b_prev = 0;
+      for (long long io = first; io < last && !failed; ++io) {
+        int i = static_cast<int>(io);
+        if (i < mt.iv0) i = static_cast<int>(mt.iv0);
+        if (i > mt.iv1) i = static_cast<int>(mt.iv1);
+        if (i == prev_i) { o[io] = prev_out; continue; }
+        int bb = i + off; if (bb > mi - 1) bb = mi - 1;
+        int aa = i - left; if (aa < 0) aa = 0; if (aa < t0) aa = t0;
+        const int nw = bb - aa + 1;
+        const double fq = __dmul_rn(q, static_cast<double>(nw - 1));      // pandas: q * (nobs - 1)
+        const int idx = static_cast<int>(fq);
+        const double frac = __dsub_rn(fq, static_cast<double>(idx));
+        const int a = aa - x0, b = bb - x0;                        // local indices, inclusive
+        if (!have || i != prev_i + 1) {
+          // #{kept window samples in rank bands <= s}: whole chunks from the table + the ragged ends.
+          // The ragged ends are counted once into a per-thread band histogram (cumulated in place).
+          const int ca = (a + ch - 1) / ch;                        // first whole chunk
+          const int cbk = (b + 1) / ch;                            // one past the last whole chunk
+          unsigned char* rg = &sl.ragged[0][0] + tid;              // [RB_NSUP][RB_THREADS]
+          for (int s2 = 0; s2 < RB_NSUP; ++s2) rg[s2 * RB_THREADS] = 0;
+          auto tally = [&](int j) {
+            const unsigned short r2 = sh.rank[j];
+            if (r2 != RB_ABOVE) rg[(r2 >> bshift) * RB_THREADS] += 1;
+          };
+          if (cbk > ca) {
+            for (int j = a; j < ca * ch; ++j) tally(j);
+            for (int j = cbk * ch; j <= b; ++j) tally(j);
+          } else {
+            for (int j = a; j <= b; ++j) tally(j);
+          }
+          {
+            unsigned int acc = 0;
+            for (int s2 = 0; s2 < RB_NSUP; ++s2) { acc += rg[s2 * RB_THREADS]; rg[s2 * RB_THREADS] = static_cast<unsigned char>(acc); }
+          }
+          auto cum = [&](int s_) -> int {
+            if (s_ < 0) return 0;
+            int cs_ = rg[s_ * RB_THREADS];
+            if (cbk > ca) cs_ += static_cast<int>(sl.pc[cbk][s_]) - static_cast<int>(sl.pc[ca][s_]);
+            return cs_;
+          };
+          int slo = 0, shi = RB_NSUP - 1;                          // smallest band with cum > idx
+          while (slo < shi) {
+            const int mid = (slo + shi) >> 1;
+            if (cum(mid) > idx) shi = mid; else slo = mid + 1;
+          }
+          p = slo << bshift;
+          cb = cum(slo - 1);
+          have = true;
+        } else {
+          if (b > b_prev) cb += (sh.rank[b] < p) ? 1 : 0;          // RB_ABOVE is never < p
+          if (a > a_prev) cb -= (sh.rank[a_prev] < p) ? 1 : 0;
+        }
+        // walk p to the in-window entry that has exactly idx in-window entries before it
+        const unsigned int span = static_cast<unsigned int>(b - a);
+        while (cb > idx) {
+          --p;
+          if (rb_in(sh.perm[p], a, span)) --cb;
+        }
+        while (true) {
+          const bool in = rb_in(sh.perm[p], a, span);              // perm[nk] is RB_ABOVE: never in
+          if (in && cb == idx) break;
+          if (p >= nk) { failed = true; break; }                   // fewer than idx+1 kept samples in this window
+          if (in) ++cb;
+          ++p;
+        }
+        if (failed) break;
+        const double vlow = sh.d[sh.perm[p]];
+        double res = vlow;
+        if (fq != static_cast<double>(idx)) {
+          int p2 = p + 1;
+          while (!rb_in(sh.perm[p2], a, span)) {                   // next in-window entry (idx + 1 < nw here)
+            if (p2 >= nk) { failed = true; break; }
+            ++p2;
+          }
+          if (failed) break;
+          const double vhigh = sh.d[sh.perm[p2]];
+          res = __dadd_rn(vlow, __dmul_rn(__dsub_rn(vhigh, vlow), frac));
+        }
+        o[io] = res;
+        prev_out = res; prev_i = i; a_prev = a; b_prev = b;
       }
-      const double vhigh = sh.d[sh.perm[p2]];
-      res = __dadd_rn(vlow, __dmul_rn(__dsub_rn(vhigh, vlow), frac));
     }
-    o[io] = res;
-    prev_out = res; prev_i = i; a_prev = a; b_prev = b;
+    if (failed) sh.fail = 1;
+    __syncthreads();
+    RB_TICK(7);
+    if (!sh.fail) break;
+    // the pivot was too low for some window: sort everything (attempt 1 cannot fail)
+    DBG(15);
+    __syncthreads();
+    if (tid == 0) sh.fail = 0;
+    pivot = INFINITY;
+    __syncthreads();
   }
 }
 
@@ -1033,22 +1188,25 @@ int rolling_floor_run(const double* env, const int64_t* knots, const int64_t* kn
   k_knot_table<<<dim3(cdiv(max_k, 256), sh.n_items), 256, 0, st>>>(env, knots, knot_count, items, window,
                                                                     b.kt32, b.kv, b.ks, b.kinv, b.kend, b.meta);
   BPM_LAUNCH_OK();
-  // outputs per thread: long enough to amortise the bisection, short enough to fill the GPU
+  // outputs per thread of the per-thread kernel: long enough to amortise the bisection
   int64_t run = sh.total_m / (148 * 1024);
   if (run < 48) run = 48;
   if (run > 512) run = 512;
   if (sh.max_m >= (1ll << 31)) return BPM_ERR_ARG;
   KnotTable kt{b.kt32, b.kv, b.ks, b.kinv, b.kend};
   // block-cooperative kernel when a CTA can stage its windows' samples; else the per-thread kernel
-  if (window + RB_THREADS <= RB_NCAP) {
-    int64_t rb = (RB_NCAP - window + 1) / RB_THREADS;
-    if (rb > 64) rb = 64;
-    // keep the grid large enough to fill the GPU on a single recording
-    while (rb > 8 && sh.total_m / (RB_THREADS * rb) < 2 * 148) rb /= 2;
+  const int64_t max_outs = static_cast<int64_t>(RB_NCAP) - window + 1;
+  if (max_outs >= RB_THREADS) {
+    // one CTA per SM: size the tiles so that the grid is a whole number of waves
+    const int64_t sms = 148;
+    const int64_t waves = (sh.total_m + sms * max_outs - 1) / (sms * max_outs);
+    int64_t outs = (sh.total_m + sms * waves - 1) / (sms * waves);
+    if (outs < RB_THREADS) outs = RB_THREADS;
+    if (outs > max_outs) outs = max_outs;
     cudaFuncSetAttribute(k_rolling_floor_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(RbShared)));
     BPM_KERNEL(k_rolling_floor_blk);
-    k_rolling_floor_blk<<<dim3(cdiv(sh.max_m, RB_THREADS * rb), sh.n_items), RB_THREADS, sizeof(RbShared), st>>>(
-        items, kt, b.meta, window, q, static_cast<int>(rb), mode, alt, cval, nan_fill, out);
+    k_rolling_floor_blk<<<dim3(cdiv(sh.max_m, outs), sh.n_items), RB_THREADS, sizeof(RbShared), st>>>(
+        items, kt, b.meta, window, q, static_cast<int>(outs), mode, alt, cval, nan_fill, out);
     BPM_LAUNCH_OK();
     return BPM_OK;
   }

@@ -155,6 +155,27 @@ def test_rolling_floor_matches_pandas(m, window, q, gap, ops):
     assert rel_err(got, ref) < TOL
 
 
+@pytest.mark.parametrize("m,window,q,burst", [(400000, 3010, 0.2, False), (400000, 3010, 0.2, True),
+                                              (300000, 6660, 0.3, True), (250000, 1505, 0.1, True),
+                                              (120000, 13000, 0.2, True)])
+def test_rolling_floor_bit_exact_multi_tile(m, window, q, burst, ops):
+    """Several CTAs per recording, heavy-tailed knot values and (burst=True) level jumps inside
+    a tile, which defeat the pivot estimate and force the sort-everything repeat.  The result
+    must be pandas' bit for bit either way."""
+    rng = np.random.default_rng(m + window)
+    level = np.ones(m)
+    if burst:
+        for _ in range(12):
+            s0 = int(rng.integers(0, m - 5000))
+            level[s0:s0 + int(rng.integers(200, 9000))] *= float(rng.choice([0.05, 8.0, 40.0]))
+    env = (np.abs(rng.standard_normal(m)) ** 3 + 0.05) * level
+    knots = np.unique(np.sort(rng.integers(40, m - 40, m // 85)))
+    s = pd.Series(index=knots, data=env[knots]).reindex(np.arange(m)).interpolate()
+    ref = s.rolling(window=window, min_periods=3, center=True).quantile(q).bfill().ffill().values
+    got = ops.rolling_floor(env, knots, window, q)
+    assert np.array_equal(got, ref)
+
+
 # ----------------------------------------------------------------------------- a2, a3, a4 on reference envelopes
 @pytest.mark.parametrize("name", ["vulpine"] + ["synth_" + s for s in SYNTH])
 def test_noise_floor_and_peaks_on_reference_envelope(name, fe, ref_params):

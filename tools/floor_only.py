@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Runs the noise-floor stage (a2) a few times on the C2 envelope: a short command for ncu.
+
+    python tools/floor_only.py [duration_sec] [repeats]
+"""
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+
+def main():
+    import torch
+    from bpm_analysis_b200 import synth
+    from bpm_analysis_b200.params import default_params
+    from bpm_analysis_b200.runtime import StageARunner
+    dur = float(sys.argv[1]) if len(sys.argv) > 1 else 3600.0
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    p = default_params()
+    p["save_filtered_wav"] = False
+    if len(sys.argv) > 3:
+        p["filter_mode"] = sys.argv[3]
+    pcm, sr, _ = synth.config_c2(seed=2, duration_sec=dur)
+    A = StageARunner([len(pcm)], sr, p)
+    A.upload([pcm])
+    for _ in range(reps):
+        A.launch()
+    torch.cuda.synchronize()
+    print("ok", int(A.out["peak_count"][0]))
+
+
+if __name__ == "__main__":
+    main()
