@@ -286,6 +286,37 @@ class DeviceEngine:
                                               rt._ptr(kc), rt._ptr(ws), nb, rt._stream_ptr()))
         return kept[:int(kc.cpu()[0])].clone()
 
+    def noise_floor(self, env: torch.Tensor, distance: int, window: int, params: Dict):
+        """a2 whole (bpm_noise_floor) on a device envelope -> (floor, kept troughs)."""
+        rt, L = self.rt, self.lib
+        n = env.numel()
+        items, items_dev = self._items(n, n)
+        floor = torch.empty(n, dtype=torch.float64, device=self.device)
+        tr = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+        cnt = torch.empty(1, dtype=torch.int64, device=self.device)
+        nb = int(L.bpm_noise_floor_workspace_bytes(n, 1))
+        ws = self._ws(nb)
+        self.nat.check(L.bpm_noise_floor(rt._ptr(env), rt._ptr(items_dev), rt._host_ptr(items), 1, int(distance),
+                                         float(params["trough_prominence_quantile"]),
+                                         float(params["noise_floor_quantile"]), int(window),
+                                         float(params.get("trough_rejection_multiplier", 4.0)), rt._ptr(floor),
+                                         rt._ptr(tr), rt._ptr(cnt), rt._ptr(ws), nb, rt._stream_ptr()))
+        return floor, tr[:int(cnt.cpu()[0])].clone()
+
+    def raw_peaks(self, env: torch.Tensor, floor: torch.Tensor, distance: int, prom_q: float) -> torch.Tensor:
+        """a3 (bpm_raw_peaks) on device tensors."""
+        rt, L = self.rt, self.lib
+        n = env.numel()
+        items, items_dev = self._items(n, n)
+        pk = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+        cnt = torch.empty(1, dtype=torch.int64, device=self.device)
+        nb = int(L.bpm_raw_peaks_workspace_bytes(n, 1))
+        ws = self._ws(nb)
+        self.nat.check(L.bpm_raw_peaks(rt._ptr(env), rt._ptr(floor), rt._ptr(items_dev), rt._host_ptr(items), 1,
+                                       int(distance), float(prom_q), rt._ptr(pk), rt._ptr(cnt), rt._ptr(ws), nb,
+                                       rt._stream_ptr()))
+        return pk[:int(cnt.cpu()[0])].clone()
+
     def peak_metrics(self, env: torch.Tensor, floor: torch.Tensor, peaks: torch.Tensor, factor: float):
         rt, L = self.rt, self.lib
         n = env.numel()
