@@ -180,38 +180,6 @@ __global__ void __launch_bounds__(256) k_contract_generic(PcmView pcm, const Bpm
   reinterpret_cast<double2*>(pb)[1] = make_double2(b[2], b[3]);
 }
 
-// ------------------------------------------------------------ contraction (block == 1)
-// The reference's decimate-then-filter order: each kept sample is one strided PCM frame, so
-// uf[j] = wf[0] x_j and ub0[j] = q[0] x_j + q[1] x_{j+1}.  Every thread loads ONE frame and
-// gets its right neighbour's by shuffle -- the PCM buffer may be mapped pinned HOST memory
-// (zero-copy ingest: only the sectors holding kept frames cross PCIe).
-__global__ void __launch_bounds__(256) k_contract_b1(PcmView pcm, const BpmItem* __restrict__ items, int64_t stride,
-                                                     const double* __restrict__ design, double* __restrict__ uf,
-                                                     double* __restrict__ ub0, double* __restrict__ xe) {
-  const BpmItem it = items[blockIdx.y];
-  // a warp covers 31 outputs + 1 shared neighbour so that every interior frame is loaded once
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_global = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t j = warp_global * 31 + lane;
-  if (warp_global * 31 >= it.m) return;
-  const DesignView d{design};
-  const ExtSignal x = make_ext(pcm, it, stride);
-  const bool valid = j < it.m;
-  const double v = valid ? x.at(PADLEN + j) : 0.0;
-  const double vn = __shfl_down_sync(0xffffffffu, v, 1);
-  if (!valid || lane == 31) return;
-  xe[it.m_off + j] = v;
-  if (j >= it.m - 1) return;
-  const double* __restrict__ wf = d.wf();
-  const double* __restrict__ q = d.q();
-  double2* pf = reinterpret_cast<double2*>(uf + 4 * (it.m_off + j));
-  double2* pb = reinterpret_cast<double2*>(ub0 + 4 * (it.m_off + j));
-  pf[0] = make_double2(wf[0] * v, wf[1] * v);
-  pf[1] = make_double2(wf[2] * v, wf[3] * v);
-  pb[0] = make_double2(q[0] * v + q[4] * vn, q[1] * v + q[5] * vn);
-  pb[1] = make_double2(q[2] * v + q[6] * vn, q[3] * v + q[7] * vn);
-}
-
 // ------------------------------------------------------ contraction (int16, full rate)
 // The HBM-bound kernel: mono int16 at the original rate (stride 1), block = ds.
 //   * a CTA owns CT_BLOCKS consecutive blocks; one elected thread brings their PCM span into
@@ -443,24 +411,66 @@ __global__ void __launch_bounds__(32 * FE_WARPS) k_filter_tail(PcmView pcm, cons
 }
 
 // ------------------------------------------------------------------ low-rate scans
+// One pass per direction.  A CTA scans its tile locally, PUBLISHES the tile aggregate (4 doubles
+// + a flag), then looks back over the K preceding tiles' aggregates -- the recurrence contracts,
+// so K = 1..4 tiles reach 1e-22 and older history is dropped -- and applies the resulting start
+// state.  Tiles only ever wait for tiles with a smaller block index (already resident or done),
+// so the spin cannot deadlock.  SRC == 1 is the reference's decimate-then-filter order (block
+// == 1): the 4-vectors uf / ub0 are two multiplies per sample and are formed on the fly -- the
+// forward pass gathers the strided PCM frames itself (device memory or mapped pinned host
+// memory) and leaves them in xe for the backward pass; nothing else is staged in HBM.
 struct ScanParams {
   const BpmItem* items;
   const double* design;
-  const double* u;        // FWD: uf       BWD: ub0
+  const double* u;        // SRC 0 -- FWD: uf, BWD: ub0
   double* sf;             // FWD: out      BWD: in
-  const double* xe;       // BWD only
+  double* xe;             // kept input samples: read (SRC 0, BWD) or written by FWD (SRC 1)
   const double* s_init;   // FWD: s0[item] BWD: sb_last[item]
   double* agg;            // tile aggregates [tile_slot][4]
-  double* y;              // BWD apply: filtered signal out
-  unsigned long long* absmax_bits;  // BWD apply: max |y| per item (bit pattern of a non-negative double)
+  int* flags;             // [tile_slot]: 1 once agg is visible
+  double* y;              // BWD: filtered signal out
+  unsigned long long* absmax_bits;  // BWD: max |y| per item (bit pattern of a non-negative double)
+  PcmView pcm;            // SRC 1, FWD
+  int64_t stride;
 };
 
 __device__ __forceinline__ int64_t tile_slot0(const BpmItem& it, int item) {
   return it.m_off / SCAN_TILE + item;
 }
 
-template <int DIR /*0 fwd, 1 bwd*/, bool APPLY>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan(ScanParams p) {
+// input term of sample r of this item's scan (and, backward, the forward-pass output y_f there)
+template <int DIR, int SRC>
+__device__ __forceinline__ void scan_input(const ScanParams& p, const BpmItem& it, const double* __restrict__ sm_P,
+                                           const double* __restrict__ sm_C, double Dd, const double* __restrict__ w0,
+                                           const double* __restrict__ w1, int64_t r, double u[4], double* yf) {
+  const int64_t j = (DIR == 0) ? r : (it.m - 2 - r);
+  if (SRC == 0) {
+    const double2* pu = reinterpret_cast<const double2*>(p.u + 4 * (it.m_off + j));
+    const double2 a = pu[0], bb = pu[1];
+    u[0] = a.x; u[1] = a.y; u[2] = bb.x; u[3] = bb.y;
+  } else if (DIR == 0) {
+    const double xj = p.xe[it.m_off + j];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = w0[k] * xj;
+  } else {
+    const double xj = p.xe[it.m_off + j], xn = p.xe[it.m_off + j + 1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = w0[k] * xj + w1[k] * xn;
+  }
+  if (DIR == 1) {
+    const double2* ps = reinterpret_cast<const double2*>(p.sf + 4 * (it.m_off + j));
+    const double2 s01 = ps[0], s23 = ps[1];
+    const double sv[4] = {s01.x, s01.y, s23.x, s23.y};
+    double t4[4];
+    matvec4(sm_P, sv, t4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] += t4[k];
+    *yf = sm_C[0] * sv[0] + sm_C[1] * sv[1] + sm_C[2] * sv[2] + sm_C[3] * sv[3] + Dd * p.xe[it.m_off + j];
+  }
+}
+
+template <int DIR /*0 fwd, 1 bwd*/, int SRC /*0 staged uf/ub0, 1 block == 1 on the fly*/>
+__global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan(ScanParams p) {
   __shared__ double sm_pow[9 * 16];      // Ad^(CHUNK*2^k), k = 0..8
   __shared__ double sm_Ad[16], sm_P[16], sm_C[4];
   __shared__ double sm_tot[SCAN_THREADS / 32][4];
@@ -474,7 +484,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(ScanParams p) {
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * SCAN_TILE;
   const double Dd = d.D();
 
-  if (APPLY && blockIdx.x == 0 && tid == 0) {
+  if (blockIdx.x == 0 && tid == 0) {
     // the state that needs no step: s_f[0], or y[m-1] from s_b[m-1]
     const double* si = p.s_init + 4 * item;
     if (DIR == 0) {
@@ -498,47 +508,42 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(ScanParams p) {
   __syncthreads();
 
   const int64_t rbeg = r0 + static_cast<int64_t>(tid) * SCAN_CHUNK;
-  double u[SCAN_CHUNK][4];
-  double yfv[SCAN_CHUNK];
-  double z[4] = {0, 0, 0, 0};
-  double start[4] = {0, 0, 0, 0};
-
-  if (APPLY && tid == 0) {
-    // look back over the preceding tiles' aggregates (contraction makes older ones vanish)
-    const int64_t b = blockIdx.x;
-    const int64_t K = d.lookback();
-    const int64_t k0 = (b > K) ? b - K : 0;
-    const double* si = p.s_init + 4 * item;
-    if (k0 == 0) {
+  double w0[4] = {0, 0, 0, 0}, w1[4] = {0, 0, 0, 0};
+  if (SRC == 1) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) start[c] = si[c];
+    for (int k = 0; k < 4; ++k) {
+      w0[k] = (DIR == 0) ? d.wf()[k] : d.q()[k];
+      w1[k] = (DIR == 0) ? 0.0 : d.q()[4 + k];
     }
-    const double* ag = p.agg + 4 * tile_slot0(it, item);
-    for (int64_t t = k0; t < b; ++t) affine4(sm_pow + 8 * 16, start, ag + 4 * t);
+  }
+  if (SRC == 1 && DIR == 0) {
+    // gather this thread's strided frames: SCAN_CHUNK independent loads in flight; they stay in
+    // xe for the second sweep below and for the backward pass
+    const ExtSignal x = make_ext(p.pcm, it, p.stride);
+    double xv[SCAN_CHUNK];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) z[c] = start[c];
+    for (int c = 0; c < SCAN_CHUNK; ++c) {
+      const int64_t r = rbeg + c;
+      xv[c] = (r < ns) ? x.at(PADLEN + r) : 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < SCAN_CHUNK; ++c) {
+      const int64_t r = rbeg + c;
+      if (r < ns) p.xe[it.m_off + r] = xv[c];
+      if (r == ns - 1) p.xe[it.m_off + it.m - 1] = x.at(PADLEN + it.m - 1);
+    }
   }
 
+  // ---- sweep 1: aggregate of this thread's chunk from a zero state (inputs are not kept in
+  //      registers: sweep 2 re-reads them through L1 / L2, which keeps three CTAs per SM resident)
+  double z[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int c = 0; c < SCAN_CHUNK; ++c) {
     const int64_t r = rbeg + c;
     if (r < ns) {
-      const int64_t j = (DIR == 0) ? r : (it.m - 2 - r);
-      const double2* pu = reinterpret_cast<const double2*>(p.u + 4 * (it.m_off + j));
-      const double2 a = pu[0], bb = pu[1];
-      u[c][0] = a.x; u[c][1] = a.y; u[c][2] = bb.x; u[c][3] = bb.y;
-      if (DIR == 1) {
-        const double2* ps = reinterpret_cast<const double2*>(p.sf + 4 * (it.m_off + j));
-        const double2 s01 = ps[0], s23 = ps[1];
-        const double sv[4] = {s01.x, s01.y, s23.x, s23.y};
-        double t4[4];
-        matvec4(sm_P, sv, t4);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) u[c][k] += t4[k];
-        if (APPLY)
-          yfv[c] = sm_C[0] * sv[0] + sm_C[1] * sv[1] + sm_C[2] * sv[2] + sm_C[3] * sv[3] + Dd * p.xe[it.m_off + j];
-      }
-      affine4(sm_Ad, z, u[c]);
+      double u[4], yf;
+      scan_input<DIR, SRC>(p, it, sm_P, sm_C, Dd, w0, w1, r, u, &yf);
+      affine4(sm_Ad, z, u);
     }
   }
 
@@ -561,31 +566,67 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(ScanParams p) {
     for (int c = 0; c < 4; ++c) sm_tot[warp][c] = z[c];
   }
   __syncthreads();
-  if (tid == 0) {
-    // exclusive prefix per warp (and the tile aggregate), 8 serial steps with Ad^(32*CHUNK)
-    double a[4] = {0, 0, 0, 0};
-    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+  if (warp == 0) {
+    const int64_t slot0 = tile_slot0(it, item);
+    const int64_t b = blockIdx.x;
+    double* ag = p.agg + 4 * slot0;
+    if (lane == 0) {
+      // tile aggregate (zero start): 8 serial steps with Ad^(32*CHUNK); publish it
+      double a[4] = {0, 0, 0, 0};
+      for (int w = 0; w < SCAN_THREADS / 32; ++w) affine4(sm_pow + 16 * 5, a, sm_tot[w]);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) sm_pre[w][c] = a[c];
-      affine4(sm_pow + 16 * 5, a, sm_tot[w]);
+      for (int c = 0; c < 4; ++c) __stcg(ag + 4 * b + c, a[c]);
+      __threadfence();
+      atomicExch(p.flags + slot0 + b, 1);
     }
-    if (!APPLY) {
-      double* ag = p.agg + 4 * (tile_slot0(it, item) + blockIdx.x);
+    // look back over the preceding tiles' aggregates (contraction makes older ones vanish).
+    // The lanes wait for / fetch 32 tiles at a time concurrently; lane 0 then folds them in
+    // oldest first:  start <- Ad^tile start + agg[t].
+    const int64_t K = d.lookback();
+    const int64_t k0 = (b > K) ? b - K : 0;
+    double start[4] = {0, 0, 0, 0};
+    if (k0 == 0) {
+      const double* si = p.s_init + 4 * item;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) ag[c] = a[c];
+      for (int c = 0; c < 4; ++c) start[c] = si[c];
+    }
+    for (int64_t t0 = k0; t0 < b; t0 += 32) {
+      const int64_t t = t0 + lane;
+      double g[4] = {0, 0, 0, 0};
+      if (t < b) {
+        volatile int* f = p.flags + slot0 + t;
+        while (*f == 0) { }
+        __threadfence();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) g[c] = __ldcg(ag + 4 * t + c);
+      }
+      const int cnt = static_cast<int>((b - t0) < 32 ? (b - t0) : 32);
+      for (int l = 0; l < cnt; ++l) {
+        double gl[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) gl[c] = shfl_f64(g[c], l);
+        affine4(sm_pow + 8 * 16, start, gl);
+      }
+    }
+    if (lane == 0) {
+      // state at the start of every warp's stretch
+      for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sm_pre[w][c] = start[c];
+        affine4(sm_pow + 16 * 5, start, sm_tot[w]);
+      }
     }
   }
-  if (!APPLY) return;
   __syncthreads();
 
-  // state before this thread's chunk = Ad^(CHUNK*lane) * warp_prefix + (inclusive state of lane-1)
+  // state before this thread's chunk = Ad^(CHUNK*lane) * warp_start + (inclusive state of lane-1)
   double st[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const double prev = shfl_up_f64(z[c], 1);
     st[c] = (lane == 0) ? 0.0 : prev;
   }
-  if (warp > 0) {
+  {
     double pre[4] = {sm_pre[warp][0], sm_pre[warp][1], sm_pre[warp][2], sm_pre[warp][3]};
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
@@ -599,17 +640,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(ScanParams p) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) st[c] += pre[c];
   }
-  if (tid == 0) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) st[c] = start[c];
-  }
 
+  // ---- sweep 2: apply
   double amax = 0.0;
 #pragma unroll
   for (int c = 0; c < SCAN_CHUNK; ++c) {
     const int64_t r = rbeg + c;
     if (r < ns) {
-      affine4(sm_Ad, st, u[c]);
+      double u[4], yf = 0.0;
+      scan_input<DIR, SRC>(p, it, sm_P, sm_C, Dd, w0, w1, r, u, &yf);
+      affine4(sm_Ad, st, u);
       if (DIR == 0) {
         double2* po = reinterpret_cast<double2*>(p.sf + 4 * (it.m_off + r + 1));
         po[0] = make_double2(st[0], st[1]);
@@ -617,7 +657,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(ScanParams p) {
       } else {
         const int64_t j = it.m - 2 - r;
         const double yb = sm_C[0] * st[0] + sm_C[1] * st[1] + sm_C[2] * st[2] + sm_C[3] * st[3];
-        const double yy = yb + Dd * yfv[c];
+        const double yy = yb + Dd * yf;
         p.y[it.m_off + j] = yy;
         amax = fmax(amax, fabs(yy));
       }
@@ -674,6 +714,8 @@ __global__ void k_debug_wav(const double* __restrict__ y, const double* __restri
 // ------------------------------------------------------------------ host side
 struct FrontendBuffers {
   double *uf, *ub0, *xe, *sf, *agg, *s0, *sb_last, *tail;
+  int* flags;
+  int64_t tiles;
   int tail_cap;
 };
 
@@ -683,7 +725,9 @@ static int carve_frontend(Workspace& ws, int64_t total_m, int n_items, int block
   b->ub0 = ws.take<double>(4 * total_m);
   b->xe = ws.take<double>(total_m);
   b->sf = ws.take<double>(4 * total_m);
-  b->agg = ws.take<double>(4 * tiles);
+  b->agg = ws.take<double>(2 * 4 * tiles);      // forward | backward
+  b->flags = ws.take<int>(2 * tiles);
+  b->tiles = tiles;
   b->s0 = ws.take<double>(4 * n_items);
   b->sb_last = ws.take<double>(4 * n_items);
   b->tail_cap = block + PADLEN + 1;
@@ -761,28 +805,22 @@ int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
       default: BPM_LAUNCH_CONTRACT(128, 1, 0); break;
     }
 #undef BPM_LAUNCH_CONTRACT
-  } else if (block == 1) {
-    BPM_KERNEL(k_contract_b1);
-    k_contract_b1<<<dim3(cdiv(sh.max_m, 8 * 31), n_items), 256, 0, st>>>(pv, items, stride, design, b.uf, b.ub0, b.xe);
-  } else {
+  } else if (block > 1) {
     BPM_KERNEL(k_contract_generic);
     k_contract_generic<<<dim3(cdiv(sh.max_m, 256), n_items), 256, 0, st>>>(pv, items, stride, design, b.uf, b.ub0, b.xe);
   }
-  BPM_LAUNCH_OK();
+  if (block > 1) BPM_LAUNCH_OK();                      // block == 1: the scans form uf / ub0 themselves
   BPM_KERNEL(k_filter_init);
   k_filter_init<<<cdiv(n_items, FE_WARPS), 32 * FE_WARPS, 0, st>>>(pv, items, n_items, stride, design, b.s0);
   BPM_LAUNCH_OK();
 
+  if (cudaMemsetAsync(b.flags, 0, sizeof(int) * 2 * b.tiles, st) != cudaSuccess) return BPM_ERR_CUDA;
   const dim3 sgrid(cdiv(sh.max_m > 1 ? sh.max_m - 1 : 1, SCAN_TILE), n_items);
-  ScanParams sp{items, design, b.uf, b.sf, b.xe, b.s0, b.agg, filtered,
-                reinterpret_cast<unsigned long long*>(absmax)};
-  if (sgrid.x > 1) {
-    BPM_KERNEL(k_scan);
-    k_scan<0, false><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
-    BPM_LAUNCH_OK();
-  }
+  ScanParams sp{items, design, b.uf, b.sf, b.xe, b.s0, b.agg, b.flags, filtered,
+                reinterpret_cast<unsigned long long*>(absmax), pv, stride};
   BPM_KERNEL(k_scan);
-  k_scan<0, true><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
+  if (block == 1) k_scan<0, 1><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
+  else k_scan<0, 0><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
   BPM_LAUNCH_OK();
   {
     const size_t smem = sizeof(double) * FE_WARPS * b.tail_cap;
@@ -794,13 +832,11 @@ int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
   BPM_LAUNCH_OK();
   sp.u = b.ub0;
   sp.s_init = b.sb_last;
-  if (sgrid.x > 1) {
-    BPM_KERNEL(k_scan);
-    k_scan<1, false><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
-    BPM_LAUNCH_OK();
-  }
+  sp.agg = b.agg + 4 * b.tiles;
+  sp.flags = b.flags + b.tiles;
   BPM_KERNEL(k_scan);
-  k_scan<1, true><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
+  if (block == 1) k_scan<1, 1><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
+  else k_scan<1, 0><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
   BPM_LAUNCH_OK();
   BPM_KERNEL(k_envelope);
   k_envelope<<<dim3(cdiv(sh.max_m, ENV_THREADS), n_items), ENV_THREADS,
