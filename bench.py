@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--no-zero-copy", action="store_true", help="e2e: copy the whole recording to the device first")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="e2e: recordings in flight (1 = strictly serial steps)")
     ap.add_argument("--dump-kernels", default=None, help="write the per-kernel table to this JSON file")
     ap.add_argument("--workload", default="recordings", choices=["recordings", "stream"],
                     help="recordings: one C2 recording per GPU (weak scaling, the headline). stream: ONE C2 "
@@ -337,60 +338,84 @@ def run_b200(args):
                       "smoothed_dev")}
     hostb = {k: torch.empty_like(v, device="cpu").pin_memory() for k, v in Bn.out.items()}
 
-    # decimate-then-filter touches every ds-th frame only: let the kernels pull those frames out
-    # of pinned host memory (zero-copy) instead of copying the whole recording first
+    # decimate-then-filter touches every ds-th frame only: the ingest kernel pulls those frames out
+    # of pinned host memory (zero-copy), and a 2-deep pipeline overlaps the PCIe-bound ingest of
+    # step k+1 with the kernels of step k and the read-back of step k-1 (runtime.StageAPipeline).
+    # Every step still moves its own input host->device and its own results device->host inside
+    # the timed region; nothing is reused between steps.
     zero_copy = (args.filter_mode == "parity") and not args.no_zero_copy
+    e2e_mode = "pipelined zero-copy" if zero_copy else "serial full copy"
     if zero_copy:
-        A.read_from_host(pcm_pin)
-        e2e_graph = None if args.no_graph else GraphedStep(A, Bn)
-        e2e_launch = step_eager if e2e_graph is None else e2e_graph.launch
+        from bpm_analysis_b200.runtime import StageAPipeline
+        depth = max(1, args.e2e_depth)
+        pipe = StageAPipeline(len(pcm), sr, params, depth=depth,
+                              beat_runner_args=(len(beat_idx), rate, params, hr_extrema_distance(beat_idx, rate)),
+                              use_graph=not args.no_graph)
+
+        def e2e_run(n_steps):
+            res = None
+            for k in range(n_steps):
+                if k >= depth:
+                    res = pipe.wait(k - depth)
+                pipe.submit(k, pcm_pin, beats_pin)
+            for k in range(max(0, n_steps - depth), n_steps):
+                res = pipe.wait(k)
+            return res
+
+        res = e2e_run(max(depth + 1, args.warmup))
+        barrier()
+        t0 = time.perf_counter()
+        res = e2e_run(args.steps)
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+        nt, npk = int(res["trough_count"][0]), int(res["peak_count"][0])
+        nv, rows = int(res["beat_n_valid"][0]), int(res["beat_hrv_rows"][0])
+        # the pipelined results are the device-resident run's results
+        assert nt == int(A.out["trough_count"][0]) and npk == int(A.out["peak_count"][0])
+        assert torch.equal(res["peaks"][:npk], A.out["peaks"][:npk].cpu())
+        assert torch.equal(res["floor"], A.out["floor"].cpu())
+        h2d = M * 32 + beats_pin.numel() * 8          # one 32-byte sector per kept frame crosses PCIe
+        d2h = pipe.d2h_bytes()
+        del pipe
     else:
-        e2e_launch = step
-
-    def e2e_step():
-        if not zero_copy:
+        def e2e_step():
             A.upload_pinned(pcm_pin)
-        Bn.upload(beats_pin)
-        e2e_launch()
-        for k in ("trough_count", "peak_count"):
-            host[k].copy_(A.out[k], non_blocking=True)
-        for k in ("n_tops", "n_bottoms", "hrv_rows", "slopes", "n_valid"):
-            hostb[k].copy_(Bn.out[k], non_blocking=True)
-        host["envelope"].copy_(A.out["envelope"], non_blocking=True)
-        host["floor"].copy_(A.out["floor"], non_blocking=True)
-        torch.cuda.synchronize()
-        nt, npk = int(host["trough_count"][0]), int(host["peak_count"][0])
-        host["troughs"][:nt].copy_(A.out["troughs"][:nt], non_blocking=True)
-        for k in ("peaks", "strength", "smoothed_dev"):
-            host[k][:npk].copy_(A.out[k][:npk], non_blocking=True)
-        nv, rows = int(hostb["n_valid"][0]), int(hostb["hrv_rows"][0])
-        for k in ("smoothed", "times", "stamps"):
-            hostb[k][:nv].copy_(Bn.out[k][:nv], non_blocking=True)
-        hostb["tops"][:int(hostb["n_tops"][0])].copy_(Bn.out["tops"][:int(hostb["n_tops"][0])], non_blocking=True)
-        hostb["bottoms"][:int(hostb["n_bottoms"][0])].copy_(Bn.out["bottoms"][:int(hostb["n_bottoms"][0])],
-                                                            non_blocking=True)
-        hostb["hrv"][:rows].copy_(Bn.out["hrv"][:rows], non_blocking=True)
-        torch.cuda.synchronize()
-        return nt, npk, nv, rows
+            Bn.upload(beats_pin)
+            step()
+            for k in ("trough_count", "peak_count"):
+                host[k].copy_(A.out[k], non_blocking=True)
+            for k in ("n_tops", "n_bottoms", "hrv_rows", "slopes", "n_valid"):
+                hostb[k].copy_(Bn.out[k], non_blocking=True)
+            host["envelope"].copy_(A.out["envelope"], non_blocking=True)
+            host["floor"].copy_(A.out["floor"], non_blocking=True)
+            torch.cuda.synchronize()
+            nt, npk = int(host["trough_count"][0]), int(host["peak_count"][0])
+            host["troughs"][:nt].copy_(A.out["troughs"][:nt], non_blocking=True)
+            for k in ("peaks", "strength", "smoothed_dev"):
+                host[k][:npk].copy_(A.out[k][:npk], non_blocking=True)
+            nv, rows = int(hostb["n_valid"][0]), int(hostb["hrv_rows"][0])
+            for k in ("smoothed", "times", "stamps"):
+                hostb[k][:nv].copy_(Bn.out[k][:nv], non_blocking=True)
+            hostb["tops"][:int(hostb["n_tops"][0])].copy_(Bn.out["tops"][:int(hostb["n_tops"][0])], non_blocking=True)
+            hostb["bottoms"][:int(hostb["n_bottoms"][0])].copy_(Bn.out["bottoms"][:int(hostb["n_bottoms"][0])],
+                                                                non_blocking=True)
+            hostb["hrv"][:rows].copy_(Bn.out["hrv"][:rows], non_blocking=True)
+            torch.cuda.synchronize()
+            return nt, npk, nv, rows
 
-    for _ in range(max(1, args.warmup // 2)):
-        nt, npk, nv, rows = e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+        for _ in range(max(1, args.warmup // 2)):
+            nt, npk, nv, rows = e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+        h2d = pcm_pin.numel() * pcm_pin.element_size() + beats_pin.numel() * 8
+        d2h = 2 * M * 8 + nt * 8 + npk * 24 + nv * 24 + rows * 32 + 8 * 8 + 7 * 8 + \
+            (int(hostb["n_tops"][0]) + int(hostb["n_bottoms"][0])) * 8
     clocks = sampler.stop()
     e2e_value = world * audio_hours / (e2e_ms / 1e3)
-    if zero_copy:
-        h2d = M * 32 + beats_pin.numel() * 8      # one 32-byte sector per kept frame crosses PCIe
-        A.upload_pinned(pcm_pin)                  # back to the device-resident copy for the profile pass
-        torch.cuda.synchronize()
-    else:
-        h2d = pcm_pin.numel() * pcm_pin.element_size() + beats_pin.numel() * 8
-    d2h = 2 * M * 8 + nt * 8 + npk * 24 + nv * 24 + rows * 32 + 8 * 8 + 7 * 8 + \
-        (int(hostb["n_tops"][0]) + int(hostb["n_bottoms"][0])) * 8
 
     # ---- per-kernel event timing (separate pass: events between launches perturb the step)
     roofline, kernels = None, {}
@@ -441,9 +466,10 @@ def run_b200(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h),
-                        "ingest": ("zero-copy: kernels read the kept frames from pinned host memory "
-                                   "(h2d bytes = 32-byte sector per kept frame)") if zero_copy else
-                                  "cudaMemcpyAsync of the whole recording from pinned host memory"},
+                        "ingest": (f"zero-copy: bpm_gather_frames reads the kept frames from pinned host memory (h2d bytes "
+                                   f"= 32-byte sector per kept frame); {args.e2e_depth}-deep pipeline ingest | compute | "
+                                   "read-back over three streams") if zero_copy else
+                                  "cudaMemcpyAsync of the whole recording from pinned host memory, serial steps"},
                 "gpu_launches": launches if graphed is None else launches_per_step * args.steps,
                 "launch_mode": "eager" if graphed is None else "cuda-graph replay", "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
         print(json.dumps(line), flush=True)

@@ -180,6 +180,32 @@ __global__ void __launch_bounds__(256) k_contract_generic(PcmView pcm, const Bpm
   reinterpret_cast<double2*>(pb)[1] = make_double2(b[2], b[3]);
 }
 
+// ------------------------------------------------------------ K0 alone: x[::stride] as float64
+// np.mean(axis=1) + audio_data[::downsample_factor] (bpm_analysis.py:1016, :1033).  Lets a host
+// pipeline overlap the PCIe-bound ingest of the NEXT recording (the PCM may be mapped pinned host
+// memory: one 32-byte sector per kept frame crosses the bus) with the compute of the current one:
+// few CTAs, eight independent loads in flight per thread, coalesced float64 stores.
+constexpr int GF_UNROLL = 8;
+__global__ void __launch_bounds__(256) k_gather_frames(PcmView pcm, const BpmItem* __restrict__ items, int64_t stride,
+                                                       double* __restrict__ out) {
+  const BpmItem it = items[blockIdx.y];
+  const int64_t n_dec = (it.n_in + stride - 1) / stride;
+  const int64_t T = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t j0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j0 < n_dec; j0 += T * GF_UNROLL) {
+    double v[GF_UNROLL];
+#pragma unroll
+    for (int k = 0; k < GF_UNROLL; ++k) {
+      const int64_t j = j0 + k * T;
+      v[k] = (j < n_dec) ? pcm_frame(pcm, it.in_off + j * stride) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < GF_UNROLL; ++k) {
+      const int64_t j = j0 + k * T;
+      if (j < n_dec) out[it.m_off + j] = v[k];
+    }
+  }
+}
+
 // ------------------------------------------------------ contraction (int16, full rate)
 // The HBM-bound kernel: mono int16 at the original rate (stride 1), block = ds.
 //   * a CTA owns CT_BLOCKS consecutive blocks; one elected thread brings their PCM span into
@@ -841,6 +867,21 @@ int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
   BPM_KERNEL(k_envelope);
   k_envelope<<<dim3(cdiv(sh.max_m, ENV_THREADS), n_items), ENV_THREADS,
                sizeof(double) * (ENV_THREADS + env_window), st>>>(filtered, items, env_window, envelope);
+  BPM_LAUNCH_OK();
+  return BPM_OK;
+}
+
+int gather_frames_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* items, const BpmItem* items_host,
+                      int n_items, int64_t stride, double* out, cudaStream_t st) {
+  if (!pcm || !items || !items_host || !out || n_items <= 0 || stride < 1 || channels < 1 || pcm_dtype < 0 ||
+      pcm_dtype > BPM_PCM_F64)
+    return BPM_ERR_ARG;
+  for (int i = 0; i < n_items; ++i)
+    if (items_host[i].m != (items_host[i].n_in + stride - 1) / stride) return BPM_ERR_ARG;   // out is laid out by m_off
+  PcmView pv{pcm, pcm_dtype, channels};
+  int gx = (148 + n_items - 1) / n_items;
+  BPM_KERNEL(k_gather_frames);
+  k_gather_frames<<<dim3(gx, n_items), 256, 0, st>>>(pv, items, stride, out);
   BPM_LAUNCH_OK();
   return BPM_OK;
 }

@@ -14,6 +14,8 @@ int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
                  int env_window, double* filtered, double* envelope, double* absmax, Workspace& ws, cudaStream_t st);
 int debug_wav_run(const double* filtered, const double* absmax, const BpmItem* items, const BpmItem* items_host,
                   int n_items, int16_t* out, cudaStream_t st);
+int gather_frames_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* items, const BpmItem* items_host,
+                      int n_items, int64_t stride, double* out, cudaStream_t st);
 // select.cu
 size_t quantile_workspace_bytes(int n_items);
 int quantile_run(const double* x, const BpmItem* items, const BatchShape& sh, double q, const int* cond,
@@ -309,6 +311,12 @@ int bpm_frontend(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
   const int block = static_cast<int>((rem - 12) / 16);
   return frontend_run(pcm, pcm_dtype, channels, items, items_host, n_items, stride, design, design_words, block,
                       env_window, filtered, envelope, absmax, ws, static_cast<cudaStream_t>(stream));
+}
+
+int bpm_gather_frames(const void* pcm, int pcm_dtype, int channels, const BpmItem* items, const BpmItem* items_host,
+                      int n_items, int64_t stride, double* frames_out, void* stream) {
+  return gather_frames_run(pcm, pcm_dtype, channels, items, items_host, n_items, stride, frames_out,
+                           static_cast<cudaStream_t>(stream));
 }
 
 int bpm_debug_wav(const double* filtered, const double* absmax, const BpmItem* items, const BpmItem* items_host,

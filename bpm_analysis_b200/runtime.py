@@ -161,7 +161,11 @@ class StageARunner:
     """
 
     def __init__(self, n_in: Sequence[int], sample_rate: int, params: Dict, pcm_dtype=np.int16,
-                 channels: int = 1, want_debug: bool = False):
+                 channels: int = 1, want_debug: bool = False, pregathered: bool = False):
+        """``pregathered``: the decimation x[::ds] (K0) runs as its own small kernel (``gather``)
+        into a float64 frame buffer that stage A then reads with stride 1 -- bit-identical to the
+        fused path, and it lets ``StageAPipeline`` overlap the PCIe-bound ingest of the next
+        recording with the compute of the current one.  Decimate-then-filter order only."""
         self.device = require_cuda()
         self.lib = nat.load_library()
         self.plan = plan_filter(sample_rate, params)
@@ -177,6 +181,15 @@ class StageARunner:
         self.total_in = int(self.items["n_in"].sum())
         self.total_m = int(self.items["m"].sum())
         self.cfg = stage_a_config(self.plan, params, nat.PCM_DTYPES[self.np_dtype], self.channels, want_debug)
+        self.pregathered = bool(pregathered)
+        if self.pregathered:
+            if self.plan.block != 1:
+                raise ValueError("pregathered ingest needs the decimate-then-filter order (filter_mode 'parity')")
+            self.src_items = self.items
+            self.src_items_dev = torch.from_numpy(self.src_items.view(np.int64).reshape(-1, 4).copy()).to(self.device)
+            self.src_stride = int(self.plan.stride)
+            self.items = make_items(self.src_items["m"], self.src_items["m"])
+            self.cfg.stride, self.cfg.pcm_dtype, self.cfg.channels = 1, nat.PCM_DTYPES[np.dtype(np.float64)], 1
         self.items_dev = torch.from_numpy(self.items.view(np.int64).reshape(-1, 4).copy()).to(self.device)
         self.design_dev = design_on_device(self.plan)
         self.design_words = int(self.design_dev.numel())
@@ -193,8 +206,14 @@ class StageARunner:
             self.out["debug_wav"] = torch.empty(M, dtype=torch.int16, device=self.device)
         self.ws_bytes = int(self.lib.bpm_stage_a_workspace_bytes(M, n))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
-        self.pcm_dev = torch.empty(self.total_in * self.channels, dtype=_torch_dtype(self.np_dtype), device=self.device)
-        self._pcm_src = self.pcm_dev          # what the kernels read: the device copy, or mapped pinned host memory
+        if self.pregathered:
+            self.frames_dev = torch.empty(M, dtype=torch.float64, device=self.device)
+            self.pcm_dev = None
+            self._pcm_src = self.frames_dev
+        else:
+            self.pcm_dev = torch.empty(self.total_in * self.channels, dtype=_torch_dtype(self.np_dtype),
+                                       device=self.device)
+            self._pcm_src = self.pcm_dev      # what the kernels read: the device copy, or mapped pinned host memory
         self.outs_struct = nat.StageAOutputs(**{k: self.out[k].data_ptr() if k in self.out else None
                                                 for k, _ in nat.StageAOutputs._fields_})
 
@@ -223,6 +242,18 @@ class StageARunner:
         if not pinned.is_pinned() or pinned.numel() != self.pcm_dev.numel() or pinned.dtype != self.pcm_dev.dtype:
             raise ValueError("need a pinned host tensor with the batch's dtype and size")
         self._pcm_src = pinned
+
+    def gather(self, pcm: torch.Tensor) -> None:
+        """K0 on the current stream (pregathered mode): kept frames of ``pcm`` -> float64 frame buffer.
+        ``pcm`` is a device tensor or a PINNED host tensor (zero-copy: the kernel reads it over PCIe)."""
+        if not self.pregathered:
+            raise RuntimeError("runner was not built with pregathered=True")
+        if not (pcm.is_cuda or pcm.is_pinned()) or pcm.numel() != self.total_in * self.channels \
+                or pcm.dtype != _torch_dtype(self.np_dtype):
+            raise ValueError("need a device or pinned host tensor with the batch's dtype and size")
+        nat.check(self.lib.bpm_gather_frames(_ptr(pcm), nat.PCM_DTYPES[self.np_dtype], self.channels,
+                                             _ptr(self.src_items_dev), _host_ptr(self.src_items), self.n_items,
+                                             self.src_stride, _ptr(self.frames_dev), _stream_ptr()))
 
     # -- compute
     def launch(self) -> None:
@@ -523,6 +554,98 @@ class GraphedStep:
 
     def launch(self) -> None:
         self.graph.replay()
+
+
+class StageAPipeline:
+    """Software pipeline over a stream of equal-shape recordings: ingest | compute | read-back.
+
+    Each of ``depth`` slots owns a pregathered ``StageARunner`` (+ optionally a ``BeatRunner``),
+    pinned host result buffers and three events.  ``submit(k, pcm_pinned)`` enqueues, without
+    blocking the host,
+      ingest stream : bpm_gather_frames reading the pinned recording over PCIe (zero-copy),
+      compute stream: a1..a4 (and a5..a8) as one CUDA-graph replay, after the slot's ingest,
+      copy stream   : D2H of every result into the slot's pinned buffers, after the compute;
+    ``wait(k)`` blocks until recording k's results are on the host.  With depth >= 2 the PCIe
+    reads of recording k+1 overlap the kernels of k and the read-back of k-1.
+    """
+
+    LISTS = ("troughs", "peaks", "strength", "deviation", "smoothed_dev")
+
+    def __init__(self, n_in: int, sample_rate: int, params: Dict, depth: int = 2, beat_runner_args=None,
+                 pcm_dtype=np.int16, channels: int = 1, use_graph: bool = True):
+        require_cuda()
+        self.depth = int(depth)
+        self.s_in, self.s_cmp, self.s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+        self.slots = []
+        for _ in range(self.depth):
+            A = StageARunner([n_in], sample_rate, params, pcm_dtype, channels, pregathered=True)
+            Bn = BeatRunner(*beat_runner_args) if beat_runner_args is not None else None
+            cap = A.total_m // max(int(A.cfg.distance), 1) + 2          # find_peaks distance bounds the list lengths
+            host = {}
+            for k, v in A.out.items():
+                if k == "filtered":                       # only the debug WAV consumes it (preprocess returns the envelope)
+                    continue
+                n = cap if k in self.LISTS else v.numel()
+                host[k] = torch.empty(n, dtype=v.dtype).pin_memory()
+            hostb = {k: torch.empty_like(v, device="cpu").pin_memory() for k, v in Bn.out.items()} if Bn else {}
+            with torch.cuda.stream(self.s_cmp):
+                A.frames_dev.zero_()
+            runners = (A,) if Bn is None else (A, Bn)
+            self.slots.append({"A": A, "B": Bn, "cap": cap, "host": host, "hostb": hostb, "runners": runners,
+                               "graph": None, "ev_in": torch.cuda.Event(), "ev_cmp": torch.cuda.Event(),
+                               "ev_out": torch.cuda.Event(), "busy": False})
+        self.use_graph = use_graph
+        self.M = self.slots[0]["A"].total_m
+        self.rate = self.slots[0]["A"].plan.rate
+
+    def _graph(self, slot):
+        if slot["graph"] is None and self.use_graph:
+            torch.cuda.synchronize()
+            slot["graph"] = GraphedStep(*slot["runners"])
+        return slot["graph"]
+
+    def submit(self, k: int, pcm_pinned: torch.Tensor, beats_pinned: Optional[torch.Tensor] = None) -> None:
+        slot = self.slots[k % self.depth]
+        if slot["busy"]:
+            raise RuntimeError("slot still in flight: call wait() for recording k - depth first")
+        A, Bn = slot["A"], slot["B"]
+        g = self._graph(slot) if self.use_graph else None
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(slot["ev_cmp"])          # the previous compute on this slot has consumed its frames
+            A.gather(pcm_pinned)
+            if Bn is not None and beats_pinned is not None:
+                Bn.upload(beats_pinned)
+            slot["ev_in"].record(self.s_in)
+        with torch.cuda.stream(self.s_cmp):
+            self.s_cmp.wait_event(slot["ev_in"])
+            self.s_cmp.wait_event(slot["ev_out"])         # the previous read-back of this slot's outputs is done
+            if g is not None:
+                g.launch()
+            else:
+                for r in slot["runners"]:
+                    r.launch()
+            slot["ev_cmp"].record(self.s_cmp)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(slot["ev_cmp"])
+            for name, h in slot["host"].items():
+                h.copy_(A.out[name][:h.numel()], non_blocking=True)
+            for name, h in slot["hostb"].items():
+                h.copy_(Bn.out[name], non_blocking=True)
+            slot["ev_out"].record(self.s_out)
+        slot["busy"] = True
+
+    def wait(self, k: int) -> Dict[str, torch.Tensor]:
+        slot = self.slots[k % self.depth]
+        slot["ev_out"].synchronize()
+        slot["busy"] = False
+        out = dict(slot["host"])
+        out.update({"beat_" + n: h for n, h in slot["hostb"].items()})
+        return out
+
+    def d2h_bytes(self) -> int:
+        s = self.slots[0]
+        return int(sum(h.numel() * h.element_size() for h in s["host"].values()) +
+                   sum(h.numel() * h.element_size() for h in s["hostb"].values()))
 
 
 def profile_kernels(fn, stream_ptr: Optional[int] = None) -> Dict[str, tuple]:

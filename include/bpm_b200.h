@@ -80,6 +80,16 @@ int bpm_frontend(const void* pcm, int pcm_dtype, int channels,
                  int env_window, double* filtered, double* envelope, double* absmax,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* K0 alone: np.mean(axis=1) + audio_data[::stride] as float64, bpm_analysis.py:1016, :1033.
+ * frames_out: float64, recording i at m_off, length m = ceil(n_in / stride).  `pcm` may be
+ * mapped pinned HOST memory (zero-copy ingest).  Feeding frames_out to bpm_frontend /
+ * bpm_stage_a as BPM_PCM_F64 with stride 1 gives bit-identical results to passing the PCM
+ * itself with this stride; a host pipeline uses the split to overlap the PCIe-bound ingest
+ * of the next recording with the compute of the current one. */
+int bpm_gather_frames(const void* pcm, int pcm_dtype, int channels, const BpmItem* items,
+                      const BpmItem* items_host, int n_items, int64_t stride, double* frames_out,
+                      void* stream);
+
 /* K2b: np.int16(y / max|y| * 32767), bpm_analysis.py:1049 (truncating cast). */
 int bpm_debug_wav(const double* filtered, const double* absmax, const BpmItem* items,
                   const BpmItem* items_host, int n_items, int16_t* out, void* stream);

@@ -325,3 +325,38 @@ def test_full_size_properties_c2(fe, ref_params):
         assert torch.equal(runner.out[k], a[k])
     n = int(runner.out["peak_count"][0])
     assert torch.equal(runner.out["peaks"][:n], a["peaks"][:n])
+
+
+# ----------------------------------------------------------------------------- ingest pipeline
+def test_pipelined_zero_copy_ingest_is_bit_identical(fe, ref_params):
+    """runtime.StageAPipeline (bpm_gather_frames from pinned host memory, compute and read-back
+    on three streams, two recordings in flight) must return exactly what the one-shot
+    StageARunner returns for each recording of a stream of equal-length recordings."""
+    import torch
+    from bpm_analysis_b200 import synth
+    from bpm_analysis_b200.runtime import StageAPipeline, StageARunner
+    recs = [synth.config_c2(seed=20 + i, duration_sec=200.0)[0] for i in range(5)]
+    sr = 48000
+    one = StageARunner([len(recs[0])], sr, ref_params)
+    want = []
+    for r in recs:
+        one.upload([r])
+        one.launch()
+        torch.cuda.synchronize()
+        want.append({k: v.clone().cpu() for k, v in one.out.items()})
+    for use_graph in (False, True):
+        pipe = StageAPipeline(len(recs[0]), sr, ref_params, depth=2, use_graph=use_graph)
+        pins = [torch.from_numpy(r).pin_memory() for r in recs]
+        got = []
+        for k in range(len(recs)):
+            if k >= 2:
+                got.append({n: t.clone() for n, t in pipe.wait(k - 2).items()})
+            pipe.submit(k, pins[k])
+        for k in range(len(recs) - 2, len(recs)):
+            got.append({n: t.clone() for n, t in pipe.wait(k).items()})
+        for g, w in zip(got, want):
+            nt, npk = int(w["trough_count"][0]), int(w["peak_count"][0])
+            assert int(g["trough_count"][0]) == nt and int(g["peak_count"][0]) == npk
+            assert torch.equal(g["envelope"], w["envelope"]) and torch.equal(g["floor"], w["floor"])
+            assert torch.equal(g["troughs"][:nt], w["troughs"][:nt]) and torch.equal(g["peaks"][:npk], w["peaks"][:npk])
+            assert torch.equal(g["smoothed_dev"][:npk - 1], w["smoothed_dev"][:npk - 1])
