@@ -71,6 +71,7 @@ _SIGNATURES = {
     "bpm_raw_peaks_workspace_bytes": (_Z, [_L, _I]),
     "bpm_raw_peaks": (_I, [_P, _P, _P, _P, _I, _I, _D, _P, _P, _P, _Z, _P]),
     "bpm_peak_metrics": (_I, [_P, _P, _P, _P, _P, _P, _I, _D, _P, _P, _P, _P]),
+    "bpm_peak_trough_noise": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _D, _D, _P, _P, _P, _P, _P]),
     "bpm_bpm_series": (_I, [_P, _P, _P, _I, _I, _L, _P, _P, _P, _P, _P, _P]),
     "bpm_steepest_slope_workspace_bytes": (_Z, [_L, _I]),
     "bpm_steepest_slope": (_I, [_P, _P, _P, _P, _P, _I, _I, _D, _P, _P, _Z, _P]),

@@ -81,6 +81,77 @@ int peak_metrics_run(const double* env, const double* floor_, const int64_t* pea
   return BPM_OK;
 }
 
+// ------------------------------------------------------------------ K8b: surrounding-trough noise
+// The north star's "trough-noise" per-peak metric.  No function of bpm_analysis.py computes it any
+// more (SURVEY.md §8a note); the definitions below are the ones its documentation and surviving
+// config keys give (PARITY UNPINNED, oracle = oracle/ref_port.py::peak_trough_noise):
+//   prev / next = amplitude of the sanitised trough just before / after the peak (NaN if none);
+//   deeper      = the lower of the two ("analyzes the deeper of the two troughs surrounding a peak",
+//                 Documentation/Changelog.md:454);
+//   ratio       = deeper / floor[peak];   bit 0: ratio > trough_noise_multiplier (config.py:31,
+//                 "BPM Detection logic explained.md":262);
+//   bit 1       : look-ahead veto  m * (env[p] - next) < (env[p_next] - next)  with m =
+//                 trough_veto_multiplier (config.py:30, "...logic explained.md":276-278), only when
+//                 the next trough lies before the next peak.
+__global__ void k_peak_trough_noise(const double* __restrict__ env, const double* __restrict__ floor_,
+                                    const int64_t* __restrict__ peaks, const int64_t* __restrict__ peak_count,
+                                    const int64_t* __restrict__ troughs, const int64_t* __restrict__ trough_count,
+                                    const BpmItem* __restrict__ items, double noise_mult, double veto_mult,
+                                    double* __restrict__ prev_amp, double* __restrict__ next_amp,
+                                    double* __restrict__ ratio, unsigned char* __restrict__ flags) {
+  const BpmItem it = items[blockIdx.y];
+  const long long np = peak_count[blockIdx.y], nt = trough_count[blockIdx.y];
+  const int64_t* tr = troughs + it.m_off;
+  const double* e = env + it.m_off;
+  const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+  for (long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < np;
+       k += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int64_t p = peaks[it.m_off + k];
+    long long lo = 0, hi = nt;                       // first trough index with tr[i] > p
+    while (lo < hi) {
+      const long long mid = (lo + hi) >> 1;
+      if (tr[mid] > p) hi = mid; else lo = mid + 1;
+    }
+    long long ip = lo - 1;                           // last trough <= p; a trough is never a peak, but be strict
+    while (ip >= 0 && tr[ip] >= p) --ip;
+    const double pa = (ip >= 0) ? e[tr[ip]] : qnan;
+    const double na = (lo < nt) ? e[tr[lo]] : qnan;
+    double deeper = qnan;
+    if (ip >= 0 && lo < nt) deeper = fmin(pa, na);
+    else if (ip >= 0) deeper = pa;
+    else if (lo < nt) deeper = na;
+    const double r = __ddiv_rn(deeper, floor_[it.m_off + p]);
+    unsigned char f = 0;
+    if (r > noise_mult) f |= 1;
+    if (k + 1 < np && lo < nt) {
+      const int64_t pn = peaks[it.m_off + k + 1];
+      if (tr[lo] < pn && __dmul_rn(veto_mult, __dsub_rn(e[p], na)) < __dsub_rn(e[pn], na)) f |= 2;
+    }
+    prev_amp[it.m_off + k] = pa;
+    next_amp[it.m_off + k] = na;
+    ratio[it.m_off + k] = r;
+    flags[it.m_off + k] = f;
+  }
+}
+
+int peak_trough_noise_run(const double* env, const double* floor_, const int64_t* peaks, const int64_t* peak_count,
+                          const int64_t* troughs, const int64_t* trough_count, const BpmItem* items,
+                          const BatchShape& sh, double noise_mult, double veto_mult, double* prev_amp,
+                          double* next_amp, double* ratio, unsigned char* flags, cudaStream_t st) {
+  if (!env || !floor_ || !peaks || !peak_count || !troughs || !trough_count || !items || !prev_amp || !next_amp ||
+      !ratio || !flags)
+    return BPM_ERR_ARG;
+  int64_t gx = (sh.max_m / 2 + 2 + 255) / 256;
+  const int64_t cap = (148 * 4 + sh.n_items - 1) / sh.n_items;
+  if (gx > cap) gx = cap;
+  BPM_KERNEL(k_peak_trough_noise);
+  k_peak_trough_noise<<<dim3(static_cast<unsigned>(gx < 1 ? 1 : gx), sh.n_items), 256, 0, st>>>(
+      env, floor_, peaks, peak_count, troughs, trough_count, items, noise_mult, veto_mult, prev_amp, next_amp, ratio,
+      flags);
+  BPM_LAUNCH_OK();
+  return BPM_OK;
+}
+
 // ------------------------------------------------------------------ K9
 // datetime.timedelta(seconds=t) keeps whole seconds exactly and rounds the fraction to the
 // nearest microsecond, ties to even (CPython Modules/_datetimemodule.c accum()/delta_new).

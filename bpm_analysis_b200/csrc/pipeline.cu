@@ -40,6 +40,10 @@ __global__ void k_floor_modes(const int64_t*, const int64_t*, int, int, int*, in
 int peak_metrics_run(const double* env, const double* floor_, const int64_t* peaks, const int64_t* peak_count,
                      const BpmItem* items, const BatchShape& sh, double factor, double* strength,
                      double* deviation, double* smoothed, cudaStream_t st);
+int peak_trough_noise_run(const double* env, const double* floor_, const int64_t* peaks, const int64_t* peak_count,
+                          const int64_t* troughs, const int64_t* trough_count, const BpmItem* items,
+                          const BatchShape& sh, double noise_mult, double veto_mult, double* prev_amp,
+                          double* next_amp, double* ratio, unsigned char* flags, cudaStream_t st);
 int bpm_series_run(const int64_t* beats, const BpmItem* lists, const BatchShape& sh, int rate, int64_t window_us,
                    double* inst, double* smoothed, double* times_sec, int64_t* stamp_us, int64_t* n_valid,
                    cudaStream_t st);
@@ -397,6 +401,17 @@ int bpm_peak_metrics(const double* envelope, const double* floor_, const int64_t
   if (!items_host || n_items <= 0) return BPM_ERR_ARG;
   return peak_metrics_run(envelope, floor_, peaks, peak_count, items, batch_shape(items_host, n_items),
                           smoothing_factor, strength, deviation, smoothed, static_cast<cudaStream_t>(stream));
+}
+
+int bpm_peak_trough_noise(const double* envelope, const double* floor_, const int64_t* peaks,
+                          const int64_t* peak_count, const int64_t* troughs, const int64_t* trough_count,
+                          const BpmItem* items, const BpmItem* items_host, int n_items, double trough_noise_multiplier,
+                          double trough_veto_multiplier, double* prev_amp, double* next_amp, double* ratio,
+                          unsigned char* flags, void* stream) {
+  if (!items_host || n_items <= 0) return BPM_ERR_ARG;
+  return peak_trough_noise_run(envelope, floor_, peaks, peak_count, troughs, trough_count, items,
+                               batch_shape(items_host, n_items), trough_noise_multiplier, trough_veto_multiplier,
+                               prev_amp, next_amp, ratio, flags, static_cast<cudaStream_t>(stream));
 }
 
 int bpm_bpm_series(const int64_t* beats, const BpmItem* lists, const BpmItem* lists_host, int n_lists, int rate,

@@ -25,7 +25,7 @@ from .params import (HR_MIN_CHANGE_BPM, HR_MIN_DURATION_SEC, HR_PROMINENCE, SLOP
 
 __all__ = ["preprocess_audio", "preprocess_pcm", "_calculate_dynamic_noise_floor", "_find_raw_peaks",
            "_initialize_state", "calculate_bpm_series", "find_peak_recovery_rate", "find_peak_exertion_rate",
-           "find_major_hr_inclines", "find_major_hr_declines", "calculate_windowed_hrv", "find_peaks",
+           "find_major_hr_inclines", "find_major_hr_declines", "calculate_windowed_hrv", "find_peaks", "peak_trough_noise",
            "install"]
 
 
@@ -105,6 +105,25 @@ def _initialize_state(self, start_bpm_hint, precomputed_noise_floor, precomputed
     state["consecutive_rr_rejections"] = 0
     state["loop_idx"] = 0
     return state
+
+
+def peak_trough_noise(audio_envelope: np.ndarray, noise_floor, raw_peaks: np.ndarray, trough_indices: np.ndarray,
+                      params: Dict) -> Dict[str, np.ndarray]:
+    """Surrounding-trough noise per raw peak (optional extra output, parity unpinned).
+
+    The reference documents this check (Documentation/Changelog.md:454, "BPM Detection logic
+    explained.md":262, :276-278) and keeps its parameters (config.py:30-31) but no longer has a
+    function for it.  Returns ``prev_amp``, ``next_amp`` (envelope at the sanitised trough before /
+    after each peak), ``ratio`` = deeper trough / floor at the peak and ``flags`` (bit 0: ratio >
+    ``trough_noise_multiplier``; bit 1: look-ahead veto with ``trough_veto_multiplier``)."""
+    env = np.ascontiguousarray(audio_envelope, dtype=np.float64)
+    floor = np.ascontiguousarray(getattr(noise_floor, "values", noise_floor), dtype=np.float64)
+    if floor.shape != env.shape:
+        raise ValueError("noise floor and envelope must have the same length")
+    return runtime.ops().peak_trough_noise(env, floor, np.asarray(raw_peaks, dtype=np.int64),
+                                           np.sort(np.asarray(trough_indices, dtype=np.int64)),
+                                           float(params.get("trough_noise_multiplier", 3.0)),
+                                           float(params.get("trough_veto_multiplier", 2.1)))
 
 
 def find_peaks(x, height=None, prominence=None, distance=None):

@@ -2,7 +2,7 @@
 
 The reference passes one flat dict (``config.py:3-108`` ``DEFAULT_PARAMS``) to
 every function.  This package consumes that dict unchanged; the table below
-only lists the 12 keys the data-parallel front end reads with
+only lists the keys the data-parallel front end reads (12 + 2 for the optional trough-noise metric) with
 the reference's default values, so the package is usable standalone.  Callers
 that already hold the reference's ``DEFAULT_PARAMS`` just pass it through.
 
@@ -32,6 +32,9 @@ HOT_PATH_DEFAULTS: Dict[str, object] = {
     "output_smoothing_window_sec": 5,
     "hrv_window_size_beats": 40,
     "hrv_step_size_beats": 5,
+    # read only by the optional surrounding-trough noise metric (frontend.peak_trough_noise)
+    "trough_veto_multiplier": 2.1,
+    "trough_noise_multiplier": 3.0,
 }
 
 # constants the reference hard-codes on the hot path (file:line in bpm_analysis.py)

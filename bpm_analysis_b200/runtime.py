@@ -410,6 +410,31 @@ class Ops:
         return pk[:c].cpu().numpy(), {"strength": st[:c].cpu().numpy(), "deviation": dv[:d].cpu().numpy(),
                                       "smoothed": sm[:d].cpu().numpy()}
 
+    def peak_trough_noise(self, env: np.ndarray, floor: np.ndarray, peaks: np.ndarray, troughs: np.ndarray,
+                          noise_mult: float, veto_mult: float) -> Dict[str, np.ndarray]:
+        n = len(env)
+        items, items_dev = self._items([n])
+        ed = to_device(np.asarray(env, dtype=np.float64))
+        fd = to_device(np.asarray(floor, dtype=np.float64))
+        pk = torch.zeros(max(n, 1), dtype=torch.int64, device=self.device)
+        tr = torch.zeros(max(n, 1), dtype=torch.int64, device=self.device)
+        if len(peaks):
+            pk[:len(peaks)] = to_device(np.asarray(peaks, dtype=np.int64))
+        if len(troughs):
+            tr[:len(troughs)] = to_device(np.asarray(troughs, dtype=np.int64))
+        pc = to_device(np.array([len(peaks)], dtype=np.int64))
+        tc = to_device(np.array([len(troughs)], dtype=np.int64))
+        f64 = dict(dtype=torch.float64, device=self.device)
+        pa, na, ra = torch.empty(n, **f64), torch.empty(n, **f64), torch.empty(n, **f64)
+        fl = torch.empty(n, dtype=torch.uint8, device=self.device)
+        nat.check(self.lib.bpm_peak_trough_noise(_ptr(ed), _ptr(fd), _ptr(pk), _ptr(pc), _ptr(tr), _ptr(tc),
+                                                 _ptr(items_dev), _host_ptr(items), 1, float(noise_mult),
+                                                 float(veto_mult), _ptr(pa), _ptr(na), _ptr(ra), _ptr(fl),
+                                                 _stream_ptr()))
+        c = len(peaks)
+        return {"prev_amp": pa[:c].cpu().numpy(), "next_amp": na[:c].cpu().numpy(), "ratio": ra[:c].cpu().numpy(),
+                "flags": fl[:c].cpu().numpy()}
+
     # ---- beat-list reductions
     def bpm_series(self, beats: np.ndarray, rate: int, window_us: int):
         b = len(beats)

@@ -162,6 +162,21 @@ int bpm_peak_metrics(const double* envelope, const double* floor, const int64_t*
                      int n_items, double smoothing_factor, double* strength, double* deviation,
                      double* smoothed, void* stream);
 
+/* ---- K8b: surrounding-trough noise per raw peak (optional extra output, PARITY UNPINNED) ----
+ * The reference's documentation describes it (Documentation/Changelog.md:454,
+ * "BPM Detection logic explained.md":262, :276-278) and its config keys survive
+ * (config.py:30-31: trough_veto_multiplier, trough_noise_multiplier), but no function of
+ * bpm_analysis.py computes it any more; the oracle is oracle/ref_port.py::peak_trough_noise.
+ *   prev_amp / next_amp: envelope at the sanitised trough just before / after each peak (NaN if
+ *   none); ratio = min(prev, next) / floor[peak]; flags bit 0: ratio > trough_noise_multiplier,
+ *   bit 1: look-ahead veto  m*(env[p]-next) < (env[p_next]-next).  Laid out like the peak list. */
+int bpm_peak_trough_noise(const double* envelope, const double* floor, const int64_t* peaks,
+                          const int64_t* peak_count, const int64_t* troughs, const int64_t* trough_count,
+                          const BpmItem* items, const BpmItem* items_host, int n_items,
+                          double trough_noise_multiplier, double trough_veto_multiplier,
+                          double* prev_amp, double* next_amp, double* ratio, unsigned char* flags,
+                          void* stream);
+
 /* ---- beat-list reductions (K9, K10, K12).  A "beat list" is int64 indices at the
  * envelope rate; lists of a batch are back to back, described by BpmItem with
  * m = number of beats and m_off = first beat (in_off / n_in unused).            */

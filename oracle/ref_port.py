@@ -164,6 +164,39 @@ def peak_metrics(envelope: np.ndarray, rate: int, params: Dict, floor: pd.Series
             "smoothed_dev_series": smoothed, "window": win}
 
 
+def peak_trough_noise(envelope: np.ndarray, floor: np.ndarray, peaks: np.ndarray, troughs: np.ndarray,
+                      params: Dict) -> Dict[str, np.ndarray]:
+    """Surrounding-trough noise per raw peak.  PARITY UNPINNED: bpm_analysis.py no longer has a
+    function for it; restated from Documentation/Changelog.md:454 ("the deeper of the two
+    troughs surrounding a peak"), "BPM Detection logic explained.md":262 (trough amplitude >
+    3 x noise floor => noisy; config.py:31) and :276-278 (look-ahead veto
+    2*(peak - next_trough) < (next_peak - next_trough); config.py:30 made the 2 a parameter)."""
+    nm = float(params.get("trough_noise_multiplier", 3.0))
+    vm = float(params.get("trough_veto_multiplier", 2.1))
+    peaks = np.asarray(peaks, dtype=np.int64)
+    troughs = np.asarray(troughs, dtype=np.int64)
+    n = len(peaks)
+    prev = np.full(n, np.nan)
+    nxt = np.full(n, np.nan)
+    ratio = np.full(n, np.nan)
+    flags = np.zeros(n, dtype=np.uint8)
+    for k, p in enumerate(peaks):
+        i_next = int(np.searchsorted(troughs, p, side="right"))
+        i_prev = int(np.searchsorted(troughs, p, side="left")) - 1
+        if i_prev >= 0:
+            prev[k] = envelope[troughs[i_prev]]
+        if i_next < len(troughs):
+            nxt[k] = envelope[troughs[i_next]]
+        deeper = np.nanmin([prev[k], nxt[k]]) if (i_prev >= 0 or i_next < len(troughs)) else np.nan
+        ratio[k] = deeper / floor[p]
+        if ratio[k] > nm:
+            flags[k] |= 1
+        if k + 1 < n and i_next < len(troughs) and troughs[i_next] < peaks[k + 1]:
+            if vm * (envelope[p] - nxt[k]) < (envelope[peaks[k + 1]] - nxt[k]):
+                flags[k] |= 2
+    return {"prev_amp": prev, "next_amp": nxt, "ratio": ratio, "flags": flags}
+
+
 # --------------------------------------------------------------------------- a5
 def calculate_bpm_series(peaks: np.ndarray, rate: int, params: Dict
                          ) -> Tuple[pd.Series, np.ndarray]:

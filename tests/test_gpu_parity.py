@@ -327,6 +327,26 @@ def test_full_size_properties_c2(fe, ref_params):
     assert torch.equal(runner.out["peaks"][:n], a["peaks"][:n])
 
 
+# ----------------------------------------------------------------------------- K8b (parity unpinned)
+@pytest.mark.parametrize("name", ["vulpine", "synth_c2_240s", "synth_holter_180s"])
+def test_peak_trough_noise_matches_oracle(name, fe, ref_params):
+    """Optional surrounding-trough noise metric: no reference function exists (SURVEY §8a note), so
+    the check is against the oracle's restatement of the documented rule -- bit for bit."""
+    from oracle import ref_port
+    g = load_golden(name)
+    env, floor, peaks, troughs = g["envelope"], g["floor"], g["raw_peaks"], g["troughs"]
+    p = dict(ref_params, trough_noise_multiplier=1.5)              # both flag values occur
+    got = fe.peak_trough_noise(env, floor, peaks, troughs, p)
+    ref = ref_port.peak_trough_noise(env, floor, peaks, troughs, p)
+    for k in ("prev_amp", "next_amp", "ratio"):
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+    assert np.array_equal(got["flags"], ref["flags"])
+    assert got["flags"].max() >= 1
+    # no troughs at all: everything NaN, no flags
+    none = fe.peak_trough_noise(env, floor, peaks, np.array([], dtype=np.int64), p)
+    assert np.all(np.isnan(none["ratio"])) and not none["flags"].any()
+
+
 # ----------------------------------------------------------------------------- ingest pipeline
 def test_pipelined_zero_copy_ingest_is_bit_identical(fe, ref_params):
     """runtime.StageAPipeline (bpm_gather_frames from pinned host memory, compute and read-back
