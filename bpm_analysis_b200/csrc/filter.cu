@@ -464,39 +464,22 @@ __device__ __forceinline__ int64_t tile_slot0(const BpmItem& it, int item) {
   return it.m_off / SCAN_TILE + item;
 }
 
-// input term of sample r of this item's scan (and, backward, the forward-pass output y_f there)
-template <int DIR, int SRC>
-__device__ __forceinline__ void scan_input(const ScanParams& p, const BpmItem& it, const double* __restrict__ sm_P,
-                                           const double* __restrict__ sm_C, double Dd, const double* __restrict__ w0,
-                                           const double* __restrict__ w1, int64_t r, double u[4], double* yf) {
-  const int64_t j = (DIR == 0) ? r : (it.m - 2 - r);
-  if (SRC == 0) {
-    const double2* pu = reinterpret_cast<const double2*>(p.u + 4 * (it.m_off + j));
-    const double2 a = pu[0], bb = pu[1];
-    u[0] = a.x; u[1] = a.y; u[2] = bb.x; u[3] = bb.y;
-  } else if (DIR == 0) {
-    const double xj = p.xe[it.m_off + j];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = w0[k] * xj;
-  } else {
-    const double xj = p.xe[it.m_off + j], xn = p.xe[it.m_off + j + 1];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = w0[k] * xj + w1[k] * xn;
-  }
-  if (DIR == 1) {
-    const double2* ps = reinterpret_cast<const double2*>(p.sf + 4 * (it.m_off + j));
-    const double2 s01 = ps[0], s23 = ps[1];
-    const double sv[4] = {s01.x, s01.y, s23.x, s23.y};
-    double t4[4];
-    matvec4(sm_P, sv, t4);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] += t4[k];
-    *yf = sm_C[0] * sv[0] + sm_C[1] * sv[1] + sm_C[2] * sv[2] + sm_C[3] * sv[3] + Dd * p.xe[it.m_off + j];
-  }
-}
+// Shared-memory staging of a warp's 256 samples: 4-vector input terms as double2 pairs, one pad
+// slot per 16 so that both the coalesced fill (consecutive lanes -> consecutive slots) and the
+// per-thread reads (lane stride 16 slots + 1) are bank-conflict free.
+constexpr int SCAN_WARP_SAMPLES = 32 * SCAN_CHUNK;
+constexpr int SCAN_BUF_SLOTS = 2 * SCAN_WARP_SAMPLES + (2 * SCAN_WARP_SAMPLES) / 16;
+__device__ __forceinline__ int scan_slot(int e) { return e + (e >> 4); }
+
+#ifdef BPM_DEBUG_COUNTERS
+__device__ unsigned long long g_dbg_scan[16];
+#define SC_TICK(i) do { if (threadIdx.x == 0) { long long t_ = clock64(); atomicAdd(&g_dbg_scan[(i) + 8 * DIR], (unsigned long long)(t_ - t_phase)); t_phase = t_; } } while (0)
+#else
+#define SC_TICK(i)
+#endif
 
 template <int DIR /*0 fwd, 1 bwd*/, int SRC /*0 staged uf/ub0, 1 block == 1 on the fly*/>
-__global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan(ScanParams p) {
+__global__ void __launch_bounds__(SCAN_THREADS, DIR == 0 ? 3 : 2) k_scan(ScanParams p) {
   __shared__ double sm_pow[9 * 16];      // Ad^(CHUNK*2^k), k = 0..8
   __shared__ double sm_Ad[16], sm_P[16], sm_C[4];
   __shared__ double sm_tot[SCAN_THREADS / 32][4];
@@ -527,48 +510,106 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan(ScanParams p) {
     }
   }
   if (r0 >= ns) return;
+#ifdef BPM_DEBUG_COUNTERS
+  long long t_phase = clock64();
+#endif
 
   for (int t = tid; t < 9 * 16; t += SCAN_THREADS) sm_pow[t] = d.pw(0)[t];
   if (tid < 16) { sm_Ad[tid] = d.Ad()[tid]; sm_P[tid] = d.P()[tid]; }
   if (tid < 4) sm_C[tid] = d.C()[tid];
   __syncthreads();
 
+  SC_TICK(0);
   const int64_t rbeg = r0 + static_cast<int64_t>(tid) * SCAN_CHUNK;
-  double w0[4] = {0, 0, 0, 0}, w1[4] = {0, 0, 0, 0};
-  if (SRC == 1) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      w0[k] = (DIR == 0) ? d.wf()[k] : d.q()[k];
-      w1[k] = (DIR == 0) ? 0.0 : d.q()[4 + k];
-    }
-  }
+  extern __shared__ __align__(16) unsigned char scan_dyn[];
+  double2* buf = reinterpret_cast<double2*>(scan_dyn) + warp * SCAN_BUF_SLOTS;          // this warp's input terms
+  double* yfs = reinterpret_cast<double*>(scan_dyn + sizeof(double2) * SCAN_BUF_SLOTS * (SCAN_THREADS / 32)) +
+                warp * SCAN_WARP_SAMPLES;                                             // BWD: forward-pass outputs y_f
+  // The warp's samples are one contiguous ascending run of j: [j_lo, j_lo + 256).  Local sample sl
+  // belongs to scan position r = rw + sl (FWD) or r = rw + 255 - sl (BWD).
+  const int64_t rw = r0 + static_cast<int64_t>(warp) * SCAN_WARP_SAMPLES;
+  const int64_t j_lo = (DIR == 0) ? rw : (it.m - 2 - rw - (SCAN_WARP_SAMPLES - 1));
+
+  // ---- fill: coalesced loads, all of a thread's loads independent and in flight together
   if (SRC == 1 && DIR == 0) {
-    // gather this thread's strided frames: SCAN_CHUNK independent loads in flight; they stay in
-    // xe for the second sweep below and for the backward pass
+    // decimate-first forward pass: gather the strided PCM frames (device memory or mapped pinned
+    // host memory), leave them in xe for the backward pass, u = wf[0] * x
     const ExtSignal x = make_ext(p.pcm, it, p.stride);
+    const double* __restrict__ wf = d.wf();
+    const double w0 = wf[0], w1 = wf[1], w2 = wf[2], w3 = wf[3];
     double xv[SCAN_CHUNK];
 #pragma unroll
-    for (int c = 0; c < SCAN_CHUNK; ++c) {
-      const int64_t r = rbeg + c;
-      xv[c] = (r < ns) ? x.at(PADLEN + r) : 0.0;
+    for (int i = 0; i < SCAN_CHUNK; ++i) {
+      const int64_t j = j_lo + i * 32 + lane;
+      xv[i] = (j < ns) ? x.at(PADLEN + j) : 0.0;
     }
 #pragma unroll
-    for (int c = 0; c < SCAN_CHUNK; ++c) {
-      const int64_t r = rbeg + c;
-      if (r < ns) p.xe[it.m_off + r] = xv[c];
-      if (r == ns - 1) p.xe[it.m_off + it.m - 1] = x.at(PADLEN + it.m - 1);
+    for (int i = 0; i < SCAN_CHUNK; ++i) {
+      const int sl = i * 32 + lane;
+      const int64_t j = j_lo + sl;
+      if (j < ns) {
+        p.xe[it.m_off + j] = xv[i];
+        buf[scan_slot(2 * sl)] = make_double2(w0 * xv[i], w1 * xv[i]);
+        buf[scan_slot(2 * sl + 1)] = make_double2(w2 * xv[i], w3 * xv[i]);
+        if (j == ns - 1) p.xe[it.m_off + it.m - 1] = x.at(PADLEN + it.m - 1);
+      }
+    }
+  } else {
+    const int h = lane & 1;                                     // which half of the 4-vector this lane carries
+    double q0a = 0, q0b = 0, q1a = 0, q1b = 0;
+    if (SRC == 1) { q0a = d.q()[2 * h]; q0b = d.q()[2 * h + 1]; q1a = d.q()[4 + 2 * h]; q1b = d.q()[4 + 2 * h + 1]; }
+    const double2* gu = reinterpret_cast<const double2*>(p.u + 4 * (it.m_off + j_lo));
+    const double2* gs = reinterpret_cast<const double2*>(p.sf + 4 * (it.m_off + j_lo));
+    constexpr int FB = 4;                                       // loads in flight per array and thread
+#pragma unroll 1
+    for (int ib = 0; ib < 2 * SCAN_CHUNK; ib += FB) {
+      double2 vu[FB], vs[FB];
+      double xj[FB], xn[FB];
+#pragma unroll
+      for (int k = 0; k < FB; ++k) {
+        const int e = (ib + k) * 32 + lane;
+        const int64_t j = j_lo + (e >> 1);
+        const bool ok = (j >= 0 && j < ns);
+        vu[k] = make_double2(0.0, 0.0); vs[k] = vu[k]; xj[k] = 0.0; xn[k] = 0.0;
+        if (ok) {
+          if (SRC == 0) vu[k] = gu[e];
+          if (DIR == 1) { vs[k] = gs[e]; xj[k] = p.xe[it.m_off + j]; }
+          if (SRC == 1) xn[k] = p.xe[it.m_off + j + 1];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < FB; ++k) {
+        const int e = (ib + k) * 32 + lane;
+        const int64_t j = j_lo + (e >> 1);
+        const bool ok = (j >= 0 && j < ns);
+        double2 v = vu[k];
+        if (SRC == 1) v = make_double2(q0a * xj[k] + q1a * xn[k], q0b * xj[k] + q1b * xn[k]);
+        if (DIR == 1) {
+          // the partner lane holds the other half of s_f[j]
+          const double ox = __shfl_xor_sync(0xffffffffu, vs[k].x, 1), oy = __shfl_xor_sync(0xffffffffu, vs[k].y, 1);
+          const double sv[4] = {h ? ox : vs[k].x, h ? oy : vs[k].y, h ? vs[k].x : ox, h ? vs[k].y : oy};
+          const double* Pr = sm_P + 8 * h;                      // rows 2h, 2h+1 of P
+          v.x += Pr[0] * sv[0] + Pr[1] * sv[1] + Pr[2] * sv[2] + Pr[3] * sv[3];
+          v.y += Pr[4] * sv[0] + Pr[5] * sv[1] + Pr[6] * sv[2] + Pr[7] * sv[3];
+          if (ok && h == 0)
+            yfs[e >> 1] = sm_C[0] * sv[0] + sm_C[1] * sv[1] + sm_C[2] * sv[2] + sm_C[3] * sv[3] + Dd * xj[k];
+        }
+        if (ok) buf[scan_slot(e)] = v;
+      }
     }
   }
+  __syncwarp();
+  SC_TICK(1);
 
-  // ---- sweep 1: aggregate of this thread's chunk from a zero state (inputs are not kept in
-  //      registers: sweep 2 re-reads them through L1 / L2, which keeps three CTAs per SM resident)
+  // ---- sweep 1: aggregate of this thread's chunk from a zero state
   double z[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int c = 0; c < SCAN_CHUNK; ++c) {
     const int64_t r = rbeg + c;
     if (r < ns) {
-      double u[4], yf;
-      scan_input<DIR, SRC>(p, it, sm_P, sm_C, Dd, w0, w1, r, u, &yf);
+      const int sl = (DIR == 0) ? (lane * SCAN_CHUNK + c) : (SCAN_WARP_SAMPLES - 1 - (lane * SCAN_CHUNK + c));
+      const double2 a = buf[scan_slot(2 * sl)], bb = buf[scan_slot(2 * sl + 1)];
+      const double u[4] = {a.x, a.y, bb.x, bb.y};
       affine4(sm_Ad, z, u);
     }
   }
@@ -592,6 +633,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan(ScanParams p) {
     for (int c = 0; c < 4; ++c) sm_tot[warp][c] = z[c];
   }
   __syncthreads();
+  SC_TICK(2);
   if (warp == 0) {
     const int64_t slot0 = tile_slot0(it, item);
     const int64_t b = blockIdx.x;
@@ -605,6 +647,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan(ScanParams p) {
       __threadfence();
       atomicExch(p.flags + slot0 + b, 1);
     }
+    SC_TICK(3);
     // look back over the preceding tiles' aggregates (contraction makes older ones vanish).
     // The lanes wait for / fetch 32 tiles at a time concurrently; lane 0 then folds them in
     // oldest first:  start <- Ad^tile start + agg[t].
@@ -634,6 +677,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan(ScanParams p) {
         affine4(sm_pow + 8 * 16, start, gl);
       }
     }
+    SC_TICK(4);
     if (lane == 0) {
       // state at the start of every warp's stretch
       for (int w = 0; w < SCAN_THREADS / 32; ++w) {
@@ -645,6 +689,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan(ScanParams p) {
   }
   __syncthreads();
 
+  SC_TICK(5);
   // state before this thread's chunk = Ad^(CHUNK*lane) * warp_start + (inclusive state of lane-1)
   double st[4];
 #pragma unroll
@@ -667,14 +712,15 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan(ScanParams p) {
     for (int c = 0; c < 4; ++c) st[c] += pre[c];
   }
 
-  // ---- sweep 2: apply
+  // ---- sweep 2: apply (input terms come back out of shared memory)
   double amax = 0.0;
 #pragma unroll
   for (int c = 0; c < SCAN_CHUNK; ++c) {
     const int64_t r = rbeg + c;
     if (r < ns) {
-      double u[4], yf = 0.0;
-      scan_input<DIR, SRC>(p, it, sm_P, sm_C, Dd, w0, w1, r, u, &yf);
+      const int sl = (DIR == 0) ? (lane * SCAN_CHUNK + c) : (SCAN_WARP_SAMPLES - 1 - (lane * SCAN_CHUNK + c));
+      const double2 a = buf[scan_slot(2 * sl)], bb = buf[scan_slot(2 * sl + 1)];
+      const double u[4] = {a.x, a.y, bb.x, bb.y};
       affine4(sm_Ad, st, u);
       if (DIR == 0) {
         double2* po = reinterpret_cast<double2*>(p.sf + 4 * (it.m_off + r + 1));
@@ -683,12 +729,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, 3) k_scan(ScanParams p) {
       } else {
         const int64_t j = it.m - 2 - r;
         const double yb = sm_C[0] * st[0] + sm_C[1] * st[1] + sm_C[2] * st[2] + sm_C[3] * st[3];
-        const double yy = yb + Dd * yf;
+        const double yy = yb + Dd * yfs[sl];
         p.y[it.m_off + j] = yy;
         amax = fmax(amax, fabs(yy));
       }
     }
   }
+  SC_TICK(6);
   if (DIR == 1) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -844,9 +891,16 @@ int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
   const dim3 sgrid(cdiv(sh.max_m > 1 ? sh.max_m - 1 : 1, SCAN_TILE), n_items);
   ScanParams sp{items, design, b.uf, b.sf, b.xe, b.s0, b.agg, b.flags, filtered,
                 reinterpret_cast<unsigned long long*>(absmax), pv, stride};
+  const size_t scan_smem_f = sizeof(double2) * SCAN_BUF_SLOTS * (SCAN_THREADS / 32);
+  const size_t scan_smem_b = scan_smem_f + sizeof(double) * SCAN_TILE;
   BPM_KERNEL(k_scan);
-  if (block == 1) k_scan<0, 1><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
-  else k_scan<0, 0><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
+  if (block == 1) {
+    cudaFuncSetAttribute(k_scan<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scan_smem_f));
+    k_scan<0, 1><<<sgrid, SCAN_THREADS, scan_smem_f, st>>>(sp);
+  } else {
+    cudaFuncSetAttribute(k_scan<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scan_smem_f));
+    k_scan<0, 0><<<sgrid, SCAN_THREADS, scan_smem_f, st>>>(sp);
+  }
   BPM_LAUNCH_OK();
   {
     const size_t smem = sizeof(double) * FE_WARPS * b.tail_cap;
@@ -861,8 +915,13 @@ int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
   sp.agg = b.agg + 4 * b.tiles;
   sp.flags = b.flags + b.tiles;
   BPM_KERNEL(k_scan);
-  if (block == 1) k_scan<1, 1><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
-  else k_scan<1, 0><<<sgrid, SCAN_THREADS, 0, st>>>(sp);
+  if (block == 1) {
+    cudaFuncSetAttribute(k_scan<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scan_smem_b));
+    k_scan<1, 1><<<sgrid, SCAN_THREADS, scan_smem_b, st>>>(sp);
+  } else {
+    cudaFuncSetAttribute(k_scan<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scan_smem_b));
+    k_scan<1, 0><<<sgrid, SCAN_THREADS, scan_smem_b, st>>>(sp);
+  }
   BPM_LAUNCH_OK();
   BPM_KERNEL(k_envelope);
   k_envelope<<<dim3(cdiv(sh.max_m, ENV_THREADS), n_items), ENV_THREADS,

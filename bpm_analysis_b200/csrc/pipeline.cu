@@ -262,6 +262,12 @@ const char* bpm_error_string(int code) {
 int64_t bpm_launch_count(void) { return g_launches; }
 
 #ifdef BPM_DEBUG_COUNTERS
+int bpm_debug_counters_scan(unsigned long long* out_host, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out_host, g_dbg_scan, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_dbg_scan, z, sizeof(z)); }
+  return 0;
+}
 int bpm_debug_counters(unsigned long long* out_host, int reset) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out_host, g_dbg, sizeof(unsigned long long) * 16);

@@ -41,6 +41,8 @@ def main():
     p = default_params()
     p["save_filtered_wav"] = False
     dur = float(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1][0] != "-" else 3600.0
+    if len(sys.argv) > 2 and sys.argv[2] in ("parity", "fullrate"):
+        p["filter_mode"] = sys.argv[2]
     pcm, sr, _ = synth.config_c2(seed=2, duration_sec=dur)
     A = StageARunner([len(pcm)], sr, p)
     A.upload([pcm])
@@ -52,6 +54,21 @@ def main():
     torch.cuda.synchronize()
     lib.bpm_debug_counters(buf, 1)
     v = np.array(list(buf), dtype=np.float64)
+    if hasattr(lib, "bpm_debug_counters_scan"):
+        lib.bpm_debug_counters_scan.restype = C.c_int
+        lib.bpm_debug_counters_scan.argtypes = [C.c_void_p, C.c_int]
+        sb = (C.c_ulonglong * 16)()
+        lib.bpm_debug_counters_scan(sb, 1)
+        A.launch()
+        torch.cuda.synchronize()
+        lib.bpm_debug_counters_scan(sb, 1)
+        sv = np.array(list(sb), dtype=np.float64)
+        sn = ["constants", "fill", "sweep1+warp scan", "publish", "look-back", "prefixes", "sweep2"]
+        for dname, o in (("fwd", 0), ("bwd", 8)):
+            tot = sv[o:o + 7].sum()
+            print(f"k_scan {dname}: thread-0 cycles summed over CTAs {tot:.3e}")
+            for i, nme in enumerate(sn):
+                print(f"  {nme:18s} {sv[o + i]:.3e}  {100 * sv[o + i] / max(tot, 1):5.1f} %")
     names = ["stage", "probes", "splitters", "bucket ids", "scan+scatter", "in-bucket+perm", "table", "slide"]
     tot = v[:8].sum()
     print(f"cycles summed over CTAs of 2 launches: {tot:.3e}; repeated CTAs: {int(v[15])}")
