@@ -41,14 +41,19 @@ __device__ __forceinline__ long long n_obs_at(long long i, long long m, long lon
   return hi - lo + 1;
 }
 
+// mode[item] == 1 selects the alternative knot list (the reference falls back to the draft floor,
+// i.e. the floor over ALL troughs, when <= 2 troughs survive sanitisation, :1107-1110).
 __global__ void k_knot_table(const double* __restrict__ env, const int64_t* __restrict__ knots,
-                             const int64_t* __restrict__ knot_count, const BpmItem* __restrict__ items,
+                             const int64_t* __restrict__ knot_count, const int64_t* __restrict__ alt_knots,
+                             const int64_t* __restrict__ alt_count, const int* __restrict__ mode,
+                             const BpmItem* __restrict__ items,
                              int window, int* __restrict__ kt32, double* __restrict__ kv, double* __restrict__ ks,
                              double* __restrict__ kinv, double* __restrict__ kend, FloorMeta* __restrict__ meta) {
   const int item = blockIdx.y;
   const BpmItem it = items[item];
-  const long long T = knot_count[item];
-  const int64_t* kt = knots + it.m_off;
+  const bool use_alt = (mode != nullptr && alt_knots != nullptr && mode[item] == 1);
+  const long long T = use_alt ? alt_count[item] : knot_count[item];
+  const int64_t* kt = (use_alt ? alt_knots : knots) + it.m_off;
   const double* e = env + it.m_off;
   const long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k < T) {
@@ -464,11 +469,12 @@ __device__ void cached_start(const WinCtx& c, short* cs, int a, int b, int ka, i
   cached_settle(c, cs, a, b, ka, kb, idx, st);
 }
 
-// mode[item]: 0 = rolling quantile over the knots; 1 = copy alt[]; 2 = constant cval[item].
+// mode[item]: 0 / 1 = rolling quantile over the knot table (k_knot_table picked the list);
+// 2 = constant cval[item].
 // nan_fill (optional): value written instead of NaN when no output is valid.
 __global__ void __launch_bounds__(RF_THREADS) k_rolling_floor(
     const BpmItem* __restrict__ items, KnotTable kt, const FloorMeta* __restrict__ meta, int window, double q,
-    int run, const int* __restrict__ mode, const double* __restrict__ alt, const double* __restrict__ cval,
+    int run, const int* __restrict__ mode, const double* __restrict__ cval,
     const double* __restrict__ nan_fill, double* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char rf_smem[];
   short* cs = reinterpret_cast<short*>(rf_smem) + threadIdx.x;       // [RF_SMAX][RF_THREADS]
@@ -485,11 +491,6 @@ __global__ void __launch_bounds__(RF_THREADS) k_rolling_floor(
   if (md == 2) {
     const double c = cval[item];
     for (long long i = first; i < last; ++i) o[i] = c;
-    return;
-  }
-  if (md == 1) {
-    const double* a = alt + it.m_off;
-    for (long long i = first; i < last; ++i) { const double v = a[i]; o[i] = isnan(v) ? nanv : v; }
     return;
   }
   const FloorMeta mt = meta[item];
@@ -726,6 +727,7 @@ struct RbShared {
   int fail;
   int probes_ok;
   int k_lo, k_hi;                      // knots around the tile's first / last sample
+  int kf, kl;                          // knots positioned inside the tile's output range
 };
 
 // in-window test on a perm entry: j in [a, a + span]  (RB_ABOVE never is: 65535 - a > span)
@@ -740,8 +742,8 @@ __device__ __forceinline__ bool rb_in(unsigned int j, int a, unsigned int span) 
 
 __global__ void __launch_bounds__(RB_THREADS, 1) k_rolling_floor_blk(
     const BpmItem* __restrict__ items, KnotTable kt, const FloorMeta* __restrict__ meta, int window, double q,
-    int outs, const int* __restrict__ mode, const double* __restrict__ alt, const double* __restrict__ cval,
-    const double* __restrict__ nan_fill, double* __restrict__ out) {
+    int outs, const int* __restrict__ mode, const double* __restrict__ cval,
+    const double* __restrict__ nan_fill, double* __restrict__ out, double* __restrict__ sparse_out) {
   extern __shared__ __align__(16) unsigned char rb_raw[];
   RbShared& sh = *reinterpret_cast<RbShared*>(rb_raw);
   const int item = blockIdx.y;
@@ -754,18 +756,21 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rolling_floor_blk(
   const int tid = threadIdx.x;
   const int md = mode ? mode[item] : 0;
   const double nanv = nan_fill ? nan_fill[item] : __longlong_as_double(0x7ff8000000000000ll);
+  // SPARSE mode (sparse_out != nullptr): outputs are wanted only AT the knots (the draft floor is
+  // read nowhere else, :1093) and are written per knot number; tiles without knots do nothing.
+  const bool sparse = (sparse_out != nullptr);
   if (md == 2) {
+    if (sparse) return;                                       // the "<5 troughs" path never reads the draft
     const double c = cval[item];
     for (long long i = blk_first + tid; i < blk_last; i += RB_THREADS) o[i] = c;
     return;
   }
-  if (md == 1) {
-    const double* al = alt + it.m_off;
-    for (long long i = blk_first + tid; i < blk_last; i += RB_THREADS) { const double v = al[i]; o[i] = isnan(v) ? nanv : v; }
-    return;
-  }
   const FloorMeta mt = meta[item];
   if (!mt.valid) {
+    if (sparse) {
+      if (blockIdx.x == 0) for (long long k = tid; k < mt.n_knots; k += RB_THREADS) sparse_out[it.m_off + k] = nanv;
+      return;
+    }
     for (long long i = blk_first + tid; i < blk_last; i += RB_THREADS) o[i] = nanv;
     return;
   }
@@ -793,7 +798,19 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rolling_floor_blk(
   // ---- S1: interpolated samples -> shared memory
   if (tid == 0) sh.k_lo = knot_at_or_before(c, x0);
   if (tid == 32) sh.k_hi = knot_at_or_before(c, x1);
+  if (tid == 64 || tid == 96) {
+    // knots whose position lies in this tile's output range: [kf, kl)
+    const long long bound = (tid == 64) ? blk_first : blk_last;
+    int lo = 0, hi = c.T;                                     // first knot with t >= bound
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (c.t[mid] >= bound) hi = mid; else lo = mid + 1;
+    }
+    if (tid == 64) sh.kf = lo; else sh.kl = lo;
+  }
   __syncthreads();
+  const int kf = sh.kf, kcnt = sh.kl - sh.kf;
+  if (sparse && kcnt <= 0) return;
   {
     const int per = (n + RB_THREADS - 1) / RB_THREADS;
     const int j0 = tid * per, j1 = min(n, j0 + per);
@@ -1018,16 +1035,21 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rolling_floor_blk(
 
     // ---- S5: every thread slides over its run
     bool failed = false;
-    if (first < blk_last) {
+    const long long nsteps = sparse ? ((kcnt > tid) ? (kcnt - tid + RB_THREADS - 1) / RB_THREADS : 0)
+                                    : ((first < blk_last) ? (last - first) : 0);
+    if (nsteps > 0) {
       bool have = false;
       int p = 0, cb = 0;            // position in sorted order; in-window entries at positions < p
       double prev_out = 0.0;
       int prev_i = -2, a_prev = 0, b_prev = 0;
-      for (long long io = first; io < last && !failed; ++io) {
+      for (long long step = 0; step < nsteps && !failed; ++step) {
+        const long long ks = kf + tid + step * RB_THREADS;      // sparse: the knot this output belongs to
+        const long long io = sparse ? static_cast<long long>(c.t[ks]) : first + step;
+        double* dst = sparse ? (sparse_out + it.m_off + ks) : (o + io);
         int i = static_cast<int>(io);
         if (i < mt.iv0) i = static_cast<int>(mt.iv0);
         if (i > mt.iv1) i = static_cast<int>(mt.iv1);
-        if (i == prev_i) { o[io] = prev_out; continue; }
+        if (i == prev_i) { *dst = prev_out; continue; }
         int bb = i + off; if (bb > mi - 1) bb = mi - 1;
         int aa = i - left; if (aa < 0) aa = 0; if (aa < t0) aa = t0;
         const int nw = bb - aa + 1;
@@ -1100,7 +1122,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rolling_floor_blk(
           const double vhigh = sh.d[sh.perm[p2]];
           res = __dadd_rn(vlow, __dmul_rn(__dsub_rn(vhigh, vlow), frac));
         }
-        o[io] = res;
+        *dst = res;
         prev_out = res; prev_i = i; a_prev = a; b_prev = b;
       }
     }
@@ -1123,7 +1145,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rolling_floor_blk(
 __global__ void k_sanitize_flags(const double* __restrict__ env, const double* __restrict__ draft,
                                  const int64_t* __restrict__ troughs, const int64_t* __restrict__ trough_count,
                                  const int* __restrict__ keep_all, const BpmItem* __restrict__ items, double mult,
-                                 unsigned char* __restrict__ flags) {
+                                 int draft_by_knot, unsigned char* __restrict__ flags) {
   const int item = blockIdx.y;
   const BpmItem it = items[item];
   const long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -1131,7 +1153,7 @@ __global__ void k_sanitize_flags(const double* __restrict__ env, const double* _
   bool keep = true;
   if (!(keep_all && keep_all[item])) {
     const int64_t t = troughs[it.m_off + k];
-    const double f = draft[it.m_off + t];
+    const double f = draft_by_knot ? draft[it.m_off + k] : draft[it.m_off + t];   // dense floor, or one value per trough
     keep = !isnan(f) && env[it.m_off + t] <= __dmul_rn(mult, f);
   }
   flags[it.m_off + k] = keep ? 1 : 0;
@@ -1177,16 +1199,24 @@ size_t rolling_floor_workspace_bytes(int64_t total_m, int n_items) {
   return ws.used;
 }
 
+// can the draft floor be computed at the knots only (block-cooperative kernel available)?
+bool rolling_floor_sparse_ok(int window) { return static_cast<int64_t>(RB_NCAP) - window + 1 >= RB_THREADS; }
+
+// sparse_out != nullptr (only with rolling_floor_sparse_ok): values at the knots, per knot number;
+// `out` is then not written.  alt_knots / alt_count: the list used for items with mode == 1.
 int rolling_floor_run(const double* env, const int64_t* knots, const int64_t* knot_count, const BpmItem* items,
-                      const BatchShape& sh, int window, double q, const int* mode, const double* alt,
-                      const double* cval, const double* nan_fill, double* out, Workspace& ws, cudaStream_t st) {
-  if (!env || !knots || !knot_count || !items || !out || sh.n_items <= 0 || window < 1) return BPM_ERR_ARG;
+                      const BatchShape& sh, int window, double q, const int* mode, const int64_t* alt_knots,
+                      const int64_t* alt_count, const double* cval, const double* nan_fill, double* out,
+                      double* sparse_out, Workspace& ws, cudaStream_t st) {
+  if (!env || !knots || !knot_count || !items || (!out && !sparse_out) || sh.n_items <= 0 || window < 1) return BPM_ERR_ARG;
+  if (sparse_out && !rolling_floor_sparse_ok(window)) return BPM_ERR_ARG;
   FloorBuffers b;
   BPM_TRY(carve_floor(ws, sh.total_m, sh.n_items, &b));
   const int64_t max_k = sh.max_m / 2 + 2;
   BPM_KERNEL(k_knot_table);
-  k_knot_table<<<dim3(cdiv(max_k, 256), sh.n_items), 256, 0, st>>>(env, knots, knot_count, items, window,
-                                                                    b.kt32, b.kv, b.ks, b.kinv, b.kend, b.meta);
+  k_knot_table<<<dim3(cdiv(max_k, 256), sh.n_items), 256, 0, st>>>(env, knots, knot_count, alt_knots, alt_count, mode,
+                                                                    items, window, b.kt32, b.kv, b.ks, b.kinv, b.kend,
+                                                                    b.meta);
   BPM_LAUNCH_OK();
   // outputs per thread of the per-thread kernel: long enough to amortise the bisection
   int64_t run = sh.total_m / (148 * 1024);
@@ -1206,7 +1236,7 @@ int rolling_floor_run(const double* env, const int64_t* knots, const int64_t* kn
     cudaFuncSetAttribute(k_rolling_floor_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(RbShared)));
     BPM_KERNEL(k_rolling_floor_blk);
     k_rolling_floor_blk<<<dim3(cdiv(sh.max_m, outs), sh.n_items), RB_THREADS, sizeof(RbShared), st>>>(
-        items, kt, b.meta, window, q, static_cast<int>(outs), mode, alt, cval, nan_fill, out);
+        items, kt, b.meta, window, q, static_cast<int>(outs), mode, cval, nan_fill, out, sparse_out);
     BPM_LAUNCH_OK();
     return BPM_OK;
   }
@@ -1214,7 +1244,7 @@ int rolling_floor_run(const double* env, const int64_t* knots, const int64_t* kn
   cudaFuncSetAttribute(k_rolling_floor, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   BPM_KERNEL(k_rolling_floor);
   k_rolling_floor<<<dim3(cdiv(sh.max_m, RF_THREADS * run), sh.n_items), RF_THREADS, smem, st>>>(
-      items, kt, b.meta, window, q, static_cast<int>(run), mode, alt, cval, nan_fill, out);
+      items, kt, b.meta, window, q, static_cast<int>(run), mode, cval, nan_fill, out);
   BPM_LAUNCH_OK();
   return BPM_OK;
 }

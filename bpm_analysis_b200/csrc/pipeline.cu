@@ -20,6 +20,8 @@ int gather_frames_run(const void* pcm, int pcm_dtype, int channels, const BpmIte
 size_t quantile_workspace_bytes(int n_items);
 int quantile_run(const double* x, const BpmItem* items, const BatchShape& sh, double q, const int* cond,
                  double* out, Workspace& ws, cudaStream_t st);
+int quantile_multi_run(const double* x, const BpmItem* items, const BatchShape& sh, int nq, const double* q,
+                       const int* const* cond, double* const* out, Workspace& ws, cudaStream_t st);
 // peaks.cu
 size_t find_peaks_workspace_bytes(int64_t total_m, int n_items);
 int find_peaks_run(const double* x, int sign, const double* height, const double* prominence, int distance,
@@ -30,11 +32,13 @@ int compact_run(const unsigned char* flags, const int64_t* src, const BpmItem* i
                 int64_t* out_count, cudaStream_t st);
 // floor.cu
 size_t rolling_floor_workspace_bytes(int64_t total_m, int n_items);
+bool rolling_floor_sparse_ok(int window);
 int rolling_floor_run(const double* env, const int64_t* knots, const int64_t* knot_count, const BpmItem* items,
-                      const BatchShape& sh, int window, double q, const int* mode, const double* alt,
-                      const double* cval, const double* nan_fill, double* out, Workspace& ws, cudaStream_t st);
+                      const BatchShape& sh, int window, double q, const int* mode, const int64_t* alt_knots,
+                      const int64_t* alt_count, const double* cval, const double* nan_fill, double* out,
+                      double* sparse_out, Workspace& ws, cudaStream_t st);
 __global__ void k_sanitize_flags(const double*, const double*, const int64_t*, const int64_t*, const int*,
-                                 const BpmItem*, double, unsigned char*);
+                                 const BpmItem*, double, int, unsigned char*);
 __global__ void k_floor_modes(const int64_t*, const int64_t*, int, int, int*, int*);
 // metrics.cu
 int peak_metrics_run(const double* env, const double* floor_, const int64_t* peaks, const int64_t* peak_count,
@@ -117,9 +121,17 @@ int noise_floor_run(const double* env, const BpmItem* items, const BatchShape& s
   NoiseFloorScratch s;
   BPM_TRY(carve_noise_floor(ws, sh.total_m, n, &s));
   double* q_tp = q_tp_out ? q_tp_out : s.q_tp;
+  const double* q_fb = q_tp;
   {
+    // every quantile of the envelope this stage can need, resolved in ONE set of radix passes:
+    // q(trough_prominence) (:1067), q(noise_floor_quantile) for the "<5 troughs" path (:1075 -- computed
+    // unconditionally, it costs no extra launch) and q(0.1) for the all-NaN path (:1114)
+    double qs[3] = {trough_prom_q, floor_q, 0.1};
+    double* outs[3] = {q_tp, s.q_nf, s.q_fb};
+    int nq = 2;
+    if (trough_prom_q != 0.1) { nq = 3; q_fb = s.q_fb; }
     Workspace w = sub_ws(ws, 0);
-    BPM_TRY(quantile_run(env, items, sh, trough_prom_q, nullptr, q_tp, w, st));                 // :1067
+    BPM_TRY(quantile_multi_run(env, items, sh, nq, qs, nullptr, outs, w, st));
   }
   {
     Workspace w = sub_ws(ws, 0);
@@ -128,25 +140,18 @@ int noise_floor_run(const double* env, const BpmItem* items, const BatchShape& s
   BPM_KERNEL(k_floor_modes);
   k_floor_modes<<<cdiv(n, 128), 128, 0, st>>>(s.n_all, nullptr, n, 0, s.few, s.mode);
   BPM_LAUNCH_OK();
+  // draft floor from all troughs (:1081-1086).  It is only ever read AT the troughs (:1093), so it
+  // is computed there only (one value per trough) whenever the block-cooperative kernel applies.
+  const bool sparse = rolling_floor_sparse_ok(window);
   {
     Workspace w = sub_ws(ws, 0);
-    BPM_TRY(quantile_run(env, items, sh, floor_q, s.few, s.q_nf, w, st));                          // :1075
-  }
-  const double* q_fb = q_tp;
-  if (trough_prom_q != 0.1) {
-    Workspace w = sub_ws(ws, 0);
-    BPM_TRY(quantile_run(env, items, sh, 0.1, nullptr, s.q_fb, w, st));                            // :1114
-    q_fb = s.q_fb;
-  }
-  {
-    // draft floor from all troughs (:1081-1086); skipped (constant, unused) on the "<5" path
-    Workspace w = sub_ws(ws, 0);
-    BPM_TRY(rolling_floor_run(env, s.all_troughs, s.n_all, items, sh, window, floor_q, s.mode, nullptr, s.q_nf,
-                              nullptr, s.draft, w, st));
+    BPM_TRY(rolling_floor_run(env, s.all_troughs, s.n_all, items, sh, window, floor_q, s.mode, nullptr, nullptr, s.q_nf,
+                              nullptr, sparse ? nullptr : s.draft, sparse ? s.draft : nullptr, w, st));
   }
   BPM_KERNEL(k_sanitize_flags);
   k_sanitize_flags<<<dim3(cdiv(sh.max_m / 2 + 2, 256), n), 256, 0, st>>>(env, s.draft, s.all_troughs, s.n_all,
-                                                                        s.few, items, mult, s.keep);     // :1090-1097
+                                                                        s.few, items, mult, sparse ? 1 : 0,
+                                                                        s.keep);                         // :1090-1097
   BPM_LAUNCH_OK();
   BPM_TRY(compact_run(s.keep, s.all_troughs, items, sh, s.n_all, sh.max_m / 2 + 2, false, s.tile_counts,
                       troughs_out, trough_count, st));
@@ -154,11 +159,13 @@ int noise_floor_run(const double* env, const BpmItem* items, const BatchShape& s
   k_floor_modes<<<cdiv(n, 128), 128, 0, st>>>(s.n_all, trough_count, n, 1, s.few, s.mode);
   BPM_LAUNCH_OK();
   {
-    // final floor from the kept troughs (:1102-1106), draft when <= 2 kept (:1107-1110),
-    // constant on the "<5" path (:1073-1077), q(0.1) when everything is NaN (:1113-1115)
+    // final floor from the kept troughs (:1102-1106); when <= 2 are kept the reference reuses the
+    // draft (:1107-1110) = the same rolling quantile over ALL troughs, recomputed here (mode 1
+    // makes the knot table take the other list); constant on the "<5" path (:1073-1077), q(0.1)
+    // when everything is NaN (:1113-1115)
     Workspace w = sub_ws(ws, 0);
-    BPM_TRY(rolling_floor_run(env, troughs_out, trough_count, items, sh, window, floor_q, s.mode, s.draft,
-                              s.q_nf, q_fb, floor_out, w, st));
+    BPM_TRY(rolling_floor_run(env, troughs_out, trough_count, items, sh, window, floor_q, s.mode, s.all_troughs,
+                              s.n_all, s.q_nf, q_fb, floor_out, nullptr, w, st));
   }
   return BPM_OK;
 }
@@ -182,7 +189,7 @@ int sanitize_run(const double* env, const double* draft, const int64_t* troughs,
   if (ws.overflow) return BPM_ERR_WORKSPACE;
   BPM_KERNEL(k_sanitize_flags);
   k_sanitize_flags<<<dim3(cdiv(sh.max_m / 2 + 2, 256), sh.n_items), 256, 0, st>>>(env, draft, troughs, trough_count,
-                                                                                 nullptr, items, mult, keep);
+                                                                                 nullptr, items, mult, 0, keep);
   BPM_LAUNCH_OK();
   return compact_run(keep, troughs, items, sh, trough_count, sh.max_m / 2 + 2, false, tile_counts, kept_out,
                      kept_count, st);
@@ -362,7 +369,8 @@ int bpm_rolling_floor(const double* envelope, const int64_t* knots, const int64_
   if (!workspace || !items_host || n_items <= 0) return BPM_ERR_ARG;
   Workspace ws(workspace, workspace_bytes);
   return rolling_floor_run(envelope, knots, knot_count, items, batch_shape(items_host, n_items), window, q, nullptr,
-                           nullptr, nullptr, nullptr, floor_out, ws, static_cast<cudaStream_t>(stream));
+                           nullptr, nullptr, nullptr, nullptr, floor_out, nullptr, ws,
+                           static_cast<cudaStream_t>(stream));
 }
 
 size_t bpm_noise_floor_workspace_bytes(int64_t total_m, int n_items) { return noise_floor_workspace_bytes(total_m, n_items); }

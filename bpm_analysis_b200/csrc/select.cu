@@ -2,9 +2,11 @@
 // numpy/lib/_function_base_impl.py:126-129, 4657-4678).
 //
 // Exact order statistics by most-significant-digit radix select on the order-preserving
-// 64-bit image of each float64 (six passes: 11,11,11,11,11,9 bits), then the next larger
-// element, then numpy's two-branch lerp evaluated with unfused float64 operations so the
-// result is bit-identical to numpy's.  Up to SEL_MAXQ quantile levels of the same data are
+// 64-bit image of each float64: two 11-bit digit passes, then the (tiny) bucket holding the
+// target is collected and sorted by one CTA (a bucket larger than SEL_CAP -- massive duplicates
+// -- falls back to the remaining digit passes 11,11,11,9 inside that CTA), then numpy's
+// two-branch lerp evaluated with unfused float64 operations so the result is bit-identical to
+// numpy's.  Up to SEL_MAXQ quantile levels of the same data are
 // resolved in the same passes (the noise-floor stage needs q(trough_prominence) always and
 // q(noise_floor_quantile) only for recordings with fewer than 5 troughs: `cond` switches a
 // level off per recording).  Histogram updates are warp-aggregated (envelope values share
@@ -199,112 +201,220 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_pass(const double* __res
   }
 }
 
-// resolve the last pass, find the smallest key above the selected one; the last block to
-// finish a recording evaluates numpy's lerp
-__global__ void __launch_bounds__(SEL_THREADS) k_select_next(const double* __restrict__ x,
-                                                             const BpmItem* __restrict__ items, SelLevels lv,
-                                                             SelState* __restrict__ states,
-                                                             const unsigned int* __restrict__ hist,
-                                                             unsigned int* __restrict__ done_count, int n_items) {
+// ---- after two digit passes (22 bits) the bucket holding the target is almost always tiny:
+// COLLECT its keys in one more sweep (plus the smallest key above the bucket), then one CTA per
+// recording sorts them and evaluates numpy's lerp.  A bucket larger than SEL_CAP (massive
+// duplicates, e.g. digital silence) is resolved by the same finishing CTA with the remaining four
+// digit passes over the whole recording -- slow, but rare and with no extra launches.
+constexpr int SEL_CAP = 4096;
+constexpr int SEL_FIN_THREADS = 1024;
+
+struct SelCollect {
+  unsigned long long* buf;          // [item][level][SEL_CAP] keys of the bucket
+  unsigned int* count;              // [item][level]
+  unsigned long long* next_above;   // [item][level] smallest key whose 22-bit prefix is above the bucket's
+};
+
+__global__ void __launch_bounds__(SEL_THREADS) k_select_collect(const double* __restrict__ x,
+                                                                const BpmItem* __restrict__ items, int nq,
+                                                                SelState* __restrict__ states,
+                                                                const unsigned int* __restrict__ hist, SelCollect cl,
+                                                                int n_items) {
   __shared__ SelState s_cur[SEL_MAXQ];
   __shared__ long long s_cum[SEL_THREADS + 1];
   __shared__ unsigned long long s_min[SEL_MAXQ][SEL_THREADS / 32];
-  __shared__ bool s_last;
   const int item = blockIdx.y;
   const BpmItem it = items[item];
-  const int nq = lv.nq;
+  bool any = false;
   for (int l = 0; l < nq; ++l) {
-    const SelState before = states[st_idx(SEL_PASSES - 1, l, item, n_items)];
+    const SelState before = states[st_idx(1, l, item, n_items)];
     if (before.active == 0) {
-      if (threadIdx.x == 0) s_cur[l].active = 0;
+      if (threadIdx.x == 0) {
+        s_cur[l].active = 0;
+        if (blockIdx.x == 0) states[st_idx(2, l, item, n_items)].active = 0;
+      }
       __syncthreads();
       continue;
     }
-    sel_advance(before, hist + hist_idx(item, l, SEL_PASSES - 1), sel_bits(SEL_PASSES - 1), &s_cur[l], s_cum);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      SelState* fin = states + st_idx(SEL_PASSES, l, item, n_items);
-      fin->prefix = s_cur[l].prefix; fin->rank = s_cur[l].rank; fin->below = s_cur[l].below;
-      fin->count = s_cur[l].count; fin->k = s_cur[l].k; fin->gamma = s_cur[l].gamma; fin->active = 1;
-    }
+    sel_advance(before, hist + hist_idx(item, l, 1), sel_bits(1), &s_cur[l], s_cum);
+    if (threadIdx.x == 0) s_cur[l].active = (s_cur[l].count <= SEL_CAP) ? 2 : 1;     // 2: collected
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) states[st_idx(2, l, item, n_items)] = s_cur[l];
+    any = any || (s_cur[l].active == 2);
   }
-  bool any = false;
-  for (int l = 0; l < nq; ++l) any = any || (s_cur[l].active != 0);
-  if (!any) return;                                      // uniform for the whole row: nobody counts tickets
   const int64_t i0 = static_cast<int64_t>(blockIdx.x) * SEL_TILE;
-  if (i0 < it.m) {
-    unsigned long long best[SEL_MAXQ];
+  if (!any || i0 >= it.m) return;
+  const int up = sel_shift(1);                              // bits below the two resolved digits
+  unsigned long long best[SEL_MAXQ];
 #pragma unroll
-    for (int l = 0; l < SEL_MAXQ; ++l) best[l] = ~0ull;
-    const double* __restrict__ xi = x + it.m_off;
-    for (int k = 0; k < SEL_PER_THREAD; ++k) {
-      const int64_t i = i0 + k * SEL_THREADS + threadIdx.x;
-      if (i < it.m) {
-        const unsigned long long key = f64_key(xi[i]);
-#pragma unroll
-        for (int l = 0; l < SEL_MAXQ; ++l)
-          if (l < nq && s_cur[l].active && key > s_cur[l].prefix && key < best[l]) best[l] = key;
-      }
-    }
+  for (int l = 0; l < SEL_MAXQ; ++l) best[l] = ~0ull;
+  const double* __restrict__ xi = x + it.m_off;
+  for (int k = 0; k < SEL_PER_THREAD; ++k) {
+    const int64_t i = i0 + k * SEL_THREADS + threadIdx.x;
+    if (i >= it.m) continue;
+    const unsigned long long key = f64_key(xi[i]);
+    const unsigned long long top = key >> up;
 #pragma unroll
     for (int l = 0; l < SEL_MAXQ; ++l) {
-#pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        const unsigned long long t = __shfl_xor_sync(0xffffffffu, best[l], o);
-        best[l] = t < best[l] ? t : best[l];
+      if (l >= nq || s_cur[l].active != 2) continue;
+      if (top == s_cur[l].prefix) {
+        const unsigned int pos = atomicAdd(cl.count + item * SEL_MAXQ + l, 1u);
+        if (pos < SEL_CAP) cl.buf[(static_cast<size_t>(item) * SEL_MAXQ + l) * SEL_CAP + pos] = key;
+      } else if (top > s_cur[l].prefix && key < best[l]) {
+        best[l] = key;
       }
-      if ((threadIdx.x & 31) == 0) s_min[l][threadIdx.x >> 5] = best[l];
-    }
-    __syncthreads();
-    if (threadIdx.x < nq && s_cur[threadIdx.x].active) {
-      const int l = threadIdx.x;
-      unsigned long long b = s_min[l][0];
-      for (int w = 1; w < SEL_THREADS / 32; ++w) b = s_min[l][w] < b ? s_min[l][w] : b;
-      if (b != ~0ull) atomicMin(&states[st_idx(SEL_PASSES, l, item, n_items)].next_key, b);
     }
   }
-  // last block of this recording finishes
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int tiles = static_cast<unsigned int>((it.m + SEL_TILE - 1) / SEL_TILE);
-    const unsigned int ticket = atomicAdd(done_count + item, 1u);
-    // blocks beyond the recording's last tile also pass here: every block of the row counts
-    s_last = (ticket == gridDim.x - 1);
-    (void)tiles;
+#pragma unroll
+  for (int l = 0; l < SEL_MAXQ; ++l) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const unsigned long long t = __shfl_xor_sync(0xffffffffu, best[l], o);
+      best[l] = t < best[l] ? t : best[l];
+    }
+    if ((threadIdx.x & 31) == 0) s_min[l][threadIdx.x >> 5] = best[l];
   }
   __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (threadIdx.x < nq) {
+  if (threadIdx.x < nq && s_cur[threadIdx.x].active == 2) {
     const int l = threadIdx.x;
-    const volatile SelState* f = states + st_idx(SEL_PASSES, l, item, n_items);
-    if (f->active) {
-      const unsigned long long pk = f->prefix, nk = f->next_key;
-      const long long below = f->below, count = f->count, k = f->k;
-      const double a = key_f64(pk);
-      // element k+1: the same value when duplicates cover it, else the next larger element
-      double b = a;
-      if (below + count <= k + 1 && nk != ~0ull) b = key_f64(nk);
-      const double t = f->gamma;
-      const double diff = __dsub_rn(b, a);
-      double r = __dadd_rn(a, __dmul_rn(diff, t));
-      if (t >= 0.5) r = __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, t)));
-      lv.out[l][item] = r;
+    unsigned long long bm = s_min[l][0];
+    for (int w = 1; w < SEL_THREADS / 32; ++w) bm = s_min[l][w] < bm ? s_min[l][w] : bm;
+    if (bm != ~0ull) atomicMin(cl.next_above + item * SEL_MAXQ + l, bm);
+  }
+}
+
+// numpy's quantile from the two neighbouring order statistics (keys) and the fractional index
+__device__ __forceinline__ double sel_lerp(unsigned long long ka, unsigned long long kb, double t) {
+  const double a = key_f64(ka), b = key_f64(kb);
+  const double diff = __dsub_rn(b, a);
+  double r = __dadd_rn(a, __dmul_rn(diff, t));
+  if (t >= 0.5) r = __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, t)));
+  return r;
+}
+
+__global__ void __launch_bounds__(SEL_FIN_THREADS) k_select_finish(const double* __restrict__ x,
+                                                                   const BpmItem* __restrict__ items, SelLevels lv,
+                                                                   const SelState* __restrict__ states, SelCollect cl,
+                                                                   int n_items) {
+  __shared__ unsigned long long s_key[SEL_CAP];             // sorted bucket | digit histogram of the slow path
+  __shared__ int s_scan[40];
+  __shared__ unsigned long long s_pref;
+  __shared__ long long s_rank, s_below, s_count;
+  __shared__ unsigned long long s_red[SEL_FIN_THREADS / 32];
+  const int item = blockIdx.x;
+  const BpmItem it = items[item];
+  const int tid = threadIdx.x;
+  for (int l = 0; l < lv.nq; ++l) {
+    const SelState s = states[st_idx(2, l, item, n_items)];
+    if (s.active == 0) continue;                            // uniform per CTA
+    unsigned long long ka, kb;
+    if (s.active == 2) {
+      const int nc = static_cast<int>(s.count);
+      int P = 32;
+      while (P < nc) P <<= 1;
+      const unsigned long long* src = cl.buf + (static_cast<size_t>(item) * SEL_MAXQ + l) * SEL_CAP;
+      for (int t = tid; t < P; t += SEL_FIN_THREADS) s_key[t] = (t < nc) ? src[t] : ~0ull;
+      __syncthreads();
+      for (int k2 = 2; k2 <= P; k2 <<= 1) {
+        for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+          for (int t = tid; t < P / 2; t += SEL_FIN_THREADS) {
+            const int lo_i = ((t & ~(j2 - 1)) << 1) | (t & (j2 - 1));
+            const int hi_i = lo_i + j2;
+            const bool upw = ((lo_i & k2) == 0);
+            const unsigned long long a = s_key[lo_i], b = s_key[hi_i];
+            if ((a > b) == upw) { s_key[lo_i] = b; s_key[hi_i] = a; }
+          }
+          __syncthreads();
+        }
+      }
+      ka = s_key[s.rank];
+      // element k+1: inside the bucket, else the smallest key above it (none: k is the maximum)
+      if (s.rank + 1 < nc) kb = s_key[s.rank + 1];
+      else {
+        const unsigned long long na = cl.next_above[item * SEL_MAXQ + l];
+        kb = (na != ~0ull) ? na : ka;
+      }
+      __syncthreads();
+    } else {
+      // slow path: the remaining digit passes by this one CTA over the whole recording
+      unsigned int* hist = reinterpret_cast<unsigned int*>(s_key);
+      if (tid == 0) { s_pref = s.prefix; s_rank = s.rank; s_below = s.below; s_count = s.count; }
+      __syncthreads();
+      const double* __restrict__ xi = x + it.m_off;
+      for (int p = 2; p < SEL_PASSES; ++p) {
+        const int sh = sel_shift(p), bits = sel_bits(p), upb = sh + bits;
+        const unsigned int mask = (1u << bits) - 1u;
+        for (int t = tid; t < SEL_BINS; t += SEL_FIN_THREADS) hist[t] = 0;
+        __syncthreads();
+        const unsigned long long pref = s_pref;
+        for (int64_t i = tid; i < it.m; i += SEL_FIN_THREADS) {
+          const unsigned long long key = f64_key(xi[i]);
+          if ((key >> upb) == pref) atomicAdd(&hist[static_cast<unsigned int>(key >> sh) & mask], 1u);
+        }
+        __syncthreads();
+        constexpr int PER = SEL_BINS / SEL_FIN_THREADS;
+        int loc[PER], sum = 0;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) { loc[u] = static_cast<int>(hist[tid * PER + u]); sum += loc[u]; }
+        int total;
+        int ex = block_exclusive_scan(sum, &total, s_scan);
+        const long long rank = s_rank;
+        __syncthreads();
+        if (rank >= ex && rank < ex + sum) {
+          long long c = ex;
+#pragma unroll
+          for (int u = 0; u < PER; ++u) {
+            if (rank >= c && rank < c + loc[u]) {
+              s_pref = (pref << bits) | static_cast<unsigned long long>(tid * PER + u);
+              s_rank = rank - c;
+              s_below = s_below + c;
+              s_count = loc[u];
+            }
+            c += loc[u];
+          }
+        }
+        __syncthreads();
+      }
+      ka = s_pref;                                          // all 64 bits resolved: the key itself
+      kb = ka;
+      if (s_below + s_count <= s.k + 1) {                   // duplicates do not cover element k+1
+        unsigned long long best = ~0ull;
+        for (int64_t i = tid; i < it.m; i += SEL_FIN_THREADS) {
+          const unsigned long long key = f64_key(xi[i]);
+          if (key > ka && key < best) best = key;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+          best = t < best ? t : best;
+        }
+        if ((tid & 31) == 0) s_red[tid >> 5] = best;
+        __syncthreads();
+        best = s_red[0];
+        for (int w = 1; w < SEL_FIN_THREADS / 32; ++w) best = s_red[w] < best ? s_red[w] : best;
+        if (best != ~0ull) kb = best;
+      }
+      __syncthreads();
     }
+    if (tid == 0) lv.out[l][item] = sel_lerp(ka, kb, s.gamma);
   }
 }
 
 struct SelectBuffers {
   SelState* states;
   unsigned int* hist;
-  unsigned int* done;
+  unsigned int* count;
+  unsigned long long* buf;
+  unsigned long long* next_above;
 };
 
 static int carve_select(Workspace& ws, int n_items, SelectBuffers* b) {
   b->states = ws.take<SelState>(static_cast<size_t>(SEL_PASSES + 1) * SEL_MAXQ * n_items);
-  // histograms and the per-recording completion counters are zeroed together
-  b->hist = ws.take<unsigned int>(static_cast<size_t>(n_items) * SEL_MAXQ * SEL_PASSES * SEL_BINS + n_items);
-  b->done = b->hist + static_cast<size_t>(n_items) * SEL_MAXQ * SEL_PASSES * SEL_BINS;
+  // the two digit histograms per level and the collect counters are zeroed together
+  b->hist = ws.take<unsigned int>(static_cast<size_t>(n_items) * SEL_MAXQ * SEL_PASSES * SEL_BINS + SEL_MAXQ * n_items);
+  b->count = b->hist + static_cast<size_t>(n_items) * SEL_MAXQ * SEL_PASSES * SEL_BINS;
+  b->buf = ws.take<unsigned long long>(static_cast<size_t>(n_items) * SEL_MAXQ * SEL_CAP);
+  b->next_above = ws.take<unsigned long long>(static_cast<size_t>(SEL_MAXQ) * n_items);
   return ws.overflow ? BPM_ERR_WORKSPACE : BPM_OK;
 }
 
@@ -332,19 +442,24 @@ int quantile_multi_run(const double* x, const BpmItem* items, const BatchShape& 
   SelectBuffers b;
   BPM_TRY(carve_select(ws, sh.n_items, &b));
   const int n = sh.n_items;
-  const size_t zero_words = static_cast<size_t>(n) * SEL_MAXQ * SEL_PASSES * SEL_BINS + n;
+  const size_t zero_words = static_cast<size_t>(n) * SEL_MAXQ * SEL_PASSES * SEL_BINS + static_cast<size_t>(SEL_MAXQ) * n;
   if (cudaMemsetAsync(b.hist, 0, sizeof(unsigned int) * zero_words, st) != cudaSuccess) return BPM_ERR_CUDA;
+  if (cudaMemsetAsync(b.next_above, 0xff, sizeof(unsigned long long) * SEL_MAXQ * n, st) != cudaSuccess) return BPM_ERR_CUDA;
   BPM_KERNEL(k_select_init);
   k_select_init<<<cdiv(n, 128), 128, 0, st>>>(items, n, lv, b.states);
   BPM_LAUNCH_OK();
   const dim3 grid(cdiv(sh.max_m, SEL_TILE), n);
-  for (int p = 0; p < SEL_PASSES; ++p) {
+  for (int p = 0; p < 2; ++p) {
     BPM_KERNEL(k_select_pass);
     k_select_pass<<<grid, SEL_THREADS, 0, st>>>(x, items, p, nq, b.states, b.hist, n);
     BPM_LAUNCH_OK();
   }
-  BPM_KERNEL(k_select_next);
-  k_select_next<<<grid, SEL_THREADS, 0, st>>>(x, items, lv, b.states, b.hist, b.done, n);
+  SelCollect cl{b.buf, b.count, b.next_above};
+  BPM_KERNEL(k_select_collect);
+  k_select_collect<<<grid, SEL_THREADS, 0, st>>>(x, items, nq, b.states, b.hist, cl, n);
+  BPM_LAUNCH_OK();
+  BPM_KERNEL(k_select_finish);
+  k_select_finish<<<n, SEL_FIN_THREADS, 0, st>>>(x, items, lv, b.states, cl, n);
   BPM_LAUNCH_OK();
   return BPM_OK;
 }

@@ -95,6 +95,23 @@ def test_quantile_bit_exact(n, q, ops):
     assert ops.quantile(y, q) == np.quantile(y, q)
 
 
+@pytest.mark.parametrize("q", [0.0, 0.1, 0.2, 0.5, 0.93, 1.0])
+def test_quantile_large_buckets_slow_path(q, ops):
+    """Buckets larger than the collect capacity (4096 keys sharing their leading 22 bits): exact
+    duplicates straddling the target rank, a constant array, and distinct values packed into
+    one binade slice -- all resolved by the finishing CTA's remaining digit passes."""
+    rng = np.random.default_rng(17)
+    a = np.abs(rng.standard_normal(60000)) * 10.0
+    a[rng.integers(0, 60000, 25000)] = 3.25                 # ~20 k exact duplicates
+    assert ops.quantile(a, q) == np.quantile(a, q)
+    c = np.full(20000, 7.5)
+    assert ops.quantile(c, q) == np.quantile(c, q)
+    d = 1.0 + 1e-9 * rng.random(50000)                      # same sign, exponent and top mantissa bits
+    assert ops.quantile(d, q) == np.quantile(d, q)
+    e = np.concatenate([np.zeros(30000), -np.abs(rng.standard_normal(100)), np.abs(rng.standard_normal(5000))])
+    assert ops.quantile(e, q) == np.quantile(e, q)
+
+
 # ----------------------------------------------------------------------------- K4
 def _signals():
     rng = np.random.default_rng(5)
@@ -202,6 +219,35 @@ def test_noise_floor_and_peaks_on_reference_envelope(name, fe, ref_params):
         assert rel_err(sd.values, g["smoothed_dev_values"]) < TOL
     # end to end on the GPU's own floor: expected identical
     assert np.array_equal(fe._find_raw_peaks(c, floor.values), g["raw_peaks"])
+
+
+def _two_survivor_envelope(inner):
+    m = 6000
+    tpos = np.array([100, 2500, 2900, 3100, 3500, 5900])
+    tval = np.array([1.0, inner, inner + 1, inner - 1, inner + .5, 1.2])
+    env = np.interp(np.arange(m), tpos, tval)
+    for a, b in zip(tpos[:-1], tpos[1:]):
+        x = np.arange(a, b + 1)
+        env[a:b + 1] += 60 * np.sin(np.pi * (x - a) / (b - a)) ** 2
+    env[:100] += np.linspace(30, 0, 100)
+    env[5900:] += np.linspace(0, 30, 100)
+    return env
+
+
+@pytest.mark.parametrize("inner,rate", [(400.0, 600), (200.0, 600), (400.0, 100), (400.0, 40)])
+def test_noise_floor_draft_fallback_branches(inner, rate, fe, ref_params):
+    """bpm_analysis.py:1107-1110: when <= 2 troughs survive sanitisation the final floor IS the
+    draft floor (here: recomputed over all troughs).  (400, 600) leaves exactly two survivors;
+    the other cases walk the neighbouring branches (4 kept; local windows; windows of a few
+    samples handled by the per-thread kernel)."""
+    from oracle import ref_port
+    env = _two_survivor_envelope(inner)
+    o_floor, o_tr = ref_port.calculate_dynamic_noise_floor(env, rate, ref_params)
+    if (inner, rate) == (400.0, 600):
+        assert len(o_tr) == 2
+    floor, tr = fe._calculate_dynamic_noise_floor(env, rate, ref_params)
+    assert np.array_equal(tr, o_tr)
+    assert np.array_equal(floor.values, o_floor.values)
 
 
 def test_vulpine_matches_shipped_debug_log(fe, ref_params):
