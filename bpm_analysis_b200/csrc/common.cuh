@@ -36,6 +36,50 @@ void profile_mark(const char* name, cudaStream_t st);
     if (_rc != BPM_OK) return _rc;    \
   } while (0)
 
+// ---------------------------------------------------------------- fork / join inside one call
+// Two sub-steps of a stage that do not depend on each other (the envelope quantiles and the
+// local-maximum / distance steps of the trough search) are enqueued on the caller's stream and on
+// a per-thread auxiliary stream, tied together with events.  Under stream capture this becomes two
+// parallel branches of the caller's CUDA graph; eagerly the two streams simply overlap.  The
+// auxiliary stream is the library's only persistent object (one per host thread and device,
+// created on first use); the events live for the duration of the call.
+struct ForkJoin {
+  cudaStream_t main = nullptr, aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool active = false;
+  // after begin(): work enqueued on `aux` runs after everything already on `st`
+  int begin(cudaStream_t st) {
+    main = st;
+    aux = st;
+    if (g_profiling) return BPM_OK;                       // per-kernel timing wants one serial stream
+    static thread_local cudaStream_t t_aux[16] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return BPM_OK;   // fall back to serial
+    if (!t_aux[dev] && cudaStreamCreateWithFlags(&t_aux[dev], cudaStreamNonBlocking) != cudaSuccess) {
+      t_aux[dev] = nullptr;
+      return BPM_OK;
+    }
+    if (cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess) return BPM_ERR_CUDA;
+    if (cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) return BPM_ERR_CUDA;
+    if (cudaEventRecord(ev_fork, st) != cudaSuccess) return BPM_ERR_CUDA;
+    if (cudaStreamWaitEvent(t_aux[dev], ev_fork, 0) != cudaSuccess) return BPM_ERR_CUDA;
+    aux = t_aux[dev];
+    active = true;
+    return BPM_OK;
+  }
+  // the aux branch is complete up to here
+  int end_aux() {
+    if (active && cudaEventRecord(ev_join, aux) != cudaSuccess) return BPM_ERR_CUDA;
+    return BPM_OK;
+  }
+  // event the main stream has to wait for before using the aux branch's results (nullptr: serial)
+  cudaEvent_t join_event() const { return active ? ev_join : nullptr; }
+  ~ForkJoin() {
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+  }
+};
+
 // ---------------------------------------------------------------- workspace
 // Bump allocator over the caller's workspace.  With base == nullptr it only
 // measures, so *_workspace_bytes() and the real call share one code path.

@@ -704,6 +704,8 @@ constexpr int RB_NPROBE = RB_THREADS / 32;
 constexpr int RB_CW = RB_S / 2 / (RB_THREADS / 32);   // bitonic compare-exchanges per warp and step
 constexpr int RB_PROBE_N = 64;         // samples per probe window (2 per lane)
 constexpr unsigned short RB_ABOVE = 0xFFFFu;
+constexpr int RB_NFINE = 4096;         // equal-width bins of the equalised bucketing (16 KB as uint32)
+constexpr int RB_EQ_MAX = 384;         // more samples than this in one fine bin: use the splitter path
 
 struct RbSortPhase {
   double piv[RB_S];                    // sorted splitter candidates, piv[RB_S-1] = +inf
@@ -726,6 +728,8 @@ struct RbShared {
   int scan_tmp[40];
   int fail;
   int probes_ok;
+  int eq_max;                          // fullest fine bin of the current attempt
+  unsigned long long vmin_key, vmax_key;   // range of the staged samples
   int k_lo, k_hi;                      // knots around the tile's first / last sample
   int kf, kl;                          // knots positioned inside the tile's output range
 };
@@ -831,8 +835,25 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rolling_floor_blk(
       }
     }
   }
-  if (tid == 0) { sh.pivot_key = 0ull; sh.fail = 0; sh.probes_ok = 1; }
+  if (tid == 0) { sh.pivot_key = 0ull; sh.fail = 0; sh.probes_ok = 1; sh.vmin_key = ~0ull; sh.vmax_key = 0ull; }
   __syncthreads();
+  {
+    unsigned long long kmin = ~0ull, kmax = 0ull;
+    for (int j = tid; j < n; j += RB_THREADS) {
+      const unsigned long long k = f64_key(sh.d[j]);
+      kmin = k < kmin ? k : kmin;
+      kmax = k > kmax ? k : kmax;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const unsigned long long a = __shfl_xor_sync(0xffffffffu, kmin, o), b = __shfl_xor_sync(0xffffffffu, kmax, o);
+      kmin = a < kmin ? a : kmin;
+      kmax = b > kmax ? b : kmax;
+    }
+    if ((tid & 31) == 0) { atomicMin(&sh.vmin_key, kmin); atomicMax(&sh.vmax_key, kmax); }
+  }
+  __syncthreads();
+  const double vmin_all = key_f64(sh.vmin_key), vmax_all = key_f64(sh.vmax_key);
   RB_TICK(0);
 
   // ---- S1b: pivot estimate.  Warp w probes the window of output ie0 + (2w+1)(ie1-ie0)/(2 NPROBE).
@@ -890,56 +911,116 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rolling_floor_blk(
 
   for (int attempt = 0; attempt < 2; ++attempt) {
     RbSortPhase& so = sh.u.sort;
-    // ---- S2: sorted sample of the staged values -> splitters below the pivot; bucket ids; histogram
-    for (int t = tid; t < RB_S; t += RB_THREADS) {
-      so.piv[t] = (t < RB_S - 1) ? sh.d[static_cast<int>((static_cast<long long>(t) * (n - 1)) / (RB_S - 2))] : INFINITY;
-      so.hist[t] = 0;
-    }
+    // ---- S2: bucket ids of the kept samples (monotone in the value, equal values share a bucket) + histogram.
+    // Fast path: a 4096-bin equal-width histogram over [vmin, min(pivot, vmax)] is EQUALISED through its
+    // prefix sum -- bucket = cdf[bin] >> shift -- which gives buckets of a few samples without sorting
+    // anything.  It cannot split one fine bin, so when a single bin holds more than RB_EQ_MAX samples
+    // (a heavily skewed tile) the tile takes the splitter path instead: splitters = the part of a
+    // bitonic-sorted 2048-sample below the pivot, bucket by binary search.
+    unsigned int* fine = reinterpret_cast<unsigned int*>(so.piv);          // [RB_NFINE], aliases the splitters
+    for (int t = tid; t < RB_NFINE; t += RB_THREADS) fine[t] = 0;
+    for (int t = tid; t < RB_S; t += RB_THREADS) so.hist[t] = 0;
+    if (tid == 0) sh.eq_max = 0;
     __syncthreads();
-    // bitonic sort; compare-exchange c of a step touches elements inside the (2 RB_CW)-element block
-    // of c / RB_CW whenever j2 <= RB_CW, so warp w owns CEs [RB_CW w, RB_CW (w+1)) and those steps
-    // only need __syncwarp
-    for (int k2 = 2; k2 <= RB_S; k2 <<= 1) {
-      for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-#pragma unroll
-        for (int h = 0; h < RB_S / 2 / RB_THREADS; ++h) {
-          const int t = (tid >> 5) * RB_CW + h * 32 + (tid & 31);
-          const int lo_i = ((t & ~(j2 - 1)) << 1) | (t & (j2 - 1));      // j2 is a power of two
-          const int hi_i = lo_i + j2;
-          const bool up = ((lo_i & k2) == 0);
-          const double x = so.piv[lo_i], y = so.piv[hi_i];
-          if ((x > y) == up) { so.piv[lo_i] = y; so.piv[hi_i] = x; }
-        }
-        if (j2 > RB_CW || (j2 == 1 && k2 > RB_CW)) __syncthreads(); else __syncwarp();
-      }
-    }
-    __syncthreads();
-    // usable splitters: piv[0 .. nsplit) are <= pivot (the +inf sentinel is never usable)
-    int nsplit;
-    {
-      int lo_i = 0, hi_i = RB_S - 1;
-      while (lo_i < hi_i) {
-        const int mid = (lo_i + hi_i) >> 1;
-        if (so.piv[mid] <= pivot) lo_i = mid + 1; else hi_i = mid;
-      }
-      nsplit = lo_i;                                           // in [0, RB_S - 1]
-    }
-    const int nbuckets = nsplit + 1;
-    RB_TICK(2);
+    const double vhi = pivot < vmax_all ? pivot : vmax_all;
+    const double eq_scale = (vhi > vmin_all) ? (static_cast<double>(RB_NFINE) / (vhi - vmin_all)) : 0.0;
     for (int j = tid; j < n; j += RB_THREADS) {
       const double x = sh.d[j];
-      unsigned short bk = RB_ABOVE;
+      unsigned short fb = RB_ABOVE;
       if (x <= pivot) {
-        // bucket = number of usable splitters strictly below the value (equal values share a bucket)
-        int lo_i = 0, hi_i = nsplit;
-        while (lo_i < hi_i) {
-          const int mid = (lo_i + hi_i) >> 1;
-          if (so.piv[mid] < x) lo_i = mid + 1; else hi_i = mid;
-        }
-        bk = static_cast<unsigned short>(lo_i);
-        atomicAdd(&so.hist[lo_i], 1u);
+        int bi = static_cast<int>((x - vmin_all) * eq_scale);
+        if (bi > RB_NFINE - 1) bi = RB_NFINE - 1;
+        if (bi < 0) bi = 0;
+        fb = static_cast<unsigned short>(bi);
+        atomicAdd(&fine[bi], 1u);
       }
-      sh.rank[j] = bk;
+      sh.rank[j] = fb;
+    }
+    __syncthreads();
+    int nbuckets;
+    {
+      constexpr int PERF = RB_NFINE / RB_THREADS;
+      unsigned int loc[PERF];
+      int sum = 0, mx = 0;
+#pragma unroll
+      for (int u2 = 0; u2 < PERF; ++u2) {
+        loc[u2] = fine[tid * PERF + u2];
+        sum += loc[u2];
+        mx = mx > static_cast<int>(loc[u2]) ? mx : static_cast<int>(loc[u2]);
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, mx, o); mx = t > mx ? t : mx; }
+      if ((tid & 31) == 0 && mx > 0) atomicMax(&sh.eq_max, mx);
+      int nk_eq;
+      int ex = block_exclusive_scan(sum, &nk_eq, sh.scan_tmp);               // (contains the barriers)
+#pragma unroll
+      for (int u2 = 0; u2 < PERF; ++u2) { fine[tid * PERF + u2] = ex; ex += loc[u2]; }
+      __syncthreads();
+      if (sh.eq_max <= RB_EQ_MAX) {
+        int shift = 0;
+        while (((nk_eq > 0 ? nk_eq - 1 : 0) >> shift) >= RB_S) ++shift;
+        nbuckets = ((nk_eq > 0 ? nk_eq - 1 : 0) >> shift) + 1;
+        for (int j = tid; j < n; j += RB_THREADS) {
+          const unsigned short fb = sh.rank[j];
+          if (fb != RB_ABOVE) {
+            const unsigned int bk = fine[fb] >> shift;
+            sh.rank[j] = static_cast<unsigned short>(bk);
+            atomicAdd(&so.hist[bk], 1u);
+          }
+        }
+        RB_TICK(2);
+      } else {
+        DBG(14);
+        __syncthreads();                                         // everyone has read eq_max / the cdf
+        for (int t = tid; t < RB_S; t += RB_THREADS)
+          so.piv[t] = (t < RB_S - 1) ? sh.d[static_cast<int>((static_cast<long long>(t) * (n - 1)) / (RB_S - 2))] : INFINITY;
+        __syncthreads();
+        // bitonic sort; compare-exchange c of a step touches elements inside the (2 RB_CW)-element block
+        // of c / RB_CW whenever j2 <= RB_CW, so warp w owns CEs [RB_CW w, RB_CW (w+1)) and those steps
+        // only need __syncwarp
+        for (int k2 = 2; k2 <= RB_S; k2 <<= 1) {
+          for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+#pragma unroll
+            for (int h = 0; h < RB_S / 2 / RB_THREADS; ++h) {
+              const int t = (tid >> 5) * RB_CW + h * 32 + (tid & 31);
+              const int lo_i = ((t & ~(j2 - 1)) << 1) | (t & (j2 - 1));      // j2 is a power of two
+              const int hi_i = lo_i + j2;
+              const bool up = ((lo_i & k2) == 0);
+              const double x = so.piv[lo_i], y = so.piv[hi_i];
+              if ((x > y) == up) { so.piv[lo_i] = y; so.piv[hi_i] = x; }
+            }
+            if (j2 > RB_CW || (j2 == 1 && k2 > RB_CW)) __syncthreads(); else __syncwarp();
+          }
+        }
+        __syncthreads();
+        // usable splitters: piv[0 .. nsplit) are <= pivot (the +inf sentinel is never usable)
+        int nsplit;
+        {
+          int lo_i = 0, hi_i = RB_S - 1;
+          while (lo_i < hi_i) {
+            const int mid = (lo_i + hi_i) >> 1;
+            if (so.piv[mid] <= pivot) lo_i = mid + 1; else hi_i = mid;
+          }
+          nsplit = lo_i;                                           // in [0, RB_S - 1]
+        }
+        nbuckets = nsplit + 1;
+        RB_TICK(2);
+        for (int j = tid; j < n; j += RB_THREADS) {
+          const double x = sh.d[j];
+          unsigned short bk = RB_ABOVE;
+          if (x <= pivot) {
+            // bucket = number of usable splitters strictly below the value (equal values share a bucket)
+            int lo_i = 0, hi_i = nsplit;
+            while (lo_i < hi_i) {
+              const int mid = (lo_i + hi_i) >> 1;
+              if (so.piv[mid] < x) lo_i = mid + 1; else hi_i = mid;
+            }
+            bk = static_cast<unsigned short>(lo_i);
+            atomicAdd(&so.hist[lo_i], 1u);
+          }
+          sh.rank[j] = bk;
+        }
+      }
     }
     __syncthreads();
     RB_TICK(3);

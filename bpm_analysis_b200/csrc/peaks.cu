@@ -555,11 +555,14 @@ int compact_run(const unsigned char* flags, const int64_t* src, const BpmItem* i
   return BPM_OK;
 }
 
+// prominence_ready: event after which the prominence threshold is valid (it may be produced on
+// another stream while the local-maximum / distance steps run here); nullptr = already valid.
 int find_peaks_run(const double* x, int sign, const double* height, const double* prominence, int distance,
                    const BpmItem* items, const BatchShape& sh, int64_t* out_idx, int64_t* out_count,
-                   Workspace& ws, cudaStream_t st) {
+                   Workspace& ws, cudaStream_t st, cudaEvent_t prominence_ready) {
   if (!x || !items || !out_idx || !out_count || sh.n_items <= 0 || distance < 1) return BPM_ERR_ARG;
   if (sh.max_m <= FPS_MAXN) {
+    if (prominence_ready && cudaStreamWaitEvent(st, prominence_ready, 0) != cudaSuccess) return BPM_ERR_CUDA;
     const size_t smem = sizeof(double) * FPS_MAXN + sizeof(int) * (FPS_MAXN / 2 + 1) + (FPS_MAXN / 2 + 1);
     cudaFuncSetAttribute(k_find_peaks_small, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     BPM_KERNEL(k_find_peaks_small);
@@ -587,6 +590,7 @@ int find_peaks_run(const double* x, int sign, const double* height, const double
                                                                                   b.cand_count, distance, b.cstate);
   }
   BPM_LAUNCH_OK();
+  if (prominence_ready && cudaStreamWaitEvent(st, prominence_ready, 0) != cudaSuccess) return BPM_ERR_CUDA;
   if (prominence != nullptr) {
     const int64_t want = (max_c + PR_THREADS / 32 - 1) / (PR_THREADS / 32);
     const unsigned gx = static_cast<unsigned>(want < PR_BLOCKS ? (want > 0 ? want : 1) : PR_BLOCKS);

@@ -26,7 +26,7 @@ int quantile_multi_run(const double* x, const BpmItem* items, const BatchShape& 
 size_t find_peaks_workspace_bytes(int64_t total_m, int n_items);
 int find_peaks_run(const double* x, int sign, const double* height, const double* prominence, int distance,
                    const BpmItem* items, const BatchShape& sh, int64_t* out_idx, int64_t* out_count,
-                   Workspace& ws, cudaStream_t st);
+                   Workspace& ws, cudaStream_t st, cudaEvent_t prominence_ready = nullptr);
 int compact_run(const unsigned char* flags, const int64_t* src, const BpmItem* items, const BatchShape& sh,
                 const int64_t* dom_len, int64_t max_len, bool counts_ready, int* tile_counts, int64_t* out,
                 int64_t* out_count, cudaStream_t st);
@@ -68,6 +68,8 @@ struct NoiseFloorScratch {
   int* mode;
   unsigned char* keep;
   int* tile_counts;
+  char* select_ws;          // the quantile passes run concurrently with the trough search: own scratch
+  size_t select_ws_bytes;
 };
 
 static int carve_noise_floor(Workspace& ws, int64_t total_m, int n, NoiseFloorScratch* s) {
@@ -81,6 +83,8 @@ static int carve_noise_floor(Workspace& ws, int64_t total_m, int n, NoiseFloorSc
   s->mode = ws.take<int>(n);
   s->keep = ws.take<unsigned char>(total_m);
   s->tile_counts = ws.take<int>(total_m / 2048 + n + 1);
+  s->select_ws_bytes = quantile_workspace_bytes(n);
+  s->select_ws = ws.take<char>(s->select_ws_bytes);
   return ws.overflow ? BPM_ERR_WORKSPACE : BPM_OK;
 }
 
@@ -125,17 +129,22 @@ int noise_floor_run(const double* env, const BpmItem* items, const BatchShape& s
   {
     // every quantile of the envelope this stage can need, resolved in ONE set of radix passes:
     // q(trough_prominence) (:1067), q(noise_floor_quantile) for the "<5 troughs" path (:1075 -- computed
-    // unconditionally, it costs no extra launch) and q(0.1) for the all-NaN path (:1114)
+    // unconditionally, it costs no extra launch) and q(0.1) for the all-NaN path (:1114).  They run on
+    // the auxiliary stream, next to the local-maximum / distance steps of the trough search, which
+    // only need the prominence threshold at their very end (own workspace: the two overlap in time).
     double qs[3] = {trough_prom_q, floor_q, 0.1};
     double* outs[3] = {q_tp, s.q_nf, s.q_fb};
     int nq = 2;
     if (trough_prom_q != 0.1) { nq = 3; q_fb = s.q_fb; }
+    ForkJoin fj;
+    BPM_TRY(fj.begin(st));
+    Workspace wq(ws.measuring() ? nullptr : s.select_ws, s.select_ws_bytes);
+    BPM_TRY(quantile_multi_run(env, items, sh, nq, qs, nullptr, outs, wq, fj.aux));
+    BPM_TRY(fj.end_aux());
     Workspace w = sub_ws(ws, 0);
-    BPM_TRY(quantile_multi_run(env, items, sh, nq, qs, nullptr, outs, w, st));
-  }
-  {
-    Workspace w = sub_ws(ws, 0);
-    BPM_TRY(find_peaks_run(env, -1, nullptr, q_tp, distance, items, sh, s.all_troughs, s.n_all, w, st));  // :1070
+    BPM_TRY(find_peaks_run(env, -1, nullptr, q_tp, distance, items, sh, s.all_troughs, s.n_all, w, st,
+                           fj.join_event()));                                                        // :1070
+    if (fj.active && cudaGetLastError() != cudaSuccess) return BPM_ERR_CUDA;
   }
   BPM_KERNEL(k_floor_modes);
   k_floor_modes<<<cdiv(n, 128), 128, 0, st>>>(s.n_all, nullptr, n, 0, s.few, s.mode);
