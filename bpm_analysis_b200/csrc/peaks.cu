@@ -432,11 +432,14 @@ __global__ void __launch_bounds__(FPS_THREADS) k_find_peaks_small(const double* 
     for (int i = b * 32; i < min(n, b * 32 + 32); ++i) { mn = fmin(mn, xs[i]); mx = fmax(mx, xs[i]); }
     s_bmin[b] = mn; s_bmax[b] = mx;
   }
-  // ---- local maxima (plateau midpoints) + height, ordered
-  for (int base = 0; base < n; base += FPS_THREADS) {
-    const int i = base + tid;
-    bool pk = false;
-    if (i >= 1 && i <= n - 2) {
+  // ---- local maxima (plateau midpoints) + height, ordered: every thread owns a contiguous run of
+  //      samples, so ONE block scan places all candidates
+  {
+    const int per = (n + FPS_THREADS - 1) / FPS_THREADS;
+    const int i0 = tid * per, i1 = min(n, i0 + per);
+    auto is_peak = [&](int i) -> bool {
+      if (i < 1 || i > n - 2) return false;
+      bool pk = false;
       const double c = xs[i], l = xs[i - 1], r = xs[i + 1];
       if (l < c && r < c) {
         pk = true;
@@ -447,13 +450,15 @@ __global__ void __launch_bounds__(FPS_THREADS) k_find_peaks_small(const double* 
         pk = (L >= 1 && R <= n - 2 && xs[L - 1] < c && xs[R + 1] < c && i == (L + R) / 2);
       }
       if (pk && height != nullptr) pk = (height[it.m_off + i] <= c);
-    }
+      return pk;
+    };
+    int cnt = 0;
+    for (int i = i0; i < i1; ++i) cnt += is_peak(i) ? 1 : 0;
     int total;
-    const int ex = block_exclusive_scan(pk ? 1 : 0, &total, s_scan);
-    const int b0 = s_base;
-    if (pk) { cpos[b0 + ex] = i; cst[b0 + ex] = 0; }
-    __syncthreads();
-    if (tid == 0) s_base = b0 + total;
+    int ex = block_exclusive_scan(cnt, &total, s_scan);
+    for (int i = i0; i < i1; ++i)
+      if (is_peak(i)) { cpos[ex] = i; cst[ex] = 0; ++ex; }
+    if (tid == 0) s_base = total;
     __syncthreads();
   }
   const int nc = s_base;
@@ -493,19 +498,18 @@ __global__ void __launch_bounds__(FPS_THREADS) k_find_peaks_small(const double* 
     }
     __syncthreads();
   }
-  // ---- ordered output
-  if (tid == 0) s_base = 0;
-  __syncthreads();
+  // ---- ordered output (contiguous runs of candidates per thread, one block scan)
   int64_t* oi = out_idx + it.m_off;
-  for (int base = 0; base < nc; base += FPS_THREADS) {
-    const int k = base + tid;
-    const bool keep = (k < nc) && cst[k] == 1;
+  {
+    const int per = (nc + FPS_THREADS - 1) / FPS_THREADS;
+    const int k0 = tid * per, k1 = min(nc, k0 + per);
+    int cnt = 0;
+    for (int k = k0; k < k1; ++k) cnt += (cst[k] == 1) ? 1 : 0;
     int total;
-    const int ex = block_exclusive_scan(keep ? 1 : 0, &total, s_scan);
-    const int b0 = s_base;
-    if (keep) oi[b0 + ex] = cpos[k];
-    __syncthreads();
-    if (tid == 0) s_base = b0 + total;
+    int ex = block_exclusive_scan(cnt, &total, s_scan);
+    for (int k = k0; k < k1; ++k)
+      if (cst[k] == 1) oi[ex++] = cpos[k];
+    if (tid == 0) s_base = total;
     __syncthreads();
   }
   if (tid == 0) out_count[item] = s_base;
