@@ -270,7 +270,7 @@ def run_reference(args):
             "config": {"workload": workload_name(args), "filter_mode": args.filter_mode},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------- GPU side
@@ -490,7 +490,7 @@ def run_b200(args):
                                   "cudaMemcpyAsync of the whole recording from pinned host memory, serial steps"},
                 "gpu_launches": launches if graphed is None else launches_per_step * args.steps,
                 "launch_mode": "eager" if graphed is None else "cuda-graph replay", "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -585,14 +585,37 @@ def run_stream(args):
                 "gpu_launches": launches, "launch_mode": "eager (host reads list lengths between stages)",
                 "roofline": None, "cpu_baseline": None,
                 "result": {"troughs": int(out["troughs"].numel()), "peaks": int(out["peaks"].numel())}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything libraries write to fd 1 (NCCL prints its version there) goes to stderr; the ONE
+    JSON line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "stream":

@@ -107,3 +107,22 @@ def test_items_layout():
     it = make_items([100, 50, 70], [10, 5, 7])
     assert it["in_off"].tolist() == [0, 100, 150] and it["m_off"].tolist() == [0, 10, 15]
     assert it.view(np.int64).reshape(-1, 4)[1].tolist() == [100, 50, 10, 5]
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference runs on the CPU (oracle port on the host cores) and must print
+    exactly one JSON line with the contract's keys; stdout carries nothing else."""
+    import json
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(repo, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--duration-sec", "60"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "audio_hours_per_sec" and d["unit"] == "audio-hours/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
