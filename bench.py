@@ -53,9 +53,11 @@ def parse_args():
     ap.add_argument("--no-zero-copy", action="store_true", help="e2e: copy the whole recording to the device first")
     ap.add_argument("--e2e-depth", type=int, default=3, help="e2e: recordings in flight (1 = strictly serial steps)")
     ap.add_argument("--dump-kernels", default=None, help="write the per-kernel table to this JSON file")
-    ap.add_argument("--workload", default="recordings", choices=["recordings", "stream"],
+    ap.add_argument("--workload", default="recordings", choices=["recordings", "stream", "batch", "holter"],
                     help="recordings: one C2 recording per GPU (weak scaling, the headline). stream: ONE C2 "
-                         "recording split into halo-overlapped time chunks over the GPUs (strong scaling)")
+                         "recording split into halo-overlapped time chunks over the GPUs (strong scaling). "
+                         "batch: BASELINE configs[2], one rank's share = 128 x 10-min 44.1 kHz recordings in one "
+                         "call. holter: configs[3], one 24-h 4 kHz recording (M = 28.8 M envelope samples)")
     return ap.parse_args()
 
 
@@ -613,6 +615,115 @@ def emit(line: dict) -> None:
         os.write(_REAL_STDOUT, data)
 
 
+def run_extra(args):
+    """Extra data points at sizes where the envelope-rate kernels stream more than L2: C3 (a rank's
+    share of the 1024-recording batch) and C4 (24-h Holter stream).  a1..a4 only, device-resident
+    timing + per-kernel event table; the e2e number is a serial full upload + read-back."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from bpm_analysis_b200 import _native, synth
+    from bpm_analysis_b200.runtime import GraphedStep, StageARunner, profile_kernels
+    lib = _native.load_library()
+    params = bench_params(args)
+    if args.workload == "batch":
+        base = [synth.config_c3_item(16 * rank + i)[0] for i in range(8)]
+        pcms = [base[i % 8] for i in range(128)]
+        sr, name = 44100, "C3: 128 x synthetic 10-min 44.1 kHz recordings per GPU (8 distinct, tiled), one bpm_stage_a call"
+    else:
+        pcm, sr, _ = synth.config_c4(seed=4 + rank, duration_sec=86400.0)
+        pcms, name = [pcm], "C4: synthetic 24-h 4 kHz Holter-style recording (bursts, dropouts), one per GPU"
+    audio_hours = sum(len(p) for p in pcms) / sr / 3600.0
+    A = StageARunner([len(p) for p in pcms], sr, params)
+    A.upload(pcms)
+    torch.cuda.synchronize()
+    graphed = None if args.no_graph else GraphedStep(A)
+    step = A.launch if graphed is None else graphed.launch
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    l0 = lib.bpm_launch_count()
+    A.launch()
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.bpm_launch_count() - l0)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    # end to end, serial: pageable upload of every recording + read-back of envelope, floor and lists
+    t0 = time.perf_counter()
+    n_e2e = max(1, min(args.steps, 3))
+    for _ in range(n_e2e):
+        A.upload(pcms)
+        step()
+        host = {k: A.out[k].cpu() for k in ("envelope", "floor", "troughs", "peaks", "trough_count", "peak_count")}
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / n_e2e)
+    clocks = sampler.stop()
+    M = A.total_m
+    nt, npk = int(host["trough_count"].sum()), int(host["peak_count"].sum())
+    prof = profile_kernels(lambda: [A.launch() for _ in range(args.steps)])
+    torch.cuda.synchronize()
+    shp = {"N": sum(len(p) for p in pcms), "M": M, "T": nt, "P": npk, "B": 0}
+    peak, peak_src = measured_peak_gbs()
+    total_ms = sum(v[1] for v in prof.values()) or 1.0
+    kernels = {}
+    for kname, (cnt, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        avg_us = ms * 1e3 / cnt
+        ab = algorithmic_bytes(kname, shp, args.filter_mode)
+        kernels[kname] = {"launches_per_step": cnt / args.steps, "avg_us": round(avg_us, 3), "share": round(ms / total_ms, 4),
+                          "alg_bytes": ab, "gbs": round(ab / (avg_us * 1e-6) / 1e9, 2) if avg_us > 0 else None,
+                          "frac_of_hbm_peak": round(ab / (avg_us * 1e-6) / 1e9 / peak, 4) if avg_us > 0 else None}
+    top = next(iter(kernels))
+    k = kernels[top]
+    if rank == 0:
+        emit({"metric": METRIC, "value": world * audio_hours / (ms_step / 1e3), "unit": UNIT, "n_gpus": world,
+              "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+              "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+              "config": {"workload": name, "filter_mode": args.filter_mode, "raw_samples": shp["N"],
+                         "envelope_samples": M, "recordings": len(pcms), "troughs": nt, "raw_peaks": npk,
+                         "l2": "inputs larger than L2", "parallelism": f"{world} x independent shares, no collective",
+                         "scope": "a1..a4 (no beat-list reductions)"},
+              "clocks": clocks,
+              "e2e": {"value": world * audio_hours / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+                      "h2d_bytes_per_step": int(shp["N"] * 2), "d2h_bytes_per_step": int(M * 32 + 16 * len(pcms)),
+                      "ingest": "serial: pageable host arrays -> device, then compute, then read-back"},
+              "gpu_launches": launches_per_step * args.steps,
+              "launch_mode": "eager" if graphed is None else "cuda-graph replay",
+              "roofline": {"kernel": top, "bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s",
+                           "frac": k["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                           "share_of_step": k["share"], "avg_launch_us": k["avg_us"], "note": ROOFLINE_NOTES.get(top, "")},
+              "cpu_baseline": None, "kernels": kernels})
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     quiet_stdout()
@@ -620,6 +731,8 @@ def main():
         run_reference(args)
     elif args.workload == "stream":
         run_stream(args)
+    elif args.workload in ("batch", "holter"):
+        run_extra(args)
     else:
         run_b200(args)
 

@@ -212,42 +212,45 @@ constexpr int SEL_FIN_THREADS = 1024;
 struct SelCollect {
   unsigned long long* buf;          // [item][level][SEL_CAP] keys of the bucket
   unsigned int* count;              // [item][level]
-  unsigned long long* next_above;   // [item][level] smallest key whose 22-bit prefix is above the bucket's
+  unsigned long long* next_above;   // [item][level] smallest key whose resolved prefix is above the bucket's
+  unsigned long long* bmin;         // [item][level] smallest / largest key inside a bucket too large to collect:
+  unsigned long long* bmax;         //   equal => the bucket is one value repeated (digital silence, clipping)
 };
 
 __global__ void __launch_bounds__(SEL_THREADS) k_select_collect(const double* __restrict__ x,
                                                                 const BpmItem* __restrict__ items, int nq,
                                                                 SelState* __restrict__ states,
                                                                 const unsigned int* __restrict__ hist, SelCollect cl,
-                                                                int n_items) {
+                                                                int npre, int n_items) {
   __shared__ SelState s_cur[SEL_MAXQ];
   __shared__ long long s_cum[SEL_THREADS + 1];
   __shared__ unsigned long long s_min[SEL_MAXQ][SEL_THREADS / 32];
+  __shared__ unsigned long long s_lo[SEL_MAXQ][SEL_THREADS / 32], s_hi[SEL_MAXQ][SEL_THREADS / 32];
   const int item = blockIdx.y;
   const BpmItem it = items[item];
   bool any = false;
   for (int l = 0; l < nq; ++l) {
-    const SelState before = states[st_idx(1, l, item, n_items)];
+    const SelState before = states[st_idx(npre - 1, l, item, n_items)];
     if (before.active == 0) {
       if (threadIdx.x == 0) {
         s_cur[l].active = 0;
-        if (blockIdx.x == 0) states[st_idx(2, l, item, n_items)].active = 0;
+        if (blockIdx.x == 0) states[st_idx(npre, l, item, n_items)].active = 0;
       }
       __syncthreads();
       continue;
     }
-    sel_advance(before, hist + hist_idx(item, l, 1), sel_bits(1), &s_cur[l], s_cum);
+    sel_advance(before, hist + hist_idx(item, l, npre - 1), sel_bits(npre - 1), &s_cur[l], s_cum);
     if (threadIdx.x == 0) s_cur[l].active = (s_cur[l].count <= SEL_CAP) ? 2 : 1;     // 2: collected
     __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x == 0) states[st_idx(2, l, item, n_items)] = s_cur[l];
-    any = any || (s_cur[l].active == 2);
+    if (blockIdx.x == 0 && threadIdx.x == 0) states[st_idx(npre, l, item, n_items)] = s_cur[l];
+    any = any || (s_cur[l].active != 0);
   }
   const int64_t i0 = static_cast<int64_t>(blockIdx.x) * SEL_TILE;
   if (!any || i0 >= it.m) return;
-  const int up = sel_shift(1);                              // bits below the two resolved digits
-  unsigned long long best[SEL_MAXQ];
+  const int up = sel_shift(npre - 1);                       // bits below the resolved digits
+  unsigned long long best[SEL_MAXQ], blo[SEL_MAXQ], bhi[SEL_MAXQ];
 #pragma unroll
-  for (int l = 0; l < SEL_MAXQ; ++l) best[l] = ~0ull;
+  for (int l = 0; l < SEL_MAXQ; ++l) { best[l] = ~0ull; blo[l] = ~0ull; bhi[l] = 0ull; }
   const double* __restrict__ xi = x + it.m_off;
   for (int k = 0; k < SEL_PER_THREAD; ++k) {
     const int64_t i = i0 + k * SEL_THREADS + threadIdx.x;
@@ -256,10 +259,15 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_collect(const double* __
     const unsigned long long top = key >> up;
 #pragma unroll
     for (int l = 0; l < SEL_MAXQ; ++l) {
-      if (l >= nq || s_cur[l].active != 2) continue;
+      if (l >= nq || s_cur[l].active == 0) continue;
       if (top == s_cur[l].prefix) {
-        const unsigned int pos = atomicAdd(cl.count + item * SEL_MAXQ + l, 1u);
-        if (pos < SEL_CAP) cl.buf[(static_cast<size_t>(item) * SEL_MAXQ + l) * SEL_CAP + pos] = key;
+        if (s_cur[l].active == 2) {
+          const unsigned int pos = atomicAdd(cl.count + item * SEL_MAXQ + l, 1u);
+          if (pos < SEL_CAP) cl.buf[(static_cast<size_t>(item) * SEL_MAXQ + l) * SEL_CAP + pos] = key;
+        } else {
+          blo[l] = key < blo[l] ? key : blo[l];
+          bhi[l] = key > bhi[l] ? key : bhi[l];
+        }
       } else if (top > s_cur[l].prefix && key < best[l]) {
         best[l] = key;
       }
@@ -272,14 +280,32 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_collect(const double* __
       const unsigned long long t = __shfl_xor_sync(0xffffffffu, best[l], o);
       best[l] = t < best[l] ? t : best[l];
     }
-    if ((threadIdx.x & 31) == 0) s_min[l][threadIdx.x >> 5] = best[l];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const unsigned long long a = __shfl_xor_sync(0xffffffffu, blo[l], o), b = __shfl_xor_sync(0xffffffffu, bhi[l], o);
+      blo[l] = a < blo[l] ? a : blo[l];
+      bhi[l] = b > bhi[l] ? b : bhi[l];
+    }
+    if ((threadIdx.x & 31) == 0) {
+      s_min[l][threadIdx.x >> 5] = best[l];
+      s_lo[l][threadIdx.x >> 5] = blo[l];
+      s_hi[l][threadIdx.x >> 5] = bhi[l];
+    }
   }
   __syncthreads();
-  if (threadIdx.x < nq && s_cur[threadIdx.x].active == 2) {
+  if (threadIdx.x < nq && s_cur[threadIdx.x].active != 0) {
     const int l = threadIdx.x;
-    unsigned long long bm = s_min[l][0];
-    for (int w = 1; w < SEL_THREADS / 32; ++w) bm = s_min[l][w] < bm ? s_min[l][w] : bm;
+    unsigned long long bm = s_min[l][0], lo = s_lo[l][0], hi = s_hi[l][0];
+    for (int w = 1; w < SEL_THREADS / 32; ++w) {
+      bm = s_min[l][w] < bm ? s_min[l][w] : bm;
+      lo = s_lo[l][w] < lo ? s_lo[l][w] : lo;
+      hi = s_hi[l][w] > hi ? s_hi[l][w] : hi;
+    }
     if (bm != ~0ull) atomicMin(cl.next_above + item * SEL_MAXQ + l, bm);
+    if (s_cur[l].active == 1) {
+      if (lo != ~0ull) atomicMin(cl.bmin + item * SEL_MAXQ + l, lo);
+      if (hi != 0ull || lo != ~0ull) atomicMax(cl.bmax + item * SEL_MAXQ + l, hi);
+    }
   }
 }
 
@@ -295,7 +321,7 @@ __device__ __forceinline__ double sel_lerp(unsigned long long ka, unsigned long 
 __global__ void __launch_bounds__(SEL_FIN_THREADS) k_select_finish(const double* __restrict__ x,
                                                                    const BpmItem* __restrict__ items, SelLevels lv,
                                                                    const SelState* __restrict__ states, SelCollect cl,
-                                                                   int n_items) {
+                                                                   int npre, int n_items) {
   __shared__ unsigned long long s_key[SEL_CAP];             // sorted bucket | digit histogram of the slow path
   __shared__ int s_scan[40];
   __shared__ unsigned long long s_pref;
@@ -305,7 +331,7 @@ __global__ void __launch_bounds__(SEL_FIN_THREADS) k_select_finish(const double*
   const BpmItem it = items[item];
   const int tid = threadIdx.x;
   for (int l = 0; l < lv.nq; ++l) {
-    const SelState s = states[st_idx(2, l, item, n_items)];
+    const SelState s = states[st_idx(npre, l, item, n_items)];
     if (s.active == 0) continue;                            // uniform per CTA
     unsigned long long ka, kb;
     if (s.active == 2) {
@@ -335,13 +361,22 @@ __global__ void __launch_bounds__(SEL_FIN_THREADS) k_select_finish(const double*
         kb = (na != ~0ull) ? na : ka;
       }
       __syncthreads();
+    } else if (cl.bmin[item * SEL_MAXQ + l] == cl.bmax[item * SEL_MAXQ + l]) {
+      // the oversized bucket is ONE value repeated (digital silence, clipping): nothing to resolve
+      ka = cl.bmin[item * SEL_MAXQ + l];
+      kb = ka;
+      if (s.rank + 1 >= s.count) {
+        const unsigned long long na = cl.next_above[item * SEL_MAXQ + l];
+        if (na != ~0ull) kb = na;
+      }
     } else {
-      // slow path: the remaining digit passes by this one CTA over the whole recording
+      // slow path (more than SEL_CAP distinct keys agreeing in every resolved digit): the remaining
+      // digit passes by this one CTA over the whole recording
       unsigned int* hist = reinterpret_cast<unsigned int*>(s_key);
       if (tid == 0) { s_pref = s.prefix; s_rank = s.rank; s_below = s.below; s_count = s.count; }
       __syncthreads();
       const double* __restrict__ xi = x + it.m_off;
-      for (int p = 2; p < SEL_PASSES; ++p) {
+      for (int p = npre; p < SEL_PASSES; ++p) {
         const int sh = sel_shift(p), bits = sel_bits(p), upb = sh + bits;
         const unsigned int mask = (1u << bits) - 1u;
         for (int t = tid; t < SEL_BINS; t += SEL_FIN_THREADS) hist[t] = 0;
@@ -405,7 +440,7 @@ struct SelectBuffers {
   unsigned int* hist;
   unsigned int* count;
   unsigned long long* buf;
-  unsigned long long* next_above;
+  unsigned long long* next_above;   // [3][MAXQ * n]: next_above | bmin (both preset to ~0) | bmax (preset to 0)
 };
 
 static int carve_select(Workspace& ws, int n_items, SelectBuffers* b) {
@@ -414,7 +449,7 @@ static int carve_select(Workspace& ws, int n_items, SelectBuffers* b) {
   b->hist = ws.take<unsigned int>(static_cast<size_t>(n_items) * SEL_MAXQ * SEL_PASSES * SEL_BINS + SEL_MAXQ * n_items);
   b->count = b->hist + static_cast<size_t>(n_items) * SEL_MAXQ * SEL_PASSES * SEL_BINS;
   b->buf = ws.take<unsigned long long>(static_cast<size_t>(n_items) * SEL_MAXQ * SEL_CAP);
-  b->next_above = ws.take<unsigned long long>(static_cast<size_t>(SEL_MAXQ) * n_items);
+  b->next_above = ws.take<unsigned long long>(static_cast<size_t>(3) * SEL_MAXQ * n_items);
   return ws.overflow ? BPM_ERR_WORKSPACE : BPM_OK;
 }
 
@@ -444,22 +479,27 @@ int quantile_multi_run(const double* x, const BpmItem* items, const BatchShape& 
   const int n = sh.n_items;
   const size_t zero_words = static_cast<size_t>(n) * SEL_MAXQ * SEL_PASSES * SEL_BINS + static_cast<size_t>(SEL_MAXQ) * n;
   if (cudaMemsetAsync(b.hist, 0, sizeof(unsigned int) * zero_words, st) != cudaSuccess) return BPM_ERR_CUDA;
-  if (cudaMemsetAsync(b.next_above, 0xff, sizeof(unsigned long long) * SEL_MAXQ * n, st) != cudaSuccess) return BPM_ERR_CUDA;
+  const size_t nlv = static_cast<size_t>(SEL_MAXQ) * n;
+  if (cudaMemsetAsync(b.next_above, 0xff, sizeof(unsigned long long) * 2 * nlv, st) != cudaSuccess) return BPM_ERR_CUDA;
+  if (cudaMemsetAsync(b.next_above + 2 * nlv, 0, sizeof(unsigned long long) * nlv, st) != cudaSuccess) return BPM_ERR_CUDA;
+  // digit passes before the bucket is collected: two resolve 22 bits, enough below ~4 M samples; a third
+  // (33 bits) keeps the bucket under SEL_CAP for the long streams (24 h at 333 Hz = 28.8 M samples)
+  const int npre = sh.max_m > (1ll << 22) ? 3 : 2;
   BPM_KERNEL(k_select_init);
   k_select_init<<<cdiv(n, 128), 128, 0, st>>>(items, n, lv, b.states);
   BPM_LAUNCH_OK();
   const dim3 grid(cdiv(sh.max_m, SEL_TILE), n);
-  for (int p = 0; p < 2; ++p) {
+  for (int p = 0; p < npre; ++p) {
     BPM_KERNEL(k_select_pass);
     k_select_pass<<<grid, SEL_THREADS, 0, st>>>(x, items, p, nq, b.states, b.hist, n);
     BPM_LAUNCH_OK();
   }
-  SelCollect cl{b.buf, b.count, b.next_above};
+  SelCollect cl{b.buf, b.count, b.next_above, b.next_above + nlv, b.next_above + 2 * nlv};
   BPM_KERNEL(k_select_collect);
-  k_select_collect<<<grid, SEL_THREADS, 0, st>>>(x, items, nq, b.states, b.hist, cl, n);
+  k_select_collect<<<grid, SEL_THREADS, 0, st>>>(x, items, nq, b.states, b.hist, cl, npre, n);
   BPM_LAUNCH_OK();
   BPM_KERNEL(k_select_finish);
-  k_select_finish<<<n, SEL_FIN_THREADS, 0, st>>>(x, items, lv, b.states, cl, n);
+  k_select_finish<<<n, SEL_FIN_THREADS, 0, st>>>(x, items, lv, b.states, cl, npre, n);
   BPM_LAUNCH_OK();
   return BPM_OK;
 }

@@ -112,6 +112,18 @@ def test_quantile_large_buckets_slow_path(q, ops):
     assert ops.quantile(e, q) == np.quantile(e, q)
 
 
+@pytest.mark.parametrize("q", [0.1, 0.2, 0.77])
+def test_quantile_long_stream_regime(q, ops):
+    """More than 4 M samples: three digit passes before the bucket is collected (the 24-h Holter
+    stream has 28.8 M envelope samples); with and without a block of exact zeros (dropouts) that
+    swallows the target rank."""
+    rng = np.random.default_rng(23)
+    x = np.abs(rng.standard_normal(5_000_000)) ** 2.5 * 300.0
+    assert ops.quantile(x, q) == np.quantile(x, q)
+    x[1_000_000:2_200_000] = 0.0                           # 24 % digital silence
+    assert ops.quantile(x, q) == np.quantile(x, q)
+
+
 # ----------------------------------------------------------------------------- K4
 def _signals():
     rng = np.random.default_rng(5)
