@@ -16,7 +16,6 @@
 //   k_scan<BWD>    s_b[j] = Ad s_b[j+1] + P s_f[j] + ub0[j];  y[j] = C s_b[j] + D y_f[j]
 //   k_envelope     |y| -> centred rolling mean (pandas FixedWindowIndexer semantics).
 #include "common.cuh"
-#include <stdlib.h>
 
 namespace bpm {
 
@@ -845,8 +844,7 @@ int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
       return BPM_ERR_CUDA;
     // tile shape: small CTAs for long blocks (more resident warps per SM measured fastest),
     // wide CTAs for short blocks (keeps each bulk copy above a few KB)
-    static const int forced = getenv("BPM_CONTRACT_VARIANT") ? atoi(getenv("BPM_CONTRACT_VARIANT")) : -1;
-    const int variant = forced >= 0 ? forced : (block >= 96 ? 8 : 2);
+    // (tile shapes were measured on C2: 32 threads x 2 blocks per thread for long blocks, 128 x 2 for short)
     BPM_KERNEL(k_contract_i16);
     // PCM span of a CTA (threads * J blocks), rounded up to whole 16-byte words on both sides
 #define BPM_LAUNCH_CONTRACT(T, J, CTAS_PER_SM)                                                           \
@@ -866,17 +864,8 @@ int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
       k_contract_i16<T, J><<<dim3(static_cast<unsigned>(gx), n_items), T, smem, st>>>(                   \
           static_cast<const int16_t*>(pcm), items, design, b.uf, b.ub0, b.xe, static_cast<int>(stage));  \
     } while (0)
-    switch (variant) {
-      case 0: BPM_LAUNCH_CONTRACT(64, 2, 0); break;
-      case 2: BPM_LAUNCH_CONTRACT(128, 2, 0); break;
-      case 3: BPM_LAUNCH_CONTRACT(64, 1, 0); break;
-      case 4: BPM_LAUNCH_CONTRACT(64, 4, 0); break;
-      case 5: BPM_LAUNCH_CONTRACT(32, 4, 0); break;
-      case 6: BPM_LAUNCH_CONTRACT(32, 4, 3); break;
-      case 7: BPM_LAUNCH_CONTRACT(128, 2, 1); break;
-      case 8: BPM_LAUNCH_CONTRACT(32, 2, 0); break;
-      default: BPM_LAUNCH_CONTRACT(128, 1, 0); break;
-    }
+    if (block >= 96) BPM_LAUNCH_CONTRACT(32, 2, 0);
+    else BPM_LAUNCH_CONTRACT(128, 2, 0);
 #undef BPM_LAUNCH_CONTRACT
   } else if (block > 1) {
     BPM_KERNEL(k_contract_generic);

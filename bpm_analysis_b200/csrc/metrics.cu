@@ -35,8 +35,91 @@ __global__ void k_peak_deviation(const double* __restrict__ strength, const int6
 }
 
 // centred rolling mean, window max(5, int((P-1)*factor)), min_periods=1          (:99-100)
-// one warp per output: lanes stride over the window, then a shuffle reduction
+// The window grows with the recording (5 % of the peak count: 10 k samples for a 24-h stream), so
+// the mean comes from a prefix sum instead of re-adding the window per output:
+//   k_dev_prefix  one CTA per recording, chunks of 1024 x 8 values with a running carry; the
+//                 prefix S[0..n] is parked in the unused tail of the deviation buffer (2P <= m);
+//   k_dev_smooth  out[i] = (S[b+1] - S[a]) / (b - a + 1).
+// |S| stays below n * max(dev) <= n, so the difference is exact to ~1e-16 * n / w relative.
+constexpr int DP_SCAN_THREADS = 1024;
+constexpr int DP_SCAN_PER = 8;
+
+__global__ void __launch_bounds__(DP_SCAN_THREADS) k_dev_prefix(double* __restrict__ dev,
+                                                                const int64_t* __restrict__ peak_count,
+                                                                const BpmItem* __restrict__ items) {
+  __shared__ double s_warp[DP_SCAN_THREADS / 32];
+  __shared__ double s_carry;
+  const BpmItem it = items[blockIdx.x];
+  const long long P = peak_count[blockIdx.x];
+  const long long n = P - 1;
+  if (n < 1) return;
+  const double* d = dev + it.m_off;
+  double* S = dev + it.m_off + P;                       // S[0..n]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { s_carry = 0.0; S[0] = 0.0; }
+  __syncthreads();
+  for (long long base = 0; base < n; base += DP_SCAN_THREADS * DP_SCAN_PER) {
+    const long long k0 = base + static_cast<long long>(tid) * DP_SCAN_PER;
+    double v[DP_SCAN_PER];
+    double run = 0.0;
+#pragma unroll
+    for (int u = 0; u < DP_SCAN_PER; ++u) {
+      v[u] = (k0 + u < n) ? d[k0 + u] : 0.0;
+      run += v[u];
+      v[u] = run;                                      // inclusive inside the thread
+    }
+    double inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      double w = s_warp[lane];
+      double wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      s_warp[lane] = wi - w;                           // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    const double before = s_carry + s_warp[warp] + (inc - run);
+#pragma unroll
+    for (int u = 0; u < DP_SCAN_PER; ++u)
+      if (k0 + u < n) S[k0 + u + 1] = before + v[u];
+    __syncthreads();
+    if (tid == DP_SCAN_THREADS - 1) s_carry = before + run;
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(256) k_dev_smooth(const double* __restrict__ dev,
+                                                    const int64_t* __restrict__ peak_count,
+                                                    const BpmItem* __restrict__ items, double factor,
+                                                    double* __restrict__ out) {
+  const BpmItem it = items[blockIdx.y];
+  const long long P = peak_count[blockIdx.y];
+  const long long n = P - 1;
+  long long w = static_cast<long long>(__dmul_rn(static_cast<double>(n), factor));
+  if (w < 5) w = 5;
+  const long long off = (w - 1) / 2;
+  const double* S = dev + it.m_off + P;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long a = i + 1 + off - w, b = i + off;
+    if (a < 0) a = 0;
+    if (b > n - 1) b = n - 1;
+    out[it.m_off + i] = __ddiv_rn(__dsub_rn(S[b + 1], S[a]), static_cast<double>(b - a + 1));
+  }
+}
+
+// centred rolling mean, window max(5, int((P-1)*factor)), min_periods=1          (:99-100)
+// (short recordings) one warp per output: lanes stride over the window, then a shuffle reduction
+__global__ void __launch_bounds__(256) k_dev_smooth_direct(const double* __restrict__ dev,
                                                     const int64_t* __restrict__ peak_count,
                                                     const BpmItem* __restrict__ items, double factor,
                                                     double* __restrict__ out) {
@@ -75,9 +158,19 @@ int peak_metrics_run(const double* env, const double* floor_, const int64_t* pea
   BPM_KERNEL(k_peak_deviation);
   k_peak_deviation<<<grid, 256, 0, st>>>(strength, peak_count, items, deviation);
   BPM_LAUNCH_OK();
-  BPM_KERNEL(k_dev_smooth);
-  k_dev_smooth<<<grid, 256, 0, st>>>(deviation, peak_count, items, factor, smoothed);
-  BPM_LAUNCH_OK();
+  if (sh.max_m <= (1ll << 22)) {
+    // short recordings: the window is a few hundred values, re-adding it per output is cheapest
+    BPM_KERNEL(k_dev_smooth_direct);
+    k_dev_smooth_direct<<<grid, 256, 0, st>>>(deviation, peak_count, items, factor, smoothed);
+    BPM_LAUNCH_OK();
+  } else {
+    BPM_KERNEL(k_dev_prefix);
+    k_dev_prefix<<<sh.n_items, DP_SCAN_THREADS, 0, st>>>(deviation, peak_count, items);
+    BPM_LAUNCH_OK();
+    BPM_KERNEL(k_dev_smooth);
+    k_dev_smooth<<<grid, 256, 0, st>>>(deviation, peak_count, items, factor, smoothed);
+    BPM_LAUNCH_OK();
+  }
   return BPM_OK;
 }
 

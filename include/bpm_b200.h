@@ -156,7 +156,8 @@ int bpm_raw_peaks(const double* envelope, const double* floor, const BpmItem* it
 /* ---- K8: numeric part of PeakClassifier._initialize_state, bpm_analysis.py:93-100 ---
  * strength[p] = max(0, env - floor) at peaks; deviation[p-1]; smoothed deviation
  * (centred rolling mean, window max(5, int((P-1)*smoothing_factor)), min_periods=1).
- * Outputs are laid out like the peak list (at m_off, length P resp. P-1). */
+ * Outputs are laid out like the peak list (at m_off, length P resp. P-1); the unused tail of
+ * `deviation` (entries P .. 2P-1 of the recording's m) is used as scratch for a prefix sum. */
 int bpm_peak_metrics(const double* envelope, const double* floor, const int64_t* peaks,
                      const int64_t* peak_count, const BpmItem* items, const BpmItem* items_host,
                      int n_items, double smoothing_factor, double* strength, double* deviation,
