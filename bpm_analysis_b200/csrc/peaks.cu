@@ -25,11 +25,45 @@ constexpr int PK_TILE = PK_THREADS * PK_PER;     // domain elements per tile
 
 __device__ __forceinline__ int64_t pk_slot0(int64_t dom_off, int item) { return dom_off / PK_TILE + item; }
 
+// ---- plateaus (scipy _local_maxima_1d: the midpoint (left + right) // 2 of a flat run that is
+// higher than both neighbours is the peak; runs touching either end are not peaks).
+// Sample i is that midpoint iff  dr == dl or dr == dl + 1  (dl / dr = equal samples to its left /
+// right).  Both sides are walked TOGETHER and the walk stops as soon as one side has ended and the
+// other is already too long, i.e. after min(dl, dr) + 2 steps -- a flat run of length L costs
+// O(L * min(L, cap)) in total instead of O(L^2), so digital silence does not stall the kernel.
+// Runs longer than 2 * cap + 1 cannot be settled by their midpoint within `cap` steps: the sample
+// exactly `cap` to the right of such a run's left edge registers the run (PLATEAU_REGISTER) and a
+// warp finishes it afterwards (k_long_plateaus).
+constexpr int PL_CAP = 512;
+enum { PLATEAU_NO = 0, PLATEAU_MID = 1, PLATEAU_REGISTER = 2 };
+
+template <class Val>
+__device__ __forceinline__ int plateau_test(Val val, int64_t i, int64_t n, double c, int cap) {
+  long long dl = -1, dr = -1;
+  for (int s = 1; s <= cap + 1; ++s) {
+    if (dl < 0 && (i - s < 0 || val(i - s) != c)) dl = s - 1;
+    if (dr < 0 && (i + s > n - 1 || val(i + s) != c)) dr = s - 1;
+    if (dl >= 0 && dr >= 0) break;
+    if (dl >= 0 && s > dl + 1) break;        // right side longer than dl + 1: not the midpoint
+    if (dr >= 0 && s > dr) break;            // left side longer than dr: not the midpoint
+  }
+  if (dl >= 0 && dr >= 0) {
+    if (dr != dl && dr != dl + 1) return PLATEAU_NO;
+    const int64_t L = i - dl, R = i + dr;
+    return (L >= 1 && R <= n - 2 && val(L - 1) < c && val(R + 1) < c) ? PLATEAU_MID : PLATEAU_NO;
+  }
+  // the run is longer than cap on the right; register it from the one sample `cap` past its left edge
+  if (dl == cap && dr < 0 && i - dl >= 1 && val(i - dl - 1) < c) return PLATEAU_REGISTER;
+  return PLATEAU_NO;
+}
+
 __global__ void __launch_bounds__(PK_THREADS) k_localmax_flags(const double* __restrict__ x, int sign,
                                                                const double* __restrict__ height,
                                                                const BpmItem* __restrict__ items,
                                                                unsigned char* __restrict__ flags,
-                                                               int* __restrict__ tile_counts) {
+                                                               int* __restrict__ tile_counts,
+                                                               int64_t* __restrict__ long_runs,
+                                                               int* __restrict__ long_count) {
   __shared__ int s_cnt[PK_THREADS / 32];
   const int item = blockIdx.y;
   const BpmItem it = items[item];
@@ -49,14 +83,12 @@ __global__ void __launch_bounds__(PK_THREADS) k_localmax_flags(const double* __r
       if (l < c && r < c) {
         pk = true;
       } else if ((l == c || r == c) && l <= c && r <= c) {
-        // plateau member: locate its edges; peak iff both outer neighbours are lower and
-        // this is the midpoint (left + right) // 2.  Plateaus touching either end are not peaks.
-        int64_t L = i, R = i;
-        while (L - 1 >= 0 && signed_val(xi[L - 1], sign) == c) --L;
-        while (R + 1 <= n - 1 && signed_val(xi[R + 1], sign) == c) ++R;
-        if (L >= 1 && R <= n - 2 && signed_val(xi[L - 1], sign) < c && signed_val(xi[R + 1], sign) < c &&
-            i == (L + R) / 2)
-          pk = true;
+        const int t = plateau_test([&](int64_t j) { return signed_val(xi[j], sign); }, i, n, c, PL_CAP);
+        pk = (t == PLATEAU_MID);
+        if (t == PLATEAU_REGISTER) {
+          const int slot = atomicAdd(long_count + item, 1);
+          long_runs[it.m_off / PL_CAP + item + slot] = i - PL_CAP;       // left edge of the run
+        }
       }
       if (pk && height != nullptr) pk = (height[it.m_off + i] <= c);
     }
@@ -73,15 +105,63 @@ __global__ void __launch_bounds__(PK_THREADS) k_localmax_flags(const double* __r
   }
 }
 
+// flat runs longer than 2 * PL_CAP + 1 (registered by k_localmax_flags): one warp walks each run
+// 32 samples per step, flags its midpoint if the run is a strict local maximum and bumps the
+// count of the tile the midpoint lies in.  Almost always there is nothing to do.  Runs at the top
+// of k_tile_scan (one CTA per recording, after every k_localmax_flags CTA has finished).
+struct LongRuns {
+  const double* x;          // nullptr: no plateau stage in this compaction
+  const double* height;
+  const int64_t* runs;
+  const int* count;
+  unsigned char* flags;
+  int sign;
+};
+
+__device__ void finish_long_plateaus(const LongRuns& lr, const BpmItem& it, int item, int* __restrict__ tile_counts) {
+  const int cnt = lr.count[item];
+  if (cnt == 0) return;
+  const double* __restrict__ xi = lr.x + it.m_off;
+  const int64_t n = it.m;
+  const int lane = threadIdx.x & 31;
+  for (int e = threadIdx.x >> 5; e < cnt; e += blockDim.x >> 5) {
+    const int64_t L = lr.runs[it.m_off / PL_CAP + item + e];
+    const double c = signed_val(xi[L], lr.sign);
+    int64_t R = L;
+    while (true) {
+      const int64_t j = R + 1 + lane;
+      const bool eq = (j <= n - 1) && signed_val(xi[j], lr.sign) == c;
+      const unsigned m = __ballot_sync(0xffffffffu, eq);
+      if (m == 0xffffffffu) { R += 32; continue; }
+      R += __ffs(~m) - 1;
+      break;
+    }
+    if (R - L + 1 <= 2 * PL_CAP + 1) continue;          // short enough: its midpoint settled it already
+    if (R > n - 2 || !(signed_val(xi[R + 1], lr.sign) < c)) continue;
+    const int64_t mid = (L + R) / 2;
+    if (lr.height != nullptr && !(lr.height[it.m_off + mid] <= c)) continue;
+    if (lane == 0) {
+      lr.flags[it.m_off + mid] = 1;
+      atomicAdd(tile_counts + pk_slot0(it.m_off, item) + mid / PK_TILE, 1);
+    }
+  }
+}
+
 // per recording: tile_counts -> exclusive offsets (in place), total -> totals[item]
 // dom_len == nullptr: the domain is the recording's m samples.
 __global__ void __launch_bounds__(256) k_tile_scan(const BpmItem* __restrict__ items,
                                                    const int64_t* __restrict__ dom_len,
-                                                   int* __restrict__ tile_counts, int64_t* __restrict__ totals) {
+                                                   int* __restrict__ tile_counts, int64_t* __restrict__ totals,
+                                                   LongRuns lr) {
   __shared__ int s_scan[34];
   __shared__ int s_carry;
   const int item = blockIdx.x;
   const BpmItem it = items[item];
+  if (lr.x != nullptr) {
+    finish_long_plateaus(lr, it, item, tile_counts);
+    __threadfence();
+    __syncthreads();
+  }
   const int64_t len = dom_len ? dom_len[item] : it.m;
   const int64_t nt = (len + PK_TILE - 1) / PK_TILE;
   int* tc = tile_counts + pk_slot0(it.m_off, item);
@@ -444,10 +524,7 @@ __global__ void __launch_bounds__(FPS_THREADS) k_find_peaks_small(const double* 
       if (l < c && r < c) {
         pk = true;
       } else if ((l == c || r == c) && l <= c && r <= c) {
-        int L = i, R = i;
-        while (L - 1 >= 0 && xs[L - 1] == c) --L;
-        while (R + 1 <= n - 1 && xs[R + 1] == c) ++R;
-        pk = (L >= 1 && R <= n - 2 && xs[L - 1] < c && xs[R + 1] < c && i == (L + R) / 2);
+        pk = plateau_test([&](int64_t j) { return xs[j]; }, i, n, c, FPS_MAXN) == PLATEAU_MID;
       }
       if (pk && height != nullptr) pk = (height[it.m_off + i] <= c);
       return pk;
@@ -522,6 +599,8 @@ struct PeakBuffers {
   int* tile_counts;         // [total_m / PK_TILE + n_items + 1]
   int64_t* cand;            // [total_m]
   int64_t* cand_count;      // [n_items]
+  int64_t* long_runs;       // [total_m / PL_CAP + n_items] left edges of very long flat runs
+  int* long_count;          // [n_items]
 };
 
 static int carve_peaks(Workspace& ws, int64_t total_m, int n_items, PeakBuffers* b) {
@@ -530,6 +609,8 @@ static int carve_peaks(Workspace& ws, int64_t total_m, int n_items, PeakBuffers*
   b->tile_counts = ws.take<int>(total_m / PK_TILE + n_items + 1);
   b->cand = ws.take<int64_t>(total_m);
   b->cand_count = ws.take<int64_t>(n_items);
+  b->long_runs = ws.take<int64_t>(total_m / PL_CAP + n_items);
+  b->long_count = ws.take<int>(n_items);
   return ws.overflow ? BPM_ERR_WORKSPACE : BPM_OK;
 }
 
@@ -541,9 +622,9 @@ size_t find_peaks_workspace_bytes(int64_t total_m, int n_items) {
 }
 
 // compaction of a flag array over a domain (samples or a device-length list)
-int compact_run(const unsigned char* flags, const int64_t* src, const BpmItem* items, const BatchShape& sh,
-                const int64_t* dom_len, int64_t max_len, bool counts_ready, int* tile_counts,
-                int64_t* out, int64_t* out_count, cudaStream_t st) {
+static int compact_run_lr(const unsigned char* flags, const int64_t* src, const BpmItem* items, const BatchShape& sh,
+                          const int64_t* dom_len, int64_t max_len, bool counts_ready, int* tile_counts,
+                          int64_t* out, int64_t* out_count, const LongRuns& lr, cudaStream_t st) {
   const dim3 grid(cdiv(max_len > 0 ? max_len : 1, PK_TILE), sh.n_items);
   if (!counts_ready) {
     BPM_KERNEL(k_count_flags);
@@ -551,12 +632,19 @@ int compact_run(const unsigned char* flags, const int64_t* src, const BpmItem* i
     BPM_LAUNCH_OK();
   }
   BPM_KERNEL(k_tile_scan);
-  k_tile_scan<<<sh.n_items, 256, 0, st>>>(items, dom_len, tile_counts, out_count);
+  k_tile_scan<<<sh.n_items, 256, 0, st>>>(items, dom_len, tile_counts, out_count, lr);
   BPM_LAUNCH_OK();
   BPM_KERNEL(k_scatter);
   k_scatter<<<grid, PK_THREADS, 0, st>>>(flags, src, items, dom_len, tile_counts, out);
   BPM_LAUNCH_OK();
   return BPM_OK;
+}
+
+int compact_run(const unsigned char* flags, const int64_t* src, const BpmItem* items, const BatchShape& sh,
+                const int64_t* dom_len, int64_t max_len, bool counts_ready, int* tile_counts,
+                int64_t* out, int64_t* out_count, cudaStream_t st) {
+  return compact_run_lr(flags, src, items, sh, dom_len, max_len, counts_ready, tile_counts, out, out_count,
+                        LongRuns{nullptr, nullptr, nullptr, nullptr, nullptr, 1}, st);
 }
 
 // prominence_ready: event after which the prominence threshold is valid (it may be produced on
@@ -578,10 +666,12 @@ int find_peaks_run(const double* x, int sign, const double* height, const double
   PeakBuffers b;
   BPM_TRY(carve_peaks(ws, sh.total_m, sh.n_items, &b));
   const dim3 grid(cdiv(sh.max_m, PK_TILE), sh.n_items);
+  if (cudaMemsetAsync(b.long_count, 0, sizeof(int) * sh.n_items, st) != cudaSuccess) return BPM_ERR_CUDA;
   BPM_KERNEL(k_localmax_flags);
-  k_localmax_flags<<<grid, PK_THREADS, 0, st>>>(x, sign, height, items, b.flags, b.tile_counts);
+  k_localmax_flags<<<grid, PK_THREADS, 0, st>>>(x, sign, height, items, b.flags, b.tile_counts, b.long_runs, b.long_count);
   BPM_LAUNCH_OK();
-  BPM_TRY(compact_run(b.flags, nullptr, items, sh, nullptr, sh.max_m, true, b.tile_counts, b.cand, b.cand_count, st));
+  BPM_TRY(compact_run_lr(b.flags, nullptr, items, sh, nullptr, sh.max_m, true, b.tile_counts, b.cand, b.cand_count,
+                         LongRuns{x, height, b.long_runs, b.long_count, b.flags, sign}, st));
   // a local maximum needs a lower neighbour on both sides: at most (m-1)/2 candidates
   const int64_t max_c = sh.max_m / 2 + 1;
   BPM_KERNEL(k_distance);

@@ -160,6 +160,60 @@ def test_find_peaks_matches_scipy(name, distance, ops):
         assert np.array_equal(got_p, ref_p)
 
 
+def test_find_peaks_long_plateaus(ops):
+    """Flat runs of every interesting length around the 512-step walk bound (shorter, exactly at
+    2*512+1, longer, far longer), as strict maxima, as shelves (one side higher) and touching the
+    array ends; plus a constant signal of a million samples, which must simply return nothing."""
+    rng = np.random.default_rng(9)
+    parts, level = [], 0.0
+    for L in (1, 2, 3, 5, 511, 512, 513, 1023, 1024, 1025, 1026, 1027, 2049, 5000, 40000):
+        for kind in ("max", "shelf_up", "shelf_down", "min"):
+            base = rng.random(40) * 0.1
+            lo = float(base.max()) + 0.5
+            run = np.full(L, lo + 1.0)
+            left = base + (2.0 if kind == "shelf_down" else 0.0) + (3.0 if kind == "min" else 0.0)
+            right = rng.random(40) * 0.1 + (2.0 if kind == "shelf_up" else 0.0) + (3.0 if kind == "min" else 0.0)
+            parts += [left, run, right]
+    x = np.concatenate([np.full(700, 9.0)] + parts + [np.full(1500, 9.0)])       # flat runs touching both ends
+    for sign in (1, -1):
+        ref, _ = scipy_find_peaks(sign * x)
+        got = ops.find_peaks(x, sign=sign)
+        assert np.array_equal(got, ref)
+    ref, _ = scipy_find_peaks(x, distance=7, prominence=0.5)
+    assert np.array_equal(ops.find_peaks(x, distance=7, prominence=0.5), ref)
+    flat = np.full(1_000_000, 0.25)
+    assert len(ops.find_peaks(flat)) == 0 and len(ops.find_peaks(flat, sign=-1)) == 0
+    flat[400_000] = 0.2                                    # two 400 k / 600 k shelves around a notch: still no maximum
+    assert len(ops.find_peaks(flat)) == 0
+    assert np.array_equal(ops.find_peaks(flat, sign=-1), [400_000])
+    bump = np.zeros(900_001)
+    bump[1:-1] = 1.0                                       # one 899 999-sample plateau above both ends
+    assert np.array_equal(ops.find_peaks(bump), scipy_find_peaks(bump)[0])
+
+
+def test_digital_silence_recording(fe, ref_params):
+    """An all-zero recording (and one that is silent for its first 40 s): the envelope is a flat
+    run, the reference finds no troughs / peaks there; the GPU path must agree and must not stall."""
+    from oracle import ref_port
+    sr = 44100
+    for pcm in (np.zeros(sr * 60, dtype=np.int16),
+                np.concatenate([np.zeros(sr * 40, dtype=np.int16),
+                                (3000 * np.sin(2 * np.pi * 50 * np.arange(sr * 20) / sr) *
+                                 (np.arange(sr * 20) % (sr // 2) < 2000)).astype(np.int16)])):
+        o = ref_port.front_end(pcm, sr, ref_params)
+        env, rate, _, _ = fe.preprocess_pcm(pcm, sr, ref_params)
+        assert rel_err(env, o["envelope"]) < TOL
+        floor, tr = fe._calculate_dynamic_noise_floor(o["envelope"], rate, ref_params)
+        assert np.array_equal(tr, o["troughs"])
+        assert rel_err(floor.values, o["floor"]) < TOL
+
+        class Clf:
+            pass
+        c = Clf()
+        c.audio_envelope, c.sample_rate, c.params = o["envelope"], rate, ref_params
+        assert np.array_equal(fe._find_raw_peaks(c, o["floor"]), o["peaks"])
+
+
 def test_find_peaks_height_array(ops):
     rng = np.random.default_rng(9)
     x = np.abs(rng.standard_normal(30000))
