@@ -35,6 +35,7 @@ __device__ __forceinline__ int64_t pk_slot0(int64_t dom_off, int item) { return 
 // exactly `cap` to the right of such a run's left edge registers the run (PLATEAU_REGISTER) and a
 // warp finishes it afterwards (k_long_plateaus).
 constexpr int PL_CAP = 512;
+constexpr int PL_PER_TILE = 8;          // registering samples lie > PL_CAP apart: at most 4 per 2048-sample tile
 enum { PLATEAU_NO = 0, PLATEAU_MID = 1, PLATEAU_REGISTER = 2 };
 
 template <class Val>
@@ -65,6 +66,10 @@ __global__ void __launch_bounds__(PK_THREADS) k_localmax_flags(const double* __r
                                                                int64_t* __restrict__ long_runs,
                                                                int* __restrict__ long_count) {
   __shared__ int s_cnt[PK_THREADS / 32];
+  __shared__ int s_nreg;                      // long flat runs registered by this tile (<= PL_PER_TILE)
+  __shared__ long long s_reg[PL_PER_TILE];
+  if (threadIdx.x == 0) s_nreg = 0;
+  __syncthreads();
   const int item = blockIdx.y;
   const BpmItem it = items[item];
   const int64_t i0 = static_cast<int64_t>(blockIdx.x) * PK_TILE;
@@ -86,8 +91,8 @@ __global__ void __launch_bounds__(PK_THREADS) k_localmax_flags(const double* __r
         const int t = plateau_test([&](int64_t j) { return signed_val(xi[j], sign); }, i, n, c, PL_CAP);
         pk = (t == PLATEAU_MID);
         if (t == PLATEAU_REGISTER) {
-          const int slot = atomicAdd(long_count + item, 1);
-          long_runs[it.m_off / PL_CAP + item + slot] = i - PL_CAP;       // left edge of the run
+          const int slot = atomicAdd(&s_nreg, 1);
+          if (slot < PL_PER_TILE) s_reg[slot] = i - PL_CAP;              // left edge of the run
         }
       }
       if (pk && height != nullptr) pk = (height[it.m_off + i] <= c);
@@ -101,7 +106,12 @@ __global__ void __launch_bounds__(PK_THREADS) k_localmax_flags(const double* __r
   if (threadIdx.x == 0) {
     int t = 0;
     for (int w = 0; w < PK_THREADS / 32; ++w) t += s_cnt[w];
-    tile_counts[pk_slot0(it.m_off, item) + blockIdx.x] = t;
+    const int64_t slot = pk_slot0(it.m_off, item) + blockIdx.x;
+    tile_counts[slot] = t;
+    // every tile writes its (almost always zero) registration count: no memset, no global atomics
+    const int nr = s_nreg < PL_PER_TILE ? s_nreg : PL_PER_TILE;
+    long_count[slot] = nr;
+    for (int e = 0; e < nr; ++e) long_runs[slot * PL_PER_TILE + e] = s_reg[e];
   }
 }
 
@@ -119,13 +129,20 @@ struct LongRuns {
 };
 
 __device__ void finish_long_plateaus(const LongRuns& lr, const BpmItem& it, int item, int* __restrict__ tile_counts) {
-  const int cnt = lr.count[item];
-  if (cnt == 0) return;
   const double* __restrict__ xi = lr.x + it.m_off;
   const int64_t n = it.m;
   const int lane = threadIdx.x & 31;
-  for (int e = threadIdx.x >> 5; e < cnt; e += blockDim.x >> 5) {
-    const int64_t L = lr.runs[it.m_off / PL_CAP + item + e];
+  const int64_t nt = (n + 2047) / 2048, slot0 = it.m_off / 2048 + item;        // sample tiles (PK_TILE)
+  // the warps look at 32 tiles at a time; tiles with registered runs are rare
+  for (int64_t tb = static_cast<int64_t>(threadIdx.x >> 5) * 32; tb < nt; tb += static_cast<int64_t>(blockDim.x >> 5) * 32) {
+    const int mine = (tb + lane < nt) ? lr.count[slot0 + tb + lane] : 0;
+    unsigned pending = __ballot_sync(0xffffffffu, mine > 0);
+    while (pending) {
+      const int src = __ffs(pending) - 1;
+      pending &= pending - 1;
+      const int cnt = __shfl_sync(0xffffffffu, mine, src);
+      for (int e = 0; e < cnt; ++e) {
+    const int64_t L = lr.runs[(slot0 + tb + src) * PL_PER_TILE + e];
     const double c = signed_val(xi[L], lr.sign);
     int64_t R = L;
     while (true) {
@@ -143,6 +160,8 @@ __device__ void finish_long_plateaus(const LongRuns& lr, const BpmItem& it, int 
     if (lane == 0) {
       lr.flags[it.m_off + mid] = 1;
       atomicAdd(tile_counts + pk_slot0(it.m_off, item) + mid / PK_TILE, 1);
+    }
+      }
     }
   }
 }
@@ -599,8 +618,8 @@ struct PeakBuffers {
   int* tile_counts;         // [total_m / PK_TILE + n_items + 1]
   int64_t* cand;            // [total_m]
   int64_t* cand_count;      // [n_items]
-  int64_t* long_runs;       // [total_m / PL_CAP + n_items] left edges of very long flat runs
-  int* long_count;          // [n_items]
+  int64_t* long_runs;       // [tiles][PL_PER_TILE] left edges of very long flat runs, per sample tile
+  int* long_count;          // [tiles]
 };
 
 static int carve_peaks(Workspace& ws, int64_t total_m, int n_items, PeakBuffers* b) {
@@ -609,8 +628,8 @@ static int carve_peaks(Workspace& ws, int64_t total_m, int n_items, PeakBuffers*
   b->tile_counts = ws.take<int>(total_m / PK_TILE + n_items + 1);
   b->cand = ws.take<int64_t>(total_m);
   b->cand_count = ws.take<int64_t>(n_items);
-  b->long_runs = ws.take<int64_t>(total_m / PL_CAP + n_items);
-  b->long_count = ws.take<int>(n_items);
+  b->long_runs = ws.take<int64_t>((total_m / PK_TILE + n_items + 1) * PL_PER_TILE);
+  b->long_count = ws.take<int>(total_m / PK_TILE + n_items + 1);
   return ws.overflow ? BPM_ERR_WORKSPACE : BPM_OK;
 }
 
@@ -666,7 +685,6 @@ int find_peaks_run(const double* x, int sign, const double* height, const double
   PeakBuffers b;
   BPM_TRY(carve_peaks(ws, sh.total_m, sh.n_items, &b));
   const dim3 grid(cdiv(sh.max_m, PK_TILE), sh.n_items);
-  if (cudaMemsetAsync(b.long_count, 0, sizeof(int) * sh.n_items, st) != cudaSuccess) return BPM_ERR_CUDA;
   BPM_KERNEL(k_localmax_flags);
   k_localmax_flags<<<grid, PK_THREADS, 0, st>>>(x, sign, height, items, b.flags, b.tile_counts, b.long_runs, b.long_count);
   BPM_LAUNCH_OK();

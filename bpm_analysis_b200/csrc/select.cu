@@ -440,16 +440,22 @@ struct SelectBuffers {
   unsigned int* hist;
   unsigned int* count;
   unsigned long long* buf;
-  unsigned long long* next_above;   // [3][MAXQ * n]: next_above | bmin (both preset to ~0) | bmax (preset to 0)
+  unsigned long long* next_above;   // [2][MAXQ * n]: next_above | bmin (both preset to ~0)
+  unsigned long long* bmax;         // [MAXQ * n] (preset to 0)
+  size_t zero_bytes;
 };
 
 static int carve_select(Workspace& ws, int n_items, SelectBuffers* b) {
   b->states = ws.take<SelState>(static_cast<size_t>(SEL_PASSES + 1) * SEL_MAXQ * n_items);
   // the two digit histograms per level and the collect counters are zeroed together
+  // one zeroed region: bmax | histograms | collect counters;  one 0xff region: next_above | bmin
+  b->bmax = ws.take<unsigned long long>(static_cast<size_t>(SEL_MAXQ) * n_items);
   b->hist = ws.take<unsigned int>(static_cast<size_t>(n_items) * SEL_MAXQ * SEL_PASSES * SEL_BINS + SEL_MAXQ * n_items);
   b->count = b->hist + static_cast<size_t>(n_items) * SEL_MAXQ * SEL_PASSES * SEL_BINS;
+  b->zero_bytes = ws.measuring() ? 0 : static_cast<size_t>(reinterpret_cast<char*>(b->count + SEL_MAXQ * n_items) -
+                                                            reinterpret_cast<char*>(b->bmax));
   b->buf = ws.take<unsigned long long>(static_cast<size_t>(n_items) * SEL_MAXQ * SEL_CAP);
-  b->next_above = ws.take<unsigned long long>(static_cast<size_t>(3) * SEL_MAXQ * n_items);
+  b->next_above = ws.take<unsigned long long>(static_cast<size_t>(2) * SEL_MAXQ * n_items);
   return ws.overflow ? BPM_ERR_WORKSPACE : BPM_OK;
 }
 
@@ -477,11 +483,9 @@ int quantile_multi_run(const double* x, const BpmItem* items, const BatchShape& 
   SelectBuffers b;
   BPM_TRY(carve_select(ws, sh.n_items, &b));
   const int n = sh.n_items;
-  const size_t zero_words = static_cast<size_t>(n) * SEL_MAXQ * SEL_PASSES * SEL_BINS + static_cast<size_t>(SEL_MAXQ) * n;
-  if (cudaMemsetAsync(b.hist, 0, sizeof(unsigned int) * zero_words, st) != cudaSuccess) return BPM_ERR_CUDA;
   const size_t nlv = static_cast<size_t>(SEL_MAXQ) * n;
+  if (cudaMemsetAsync(b.bmax, 0, b.zero_bytes, st) != cudaSuccess) return BPM_ERR_CUDA;
   if (cudaMemsetAsync(b.next_above, 0xff, sizeof(unsigned long long) * 2 * nlv, st) != cudaSuccess) return BPM_ERR_CUDA;
-  if (cudaMemsetAsync(b.next_above + 2 * nlv, 0, sizeof(unsigned long long) * nlv, st) != cudaSuccess) return BPM_ERR_CUDA;
   // digit passes before the bucket is collected: two resolve 22 bits, enough below ~4 M samples; a third
   // (33 bits) keeps the bucket under SEL_CAP for the long streams (24 h at 333 Hz = 28.8 M samples)
   const int npre = sh.max_m > (1ll << 22) ? 3 : 2;
@@ -494,7 +498,7 @@ int quantile_multi_run(const double* x, const BpmItem* items, const BatchShape& 
     k_select_pass<<<grid, SEL_THREADS, 0, st>>>(x, items, p, nq, b.states, b.hist, n);
     BPM_LAUNCH_OK();
   }
-  SelCollect cl{b.buf, b.count, b.next_above, b.next_above + nlv, b.next_above + 2 * nlv};
+  SelCollect cl{b.buf, b.count, b.next_above, b.next_above + nlv, b.bmax};
   BPM_KERNEL(k_select_collect);
   k_select_collect<<<grid, SEL_THREADS, 0, st>>>(x, items, nq, b.states, b.hist, cl, npre, n);
   BPM_LAUNCH_OK();
