@@ -287,6 +287,8 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        from bpm_analysis_b200.dist import bind_to_gpu_numa
+        bind_to_gpu_numa(local_rank)                # pinned ingest buffers on the GPU's own socket
 
     from bpm_analysis_b200 import _native, synth
     from bpm_analysis_b200.runtime import BeatRunner, GraphedStep, StageARunner, profile_kernels

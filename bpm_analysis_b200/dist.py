@@ -63,3 +63,25 @@ def summarize(result_item: Dict[str, object], duration_sec: float) -> np.ndarray
     """Per-recording summary row: [duration_s, n_troughs, n_peaks, mean envelope, mean floor]."""
     return np.array([duration_sec, len(result_item["troughs"]), len(result_item["peaks"]),
                      float(np.mean(result_item["envelope"])), float(np.mean(result_item["floor"]))])
+
+
+def bind_to_gpu_numa(device_index: int) -> bool:
+    """Pin the calling process to the CPU cores nearest to GPU ``device_index`` (NVML's ideal CPU
+    affinity) BEFORE it allocates pinned host buffers: the zero-copy ingest reads those buffers over
+    PCIe, and pages that sit on the other socket cross the inter-socket link as well.  Returns
+    False (and changes nothing) when NVML or sched_setaffinity is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:                                   # noqa: BLE001 - an optimisation only
+        return False
