@@ -746,7 +746,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, DIR == 0 ? 3 : 2) k_scan(ScanPar
 // pandas rolling(window=w, min_periods=1, center=True).mean() of |y|
 // (bpm_analysis.py:1052-1054): window [i+1+off-w, i+off] clipped, off=(w-1)//2.
 constexpr int ENV_THREADS = 256;
-constexpr int ENV_MAX_W = 1024;
+constexpr int ENV_MAX_W = 16384;     // rate // 10 of an undecimated 96 kHz recording still fits (133 KB of smem)
 
 __global__ void __launch_bounds__(ENV_THREADS) k_envelope(const double* __restrict__ y,
                                                           const BpmItem* __restrict__ items, int w,
@@ -912,9 +912,14 @@ int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
     k_scan<1, 0><<<sgrid, SCAN_THREADS, scan_smem_b, st>>>(sp);
   }
   BPM_LAUNCH_OK();
-  BPM_KERNEL(k_envelope);
-  k_envelope<<<dim3(cdiv(sh.max_m, ENV_THREADS), n_items), ENV_THREADS,
-               sizeof(double) * (ENV_THREADS + env_window), st>>>(filtered, items, env_window, envelope);
+  {
+    const size_t smem = sizeof(double) * (ENV_THREADS + env_window);
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(k_envelope, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    BPM_KERNEL(k_envelope);
+    k_envelope<<<dim3(cdiv(sh.max_m, ENV_THREADS), n_items), ENV_THREADS, smem, st>>>(filtered, items, env_window,
+                                                                                   envelope);
+  }
   BPM_LAUNCH_OK();
   return BPM_OK;
 }

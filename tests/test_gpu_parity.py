@@ -492,3 +492,68 @@ def test_pipelined_zero_copy_ingest_is_bit_identical(fe, ref_params):
             assert torch.equal(g["envelope"], w["envelope"]) and torch.equal(g["floor"], w["floor"])
             assert torch.equal(g["troughs"][:nt], w["troughs"][:nt]) and torch.equal(g["peaks"][:npk], w["peaks"][:npk])
             assert torch.equal(g["smoothed_dev"][:npk - 1], w["smoothed_dev"][:npk - 1])
+
+
+# ----------------------------------------------------------------------------- randomized sweep
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_randomized_recordings_match_oracle(seed, fe, ref_params):
+    """Random sample rates, durations, channel counts, sample formats, amplitudes and parameter
+    values (seeded): whatever the oracle returns -- or raises -- for a1..a4, the GPU path must too."""
+    import pandas as pd
+    from bpm_analysis_b200 import synth
+    from oracle import ref_port
+    rng = np.random.default_rng(1000 + seed)
+    sr = int(rng.choice([4000, 8000, 11025, 16000, 22050, 44100, 48000, 96000]))
+    dur = float(rng.uniform(0.4, 25.0))
+    bpm = float(rng.uniform(45, 180))
+    pcm, _, _ = synth.pcg_recording(dur, sr, lambda t: bpm, seed=seed)
+    kind = rng.choice(["i16", "i16", "f32", "u8", "i32", "f64", "stereo"])
+    if kind == "f32":
+        pcm = (pcm / 32768.0).astype(np.float32)
+    elif kind == "f64":
+        pcm = pcm / 32768.0 * float(rng.uniform(1e-3, 1e3))
+    elif kind == "u8":
+        pcm = ((pcm.astype(np.int32) >> 8) + 128).astype(np.uint8)
+    elif kind == "i32":
+        pcm = pcm.astype(np.int32) * 65536
+    elif kind == "stereo":
+        pcm = np.stack([pcm, (pcm * 0.5).astype(np.int16)], axis=1)
+    p = dict(ref_params)
+    p["downsample_factor"] = int(rng.choice([1, 7, 50, 300, 1000]))
+    p["noise_window_sec"] = float(rng.choice([0.5, 2, 10, 30]))
+    p["noise_floor_quantile"] = float(rng.choice([0.05, 0.2, 0.5]))
+    p["min_peak_distance_sec"] = float(rng.choice([0.02, 0.05, 0.2]))
+    p["peak_prominence_quantile"] = float(rng.choice([0.1, 0.1, 0.3]))
+    p["trough_rejection_multiplier"] = float(rng.choice([1.5, 4.0]))
+    try:
+        o = ref_port.front_end(pcm, sr, p)
+    except Exception as e:                                   # noqa: BLE001 - the reference's own failure modes
+        with pytest.raises(type(e)):
+            env, rate, _, _ = fe.preprocess_pcm(pcm, sr, p)
+            floor, tr = fe._calculate_dynamic_noise_floor(env, rate, p)
+            class C0:
+                pass
+            c0 = C0()
+            c0.audio_envelope, c0.sample_rate, c0.params = env, rate, p
+            fe._find_raw_peaks(c0, floor.values)
+        return
+    env, rate, filt, _ = fe.preprocess_pcm(pcm, sr, p)
+    assert rate == o["rate"]
+    # The reference filters with the transfer-function form (butter(...)->(b, a), filtfilt).  At the
+    # default decimated rate (~300 Hz) it agrees with the exact (SOS / state-space) filter to 6e-14; with
+    # decimation switched off the 20 Hz edge sits at 1e-3 of Nyquist and scipy's OWN tf-form result is
+    # 7e-11 (11 kHz) ... 7e-8 (44.1 kHz) away from its sosfiltfilt: that rounding noise of an
+    # ill-conditioned recursion is not reproducible by a reordered evaluation, so the envelope tolerance
+    # follows it there.  Index parity below is unaffected (it is asserted on the reference's envelope).
+    assert rel_err(env, o["envelope"]) < (TOL if rate <= 12000 else 1e-6)
+    # index outputs on the reference's own envelope (SURVEY 8c), floats to 1e-9
+    floor, tr = fe._calculate_dynamic_noise_floor(o["envelope"], rate, p)
+    assert np.array_equal(tr, o["troughs"])
+    assert rel_err(floor.values, o["floor"]) < TOL
+
+    class Clf:
+        pass
+    c = Clf()
+    c.audio_envelope, c.sample_rate, c.params = o["envelope"], rate, p
+    assert np.array_equal(fe._find_raw_peaks(c, o["floor"]), o["peaks"])
