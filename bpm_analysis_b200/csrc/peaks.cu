@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(DP_THREADS) k_distance(const double* __restric
 
 // Prominence rule on the survivors of the distance rule: one warp per candidate, grid-stride.
 constexpr int PR_THREADS = 256;
-constexpr int PR_BLOCKS = 148 * 4;
+constexpr int PR_BLOCKS = 148 * 8;
 
 __global__ void __launch_bounds__(PR_THREADS) k_prominence(const double* __restrict__ x, int sign,
                                                            const BpmItem* __restrict__ items,
@@ -416,10 +416,23 @@ __global__ void __launch_bounds__(PR_THREADS) k_prominence(const double* __restr
   unsigned char* stt = state + it.m_off;
   const int lane = threadIdx.x & 31;
   const int64_t warps = static_cast<int64_t>(gridDim.x) * (PR_THREADS / 32);
-  for (int64_t k = static_cast<int64_t>(blockIdx.x) * (PR_THREADS / 32) + (threadIdx.x >> 5); k < nc; k += warps) {
-    if (stt[k] != 1) continue;                            // warp-uniform
-    const bool ok = warp_prominence_ok(xi, sign, it.m, pos[k], thr);
-    if (lane == 0 && !ok) stt[k] = 0;
+  // a warp takes 32 consecutive candidates at a time: state and position come in with one coalesced
+  // load each, then the survivors of the distance step are walked one after the other
+  for (int64_t c0 = (static_cast<int64_t>(blockIdx.x) * (PR_THREADS / 32) + (threadIdx.x >> 5)) * 32; c0 < nc;
+       c0 += warps * 32) {
+    const int64_t k = c0 + lane;
+    const bool live = (k < nc) && stt[k] == 1;
+    const int64_t p = live ? pos[k] : 0;
+    unsigned todo = __ballot_sync(0xffffffffu, live);
+    bool drop = false;
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int64_t ps = __shfl_sync(0xffffffffu, p, src);
+      const bool ok = warp_prominence_ok(xi, sign, it.m, ps, thr);
+      if (lane == src && !ok) drop = true;
+    }
+    if (drop) stt[k] = 0;
   }
 }
 
