@@ -746,31 +746,72 @@ __global__ void __launch_bounds__(SCAN_THREADS, DIR == 0 ? 3 : 2) k_scan(ScanPar
 // pandas rolling(window=w, min_periods=1, center=True).mean() of |y|
 // (bpm_analysis.py:1052-1054): window [i+1+off-w, i+off] clipped, off=(w-1)//2.
 constexpr int ENV_THREADS = 256;
-constexpr int ENV_MAX_W = 16384;     // rate // 10 of an undecimated 96 kHz recording still fits (133 KB of smem)
+constexpr int ENV_R = 4;             // consecutive outputs per thread (they share the staged window)
+constexpr int ENV_TILE = ENV_THREADS * ENV_R;
+constexpr int ENV_MAX_W = 16384;     // rate // 10 of an undecimated 96 kHz recording still fits (174 KB of smem)
 
+// staged element e lives at e + e/4: the fill (consecutive e) and the per-thread reads (element
+// 4 t + k, i.e. 5 doubles between neighbouring lanes) are both bank-conflict free
+__device__ __forceinline__ int env_slot(int e) { return e + (e >> 2); }
+static size_t env_smem_bytes(int w) { return sizeof(double) * (static_cast<size_t>(ENV_TILE + w - 1) * 5 / 4 + 2); }
+
+// A thread forms ENV_R consecutive means from ONE pass over the w + ENV_R - 1 staged values they
+// share (9 shared-memory loads per output instead of 33 at the default window: the per-output
+// version was bound by shared-memory bandwidth, not HBM).  Every sum still adds its window in
+// ascending index order from 0.0, and positions outside the recording are staged as +0.0
+// (x + 0.0 == x for the non-negative partial sums), so the results are bit-identical to the
+// one-output-per-thread evaluation.
 __global__ void __launch_bounds__(ENV_THREADS) k_envelope(const double* __restrict__ y,
                                                           const BpmItem* __restrict__ items, int w,
                                                           double* __restrict__ env) {
-  extern __shared__ double s_abs[];          // ENV_THREADS + w
+  extern __shared__ double s_abs[];          // env_slot(ENV_TILE + w - 1) + 1
   const BpmItem it = items[blockIdx.y];
-  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * ENV_THREADS;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * ENV_TILE;
   if (i0 >= it.m) return;
   const int off = (w - 1) / 2;
   const int left = w - 1 - off;
   const int64_t lo = i0 - left;
-  const int n = ENV_THREADS + w - 1;
+  const int n = ENV_TILE + w - 1;
   for (int t = threadIdx.x; t < n; t += ENV_THREADS) {
     const int64_t k = lo + t;
-    s_abs[t] = (k >= 0 && k < it.m) ? fabs(y[it.m_off + k]) : 0.0;
+    s_abs[env_slot(t)] = (k >= 0 && k < it.m) ? fabs(y[it.m_off + k]) : 0.0;
   }
   __syncthreads();
-  const int64_t i = i0 + threadIdx.x;
-  if (i >= it.m) return;
-  const int64_t a = max(static_cast<int64_t>(0), i - left), b = min(it.m - 1, i + off);
-  double s = 0.0;
-  const int ta = static_cast<int>(a - lo), tb = static_cast<int>(b - lo);
-  for (int t = ta; t <= tb; ++t) s = __dadd_rn(s, s_abs[t]);
-  env[it.m_off + i] = __ddiv_rn(s, static_cast<double>(b - a + 1));
+  const int64_t ib = i0 + static_cast<int64_t>(threadIdx.x) * ENV_R;
+  if (ib >= it.m) return;
+  // output r (r = 0..3) sums the thread's elements k = r .. r + w - 1; element k is staged at
+  // 5 * threadIdx.x + k + k / 4
+  const double* __restrict__ e0 = s_abs + 5 * threadIdx.x;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int k = 0;
+#pragma unroll
+  for (; k < 3; ++k) {
+    const double v = e0[k];
+    if (k < w) s0 = __dadd_rn(s0, v);
+    if (k >= 1 && k <= w) s1 = __dadd_rn(s1, v);
+    if (k >= 2 && k <= w + 1) s2 = __dadd_rn(s2, v);
+  }
+#pragma unroll 4
+  for (; k < w; ++k) {
+    const double v = e0[k + (k >> 2)];
+    s0 = __dadd_rn(s0, v); s1 = __dadd_rn(s1, v); s2 = __dadd_rn(s2, v); s3 = __dadd_rn(s3, v);
+  }
+  for (; k < w + 3; ++k) {
+    const double v = e0[k + (k >> 2)];
+    if (k < w) s0 = __dadd_rn(s0, v);
+    if (k >= 1 && k <= w) s1 = __dadd_rn(s1, v);
+    if (k >= 2 && k <= w + 1) s2 = __dadd_rn(s2, v);
+    if (k >= 3) s3 = __dadd_rn(s3, v);
+  }
+  const double sums[ENV_R] = {s0, s1, s2, s3};
+#pragma unroll
+  for (int r = 0; r < ENV_R; ++r) {
+    const int64_t i = ib + r;
+    if (i < it.m) {
+      const int64_t a = max(static_cast<int64_t>(0), i - left), b = min(it.m - 1, i + off);
+      env[it.m_off + i] = __ddiv_rn(sums[r], static_cast<double>(b - a + 1));
+    }
+  }
 }
 
 // K2b: np.int16(y / max|y| * 32767)
@@ -913,11 +954,11 @@ int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
   }
   BPM_LAUNCH_OK();
   {
-    const size_t smem = sizeof(double) * (ENV_THREADS + env_window);
+    const size_t smem = env_smem_bytes(env_window);
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(k_envelope, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     BPM_KERNEL(k_envelope);
-    k_envelope<<<dim3(cdiv(sh.max_m, ENV_THREADS), n_items), ENV_THREADS, smem, st>>>(filtered, items, env_window,
+    k_envelope<<<dim3(cdiv(sh.max_m, ENV_TILE), n_items), ENV_THREADS, smem, st>>>(filtered, items, env_window,
                                                                                    envelope);
   }
   BPM_LAUNCH_OK();

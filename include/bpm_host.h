@@ -1,0 +1,125 @@
+/*
+ * bpm_host.h -- C ABI of libbpm_host.so: compiled HOST code for the sequential stage that
+ * consumes the B200 front end's outputs.
+ *
+ * The reference runs its S1/S2 classifier as a Python loop over the raw peaks with
+ * loop-carried state (bpm_analysis.py:113-329 and the helpers at :1120-1255), twice per
+ * file (:1635, :1740); once the front end is on the GPU it is what is left of the run time.
+ * It does not data-parallelise (every decision feeds the next through the long-term BPM
+ * belief, the candidate list and the rejection counter), so it is compiled host code, not
+ * a kernel; batches are classified one recording per host thread by the caller.
+ *
+ * All pointers are HOST pointers.  The library has no global state and is re-entrant.
+ * Return value: 0, or BPM_HOST_ERR_*.  It never throws and never exits.
+ */
+#ifndef BPM_HOST_H_
+#define BPM_HOST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPM_HOST_ABI_VERSION 1
+
+enum { BPM_HOST_OK = 0, BPM_HOST_ERR_ARG = -1, BPM_HOST_ERR_NOMEM = -2 };
+
+/* PeakType of the reference (bpm_analysis.py:26-36) as far as the classifier assigns it */
+enum {
+  BPM_PEAK_UNSET = 0,
+  BPM_PEAK_S1_PAIRED = 1,          /* "S1 (Paired)" */
+  BPM_PEAK_S2_PAIRED = 2,          /* "S2 (Paired)" */
+  BPM_PEAK_LONE_S1 = 3,            /* "Lone S1" */
+  BPM_PEAK_LONE_S1_CASCADE = 4,    /* "Lone S1 (Corrected by Cascade Reset)" */
+  BPM_PEAK_LONE_S1_LAST = 5,       /* "Lone S1 (Last Peak)" */
+  BPM_PEAK_NOISE = 6               /* "Noise" */
+};
+
+/* The parameters classify_peaks reads from DEFAULT_PARAMS (config.py), with the reference's
+ * .get() defaults applied by the caller, plus the constructor arguments of PeakClassifier
+ * (bpm_analysis.py:71-83).  Integers of the Python dict are passed as doubles: every use is
+ * a float expression.  */
+typedef struct {
+  double pairing_confidence_threshold;      /* :267 */
+  double contractility_bpm_low;             /* :237, :1136, :1171 */
+  double contractility_bpm_high;
+  double s1_s2_interval_cap_sec;            /* :246 */
+  double s1_s2_interval_rr_fraction;
+  double interval_penalty_start_factor;     /* :250-252 */
+  double interval_penalty_full_factor;
+  double interval_max_penalty;
+  double kickstart_check_threshold;         /* :143 */
+  double stability_confidence_floor;        /* :1155-1156 */
+  double stability_confidence_ceiling;
+  double s2_s1_ratio_low_bpm;               /* :1172-1174 */
+  double s2_s1_ratio_high_bpm;
+  double penalty_amount_min;                /* :1179-1180 */
+  double penalty_amount_max;
+  double s1_s2_boost_ratio;                 /* :1188 */
+  double boost_amount_min;                  /* :1190-1191 */
+  double boost_amount_max;
+  double lone_s1_confidence_threshold;      /* :310 */
+  double lone_s1_forward_check_pct;         /* :319 */
+  double lone_s1_rhythm_weight;             /* :326, :1236 */
+  double lone_s1_amplitude_weight;
+  double cascade_reset_trigger_count;       /* :293 */
+  double min_bpm;                           /* :1258 */
+  double max_bpm;
+  double start_bpm;                         /* state['long_term_bpm'] at entry (:103) */
+  double peak_bpm_time_sec;                 /* used when has_recovery_window != 0 (:1168-1169) */
+  double recovery_end_time_sec;
+  int32_t has_recovery_window;
+  int32_t enable_interval_penalty;          /* :249 */
+  int32_t stability_history_window;         /* :135, :180 */
+  int32_t reserved;
+} BpmClassifierParams;
+
+/* things the reference reports through logging.info while classifying */
+enum { BPM_EVENT_KICKSTART = 1, BPM_EVENT_CASCADE_RESET = 2 };
+typedef struct {
+  int32_t kind;
+  int32_t a;       /* KICKSTART: matches            CASCADE_RESET: position of the forced peak */
+  int32_t b;       /* KICKSTART: recent lone S1s     CASCADE_RESET: 0 */
+  int32_t pad;
+} BpmClassifierEvent;
+
+/* Result of one classification; owned by the library, released with bpm_classification_free. */
+typedef struct {
+  int64_t n_peaks;                 /* raw peaks classified */
+  int64_t n_beats;                 /* len(candidate_beats) */
+  int64_t n_history;               /* len(long_term_bpm_history) */
+  int64_t n_events;
+  int64_t text_bytes;
+  const int64_t* beat_positions;   /* [n_beats] positions INTO raw_peaks, ascending */
+  const int32_t* peak_types;       /* [n_peaks] BPM_PEAK_* */
+  const int64_t* text_offsets;     /* [n_peaks + 1] byte offsets into text */
+  const char* text;                /* UTF-8: beat_debug_info[raw_peaks[i]] = text[off[i] .. off[i+1]) */
+  const double* history_times;     /* [n_history] candidate_beats[-1] / sample_rate */
+  const double* history_bpm;       /* [n_history] long_term_bpm after each decision */
+  const BpmClassifierEvent* events;
+  double final_long_term_bpm;
+  int64_t final_consecutive_rr_rejections;
+} BpmClassification;
+
+int bpm_host_abi_version(void);
+
+/* PeakClassifier.classify_peaks (bpm_analysis.py:113-131) for n_peaks >= 2 raw peaks.
+ *   envelope, noise_floor: float64[m] (audio_envelope, dynamic_noise_floor.values)
+ *   raw_peaks: int64[n_peaks], strictly ascending, each in [0, m)  (state['all_peaks'])
+ *   dev_times, dev_values: float64[n_dev], the smoothed deviation series (index seconds ascending, values)
+ *   sample_rate: the envelope rate (a Python int in the reference; every use is a true division)
+ * Decisions, candidate beats, the long-term BPM trace and every per-peak debug string are those
+ * of the reference, bit for bit and byte for byte.  */
+int bpm_classify_peaks(const double* envelope, const double* noise_floor, int64_t m,
+                       const int64_t* raw_peaks, int64_t n_peaks,
+                       const double* dev_times, const double* dev_values, int64_t n_dev,
+                       double sample_rate, const BpmClassifierParams* params,
+                       BpmClassification** out);
+void bpm_classification_free(BpmClassification* c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPM_HOST_H_ */
