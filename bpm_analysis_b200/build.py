@@ -1,9 +1,10 @@
-"""Builds libbpm_b200.so (hand-written CUDA for sm_100a) in-tree with nvcc.
+"""Builds libbpm_b200.so (hand-written CUDA for sm_100a, nvcc) and libbpm_host.so (the
+compiled sequential classifier, g++) in-tree.
 
     python -m bpm_analysis_b200.build [--force]
 
-The shared library is git-ignored but travels with the source tree; the Python
-package loads it with ctypes and refuses to work without it.
+The shared libraries are git-ignored but travel with the source tree; the Python
+package loads them with ctypes and refuses to work without them.
 """
 from __future__ import annotations
 
@@ -51,5 +52,29 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+HOST_LIB_PATH = os.path.join(HERE, "libbpm_host.so")
+HOST_SOURCES = ["classifier.cpp"]
+# -ffp-contract=off: the classifier's decisions must round exactly like CPython's float arithmetic
+GXX_FLAGS = ["-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wextra"]
+
+
+def build_host(force: bool = False) -> str:
+    """libbpm_host.so: include/bpm_host.h (host-only code, no CUDA dependency)."""
+    srcs = [os.path.join(CSRC, s) for s in HOST_SOURCES]
+    newest = max([os.path.getmtime(f) for f in srcs] +
+                 [os.path.getmtime(os.path.join(os.path.dirname(HERE), "include", "bpm_host.h"))])
+    if not force and os.path.exists(HOST_LIB_PATH) and os.path.getmtime(HOST_LIB_PATH) >= newest:
+        return HOST_LIB_PATH
+    cmd = [os.environ.get("CXX", "g++"), *GXX_FLAGS, "-o", HOST_LIB_PATH, *srcs]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError(f"g++ failed with exit code {res.returncode}")
+    if res.stderr:
+        sys.stderr.write(res.stderr)
+    return HOST_LIB_PATH
+
+
 if __name__ == "__main__":
+    print(build_host(force="--force" in sys.argv))
     print(build_native(force="--force" in sys.argv, verbose=True))

@@ -37,6 +37,38 @@ HOT_PATH_DEFAULTS: Dict[str, object] = {
     "trough_noise_multiplier": 3.0,
 }
 
+# keys the sequential classifier reads (classifier.py -> libbpm_host.so), at the values of the
+# reference's DEFAULT_PARAMS (config.py); keys absent there fall back to the .get() defaults in
+# bpm_analysis.py (cascade_reset_trigger_count 3, enable_interval_penalty True)
+CLASSIFIER_DEFAULTS: Dict[str, object] = {
+    "pairing_confidence_threshold": 0.5,
+    "contractility_bpm_low": 120.0,
+    "contractility_bpm_high": 140.0,
+    "s1_s2_interval_cap_sec": 0.4,
+    "s1_s2_interval_rr_fraction": 0.7,
+    "interval_penalty_start_factor": 1.0,
+    "interval_penalty_full_factor": 1.4,
+    "interval_max_penalty": 0.75,
+    "kickstart_check_threshold": 0.3,
+    "kickstart_override_ratio": 0.6,
+    "stability_history_window": 20,
+    "stability_confidence_floor": 0.6,
+    "stability_confidence_ceiling": 1.25,
+    "s2_s1_ratio_low_bpm": 1.5,
+    "s2_s1_ratio_high_bpm": 1.1,
+    "penalty_amount_min": 0.1,
+    "penalty_amount_max": 0.3,
+    "s1_s2_boost_ratio": 1.2,
+    "boost_amount_min": 0.1,
+    "boost_amount_max": 0.35,
+    "lone_s1_confidence_threshold": 0.5,
+    "lone_s1_forward_check_pct": 0.5,
+    "lone_s1_rhythm_weight": 0.65,
+    "lone_s1_amplitude_weight": 0.35,
+    "min_bpm": 40,
+    "max_bpm": 240,
+}
+
 # constants the reference hard-codes on the hot path (file:line in bpm_analysis.py)
 LOWCUT_HZ = 20.0            # :1018
 HIGHCUT_HZ = 150.0          # :1018
@@ -55,8 +87,8 @@ HR_MIN_CHANGE_BPM = 15      # :1486
 
 
 def default_params() -> Dict[str, object]:
-    """A fresh copy of the hot-path defaults."""
-    return dict(HOT_PATH_DEFAULTS)
+    """A fresh copy of the hot-path defaults (front end + classifier keys)."""
+    return {**HOT_PATH_DEFAULTS, **CLASSIFIER_DEFAULTS}
 
 
 def band_edges(params: Dict) -> tuple:

@@ -1,0 +1,77 @@
+"""CPU ORACLE -- TEST INFRASTRUCTURE ONLY.  Generates ``tests/golden/classifier_cases.json.gz``.
+
+Run in the authoring container (needs ``/root/reference``):
+
+    python -m oracle.make_golden_classifier
+
+For each seeded case of ``tests/_classifier_cases.py`` the UNMODIFIED reference
+``PeakClassifier.classify_peaks`` (bpm_analysis.py:113-131) is run on a classifier object whose
+state was filled in directly (the constructor's numeric work is not what is being recorded), and
+its candidate beats, per-peak debug strings, long-term BPM trace (hex floats) and log lines are
+stored.  ``tests/test_classifier_cpu.py`` requires libbpm_host.so to reproduce them exactly.
+"""
+from __future__ import annotations
+
+import gzip
+import json
+import logging
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+from _classifier_cases import make_case, pack_result, state_of   # noqa: E402
+from oracle.load_reference import load_reference               # noqa: E402
+
+GOLDEN_SEEDS = list(range(24))
+OUT = os.path.join(REPO, "tests", "golden", "classifier_cases.json.gz")
+
+
+class _Capture(logging.Handler):
+    def __init__(self):
+        super().__init__(level=logging.INFO)
+        self.lines = []
+
+    def emit(self, record):
+        self.lines.append(record.getMessage())
+
+
+def reference_classifier(ref, case):
+    obj = object.__new__(ref.PeakClassifier)
+    obj.audio_envelope, obj.sample_rate, obj.params = case["env"], case["rate"], case["params"]
+    obj.peak_bpm_time_sec, obj.recovery_end_time_sec = case["peak_time"], case["recovery_time"]
+    obj.state = state_of(case)
+    return obj
+
+
+def run_reference(ref, case):
+    cap = _Capture()
+    root = logging.getLogger()
+    level = root.level
+    root.addHandler(cap)
+    root.setLevel(logging.INFO)
+    try:
+        obj = reference_classifier(ref, case)
+        packed = pack_result(obj.classify_peaks())
+    finally:
+        root.removeHandler(cap)
+        root.setLevel(level)
+    packed["log"] = cap.lines
+    packed["final_long_term_bpm"] = float(obj.state["long_term_bpm"]).hex()
+    packed["final_consecutive_rr_rejections"] = int(obj.state["consecutive_rr_rejections"])
+    return packed
+
+
+def main():
+    ref = load_reference()
+    out = {str(seed): run_reference(ref, make_case(seed)) for seed in GOLDEN_SEEDS}
+    with gzip.GzipFile(OUT, "wb", mtime=0) as fh:
+        fh.write(json.dumps(out, ensure_ascii=False, sort_keys=True).encode("utf-8"))
+    n = sum(len(v["keys"]) for v in out.values())
+    print(f"{OUT}: {len(out)} cases, {n} classified peaks, {os.path.getsize(OUT)} bytes")
+
+
+if __name__ == "__main__":
+    main()

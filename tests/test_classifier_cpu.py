@@ -1,0 +1,147 @@
+"""The compiled sequential classifier (libbpm_host.so, include/bpm_host.h) against the reference's
+``PeakClassifier.classify_peaks`` (bpm_analysis.py:113-329, :1120-1258): candidate beats, every
+per-peak debug string, the long-term BPM trace and the log lines must be IDENTICAL (bit for bit,
+byte for byte).  Golden outputs of the unmodified reference: tests/golden/classifier_cases.json.gz
+(oracle/make_golden_classifier.py); where the reference tree is present the comparison is also
+made live on many more seeds and on full recordings through the reference's own constructor.
+"""
+import collections
+import ctypes
+import gzip
+import json
+import logging
+import os
+
+import numpy as np
+import pytest
+
+from _classifier_cases import ClassifierStandIn, make_case, pack_result
+from bpm_analysis_b200 import classifier
+from conftest import GOLDEN_DIR, REPO
+from oracle.load_reference import load_reference, reference_available
+
+needs_reference = pytest.mark.skipif(not reference_available(), reason="needs /root/reference")
+
+
+def run_ours(case, caplog):
+    obj = ClassifierStandIn(case)
+    caplog.clear()
+    with caplog.at_level(logging.INFO):
+        packed = pack_result(classifier.classify_peaks(obj))
+    packed["log"] = [r.getMessage() for r in caplog.records]
+    packed["final_long_term_bpm"] = float(obj.state["long_term_bpm"]).hex()
+    packed["final_consecutive_rr_rejections"] = int(obj.state["consecutive_rr_rejections"])
+    return packed, obj
+
+
+def assert_same(got, want, label):
+    assert got["final_peaks"] == want["final_peaks"], label
+    assert got["keys"] == want["keys"], label
+    for k, a, b in zip(want["keys"], got["texts"], want["texts"]):
+        assert a == b, f"{label}: debug string of peak {k}"
+    assert got["lt_times"] == want["lt_times"], label
+    assert got["lt_values"] == want["lt_values"], label
+    assert got["log"] == want["log"], label
+    assert got["final_long_term_bpm"] == want["final_long_term_bpm"], label
+    assert got["final_consecutive_rr_rejections"] == want["final_consecutive_rr_rejections"], label
+
+
+def test_host_library_exports_header_symbols():
+    import re
+    lib = ctypes.CDLL(classifier.HOST_LIB_PATH)
+    header = open(os.path.join(REPO, "include", "bpm_host.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|void)\s+(bpm_\w+)\s*\(", header, flags=re.M))
+    assert declared == set(classifier.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert classifier.load_host_library().bpm_host_abi_version() == classifier.HOST_ABI_VERSION
+    assert ctypes.sizeof(classifier.ClassifierParams) == 28 * 8 + 4 * 4
+
+
+def test_golden_cases_reproduced_exactly(caplog):
+    with gzip.open(os.path.join(GOLDEN_DIR, "classifier_cases.json.gz"), "rb") as fh:
+        golden = json.loads(fh.read().decode("utf-8"))
+    labels = collections.Counter()
+    events = 0
+    for seed, want in sorted(golden.items(), key=lambda kv: int(kv[0])):
+        got, _ = run_ours(make_case(int(seed)), caplog)
+        assert_same(got, want, f"seed {seed}")
+        labels.update(t.split("§")[0] for t in want["texts"])
+        events += len(want["log"])
+    # the fixture exercises every label the classifier can assign and both log lines
+    assert set(labels) == set(classifier.PEAK_TYPE_LABELS.values()), labels
+    assert min(labels.values()) >= 5 and labels["Noise"] >= 100 and labels["Lone S1 (Corrected by Cascade Reset)"] >= 50, labels
+    assert events > 10
+
+
+@needs_reference
+def test_live_reference_many_seeds(caplog):
+    from oracle.make_golden_classifier import run_reference
+    ref = load_reference()
+    for seed in range(100, 260):
+        case = make_case(seed)
+        want = run_reference(ref, case)
+        got, _ = run_ours(case, caplog)
+        assert_same(got, want, f"seed {seed}")
+
+
+@needs_reference
+def test_full_recording_through_reference_constructor(caplog, tmp_path):
+    """Recordings through the reference's own front end and constructor (CPU), then both loops."""
+    from scipy.io import wavfile
+    from bpm_analysis_b200 import synth
+    from oracle.load_reference import reference_params
+    ref = load_reference()
+    params = reference_params()
+    params["save_filtered_wav"] = False
+    for seed, (rate, sigma, bpm) in enumerate([(8000, 0.02, lambda t: 70.0), (8000, 0.2, lambda t: 140.0 + 50 * np.sin(t / 15))]):
+        pcm, sr, _ = synth.pcg_recording(120.0, rate, bpm, 40 + seed, noise_sigma=sigma)
+        path = str(tmp_path / f"r{seed}.wav")
+        wavfile.write(path, sr, pcm)
+        env, nsr = ref.preprocess_audio(path, params, str(tmp_path))
+        floor, troughs = ref._calculate_dynamic_noise_floor(env, nsr, params)
+        for thr, hint, window in ((0.75, None, (None, None)), (0.5, 95.0, (30.0, 80.0))):
+            p = dict(params, pairing_confidence_threshold=thr)
+            a = ref.PeakClassifier(env, nsr, p, hint, floor, troughs, *window)
+            b = ref.PeakClassifier(env, nsr, p, hint, floor, troughs, *window)
+            want = pack_result(a.classify_peaks())
+            got = pack_result(classifier.classify_peaks(b))
+            for k in ("final_peaks", "keys", "texts", "lt_times", "lt_values"):
+                assert got[k] == want[k], (seed, thr, k)
+            assert a.state["long_term_bpm"] == b.state["long_term_bpm"]
+            assert [int(x) for x in a.state["candidate_beats"]] == [int(x) for x in b.state["candidate_beats"]]
+
+
+def test_fewer_than_two_peaks_and_second_call(caplog):
+    case = make_case(3)
+    one = dict(case, peaks=case["peaks"][:1], dev_index=case["dev_index"][:0], dev_values=case["dev_values"][:0])
+    obj = ClassifierStandIn(one)
+    final, allp, data = classifier.classify_peaks(obj)                  # bpm_analysis.py:115-116
+    assert final is obj.state["all_peaks"] and allp is final and data == {"beat_debug_info": {}}
+    obj = ClassifierStandIn(case)
+    first = pack_result(classifier.classify_peaks(obj))
+    again = pack_result(classifier.classify_peaks(obj))                 # the loop is over: only finalisation repeats
+    assert first == again
+
+
+def test_argument_errors_are_reported():
+    case = make_case(2)
+    packed = classifier.pack_params(case["params"], 80.0, None, None)
+    bad = case["peaks"].copy()
+    bad[3] = bad[2]                                                     # not strictly ascending
+    with pytest.raises(ValueError):
+        classifier.classify_arrays(case["env"], case["floor"], bad, case["dev_index"], case["dev_values"], 300, packed)
+    with pytest.raises(ValueError):
+        classifier.classify_arrays(case["env"], case["floor"][:-1], case["peaks"], case["dev_index"],
+                                   case["dev_values"], 300, packed)
+    with pytest.raises(KeyError):                                       # required key, like the reference's params[...]
+        classifier.pack_params({k: v for k, v in case["params"].items() if k != "min_bpm"}, 80.0, None, None)
+
+
+def test_install_rebinds_classify_peaks():
+    class Mod:
+        class PeakClassifier:
+            def classify_peaks(self):
+                raise AssertionError("not replaced")
+    classifier.install(Mod)
+    assert Mod.PeakClassifier.classify_peaks is classifier.classify_peaks
