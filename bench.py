@@ -285,6 +285,12 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    l2_fetch = os.environ.get("BPM_L2_FETCH_GRANULARITY")     # experiment knob (bytes: 32 / 64 / 128), off by default
+    if l2_fetch:
+        import ctypes
+        torch.cuda.init()
+        rc = ctypes.CDLL("libcudart.so.12").cudaDeviceSetLimit(0x05, ctypes.c_size_t(int(l2_fetch)))
+        sys.stderr.write(f"cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, {l2_fetch}) -> {rc}\n")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         from bpm_analysis_b200.dist import bind_to_gpu_numa
@@ -484,7 +490,8 @@ def run_b200(args):
                 "config": {"workload": workload_name(args), "filter_mode": args.filter_mode,
                            "raw_samples": len(pcm), "envelope_samples": M, "beats": len(beat_idx),
                            "l2": "inputs larger than L2 (PCM %.1f MB per step)" % (len(pcm) * 2 / 1e6),
-                           "parallelism": f"{world} x independent recordings, no collective"},
+                           "parallelism": f"{world} x independent recordings, no collective",
+                           **({"l2_fetch_granularity": int(l2_fetch)} if l2_fetch else {})},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h),

@@ -155,9 +155,7 @@ def classify_arrays(envelope: np.ndarray, noise_floor: np.ndarray, raw_peaks: np
     try:
         r = out.contents
         n = int(r.n_peaks)
-        offsets = _as(r.text_offsets, n + 1, np.int64)
-        blob = C.string_at(r.text, int(r.text_bytes))
-        texts = [blob[offsets[i]:offsets[i + 1]].decode("utf-8") for i in range(n)]
+        texts = C.string_at(r.text, int(r.text_bytes)).decode("utf-8").split("\x00")[:n]   # NUL-terminated entries
         return {
             "beat_positions": _as(r.beat_positions, int(r.n_beats), np.int64),
             "peak_types": _as(r.peak_types, n, np.int32),

@@ -381,11 +381,12 @@ int bpm_classify_peaks(const double* envelope, const double* noise_floor, int64_
     o->events = std::move(c.events);
     o->offsets.resize(static_cast<size_t>(n_peaks) + 1);
     size_t total = 0;
-    for (int64_t i = 0; i < n_peaks; ++i) total += c.text[i].size();
+    for (int64_t i = 0; i < n_peaks; ++i) total += c.text[i].size() + 1;
     o->text.reserve(total);
-    for (int64_t i = 0; i < n_peaks; ++i) {
+    for (int64_t i = 0; i < n_peaks; ++i) {                            // NUL-terminated entries, back to back
       o->offsets[i] = static_cast<int64_t>(o->text.size());
       o->text += c.text[i];
+      o->text += '\0';
     }
     o->offsets[n_peaks] = static_cast<int64_t>(o->text.size());
     BpmClassification& r = o->pub;

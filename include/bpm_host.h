@@ -95,7 +95,8 @@ typedef struct {
   const int64_t* beat_positions;   /* [n_beats] positions INTO raw_peaks, ascending */
   const int32_t* peak_types;       /* [n_peaks] BPM_PEAK_* */
   const int64_t* text_offsets;     /* [n_peaks + 1] byte offsets into text */
-  const char* text;                /* UTF-8: beat_debug_info[raw_peaks[i]] = text[off[i] .. off[i+1]) */
+  const char* text;                /* UTF-8, one NUL-terminated entry per raw peak, back to back:
+                                      beat_debug_info[raw_peaks[i]] = text + off[i]  (off[i+1] - off[i] - 1 bytes) */
   const double* history_times;     /* [n_history] candidate_beats[-1] / sample_rate */
   const double* history_bpm;       /* [n_history] long_term_bpm after each decision */
   const BpmClassifierEvent* events;
