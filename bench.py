@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--no-zero-copy", action="store_true", help="e2e: copy the whole recording to the device first")
     ap.add_argument("--e2e-depth", type=int, default=3, help="e2e: recordings in flight (1 = strictly serial steps)")
+    ap.add_argument("--e2e-ingest", default="ce", choices=["ce", "sm"],
+                    help="e2e: kept frames cross PCIe by a strided copy-engine copy (ce) or by a kernel reading mapped "
+                         "pinned memory (sm)")
     ap.add_argument("--dump-kernels", default=None, help="write the per-kernel table to this JSON file")
     ap.add_argument("--workload", default="recordings", choices=["recordings", "stream", "batch", "holter"],
                     help="recordings: one C2 recording per GPU (weak scaling, the headline). stream: ONE C2 "
@@ -375,7 +378,7 @@ def run_b200(args):
         depth = max(1, args.e2e_depth)
         pipe = StageAPipeline(len(pcm), sr, params, depth=depth,
                               beat_runner_args=(len(beat_idx), rate, params, hr_extrema_distance(beat_idx, rate)),
-                              use_graph=not args.no_graph)
+                              use_graph=not args.no_graph, ingest=args.e2e_ingest)
 
         def e2e_run(n_steps):
             res = None
@@ -399,7 +402,8 @@ def run_b200(args):
         assert nt == int(A.out["trough_count"][0]) and npk == int(A.out["peak_count"][0])
         assert torch.equal(res["peaks"][:npk], A.out["peaks"][:npk].cpu())
         assert torch.equal(res["floor"], A.out["floor"].cpu())
-        h2d = M * 32 + beats_pin.numel() * 8          # one 32-byte sector per kept frame crosses PCIe
+        # sm: one 32-byte sector per kept frame crosses PCIe; ce: the 2-D copy moves the kept frames themselves
+        h2d = M * (32 if args.e2e_ingest == "sm" else pcm_pin.element_size()) + beats_pin.numel() * 8
         d2h = pipe.d2h_bytes()
         del pipe
     else:
@@ -495,8 +499,11 @@ def run_b200(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h),
-                        "ingest": (f"zero-copy: bpm_gather_frames reads the kept frames from pinned host memory (h2d bytes "
-                                   f"= 32-byte sector per kept frame); {args.e2e_depth}-deep pipeline ingest | compute | "
+                        "ingest": ((f"bpm_copy_frames: the kept frames x[::ds] leave pinned host memory as one strided 2-D "
+                                    f"copy on the copy engine (h2d bytes = the kept frames); " if args.e2e_ingest == "ce" else
+                                    f"zero-copy: bpm_gather_frames reads the kept frames from pinned host memory (h2d bytes "
+                                    f"= 32-byte sector per kept frame); ") +
+                                   f"{args.e2e_depth}-deep pipeline ingest | compute | "
                                    "read-back over three streams") if zero_copy else
                                   "cudaMemcpyAsync of the whole recording from pinned host memory, serial steps"},
                 "gpu_launches": launches if graphed is None else launches_per_step * args.steps,

@@ -58,6 +58,7 @@ _SIGNATURES = {
     "bpm_frontend": (_I, [_P, _I, _I, _P, _P, _I, _L, _P, _L, _I, _P, _P, _P, _P, _Z, _P]),
     "bpm_debug_wav": (_I, [_P, _P, _P, _P, _I, _P, _P]),
     "bpm_gather_frames": (_I, [_P, _I, _I, _P, _P, _I, _L, _P, _P]),
+    "bpm_copy_frames": (_I, [_P, _I, _I, _P, _I, _L, _P, _P]),
     "bpm_quantile_workspace_bytes": (_Z, [_I]),
     "bpm_quantile": (_I, [_P, _P, _P, _I, _D, _P, _P, _Z, _P]),
     "bpm_find_peaks_workspace_bytes": (_Z, [_L, _I]),

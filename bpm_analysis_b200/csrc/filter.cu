@@ -745,28 +745,28 @@ __global__ void __launch_bounds__(SCAN_THREADS, DIR == 0 ? 3 : 2) k_scan(ScanPar
 // ------------------------------------------------------------------ envelope (K2)
 // pandas rolling(window=w, min_periods=1, center=True).mean() of |y|
 // (bpm_analysis.py:1052-1054): window [i+1+off-w, i+off] clipped, off=(w-1)//2.
-constexpr int ENV_THREADS = 128;
-constexpr int ENV_R = 8;             // consecutive outputs per thread (they share the staged window)
+constexpr int ENV_THREADS = 256;
+constexpr int ENV_R = 4;             // consecutive outputs per thread (they share the staged window)
 constexpr int ENV_TILE = ENV_THREADS * ENV_R;
-constexpr int ENV_MAX_W = 16384;     // rate // 10 of an undecimated 96 kHz recording still fits (157 KB of smem)
+constexpr int ENV_MAX_W = 16384;     // rate // 10 of an undecimated 96 kHz recording still fits (174 KB of smem)
 
-// staged element e lives at e + e / ENV_R: the fill (consecutive e) and the per-thread reads
-// (element ENV_R t + k, i.e. ENV_R + 1 doubles between neighbouring lanes) are bank-conflict free
-__device__ __forceinline__ int env_slot(int e) { return e + e / ENV_R; }
-static size_t env_smem_bytes(int w) {
-  return sizeof(double) * (static_cast<size_t>(ENV_TILE + w - 1) * (ENV_R + 1) / ENV_R + 2);
-}
+// staged element e lives at e + e/4: the fill (consecutive e) and the per-thread reads (element
+// 4 t + k, i.e. 5 doubles between neighbouring lanes) are both bank-conflict free
+__device__ __forceinline__ int env_slot(int e) { return e + (e >> 2); }
+static size_t env_smem_bytes(int w) { return sizeof(double) * (static_cast<size_t>(ENV_TILE + w - 1) * 5 / 4 + 2); }
 
 // A thread forms ENV_R consecutive means from ONE pass over the w + ENV_R - 1 staged values they
-// share (5 shared-memory loads per output instead of 33 at the default window: the per-output
-// version was bound by shared-memory bandwidth, not HBM).  Every sum still adds its window in
+// share (9 shared-memory loads per output instead of 33 at the default window: the per-output
+// version was bound by shared-memory bandwidth, not HBM; eight outputs per thread with the means
+// staged back through shared memory for coalesced stores measured SLOWER: 178 vs 152 us at C4).
+// Every sum still adds its window in
 // ascending index order from 0.0, and positions outside the recording are staged as +0.0
 // (x + 0.0 == x for the non-negative partial sums), so the results are bit-identical to the
 // one-output-per-thread evaluation.
 __global__ void __launch_bounds__(ENV_THREADS) k_envelope(const double* __restrict__ y,
                                                           const BpmItem* __restrict__ items, int w,
                                                           double* __restrict__ env) {
-  extern __shared__ double s_abs[];          // env_slot(ENV_TILE + w - 2) + 1
+  extern __shared__ double s_abs[];          // env_slot(ENV_TILE + w - 1) + 1
   const BpmItem it = items[blockIdx.y];
   const int64_t i0 = static_cast<int64_t>(blockIdx.x) * ENV_TILE;
   if (i0 >= it.m) return;
@@ -780,61 +780,40 @@ __global__ void __launch_bounds__(ENV_THREADS) k_envelope(const double* __restri
   }
   __syncthreads();
   const int64_t ib = i0 + static_cast<int64_t>(threadIdx.x) * ENV_R;
-  // output r sums the thread's elements k = r .. r + w - 1; element k is staged at
-  // (ENV_R + 1) * threadIdx.x + k + k / ENV_R
-  double* e0 = s_abs + (ENV_R + 1) * threadIdx.x;
-  double s[ENV_R];
-#pragma unroll
-  for (int r = 0; r < ENV_R; ++r) s[r] = 0.0;
-  // threads wholly past the end of the recording skip the sums (they still join the barriers)
-  const int wk = (ib < it.m) ? w : 0;
+  if (ib >= it.m) return;
+  // output r (r = 0..3) sums the thread's elements k = r .. r + w - 1; element k is staged at
+  // 5 * threadIdx.x + k + k / 4
+  const double* __restrict__ e0 = s_abs + 5 * threadIdx.x;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   int k = 0;
 #pragma unroll
-  for (; k < ENV_R - 1; ++k) {               // head: outputs r <= k have started
+  for (; k < 3; ++k) {
     const double v = e0[k];
-#pragma unroll
-    for (int r = 0; r < ENV_R; ++r)
-      if (k >= r && k - r < wk) s[r] = __dadd_rn(s[r], v);
+    if (k < w) s0 = __dadd_rn(s0, v);
+    if (k >= 1 && k <= w) s1 = __dadd_rn(s1, v);
+    if (k >= 2 && k <= w + 1) s2 = __dadd_rn(s2, v);
   }
-  if (ENV_R - 1 < wk) {                       // middle: every output's window holds element k
-    {
-      const double v = e0[ENV_R - 1];
-#pragma unroll
-      for (int r = 0; r < ENV_R; ++r) s[r] = __dadd_rn(s[r], v);
-    }
-    k = ENV_R;
-    const double* __restrict__ g = e0 + (ENV_R + 1);
-    for (; k + ENV_R <= wk; k += ENV_R, g += ENV_R + 1) {
-#pragma unroll
-      for (int j = 0; j < ENV_R; ++j) {
-        const double v = g[j];
-#pragma unroll
-        for (int r = 0; r < ENV_R; ++r) s[r] = __dadd_rn(s[r], v);
-      }
-    }
-    for (; k < wk; ++k) {
-      const double v = e0[k + k / ENV_R];
-#pragma unroll
-      for (int r = 0; r < ENV_R; ++r) s[r] = __dadd_rn(s[r], v);
-    }
+#pragma unroll 4
+  for (; k < w; ++k) {
+    const double v = e0[k + (k >> 2)];
+    s0 = __dadd_rn(s0, v); s1 = __dadd_rn(s1, v); s2 = __dadd_rn(s2, v); s3 = __dadd_rn(s3, v);
   }
-  for (; k < wk + ENV_R - 1; ++k) {          // tail: outputs r < k - w + 1 have finished
-    const double v = e0[k + k / ENV_R];
-#pragma unroll
-    for (int r = 0; r < ENV_R; ++r)
-      if (k >= r && k - r < wk) s[r] = __dadd_rn(s[r], v);
+  for (; k < w + 3; ++k) {
+    const double v = e0[k + (k >> 2)];
+    if (k < w) s0 = __dadd_rn(s0, v);
+    if (k >= 1 && k <= w) s1 = __dadd_rn(s1, v);
+    if (k >= 2 && k <= w + 1) s2 = __dadd_rn(s2, v);
+    if (k >= 3) s3 = __dadd_rn(s3, v);
   }
-  // the means go back through shared memory so that the stores to HBM are coalesced
-  __syncthreads();
+  const double sums[ENV_R] = {s0, s1, s2, s3};
 #pragma unroll
   for (int r = 0; r < ENV_R; ++r) {
     const int64_t i = ib + r;
-    const int64_t a = max(static_cast<int64_t>(0), i - left), b = min(it.m - 1, i + off);
-    if (i < it.m) e0[r] = __ddiv_rn(s[r], static_cast<double>(b - a + 1));
+    if (i < it.m) {
+      const int64_t a = max(static_cast<int64_t>(0), i - left), b = min(it.m - 1, i + off);
+      env[it.m_off + i] = __ddiv_rn(sums[r], static_cast<double>(b - a + 1));
+    }
   }
-  __syncthreads();
-  for (int t = threadIdx.x; t < ENV_TILE; t += ENV_THREADS)
-    if (i0 + t < it.m) env[it.m_off + i0 + t] = s_abs[env_slot(t)];
 }
 
 // K2b: np.int16(y / max|y| * 32767)

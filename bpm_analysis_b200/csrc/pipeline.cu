@@ -345,6 +345,30 @@ int bpm_gather_frames(const void* pcm, int pcm_dtype, int channels, const BpmIte
                            static_cast<cudaStream_t>(stream));
 }
 
+int bpm_copy_frames(const void* pcm, int pcm_dtype, int channels, const BpmItem* items_host, int n_items,
+                    int64_t stride, void* frames_out, void* stream) {
+  static const size_t sample_bytes[5] = {2, 4, 1, 4, 8};               // BPM_PCM_I16, I32, U8, F32, F64
+  if (!pcm || !items_host || !frames_out || n_items <= 0 || channels < 1 || stride < 1 || pcm_dtype < 0 ||
+      pcm_dtype > BPM_PCM_F64)
+    return BPM_ERR_ARG;
+  const size_t fb = sample_bytes[pcm_dtype] * static_cast<size_t>(channels);
+  for (int i = 0; i < n_items; ++i) {
+    const BpmItem& it = items_host[i];
+    if (it.n_in <= 0 || it.m != (it.n_in + stride - 1) / stride) return BPM_ERR_ARG;
+  }
+  for (int i = 0; i < n_items; ++i) {
+    const BpmItem& it = items_host[i];
+    const char* src = static_cast<const char*>(pcm) + static_cast<size_t>(it.in_off) * fb;
+    char* dst = static_cast<char*>(frames_out) + static_cast<size_t>(it.m_off) * fb;
+    if (cudaMemcpy2DAsync(dst, fb, src, static_cast<size_t>(stride) * fb, fb, static_cast<size_t>(it.m),
+                          cudaMemcpyDefault, static_cast<cudaStream_t>(stream)) != cudaSuccess) {
+      cudaGetLastError();
+      return BPM_ERR_CUDA;
+    }
+  }
+  return BPM_OK;
+}
+
 int bpm_debug_wav(const double* filtered, const double* absmax, const BpmItem* items, const BpmItem* items_host,
                   int n_items, int16_t* out, void* stream) {
   return debug_wav_run(filtered, absmax, items, items_host, n_items, out, static_cast<cudaStream_t>(stream));

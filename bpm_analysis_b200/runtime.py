@@ -162,10 +162,13 @@ class StageARunner:
 
     def __init__(self, n_in: Sequence[int], sample_rate: int, params: Dict, pcm_dtype=np.int16,
                  channels: int = 1, want_debug: bool = False, pregathered: bool = False):
-        """``pregathered``: the decimation x[::ds] (K0) runs as its own small kernel (``gather``)
-        into a float64 frame buffer that stage A then reads with stride 1 -- bit-identical to the
-        fused path, and it lets ``StageAPipeline`` overlap the PCIe-bound ingest of the next
-        recording with the compute of the current one.  Decimate-then-filter order only."""
+        """``pregathered``: the decimation x[::ds] (K0) runs on its own (``gather``) into a frame
+        buffer that stage A then reads with stride 1 -- bit-identical to the fused path, and it
+        lets ``StageAPipeline`` overlap the PCIe-bound ingest of the next recording with the
+        compute of the current one.  ``True`` / ``"sm"``: bpm_gather_frames, a small kernel that
+        writes float64 frames; ``"ce"``: bpm_copy_frames, one strided 2-D copy on the copy engine
+        that keeps the PCM's dtype and channels (no SM involved, faster over PCIe).
+        Decimate-then-filter order only."""
         self.device = require_cuda()
         self.lib = nat.load_library()
         self.plan = plan_filter(sample_rate, params)
@@ -181,7 +184,10 @@ class StageARunner:
         self.total_in = int(self.items["n_in"].sum())
         self.total_m = int(self.items["m"].sum())
         self.cfg = stage_a_config(self.plan, params, nat.PCM_DTYPES[self.np_dtype], self.channels, want_debug)
+        if pregathered not in (False, True, "sm", "ce"):
+            raise ValueError("pregathered must be False, True / 'sm' or 'ce'")
         self.pregathered = bool(pregathered)
+        self.ingest = "ce" if pregathered == "ce" else ("sm" if pregathered else None)
         if self.pregathered:
             if self.plan.block != 1:
                 raise ValueError("pregathered ingest needs the decimate-then-filter order (filter_mode 'parity')")
@@ -189,7 +195,9 @@ class StageARunner:
             self.src_items_dev = torch.from_numpy(self.src_items.view(np.int64).reshape(-1, 4).copy()).to(self.device)
             self.src_stride = int(self.plan.stride)
             self.items = make_items(self.src_items["m"], self.src_items["m"])
-            self.cfg.stride, self.cfg.pcm_dtype, self.cfg.channels = 1, nat.PCM_DTYPES[np.dtype(np.float64)], 1
+            self.cfg.stride = 1
+            if self.ingest == "sm":
+                self.cfg.pcm_dtype, self.cfg.channels = nat.PCM_DTYPES[np.dtype(np.float64)], 1
         self.items_dev = torch.from_numpy(self.items.view(np.int64).reshape(-1, 4).copy()).to(self.device)
         self.design_dev = design_on_device(self.plan)
         self.design_words = int(self.design_dev.numel())
@@ -207,7 +215,8 @@ class StageARunner:
         self.ws_bytes = int(self.lib.bpm_stage_a_workspace_bytes(M, n))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
         if self.pregathered:
-            self.frames_dev = torch.empty(M, dtype=torch.float64, device=self.device)
+            self.frames_dev = (torch.empty(M, dtype=torch.float64, device=self.device) if self.ingest == "sm" else
+                               torch.empty(M * self.channels, dtype=_torch_dtype(self.np_dtype), device=self.device))
             self.pcm_dev = None
             self._pcm_src = self.frames_dev
         else:
@@ -244,13 +253,19 @@ class StageARunner:
         self._pcm_src = pinned
 
     def gather(self, pcm: torch.Tensor) -> None:
-        """K0 on the current stream (pregathered mode): kept frames of ``pcm`` -> float64 frame buffer.
-        ``pcm`` is a device tensor or a PINNED host tensor (zero-copy: the kernel reads it over PCIe)."""
+        """K0 on the current stream (pregathered mode): kept frames of ``pcm`` -> the frame buffer.
+        ``pcm`` is a device tensor or a PINNED host tensor ('sm': the kernel reads it over PCIe,
+        zero-copy; 'ce': the copy engine fetches one frame per row of a strided 2-D copy)."""
         if not self.pregathered:
             raise RuntimeError("runner was not built with pregathered=True")
         if not (pcm.is_cuda or pcm.is_pinned()) or pcm.numel() != self.total_in * self.channels \
                 or pcm.dtype != _torch_dtype(self.np_dtype):
             raise ValueError("need a device or pinned host tensor with the batch's dtype and size")
+        if self.ingest == "ce":
+            nat.check(self.lib.bpm_copy_frames(_ptr(pcm), nat.PCM_DTYPES[self.np_dtype], self.channels,
+                                               _host_ptr(self.src_items), self.n_items, self.src_stride,
+                                               _ptr(self.frames_dev), _stream_ptr()))
+            return
         nat.check(self.lib.bpm_gather_frames(_ptr(pcm), nat.PCM_DTYPES[self.np_dtype], self.channels,
                                              _ptr(self.src_items_dev), _host_ptr(self.src_items), self.n_items,
                                              self.src_stride, _ptr(self.frames_dev), _stream_ptr()))
@@ -587,7 +602,9 @@ class StageAPipeline:
     Each of ``depth`` slots owns a pregathered ``StageARunner`` (+ optionally a ``BeatRunner``),
     pinned host result buffers and three events.  ``submit(k, pcm_pinned)`` enqueues, without
     blocking the host,
-      ingest stream : bpm_gather_frames reading the pinned recording over PCIe (zero-copy),
+      ingest stream : the kept frames of the pinned recording cross PCIe -- ``ingest="ce"``: one
+                      strided 2-D copy on the copy engine (bpm_copy_frames, default);
+                      ``"sm"``: bpm_gather_frames reading mapped pinned memory (zero-copy),
       compute stream: a1..a4 (and a5..a8) as one CUDA-graph replay, after the slot's ingest,
       copy stream   : D2H of every result into the slot's pinned buffers, after the compute;
     ``wait(k)`` blocks until recording k's results are on the host.  With depth >= 2 the PCIe
@@ -597,13 +614,16 @@ class StageAPipeline:
     LISTS = ("troughs", "peaks", "strength", "deviation", "smoothed_dev")
 
     def __init__(self, n_in: int, sample_rate: int, params: Dict, depth: int = 2, beat_runner_args=None,
-                 pcm_dtype=np.int16, channels: int = 1, use_graph: bool = True):
+                 pcm_dtype=np.int16, channels: int = 1, use_graph: bool = True, ingest: str = "ce"):
         require_cuda()
+        if ingest not in ("ce", "sm"):
+            raise ValueError("ingest must be 'ce' or 'sm'")
+        self.ingest = ingest
         self.depth = int(depth)
         self.s_in, self.s_cmp, self.s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
         self.slots = []
         for _ in range(self.depth):
-            A = StageARunner([n_in], sample_rate, params, pcm_dtype, channels, pregathered=True)
+            A = StageARunner([n_in], sample_rate, params, pcm_dtype, channels, pregathered=ingest)
             Bn = BeatRunner(*beat_runner_args) if beat_runner_args is not None else None
             cap = A.total_m // max(int(A.cfg.distance), 1) + 2          # find_peaks distance bounds the list lengths
             host = {}

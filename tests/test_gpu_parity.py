@@ -460,10 +460,12 @@ def test_peak_trough_noise_matches_oracle(name, fe, ref_params):
 
 
 # ----------------------------------------------------------------------------- ingest pipeline
-def test_pipelined_zero_copy_ingest_is_bit_identical(fe, ref_params):
-    """runtime.StageAPipeline (bpm_gather_frames from pinned host memory, compute and read-back
-    on three streams, two recordings in flight) must return exactly what the one-shot
-    StageARunner returns for each recording of a stream of equal-length recordings."""
+@pytest.mark.parametrize("ingest", ["ce", "sm"])
+def test_pipelined_zero_copy_ingest_is_bit_identical(fe, ref_params, ingest):
+    """runtime.StageAPipeline (kept frames out of pinned host memory by bpm_copy_frames on the
+    copy engine / by bpm_gather_frames from the SMs, compute and read-back on three streams, two
+    recordings in flight) must return exactly what the one-shot StageARunner returns for each
+    recording of a stream of equal-length recordings."""
     import torch
     from bpm_analysis_b200 import synth
     from bpm_analysis_b200.runtime import StageAPipeline, StageARunner
@@ -477,7 +479,7 @@ def test_pipelined_zero_copy_ingest_is_bit_identical(fe, ref_params):
         torch.cuda.synchronize()
         want.append({k: v.clone().cpu() for k, v in one.out.items()})
     for use_graph in (False, True):
-        pipe = StageAPipeline(len(recs[0]), sr, ref_params, depth=2, use_graph=use_graph)
+        pipe = StageAPipeline(len(recs[0]), sr, ref_params, depth=2, use_graph=use_graph, ingest=ingest)
         pins = [torch.from_numpy(r).pin_memory() for r in recs]
         got = []
         for k in range(len(recs)):
@@ -492,6 +494,40 @@ def test_pipelined_zero_copy_ingest_is_bit_identical(fe, ref_params):
             assert torch.equal(g["envelope"], w["envelope"]) and torch.equal(g["floor"], w["floor"])
             assert torch.equal(g["troughs"][:nt], w["troughs"][:nt]) and torch.equal(g["peaks"][:npk], w["peaks"][:npk])
             assert torch.equal(g["smoothed_dev"][:npk - 1], w["smoothed_dev"][:npk - 1])
+
+
+@pytest.mark.parametrize("kind", ["stereo_i16", "f32", "u8", "stereo_f64"])
+def test_copy_engine_ingest_other_formats(fe, ref_params, kind):
+    """bpm_copy_frames keeps the PCM's dtype and channels: a pregathered='ce' runner fed from pinned
+    host memory equals the fused one-shot runner bit for bit for multi-channel and non-int16 input."""
+    import torch
+    from bpm_analysis_b200 import synth
+    from bpm_analysis_b200.runtime import StageARunner
+    pcm, sr, _ = synth.config_c1(seed=31, duration_sec=47.3)
+    if kind == "stereo_i16":
+        pcm = np.stack([pcm, np.roll(pcm, 7) // 2], axis=1)
+    elif kind == "f32":
+        pcm = (pcm / 32768.0).astype(np.float32)
+    elif kind == "u8":
+        pcm = ((pcm.astype(np.int32) >> 8) + 128).astype(np.uint8)
+    elif kind == "stereo_f64":
+        pcm = np.stack([pcm / 3.0, np.roll(pcm, 3) / 7.0], axis=1)
+    channels = 1 if pcm.ndim == 1 else pcm.shape[1]
+    one = StageARunner([pcm.shape[0]], sr, ref_params, pcm.dtype, channels)
+    one.upload([pcm])
+    one.launch()
+    ce = StageARunner([pcm.shape[0]], sr, ref_params, pcm.dtype, channels, pregathered="ce")
+    pin = torch.from_numpy(np.ascontiguousarray(pcm).reshape(-1)).pin_memory()
+    ce.gather(pin)
+    ce.launch()
+    torch.cuda.synchronize()
+    nt, npk = int(one.out["trough_count"][0]), int(one.out["peak_count"][0])
+    assert nt > 20 and npk > 20
+    assert int(ce.out["trough_count"][0]) == nt and int(ce.out["peak_count"][0]) == npk
+    for k in ("filtered", "envelope", "floor"):
+        assert torch.equal(ce.out[k], one.out[k]), k
+    assert torch.equal(ce.out["troughs"][:nt], one.out["troughs"][:nt])
+    assert torch.equal(ce.out["peaks"][:npk], one.out["peaks"][:npk])
 
 
 # ----------------------------------------------------------------------------- randomized sweep

@@ -14,6 +14,10 @@ fi
 python bench.py --impl reference --steps 3 --warmup 1 > $O/ev_${TAG}_bench_reference.json 2> $O/ev_${TAG}_bench_reference.err
 python bench.py --dump-kernels $O/ev_${TAG}_kernels_parity.json > $O/ev_${TAG}_bench_parity.json 2> $O/ev_${TAG}_bench_parity.err
 python bench.py --filter-mode fullrate --no-cpu-baseline --dump-kernels $O/ev_${TAG}_kernels_fullrate.json > $O/ev_${TAG}_bench_fullrate.json 2> $O/ev_${TAG}_bench_fullrate.err
+python bench.py --e2e-ingest sm --no-cpu-baseline --no-profile > $O/ev_${TAG}_bench_parity_ingest_sm.json 2> $O/ev_${TAG}_bench_parity_ingest_sm.err
+python bench.py --workload holter --steps 5 --warmup 3 > $O/ev_${TAG}_bench_holter_c4.json 2> $O/ev_${TAG}_bench_holter_c4.err
+python bench.py --workload batch --steps 5 --warmup 3 > $O/ev_${TAG}_bench_batch_c3.json 2> $O/ev_${TAG}_bench_batch_c3.err
+timeout 120 python tools/ingest_probe.py > $O/ev_${TAG}_ingest_probe.json 2> $O/ev_${TAG}_ingest_probe.err
 cut -c1-300 $O/ev_${TAG}_bench_parity.json
 # per-launch device times of the bench command (cold-cache, serialised: compare SHARES)
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-profile > $O/ev_${TAG}_plain_launches.log 2>&1 &&

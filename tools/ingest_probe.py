@@ -94,6 +94,33 @@ def main():
         with torch.cuda.stream(s0):
             full.copy_(pinned, non_blocking=True)
     out["d_full_copy_ms"] = timed(plain, [s0], reps=3)
+    # ---- does the read-back of a step's results (D2H) share a resource with the sparse ingest?
+    res_dev = torch.randn(2 * m + 40000, dtype=torch.float64, device="cuda")        # envelope + floor + lists
+    res_pin = torch.empty(res_dev.numel(), dtype=torch.float64).pin_memory()
+    s2 = torch.cuda.Stream()
+
+    def d2h_ce():
+        with torch.cuda.stream(s2):
+            res_pin.copy_(res_dev, non_blocking=True)
+
+    class _Alias:                                              # the pinned buffer as a device-visible tensor (UVA)
+        __cuda_array_interface__ = {"shape": (res_pin.numel(),), "typestr": "<f8", "data": (res_pin.data_ptr(), False),
+                                    "version": 2}
+    alias = torch.as_tensor(_Alias(), device="cuda")
+
+    def d2h_sm():                                              # an elementwise kernel storing into mapped host memory
+        with torch.cuda.stream(s2):
+            torch.add(res_dev, 0.0, out=alias)
+    out["e_d2h_bytes"] = int(res_dev.numel() * 8)
+    out["e_d2h_ce_alone_ms"] = timed(d2h_ce, [s2])
+    out["e_d2h_sm_alone_ms"] = timed(d2h_sm, [s2])
+    torch.cuda.synchronize()
+    out["e_d2h_sm_correct"] = bool(torch.equal(res_pin, res_dev.cpu()))
+    if "b_ce_all_rows_ms" in out:
+        out["f_ce_ingest_with_ce_d2h_ms"] = timed(lambda: (ce(m), d2h_ce()), [s1, s2])
+        out["f_ce_ingest_with_sm_d2h_ms"] = timed(lambda: (ce(m), d2h_sm()), [s1, s2])
+    out["f_sm_ingest_with_ce_d2h_ms"] = timed(lambda: (gather(), d2h_ce()), [s0, s2])
+    out["f_sm_ingest_with_sm_d2h_ms"] = timed(lambda: (gather(), d2h_sm()), [s0, s2])
     rc = cudart.cudaDeviceSetLimit(0x05, ctypes.c_size_t(32))
     out["set_l2_fetch_32_rc"] = int(rc)
     out["a_sm_gather_l2fetch32_ms"] = timed(gather, [s0])
