@@ -12,7 +12,7 @@ __version__ = "0.1.0"
 
 def __getattr__(name):
     # lazy: importing the package must work without torch/CUDA (CPU-side tooling, oracle tests)
-    if name in ("frontend", "runtime", "design", "synth", "dist", "classifier"):
+    if name in ("frontend", "runtime", "design", "synth", "dist", "classifier", "corrections"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

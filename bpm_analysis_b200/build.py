@@ -53,7 +53,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
 
 
 HOST_LIB_PATH = os.path.join(HERE, "libbpm_host.so")
-HOST_SOURCES = ["classifier.cpp"]
+HOST_SOURCES = ["classifier.cpp", "corrections.cpp"]
 # -ffp-contract=off: the classifier's decisions must round exactly like CPython's float arithmetic
 GXX_FLAGS = ["-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wextra"]
 

@@ -282,14 +282,15 @@ def calculate_windowed_hrv(s1_peaks: np.ndarray, sample_rate: int, params: Dict)
 
 
 # --------------------------------------------------------------------------- install
-def install(ref_module, classifier: bool = True):
+def install(ref_module, classifier: bool = True, corrections: bool = True):
     """Rebind the reference module's front-end names to this package.
 
     ``ref_module`` is an imported reference ``bpm_analysis`` module.  Callers that did
     ``from bpm_analysis import analyze_wav_file`` keep working because that function
     resolves these names from the module's globals at call time.  With ``classifier=True``
     (default) ``PeakClassifier.classify_peaks`` is rebound to the compiled sequential loop
-    (``classifier.py`` -> libbpm_host.so) as well.
+    (``classifier.py`` -> libbpm_host.so) as well; with ``corrections=True`` (default) so are
+    ``correct_peaks_by_rhythm`` and ``_fix_rhythmic_discontinuities`` (``corrections.py``).
     """
     for name in ("preprocess_audio", "_calculate_dynamic_noise_floor", "calculate_bpm_series",
                  "find_peak_recovery_rate", "find_peak_exertion_rate", "find_major_hr_inclines",
@@ -300,4 +301,7 @@ def install(ref_module, classifier: bool = True):
     if classifier:
         from . import classifier as _classifier
         _classifier.install(ref_module)
+    if corrections:
+        from . import corrections as _corrections
+        _corrections.install(ref_module)
     return ref_module

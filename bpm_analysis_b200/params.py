@@ -67,6 +67,11 @@ CLASSIFIER_DEFAULTS: Dict[str, object] = {
     "lone_s1_amplitude_weight": 0.35,
     "min_bpm": 40,
     "max_bpm": 240,
+    # correction passes (corrections.py)
+    "rr_correction_threshold_pct": 0.4,
+    "rr_correction_long_interval_pct": 1.7,
+    "penalty_waiver_strength_ratio": 4.0,
+    "penalty_waiver_max_s2_s1_ratio": 2.5,
 }
 
 # constants the reference hard-codes on the hot path (file:line in bpm_analysis.py)

@@ -120,6 +120,47 @@ int bpm_classify_peaks(const double* envelope, const double* noise_floor, int64_
                        BpmClassification** out);
 void bpm_classification_free(BpmClassification* c);
 
+/* ---- correction passes over the classified beat list ----------
+ * The loops of correct_peaks_by_rhythm (bpm_analysis.py:1257-1306) and
+ * _fix_rhythmic_discontinuities (:1309-1412).  The few vectorised numpy calls in front of them
+ * (np.diff, np.median, np.percentile -> the thresholds) stay numpy calls in the Python mirror;
+ * what is compiled is the per-beat Python loop, including the scan of EVERY raw peak the
+ * reference repeats for each long gap (:1355-1356).  Decisions are reported as events; the
+ * mirror applies them to the debug-string dict and writes the reference's log lines. */
+enum {
+  BPM_CORR_REPLACED = 1,        /* a = current peak, b = the accepted peak it replaced   (:1291) */
+  BPM_CORR_DISCARDED = 2,       /* a = current peak                                      (:1295) */
+  BPM_CORR_LONG_INTERVAL = 3,   /* a = S1 peak that starts the long interval             (:1353) */
+  BPM_CORR_RELABELLED = 4,      /* a, b = POSITIONS in raw_peaks of the new S1 / S2      (:1373-1381) */
+  BPM_CORR_SHORT_INTERVAL = 5,  /* a, b = the two beats, x = their interval in seconds   (:1398) */
+  BPM_CORR_REMOVED = 6          /* a = the weaker beat                                   (:1405-1411) */
+};
+typedef struct {
+  int32_t kind;
+  int32_t pad;
+  int64_t a;
+  int64_t b;
+  double x;
+} BpmCorrectionEvent;
+
+/* correct_peaks_by_rhythm for len(peaks) >= 5: peaks closer than threshold_sec to the last accepted
+ * one conflict; the higher envelope amplitude wins.  out: capacity n; events: capacity n. */
+int bpm_correct_peaks_by_rhythm(const int64_t* peaks, int64_t n, const double* envelope, int64_t m,
+                                double sample_rate, double threshold_sec,
+                                int64_t* out, int64_t* n_out, BpmCorrectionEvent* events, int64_t* n_events);
+
+/* _fix_rhythmic_discontinuities after its thresholds are known (len(s1_peaks) >= 6).
+ *   raw_is_noise[i] != 0  <=>  "Noise" in debug_info.get(raw_peaks[i], "")   (evaluated by the caller on
+ *   the strings, as the reference does: a re-labelled peak keeps "Noise" inside its ORIGINAL_REASON)
+ *   out: capacity n_s1 + n_raw; events: capacity 4 * (n_s1 + n_raw) + 8. */
+int bpm_fix_rhythmic_discontinuities(const int64_t* s1_peaks, int64_t n_s1, const int64_t* raw_peaks, int64_t n_raw,
+                                     const uint8_t* raw_is_noise, const double* envelope, const double* noise_floor,
+                                     int64_t m, double sample_rate, double short_threshold_sec,
+                                     double long_threshold_sec, double waiver_strength_ratio,
+                                     double waiver_max_s2_s1_ratio, int64_t* out, int64_t* n_out,
+                                     BpmCorrectionEvent* events, int64_t events_capacity, int64_t* n_events,
+                                     int64_t* corrections_made);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,9 +64,46 @@ def run_reference(ref, case):
     return packed
 
 
+def run_reference_corrections(ref, case, classified):
+    """The reference's stages 4 and 5 (``_refine_and_correct_peaks``, bpm_analysis.py:1655-1698) on
+    the classifier's result, with every intermediate recorded."""
+    import numpy as np
+    import pandas as pd
+    cap = _Capture()
+    root = logging.getLogger()
+    level = root.level
+    root.addHandler(cap)
+    root.setLevel(logging.INFO)
+    try:
+        raw = case["peaks"]
+        keys = list(raw)
+        info = {keys[raw.tolist().index(k)]: t for k, t in zip(classified["keys"], classified["texts"])}
+        s1 = np.array(classified["final_peaks"], dtype=np.int64)
+        floor = pd.Series(case["floor"], index=np.arange(len(case["floor"])))
+        peaks = ref.correct_peaks_by_rhythm(s1, case["env"], case["rate"], case["params"])
+        out = {"after_rhythm": [int(x) for x in peaks], "iterations": []}
+        for _ in range(5):
+            peaks, info, made = ref._fix_rhythmic_discontinuities(peaks, raw, info, case["env"], floor, case["params"],
+                                                                  case["rate"])
+            out["iterations"].append({"peaks": [int(x) for x in peaks], "made": int(made)})
+            if made == 0:
+                break
+        out["final_keys"] = [int(k) for k in info.keys()]
+        out["final_texts"] = list(info.values())
+    finally:
+        root.removeHandler(cap)
+        root.setLevel(level)
+    out["log"] = cap.lines
+    return out
+
+
 def main():
     ref = load_reference()
-    out = {str(seed): run_reference(ref, make_case(seed)) for seed in GOLDEN_SEEDS}
+    out = {}
+    for seed in GOLDEN_SEEDS:
+        case = make_case(seed)
+        out[str(seed)] = run_reference(ref, case)
+        out[str(seed)]["corrections"] = run_reference_corrections(ref, case, out[str(seed)])
     with gzip.GzipFile(OUT, "wb", mtime=0) as fh:
         fh.write(json.dumps(out, ensure_ascii=False, sort_keys=True).encode("utf-8"))
     n = sum(len(v["keys"]) for v in out.values())

@@ -50,8 +50,9 @@ def test_host_library_exports_header_symbols():
     import re
     lib = ctypes.CDLL(classifier.HOST_LIB_PATH)
     header = open(os.path.join(REPO, "include", "bpm_host.h")).read()
+    from bpm_analysis_b200 import corrections
     declared = set(re.findall(r"^\s*(?:int|void)\s+(bpm_\w+)\s*\(", header, flags=re.M))
-    assert declared == set(classifier.EXPORTED_SYMBOLS)
+    assert declared == set(classifier.EXPORTED_SYMBOLS) | set(corrections.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
     assert classifier.load_host_library().bpm_host_abi_version() == classifier.HOST_ABI_VERSION
