@@ -692,28 +692,38 @@ def run_extra(args):
     e1.record()
     barrier()
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-    # end to end, serial steps: the whole batch host -> device from ONE pinned buffer, compute, then
-    # envelope + floor + counts + the (distance-bounded) trough / peak lists device -> pinned host
+    # end to end, serial steps: the batch leaves ONE pinned buffer -- as strided copy-engine copies of
+    # the kept frames when the decimation is coarse enough for that to beat copying everything
+    # (bpm_copy_frames moves ~0.7 G frames/s, a plain copy ~55 GB/s: worth it from ds >= 40 for int16)
+    # -- then compute, then envelope + floor + counts + the (distance-bounded) trough / peak lists
+    # device -> pinned host
     pin_in = torch.empty(A.total_in, dtype=torch.int16).pin_memory()
     off = 0
     for p_ in pcms:
         pin_in.numpy()[off:off + len(p_)] = p_
         off += len(p_)
-    dist_samples = max(int(A.cfg.distance), 1)
-    caps = [int(it["m"]) // dist_samples + 2 for it in A.items]
-    host = {k: torch.empty_like(A.out[k], device="cpu").pin_memory()
+    sparse = args.filter_mode == "parity" and A.plan.stride >= 40
+    E = StageARunner([len(p) for p in pcms], sr, params, pregathered="ce") if sparse else A
+    dist_samples = max(int(E.cfg.distance), 1)
+    caps = [int(it["m"]) // dist_samples + 2 for it in E.items]
+    host = {k: torch.empty_like(E.out[k], device="cpu").pin_memory()
             for k in ("envelope", "floor", "trough_count", "peak_count")}
     host_lists = {k: [torch.empty(c, dtype=torch.int64).pin_memory() for c in caps] for k in ("troughs", "peaks")}
     d2h = sum(h.numel() * h.element_size() for h in host.values()) + 2 * 8 * sum(caps)
+    h2d = E.total_m * 2 if sparse else A.total_in * 2
 
     def e2e_step():
-        A.upload_pinned(pin_in)
-        step()
+        if sparse:
+            E.gather(pin_in)
+            E.launch()
+        else:
+            A.upload_pinned(pin_in)
+            step()
         for k, h in host.items():
-            h.copy_(A.out[k], non_blocking=True)
+            h.copy_(E.out[k], non_blocking=True)
         for k, hs in host_lists.items():
-            for it, h in zip(A.items, hs):
-                h.copy_(A.out[k][int(it["m_off"]):int(it["m_off"]) + h.numel()], non_blocking=True)
+            for it, h in zip(E.items, hs):
+                h.copy_(E.out[k][int(it["m_off"]):int(it["m_off"]) + h.numel()], non_blocking=True)
         torch.cuda.synchronize()
 
     e2e_step()
@@ -724,9 +734,10 @@ def run_extra(args):
         e2e_step()
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / n_e2e)
-    for it, ht, hp, ct, cp in zip(A.items, host_lists["troughs"], host_lists["peaks"], host["trough_count"].tolist(),
+    for it, ht, hp, ct, cp in zip(E.items, host_lists["troughs"], host_lists["peaks"], host["trough_count"].tolist(),
                                   host["peak_count"].tolist()):
         assert ct <= ht.numel() and cp <= hp.numel(), "find_peaks distance bounds the list lengths"
+    assert torch.equal(host["peak_count"], A.out["peak_count"].cpu()) and torch.equal(host["floor"], A.out["floor"].cpu())
     clocks = sampler.stop()
     M = A.total_m
     nt, npk = int(host["trough_count"].sum()), int(host["peak_count"].sum())
@@ -754,9 +765,11 @@ def run_extra(args):
                          "scope": "a1..a4 (no beat-list reductions)"},
               "clocks": clocks,
               "e2e": {"value": world * audio_hours / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
-                      "h2d_bytes_per_step": int(shp["N"] * 2), "d2h_bytes_per_step": int(d2h),
-                      "ingest": "serial steps: one pinned buffer -> device (cudaMemcpyAsync of the whole batch), compute, "
-                                "envelope + floor + counts + distance-bounded lists -> pinned host"},
+                      "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                      "ingest": ("serial steps: one pinned buffer -> device (" +
+                                 ("bpm_copy_frames: strided copy-engine copies of the kept frames x[::ds]" if sparse else
+                                  "cudaMemcpyAsync of the whole batch") +
+                                 "), compute, envelope + floor + counts + distance-bounded lists -> pinned host")},
               "gpu_launches": launches_per_step * args.steps,
               "launch_mode": "eager" if graphed is None else "cuda-graph replay",
               "roofline": {"kernel": top, "bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s",
