@@ -126,3 +126,18 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_copy_frames_rejects_bad_arguments_without_touching_the_device(lib):
+    """bpm_copy_frames validates before it enqueues anything: these calls never reach CUDA."""
+    import ctypes
+    from bpm_analysis_b200.runtime import make_items
+    items = make_items([1000], [7])                      # m must be ceil(n_in / stride) = 7 for stride 159
+    buf = ctypes.create_string_buffer(64)
+    ok_items = items.ctypes.data
+    assert lib.bpm_copy_frames(None, 0, 1, ok_items, 1, 159, ctypes.addressof(buf), None) == -1       # null pcm
+    assert lib.bpm_copy_frames(ctypes.addressof(buf), 9, 1, ok_items, 1, 159, ctypes.addressof(buf), None) == -1   # dtype
+    assert lib.bpm_copy_frames(ctypes.addressof(buf), 0, 0, ok_items, 1, 159, ctypes.addressof(buf), None) == -1   # channels
+    assert lib.bpm_copy_frames(ctypes.addressof(buf), 0, 1, ok_items, 1, 0, ctypes.addressof(buf), None) == -1     # stride
+    bad = make_items([1000], [8])
+    assert lib.bpm_copy_frames(ctypes.addressof(buf), 0, 1, bad.ctypes.data, 1, 159, ctypes.addressof(buf), None) == -1
