@@ -24,7 +24,7 @@ def _newest_source_mtime() -> float:
     m = 0.0
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for f in os.listdir(root):
-            if f.endswith((".cu", ".cuh", ".h")):
+            if f.endswith((".cu", ".cuh", ".h")) and f != "bpm_host.h":     # the host library's header
                 m = max(m, os.path.getmtime(os.path.join(root, f)))
     return m
 
