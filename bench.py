@@ -482,10 +482,12 @@ def run_b200(args):
         sample_sec = min(args.duration_sec, 3600.0)
         n = int(sample_sec * sr)
         bi = synth.beats_to_envelope_indices(beats[beats < sample_sec - 1.0], rate)
-        t = cpu_step(pcm[:n], sr, bi, params, 1)
+        reps = 4                                     # ~11 s of CPU work at the default size
+        ts = [cpu_step(pcm[:n], sr, bi, params, 1) for _ in range(reps)]
+        t = sum(ts) / reps
         cpu = {"value": (sample_sec / 3600.0) / t, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"1 x first {sample_sec:g} s of the same recording, a1..a8, one core "
-                         f"(the reference is single-threaded); {t:.2f} s"}
+               "sample": f"{reps} x first {sample_sec:g} s of the same recording, a1..a8, one core "
+                         f"(the reference is single-threaded); {sum(ts):.2f} s in all"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
