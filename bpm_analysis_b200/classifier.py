@@ -178,6 +178,12 @@ def classify_peaks(self) -> Tuple[np.ndarray, np.ndarray, Dict]:
     if len(all_peaks) < 2:                                          # :115-116
         return all_peaks, all_peaks, {"beat_debug_info": {}}
     if st["loop_idx"] == 0 and not st["candidate_beats"]:
+        # Python-level errors the reference's first iteration raises before any decision is made
+        # (:135-141 with an empty window, :1136 with equal contractility anchors and a Python-float BPM)
+        if self.params.get("stability_history_window", 20) == 0:
+            raise ZeroDivisionError("division by zero")
+        _ = ((st["long_term_bpm"] - self.params["contractility_bpm_low"]) /
+             (self.params["contractility_bpm_high"] - self.params["contractility_bpm_low"]))
         packed = pack_params(self.params, st["long_term_bpm"], self.peak_bpm_time_sec, self.recovery_end_time_sec)
         dev = st["smoothed_dev_series"]
         res = classify_arrays(self.audio_envelope, st["dynamic_noise_floor"].values, all_peaks,

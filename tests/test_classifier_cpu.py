@@ -139,6 +139,47 @@ def test_argument_errors_are_reported():
         classifier.pack_params({k: v for k, v in case["params"].items() if k != "min_bpm"}, 80.0, None, None)
 
 
+def test_python_level_errors_of_the_first_iteration_are_mirrored():
+    case = make_case(4)
+    case["params"] = dict(case["params"], contractility_bpm_low=120.0, contractility_bpm_high=120.0)
+    with pytest.raises(ZeroDivisionError):                              # bpm_analysis.py:1136, Python floats
+        classifier.classify_peaks(ClassifierStandIn(case))
+    case = make_case(4)
+    case["params"] = dict(case["params"], stability_history_window=0)
+    with pytest.raises(ZeroDivisionError):                              # :141, paired_count / 0
+        classifier.classify_peaks(ClassifierStandIn(case))
+
+
+@needs_reference
+def test_live_reference_adversarial_inputs(caplog):
+    """NaNs in the deviation series and in the floor, amplitudes scaled by 1e12 and 1e-12, extreme
+    parameter values: the NaN / inf paths of max(), min(), np.clip, np.interp, asof and the
+    formatting agree with the reference."""
+    from oracle.make_golden_classifier import run_reference
+    ref = load_reference()
+    for seed in range(500, 548):
+        case = make_case(seed)
+        rng = np.random.default_rng(seed)
+        mode = seed % 5
+        if mode == 0:
+            idx = rng.choice(len(case["dev_values"]), size=max(1, len(case["dev_values"]) // 5), replace=False)
+            case["dev_values"][idx] = np.nan
+            case["dev_values"][0] = np.nan
+        elif mode == 1:
+            case["env"] = case["env"] * 1e12
+        elif mode == 2:
+            case["env"], case["floor"] = case["env"] * 1e-12, case["floor"] * 1e-12
+        elif mode == 3:
+            case["floor"][case["peaks"][::5]] = np.nan
+        else:
+            case["params"].update(min_bpm=10, max_bpm=400, stability_history_window=1, kickstart_check_threshold=1.1,
+                                  cascade_reset_trigger_count=1, pairing_confidence_threshold=0.0)
+        with np.errstate(all="ignore"):
+            want = run_reference(ref, case)
+        got, _ = run_ours(case, caplog)
+        assert_same(got, want, f"seed {seed} mode {mode}")
+
+
 def test_install_rebinds_classify_peaks():
     class Mod:
         class PeakClassifier:
