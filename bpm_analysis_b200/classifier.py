@@ -78,7 +78,7 @@ class Classification(C.Structure):
                 ("final_long_term_bpm", C.c_double), ("final_consecutive_rr_rejections", C.c_int64)]
 
 
-EXPORTED_SYMBOLS = ("bpm_host_abi_version", "bpm_classify_peaks", "bpm_classification_free")
+EXPORTED_SYMBOLS = ("bpm_host_abi_version", "bpm_host_format_fixed", "bpm_classify_peaks", "bpm_classification_free")
 
 
 class HostLibraryError(RuntimeError):
@@ -107,6 +107,8 @@ def load_host_library(path: str = HOST_LIB_PATH):
                                            C.c_void_p, C.c_int64, C.c_double, C.POINTER(ClassifierParams),
                                            C.POINTER(C.POINTER(Classification))]
         lib.bpm_classification_free.restype, lib.bpm_classification_free.argtypes = None, [C.POINTER(Classification)]
+        lib.bpm_host_format_fixed.restype = C.c_int
+        lib.bpm_host_format_fixed.argtypes = [C.c_double, C.c_int, C.c_char_p, C.c_size_t]
         if lib.bpm_host_abi_version() != HOST_ABI_VERSION:
             raise HostLibraryError(f"ABI mismatch: library {lib.bpm_host_abi_version()}, binding {HOST_ABI_VERSION}")
         _lib = lib

@@ -68,9 +68,32 @@ double series_asof(const double* idx, const double* val, int64_t n, double t) {
   return val[loc];
 }
 
-// format(v, f".{prec}f") and format(v, ".0%")
+// format(v, f".{prec}f") and format(v, ".0%").
+// Fast path: x = |v| * 10^prec is formed in double (relative error <= 2^-53: below 1.3e-4
+// absolute while x < 2^40) and rounded only when its fractional part is at least 1e-3 away
+// from one half, where the correctly rounded decimal -- what printf and Python print -- is
+// decided without ambiguity; the integer is then exact.  Anything else (ties and near-ties, huge
+// values, inf, larger precisions) goes through snprintf.
 void put_f(std::string& s, double v, int prec) {
   if (std::isnan(v)) { s += "nan"; return; }
+  static const double p10[4] = {1.0, 10.0, 100.0, 1000.0};
+  const double a = std::fabs(v);
+  if (prec >= 0 && prec <= 3 && a < 1099511627776.0) {                  // 2^40
+    const double x = a * p10[prec];
+    const double fl = std::floor(x);
+    const double frac = x - fl;
+    if (x < 1099511627776.0 && std::fabs(frac - 0.5) > 1e-3) {
+      unsigned long long r = static_cast<unsigned long long>(fl) + (frac > 0.5 ? 1ull : 0ull);
+      char buf[32];
+      int pos = 32;
+      for (int d = 0; d < prec; ++d) { buf[--pos] = static_cast<char>('0' + r % 10); r /= 10; }
+      if (prec > 0) buf[--pos] = '.';
+      do { buf[--pos] = static_cast<char>('0' + r % 10); r /= 10; } while (r);
+      if (std::signbit(v)) buf[--pos] = '-';
+      s.append(buf + pos, static_cast<size_t>(32 - pos));
+      return;
+    }
+  }
   char buf[400];
   const int k = std::snprintf(buf, sizeof buf, "%.*f", prec, v);
   if (k > 0) s.append(buf, static_cast<size_t>(k) < sizeof buf ? static_cast<size_t>(k) : sizeof buf - 1);
@@ -359,6 +382,15 @@ struct Owned {
 extern "C" {
 
 int bpm_host_abi_version(void) { return BPM_HOST_ABI_VERSION; }
+
+int bpm_host_format_fixed(double v, int prec, char* out, size_t capacity) {
+  if (!out || capacity == 0 || prec < 0 || prec > 17) return BPM_HOST_ERR_ARG;
+  std::string s;
+  put_f(s, v, prec);
+  if (s.size() + 1 > capacity) return BPM_HOST_ERR_ARG;
+  std::memcpy(out, s.c_str(), s.size() + 1);
+  return static_cast<int>(s.size());
+}
 
 int bpm_classify_peaks(const double* envelope, const double* noise_floor, int64_t m, const int64_t* raw_peaks,
                        int64_t n_peaks, const double* dev_times, const double* dev_values, int64_t n_dev,

@@ -106,6 +106,11 @@ typedef struct {
 
 int bpm_host_abi_version(void);
 
+/* The fixed-point formatter behind the debug strings: writes format(v, ".{prec}f") as Python
+ * prints it (correctly rounded, "nan" / "inf" spelled like Python), NUL-terminated; returns the
+ * length or BPM_HOST_ERR_ARG.  Exported so that tests can pin it against Python directly. */
+int bpm_host_format_fixed(double v, int prec, char* out, size_t capacity);
+
 /* PeakClassifier.classify_peaks (bpm_analysis.py:113-131) for n_peaks >= 2 raw peaks.
  *   envelope, noise_floor: float64[m] (audio_envelope, dynamic_noise_floor.values)
  *   raw_peaks: int64[n_peaks], strictly ascending, each in [0, m)  (state['all_peaks'])

@@ -59,6 +59,26 @@ def test_host_library_exports_header_symbols():
     assert ctypes.sizeof(classifier.ClassifierParams) == 28 * 8 + 4 * 4
 
 
+def test_fixed_point_formatter_matches_python():
+    """Every number in a debug string goes through this formatter; it must print what Python's
+    format(v, '.Nf') prints, including exact ties (round-half-even on the binary value), values
+    just off a tie, negative zero results, huge values, inf and nan."""
+    lib = classifier.load_host_library()
+    buf = ctypes.create_string_buffer(512)
+    rng = np.random.default_rng(11)
+    values = [0.0, -0.0, 0.125, 0.375, 2.5, 3.5, 0.5, 1.5, -0.5, -0.001, 0.005, 0.015, 0.025, 1.005, 2.675, 1e-9,
+              0.9999999, 0.99999, 999.9995, 1234567.8915, 2.0 ** 40, 2.0 ** 40 - 0.5, 1e15 + 0.5, 1e22, 1e300,
+              float("inf"), float("-inf"), float("nan"), 0.285, 0.28500000000000003, 0.145, 100.0 * 0.125]
+    values += list(rng.uniform(0, 2, 4000)) + list(rng.uniform(-300, 300, 2000)) + list(10.0 ** rng.uniform(-12, 14, 2000))
+    values += [k / 8.0 for k in range(-40, 200)] + [k / 1000.0 + 0.0005 for k in range(300)]       # ties and near-ties
+    values += [np.nextafter(k / 200.0 + 0.0025, s) for k in range(200) for s in (-1e9, 1e9)]
+    for prec in (0, 1, 2, 3):
+        for v in values:
+            n = lib.bpm_host_format_fixed(float(v), prec, buf, len(buf))
+            assert n >= 0
+            assert buf.value.decode() == format(float(v), f".{prec}f"), (v, prec)
+
+
 def test_golden_cases_reproduced_exactly(caplog):
     with gzip.open(os.path.join(GOLDEN_DIR, "classifier_cases.json.gz"), "rb") as fh:
         golden = json.loads(fh.read().decode("utf-8"))
