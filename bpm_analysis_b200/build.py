@@ -55,7 +55,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
 HOST_LIB_PATH = os.path.join(HERE, "libbpm_host.so")
 HOST_SOURCES = ["classifier.cpp", "corrections.cpp"]
 # -ffp-contract=off: the classifier's decisions must round exactly like CPython's float arithmetic
-GXX_FLAGS = ["-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wextra"]
+GXX_FLAGS = ["-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-Wall",
+             "-Wextra"]
 
 
 def build_host(force: bool = False) -> str:

@@ -62,7 +62,16 @@ class ClassifierParams(C.Structure):
     _fields_ = ([(f, C.c_double) for f, _, _ in _DOUBLE_FIELDS] +
                 [("start_bpm", C.c_double), ("peak_bpm_time_sec", C.c_double), ("recovery_end_time_sec", C.c_double),
                  ("has_recovery_window", C.c_int32), ("enable_interval_penalty", C.c_int32),
-                 ("stability_history_window", C.c_int32), ("reserved", C.c_int32)])
+                 ("stability_history_window", C.c_int32), ("flags", C.c_int32)])
+
+
+CLASSIFY_NO_TEXT = 1
+
+
+class ClassifyJob(C.Structure):
+    _fields_ = [("envelope", C.c_void_p), ("noise_floor", C.c_void_p), ("m", C.c_int64), ("raw_peaks", C.c_void_p),
+                ("n_peaks", C.c_int64), ("dev_times", C.c_void_p), ("dev_values", C.c_void_p), ("n_dev", C.c_int64),
+                ("sample_rate", C.c_double), ("params", C.POINTER(ClassifierParams))]
 
 
 class ClassifierEvent(C.Structure):
@@ -78,7 +87,8 @@ class Classification(C.Structure):
                 ("final_long_term_bpm", C.c_double), ("final_consecutive_rr_rejections", C.c_int64)]
 
 
-EXPORTED_SYMBOLS = ("bpm_host_abi_version", "bpm_host_format_fixed", "bpm_classify_peaks", "bpm_classification_free")
+EXPORTED_SYMBOLS = ("bpm_host_abi_version", "bpm_host_format_fixed", "bpm_classify_peaks", "bpm_classify_peaks_batch",
+                    "bpm_classification_free")
 
 
 class HostLibraryError(RuntimeError):
@@ -107,6 +117,9 @@ def load_host_library(path: str = HOST_LIB_PATH):
                                            C.c_void_p, C.c_int64, C.c_double, C.POINTER(ClassifierParams),
                                            C.POINTER(C.POINTER(Classification))]
         lib.bpm_classification_free.restype, lib.bpm_classification_free.argtypes = None, [C.POINTER(Classification)]
+        lib.bpm_classify_peaks_batch.restype = C.c_int
+        lib.bpm_classify_peaks_batch.argtypes = [C.POINTER(ClassifyJob), C.c_int64, C.c_int,
+                                                 C.POINTER(C.POINTER(Classification)), C.POINTER(C.c_int)]
         lib.bpm_host_format_fixed.restype = C.c_int
         lib.bpm_host_format_fixed.argtypes = [C.c_double, C.c_int, C.c_char_p, C.c_size_t]
         if lib.bpm_host_abi_version() != HOST_ABI_VERSION:
@@ -115,8 +128,10 @@ def load_host_library(path: str = HOST_LIB_PATH):
         return lib
 
 
-def pack_params(params: Dict, start_bpm: float, peak_bpm_time_sec, recovery_end_time_sec) -> ClassifierParams:
-    """DEFAULT_PARAMS (config.py) -> BpmClassifierParams, with the reference's ``.get`` defaults."""
+def pack_params(params: Dict, start_bpm: float, peak_bpm_time_sec, recovery_end_time_sec,
+                with_text: bool = True) -> ClassifierParams:
+    """DEFAULT_PARAMS (config.py) -> BpmClassifierParams, with the reference's ``.get`` defaults.
+    ``with_text=False`` skips the per-peak debug strings (decisions are unchanged)."""
     p = ClassifierParams()
     for field, key, default in _DOUBLE_FIELDS:
         setattr(p, field, float(params[key] if default is None else params.get(key, default)))
@@ -126,6 +141,7 @@ def pack_params(params: Dict, start_bpm: float, peak_bpm_time_sec, recovery_end_
     p.recovery_end_time_sec = float(recovery_end_time_sec) if p.has_recovery_window else 0.0
     p.enable_interval_penalty = int(bool(params.get("enable_interval_penalty", True)))
     p.stability_history_window = int(params.get("stability_history_window", 20))
+    p.flags = 0 if with_text else CLASSIFY_NO_TEXT
     return p
 
 
@@ -155,21 +171,59 @@ def classify_arrays(envelope: np.ndarray, noise_floor: np.ndarray, raw_peaks: np
         raise ValueError(f"bpm_classify_peaks rejected its arguments (code {rc}): raw peaks must be >= 2, strictly "
                          "ascending and inside the envelope; stability_history_window >= 1")
     try:
-        r = out.contents
-        n = int(r.n_peaks)
-        texts = C.string_at(r.text, int(r.text_bytes)).decode("utf-8").split("\x00")[:n]   # NUL-terminated entries
-        return {
-            "beat_positions": _as(r.beat_positions, int(r.n_beats), np.int64),
-            "peak_types": _as(r.peak_types, n, np.int32),
-            "texts": texts,
-            "history_times": _as(r.history_times, int(r.n_history), np.float64),
-            "history_bpm": _as(r.history_bpm, int(r.n_history), np.float64),
-            "events": [(int(r.events[i].kind), int(r.events[i].a), int(r.events[i].b)) for i in range(int(r.n_events))],
-            "final_long_term_bpm": float(r.final_long_term_bpm),
-            "final_consecutive_rr_rejections": int(r.final_consecutive_rr_rejections),
-        }
+        return _unpack(out.contents)
     finally:
         lib.bpm_classification_free(out)
+
+
+def _unpack(r: Classification) -> Dict[str, object]:
+    n = int(r.n_peaks)
+    texts = C.string_at(r.text, int(r.text_bytes)).decode("utf-8").split("\x00")[:n]   # NUL-terminated entries
+    return {
+        "beat_positions": _as(r.beat_positions, int(r.n_beats), np.int64),
+        "peak_types": _as(r.peak_types, n, np.int32),
+        "texts": texts,
+        "history_times": _as(r.history_times, int(r.n_history), np.float64),
+        "history_bpm": _as(r.history_bpm, int(r.n_history), np.float64),
+        "events": [(int(r.events[i].kind), int(r.events[i].a), int(r.events[i].b)) for i in range(int(r.n_events))],
+        "final_long_term_bpm": float(r.final_long_term_bpm),
+        "final_consecutive_rr_rejections": int(r.final_consecutive_rr_rejections),
+    }
+
+
+def classify_batch(jobs, n_threads: int = 0):
+    """Classify independent recordings on host threads (``bpm_classify_peaks_batch``).
+
+    ``jobs``: sequence of ``(envelope, noise_floor, raw_peaks, dev_times, dev_values, sample_rate,
+    packed_params)``.  Returns one result dict per job (as ``classify_arrays``); raises
+    ``ValueError`` naming the first job the library rejected."""
+    lib = load_host_library()
+    n = len(jobs)
+    arr = (ClassifyJob * n)()
+    keep = []
+    for i, (env, floor, peaks, dt, dv, rate, packed) in enumerate(jobs):
+        a = [np.ascontiguousarray(env, dtype=np.float64), np.ascontiguousarray(floor, dtype=np.float64),
+             np.ascontiguousarray(peaks, dtype=np.int64), np.ascontiguousarray(dt, dtype=np.float64),
+             np.ascontiguousarray(dv, dtype=np.float64)]
+        if a[1].shape != a[0].shape or a[3].shape != a[4].shape:
+            raise ValueError(f"job {i}: envelope / noise floor and deviation index / values must have matching lengths")
+        keep.append((a, packed))
+        arr[i] = ClassifyJob(a[0].ctypes.data, a[1].ctypes.data, a[0].shape[0], a[2].ctypes.data, a[2].shape[0],
+                             a[3].ctypes.data, a[4].ctypes.data, a[3].shape[0], float(rate), C.pointer(packed))
+    outs = (C.POINTER(Classification) * n)()
+    status = (C.c_int * n)()
+    rc = lib.bpm_classify_peaks_batch(arr, n, int(n_threads), outs, status)
+    try:
+        if rc != 0:
+            raise ValueError(f"bpm_classify_peaks_batch failed (code {rc})")
+        for i in range(n):
+            if status[i] != 0:
+                raise ValueError(f"job {i}: bpm_classify_peaks rejected its arguments (code {status[i]})")
+        return [_unpack(outs[i].contents) for i in range(n)]
+    finally:
+        for i in range(n):
+            if outs[i]:
+                lib.bpm_classification_free(outs[i])
 
 
 def classify_peaks(self) -> Tuple[np.ndarray, np.ndarray, Dict]:

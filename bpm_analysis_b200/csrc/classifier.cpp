@@ -18,7 +18,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -100,6 +102,20 @@ void put_f(std::string& s, double v, int prec) {
 }
 void put_pct0(std::string& s, double v) { put_f(s, v * 100.0, 0); s += '%'; }
 
+// Debug text that is only assembled when the caller wants it (BPM_CLASSIFY_NO_TEXT skips every
+// append and every number formatting; the decisions never read the text).
+struct Text {
+  std::string s;
+  bool on = true;
+  explicit Text(bool enabled) : on(enabled) {}
+  Text& operator=(const char* c) { if (on) s = c; return *this; }
+  Text& operator+=(const char* c) { if (on) s += c; return *this; }
+  Text& operator+=(const std::string& c) { if (on) s += c; return *this; }
+  Text& operator+=(const Text& c) { if (on) s += c.s; return *this; }
+};
+void put_f(Text& t, double v, int prec) { if (t.on) put_f(t.s, v, prec); }
+void put_pct0(Text& t, double v) { if (t.on) put_pct0(t.s, v); }
+
 struct Classifier {
   const double* env; const double* floor; const int64_t* peaks; int64_t n;
   const double* dev_t; const double* dev_v; int64_t n_dev;
@@ -111,11 +127,13 @@ struct Classifier {
   std::vector<double> hist_t, hist_v;
   std::vector<BpmClassifierEvent> events;
   double lt_bpm; int64_t consecutive = 0; int64_t loop_idx = 0;
+  bool want_text;
 
   Classifier(const double* e, const double* f, const int64_t* pk, int64_t n_, const double* dt, const double* dv,
              int64_t nd, double sr_, const BpmClassifierParams& pr)
       : env(e), floor(f), peaks(pk), n(n_), dev_t(dt), dev_v(dv), n_dev(nd), sr(sr_), p(pr),
-        type(static_cast<size_t>(n_), BPM_PEAK_UNSET), text(static_cast<size_t>(n_)), lt_bpm(pr.start_bpm) {}
+        type(static_cast<size_t>(n_), BPM_PEAK_UNSET), text(static_cast<size_t>(n_)), lt_bpm(pr.start_bpm),
+        want_text((pr.flags & BPM_CLASSIFY_NO_TEXT) == 0) {}
 
   double strength(int64_t pos) const {                                  // max(0, env[i] - floor.iloc[i])
     const int64_t i = peaks[pos];
@@ -166,7 +184,7 @@ struct Classifier {
   }
 
   // :1147-1202
-  double adjust_confidence(double confidence, int64_t s1, int64_t s2, double ratio, std::string& reason) const {
+  double adjust_confidence(double confidence, int64_t s1, int64_t s2, double ratio, Text& reason) const {
     if (static_cast<int64_t>(cand.size()) >= 5) {
       const double xp[2] = {0.0, 1.0}, fp[2] = {p.stability_confidence_floor, p.stability_confidence_ceiling};
       const double factor = np_interp(ratio, xp, fp, 2);
@@ -204,7 +222,7 @@ struct Classifier {
   }
 
   // :231-269
-  bool attempt_pairing(int64_t s1, int64_t s2, double ratio, std::string& reason) const {
+  bool attempt_pairing(int64_t s1, int64_t s2, double ratio, Text& reason) const {
     const double interval = static_cast<double>(peaks[s2] - peaks[s1]) / sr;
     const double deviation = series_asof(dev_t, dev_v, n_dev, static_cast<double>(peaks[s1]) / sr);
     double confidence = blended_confidence(deviation, lt_bpm);
@@ -234,7 +252,7 @@ struct Classifier {
   }
 
   // :1206-1242
-  double lone_s1_confidence(int64_t cur, int64_t last, std::string& reason) const {
+  double lone_s1_confidence(int64_t cur, int64_t last, Text& reason) const {
     const double expected_rr = 60.0 / lt_bpm;
     const double actual_rr = static_cast<double>(peaks[cur] - peaks[last]) / sr;
     const double dev_pct = std::fabs(actual_rr - expected_rr) / expected_rr;
@@ -252,16 +270,17 @@ struct Classifier {
     return (rhythm * p.lone_s1_rhythm_weight) + (amplitude * p.lone_s1_amplitude_weight);
   }
 
-  // :304-329
-  bool validate_lone_s1(int64_t cur, std::string& detail) const {
-    if (cand.empty()) { detail = "First beat"; return true; }
-    std::string reason;
+  // :304-329.  0 = valid, 1 = rejected on confidence (the detail then contains "Rhythm Fit", which is
+  // what the caller's substring test at :286 looks for), 2 = rejected by the forward check
+  int validate_lone_s1(int64_t cur, Text& detail) const {
+    if (cand.empty()) { detail = "First beat"; return 0; }
+    Text reason(want_text);
     const double confidence = lone_s1_confidence(cur, cand.back(), reason);
     const double thr = p.lone_s1_confidence_threshold;
     if (confidence < thr) {
       detail = "Rejected Lone S1: Confidence "; put_f(detail, confidence, 2);
       detail += " < Threshold "; put_f(detail, thr, 2); detail += ". ("; detail += reason; detail += ")";
-      return false;
+      return 1;
     }
     if (cur < n - 1) {
       const int64_t i = peaks[cur], nx = peaks[cur + 1];
@@ -271,7 +290,7 @@ struct Classifier {
       if (forward < min_forward && !(env[i] > (env[nx] * 1.7))) {
         const double implied = forward > 0 ? 60.0 / forward : HUGE_VAL;
         detail = "Rejected Lone S1: Forward check failed (Implies "; put_f(detail, implied, 0); detail += " BPM)";
-        return false;
+        return 2;
       }
     }
     detail = "Validated Lone S1: Confidence "; put_f(detail, confidence, 3);
@@ -279,35 +298,39 @@ struct Classifier {
     detail += ", Weights: Rhythm="; put_f(detail, p.lone_s1_rhythm_weight, 2);
     detail += ", Amplitude="; put_f(detail, p.lone_s1_amplitude_weight, 2);
     detail += ", Final="; put_f(detail, confidence, 3); detail += ")";
-    return true;
+    return 0;
   }
 
   // :271-302
-  void classify_lone_peak(int64_t cur, const std::string& fail_reason) {
-    std::string detail;
-    const bool valid = validate_lone_s1(cur, detail);
-    size_t skip = 0;                                                    // reason.lstrip(' |')
-    while (skip < fail_reason.size() && (fail_reason[skip] == ' ' || fail_reason[skip] == '|')) ++skip;
-    std::string info = std::string("PAIRING_FAIL_REASON") + SEP + fail_reason.substr(skip);
+  void classify_lone_peak(int64_t cur, const Text& fail_reason) {
+    Text detail(want_text);
+    const int verdict = validate_lone_s1(cur, detail);
+    std::string info;
+    if (want_text) {
+      size_t skip = 0;                                                  // reason.lstrip(' |')
+      const std::string& fr = fail_reason.s;
+      while (skip < fr.size() && (fr[skip] == ' ' || fr[skip] == '|')) ++skip;
+      info = std::string("PAIRING_FAIL_REASON") + SEP + fr.substr(skip);
+    }
     std::string& out = text[cur];
-    if (valid) {
+    if (verdict == 0) {
       cand.push_back(cur);
       type[cur] = BPM_PEAK_LONE_S1;
-      out = std::string("Lone S1") + SEP + info + SEP + "LONE_S1_VALIDATE_REASON" + SEP + detail;
+      if (want_text) out = std::string("Lone S1") + SEP + info + SEP + "LONE_S1_VALIDATE_REASON" + SEP + detail.s;
       consecutive = 0;
       return;
     }
-    if (detail.find("Rhythm Fit") != std::string::npos) consecutive += 1; else consecutive = 0;
-    const std::string reject = std::string("LONE_S1_REJECT_REASON") + SEP + detail;
+    if (verdict == 1) consecutive += 1; else consecutive = 0;           // "Rhythm Fit" in rejection_detail
+    const std::string reject = want_text ? std::string("LONE_S1_REJECT_REASON") + SEP + detail.s : std::string();
     if (static_cast<double>(consecutive) >= p.cascade_reset_trigger_count) {
       events.push_back({BPM_EVENT_CASCADE_RESET, static_cast<int32_t>(cur), 0, 0});
       cand.push_back(cur);
       type[cur] = BPM_PEAK_LONE_S1_CASCADE;
-      out = std::string("Lone S1 (Corrected by Cascade Reset)") + SEP + info + SEP + reject;
+      if (want_text) out = std::string("Lone S1 (Corrected by Cascade Reset)") + SEP + info + SEP + reject;
       consecutive = 0;
     } else {
       type[cur] = BPM_PEAK_NOISE;
-      out = std::string("Noise") + SEP + info + SEP + reject;
+      if (want_text) out = std::string("Noise") + SEP + info + SEP + reject;
     }
   }
 
@@ -315,12 +338,16 @@ struct Classifier {
   void process_peak_pair(int64_t cur) {
     const int64_t next = cur + 1;
     const double ratio = pairing_ratio();
-    std::string reason;
+    Text reason(want_text);
     if (attempt_pairing(cur, next, ratio, reason)) {
       cand.push_back(cur);
-      const std::string tag = std::string(SEP) + "PAIRING_SUCCESS_REASON" + SEP + reason;
-      type[cur] = BPM_PEAK_S1_PAIRED; text[cur] = "S1 (Paired)" + tag;
-      type[next] = BPM_PEAK_S2_PAIRED; text[next] = "S2 (Paired)" + tag;
+      type[cur] = BPM_PEAK_S1_PAIRED;
+      type[next] = BPM_PEAK_S2_PAIRED;
+      if (want_text) {
+        const std::string tag = std::string(SEP) + "PAIRING_SUCCESS_REASON" + SEP + reason.s;
+        text[cur] = "S1 (Paired)" + tag;
+        text[next] = "S2 (Paired)" + tag;
+      }
       consecutive = 0;
       loop_idx += 2;
     } else {
@@ -358,7 +385,7 @@ struct Classifier {
       if (loop_idx >= n - 1) {                                          // :170-174
         cand.push_back(cur);
         type[cur] = BPM_PEAK_LONE_S1_LAST;
-        text[cur] = "Lone S1 (Last Peak)";
+        if (want_text) text[cur] = "Lone S1 (Last Peak)";
         loop_idx += 1;
       } else {
         process_peak_pair(cur);
@@ -443,6 +470,35 @@ int bpm_classify_peaks(const double* envelope, const double* noise_floor, int64_
   } catch (...) {
     return BPM_HOST_ERR_ARG;
   }
+}
+
+int bpm_classify_peaks_batch(const BpmClassifyJob* jobs, int64_t n_jobs, int n_threads, BpmClassification** out,
+                             int* status) {
+  if (!jobs || !out || !status || n_jobs < 0) return BPM_HOST_ERR_ARG;
+  if (n_jobs == 0) return BPM_HOST_OK;
+  int64_t workers = n_threads > 0 ? n_threads : static_cast<int64_t>(std::thread::hardware_concurrency());
+  if (workers < 1) workers = 1;
+  if (workers > n_jobs) workers = n_jobs;
+  std::atomic<int64_t> next{0};
+  auto work = [&]() {
+    for (;;) {
+      const int64_t i = next.fetch_add(1);
+      if (i >= n_jobs) return;
+      const BpmClassifyJob& j = jobs[i];
+      out[i] = nullptr;
+      status[i] = bpm_classify_peaks(j.envelope, j.noise_floor, j.m, j.raw_peaks, j.n_peaks, j.dev_times, j.dev_values,
+                                     j.n_dev, j.sample_rate, j.params, &out[i]);
+    }
+  };
+  try {
+    std::vector<std::thread> pool;
+    for (int64_t t = 1; t < workers; ++t) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+  } catch (...) {
+    return BPM_HOST_ERR_NOMEM;
+  }
+  return BPM_HOST_OK;
 }
 
 void bpm_classification_free(BpmClassification* c) {

@@ -73,8 +73,13 @@ typedef struct {
   int32_t has_recovery_window;
   int32_t enable_interval_penalty;          /* :249 */
   int32_t stability_history_window;         /* :135, :180 */
-  int32_t reserved;
+  int32_t flags;                            /* BPM_CLASSIFY_* */
 } BpmClassifierParams;
+
+/* flags: skip the per-peak debug strings (text_bytes = n_peaks NULs).  Decisions, beats, types,
+ * the BPM trace and the events are unchanged -- e.g. for the preliminary pass, whose strings the
+ * reference throws away (bpm_analysis.py:1635), or for batch services that only want beats. */
+#define BPM_CLASSIFY_NO_TEXT 1
 
 /* things the reference reports through logging.info while classifying */
 enum { BPM_EVENT_KICKSTART = 1, BPM_EVENT_CASCADE_RESET = 2 };
@@ -124,6 +129,25 @@ int bpm_classify_peaks(const double* envelope, const double* noise_floor, int64_
                        double sample_rate, const BpmClassifierParams* params,
                        BpmClassification** out);
 void bpm_classification_free(BpmClassification* c);
+
+/* A batch of independent recordings, one per host thread (the loop inside a recording is
+ * sequential; recordings are not).  Job i is classified exactly as bpm_classify_peaks would;
+ * status[i] receives its return code and out[i] its result (NULL on error), each released with
+ * bpm_classification_free.  n_threads <= 0: one thread per hardware thread, at most n_jobs. */
+typedef struct {
+  const double* envelope;
+  const double* noise_floor;
+  int64_t m;
+  const int64_t* raw_peaks;
+  int64_t n_peaks;
+  const double* dev_times;
+  const double* dev_values;
+  int64_t n_dev;
+  double sample_rate;
+  const BpmClassifierParams* params;
+} BpmClassifyJob;
+int bpm_classify_peaks_batch(const BpmClassifyJob* jobs, int64_t n_jobs, int n_threads,
+                             BpmClassification** out, int* status);
 
 /* ---- correction passes over the classified beat list ----------
  * The loops of correct_peaks_by_rhythm (bpm_analysis.py:1257-1306) and

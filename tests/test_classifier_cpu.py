@@ -57,6 +57,7 @@ def test_host_library_exports_header_symbols():
         assert hasattr(lib, name), name
     assert classifier.load_host_library().bpm_host_abi_version() == classifier.HOST_ABI_VERSION
     assert ctypes.sizeof(classifier.ClassifierParams) == 28 * 8 + 4 * 4
+    assert ctypes.sizeof(classifier.ClassifyJob) == 10 * 8
 
 
 def test_fixed_point_formatter_matches_python():
@@ -198,6 +199,36 @@ def test_live_reference_adversarial_inputs(caplog):
             want = run_reference(ref, case)
         got, _ = run_ours(case, caplog)
         assert_same(got, want, f"seed {seed} mode {mode}")
+
+
+def _job(case, with_text=True):
+    hint = case["start_bpm"]
+    packed = classifier.pack_params(case["params"], float(hint) if hint else 80.0, case["peak_time"],
+                                    case["recovery_time"], with_text=with_text)
+    return (case["env"], case["floor"], case["peaks"], case["dev_index"], case["dev_values"], case["rate"], packed)
+
+
+def test_no_text_mode_and_threaded_batch_give_the_same_decisions():
+    """BPM_CLASSIFY_NO_TEXT only drops the strings; bpm_classify_peaks_batch (one recording per host
+    thread) returns for every job what the single call returns."""
+    cases = [make_case(seed) for seed in range(40, 64)]
+    single = [classifier.classify_arrays(*_job(c)) for c in cases]
+    for n_threads in (1, 4, 0):
+        batch = classifier.classify_batch([_job(c) for c in cases], n_threads=n_threads)
+        for a, b in zip(single, batch):
+            assert a["texts"] == b["texts"] and a["events"] == b["events"]
+            for k in ("beat_positions", "peak_types", "history_times", "history_bpm"):
+                assert np.array_equal(a[k], b[k]), k
+    quiet = classifier.classify_batch([_job(c, with_text=False) for c in cases], n_threads=3)
+    for a, b in zip(single, quiet):
+        assert all(t == "" for t in b["texts"]) and len(b["texts"]) == len(a["texts"])
+        assert a["events"] == b["events"] and a["final_long_term_bpm"] == b["final_long_term_bpm"]
+        for k in ("beat_positions", "peak_types", "history_times", "history_bpm"):
+            assert np.array_equal(a[k], b[k]), k
+    bad = list(_job(cases[0]))
+    bad[2] = bad[2][::-1].copy()                                        # descending peaks
+    with pytest.raises(ValueError, match="job 1"):
+        classifier.classify_batch([_job(cases[1]), tuple(bad)], n_threads=2)
 
 
 def test_install_rebinds_classify_peaks():
