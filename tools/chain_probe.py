@@ -5,11 +5,12 @@
   a1 preprocess -> a2 noise floor -> preliminary classifier pass (threshold 0.75) -> start BPM /
   recovery window -> main classifier pass -> correction passes -> BPM series, slopes, HRV.
 
-    python tools/chain_probe.py [duration_sec] [sample_rate] [--cpu-oracle]
+    python tools/chain_probe.py [duration_sec] [sample_rate]
 
-Default: the GPU front end (frontend.py -> libbpm_b200.so) + the compiled sequential stage
-(libbpm_host.so).  --cpu-oracle: the same chain with the CPU oracle as front end (dry run on a
-machine without a GPU; also the "before" column).  Prints one JSON line.
+The GPU front end (frontend.py -> libbpm_b200.so) + the compiled sequential stage
+(libbpm_host.so).  Prints one JSON line.  The same chain with the CPU oracle as front end (the
+"before" column, and a dry run on a machine without a GPU) is tests/chain_probe_cpu_oracle.py,
+which reuses run() below -- only tests/ may import oracle/.
 """
 import json
 import os
@@ -34,49 +35,49 @@ class Clf:
         self.state = init_state(self, hint, floor, troughs)
 
 
-def main():
+class GpuFrontEnd:
+    """The drop-in functions of frontend.py, bound to one params dict."""
+
+    label = "gpu"
+
+    def __init__(self, sr, params):
+        import torch
+        from bpm_analysis_b200 import frontend as fe
+        torch.cuda.set_device(0)
+        self.fe, self.sr, self.params = fe, sr, params
+        self.init_state = fe._initialize_state
+        self.metrics = [fe.find_major_hr_inclines, fe.find_major_hr_declines, fe.find_peak_recovery_rate,
+                        fe.find_peak_exertion_rate]
+
+    def preprocess(self, x):
+        env, rate, _, _ = self.fe.preprocess_pcm(x, self.sr, self.params)
+        return env, rate
+
+    def noise_floor(self, env, rate):
+        return self.fe._calculate_dynamic_noise_floor(env, rate, self.params)
+
+    def bpm_series(self, beats, rate):
+        return self.fe.calculate_bpm_series(beats, rate, self.params)
+
+    def hrv(self, beats, rate):
+        return self.fe.calculate_windowed_hrv(beats, rate, self.params)
+
+
+def parse_args():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     dur = float(args[0]) if args else 3600.0
     sr = int(args[1]) if len(args) > 1 else 48000
-    cpu = "--cpu-oracle" in sys.argv
+    return dur, sr
+
+
+def run(front_end_factory):
+    dur, sr = parse_args()
     params = default_params()
     params["save_filtered_wav"] = False
     pcm, sr, _ = synth.config_c2(seed=2, duration_sec=dur) if sr == 48000 else synth.pcg_recording(dur, sr, lambda t: 75.0, 2)
-
-    if cpu:
-        import pandas as pd
-        from oracle import ref_port as fe_mod
-
-        def preprocess(x):
-            env, rate, _ = fe_mod.preprocess_pcm(x, sr, params)
-            return env, rate
-        noise_floor = lambda env, rate: fe_mod.calculate_dynamic_noise_floor(env, rate, params)       # noqa: E731
-
-        def init_state(self, hint, floor, troughs):
-            peaks = fe_mod.find_raw_peaks(self.audio_envelope, self.sample_rate, self.params, floor.values)
-            met = fe_mod.peak_metrics(self.audio_envelope, self.sample_rate, self.params, floor, peaks)
-            return {"analysis_data": {}, "dynamic_noise_floor": floor, "trough_indices": troughs, "all_peaks": peaks,
-                    "smoothed_dev_series": met["smoothed_dev_series"], "long_term_bpm": float(hint) if hint else 80.0,
-                    "candidate_beats": [], "beat_debug_info": {}, "long_term_bpm_history": [],
-                    "consecutive_rr_rejections": 0, "loop_idx": 0}
-        bpm_series = lambda b, rate: fe_mod.calculate_bpm_series(b, rate, params)                     # noqa: E731
-        metrics = [lambda s: fe_mod.find_major_hr_inclines(s), lambda s: fe_mod.find_major_hr_declines(s),
-                   lambda s: fe_mod.find_peak_recovery_rate(s), lambda s: fe_mod.find_peak_exertion_rate(s)]
-        hrv = lambda b, rate: fe_mod.calculate_windowed_hrv(b, rate, params)                          # noqa: E731
-    else:
-        import torch
-        from bpm_analysis_b200 import frontend as fe_mod
-        torch.cuda.set_device(0)
-
-        def preprocess(x):
-            env, rate, _, _ = fe_mod.preprocess_pcm(x, sr, params)
-            return env, rate
-        noise_floor = lambda env, rate: fe_mod._calculate_dynamic_noise_floor(env, rate, params)      # noqa: E731
-        init_state = fe_mod._initialize_state
-        bpm_series = lambda b, rate: fe_mod.calculate_bpm_series(b, rate, params)                     # noqa: E731
-        metrics = [fe_mod.find_major_hr_inclines, fe_mod.find_major_hr_declines, fe_mod.find_peak_recovery_rate,
-                   fe_mod.find_peak_exertion_rate]
-        hrv = lambda b, rate: fe_mod.calculate_windowed_hrv(b, rate, params)                          # noqa: E731
+    F = front_end_factory(sr, params)
+    preprocess, noise_floor, init_state = F.preprocess, F.noise_floor, F.init_state
+    bpm_series, metrics, hrv = F.bpm_series, F.metrics, F.hrv
 
     def chain():
         t = {}
@@ -133,10 +134,10 @@ def main():
     chain()                                                                       # warm-up (allocations, library loads)
     runs = [chain() for _ in range(3)]
     best = min(runs, key=lambda r: r[0]["total"])
-    print(json.dumps({"front_end": "cpu oracle" if cpu else "gpu", "duration_sec": dur, "sample_rate": sr,
+    print(json.dumps({"front_end": F.label, "duration_sec": dur, "sample_rate": sr,
                       "counts": best[1], "ms": {k: round(1e3 * v, 2) for k, v in best[0].items()},
                       "audio_hours_per_sec_whole_chain": dur / 3600.0 / best[0]["total"]}))
 
 
 if __name__ == "__main__":
-    main()
+    run(GpuFrontEnd)
