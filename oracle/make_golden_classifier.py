@@ -97,7 +97,24 @@ def run_reference_corrections(ref, case, classified):
     return out
 
 
+def shipped_vulpine_labels():
+    """The label the reference's OWN shipped run gave every raw peak of ``samples/vulpine``:
+    ``samples/vulpine_Debug_Log.md`` lists each raw peak (and trough) in time order with its label
+    in bold.  -> tests/golden/vulpine_labels.json"""
+    import re
+    from oracle.load_reference import REFERENCE_ROOT
+    log = open(os.path.join(REFERENCE_ROOT, "samples", "vulpine_Debug_Log.md"), encoding="utf-8").read()
+    entries = re.findall(r"## Time: `([0-9.]+)s`\n\*\*(.+?)\*\*", log)
+    peaks = [(float(t), label.rstrip(".")) for t, label in entries if "Trough" not in label]
+    out = os.path.join(REPO, "tests", "golden", "vulpine_labels.json")
+    with open(out, "w") as fh:
+        json.dump({"source": "samples/vulpine_Debug_Log.md", "times": [t for t, _ in peaks],
+                   "labels": [l for _, l in peaks]}, fh)
+    print(f"{out}: {len(peaks)} raw-peak labels")
+
+
 def main():
+    shipped_vulpine_labels()
     ref = load_reference()
     out = {}
     for seed in GOLDEN_SEEDS:

@@ -238,3 +238,45 @@ def test_install_rebinds_classify_peaks():
                 raise AssertionError("not replaced")
     classifier.install(Mod)
     assert Mod.PeakClassifier.classify_peaks is classifier.classify_peaks
+
+
+def test_shipped_vulpine_run_labels_reproduced():
+    """The reference's own shipped artefact for the sequential stage: samples/vulpine_Debug_Log.md
+    labels each of the 1456 raw peaks of samples/vulpine (S1 / S2 / Lone S1 / Noise).  The compiled
+    classifier + correction passes, chained as analyze_wav_file chains them (preliminary pass at
+    0.75 -> start BPM and recovery window -> main pass -> stages 4 and 5) on the reference's own
+    envelope / floor / raw peaks (tests/golden/vulpine.npz), must give every peak the shipped label
+    and the 734 final beats."""
+    import pandas as pd
+    from bpm_analysis_b200 import corrections
+    from bpm_analysis_b200.params import default_params
+    from conftest import load_golden
+    from oracle import ref_port
+    g = load_golden("vulpine")
+    with open(os.path.join(GOLDEN_DIR, "vulpine_labels.json")) as fh:
+        shipped = json.load(fh)
+    env, rate, peaks = g["envelope"], int(g["rate"]), g["raw_peaks"]
+    assert np.allclose(np.array(shipped["times"]), peaks / rate, atol=6e-5) and len(shipped["labels"]) == len(peaks)
+    params = default_params()
+    base = {"env": env, "floor": g["floor"], "peaks": peaks, "dev_index": g["smoothed_dev_index"],
+            "dev_values": g["smoothed_dev_values"], "rate": rate}
+    pre = ClassifierStandIn(dict(base, params=dict(params, pairing_confidence_threshold=0.75), start_bpm=None,
+                                 peak_time=None, recovery_time=None))
+    anchors, _, _ = classifier.classify_peaks(pre)                      # _run_preliminary_pass, :1622-1653
+    assert len(anchors) >= 10
+    start_bpm = 60.0 / np.median(np.diff(anchors) / rate)
+    series, times = ref_port.calculate_bpm_series(anchors, rate, params)
+    peak_t = times[np.argmax(series.to_numpy())]                        # find_recovery_phase, :1612-1620
+    main = ClassifierStandIn(dict(base, params=params, start_bpm=start_bpm, peak_time=peak_t,
+                                  recovery_time=peak_t + 120.0))
+    s1, raw, data = classifier.classify_peaks(main)
+    floor = pd.Series(g["floor"], index=np.arange(len(env)))
+    final = corrections.correct_peaks_by_rhythm(s1, env, rate, params)
+    info = data["beat_debug_info"]
+    for _ in range(5):
+        final, info, made = corrections._fix_rhythmic_discontinuities(final, raw, info, env, floor, params, rate)
+        if made == 0:
+            break
+    labels = [info[p].split("§")[0] for p in raw]
+    assert labels == shipped["labels"]
+    assert np.array_equal(final, g["beats"])
