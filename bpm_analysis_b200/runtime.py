@@ -27,9 +27,11 @@ def require_cuda() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
-# Ops.frontend moves only the kept frames when the decimation is at least this coarse (a strided
-# copy handles ~0.7 G frames/s, a plain copy ~55 GB/s from pinned and ~10 GB/s from pageable memory)
-SPARSE_INGEST_MIN_STRIDE = 40
+# Ops.frontend moves only the kept frames when consecutive kept frames are at least this many bytes
+# apart in the caller's (pageable) array.  Measured on the B200 box for C2: the driver-staged strided
+# copy costs ~11 ns per kept frame, a plain pageable copy ~0.09 ns per byte -> break-even ~128 bytes
+# (stride 64 for mono int16; the reference's defaults give 292 / 318 bytes at 44.1 / 48 kHz).
+SPARSE_INGEST_MIN_PITCH_BYTES = 128
 
 
 def _stream_ptr() -> int:
@@ -320,7 +322,9 @@ class Ops:
             raise ValueError("The length of the input vector x must be greater than padlen, which is 15.")
         m = plan.m(n_in)
         stride = plan.stride
-        if plan.block == 1 and stride >= SPARSE_INGEST_MIN_STRIDE and os.environ.get("BPM_SPARSE_INGEST", "1") != "0":
+        pitch_bytes = stride * channels * pcm.dtype.itemsize
+        if plan.block == 1 and stride > 1 and pitch_bytes >= SPARSE_INGEST_MIN_PITCH_BYTES \
+                and os.environ.get("BPM_SPARSE_INGEST", "1") != "0":
             # decimate-then-filter touches one frame in `stride`: move only those (bpm_copy_frames, a
             # strided 2-D copy straight out of the caller's array) instead of the whole recording;
             # stage A then reads the compact frames with stride 1 -- bit-identical
