@@ -30,7 +30,8 @@ def require_cuda() -> torch.device:
 # Ops.frontend moves only the kept frames when consecutive kept frames are at least this many bytes
 # apart in the caller's (pageable) array.  Measured on the B200 box for C2: the driver-staged strided
 # copy costs ~11 ns per kept frame, a plain pageable copy ~0.09 ns per byte -> break-even ~128 bytes
-# (stride 64 for mono int16; the reference's defaults give 292 / 318 bytes at 44.1 / 48 kHz).
+# (stride 64 for mono int16; the reference's defaults give 292 / 318 bytes at 44.1 / 48 kHz).  Strides
+# under 40 always take the plain copy.
 SPARSE_INGEST_MIN_PITCH_BYTES = 128
 
 
@@ -323,7 +324,7 @@ class Ops:
         m = plan.m(n_in)
         stride = plan.stride
         pitch_bytes = stride * channels * pcm.dtype.itemsize
-        if plan.block == 1 and stride > 1 and pitch_bytes >= SPARSE_INGEST_MIN_PITCH_BYTES \
+        if plan.block == 1 and stride >= 40 and pitch_bytes >= SPARSE_INGEST_MIN_PITCH_BYTES \
                 and os.environ.get("BPM_SPARSE_INGEST", "1") != "0":
             # decimate-then-filter touches one frame in `stride`: move only those (bpm_copy_frames, a
             # strided 2-D copy straight out of the caller's array) instead of the whole recording;
