@@ -14,7 +14,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BPM_B200_LIB") or os.path.join(HERE, "libbpm_b200.so")   # override: diagnostic builds
-ABI_VERSION = 1
+ABI_VERSION = 2
 DESIGN_HEADER_WORDS = 312
 
 PCM_DTYPES = {np.dtype(np.int16): 0, np.dtype(np.int32): 1, np.dtype(np.uint8): 2,
@@ -55,7 +55,7 @@ _SIGNATURES = {
     "bpm_profile_begin": (_I, [_P]),
     "bpm_profile_end": (_I, [C.c_char_p, _Z]),
     "bpm_frontend_workspace_bytes": (_Z, [_L, _I]),
-    "bpm_frontend": (_I, [_P, _I, _I, _P, _P, _I, _L, _P, _L, _I, _P, _P, _P, _P, _Z, _P]),
+    "bpm_frontend": (_I, [_P, _I, _I, _P, _P, _I, _L, _P, _P, _L, _I, _P, _P, _P, _P, _Z, _P]),
     "bpm_debug_wav": (_I, [_P, _P, _P, _P, _I, _P, _P]),
     "bpm_gather_frames": (_I, [_P, _I, _I, _P, _P, _I, _L, _P, _P]),
     "bpm_copy_frames": (_I, [_P, _I, _I, _P, _I, _L, _P, _P]),
@@ -78,7 +78,7 @@ _SIGNATURES = {
     "bpm_steepest_slope": (_I, [_P, _P, _P, _P, _P, _I, _I, _D, _P, _P, _Z, _P]),
     "bpm_windowed_hrv": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "bpm_stage_a_workspace_bytes": (_Z, [_L, _I]),
-    "bpm_stage_a": (_I, [_P, _P, _P, _I, _P, _L, C.POINTER(StageAConfig), C.POINTER(StageAOutputs), _P, _Z, _P]),
+    "bpm_stage_a": (_I, [_P, _P, _P, _I, _P, _P, _L, C.POINTER(StageAConfig), C.POINTER(StageAOutputs), _P, _Z, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -14,6 +14,7 @@ constexpr int SCAN_CHUNK = 8;         // == design.py SCAN_CHUNK
 constexpr int SCAN_THREADS = 256;     // == design.py SCAN_THREADS
 constexpr int SCAN_TILE = SCAN_CHUNK * SCAN_THREADS;
 constexpr int N_POW = 16;
+constexpr int MIN_PERIODS = 3;       // rolling(..., min_periods=3), bpm_analysis.py:1085
 
 extern int64_t g_launches;            // counted by BPM_LAUNCH_OK
 extern const char* g_cur_kernel;      // set by BPM_KERNEL just before a launch

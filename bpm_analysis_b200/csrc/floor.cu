@@ -33,8 +33,6 @@ struct KnotTable {
   const double* end;      // value of the last sample of the segment (index t[k+1]-1)
 };
 
-constexpr int MIN_PERIODS = 3;   // bpm_analysis.py:1085
-
 __device__ __forceinline__ long long n_obs_at(long long i, long long m, long long t0, int left, int off) {
   long long hi = i + off; if (hi > m - 1) hi = m - 1;
   long long lo = i - left; if (lo < 0) lo = 0; if (lo < t0) lo = t0;
@@ -1256,6 +1254,27 @@ __global__ void k_floor_modes(const int64_t* __restrict__ n_all, const int64_t* 
   }
 }
 
+// host launchers of the two small kernels above (called from pipeline.cu: every translation unit
+// launches only kernels it defines, so no relocatable device code is needed)
+int sanitize_flags_run(const double* env, const double* draft, const int64_t* troughs, const int64_t* trough_count,
+                       const int* keep_all, const BpmItem* items, const BatchShape& sh, double mult, int draft_by_knot,
+                       unsigned char* flags, cudaStream_t st) {
+  BPM_KERNEL(k_sanitize_flags);
+  k_sanitize_flags<<<dim3(cdiv(sh.max_m / 2 + 2, 256), sh.n_items), 256, 0, st>>>(env, draft, troughs, trough_count,
+                                                                                 keep_all, items, mult, draft_by_knot,
+                                                                                 flags);
+  BPM_LAUNCH_OK();
+  return BPM_OK;
+}
+
+int floor_modes_run(const int64_t* n_all, const int64_t* n_kept, int n_items, int stage, int* few, int* mode,
+                    cudaStream_t st) {
+  BPM_KERNEL(k_floor_modes);
+  k_floor_modes<<<cdiv(n_items, 128), 128, 0, st>>>(n_all, n_kept, n_items, stage, few, mode);
+  BPM_LAUNCH_OK();
+  return BPM_OK;
+}
+
 // ------------------------------------------------------------------ host side
 struct FloorBuffers {
   int* kt32;
@@ -1331,3 +1350,12 @@ int rolling_floor_run(const double* env, const int64_t* knots, const int64_t* kn
 }
 
 }  // namespace bpm
+
+#ifdef BPM_DEBUG_COUNTERS
+extern "C" int bpm_debug_counters(unsigned long long* out_host, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out_host, bpm::g_dbg, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(bpm::g_dbg, z, sizeof(z)); }
+  return 0;
+}
+#endif

@@ -10,8 +10,9 @@ namespace bpm {
 // filter.cu
 size_t frontend_workspace_bytes(int64_t total_m, int n_items);
 int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* items, const BpmItem* items_host,
-                 int n_items, int64_t stride, const double* design, int64_t design_words, int block,
-                 int env_window, double* filtered, double* envelope, double* absmax, Workspace& ws, cudaStream_t st);
+                 int n_items, int64_t stride, const double* design, const double* design_host, int64_t design_words,
+                 int block, int env_window, double* filtered, double* envelope, double* absmax, Workspace& ws,
+                 cudaStream_t st);
 int debug_wav_run(const double* filtered, const double* absmax, const BpmItem* items, const BpmItem* items_host,
                   int n_items, int16_t* out, cudaStream_t st);
 int gather_frames_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* items, const BpmItem* items_host,
@@ -37,9 +38,11 @@ int rolling_floor_run(const double* env, const int64_t* knots, const int64_t* kn
                       const BatchShape& sh, int window, double q, const int* mode, const int64_t* alt_knots,
                       const int64_t* alt_count, const double* cval, const double* nan_fill, double* out,
                       double* sparse_out, Workspace& ws, cudaStream_t st);
-__global__ void k_sanitize_flags(const double*, const double*, const int64_t*, const int64_t*, const int*,
-                                 const BpmItem*, double, int, unsigned char*);
-__global__ void k_floor_modes(const int64_t*, const int64_t*, int, int, int*, int*);
+int sanitize_flags_run(const double* env, const double* draft, const int64_t* troughs, const int64_t* trough_count,
+                       const int* keep_all, const BpmItem* items, const BatchShape& sh, double mult, int draft_by_knot,
+                       unsigned char* flags, cudaStream_t st);
+int floor_modes_run(const int64_t* n_all, const int64_t* n_kept, int n_items, int stage, int* few, int* mode,
+                    cudaStream_t st);
 // metrics.cu
 int peak_metrics_run(const double* env, const double* floor_, const int64_t* peaks, const int64_t* peak_count,
                      const BpmItem* items, const BatchShape& sh, double factor, double* strength,
@@ -146,9 +149,7 @@ int noise_floor_run(const double* env, const BpmItem* items, const BatchShape& s
                            fj.join_event()));                                                        // :1070
     if (fj.active && cudaGetLastError() != cudaSuccess) return BPM_ERR_CUDA;
   }
-  BPM_KERNEL(k_floor_modes);
-  k_floor_modes<<<cdiv(n, 128), 128, 0, st>>>(s.n_all, nullptr, n, 0, s.few, s.mode);
-  BPM_LAUNCH_OK();
+  BPM_TRY(floor_modes_run(s.n_all, nullptr, n, 0, s.few, s.mode, st));
   // draft floor from all troughs (:1081-1086).  It is only ever read AT the troughs (:1093), so it
   // is computed there only (one value per trough) whenever the block-cooperative kernel applies.
   const bool sparse = rolling_floor_sparse_ok(window);
@@ -157,16 +158,11 @@ int noise_floor_run(const double* env, const BpmItem* items, const BatchShape& s
     BPM_TRY(rolling_floor_run(env, s.all_troughs, s.n_all, items, sh, window, floor_q, s.mode, nullptr, nullptr, s.q_nf,
                               nullptr, sparse ? nullptr : s.draft, sparse ? s.draft : nullptr, w, st));
   }
-  BPM_KERNEL(k_sanitize_flags);
-  k_sanitize_flags<<<dim3(cdiv(sh.max_m / 2 + 2, 256), n), 256, 0, st>>>(env, s.draft, s.all_troughs, s.n_all,
-                                                                        s.few, items, mult, sparse ? 1 : 0,
-                                                                        s.keep);                         // :1090-1097
-  BPM_LAUNCH_OK();
+  BPM_TRY(sanitize_flags_run(env, s.draft, s.all_troughs, s.n_all, s.few, items, sh, mult, sparse ? 1 : 0, s.keep,
+                             st));                                                                   // :1090-1097
   BPM_TRY(compact_run(s.keep, s.all_troughs, items, sh, s.n_all, sh.max_m / 2 + 2, false, s.tile_counts,
                       troughs_out, trough_count, st));
-  BPM_KERNEL(k_floor_modes);
-  k_floor_modes<<<cdiv(n, 128), 128, 0, st>>>(s.n_all, trough_count, n, 1, s.few, s.mode);
-  BPM_LAUNCH_OK();
+  BPM_TRY(floor_modes_run(s.n_all, trough_count, n, 1, s.few, s.mode, st));
   {
     // final floor from the kept troughs (:1102-1106); when <= 2 are kept the reference reuses the
     // draft (:1107-1110) = the same rolling quantile over ALL troughs, recomputed here (mode 1
@@ -196,10 +192,7 @@ int sanitize_run(const double* env, const double* draft, const int64_t* troughs,
   unsigned char* keep = ws.take<unsigned char>(sh.total_m);
   int* tile_counts = ws.take<int>(sh.total_m / 2048 + sh.n_items + 1);
   if (ws.overflow) return BPM_ERR_WORKSPACE;
-  BPM_KERNEL(k_sanitize_flags);
-  k_sanitize_flags<<<dim3(cdiv(sh.max_m / 2 + 2, 256), sh.n_items), 256, 0, st>>>(env, draft, troughs, trough_count,
-                                                                                 nullptr, items, mult, 0, keep);
-  BPM_LAUNCH_OK();
+  BPM_TRY(sanitize_flags_run(env, draft, troughs, trough_count, nullptr, items, sh, mult, 0, keep, st));
   return compact_run(keep, troughs, items, sh, trough_count, sh.max_m / 2 + 2, false, tile_counts, kept_out,
                      kept_count, st);
 }
@@ -277,20 +270,6 @@ const char* bpm_error_string(int code) {
 
 int64_t bpm_launch_count(void) { return g_launches; }
 
-#ifdef BPM_DEBUG_COUNTERS
-int bpm_debug_counters_scan(unsigned long long* out_host, int reset) {
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out_host, g_dbg_scan, sizeof(unsigned long long) * 16);
-  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_dbg_scan, z, sizeof(z)); }
-  return 0;
-}
-int bpm_debug_counters(unsigned long long* out_host, int reset) {
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out_host, g_dbg, sizeof(unsigned long long) * 16);
-  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_dbg, z, sizeof(z)); }
-  return 0;
-}
-#endif
 
 int bpm_profile_begin(void* stream) {
   g_prof_used = 0;
@@ -324,19 +303,19 @@ int bpm_profile_end(char* text, size_t cap) {
 size_t bpm_frontend_workspace_bytes(int64_t total_m, int n_items) { return frontend_workspace_bytes(total_m, n_items); }
 
 int bpm_frontend(const void* pcm, int pcm_dtype, int channels, const BpmItem* items, const BpmItem* items_host,
-                 int n_items, int64_t stride, const double* design, int64_t design_words, int env_window,
-                 double* filtered, double* envelope, double* absmax, void* workspace, size_t workspace_bytes,
-                 void* stream) {
+                 int n_items, int64_t stride, const double* design, const double* design_host, int64_t design_words,
+                 int env_window, double* filtered, double* envelope, double* absmax, void* workspace,
+                 size_t workspace_bytes, void* stream) {
   if (!workspace || n_items <= 0 || !items_host) return BPM_ERR_ARG;
   // block length is word 0 of the design image; the caller states it through items' m
   // (validated in frontend_run), so read it from the host-visible relation m = ceil(n_dec / block)
   Workspace ws(workspace, workspace_bytes);
   // block is passed implicitly: design_words = header + 4 * (2 * block + 1)
-  const int64_t rem = design_words - BPM_DESIGN_HEADER_WORDS;
+  const int64_t rem = design_words - BPM_DESIGN_HEADER_WORDS - BPM_DESIGN_LANE_WORDS;
   if (rem < 28 || (rem - 12) % 16 != 0) return BPM_ERR_ARG;
   const int block = static_cast<int>((rem - 12) / 16);
-  return frontend_run(pcm, pcm_dtype, channels, items, items_host, n_items, stride, design, design_words, block,
-                      env_window, filtered, envelope, absmax, ws, static_cast<cudaStream_t>(stream));
+  return frontend_run(pcm, pcm_dtype, channels, items, items_host, n_items, stride, design, design_host, design_words,
+                      block, env_window, filtered, envelope, absmax, ws, static_cast<cudaStream_t>(stream));
 }
 
 int bpm_gather_frames(const void* pcm, int pcm_dtype, int channels, const BpmItem* items, const BpmItem* items_host,
@@ -501,8 +480,8 @@ size_t bpm_stage_a_workspace_bytes(int64_t total_m, int n_items) {
 }
 
 int bpm_stage_a(const void* pcm, const BpmItem* items, const BpmItem* items_host, int n_items, const double* design,
-                int64_t design_words, const BpmStageAConfig* cfg, const BpmStageAOutputs* out, void* workspace,
-                size_t workspace_bytes, void* stream) {
+                const double* design_host, int64_t design_words, const BpmStageAConfig* cfg,
+                const BpmStageAOutputs* out, void* workspace, size_t workspace_bytes, void* stream) {
   if (!workspace || !items_host || !cfg || !out || n_items <= 0) return BPM_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const BatchShape sh = batch_shape(items_host, n_items);
@@ -512,10 +491,10 @@ int bpm_stage_a(const void* pcm, const BpmItem* items, const BpmItem* items_host
   {
     Workspace ws(top.base + top.used, top.cap - top.used);
     BPM_TRY(frontend_run(pcm, cfg->pcm_dtype, cfg->channels, items, items_host, n_items, cfg->stride, design,
-                         design_words, static_cast<int>(cfg->block), cfg->env_window, out->filtered, out->envelope,
-                         out->absmax, ws, st));
+                         design_host, design_words, static_cast<int>(cfg->block), cfg->env_window, out->filtered,
+                         out->envelope, out->absmax, ws, st));
   }
-  if (cfg->want_debug_wav && out->debug_wav)
+  if (cfg->want_debug_wav && out->debug_wav && out->filtered)
     BPM_TRY(debug_wav_run(out->filtered, out->absmax, items, items_host, n_items, out->debug_wav, st));
   {
     Workspace ws(top.base + top.used, top.cap - top.used);

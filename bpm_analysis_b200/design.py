@@ -119,6 +119,7 @@ class BlockFilterDesign:
     wf: np.ndarray             # (block, 4)
     q: np.ndarray              # (block + 1, 4)
     pow_chunk: np.ndarray      # (N_POW, 4, 4)  Ad^(SCAN_CHUNK * 2^k)
+    pow_lane: np.ndarray       # (32, 4, 4)     Ad^(SCAN_CHUNK * l), l = 0..31 (start state of lane l's chunk)
     lookback_tiles: int        # how many preceding scan tiles still matter at 1e-22
     spectral_radius: float     # of A (per input sample)
 
@@ -130,7 +131,8 @@ class BlockFilterDesign:
         wq8 = np.concatenate([np.vstack([self.wf, np.zeros((1, 4))]), self.q], axis=1)
         return np.concatenate([head, self.sos.ravel(), self.zi, self.C, self.Ad.ravel(),
                                self.P.ravel(), self.pow_chunk.ravel(),
-                               self.wf.ravel(), self.q.ravel(), wq8.ravel()]).astype(np.float64)
+                               self.wf.ravel(), self.q.ravel(), wq8.ravel(),
+                               self.pow_lane.ravel()]).astype(np.float64)
 
 
 def _matpow(M, e: int):
@@ -177,6 +179,7 @@ def design_block_filter(low: float, high: float, block: int) -> BlockFilterDesig
             q[l] += g * h[m - 1 - l]
     exps = [SCAN_CHUNK * (1 << k) for k in range(N_POW)]
     pows = np.stack([_matpow(Ad, e) for e in exps])
+    lane_pows = np.stack([_matpow(Ad, SCAN_CHUNK * l) for l in range(32)])
     rho = float(np.max(np.abs(np.linalg.eigvals(A.astype(np.float64)))))
     per_tile = rho ** (block * SCAN_TILE)
     if per_tile <= 0.0:
@@ -185,5 +188,5 @@ def design_block_filter(low: float, high: float, block: int) -> BlockFilterDesig
         look = max(1, int(math.ceil(math.log(1e-22) / math.log(per_tile)))) if per_tile < 1.0 else 1 << 30
     f = lambda x: np.asarray(x, dtype=np.float64)
     return BlockFilterDesign(block=int(block), sos=sos, zi=f(zi), C=f(C), D=float(D), Ad=f(Ad), P=f(P),
-                             wf=f(wf), q=f(q), pow_chunk=f(pows), lookback_tiles=int(min(look, 1 << 30)),
+                             wf=f(wf), q=f(q), pow_chunk=f(pows), pow_lane=f(lane_pows), lookback_tiles=int(min(look, 1 << 30)),
                              spectral_radius=rho)

@@ -9,6 +9,8 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
+from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -76,6 +78,8 @@ class FilterPlan:
     block: int           # filter outputs skipped (1 in 'parity', ds in 'fullrate')
     clamped: bool
     design: object       # BlockFilterDesign
+    low: float = 0.0     # band edges as fractions of Nyquist at the rate the filter runs at
+    high: float = 0.0
 
     def n_dec(self, n_in: int) -> int:
         return (n_in + self.stride - 1) // self.stride
@@ -94,24 +98,43 @@ def plan_filter(sample_rate: int, params: Dict) -> FilterPlan:
         if hi >= 1.0:                                           # bpm_analysis.py:1041-1042
             raise ValueError(f"Cannot create a {int(highcut) if float(highcut).is_integer() else highcut}Hz "
                              f"filter. The effective sample rate of {rate}Hz is too low.")
-        return FilterPlan(sample_rate, ds, rate, ds, 1, clamped, design_block_filter(lo, hi, 1))
+        return FilterPlan(sample_rate, ds, rate, ds, 1, clamped, design_block_filter(lo, hi, 1), lo, hi)
     nyq = 0.5 * sample_rate
     lo, hi = lowcut / nyq, highcut / nyq
     if hi >= 1.0:
         raise ValueError(f"Cannot create a {highcut}Hz filter. The sample rate of {sample_rate}Hz is too low.")
-    return FilterPlan(sample_rate, ds, rate, 1, ds, clamped, design_block_filter(lo, hi, ds))
+    return FilterPlan(sample_rate, ds, rate, 1, ds, clamped, design_block_filter(lo, hi, ds), lo, hi)
 
 
-_design_cache: Dict[tuple, torch.Tensor] = {}
+DESIGN_CACHE_SIZE = 64
+_design_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
+_design_lock = threading.Lock()
+
+
+def design_images(plan: FilterPlan):
+    """(device tensor, host array) of the packed design image of ``plan``.
+
+    Cached by VALUE -- (device, band edges, block) -- and bounded (LRU): a long-lived process or a
+    band-edge sweep creates many designs, and an identity key would be reused by CPython after the
+    design object is collected.  The host array is what the decimate-first kernels read (their
+    coefficients travel as launch parameters); an entry keeps both alive while it is cached."""
+    key = (torch.cuda.current_device(), float(plan.low), float(plan.high), int(plan.block))
+    with _design_lock:
+        hit = _design_cache.get(key)
+        if hit is not None:
+            _design_cache.move_to_end(key)
+            return hit
+    host = np.ascontiguousarray(plan.design.packed(), dtype=np.float64)
+    entry = (to_device(host), host)
+    with _design_lock:
+        _design_cache[key] = entry
+        while len(_design_cache) > DESIGN_CACHE_SIZE:
+            _design_cache.popitem(last=False)
+    return entry
 
 
 def design_on_device(plan: FilterPlan) -> torch.Tensor:
-    key = (torch.cuda.current_device(), id(plan.design))
-    t = _design_cache.get(key)
-    if t is None:
-        t = to_device(plan.design.packed())
-        _design_cache[key] = t
-    return t
+    return design_images(plan)[0]
 
 
 def stage_a_config(plan: FilterPlan, params: Dict, pcm_dtype: int, channels: int, want_debug: bool
@@ -208,7 +231,7 @@ class StageARunner:
             if self.ingest == "sm":
                 self.cfg.pcm_dtype, self.cfg.channels = nat.PCM_DTYPES[np.dtype(np.float64)], 1
         self.items_dev = torch.from_numpy(self.items.view(np.int64).reshape(-1, 4).copy()).to(self.device)
-        self.design_dev = design_on_device(self.plan)
+        self.design_dev, self.design_host = design_images(self.plan)
         self.design_words = int(self.design_dev.numel())
         f64 = dict(dtype=torch.float64, device=self.device)
         i64 = dict(dtype=torch.int64, device=self.device)
@@ -283,7 +306,8 @@ class StageARunner:
     def launch(self) -> None:
         """Enqueue a1..a4 on the current stream (no host synchronisation)."""
         rc = self.lib.bpm_stage_a(_ptr(self._pcm_src), _ptr(self.items_dev), _host_ptr(self.items), self.n_items,
-                                  _ptr(self.design_dev), self.design_words, C.byref(self.cfg),
+                                  _ptr(self.design_dev), _host_ptr(self.design_host), self.design_words,
+                                  C.byref(self.cfg),
                                   C.byref(self.outs_struct), _ptr(self.ws), self.ws_bytes, _stream_ptr())
         nat.check(rc)
 
@@ -339,13 +363,14 @@ class Ops:
             items = make_items([n_in], [m])
             pcm_dev = to_device(pcm.reshape(-1))
         items_dev = torch.from_numpy(items.view(np.int64).reshape(-1, 4).copy()).to(self.device)
-        design = design_on_device(plan)
+        design, design_host = design_images(plan)
         f64 = dict(dtype=torch.float64, device=self.device)
         filt, env, amax = torch.empty(m, **f64), torch.empty(m, **f64), torch.empty(1, **f64)
         nb = int(self.lib.bpm_frontend_workspace_bytes(m, 1))
         ws = self._ws(nb)
         nat.check(self.lib.bpm_frontend(_ptr(pcm_dev), nat.PCM_DTYPES[pcm.dtype], channels, _ptr(items_dev),
-                                        _host_ptr(items), 1, stride, _ptr(design), int(design.numel()),
+                                        _host_ptr(items), 1, stride, _ptr(design), _host_ptr(design_host),
+                                        int(design.numel()),
                                         plan.rate // 10, _ptr(filt), _ptr(env), _ptr(amax), _ptr(ws), nb,
                                         _stream_ptr()))
         dbg = None

@@ -217,13 +217,14 @@ class DeviceEngine:
         rt, nat, L = self.rt, self.nat, self.lib
         m = plan.m(n_in)
         items, items_dev = self._items(n_in, m)
-        design = rt.design_on_device(plan)
+        design, design_host = rt.design_images(plan)
         f64 = dict(dtype=torch.float64, device=self.device)
         filt, env, amax = torch.empty(m, **f64), torch.empty(m, **f64), torch.empty(1, **f64)
         nb = int(L.bpm_frontend_workspace_bytes(m, 1))
         ws = self._ws(nb)
         nat.check(L.bpm_frontend(rt._ptr(pcm), nat.PCM_DTYPES[np.dtype(np_dtype)], channels, rt._ptr(items_dev),
-                                 rt._host_ptr(items), 1, plan.stride, rt._ptr(design), int(design.numel()),
+                                 rt._host_ptr(items), 1, plan.stride, rt._ptr(design), rt._host_ptr(design_host),
+                                 int(design.numel()),
                                  plan.rate // 10, rt._ptr(filt), rt._ptr(env), rt._ptr(amax), rt._ptr(ws), nb,
                                  rt._stream_ptr()))
         self._keep = (ws, items_dev)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BPM_ABI_VERSION 1
+#define BPM_ABI_VERSION 2
 
 enum {
   BPM_OK = 0,
@@ -61,8 +61,10 @@ typedef struct {
  *   [312 .. 312+4*block)               wf[block][4]
  *   [312+4*block .. 312+4*(2*block+1))  q[block+1][4]
  *   [312+4*(2*block+1) .. +8*(block+1)) wq8[block+1][8] = (wf[l] | q[l]), wf[block] = 0
- * total words = 312 + 16*block + 12                                               */
+ *   [312+16*block+12 .. +512)           pow_lane[32][4][4] = Ad^(8 l), l = 0..31
+ * total words = 312 + 16*block + 12 + 512                                         */
 #define BPM_DESIGN_HEADER_WORDS 312
+#define BPM_DESIGN_LANE_WORDS 512
 
 int bpm_abi_version(void);
 const char* bpm_error_string(int code);
@@ -72,11 +74,16 @@ const char* bpm_error_string(int code);
  * steady-state zi) evaluated at the kept samples -> |.| -> centred rolling mean.
  *   stride/block: (ds, 1) = the reference's decimate-then-filter order;
  *                 (1, ds) = filter at the original rate, keep every ds-th output.
- *   filtered, envelope: out, float64[total_m];  absmax: out, float64[n_items] = max|filtered|. */
+ *   design / design_host: the same packed design image (layout above) in device and in HOST
+ *   memory; the (stride = ds, block = 1) order passes its coefficients to the kernels as launch
+ *   parameters (constant bank) and reads only design_host, which may then be the only one given.
+ *   filtered, envelope: out, float64[total_m];  absmax: out, float64[n_items] = max|filtered|.
+ *   filtered may be NULL when block == 1 and env_window <= 65 (the envelope is then formed inside
+ *   the backward pass and the band-passed signal never reaches HBM). */
 size_t bpm_frontend_workspace_bytes(int64_t total_m, int n_items);
 int bpm_frontend(const void* pcm, int pcm_dtype, int channels,
                  const BpmItem* items, const BpmItem* items_host, int n_items,
-                 int64_t stride, const double* design, int64_t design_words,
+                 int64_t stride, const double* design, const double* design_host, int64_t design_words,
                  int env_window, double* filtered, double* envelope, double* absmax,
                  void* workspace, size_t workspace_bytes, void* stream);
 
@@ -243,7 +250,8 @@ typedef struct {
 
 size_t bpm_stage_a_workspace_bytes(int64_t total_m, int n_items);
 int bpm_stage_a(const void* pcm, const BpmItem* items, const BpmItem* items_host, int n_items,
-                const double* design, int64_t design_words, const BpmStageAConfig* cfg_host,
+                const double* design, const double* design_host, int64_t design_words,
+                const BpmStageAConfig* cfg_host,
                 const BpmStageAOutputs* out_host, void* workspace, size_t workspace_bytes,
                 void* stream);
 

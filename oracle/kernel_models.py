@@ -86,3 +86,147 @@ def blocked_filtfilt(x: np.ndarray, d: BlockFilterDesign, stride: int = 1) -> np
     xe = ext_sample(x, n_dec, stride, E)
     yf = sf @ d.C + d.D * xe
     return sbv @ d.C + d.D * yf
+
+
+# ----------------------------------------------------------------------------- csrc/sosfilt.cu
+SS_CHUNK, SS_THREADS, SS_HALO = 8, 256, 64
+SS_TILE = SS_CHUNK * SS_THREADS
+
+
+def _matpow(M, e):
+    R = np.eye(4)
+    Bm = M.copy()
+    while e:
+        if e & 1:
+            R = R @ Bm
+        Bm = Bm @ Bm
+        e >>= 1
+    return R
+
+
+def _sos_scan_pass(u: np.ndarray, n_scan: int, d: BlockFilterDesign, part: int, ppart: np.ndarray, lookback: int,
+                   s_init: np.ndarray):
+    """One direction of k_sos_scan over the inputs ``u[0 .. n_scan)`` (scan order), tile by tile, the
+    way the CTAs do it: chunk zero-state responses, inclusive combination inside the tile with the
+    tabulated powers, aggregate after ``part`` samples, look-back over ``lookback`` aggregates.
+    Returns one array of tile outputs per tile (SS_TILE scan positions each, zeros past n_scan)."""
+    pw = d.pow_chunk                                  # A^(8 2^k)
+    tiles = (n_scan + part - 1) // part
+    aggs = np.zeros((tiles, 4))
+    outs = []
+    for b in range(tiles):
+        t0 = b * part
+        x = np.zeros(SS_TILE)
+        nv = min(SS_TILE, n_scan - t0)
+        x[:nv] = u[t0:t0 + nv]
+        # sweep 1: zero-state response of every chunk
+        z = np.zeros((SS_THREADS, 4))
+        for t in range(SS_THREADS):
+            s = np.zeros(4)
+            for c in range(SS_CHUNK):
+                s, _ = _df2t_step(d.sos, s, x[t * SS_CHUNK + c])
+            z[t] = s
+        # inclusive scan inside each warp (shuffle steps with A^(8 2^k))
+        zi = z.copy()
+        for k in range(5):
+            o = 1 << k
+            prev = zi.copy()
+            for t in range(SS_THREADS):
+                if (t & 31) >= o:
+                    zi[t] = pw[k] @ prev[t - o] + prev[t]
+        # warp totals -> zero-start state at the end / start of every warp
+        T = zi[31::32].copy()
+        for k in range(3):
+            o = 1 << k
+            prev = T.copy()
+            for w in range(8):
+                if w >= o:
+                    T[w] = pw[5 + k] @ prev[w - o] + prev[w]
+        pre0 = np.vstack([np.zeros((1, 4)), T[:-1]])
+        pc = part // SS_CHUNK
+        if part == SS_TILE:
+            ag = T[7]
+        else:
+            wq, nq = (pc - 1) >> 5, ((pc - 1) & 31) + 1
+            v = pre0[wq].copy()
+            for k in range(6):
+                if (nq >> k) & 1:
+                    v = pw[k] @ v
+            ag = v + zi[pc - 1]
+        aggs[b] = ag
+        k0 = b - lookback if b > lookback else 0
+        start = s_init.copy() if k0 == 0 else np.zeros(4)
+        for t in range(k0, b):
+            start = ppart @ start + aggs[t]
+        # sweep 2
+        y = np.zeros(SS_TILE)
+        for w in range(8):
+            sp = _matpow(pw[5], w) @ start + pre0[w]
+            for l in range(32):
+                t = 32 * w + l
+                st = d.pow_lane[l] @ sp + (zi[t - 1] if l else 0.0)
+                for c in range(SS_CHUNK):
+                    st, y[t * SS_CHUNK + c] = _df2t_step(d.sos, st, x[t * SS_CHUNK + c])
+        outs.append(y)
+    return outs
+
+
+def sos_filtfilt_envelope(x_kept: np.ndarray, d: BlockFilterDesign, env_window: int):
+    """Model of sosfilt_run (decimate-first order, ``d.block == 1``) on the already decimated
+    samples: returns (filtered, envelope, absmax) as the two k_sos_scan launches produce them."""
+    assert d.block == 1 and env_window - 1 <= SS_HALO
+    m = len(x_kept)
+    n_ext = m + 2 * PADLEN
+    xe = ext_sample(np.asarray(x_kept), m, 1, np.arange(n_ext))
+    K = d.lookback_tiles
+    # forward: part = tile
+    outs = _sos_scan_pass(xe, n_ext, d, SS_TILE, d.pow_chunk[8], K, d.zi * xe[0])
+    yf = np.concatenate(outs)[:n_ext]
+    # backward over y_f reversed, down to the first real sample, aggregates SS_TILE - SS_HALO apart
+    part = SS_TILE - SS_HALO
+    ppart = d.pow_chunk[7]
+    for k in (6, 5, 4, 3):
+        ppart = ppart @ d.pow_chunk[k]
+    n_scan = m + PADLEN
+    Kb = K if K > 900000000 else K + K // 16 + 1
+    outs = _sos_scan_pass(yf[::-1], n_scan, d, part, ppart, Kb, d.zi * yf[-1])
+    w = env_window
+    off = (w - 1) // 2
+    left = w - 1 - off
+    y = np.full(m, np.nan)
+    env = np.full(m, np.nan)
+    for b, yt in enumerate(outs):
+        t0 = b * part
+        jhi = m + (PADLEN - 1) - t0
+        jlo = jhi - (SS_TILE - 1)
+        tile = np.zeros(SS_TILE)                      # ascending tile-local index la; j = jlo + la
+        for sl in range(SS_TILE):
+            j = jhi - sl
+            tile[SS_TILE - 1 - sl] = yt[sl] if 0 <= j < m else 0.0
+        for sl in range(part):
+            j = jhi - sl
+            if 0 <= j < m:
+                assert np.isnan(y[j])
+                y[j] = tile[SS_TILE - 1 - sl]
+        own_hi = m - 1 if b == 0 else jhi - off
+        own_lo = max(0, jhi - off - part + 1)
+        first = jhi - off - part + 1
+        val = lambda la: abs(tile[la]) if la < SS_TILE else 0.0
+        for t in range(SS_THREADS):
+            jb = first + t * SS_CHUNK
+            if jb + SS_CHUNK - 1 < own_lo or jb > own_hi:
+                continue
+            lb = jb - left - jlo
+            assert lb >= 0
+            s = 0.0
+            for q in range(w):
+                s += val(lb + q)
+            for k in range(SS_CHUNK):
+                j = jb + k
+                if own_lo <= j <= own_hi:
+                    wa, wb = max(0, j - left), min(m - 1, j + off)
+                    assert np.isnan(env[j])
+                    env[j] = s / (wb - wa + 1)
+                s = (s + val(lb + k + w)) - val(lb + k)
+    assert not np.any(np.isnan(y)) and not np.any(np.isnan(env))
+    return y, env, float(np.max(np.abs(y)))

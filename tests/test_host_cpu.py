@@ -82,12 +82,35 @@ def test_blocked_model_fullrate_matches_sosfiltfilt():
 def test_design_image_layout():
     d = design.design_block_filter(0.1, 0.9, 7)
     img = d.packed()
-    assert img.shape[0] == _native.DESIGN_HEADER_WORDS + 16 * 7 + 12
+    assert img.shape[0] == _native.DESIGN_HEADER_WORDS + 16 * 7 + 12 + 512
     assert img[0] == 7 and img[2] == d.D
     assert np.array_equal(img[24:40].reshape(4, 4), d.Ad)
     assert np.array_equal(img[312:312 + 28].reshape(7, 4), d.wf)
-    wq8 = img[312 + 4 * 15:].reshape(8, 8)
+    wq8 = img[312 + 4 * 15:312 + 4 * 15 + 64].reshape(8, 8)
     assert np.array_equal(wq8[:7, :4], d.wf) and np.all(wq8[7, :4] == 0) and np.array_equal(wq8[:, 4:], d.q)
+    lane = img[-512:].reshape(32, 4, 4)
+    assert np.array_equal(lane[0], np.eye(4)) and np.array_equal(lane, d.pow_lane)
+    assert np.allclose(lane[4], d.pow_chunk[2], rtol=1e-13, atol=0)        # Ad^(8*4) == Ad^(8*2^2)
+
+
+@pytest.mark.parametrize("dur,sr,w", [(12.0, 44100, None), (60.0, 4000, None), (0.2, 44100, None), (14.0, 48000, 65)])
+def test_sos_scan_model_matches_filtfilt_and_rolling_mean(dur, sr, w):
+    """numpy model of csrc/sosfilt.cu (tiles, partition / halo, look-back, envelope ownership) against
+    scipy.signal.filtfilt + pandas' centred rolling mean (bpm_analysis.py:1044-1054)."""
+    import pandas as pd
+    pcm, sr, _ = synth.pcg_recording(dur, sr, lambda t: 75.0, 11)
+    ds, rate, _ = P.effective_decimation(sr, P.default_params())
+    lo, hi = 20 / (rate / 2), 150 / (rate / 2)
+    d = design.design_block_filter(lo, hi, 1)
+    x = pcm[::ds]
+    w = w or rate // 10
+    y, env, amax = kernel_models.sos_filtfilt_envelope(x, d, w)
+    b, a = butter(2, [lo, hi], btype="band")
+    ref = filtfilt(b, a, x)
+    renv = pd.Series(np.abs(ref)).rolling(window=w, min_periods=1, center=True).mean().values
+    assert np.max(np.abs(y - ref)) < 1e-11 * np.max(np.abs(ref))
+    assert np.max(np.abs(env - renv)) < 1e-11 * np.max(renv)
+    assert amax == np.max(np.abs(y))
 
 
 def test_decimation_plan_matches_reference_arithmetic():
