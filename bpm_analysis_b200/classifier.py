@@ -23,7 +23,7 @@ import pandas as pd
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 HOST_LIB_PATH = os.environ.get("BPM_HOST_LIB") or os.path.join(HERE, "libbpm_host.so")
-HOST_ABI_VERSION = 1
+HOST_ABI_VERSION = 2
 
 PEAK_TYPE_LABELS = {1: "S1 (Paired)", 2: "S2 (Paired)", 3: "Lone S1", 4: "Lone S1 (Corrected by Cascade Reset)",
                     5: "Lone S1 (Last Peak)", 6: "Noise"}
@@ -88,7 +88,7 @@ class Classification(C.Structure):
 
 
 EXPORTED_SYMBOLS = ("bpm_host_abi_version", "bpm_host_format_fixed", "bpm_classify_peaks", "bpm_classify_peaks_batch",
-                    "bpm_classification_free")
+                    "bpm_classification_free", "bpm_host_threads", "bpm_host_gather_frames")
 
 
 class HostLibraryError(RuntimeError):
@@ -120,6 +120,9 @@ def load_host_library(path: str = HOST_LIB_PATH):
         lib.bpm_classify_peaks_batch.restype = C.c_int
         lib.bpm_classify_peaks_batch.argtypes = [C.POINTER(ClassifyJob), C.c_int64, C.c_int,
                                                  C.POINTER(C.POINTER(Classification)), C.POINTER(C.c_int)]
+        lib.bpm_host_threads.restype, lib.bpm_host_threads.argtypes = C.c_int, []
+        lib.bpm_host_gather_frames.restype = C.c_int
+        lib.bpm_host_gather_frames.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int]
         lib.bpm_host_format_fixed.restype = C.c_int
         lib.bpm_host_format_fixed.argtypes = [C.c_double, C.c_int, C.c_char_p, C.c_size_t]
         if lib.bpm_host_abi_version() != HOST_ABI_VERSION:

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define BPM_HOST_ABI_VERSION 1
+#define BPM_HOST_ABI_VERSION 2
 
 enum { BPM_HOST_OK = 0, BPM_HOST_ERR_ARG = -1, BPM_HOST_ERR_NOMEM = -2 };
 
@@ -189,6 +189,17 @@ int bpm_fix_rhythmic_discontinuities(const int64_t* s1_peaks, int64_t n_s1, cons
                                      double waiver_max_s2_s1_ratio, int64_t* out, int64_t* n_out,
                                      BpmCorrectionEvent* events, int64_t events_capacity, int64_t* n_events,
                                      int64_t* corrections_made);
+
+/* ---- ingest -------------------------------------------------------
+ * K0 on the host cores: out[j] = frame j * stride of pcm, j = 0 .. ceil(n_frames / stride) - 1
+ * (audio_data[::downsample_factor], bpm_analysis.py:1033; a frame = all channels of one sample,
+ * frame_bytes = channels * sample size, kept in the PCM's own dtype).  `out` is normally a pinned
+ * staging buffer that one cudaMemcpyAsync then moves to the device, where bpm_frontend / bpm_stage_a
+ * read it with stride 1 -- bit-identical to passing the whole recording with this stride.
+ * n_threads <= 0: all threads of the library's pool (bpm_host_threads()). */
+int bpm_host_threads(void);
+int bpm_host_gather_frames(const void* pcm, int64_t frame_bytes, int64_t n_frames, int64_t stride, void* out,
+                           int n_threads);
 
 #ifdef __cplusplus
 }
