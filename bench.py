@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--no-zero-copy", action="store_true", help="e2e: copy the whole recording to the device first")
     ap.add_argument("--e2e-depth", type=int, default=3, help="e2e: recordings in flight (1 = strictly serial steps)")
-    ap.add_argument("--e2e-ingest", default="ce", choices=["ce", "sm"],
+    ap.add_argument("--e2e-ingest", default="host", choices=["host", "ce", "sm"],
                     help="e2e: kept frames cross PCIe by a strided copy-engine copy (ce) or by a kernel reading mapped "
                          "pinned memory (sm)")
     ap.add_argument("--dump-kernels", default=None, help="write the per-kernel table to this JSON file")
@@ -80,6 +80,11 @@ def bench_params(args):
     p["save_filtered_wav"] = False
     p["filter_mode"] = args.filter_mode
     return p
+
+
+def svc_cap(M: int, A) -> int:
+    """entries per list read-back of a drop-in step (find_peaks distance bounds the list lengths)"""
+    return min(M, M // max(int(A.cfg.distance), 1) + 2)
 
 
 def hr_extrema_distance(beat_idx: np.ndarray, rate: int) -> int:
@@ -172,6 +177,15 @@ def algorithmic_bytes(kernel: str, shp: dict, mode: str = "parity") -> float:
     return float(table.get(kernel, 0.0))
 
 
+PIPE_INGEST = {
+    "host": "bpm_host_gather_frames: the host cores pack the kept frames x[::ds] into pinned staging, one cudaMemcpyAsync "
+            "moves them (h2d bytes = the kept frames); ",
+    "ce": "bpm_copy_frames: the kept frames x[::ds] leave pinned host memory as one strided 2-D copy on the copy engine "
+          "(h2d bytes = the kept frames); ",
+    "sm": "zero-copy: bpm_gather_frames reads the kept frames from pinned host memory (h2d bytes = 32-byte sector per "
+          "kept frame); ",
+}
+
 BEAT_BRANCH_KERNELS = {"k_find_peaks_small", "k_steepest", "k_bpm_instant", "k_bpm_smooth", "k_hrv"}
 
 ROOFLINE_NOTES = {
@@ -202,13 +216,80 @@ def ncu_traffic(kernel: str, mode: str):
         return None
 
 
+# --------------------------------------------------------------------------- parity of the run's own outputs
+def parity_report(got: dict, oracle_out, A) -> dict:
+    """The drop-in step's outputs on the bench recording against the CPU oracle on the same
+    recording ('parity asserted in the same run').  Float signals: max|d| /
+    max|ref| <= 1e-9; index lists and beat-list reductions: exact."""
+    fe, br = oracle_out
+
+    def rel(a, b):
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        if a.shape != b.shape:
+            return float("inf")
+        if a.size == 0:
+            return 0.0
+        return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) or 1.0))
+
+    def same_records(x, y):
+        xs, ys = (x, y) if isinstance(x, list) else ([x], [y])
+        if (x is None) != (y is None) or len(xs) != len(ys):
+            return False
+        if x is None:
+            return True
+        return all(list(p) == list(q) and all((abs(p[k] - q[k]) <= 1e-9 * max(1.0, abs(q[k]))) if isinstance(p[k], float)
+                                              else p[k] == q[k] for k in p) for p, q in zip(xs, ys))
+
+    rep = {"tolerance": 1e-9,
+           "envelope_rel_err": rel(got["envelope"], fe["envelope"]),
+           "floor_rel_err": rel(got["floor"].values, fe["floor"]),
+           "troughs_exact": bool(np.array_equal(got["troughs"], fe["troughs"])),
+           "raw_peaks_exact": bool(np.array_equal(got["peaks"], fe["peaks"]) and np.array_equal(got["prelim_peaks"], fe["peaks"])),
+           "smoothed_deviation_rel_err": rel(got["smoothed_dev"].values, fe["smoothed_dev_series"].values) if "smoothed_dev_series" in fe else None,
+           "bpm_series_index_exact": bool(got["smoothed_bpm"].index.equals(br["smoothed_bpm"].index)),
+           "bpm_series_rel_err": rel(got["smoothed_bpm"].values, br["smoothed_bpm"].values),
+           "slopes_exact": bool(same_records(got["peak_recovery_stats"], br["peak_recovery_stats"]) and
+                                same_records(got["peak_exertion_stats"], br["peak_exertion_stats"])),
+           "inclines_declines_exact": bool(same_records(got["major_inclines"], br["major_inclines"]) and
+                                           same_records(got["major_declines"], br["major_declines"])),
+           "hrv_rel_err": rel(got["windowed_hrv_df"].values, br["windowed_hrv_df"].values),
+           "n_troughs": int(len(fe["troughs"])), "n_raw_peaks": int(len(fe["peaks"])),
+           "n_hrv_rows": int(len(br["windowed_hrv_df"]))}
+    floats = [v for k, v in rep.items() if k.endswith("rel_err") and v is not None]
+    rep["ok"] = bool(all(v <= 1e-9 for v in floats) and all(v for k, v in rep.items() if k.endswith("exact")))
+    return rep
+
+
 # --------------------------------------------------------------------------- CPU side
-def _cpu_one(job):
+def _cpu_one(job, keep: bool = False):
     pcm, sr, beat_idx, params = job
     from oracle import ref_port
     fe = ref_port.front_end(pcm, sr, params)
-    ref_port.beat_reductions(beat_idx, fe["rate"], params)
-    return len(fe["peaks"])
+    br = ref_port.beat_reductions(beat_idx, fe["rate"], params)
+    return (fe, br) if keep else len(fe["peaks"])
+
+
+# ---- the UNMODIFIED reference (baseline/_ref, see baseline/install_ref.sh) on the host cores
+_REF_JOB = None
+
+
+def _reference_one(_):
+    """One recording through the reference's own functions for a1..a8 (bpm_analysis.py:1731-1732,
+    :1635 -> :85-111, :223-229, :1704-1710), WAV file in, pandas objects out."""
+    path, out_dir, beat_idx, params = _REF_JOB
+    from baseline import ref_loader
+    ref = ref_loader.load()
+    env, rate = ref.preprocess_audio(path, params, out_dir)
+    floor, troughs = ref._calculate_dynamic_noise_floor(env, rate, params)
+    clf = ref.PeakClassifier(env, rate, params, None, floor, troughs, None, None)      # _initialize_state + _find_raw_peaks
+    m = {}
+    m["smoothed_bpm"], m["bpm_times"] = ref.calculate_bpm_series(beat_idx, rate, params)
+    m["major_inclines"] = ref.find_major_hr_inclines(m["smoothed_bpm"])
+    m["major_declines"] = ref.find_major_hr_declines(m["smoothed_bpm"])
+    m["peak_recovery_stats"] = ref.find_peak_recovery_rate(m["smoothed_bpm"])
+    m["peak_exertion_stats"] = ref.find_peak_exertion_rate(m["smoothed_bpm"])
+    m["windowed_hrv_df"] = ref.calculate_windowed_hrv(beat_idx, rate, params)
+    return len(clf.state["all_peaks"])
 
 
 _POOL_JOB = None
@@ -218,13 +299,14 @@ def _cpu_pool_worker(_):
     return _cpu_one(_POOL_JOB)
 
 
-def cpu_step(pcm, sr, beat_idx, params, workers: int):
+def cpu_step(pcm, sr, beat_idx, params, workers: int, keep: bool = False):
     """One CPU step: `workers` recordings, one per process (the reference is single-threaded)."""
     global _POOL_JOB
     if workers <= 1:
         t0 = time.perf_counter()
-        _cpu_one((pcm, sr, beat_idx, params))
-        return time.perf_counter() - t0
+        res = _cpu_one((pcm, sr, beat_idx, params), keep)
+        dt = time.perf_counter() - t0
+        return (dt, res) if keep else dt
     import multiprocessing as mp
     _POOL_JOB = (pcm, sr, beat_idx, params)
     ctx = mp.get_context("fork")
@@ -253,27 +335,54 @@ def run_reference(args):
     n = int(sample_sec * sr)
     pcm_s = pcm[:n]
     beat_idx = synth.beats_to_envelope_indices(beats[beats < sample_sec - 1.0], rate)
-    global _POOL_JOB
-    _POOL_JOB = (pcm_s, sr, beat_idx, params)
     import multiprocessing as mp
+    import tempfile
+    from baseline import ref_loader
+    global _POOL_JOB, _REF_JOB
+    use_ref = ref_loader.available() and args.filter_mode == "parity"
+    tmp = None
+    if use_ref:
+        # the reference's entry point reads a WAV file (bpm_analysis.py:1014): the sample is written once,
+        # outside the timed region, to shared memory
+        from scipy.io import wavfile
+        base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+        tmp = tempfile.mkdtemp(prefix="bpm_ref_", dir=base)
+        path = os.path.join(tmp, "sample.wav")
+        wavfile.write(path, sr, pcm_s)
+        ref_params = dict(ref_loader.default_params(), save_filtered_wav=False)
+        _REF_JOB = (path, tmp, beat_idx, ref_params)
+        worker, kind = _reference_one, "reference"
+        what = ("the UNMODIFIED reference (baseline/_ref): preprocess_audio on a WAV in /dev/shm, "
+                "_calculate_dynamic_noise_floor, PeakClassifier.__init__ (_initialize_state + _find_raw_peaks), "
+                "calculate_bpm_series, find_major_hr_inclines/declines, find_peak_recovery/exertion_rate, "
+                "calculate_windowed_hrv")
+    else:
+        _POOL_JOB = (pcm_s, sr, beat_idx, params)
+        worker, kind = _cpu_pool_worker, "port"
+        what = "oracle/ref_port.py (the reference's numpy/scipy/pandas calls restated), a1..a8"
     ctx = mp.get_context("fork")
     times = []
-    with ctx.Pool(workers) as pool:
-        for _ in range(args.warmup):
-            pool.map(_cpu_pool_worker, range(workers))
-        for _ in range(args.steps):
-            t0 = time.perf_counter()
-            pool.map(_cpu_pool_worker, range(workers))
-            times.append(time.perf_counter() - t0)
+    try:
+        with ctx.Pool(workers) as pool:
+            for _ in range(args.warmup):
+                pool.map(worker, range(workers))
+            for _ in range(args.steps):
+                t0 = time.perf_counter()
+                pool.map(worker, range(workers))
+                times.append(time.perf_counter() - t0)
+    finally:
+        if tmp:
+            import shutil
+            shutil.rmtree(tmp, ignore_errors=True)
     step = sum(times) / len(times)
     value = workers * (sample_sec / 3600.0) / step
     sample = (f"{workers} x first {sample_sec:g} s of the C2 recording per step, one process per recording "
-              f"(numpy/scipy/pandas are single-threaded on this path), a1..a8")
+              f"(numpy/scipy/pandas are single-threaded on this path); {what}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "filter_mode": args.filter_mode},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -443,6 +552,62 @@ def run_b200(args):
         h2d = pcm_pin.numel() * pcm_pin.element_size() + beats_pin.numel() * 8
         d2h = 2 * M * 8 + nt * 8 + npk * 24 + nv * 24 + rows * 32 + 8 * 8 + 7 * 8 + \
             (int(hostb["n_tops"][0]) + int(hostb["n_bottoms"][0])) * 8
+    pipe_ms, pipe_h2d, pipe_d2h = e2e_ms, h2d, d2h
+
+    # ---- end to end through the DROP-IN functions: what a caller of the reference's names gets.
+    # One recording at a time, the ten frontend.* calls in analyze_wav_file's order (bpm_analysis.py:
+    # 1731-1732, :1635, :1649-1650, :1740, :1704-1710), host arrays in, host arrays / pandas objects
+    # out, no pipelining across recordings.  The session layer (dropin.py) is emptied at the top of
+    # every step, so nothing is carried from one step to the next; the preliminary pass gets its own
+    # (thinned) beat list, as in the reference, so both BPM-series calls do their work.
+    from bpm_analysis_b200 import frontend
+    from bpm_analysis_b200.dropin import dropin as _dropin
+    svc = _dropin()
+    pcm_host = pcm_pin.numpy()
+    prelim_beats = beat_idx[(np.arange(len(beat_idx)) % 9) != 4]
+
+    class _Clf:                                       # the attributes _initialize_state / _find_raw_peaks read
+        pass
+
+    def dropin_step():
+        svc.forget()
+        clf = _Clf()
+        env, r, _, _ = frontend.preprocess_pcm(pcm_host, sr, params, want_filtered=False)
+        floor, troughs = frontend._calculate_dynamic_noise_floor(env, r, params)
+        clf.audio_envelope, clf.sample_rate, clf.params = env, r, params
+        st1 = frontend._initialize_state(clf, None, floor, troughs)
+        ps, pt = frontend.calculate_bpm_series(prelim_beats, r, params)
+        phase = frontend.find_recovery_phase(ps, pt, params)
+        st2 = frontend._initialize_state(clf, 80.0, floor, troughs)
+        sm, bt = frontend.calculate_bpm_series(beat_idx, r, params)
+        res = {"envelope": env, "floor": floor, "troughs": troughs, "peaks": st2["all_peaks"],
+               "smoothed_dev": st2["smoothed_dev_series"], "prelim_peaks": st1["all_peaks"], "phase": phase,
+               "smoothed_bpm": sm, "bpm_times": bt,
+               "major_inclines": frontend.find_major_hr_inclines(sm),
+               "major_declines": frontend.find_major_hr_declines(sm),
+               "hrr_stats": frontend.calculate_hrr(sm),
+               "peak_recovery_stats": frontend.find_peak_recovery_rate(sm),
+               "peak_exertion_stats": frontend.find_peak_exertion_rate(sm),
+               "windowed_hrv_df": frontend.calculate_windowed_hrv(beat_idx, r, params)}
+        return res
+
+    import logging
+    logging.getLogger().setLevel(logging.ERROR)
+    for _ in range(max(3, args.warmup)):
+        dres = dropin_step()
+    barrier()
+    s0 = dict(svc.stats)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dres = dropin_step()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    s1 = dict(svc.stats)
+    assert s1["stage_a_calls"] - s0["stage_a_calls"] == args.steps
+    nt_d, npk_d = len(dres["troughs"]), len(dres["peaks"])
+    nb, nb2 = len(beat_idx), len(prelim_beats)
+    h2d = M * pcm_pin.element_size() + (nb + nb2) * 8 + 2 * 64            # kept frames + two beat lists + descriptors
+    d2h = (2 * M * 8 + 5 * svc_cap(M, A) * 8 + 4 * 8) + (7 * nb + 8 + 3 * nb + 4) * 8 + (7 * nb2 + 8 + 3 * nb2 + 4) * 8
     clocks = sampler.stop()
     e2e_value = world * audio_hours / (e2e_ms / 1e3)
 
@@ -475,16 +640,19 @@ def run_b200(args):
                 json.dump({"filter_mode": args.filter_mode, "shape": shp, "ms_per_step": ms_step, "kernels": kernels},
                           fh, indent=1)
 
-    # ---- CPU baseline beside it (rank 0, single GPU runs only)
-    cpu = None
+    # ---- CPU baseline beside it (rank 0, single GPU runs only) + parity of this run's GPU outputs
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         os.environ.setdefault("OMP_NUM_THREADS", "1")
         sample_sec = min(args.duration_sec, 3600.0)
         n = int(sample_sec * sr)
         bi = synth.beats_to_envelope_indices(beats[beats < sample_sec - 1.0], rate)
         reps = 4                                     # ~11 s of CPU work at the default size
-        ts = [cpu_step(pcm[:n], sr, bi, params, 1) for _ in range(reps)]
+        t_first, oracle_out = cpu_step(pcm[:n], sr, bi, params, 1, keep=True)
+        ts = [t_first] + [cpu_step(pcm[:n], sr, bi, params, 1) for _ in range(reps - 1)]
         t = sum(ts) / reps
+        if n == len(pcm):
+            parity = parity_report(dres, oracle_out, A)
         cpu = {"value": (sample_sec / 3600.0) / t, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"{reps} x first {sample_sec:g} s of the same recording, a1..a8, one core "
                          f"(the reference is single-threaded); {sum(ts):.2f} s in all"}
@@ -501,15 +669,21 @@ def run_b200(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h),
-                        "ingest": ((f"bpm_copy_frames: the kept frames x[::ds] leave pinned host memory as one strided 2-D "
-                                    f"copy on the copy engine (h2d bytes = the kept frames); " if args.e2e_ingest == "ce" else
-                                    f"zero-copy: bpm_gather_frames reads the kept frames from pinned host memory (h2d bytes "
-                                    f"= 32-byte sector per kept frame); ") +
-                                   f"{args.e2e_depth}-deep pipeline ingest | compute | "
+                        "api": "the drop-in functions: frontend.preprocess_pcm, _calculate_dynamic_noise_floor, "
+                               "_initialize_state x2, calculate_bpm_series x2, find_recovery_phase, find_major_hr_inclines/"
+                               "declines, calculate_hrr, find_peak_recovery/exertion_rate, calculate_windowed_hrv -- one "
+                               "recording at a time, host arrays in, numpy / pandas objects out, sessions emptied every step",
+                        "ingest": "bpm_host_gather_frames (host cores pack x[::ds] into pinned staging) + one cudaMemcpyAsync; "
+                                  "results come back into pinned host arrays handed to the caller"},
+                "e2e_pipelined": {"value": world * audio_hours / (pipe_ms / 1e3), "unit": UNIT, "ms_per_step": pipe_ms,
+                        "h2d_bytes_per_step": int(pipe_h2d), "d2h_bytes_per_step": int(pipe_d2h),
+                        "api": "runtime.StageAPipeline (throughput API: several recordings in flight)",
+                        "ingest": (PIPE_INGEST[args.e2e_ingest] + f"{args.e2e_depth}-deep pipeline ingest | compute | "
                                    "read-back over three streams") if zero_copy else
                                   "cudaMemcpyAsync of the whole recording from pinned host memory, serial steps"},
                 "gpu_launches": launches if graphed is None else launches_per_step * args.steps,
-                "launch_mode": "eager" if graphed is None else "cuda-graph replay", "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
+                "launch_mode": "eager" if graphed is None else "cuda-graph replay", "roofline": roofline,
+                "cpu_baseline": cpu, "parity": parity, "kernels": kernels}
         emit(line)
     if world > 1:
         dist.barrier()

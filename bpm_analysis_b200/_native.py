@@ -43,7 +43,7 @@ class StageAConfig(C.Structure):
 class StageAOutputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("filtered", "envelope", "absmax", "debug_wav", "floor", "troughs",
                                           "trough_count", "peaks", "peak_count", "strength", "deviation",
-                                          "smoothed_dev")]
+                                          "smoothed_dev", "trough_total", "floor_mode")]
 
 
 _P, _I, _L, _D, _Z = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_size_t
@@ -66,7 +66,7 @@ _SIGNATURES = {
     "bpm_rolling_floor_workspace_bytes": (_Z, [_L, _I]),
     "bpm_rolling_floor": (_I, [_P, _P, _P, _P, _P, _I, _I, _D, _P, _P, _Z, _P]),
     "bpm_noise_floor_workspace_bytes": (_Z, [_L, _I]),
-    "bpm_noise_floor": (_I, [_P, _P, _P, _I, _I, _D, _D, _I, _D, _P, _P, _P, _P, _Z, _P]),
+    "bpm_noise_floor": (_I, [_P, _P, _P, _I, _I, _D, _D, _I, _D, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "bpm_sanitize_troughs_workspace_bytes": (_Z, [_L, _I]),
     "bpm_sanitize_troughs": (_I, [_P, _P, _P, _P, _P, _P, _I, _D, _P, _P, _P, _Z, _P]),
     "bpm_raw_peaks_workspace_bytes": (_Z, [_L, _I]),

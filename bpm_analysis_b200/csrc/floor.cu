@@ -1241,8 +1241,11 @@ __global__ void k_sanitize_flags(const double* __restrict__ env, const double* _
 // per-item control words of _calculate_dynamic_noise_floor
 //   stage 0 (after the trough search):  few[i] = n_all < 5 ; draft_mode[i] = few ? skip(2 -> constant) : 0
 //   stage 1 (after sanitisation):       final_mode[i] = few ? 2 : (n_kept > 2 ? 0 : 1)
+// total_out / mode_out (optional, stage 1): the trough count before sanitisation and the branch
+// taken, for the caller's log lines (bpm_analysis.py:1074, :1099, :1109)
 __global__ void k_floor_modes(const int64_t* __restrict__ n_all, const int64_t* __restrict__ n_kept, int n_items,
-                              int stage, int* __restrict__ few, int* __restrict__ mode) {
+                              int stage, int* __restrict__ few, int* __restrict__ mode,
+                              int64_t* __restrict__ total_out, int64_t* __restrict__ mode_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_items) return;
   if (stage == 0) {
@@ -1250,7 +1253,10 @@ __global__ void k_floor_modes(const int64_t* __restrict__ n_all, const int64_t* 
     few[i] = f;
     mode[i] = f ? 2 : 0;
   } else {
-    mode[i] = few[i] ? 2 : (n_kept[i] > 2 ? 0 : 1);
+    const int md = few[i] ? 2 : (n_kept[i] > 2 ? 0 : 1);
+    mode[i] = md;
+    if (total_out) total_out[i] = n_all[i];
+    if (mode_out) mode_out[i] = md;
   }
 }
 
@@ -1268,9 +1274,9 @@ int sanitize_flags_run(const double* env, const double* draft, const int64_t* tr
 }
 
 int floor_modes_run(const int64_t* n_all, const int64_t* n_kept, int n_items, int stage, int* few, int* mode,
-                    cudaStream_t st) {
+                    int64_t* total_out, int64_t* mode_out, cudaStream_t st) {
   BPM_KERNEL(k_floor_modes);
-  k_floor_modes<<<cdiv(n_items, 128), 128, 0, st>>>(n_all, n_kept, n_items, stage, few, mode);
+  k_floor_modes<<<cdiv(n_items, 128), 128, 0, st>>>(n_all, n_kept, n_items, stage, few, mode, total_out, mode_out);
   BPM_LAUNCH_OK();
   return BPM_OK;
 }

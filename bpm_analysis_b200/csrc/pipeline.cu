@@ -42,7 +42,7 @@ int sanitize_flags_run(const double* env, const double* draft, const int64_t* tr
                        const int* keep_all, const BpmItem* items, const BatchShape& sh, double mult, int draft_by_knot,
                        unsigned char* flags, cudaStream_t st);
 int floor_modes_run(const int64_t* n_all, const int64_t* n_kept, int n_items, int stage, int* few, int* mode,
-                    cudaStream_t st);
+                    int64_t* total_out, int64_t* mode_out, cudaStream_t st);
 // metrics.cu
 int peak_metrics_run(const double* env, const double* floor_, const int64_t* peaks, const int64_t* peak_count,
                      const BpmItem* items, const BatchShape& sh, double factor, double* strength,
@@ -120,7 +120,8 @@ size_t noise_floor_workspace_bytes(int64_t total_m, int n) {
 
 int noise_floor_run(const double* env, const BpmItem* items, const BatchShape& sh, int distance,
                     double trough_prom_q, double floor_q, int window, double mult, double* floor_out,
-                    int64_t* troughs_out, int64_t* trough_count, double* q_tp_out /* optional [n] */,
+                    int64_t* troughs_out, int64_t* trough_count, int64_t* total_out /* optional [n] */,
+                    int64_t* mode_out /* optional [n] */, double* q_tp_out /* optional [n] */,
                     Workspace& ws, cudaStream_t st) {
   if (!env || !items || !floor_out || !troughs_out || !trough_count) return BPM_ERR_ARG;
   if (distance < 1 || window < MIN_PERIODS) return BPM_ERR_ARG;
@@ -149,7 +150,7 @@ int noise_floor_run(const double* env, const BpmItem* items, const BatchShape& s
                            fj.join_event()));                                                        // :1070
     if (fj.active && cudaGetLastError() != cudaSuccess) return BPM_ERR_CUDA;
   }
-  BPM_TRY(floor_modes_run(s.n_all, nullptr, n, 0, s.few, s.mode, st));
+  BPM_TRY(floor_modes_run(s.n_all, nullptr, n, 0, s.few, s.mode, nullptr, nullptr, st));
   // draft floor from all troughs (:1081-1086).  It is only ever read AT the troughs (:1093), so it
   // is computed there only (one value per trough) whenever the block-cooperative kernel applies.
   const bool sparse = rolling_floor_sparse_ok(window);
@@ -162,7 +163,7 @@ int noise_floor_run(const double* env, const BpmItem* items, const BatchShape& s
                              st));                                                                   // :1090-1097
   BPM_TRY(compact_run(s.keep, s.all_troughs, items, sh, s.n_all, sh.max_m / 2 + 2, false, s.tile_counts,
                       troughs_out, trough_count, st));
-  BPM_TRY(floor_modes_run(s.n_all, trough_count, n, 1, s.few, s.mode, st));
+  BPM_TRY(floor_modes_run(s.n_all, trough_count, n, 1, s.few, s.mode, total_out, mode_out, st));
   {
     // final floor from the kept troughs (:1102-1106); when <= 2 are kept the reference reuses the
     // draft (:1107-1110) = the same rolling quantile over ALL troughs, recomputed here (mode 1
@@ -389,13 +390,13 @@ size_t bpm_noise_floor_workspace_bytes(int64_t total_m, int n_items) { return no
 
 int bpm_noise_floor(const double* envelope, const BpmItem* items, const BpmItem* items_host, int n_items,
                     int distance, double trough_prom_q, double floor_q, int window, double rejection_multiplier,
-                    double* floor_out, int64_t* troughs_out, int64_t* trough_count, void* workspace,
-                    size_t workspace_bytes, void* stream) {
+                    double* floor_out, int64_t* troughs_out, int64_t* trough_count, int64_t* trough_total,
+                    int64_t* floor_mode, void* workspace, size_t workspace_bytes, void* stream) {
   if (!workspace || !items_host || n_items <= 0) return BPM_ERR_ARG;
   Workspace ws(workspace, workspace_bytes);
   return noise_floor_run(envelope, items, batch_shape(items_host, n_items), distance, trough_prom_q, floor_q, window,
-                         rejection_multiplier, floor_out, troughs_out, trough_count, nullptr, ws,
-                         static_cast<cudaStream_t>(stream));
+                         rejection_multiplier, floor_out, troughs_out, trough_count, trough_total, floor_mode, nullptr,
+                         ws, static_cast<cudaStream_t>(stream));
 }
 
 size_t bpm_sanitize_troughs_workspace_bytes(int64_t total_m, int n_items) { return sanitize_workspace_bytes(total_m, n_items); }
@@ -500,7 +501,7 @@ int bpm_stage_a(const void* pcm, const BpmItem* items, const BpmItem* items_host
     Workspace ws(top.base + top.used, top.cap - top.used);
     BPM_TRY(noise_floor_run(out->envelope, items, sh, cfg->distance, cfg->trough_prom_q, cfg->floor_q,
                             cfg->noise_window, cfg->rejection_multiplier, out->floor, out->troughs,
-                            out->trough_count, q_tp, ws, st));
+                            out->trough_count, out->trough_total, out->floor_mode, q_tp, ws, st));
   }
   {
     Workspace ws(top.base + top.used, top.cap - top.used);

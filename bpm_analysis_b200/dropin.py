@@ -142,6 +142,14 @@ class DropIn:
         self.stream = torch.cuda.Stream()
         self.stats = {"session_hits": 0, "session_misses": 0, "stage_a_calls": 0, "beat_hits": 0, "beat_misses": 0}
 
+    def forget(self) -> None:
+        """Drop every session and cached result (the preallocated runner buffers stay)."""
+        with self.lock:
+            self.sessions.clear()
+            self.beat_cache.clear()
+            from . import frontend
+            frontend._series_results.clear()
+
     # ------------------------------------------------------------------ sessions
     def _remember(self, s: Session) -> None:
         self.sessions[s.env_watch.key] = s
@@ -184,7 +192,6 @@ class DropIn:
         with torch.cuda.stream(self.stream):
             dev = torch.empty(max(a.size, 1), dtype=stage.dtype, device=self.device)
             dev[:a.size].copy_(stage[:a.size], non_blocking=True)
-            stage.record_stream(self.stream) if stage.is_cuda else None
         self._keep_alive = stage                      # until the next synchronisation of the stream
         return dev[:a.size] if a.size else dev[:0]
 
@@ -319,8 +326,7 @@ class DropIn:
                 t_host = _pinned(cap, torch.int64)
                 t_host[:cap].copy_(tr[:cap], non_blocking=True)
             self.stream.synchronize()
-            nt, n_all = int(c_host[0]), int(c_host[1])
-            mode = int(c_host.numpy().view(np.int32)[4])
+            nt, n_all, mode = int(c_host[0]), int(c_host[1]), int(c_host[2])
             fl = f_host.numpy()[:n]
             troughs = t_host.numpy()[:nt].copy()
             s.a2[cfg] = {"floor": fl, "troughs": troughs, "n_all": n_all, "mode": mode, "floor_dev": floor[:n],

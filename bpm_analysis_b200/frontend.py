@@ -13,6 +13,7 @@ import datetime
 import logging
 import os
 import warnings
+from collections import OrderedDict
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -20,25 +21,33 @@ import pandas as pd
 from scipy.io import wavfile
 
 from . import runtime
+from .dropin import dropin
 from .params import (HR_MIN_CHANGE_BPM, HR_MIN_DURATION_SEC, HR_PROMINENCE, SLOPE_WINDOW_SEC, band_edges,
                      effective_decimation)
 
 __all__ = ["preprocess_audio", "preprocess_pcm", "_calculate_dynamic_noise_floor", "_find_raw_peaks",
            "_initialize_state", "calculate_bpm_series", "find_peak_recovery_rate", "find_peak_exertion_rate",
-           "find_major_hr_inclines", "find_major_hr_declines", "calculate_windowed_hrv", "find_peaks", "peak_trough_noise",
-           "install"]
+           "find_major_hr_inclines", "find_major_hr_declines", "calculate_windowed_hrv", "calculate_hrr",
+           "find_recovery_phase", "find_peaks", "peak_trough_noise", "install"]
 
 
 # --------------------------------------------------------------------------- a1
-def preprocess_pcm(audio_data: np.ndarray, sample_rate: int, params: Dict, want_debug: bool = False):
-    """Array-level body of ``preprocess_audio``: (envelope, rate, filtered, debug_int16 | None)."""
+def preprocess_pcm(audio_data: np.ndarray, sample_rate: int, params: Dict, want_debug: bool = False,
+                   want_filtered: bool = True):
+    """Array-level body of ``preprocess_audio``: (envelope, rate, filtered | None, debug_int16 | None).
+
+    The call also runs the noise-floor, raw-peak and per-peak-metric stages on the device
+    (one ``bpm_stage_a``) and parks their results in a session keyed by the returned envelope
+    array, so the calls ``analyze_wav_file`` makes next are served without another round trip
+    (``dropin.py``).  ``want_filtered=False`` skips the band-passed signal (only tests and the
+    debug WAV read it)."""
     ds, rate, clamped = effective_decimation(sample_rate, params)
     if clamped:                                                     # bpm_analysis.py:1023-1029
         _, highcut = band_edges(params)
         logging.warning(f"Original 'downsample_factor' of {params['downsample_factor']} is too high for a "
                         f"{highcut:g}Hz filter with a {sample_rate}Hz sample rate.")
         logging.warning(f"Adjusting 'downsample_factor' to a safe value of {ds}.")
-    return runtime.ops().frontend(np.asarray(audio_data), int(sample_rate), params, want_debug)
+    return dropin().preprocess(np.asarray(audio_data), int(sample_rate), params, bool(want_debug), bool(want_filtered))
 
 
 def preprocess_audio(file_path: str, params: Dict, output_directory: str) -> Tuple[np.ndarray, int]:
@@ -48,7 +57,8 @@ def preprocess_audio(file_path: str, params: Dict, output_directory: str) -> Tup
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         sample_rate, audio_data = wavfile.read(file_path)
-    envelope, rate, _, debug = preprocess_pcm(audio_data, sample_rate, params, want_debug=bool(save_debug_file))
+    envelope, rate, _, debug = preprocess_pcm(audio_data, sample_rate, params, want_debug=bool(save_debug_file),
+                                              want_filtered=False)
     if save_debug_file:
         # the reference writes the same int16 signal twice (:1047-1050 and :1056-1060)
         wavfile.write(f"{os.path.splitext(file_path)[0]}_filtered_debug.wav", rate, debug)
@@ -58,13 +68,37 @@ def preprocess_audio(file_path: str, params: Dict, output_directory: str) -> Tup
 
 
 # --------------------------------------------------------------------------- a2
+_index_cache: Dict[int, pd.Index] = {}
+
+
+def _arange_index(n: int) -> pd.Index:
+    """pd.Index(np.arange(n)) -- what the reference builds per call (:1076, :1082); an Index is
+    immutable, so one per length is shared between the Series handed out."""
+    ix = _index_cache.get(n)
+    if ix is None:
+        if len(_index_cache) > 8:
+            _index_cache.clear()
+        ix = _index_cache[n] = pd.Index(np.arange(n))
+    return ix
+
+
 def _calculate_dynamic_noise_floor(audio_envelope: np.ndarray, sample_rate: int, params: Dict
                                    ) -> Tuple[pd.Series, np.ndarray]:
     """Dynamic noise floor from sanitised troughs.  Mirrors bpm_analysis.py:1064-1117."""
     env = np.ascontiguousarray(audio_envelope, dtype=np.float64)
-    floor, troughs = runtime.ops().noise_floor(env, int(sample_rate), params)
-    logging.info(f"Trough Sanitization: Kept {len(troughs)} troughs.")
-    return pd.Series(floor, index=np.arange(len(env))), troughs
+    d = dropin()
+    floor, troughs, n_all, mode = d.noise_floor(env, int(sample_rate), params)
+    if mode == 2:                                                   # :1073-1077
+        logging.warning("Not enough troughs found for sanitization. Using a static noise floor.")
+    else:
+        logging.info(f"Trough Sanitization: Kept {len(troughs)} of {n_all} initial troughs.")     # :1099
+        if mode == 1:                                               # :1107-1110
+            logging.warning("Not enough sanitized troughs remaining. Using non-sanitized floor as fallback.")
+    series = pd.Series(floor, index=_arange_index(len(env)), copy=False)
+    d.note_floor_alias(env, floor, series.values, series)
+    if mode != 2 and len(troughs) == 0:
+        troughs = np.array([])                                      # np.array([]) of an empty list is float64 (:1117)
+    return series, troughs
 
 
 # --------------------------------------------------------------------------- a3 / a4
@@ -74,7 +108,7 @@ def _raw_peaks(envelope: np.ndarray, height_threshold: np.ndarray, sample_rate: 
     height = np.ascontiguousarray(height_threshold, dtype=np.float64)
     if height.shape != env.shape:                                   # what scipy's find_peaks raises
         raise ValueError("array size of lower interval border must match x")
-    return runtime.ops().raw_peaks_and_metrics(env, height, int(sample_rate), params, with_metrics)
+    return dropin().raw_peaks(env, height, int(sample_rate), params, with_metrics)
 
 
 def _find_raw_peaks(self, height_threshold: np.ndarray) -> np.ndarray:
@@ -147,20 +181,42 @@ def _epoch_us() -> int:
     return int((e - datetime.datetime(1970, 1, 1)) // datetime.timedelta(microseconds=1))
 
 
+def _series_key(series: pd.Series) -> tuple:
+    v = np.ascontiguousarray(series.values, dtype=np.float64)
+    return (len(v), hash(v.tobytes()), hash(series.index.asi8.tobytes()) if len(v) else 0)
+
+
+_series_results: "OrderedDict[tuple, dict]" = OrderedDict()
+
+
+def _beat_results_of(series: pd.Series) -> Optional[dict]:
+    """The a5..a8 results computed together with ``series`` (``calculate_bpm_series`` registers
+    every Series it hands out by content), or None for a Series from somewhere else."""
+    if not isinstance(series.index, pd.DatetimeIndex):
+        return None
+    return _series_results.get(_series_key(series))
+
+
 def calculate_bpm_series(peaks: np.ndarray, sample_rate: int, params: Dict) -> Tuple[pd.Series, np.ndarray]:
-    """Smoothed BPM series from S1 peaks.  Mirrors bpm_analysis.py:1463-1484."""
+    """Smoothed BPM series from S1 peaks.  Mirrors bpm_analysis.py:1463-1484.
+
+    The same device round trip computes the steepest slopes, the extrema of the smoothed series
+    and the windowed HRV table of this beat list (``dropin.beat_metrics``); the reductions that
+    ``_calculate_final_metrics`` applies next (:1704-1710) find them by the Series they are given."""
     if len(peaks) < 2:
         return pd.Series(dtype=np.float64), np.array([])
-    window_sec = params["output_smoothing_window_sec"]
-    window_us = int(pd.Timedelta(f"{window_sec}s") // pd.Timedelta(microseconds=1))
-    inst, smoothed, times, us = runtime.ops().bpm_series(np.asarray(peaks, dtype=np.int64), int(sample_rate),
-                                                         window_us)
-    if len(inst) == 0:
+    res = dropin().beat_metrics(np.asarray(peaks, dtype=np.int64), int(sample_rate), params)
+    if res.get("n_series", 0) == 0:
         return pd.Series(dtype=np.float64), np.array([])
-    index = pd.DatetimeIndex((us + _epoch_us()).astype("datetime64[us]"))
+    inst, smoothed, times, us = res["inst"], res["smoothed"], res["times"], res["stamps"]
     if not (np.median(inst) > 0):
-        return pd.Series(dtype=np.float64), times
-    return pd.Series(smoothed, index=index), times
+        return pd.Series(dtype=np.float64), times.copy()
+    index = pd.DatetimeIndex((us + _epoch_us()).astype("datetime64[us]"))
+    series = pd.Series(smoothed.copy(), index=index)
+    _series_results[_series_key(series)] = res
+    while len(_series_results) > 16:
+        _series_results.popitem(last=False)
+    return series, times.copy()
 
 
 # --------------------------------------------------------------------------- a6
@@ -168,35 +224,43 @@ def _series_arrays(series: pd.Series):
     return np.ascontiguousarray(series.values, dtype=np.float64), series.index.as_unit("us").asi8
 
 
+def _slope_record(series: pd.Series, vals, us, hit, origin: int) -> Dict:
+    i, j, slope = hit
+    dur = float((us[j] - us[origin]) / 1e6 - (us[i] - us[origin]) / 1e6)
+    ix = series.index
+    return {"start_time": ix[i], "end_time": ix[j], "start_bpm": vals[i], "end_bpm": vals[j],
+            "slope_bpm_per_sec": slope, "duration_sec": dur}
+
+
+def _steepest(series: pd.Series, sign: int, window_sec):
+    vals, us = _series_arrays(series)
+    res = _beat_results_of(series) if float(window_sec) == float(SLOPE_WINDOW_SEC) else None
+    if res is not None:
+        r = res["slopes"][0:4] if sign > 0 else res["slopes"][4:8]
+        hit = None if r[0] == 0.0 else (int(r[1]), int(r[2]), float(r[3]))
+    else:
+        hit = runtime.ops().steepest(vals, us, sign, float(window_sec))
+    return vals, us, hit
+
+
 def find_peak_recovery_rate(smoothed_bpm_series: pd.Series, window_sec: int = SLOPE_WINDOW_SEC) -> Optional[Dict]:
     """Steepest HR decline after the peak BPM.  Mirrors bpm_analysis.py:1552-1574."""
     if smoothed_bpm_series.empty or len(smoothed_bpm_series) < 2:
         return None
-    vals, us = _series_arrays(smoothed_bpm_series)
-    hit = runtime.ops().steepest(vals, us, -1, float(window_sec))
+    vals, us, hit = _steepest(smoothed_bpm_series, -1, window_sec)
     if hit is None:
         return None
-    i, j, slope = hit
-    start = int(np.argmax(vals))
-    dur = float((us[j] - us[start]) / 1e6 - (us[i] - us[start]) / 1e6)
-    ix = smoothed_bpm_series.index
-    return {"start_time": ix[i], "end_time": ix[j], "start_bpm": vals[i], "end_bpm": vals[j],
-            "slope_bpm_per_sec": slope, "duration_sec": dur}
+    return _slope_record(smoothed_bpm_series, vals, us, hit, int(np.argmax(vals)))
 
 
 def find_peak_exertion_rate(smoothed_bpm_series: pd.Series, window_sec: int = SLOPE_WINDOW_SEC) -> Optional[Dict]:
     """Steepest HR increase over the recording.  Mirrors bpm_analysis.py:1576-1595."""
     if smoothed_bpm_series.empty or len(smoothed_bpm_series) < 2:
         return None
-    vals, us = _series_arrays(smoothed_bpm_series)
-    hit = runtime.ops().steepest(vals, us, +1, float(window_sec))
+    vals, us, hit = _steepest(smoothed_bpm_series, +1, window_sec)
     if hit is None:
         return None
-    i, j, slope = hit
-    dur = float((us[j] - us[0]) / 1e6 - (us[i] - us[0]) / 1e6)
-    ix = smoothed_bpm_series.index
-    return {"start_time": ix[i], "end_time": ix[j], "start_bpm": vals[i], "end_bpm": vals[j],
-            "slope_bpm_per_sec": slope, "duration_sec": dur}
+    return _slope_record(smoothed_bpm_series, vals, us, hit, 0)
 
 
 # --------------------------------------------------------------------------- a7
@@ -208,6 +272,9 @@ def _hr_extrema(series: pd.Series, min_duration_sec: float):
     dist = 5 if np.isnan(mean_gap) or mean_gap == 0 else int((min_duration_sec / 2) / mean_gap)
     if dist < 1:
         raise ValueError("`distance` must be greater or equal to 1")
+    res = _beat_results_of(series)
+    if res is not None and res.get("hr_distance") == dist and "tops" in res:
+        return vals, res["tops"], res["bottoms"]
     o = runtime.ops()
     tops = o.find_peaks(vals, None, float(HR_PROMINENCE), dist, +1)
     bottoms = o.find_peaks(vals, None, float(HR_PROMINENCE), dist, -1)
@@ -272,13 +339,48 @@ def calculate_windowed_hrv(s1_peaks: np.ndarray, sample_rate: int, params: Dict)
         logging.warning(f"Not enough beats ({len(s1_peaks)}) to perform windowed HRV analysis with a window of "
                         f"{window_size_beats} beats.")
         return pd.DataFrame(columns=cols)
-    rows = runtime.ops().windowed_hrv(np.asarray(s1_peaks, dtype=np.int64), int(sample_rate),
-                                      int(window_size_beats), int(step_size_beats))
+    res = dropin().beat_metrics(np.asarray(s1_peaks, dtype=np.int64), int(sample_rate), params)
+    rows = res.get("hrv", np.zeros((0, 4)))
     if len(rows) == 0:
         logging.warning("Could not perform windowed HRV analysis. Recording may be too short or have too few beats.")
         return pd.DataFrame(columns=cols)
     logging.info(f"Beat-based windowed HRV analysis complete. Generated {len(rows)} data points.")
-    return pd.DataFrame(rows, columns=cols)
+    return pd.DataFrame(rows.copy(), columns=cols)
+
+
+# --------------------------------------------------------------------------- hrr / recovery phase
+def calculate_hrr(smoothed_bpm_series: pd.Series, interval_sec: int = 60) -> Optional[Dict]:
+    """Heart-rate recovery over a fixed interval after the peak.  Mirrors bpm_analysis.py:1597-1610,
+    including what it does with the index under the installed pandas: the interpolation abscissa is
+    ``index.astype(int64) // 10**9`` -- seconds only while the index unit is ns (pandas 3 stores
+    these stamps as datetime64[us]; SURVEY.md section 8c "version hazards").  Host glue on a
+    series of one value per beat: an arg-max and one np.interp."""
+    if smoothed_bpm_series.empty or len(smoothed_bpm_series) < 2:
+        return None
+    peak_time = smoothed_bpm_series.idxmax()
+    peak_bpm = smoothed_bpm_series.max()
+    check_time = peak_time + pd.Timedelta(seconds=interval_sec)
+    if check_time > smoothed_bpm_series.index.max():
+        return None
+    xp = (smoothed_bpm_series.index.astype(np.int64) // 10**9).to_numpy(dtype=float)
+    fp = np.asarray(smoothed_bpm_series.values, dtype=float)
+    recovery_bpm = np.interp(check_time.timestamp(), xp, fp)
+    return {"peak_bpm": peak_bpm, "peak_time": peak_time, "recovery_bpm": recovery_bpm,
+            "recovery_check_time": check_time, "hrr_value_bpm": peak_bpm - recovery_bpm, "interval_sec": interval_sec}
+
+
+def find_recovery_phase(bpm_series: pd.Series, bpm_times_sec: np.ndarray, params: Dict
+                        ) -> Tuple[Optional[float], Optional[float]]:
+    """Peak of the preliminary BPM series and the end of the high-contractility window after it.
+    Mirrors bpm_analysis.py:1612-1620."""
+    if bpm_times_sec is None or len(bpm_times_sec) < 2:
+        logging.warning("Not enough preliminary beats to determine a recovery phase.")
+        return None, None
+    peak_time_sec = bpm_times_sec[np.argmax(bpm_series.to_numpy())]
+    recovery_end_time_sec = peak_time_sec + params.get("recovery_phase_duration_sec", 120.0)
+    logging.info(f"Peak BPM detected in preliminary pass at {peak_time_sec:.2f}s. High-contractility state defined "
+                 f"until {recovery_end_time_sec:.2f}s.")
+    return peak_time_sec, recovery_end_time_sec
 
 
 # --------------------------------------------------------------------------- install
@@ -294,7 +396,7 @@ def install(ref_module, classifier: bool = True, corrections: bool = True):
     """
     for name in ("preprocess_audio", "_calculate_dynamic_noise_floor", "calculate_bpm_series",
                  "find_peak_recovery_rate", "find_peak_exertion_rate", "find_major_hr_inclines",
-                 "find_major_hr_declines", "calculate_windowed_hrv"):
+                 "find_major_hr_declines", "calculate_windowed_hrv", "calculate_hrr", "find_recovery_phase"):
         setattr(ref_module, name, globals()[name])
     ref_module.PeakClassifier._find_raw_peaks = _find_raw_peaks
     ref_module.PeakClassifier._initialize_state = _initialize_state

@@ -174,7 +174,8 @@ class StageAResult:
         o, m = int(it["m_off"]), int(it["m"])
         nt, npk = int(self.host("trough_count")[i]), int(self.host("peak_count")[i])
         out = {"rate": self.rate,
-               "filtered": self.host("filtered")[o:o + m], "envelope": self.host("envelope")[o:o + m],
+               "filtered": self.host("filtered")[o:o + m] if "filtered" in self.dev else None,
+               "envelope": self.host("envelope")[o:o + m],
                "floor": self.host("floor")[o:o + m], "absmax": float(self.host("absmax")[i]),
                "troughs": self.host("troughs")[o:o + nt].copy(), "peaks": self.host("peaks")[o:o + npk].copy(),
                "strength": self.host("strength")[o:o + npk],
@@ -193,14 +194,18 @@ class StageARunner:
     """
 
     def __init__(self, n_in: Sequence[int], sample_rate: int, params: Dict, pcm_dtype=np.int16,
-                 channels: int = 1, want_debug: bool = False, pregathered: bool = False):
+                 channels: int = 1, want_debug: bool = False, pregathered: bool = False, want_filtered: bool = True):
         """``pregathered``: the decimation x[::ds] (K0) runs on its own (``gather``) into a frame
         buffer that stage A then reads with stride 1 -- bit-identical to the fused path, and it
         lets ``StageAPipeline`` overlap the PCIe-bound ingest of the next recording with the
         compute of the current one.  ``True`` / ``"sm"``: bpm_gather_frames, a small kernel that
         writes float64 frames; ``"ce"``: bpm_copy_frames, one strided 2-D copy on the copy engine
-        that keeps the PCM's dtype and channels (no SM involved, faster over PCIe).
-        Decimate-then-filter order only."""
+        that keeps the PCM's dtype and channels (no SM involved, faster over PCIe); ``"host"``: the
+        frames were packed by the host cores (bpm_host_gather_frames) into a pinned staging buffer
+        that ``ingest`` copies in one piece -- same device layout as ``"ce"``.
+        Decimate-then-filter order only.
+        ``want_filtered=False``: the band-passed signal is not written to HBM at all (the envelope
+        is formed inside the backward pass); only the debug WAV and the tests read it."""
         self.device = require_cuda()
         self.lib = nat.load_library()
         self.plan = plan_filter(sample_rate, params)
@@ -216,10 +221,10 @@ class StageARunner:
         self.total_in = int(self.items["n_in"].sum())
         self.total_m = int(self.items["m"].sum())
         self.cfg = stage_a_config(self.plan, params, nat.PCM_DTYPES[self.np_dtype], self.channels, want_debug)
-        if pregathered not in (False, True, "sm", "ce"):
-            raise ValueError("pregathered must be False, True / 'sm' or 'ce'")
+        if pregathered not in (False, True, "sm", "ce", "host"):
+            raise ValueError("pregathered must be False, True / 'sm', 'ce' or 'host'")
         self.pregathered = bool(pregathered)
-        self.ingest = "ce" if pregathered == "ce" else ("sm" if pregathered else None)
+        self.ingest_kind = pregathered if pregathered in ("ce", "host") else ("sm" if pregathered else None)
         if self.pregathered:
             if self.plan.block != 1:
                 raise ValueError("pregathered ingest needs the decimate-then-filter order (filter_mode 'parity')")
@@ -228,7 +233,7 @@ class StageARunner:
             self.src_stride = int(self.plan.stride)
             self.items = make_items(self.src_items["m"], self.src_items["m"])
             self.cfg.stride = 1
-            if self.ingest == "sm":
+            if self.ingest_kind == "sm":
                 self.cfg.pcm_dtype, self.cfg.channels = nat.PCM_DTYPES[np.dtype(np.float64)], 1
         self.items_dev = torch.from_numpy(self.items.view(np.int64).reshape(-1, 4).copy()).to(self.device)
         self.design_dev, self.design_host = design_images(self.plan)
@@ -241,13 +246,19 @@ class StageARunner:
                     "troughs": torch.empty(M, **i64), "trough_count": torch.empty(n, **i64),
                     "peaks": torch.empty(M, **i64), "peak_count": torch.empty(n, **i64),
                     "strength": torch.empty(M, **f64), "deviation": torch.empty(M, **f64),
-                    "smoothed_dev": torch.empty(M, **f64)}
+                    "smoothed_dev": torch.empty(M, **f64), "trough_total": torch.empty(n, **i64),
+                    "floor_mode": torch.empty(n, **i64)}
+        self.want_filtered = bool(want_filtered) or bool(want_debug)
+        if not self.want_filtered:
+            if self.plan.block != 1 or self.cfg.env_window > 65:
+                raise ValueError("want_filtered=False needs the decimate-then-filter order and an envelope window <= 65")
+            del self.out["filtered"]
         if want_debug:
             self.out["debug_wav"] = torch.empty(M, dtype=torch.int16, device=self.device)
         self.ws_bytes = int(self.lib.bpm_stage_a_workspace_bytes(M, n))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
         if self.pregathered:
-            self.frames_dev = (torch.empty(M, dtype=torch.float64, device=self.device) if self.ingest == "sm" else
+            self.frames_dev = (torch.empty(M, dtype=torch.float64, device=self.device) if self.ingest_kind == "sm" else
                                torch.empty(M * self.channels, dtype=_torch_dtype(self.np_dtype), device=self.device))
             self.pcm_dev = None
             self._pcm_src = self.frames_dev
@@ -293,7 +304,9 @@ class StageARunner:
         if not (pcm.is_cuda or pcm.is_pinned()) or pcm.numel() != self.total_in * self.channels \
                 or pcm.dtype != _torch_dtype(self.np_dtype):
             raise ValueError("need a device or pinned host tensor with the batch's dtype and size")
-        if self.ingest == "ce":
+        if self.ingest_kind == "host":
+            raise RuntimeError("host-gathered runner: pack the frames with bpm_host_gather_frames and call ingest()")
+        if self.ingest_kind == "ce":
             nat.check(self.lib.bpm_copy_frames(_ptr(pcm), nat.PCM_DTYPES[self.np_dtype], self.channels,
                                                _host_ptr(self.src_items), self.n_items, self.src_stride,
                                                _ptr(self.frames_dev), _stream_ptr()))
@@ -301,6 +314,15 @@ class StageARunner:
         nat.check(self.lib.bpm_gather_frames(_ptr(pcm), nat.PCM_DTYPES[self.np_dtype], self.channels,
                                              _ptr(self.src_items_dev), _host_ptr(self.src_items), self.n_items,
                                              self.src_stride, _ptr(self.frames_dev), _stream_ptr()))
+
+    def ingest(self, staged: torch.Tensor) -> None:
+        """One async H2D copy of a pinned staging buffer: the packed kept frames (``pregathered="host"``)
+        or the whole batch."""
+        dst = self.frames_dev if self.pregathered else self.pcm_dev
+        if staged.numel() != dst.numel() or staged.dtype != dst.dtype:
+            raise ValueError("staging buffer does not match the runner's frame buffer")
+        dst.copy_(staged, non_blocking=True)
+        self._pcm_src = dst
 
     # -- compute
     def launch(self) -> None:
@@ -440,7 +462,7 @@ class Ops:
                                            float(params["trough_prominence_quantile"]),
                                            float(params["noise_floor_quantile"]), window,
                                            float(params.get("trough_rejection_multiplier", 4.0)), _ptr(floor),
-                                           _ptr(tr), _ptr(cnt), _ptr(ws), nb, _stream_ptr()))
+                                           _ptr(tr), _ptr(cnt), None, None, _ptr(ws), nb, _stream_ptr()))
         c = int(cnt.cpu()[0])
         return floor.cpu().numpy(), tr[:c].cpu().numpy()
 
@@ -539,6 +561,99 @@ class Ops:
         return out[:r].cpu().numpy()
 
 
+def smoothing_window_us(params: Dict) -> int:
+    """rolling(f"{output_smoothing_window_sec}s") in microseconds (bpm_analysis.py:1477-1479)."""
+    import pandas as pd
+    return int(pd.Timedelta(f"{params['output_smoothing_window_sec']}s") // pd.Timedelta(microseconds=1))
+
+
+def hr_extrema_distance(beats: np.ndarray, rate: int, min_duration_sec: float = 10.0) -> int:
+    """`distance` the reference derives for find_major_hr_* from the series index
+    (bpm_analysis.py:1492-1494): int((min_duration / 2) / mean gap of the microsecond stamps),
+    5 when there is no gap.  Same arithmetic on the beat list the series is made from
+    (descriptor-sized host work: one value per beat)."""
+    t = np.asarray(beats, dtype=np.int64) / rate
+    dt = np.diff(t)
+    t1 = t[1:][dt > 1e-6]
+    ip = np.trunc(t1)
+    us = ip.astype(np.int64) * 1000000 + np.rint((t1 - ip) * 1e6).astype(np.int64)
+    gaps = np.diff(us) / 1e6
+    if len(gaps) == 0:
+        return 5
+    mean_gap = np.sum(np.concatenate([[0.0], gaps])) / len(gaps)
+    if mean_gap == 0:
+        return 5
+    return int((min_duration_sec / 2) / mean_gap)
+
+
+def beat_chain(owner, beats: np.ndarray, rate: int, window_us: int, win: int, step: int) -> Dict[str, object]:
+    """a5..a8 of one beat list in one device round trip (see dropin.DropIn.beat_metrics)."""
+    lib, dev, stream = owner.lib, owner.device, owner.stream
+    b = int(beats.size)
+    res: Dict[str, object] = {"n_beats": b}
+    if b < 2:
+        return res
+    dist = hr_extrema_distance(beats, rate)
+    items = make_items([b], [b])
+    tsec = beats / rate
+    n_series = int(np.count_nonzero(np.diff(tsec) > 1e-6))          # == n_valid the device will report (:1468)
+    res["n_series"] = n_series
+    if n_series == 0:
+        return res
+    sitems = make_items([n_series], [n_series])
+    stage = torch.empty(b, dtype=torch.int64, pin_memory=True)
+    stage.numpy()[:] = beats
+    f64 = dict(dtype=torch.float64, device=dev)
+    i64 = dict(dtype=torch.int64, device=dev)
+    with torch.cuda.stream(stream):
+        st = stream.cuda_stream
+        both = np.concatenate([items.view(np.int64).reshape(-1, 4), sitems.view(np.int64).reshape(-1, 4)])
+        desc = torch.from_numpy(both).to(dev, non_blocking=True)
+        items_dev, sitems_dev = desc[0:1], desc[1:2]
+        bd = torch.empty(b, **i64)
+        bd.copy_(stage, non_blocking=True)
+        # one float64 block [inst | smoothed | times | hrv(4b) | slopes(8)] and one int64 block
+        # [stamps | tops | bottoms | n_valid n_tops n_bottoms hrv_rows]: two read-backs in all
+        fblk = torch.empty(7 * b + 8, **f64)
+        iblk = torch.empty(3 * b + 4, **i64)
+        inst, smooth, times, hrv, slopes = fblk[:b], fblk[b:2 * b], fblk[2 * b:3 * b], fblk[3 * b:7 * b], fblk[7 * b:]
+        stamps, tops, bottoms, scal = iblk[:b], iblk[b:2 * b], iblk[2 * b:3 * b], iblk[3 * b:]
+        nat.check(lib.bpm_bpm_series(_ptr(bd), _ptr(items_dev), _host_ptr(items), 1, rate, window_us, _ptr(inst),
+                                     _ptr(smooth), _ptr(times), _ptr(stamps), C.c_void_p(scal.data_ptr()), st))
+        # the series holds the valid intervals only (dt > 1e-6 s): its length was counted on the host
+        # with the same arithmetic, so the follow-up kernels get an exact descriptor
+        ws = torch.empty(max(int(lib.bpm_find_peaks_workspace_bytes(b, 1)), 256), dtype=torch.uint8, device=dev)
+        nat.check(lib.bpm_steepest_slope(_ptr(smooth), _ptr(stamps), C.c_void_p(scal.data_ptr()), _ptr(sitems_dev),
+                                         _host_ptr(sitems), 1, 0, 20.0, _ptr(slopes), _ptr(ws), ws.numel(), st))
+        res["hr_distance"] = dist
+        if dist >= 1:
+            prom = torch.full((1,), 5.0, **f64)
+            for sign, idx, k in ((+1, tops, 1), (-1, bottoms, 2)):
+                nat.check(lib.bpm_find_peaks(_ptr(smooth), sign, None, _ptr(prom), dist, _ptr(sitems_dev),
+                                             _host_ptr(sitems), 1, _ptr(idx), C.c_void_p(scal.data_ptr() + 8 * k),
+                                             _ptr(ws), ws.numel(), st))
+        if b >= win:
+            nat.check(lib.bpm_windowed_hrv(_ptr(bd), _ptr(items_dev), _host_ptr(items), 1, rate, win, step, _ptr(hrv),
+                                           C.c_void_p(scal.data_ptr() + 24), st))
+        fh = torch.empty(fblk.numel(), dtype=torch.float64, pin_memory=True)
+        ih = torch.empty(iblk.numel(), dtype=torch.int64, pin_memory=True)
+        fh.copy_(fblk, non_blocking=True)
+        ih.copy_(iblk, non_blocking=True)
+    stream.synchronize()
+    f, i = fh.numpy(), ih.numpy()
+    nv = int(i[3 * b])
+    if nv != n_series:
+        raise RuntimeError(f"beat series length: device {nv}, host {n_series}")
+    res.update(n_valid=nv, inst=f[:nv].copy(), smoothed=f[b:b + nv].copy(), times=f[2 * b:2 * b + nv].copy(),
+               stamps=i[:nv].copy(), slopes=f[7 * b:7 * b + 8].copy())
+    if dist >= 1:
+        res["tops"] = i[b:b + int(i[3 * b + 1])].copy()
+        res["bottoms"] = i[2 * b:2 * b + int(i[3 * b + 2])].copy()
+    if b >= win:
+        res["hrv"] = f[3 * b:3 * b + 4 * int(i[3 * b + 3])].reshape(-1, 4).copy()
+    return res
+
+
 _ops_singleton: Optional[Ops] = None
 
 
@@ -573,7 +688,7 @@ class BeatRunner:
         self.series_items_dev = torch.from_numpy(self.series_items.view(np.int64).reshape(-1, 4).copy()).to(self.device)
         f64 = dict(dtype=torch.float64, device=self.device)
         i64 = dict(dtype=torch.int64, device=self.device)
-        self.beats_dev = torch.empty(self.B, **i64)
+        self.beats_dev = torch.arange(self.B, **i64)         # a valid (strictly increasing) list until upload()
         self.out = {"inst": torch.empty(self.B, **f64), "smoothed": torch.empty(self.B, **f64),
                     "times": torch.empty(self.B, **f64), "stamps": torch.empty(self.B, **i64),
                     "n_valid": torch.empty(1, **i64), "slopes": torch.empty(8, **f64),
@@ -664,29 +779,35 @@ class StageAPipeline:
     def __init__(self, n_in: int, sample_rate: int, params: Dict, depth: int = 2, beat_runner_args=None,
                  pcm_dtype=np.int16, channels: int = 1, use_graph: bool = True, ingest: str = "ce"):
         require_cuda()
-        if ingest not in ("ce", "sm"):
-            raise ValueError("ingest must be 'ce' or 'sm'")
+        if ingest not in ("ce", "sm", "host"):
+            raise ValueError("ingest must be 'ce', 'sm' or 'host'")
         self.ingest = ingest
         self.depth = int(depth)
         self.s_in, self.s_cmp, self.s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
         self.slots = []
         for _ in range(self.depth):
-            A = StageARunner([n_in], sample_rate, params, pcm_dtype, channels, pregathered=ingest)
+            A = StageARunner([n_in], sample_rate, params, pcm_dtype, channels, pregathered=ingest,
+                             want_filtered=False)
             Bn = BeatRunner(*beat_runner_args) if beat_runner_args is not None else None
-            cap = A.total_m // max(int(A.cfg.distance), 1) + 2          # find_peaks distance bounds the list lengths
+            cap = min(A.total_m, A.total_m // max(int(A.cfg.distance), 1) + 2)   # find_peaks distance bounds the list lengths
             host = {}
             for k, v in A.out.items():
-                if k == "filtered":                       # only the debug WAV consumes it (preprocess returns the envelope)
-                    continue
                 n = cap if k in self.LISTS else v.numel()
                 host[k] = torch.empty(n, dtype=v.dtype).pin_memory()
+            stage = (torch.empty(A.total_m * channels, dtype=_torch_dtype(np.dtype(pcm_dtype))).pin_memory()
+                     if ingest == "host" else None)
             hostb = {k: torch.empty_like(v, device="cpu").pin_memory() for k, v in Bn.out.items()} if Bn else {}
             with torch.cuda.stream(self.s_cmp):
                 A.frames_dev.zero_()
             runners = (A,) if Bn is None else (A, Bn)
             self.slots.append({"A": A, "B": Bn, "cap": cap, "host": host, "hostb": hostb, "runners": runners,
+                               "stage": stage,
                                "graph": None, "ev_in": torch.cuda.Event(), "ev_cmp": torch.cuda.Event(),
                                "ev_out": torch.cuda.Event(), "busy": False})
+        if ingest == "host":
+            from . import classifier
+            self.host_lib = classifier.load_host_library()
+            self.frame_bytes = int(channels) * np.dtype(pcm_dtype).itemsize
         self.use_graph = use_graph
         self.M = self.slots[0]["A"].total_m
         self.rate = self.slots[0]["A"].plan.rate
@@ -703,9 +824,19 @@ class StageAPipeline:
             raise RuntimeError("slot still in flight: call wait() for recording k - depth first")
         A, Bn = slot["A"], slot["B"]
         g = self._graph(slot) if self.use_graph else None
+        if self.ingest == "host":
+            # K0 by the host cores into this slot's pinned staging buffer (its previous H2D copy finished
+            # before the slot's last compute, which wait() has seen complete)
+            rc = self.host_lib.bpm_host_gather_frames(C.c_void_p(pcm_pinned.data_ptr()), self.frame_bytes,
+                                                      A.total_in, A.src_stride, C.c_void_p(slot["stage"].data_ptr()), 0)
+            if rc != 0:
+                raise RuntimeError(f"bpm_host_gather_frames failed ({rc})")
         with torch.cuda.stream(self.s_in):
             self.s_in.wait_event(slot["ev_cmp"])          # the previous compute on this slot has consumed its frames
-            A.gather(pcm_pinned)
+            if self.ingest == "host":
+                A.ingest(slot["stage"])
+            else:
+                A.gather(pcm_pinned)
             if Bn is not None and beats_pinned is not None:
                 Bn.upload(beats_pinned)
             slot["ev_in"].record(self.s_in)

@@ -301,7 +301,7 @@ class DeviceEngine:
                                          float(params["trough_prominence_quantile"]),
                                          float(params["noise_floor_quantile"]), int(window),
                                          float(params.get("trough_rejection_multiplier", 4.0)), rt._ptr(floor),
-                                         rt._ptr(tr), rt._ptr(cnt), rt._ptr(ws), nb, rt._stream_ptr()))
+                                         rt._ptr(tr), rt._ptr(cnt), None, None, rt._ptr(ws), nb, rt._stream_ptr()))
         return floor, tr[:int(cnt.cpu()[0])].clone()
 
     def raw_peaks(self, env: torch.Tensor, floor: torch.Tensor, distance: int, prom_q: float) -> torch.Tensor:

@@ -148,12 +148,16 @@ int bpm_rolling_floor(const double* envelope, const int64_t* knots, const int64_
  * K3 + K4(-env) + draft floor + K7 sanitisation + final floor, with the reference's
  * fall-backs (<5 troughs: constant floor and ALL troughs returned; <=2 kept: draft
  * floor; all-NaN: q(0.1)) resolved on the device.
- *   floor_out: float64[total_m]; troughs_out: int64[total_m]; trough_count: int64[n_items]. */
+ *   floor_out: float64[total_m]; troughs_out: int64[total_m]; trough_count: int64[n_items].
+ *   trough_total, floor_mode (optional, int64[n_items]): troughs before sanitisation and the
+ *   branch taken -- 0 sanitised floor, 1 draft floor (:1107-1110), 2 static floor (:1073-1077) --
+ *   which is what the reference's log lines :1074, :1099, :1109 report. */
 size_t bpm_noise_floor_workspace_bytes(int64_t total_m, int n_items);
 int bpm_noise_floor(const double* envelope, const BpmItem* items, const BpmItem* items_host,
                     int n_items, int distance, double trough_prom_q, double floor_q, int window,
                     double rejection_multiplier, double* floor_out, int64_t* troughs_out,
-                    int64_t* trough_count, void* workspace, size_t workspace_bytes, void* stream);
+                    int64_t* trough_count, int64_t* trough_total, int64_t* floor_mode,
+                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K7 on its own: trough sanitisation, bpm_analysis.py:1090-1097 -------------------
  * kept = [t for t in troughs if not isnan(draft[t]) and envelope[t] <= mult * draft[t]].
@@ -242,10 +246,12 @@ typedef struct {
 } BpmStageAConfig;
 
 typedef struct {
-  double* filtered;   double* envelope;  double* absmax;   int16_t* debug_wav; /* may be NULL */
+  double* filtered; /* may be NULL, see bpm_frontend */
+  double* envelope;  double* absmax;   int16_t* debug_wav; /* may be NULL */
   double* floor;      int64_t* troughs;  int64_t* trough_count;
   int64_t* peaks;     int64_t* peak_count;
   double* strength;   double* deviation; double* smoothed_dev;
+  int64_t* trough_total; int64_t* floor_mode;   /* may be NULL, see bpm_noise_floor */
 } BpmStageAOutputs;
 
 size_t bpm_stage_a_workspace_bytes(int64_t total_m, int n_items);

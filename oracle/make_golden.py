@@ -95,6 +95,17 @@ def run_reference_chain(ref, env, rate, params, out):
     _period_pack("exertion", ref.find_peak_exertion_rate(series), out, epoch_us)
     _segments_pack("inclines", ref.find_major_hr_inclines(series), out, "bpm_increase")
     _segments_pack("declines", ref.find_major_hr_declines(series), out, "bpm_decrease")
+    # the two remaining helpers of the metrics chain (:1597-1620), as the reference evaluates them under
+    # the pandas installed here (calculate_hrr divides a datetime64[us] index by 1e9)
+    hrr = ref.calculate_hrr(series)
+    out["hrr_found"] = np.array(hrr is not None)
+    if hrr is not None:
+        out["hrr_values"] = np.array([hrr["peak_bpm"], hrr["recovery_bpm"], hrr["hrr_value_bpm"], hrr["interval_sec"]],
+                                     dtype=np.float64)
+        out["hrr_times_us"] = np.array([pd.Timestamp(hrr["peak_time"]).as_unit("us").value,
+                                        pd.Timestamp(hrr["recovery_check_time"]).as_unit("us").value], dtype=np.int64)
+    phase = ref.find_recovery_phase(series, times, params)
+    out["recovery_phase"] = np.array([np.nan if v is None else float(v) for v in phase], dtype=np.float64)
     hrv = ref.calculate_windowed_hrv(final, rate, params)
     out["hrv"] = np.asarray(hrv[["time", "rmssdc", "sdnn", "bpm"]].values, dtype=np.float64) \
         if len(hrv) else np.zeros((0, 4))

@@ -344,6 +344,32 @@ def calculate_windowed_hrv(s1_peaks: np.ndarray, rate: int, params: Dict) -> pd.
     return pd.DataFrame(rows)
 
 
+# ------------------------------------------------------------------ hrr / recovery phase
+def calculate_hrr(smoothed_bpm_series: pd.Series, interval_sec: int = 60) -> Optional[Dict]:
+    """bpm_analysis.py:1597-1610.  The abscissa of the interpolation is the index cast to int64 and
+    floor-divided by 1e9 (:1606) -- seconds only for a datetime64[ns] index; the pandas installed
+    here stores it as datetime64[us], and the restatement keeps that expression as it is."""
+    if smoothed_bpm_series.empty or len(smoothed_bpm_series) < 2:
+        return None
+    peak_bpm, peak_time = smoothed_bpm_series.max(), smoothed_bpm_series.idxmax()                  # :1600
+    check = peak_time + pd.Timedelta(seconds=interval_sec)                                         # :1601
+    if check > smoothed_bpm_series.index.max():                                                    # :1602
+        return None
+    recovery_bpm = np.interp(check.timestamp(),                                                    # :1604-1607
+                             (smoothed_bpm_series.index.astype(np.int64) // 10**9).to_numpy(dtype=float),
+                             np.asarray(smoothed_bpm_series.values, dtype=float))
+    return {"peak_bpm": peak_bpm, "peak_time": peak_time, "recovery_bpm": recovery_bpm,
+            "recovery_check_time": check, "hrr_value_bpm": peak_bpm - recovery_bpm, "interval_sec": interval_sec}
+
+
+def find_recovery_phase(bpm_series: pd.Series, bpm_times_sec: np.ndarray, params: Dict):
+    """bpm_analysis.py:1612-1620."""
+    if bpm_times_sec is None or len(bpm_times_sec) < 2:                                            # :1614
+        return None, None
+    peak_time_sec = bpm_times_sec[np.argmax(bpm_series.to_numpy())]                                # :1617
+    return peak_time_sec, peak_time_sec + params.get("recovery_phase_duration_sec", 120.0)         # :1618
+
+
 # ------------------------------------------------------------------ whole path
 def front_end(audio_data: np.ndarray, sample_rate: int, params: Dict) -> Dict[str, object]:
     """a1..a4 chained the way analyze_wav_file does (:1731-1732, :1635)."""
@@ -365,4 +391,6 @@ def beat_reductions(beats: np.ndarray, rate: int, params: Dict) -> Dict[str, obj
             "major_declines": find_major_hr_declines(series),
             "peak_recovery_stats": find_peak_recovery_rate(series),
             "peak_exertion_stats": find_peak_exertion_rate(series),
+            "hrr_stats": calculate_hrr(series),
+            "recovery_phase": find_recovery_phase(series, times, params),
             "windowed_hrv_df": calculate_windowed_hrv(beats, rate, params)}

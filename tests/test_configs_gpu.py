@@ -126,3 +126,90 @@ def test_c5_parameter_sweep(gpu, ref_params):
     assert all(x["n_peaks"] > 1000 and x["n_troughs"] > 1000 for x in ok)
     # settings that differ only in the noise floor share the band-pass, hence rate and length
     assert len({(x["rate"], x["m"]) for x in flat[16:32]}) == 1
+
+
+def _dropin_chain(frontend, pcm, sr, params, beat_idx):
+    """The ten drop-in calls in analyze_wav_file's order on host arrays (bpm_analysis.py:1731-1757)."""
+    class _Clf:
+        pass
+    clf = _Clf()
+    env, rate, _, _ = frontend.preprocess_pcm(pcm, sr, params, want_filtered=False)
+    floor, troughs = frontend._calculate_dynamic_noise_floor(env, rate, params)
+    clf.audio_envelope, clf.sample_rate, clf.params = env, rate, params
+    st1 = frontend._initialize_state(clf, None, floor, troughs)
+    st2 = frontend._initialize_state(clf, 80.0, floor, troughs)
+    sm, bt = frontend.calculate_bpm_series(beat_idx, rate, params)
+    return {"envelope": env, "rate": rate, "floor": floor, "troughs": troughs, "peaks": st2["all_peaks"],
+            "peaks_first": st1["all_peaks"], "smoothed_dev": st2["smoothed_dev_series"], "smoothed_bpm": sm,
+            "bpm_times": bt, "major_inclines": frontend.find_major_hr_inclines(sm),
+            "major_declines": frontend.find_major_hr_declines(sm), "hrr": frontend.calculate_hrr(sm),
+            "recovery": frontend.find_peak_recovery_rate(sm), "exertion": frontend.find_peak_exertion_rate(sm),
+            "hrv": frontend.calculate_windowed_hrv(beat_idx, rate, params)}
+
+
+def _check_against_oracle(got, fe, br):
+    assert rel_err(got["envelope"], fe["envelope"]) < TOL
+    assert rel_err(got["floor"].values, fe["floor"]) < TOL
+    assert np.array_equal(got["troughs"], fe["troughs"])
+    assert np.array_equal(got["peaks"], fe["peaks"]) and np.array_equal(got["peaks_first"], fe["peaks"])
+    assert rel_err(got["smoothed_dev"].values, fe["smoothed_dev_series"].values) < TOL
+    assert np.array_equal(got["smoothed_dev"].index.values, fe["smoothed_dev_series"].index.values)
+    assert got["smoothed_bpm"].index.equals(br["smoothed_bpm"].index)
+    assert rel_err(got["smoothed_bpm"].values, br["smoothed_bpm"].values) < TOL
+    assert np.array_equal(got["bpm_times"], br["bpm_times"])
+    for a, b in ((got["recovery"], br["peak_recovery_stats"]), (got["exertion"], br["peak_exertion_stats"])):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert a["start_time"] == b["start_time"] and a["end_time"] == b["end_time"]
+            assert a["slope_bpm_per_sec"] == b["slope_bpm_per_sec"] and a["duration_sec"] == b["duration_sec"]
+    for a, b in ((got["major_inclines"], br["major_inclines"]), (got["major_declines"], br["major_declines"])):
+        assert [(x["start_time"], x["end_time"]) for x in a] == [(x["start_time"], x["end_time"]) for x in b]
+    assert rel_err(got["hrv"].values, br["windowed_hrv_df"].values) < TOL
+
+
+def test_full_size_c2_matches_oracle_through_the_drop_in_functions(gpu, ref_params):
+    """The bench configuration itself (BASELINE configs[1]: 60 min @ 48 kHz, M = 1 086 793) against
+    the CPU oracle, through the drop-in functions: envelope / floor / deviation series to 1e-9,
+    trough and raw-peak lists and every beat-list reduction exact -- on the GPU's own envelope."""
+    from bpm_analysis_b200 import dropin, frontend, synth
+    from oracle import ref_port
+    pcm, sr, beats = synth.config_c2(seed=2)
+    d = dropin.dropin()
+    d.forget()
+    before = dict(d.stats)
+    fe = ref_port.front_end(pcm, sr, ref_params)
+    beat_idx = synth.beats_to_envelope_indices(beats, fe["rate"])
+    br = ref_port.beat_reductions(beat_idx, fe["rate"], ref_params)
+    got = _dropin_chain(frontend, pcm, sr, ref_params, beat_idx)
+    assert len(got["envelope"]) == 1086793 and got["rate"] == 301
+    _check_against_oracle(got, fe, br)
+    assert len(fe["peaks"]) > 10000 and len(br["windowed_hrv_df"]) > 1000 and len(br["major_inclines"]) >= 1
+    after = dict(d.stats)
+    assert after["stage_a_calls"] - before["stage_a_calls"] == 1        # the whole chain cost one stage-A call
+    assert after["session_misses"] == before["session_misses"]          # nothing was uploaded a second time
+
+
+def test_c4_two_hours_match_oracle_one_shot_and_chunked(gpu, ref_params):
+    """C4 (4 kHz Holter stream with bursts and dropouts), first 2 h (M = 2.4 M): the one-shot drop-in
+    chain AND the halo-chunked front end (4 ranks) against the CPU oracle."""
+    from bpm_analysis_b200 import frontend, stream, synth
+    from oracle import ref_port
+    pcm, sr, beats = synth.config_c4(seed=4, duration_sec=7200.0)
+    fe = ref_port.front_end(pcm, sr, ref_params)
+    beat_idx = synth.beats_to_envelope_indices(beats, fe["rate"])
+    br = ref_port.beat_reductions(beat_idx, fe["rate"], ref_params)
+    got = _dropin_chain(frontend, pcm, sr, ref_params, beat_idx)
+    assert len(got["envelope"]) == 2400000
+    _check_against_oracle(got, fe, br)
+    eng = stream.DeviceEngine()
+
+    def body(comm):
+        f = stream.ChunkedFrontEnd(len(pcm), sr, ref_params, comm, eng)
+        f0, f1 = f.frames()
+        out = f.run(eng.tensor(pcm[f0:f1]))
+        gpu.cuda.synchronize()
+        return {k: v.cpu().numpy() for k, v in out.items() if k in ("envelope", "floor", "troughs", "peaks")}
+
+    for ch in stream.run_thread_world(4, body)[:2]:
+        assert rel_err(ch["envelope"], fe["envelope"]) < TOL and rel_err(ch["floor"], fe["floor"]) < TOL
+        assert np.array_equal(ch["troughs"], fe["troughs"]) and np.array_equal(ch["peaks"], fe["peaks"])

@@ -1,0 +1,139 @@
+"""The session layer behind the drop-in functions (bpm_analysis_b200/dropin.py): results handed
+from one reference call to the next are served from the device-side session, arrays that did not
+come out of a session take the generic path, and stale or edited arrays are never trusted."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def svc():
+    import torch
+    assert torch.cuda.is_available(), "gpu-marked tests need a CUDA device"
+    from bpm_analysis_b200 import _native, dropin
+    _native.load_library()
+    return dropin.dropin()
+
+
+class _Clf:
+    def __init__(self, env, rate, params):
+        self.audio_envelope, self.sample_rate, self.params = env, rate, params
+
+
+def test_chain_is_served_from_one_stage_a_call(svc, ref_params, synth_inputs):
+    from bpm_analysis_b200 import frontend
+    from oracle import ref_port
+    pcm, sr = synth_inputs["c2_240s"]
+    svc.forget()
+    s0 = dict(svc.stats)
+    env, rate, filt, dbg = frontend.preprocess_pcm(pcm, sr, ref_params, want_debug=True)
+    floor, troughs = frontend._calculate_dynamic_noise_floor(env, rate, ref_params)
+    clf = _Clf(env, rate, ref_params)
+    st1 = frontend._initialize_state(clf, None, floor, troughs)
+    peaks_only = frontend._find_raw_peaks(clf, floor.values)
+    st2 = frontend._initialize_state(clf, 75.0, floor, troughs)
+    s1 = dict(svc.stats)
+    assert s1["stage_a_calls"] - s0["stage_a_calls"] == 1 and s1["session_misses"] == s0["session_misses"]
+    o = ref_port.front_end(pcm, sr, ref_params)
+    assert rel_err(env, o["envelope"]) < TOL and rel_err(filt, o["filtered"]) < TOL
+    assert rel_err(floor.values, o["floor"]) < TOL
+    assert np.array_equal(troughs, o["troughs"]) and troughs.dtype == np.int64
+    for p in (st1["all_peaks"], st2["all_peaks"], peaks_only):
+        assert np.array_equal(p, o["peaks"])
+    assert st1["all_peaks"] is not st2["all_peaks"]                  # callers own what they get
+    assert rel_err(st2["smoothed_dev_series"].values, o["smoothed_dev_series"].values) < TOL
+    assert st2["long_term_bpm"] == 75.0 and st1["long_term_bpm"] == 80.0
+    assert dbg.dtype == np.int16 and len(dbg) == len(env)
+
+
+def test_foreign_arrays_take_the_generic_path_and_stay_resident(svc, ref_params):
+    """The reference's own envelope (a plain numpy array): uploaded once for the three calls."""
+    from bpm_analysis_b200 import frontend
+    g = load_golden("vulpine")
+    env, rate = g["envelope"].copy(), int(g["rate"])
+    svc.forget()
+    s0 = dict(svc.stats)
+    floor, troughs = frontend._calculate_dynamic_noise_floor(env, rate, ref_params)
+    clf = _Clf(env, rate, ref_params)
+    peaks = frontend._find_raw_peaks(clf, floor.values)
+    st = frontend._initialize_state(clf, None, floor, troughs)
+    s1 = dict(svc.stats)
+    assert s1["session_misses"] - s0["session_misses"] == 1 and s1["stage_a_calls"] == s0["stage_a_calls"]
+    assert np.array_equal(troughs, g["troughs"]) and np.array_equal(peaks, g["raw_peaks"])
+    assert np.array_equal(st["all_peaks"], g["raw_peaks"]) and rel_err(floor.values, g["floor"]) < TOL
+
+
+def test_edited_or_recycled_arrays_are_not_trusted(svc, ref_params, synth_inputs):
+    from bpm_analysis_b200 import frontend
+    from oracle import ref_port
+    pcm, sr = synth_inputs["c1_30s"]
+    svc.forget()
+    env, rate, _, _ = frontend.preprocess_pcm(pcm, sr, ref_params, want_filtered=False)
+    floor, troughs = frontend._calculate_dynamic_noise_floor(env, rate, ref_params)
+    # the caller scales its envelope in place: the session must notice and recompute from the new content
+    env *= 2.0
+    floor2, troughs2 = frontend._calculate_dynamic_noise_floor(env, rate, ref_params)
+    o_floor, o_troughs = ref_port.calculate_dynamic_noise_floor(env, rate, ref_params)
+    assert np.array_equal(troughs2, o_troughs) and rel_err(floor2.values, o_floor.values) < TOL
+    # a different floor for the same envelope (e.g. a caller's own threshold array)
+    clf = _Clf(env, rate, ref_params)
+    other = np.full(len(env), float(np.quantile(env, 0.5)))
+    pk = frontend._find_raw_peaks(clf, other)
+    assert np.array_equal(pk, ref_port.find_raw_peaks(env, rate, ref_params, other))
+    # different parameters for the same arrays
+    p2 = dict(ref_params, noise_window_sec=4, noise_floor_quantile=0.3, peak_prominence_quantile=0.25)
+    f3, t3 = frontend._calculate_dynamic_noise_floor(env, rate, p2)
+    o3, ot3 = ref_port.calculate_dynamic_noise_floor(env, rate, p2)
+    assert np.array_equal(t3, ot3) and rel_err(f3.values, o3.values) < TOL
+    pk3 = frontend._find_raw_peaks(_Clf(env, rate, p2), f3.values)
+    assert np.array_equal(pk3, ref_port.find_raw_peaks(env, rate, p2, o3.values))
+
+
+def test_beat_list_reductions_share_one_round_trip(svc, ref_params, synth_inputs):
+    from bpm_analysis_b200 import frontend, synth
+    from oracle import ref_port
+    pcm, sr, beats = synth.config_c2(seed=9, duration_sec=600.0)
+    bi = synth.beats_to_envelope_indices(beats, 301)
+    svc.forget()
+    s0 = dict(svc.stats)
+    sm, bt = frontend.calculate_bpm_series(bi, 301, ref_params)
+    inc, dec = frontend.find_major_hr_inclines(sm), frontend.find_major_hr_declines(sm)
+    rec, exe = frontend.find_peak_recovery_rate(sm), frontend.find_peak_exertion_rate(sm)
+    hrv = frontend.calculate_windowed_hrv(bi, 301, ref_params)
+    s1 = dict(svc.stats)
+    assert s1["beat_misses"] - s0["beat_misses"] == 1 and s1["beat_hits"] - s0["beat_hits"] == 1
+    o = ref_port.beat_reductions(bi, 301, ref_params)
+    assert sm.index.equals(o["smoothed_bpm"].index) and rel_err(sm.values, o["smoothed_bpm"].values) < TOL
+    assert [(x["start_time"], x["end_time"]) for x in inc] == [(x["start_time"], x["end_time"]) for x in o["major_inclines"]]
+    assert [(x["start_time"], x["end_time"]) for x in dec] == [(x["start_time"], x["end_time"]) for x in o["major_declines"]]
+    assert rec["slope_bpm_per_sec"] == o["peak_recovery_stats"]["slope_bpm_per_sec"]
+    assert exe["slope_bpm_per_sec"] == o["peak_exertion_stats"]["slope_bpm_per_sec"]
+    assert rel_err(hrv.values, o["windowed_hrv_df"].values) < TOL
+    # a Series that did not come from calculate_bpm_series (shifted copy) takes the generic kernels
+    other = sm * 1.0 + 0.25
+    r2 = frontend.find_peak_recovery_rate(other)
+    assert r2["slope_bpm_per_sec"] == ref_port.find_peak_recovery_rate(other)["slope_bpm_per_sec"]
+    # non-default arguments as well
+    r3 = frontend.find_peak_exertion_rate(sm, window_sec=35)
+    assert r3["slope_bpm_per_sec"] == ref_port.find_peak_exertion_rate(sm, window_sec=35)["slope_bpm_per_sec"]
+    i4 = frontend.find_major_hr_inclines(sm, min_duration_sec=30)
+    assert [(x["start_time"], x["end_time"]) for x in i4] == \
+        [(x["start_time"], x["end_time"]) for x in ref_port.find_major_hr_inclines(sm, min_duration_sec=30)]
+
+
+def test_hrr_and_recovery_phase_mirrors(svc, ref_params):
+    from bpm_analysis_b200 import frontend, synth
+    from oracle import ref_port
+    _, _, beats = synth.config_c2(seed=3, duration_sec=900.0)
+    bi = synth.beats_to_envelope_indices(beats, 301)
+    sm, bt = frontend.calculate_bpm_series(bi, 301, ref_params)
+    got, want = frontend.calculate_hrr(sm), ref_port.calculate_hrr(sm)
+    assert (got is None) == (want is None)
+    if got is not None:
+        assert got.keys() == want.keys() and all(got[k] == want[k] for k in got)
+    assert frontend.find_recovery_phase(sm, bt, ref_params) == ref_port.find_recovery_phase(sm, bt, ref_params)
+    assert frontend.find_recovery_phase(sm, bt[:1], ref_params) == (None, None)

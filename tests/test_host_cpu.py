@@ -133,7 +133,8 @@ def test_items_layout():
 
 
 def test_bench_reference_arm_prints_one_json_line():
-    """bench.py --impl reference runs on the CPU (oracle port on the host cores) and must print
+    """bench.py --impl reference runs on the CPU (the unmodified reference from baseline/_ref when it is
+    installed there, else the oracle port, on the host cores) and must print
     exactly one JSON line with the contract's keys; stdout carries nothing else."""
     import json
     import subprocess
@@ -147,7 +148,9 @@ def test_bench_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "audio_hours_per_sec" and d["unit"] == "audio-hours/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    from baseline import ref_loader
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_loader.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
 
 
@@ -164,3 +167,52 @@ def test_copy_frames_rejects_bad_arguments_without_touching_the_device(lib):
     assert lib.bpm_copy_frames(ctypes.addressof(buf), 0, 1, ok_items, 1, 0, ctypes.addressof(buf), None) == -1     # stride
     bad = make_items([1000], [8])
     assert lib.bpm_copy_frames(ctypes.addressof(buf), 0, 1, bad.ctypes.data, 1, 159, ctypes.addressof(buf), None) == -1
+
+
+def test_design_cache_is_keyed_by_value_and_bounded(monkeypatch):
+    """More designs than design_block_filter's lru_cache holds (256): evicted design objects are
+    collected and CPython reuses their id(); the device cache must still hand every plan ITS image."""
+    import torch
+    from bpm_analysis_b200 import runtime
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(runtime, "to_device", lambda a: torch.from_numpy(np.array(a, copy=True)))
+    runtime._design_cache.clear()
+    p = P.default_params()
+    n = 0
+    for k in range(320):
+        params = dict(p, lowcut_hz=15.0 + 0.01 * k, highcut_hz=120.0 + 0.02 * k)
+        plan = runtime.plan_filter(48000, params)
+        dev, host = runtime.design_images(plan)
+        assert np.array_equal(dev.numpy(), plan.design.packed()) and np.array_equal(host, plan.design.packed())
+        n += 1
+    assert n == 320 and len(runtime._design_cache) <= runtime.DESIGN_CACHE_SIZE
+    # and a repeat of an early (long evicted) design is rebuilt, not confused with a newer one
+    plan = runtime.plan_filter(48000, dict(p, lowcut_hz=15.0, highcut_hz=120.0))
+    dev, _ = runtime.design_images(plan)
+    assert np.array_equal(dev.numpy(), plan.design.packed())
+    runtime._design_cache.clear()
+
+
+def test_host_gather_frames_matches_numpy_slicing():
+    """bpm_host_gather_frames == audio_data[::stride] (bpm_analysis.py:1033) for every frame size."""
+    import ctypes as C
+    from bpm_analysis_b200 import classifier
+    from bpm_analysis_b200.build import build_host
+    build_host()
+    lib = classifier.load_host_library()
+    assert lib.bpm_host_threads() >= 1
+    rng = np.random.default_rng(5)
+    for dtype, ch, n, stride in ((np.int16, 1, 1000003, 159), (np.int16, 2, 300001, 146), (np.uint8, 1, 70001, 12),
+                                 (np.float32, 1, 99999, 7), (np.float64, 3, 4100, 3), (np.int32, 1, 17, 1),
+                                 (np.int16, 1, 5, 300)):
+        x = rng.integers(-100, 100, size=(n, ch)).astype(dtype)
+        if ch == 1:
+            x = x[:, 0].copy()
+        want = x[::stride]
+        out = np.empty_like(want)
+        for threads in (0, 1, 3):
+            out[...] = 0
+            rc = lib.bpm_host_gather_frames(C.c_void_p(x.ctypes.data), x.dtype.itemsize * ch, n, stride,
+                                            C.c_void_p(out.ctypes.data), threads)
+            assert rc == 0 and np.array_equal(out, want)
+    assert lib.bpm_host_gather_frames(None, 2, 10, 1, None, 0) != 0

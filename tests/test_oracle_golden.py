@@ -109,3 +109,23 @@ def test_synth_oracle_matches_reference(name, ref_params, synth_inputs):
                 assert pd.Timestamp(d["start_time"]).as_unit("us").value == int(g[key + "_start_us"])
         assert len(r["major_inclines"]) == int(g["inclines_n"])
         assert len(r["major_declines"]) == int(g["declines_n"])
+
+
+@pytest.mark.parametrize("name", ["vulpine"] + ["synth_" + n for n in SYNTH])
+def test_hrr_and_recovery_phase_match_reference(name, ref_params):
+    """calculate_hrr / find_recovery_phase (bpm_analysis.py:1597-1620) as the unmodified reference
+    evaluated them on its own final beat list -- including what the installed pandas does with the
+    index arithmetic of :1604-1607 (vulpine: 75.5, not the 58.9 of the shipped summary)."""
+    g = load_golden(name)
+    if len(g["beats"]) < 2:
+        pytest.skip("no beat series in this fixture")
+    r = ref_port.beat_reductions(g["beats"], int(g["rate"]), ref_params)
+    hrr = r["hrr_stats"]
+    assert (hrr is not None) == bool(g["hrr_found"])
+    if hrr is not None:
+        assert np.array_equal([hrr["peak_bpm"], hrr["recovery_bpm"], hrr["hrr_value_bpm"], hrr["interval_sec"]],
+                              g["hrr_values"])
+        assert [pd.Timestamp(hrr["peak_time"]).as_unit("us").value,
+                pd.Timestamp(hrr["recovery_check_time"]).as_unit("us").value] == list(g["hrr_times_us"])
+    want = [None if np.isnan(v) else float(v) for v in g["recovery_phase"]]
+    assert list(r["recovery_phase"]) == want
