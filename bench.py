@@ -151,6 +151,7 @@ def algorithmic_bytes(kernel: str, shp: dict, mode: str = "parity") -> float:
     """Compulsory bytes per launch of one kernel at its own interface:
     every input element it needs read once + every output element written once."""
     N, M, T, P, B = shp["N"], shp["M"], shp["T"], shp["P"], shp["B"]
+    C = shp.get("C", 4 * max(T, P))                      # local maxima before the distance / prominence rules
     s_in = 2
     table = {
         "k_contract_i16": N * s_in + 8 * M,            # SURVEY §8(d): N*s_in + 8*M
@@ -162,10 +163,10 @@ def algorithmic_bytes(kernel: str, shp: dict, mode: str = "parity") -> float:
         "k_envelope": 16 * M,
         "k_select_pass": 8 * M,
         "k_select_next": 8 * M,
-        "k_localmax_flags": 9 * M,
-        "k_scatter": M + 8 * max(T, P),
-        "k_distance": 17 * max(T, P), "k_prominence": 24 * max(T, P),
-        "k_count_flags": max(T, P),
+        # parity mode: fwd reads M*s_in frames, writes y_f (8 M); bwd reads y_f, writes the envelope (8 M)
+        "k_sos_fwd": (s_in + 8) * M, "k_sos_bwd": 16 * M,
+        "k_localmax_compact": 8 * M + 8 * C, "k_distance_tiles": 17 * C, "k_prominence_compact": 17 * C + 8 * max(T, P),
+        "k_sanitize_compact": 24 * T,
         "k_knot_table": 40 * T,
         "k_rolling_floor": 16 * T + 8 * M,             # SURVEY §8(d) K5+K6
         "k_rolling_floor_blk": 16 * T + 8 * M,
@@ -186,15 +187,17 @@ PIPE_INGEST = {
           "kept frame); ",
 }
 
-BEAT_BRANCH_KERNELS = {"k_find_peaks_small", "k_steepest", "k_bpm_instant", "k_bpm_smooth", "k_hrv"}
+BEAT_BRANCH_KERNELS = {"k_steepest", "k_bpm_instant", "k_bpm_smooth", "k_hrv"}
 
 ROOFLINE_NOTES = {
     "k_rolling_floor_blk": "bounded by shared-memory latency / instruction issue, not HBM: an exact rolling quantile "
                            "(sample sort + sliding rank pointer per CTA) whose algorithmic traffic is 8 B per output; "
                            "the HBM fraction is reported because the contract asks for it (DESIGN.md section 4)",
     "k_contract_i16": "HBM and FP64-pipe bound together: 8 DFMA per 2-byte sample",
-    "k_scan": "forward pass: strided PCM gather (one 128-byte DRAM fetch per 2-byte kept frame, see traffic) + dependent "
-              "FP64 chains of the 4x4 state recurrence; two waves of CTAs whose phases are serialised by barriers",
+    "k_sos_fwd": "forward cascade scan over the extended signal; gathers the strided PCM itself (ld.global.L2::64B: one "
+                 "64-byte DRAM fetch per 2-byte kept frame -- the algorithmic bytes count the 2 bytes)",
+    "k_sos_bwd": "backward cascade scan with |y| and the centred rolling mean formed in its epilogue; the band-passed "
+                 "signal never reaches HBM",
 }
 
 

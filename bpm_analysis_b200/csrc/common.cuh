@@ -178,6 +178,50 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* smem
   return res;
 }
 
+// ------------------------------------------------------------- single-pass ordered compaction
+// Decoupled look-back over per-tile counts: a tile publishes (status | count) as ONE 64-bit word
+// -- status 1: this tile's own count, status 2: inclusive prefix up to and including this tile --
+// and then reads its predecessors' words, newest first, until it meets an inclusive prefix.  Tiles
+// only ever wait for tiles with a smaller index (already resident or finished).  `status` points
+// at the recording's first word; the words must be zero before the launch.
+constexpr unsigned long long LB_VALUE_MASK = (1ull << 62) - 1ull;
+
+// Called by ALL 32 lanes of one warp; returns the number of elements in tiles before `tile`.
+__device__ __forceinline__ long long lookback_exclusive(unsigned long long* status, long long tile, long long my_count) {
+  const int lane = threadIdx.x & 31;
+  volatile unsigned long long* st = status;
+  if (tile == 0) {
+    if (lane == 0) st[0] = (2ull << 62) | static_cast<unsigned long long>(my_count);
+    return 0;
+  }
+  if (lane == 0) st[tile] = (1ull << 62) | static_cast<unsigned long long>(my_count);
+  long long excl = 0;
+  long long base = tile - 1;
+  while (true) {
+    const long long t = base - lane;
+    unsigned long long w = (2ull << 62);                        // before the first tile: inclusive prefix 0
+    if (t >= 0) {
+      do { w = st[t]; } while ((w >> 62) == 0ull);
+    }
+    const unsigned incl = __ballot_sync(0xffffffffu, (w >> 62) == 2ull);
+    long long v = static_cast<long long>(w & LB_VALUE_MASK);
+    if (incl) {
+      const int first = __ffs(incl) - 1;                        // nearest tile holding an inclusive prefix
+      if (lane > first) v = 0;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      excl += v;
+      break;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    excl += v;
+    base -= 32;
+  }
+  if (lane == 0) st[tile] = (2ull << 62) | static_cast<unsigned long long>(excl + my_count);
+  return excl;
+}
+
 // x' = sign * x with sign in {+1, -1} (exact)
 __device__ __forceinline__ double signed_val(double v, int sign) { return sign < 0 ? -v : v; }
 

@@ -1219,23 +1219,56 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rolling_floor_blk(
 }
 
 // K7: keep trough t iff the draft floor there is not NaN and env[t] <= mult * floor[t]
-// (bpm_analysis.py:1090-1097).  keep_all[item] != 0 keeps every trough (the <5 troughs path
+// (bpm_analysis.py:1090-1097), written in order by a single-pass compaction (decoupled look-back
+// over tile counts, common.cuh).  keep_all[item] != 0 keeps every trough (the <5 troughs path
 // returns the unsanitised list, :1077).
-__global__ void k_sanitize_flags(const double* __restrict__ env, const double* __restrict__ draft,
-                                 const int64_t* __restrict__ troughs, const int64_t* __restrict__ trough_count,
-                                 const int* __restrict__ keep_all, const BpmItem* __restrict__ items, double mult,
-                                 int draft_by_knot, unsigned char* __restrict__ flags) {
+constexpr int SZ_THREADS = 256;
+constexpr int SZ_PER = 4;
+constexpr int SZ_TILE = SZ_THREADS * SZ_PER;
+
+__global__ void __launch_bounds__(SZ_THREADS) k_sanitize_compact(
+    const double* __restrict__ env, const double* __restrict__ draft, const int64_t* __restrict__ troughs,
+    const int64_t* __restrict__ trough_count, const int* __restrict__ keep_all, const BpmItem* __restrict__ items,
+    double mult, int draft_by_knot, unsigned long long* __restrict__ status, int64_t status_stride,
+    int64_t* __restrict__ kept_out, int64_t* __restrict__ kept_count) {
+  __shared__ int s_scan[34];
+  __shared__ long long s_off;
   const int item = blockIdx.y;
   const BpmItem it = items[item];
-  const long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (k >= trough_count[item]) return;
-  bool keep = true;
-  if (!(keep_all && keep_all[item])) {
-    const int64_t t = troughs[it.m_off + k];
-    const double f = draft_by_knot ? draft[it.m_off + k] : draft[it.m_off + t];   // dense floor, or one value per trough
-    keep = !isnan(f) && env[it.m_off + t] <= __dmul_rn(mult, f);
+  const long long nt = trough_count[item];
+  const long long k0 = static_cast<long long>(blockIdx.x) * SZ_TILE;
+  if (k0 >= nt) {
+    if (nt == 0 && blockIdx.x == 0 && threadIdx.x == 0) kept_count[item] = 0;
+    return;
   }
-  flags[it.m_off + k] = keep ? 1 : 0;
+  const bool all = keep_all && keep_all[item];
+  int64_t t[SZ_PER];
+  unsigned mask = 0;
+#pragma unroll
+  for (int u = 0; u < SZ_PER; ++u) {
+    const long long k = k0 + threadIdx.x * SZ_PER + u;
+    t[u] = 0;
+    if (k >= nt) continue;
+    t[u] = troughs[it.m_off + k];
+    bool keep = true;
+    if (!all) {
+      const double f = draft_by_knot ? draft[it.m_off + k] : draft[it.m_off + t[u]];   // one value per trough, or dense
+      keep = !isnan(f) && env[it.m_off + t[u]] <= __dmul_rn(mult, f);
+    }
+    if (keep) mask |= 1u << u;
+  }
+  int total;
+  const int ex = block_exclusive_scan(__popc(mask), &total, s_scan);
+  if (threadIdx.x < 32) {
+    const long long off = lookback_exclusive(status + static_cast<int64_t>(item) * status_stride, blockIdx.x, total);
+    if (threadIdx.x == 0) s_off = off;
+  }
+  __syncthreads();
+  int64_t o = it.m_off + s_off + ex;
+#pragma unroll
+  for (int u = 0; u < SZ_PER; ++u)
+    if ((mask >> u) & 1) kept_out[o++] = t[u];
+  if (threadIdx.x == 0 && k0 + SZ_TILE >= nt) kept_count[item] = s_off + total;
 }
 
 // per-item control words of _calculate_dynamic_noise_floor
@@ -1260,15 +1293,26 @@ __global__ void k_floor_modes(const int64_t* __restrict__ n_all, const int64_t* 
   }
 }
 
-// host launchers of the two small kernels above (called from pipeline.cu: every translation unit
+// host launchers of the small kernels above (called from pipeline.cu: every translation unit
 // launches only kernels it defines, so no relocatable device code is needed)
-int sanitize_flags_run(const double* env, const double* draft, const int64_t* troughs, const int64_t* trough_count,
-                       const int* keep_all, const BpmItem* items, const BatchShape& sh, double mult, int draft_by_knot,
-                       unsigned char* flags, cudaStream_t st) {
-  BPM_KERNEL(k_sanitize_flags);
-  k_sanitize_flags<<<dim3(cdiv(sh.max_m / 2 + 2, 256), sh.n_items), 256, 0, st>>>(env, draft, troughs, trough_count,
-                                                                                 keep_all, items, mult, draft_by_knot,
-                                                                                 flags);
+size_t sanitize_workspace_bytes(int64_t total_m, int n) {
+  Workspace ws(nullptr, 0);
+  ws.take<unsigned long long>(static_cast<size_t>(n) * ((total_m / 2 + 2) / SZ_TILE + 2));
+  return ws.used;
+}
+
+int sanitize_run(const double* env, const double* draft, const int64_t* troughs, const int64_t* trough_count,
+                 const int* keep_all, const BpmItem* items, const BatchShape& sh, double mult, int draft_by_knot,
+                 int64_t* kept_out, int64_t* kept_count, Workspace& ws, cudaStream_t st) {
+  if (!env || !draft || !troughs || !trough_count || !items || !kept_out || !kept_count) return BPM_ERR_ARG;
+  const int64_t max_t = sh.max_m / 2 + 2;
+  const int64_t stride = max_t / SZ_TILE + 2;
+  unsigned long long* status = ws.take<unsigned long long>(static_cast<size_t>(sh.n_items) * stride);
+  if (ws.overflow) return BPM_ERR_WORKSPACE;
+  if (cudaMemsetAsync(status, 0, sizeof(unsigned long long) * sh.n_items * stride, st) != cudaSuccess) return BPM_ERR_CUDA;
+  BPM_KERNEL(k_sanitize_compact);
+  k_sanitize_compact<<<dim3(cdiv(max_t, SZ_TILE), sh.n_items), SZ_THREADS, 0, st>>>(
+      env, draft, troughs, trough_count, keep_all, items, mult, draft_by_knot, status, stride, kept_out, kept_count);
   BPM_LAUNCH_OK();
   return BPM_OK;
 }

@@ -28,9 +28,6 @@ size_t find_peaks_workspace_bytes(int64_t total_m, int n_items);
 int find_peaks_run(const double* x, int sign, const double* height, const double* prominence, int distance,
                    const BpmItem* items, const BatchShape& sh, int64_t* out_idx, int64_t* out_count,
                    Workspace& ws, cudaStream_t st, cudaEvent_t prominence_ready = nullptr);
-int compact_run(const unsigned char* flags, const int64_t* src, const BpmItem* items, const BatchShape& sh,
-                const int64_t* dom_len, int64_t max_len, bool counts_ready, int* tile_counts, int64_t* out,
-                int64_t* out_count, cudaStream_t st);
 // floor.cu
 size_t rolling_floor_workspace_bytes(int64_t total_m, int n_items);
 bool rolling_floor_sparse_ok(int window);
@@ -38,9 +35,10 @@ int rolling_floor_run(const double* env, const int64_t* knots, const int64_t* kn
                       const BatchShape& sh, int window, double q, const int* mode, const int64_t* alt_knots,
                       const int64_t* alt_count, const double* cval, const double* nan_fill, double* out,
                       double* sparse_out, Workspace& ws, cudaStream_t st);
-int sanitize_flags_run(const double* env, const double* draft, const int64_t* troughs, const int64_t* trough_count,
-                       const int* keep_all, const BpmItem* items, const BatchShape& sh, double mult, int draft_by_knot,
-                       unsigned char* flags, cudaStream_t st);
+size_t sanitize_workspace_bytes(int64_t total_m, int n);
+int sanitize_run(const double* env, const double* draft, const int64_t* troughs, const int64_t* trough_count,
+                 const int* keep_all, const BpmItem* items, const BatchShape& sh, double mult, int draft_by_knot,
+                 int64_t* kept_out, int64_t* kept_count, Workspace& ws, cudaStream_t st);
 int floor_modes_run(const int64_t* n_all, const int64_t* n_kept, int n_items, int stage, int* few, int* mode,
                     int64_t* total_out, int64_t* mode_out, cudaStream_t st);
 // metrics.cu
@@ -69,8 +67,8 @@ struct NoiseFloorScratch {
   double* draft;
   int* few;
   int* mode;
-  unsigned char* keep;
-  int* tile_counts;
+  char* sanitize_ws;
+  size_t sanitize_ws_bytes;
   char* select_ws;          // the quantile passes run concurrently with the trough search: own scratch
   size_t select_ws_bytes;
 };
@@ -84,8 +82,8 @@ static int carve_noise_floor(Workspace& ws, int64_t total_m, int n, NoiseFloorSc
   s->draft = ws.take<double>(total_m);
   s->few = ws.take<int>(n);
   s->mode = ws.take<int>(n);
-  s->keep = ws.take<unsigned char>(total_m);
-  s->tile_counts = ws.take<int>(total_m / 2048 + n + 1);
+  s->sanitize_ws_bytes = sanitize_workspace_bytes(total_m, n);
+  s->sanitize_ws = ws.take<char>(s->sanitize_ws_bytes);
   s->select_ws_bytes = quantile_workspace_bytes(n);
   s->select_ws = ws.take<char>(s->select_ws_bytes);
   return ws.overflow ? BPM_ERR_WORKSPACE : BPM_OK;
@@ -159,10 +157,11 @@ int noise_floor_run(const double* env, const BpmItem* items, const BatchShape& s
     BPM_TRY(rolling_floor_run(env, s.all_troughs, s.n_all, items, sh, window, floor_q, s.mode, nullptr, nullptr, s.q_nf,
                               nullptr, sparse ? nullptr : s.draft, sparse ? s.draft : nullptr, w, st));
   }
-  BPM_TRY(sanitize_flags_run(env, s.draft, s.all_troughs, s.n_all, s.few, items, sh, mult, sparse ? 1 : 0, s.keep,
-                             st));                                                                   // :1090-1097
-  BPM_TRY(compact_run(s.keep, s.all_troughs, items, sh, s.n_all, sh.max_m / 2 + 2, false, s.tile_counts,
-                      troughs_out, trough_count, st));
+  {
+    Workspace wz(ws.measuring() ? nullptr : s.sanitize_ws, s.sanitize_ws_bytes);
+    BPM_TRY(sanitize_run(env, s.draft, s.all_troughs, s.n_all, s.few, items, sh, mult, sparse ? 1 : 0, troughs_out,
+                         trough_count, wz, st));                                                     // :1090-1097
+  }
   BPM_TRY(floor_modes_run(s.n_all, trough_count, n, 1, s.few, s.mode, total_out, mode_out, st));
   {
     // final floor from the kept troughs (:1102-1106); when <= 2 are kept the reference reuses the
@@ -178,25 +177,8 @@ int noise_floor_run(const double* env, const BpmItem* items, const BatchShape& s
 
 // ------------------------------------------------------------------ K7 on its own
 // Used when a long recording is processed as halo-overlapped time chunks (stream.py): the draft
-// floor of a chunk exists only on the rank that owns it, so that rank sanitises its troughs.
-size_t sanitize_workspace_bytes(int64_t total_m, int n) {
-  Workspace ws(nullptr, 0);
-  ws.take<unsigned char>(total_m);
-  ws.take<int>(total_m / 2048 + n + 1);
-  return ws.used;
-}
-
-int sanitize_run(const double* env, const double* draft, const int64_t* troughs, const int64_t* trough_count,
-                 const BpmItem* items, const BatchShape& sh, double mult, int64_t* kept_out, int64_t* kept_count,
-                 Workspace& ws, cudaStream_t st) {
-  if (!env || !draft || !troughs || !trough_count || !items || !kept_out || !kept_count) return BPM_ERR_ARG;
-  unsigned char* keep = ws.take<unsigned char>(sh.total_m);
-  int* tile_counts = ws.take<int>(sh.total_m / 2048 + sh.n_items + 1);
-  if (ws.overflow) return BPM_ERR_WORKSPACE;
-  BPM_TRY(sanitize_flags_run(env, draft, troughs, trough_count, nullptr, items, sh, mult, 0, keep, st));
-  return compact_run(keep, troughs, items, sh, trough_count, sh.max_m / 2 + 2, false, tile_counts, kept_out,
-                     kept_count, st);
-}
+// floor of a chunk exists only on the rank that owns it, so that rank sanitises its troughs
+// (sanitize_run, floor.cu).
 
 // ------------------------------------------------------------------ a3
 size_t raw_peaks_workspace_bytes(int64_t total_m, int n) {
@@ -407,8 +389,8 @@ int bpm_sanitize_troughs(const double* envelope, const double* draft_floor, cons
                          size_t workspace_bytes, void* stream) {
   if (!workspace || !items_host || n_items <= 0) return BPM_ERR_ARG;
   Workspace ws(workspace, workspace_bytes);
-  return sanitize_run(envelope, draft_floor, troughs, trough_count, items, batch_shape(items_host, n_items),
-                      rejection_multiplier, kept_out, kept_count, ws, static_cast<cudaStream_t>(stream));
+  return sanitize_run(envelope, draft_floor, troughs, trough_count, nullptr, items, batch_shape(items_host, n_items),
+                      rejection_multiplier, 0, kept_out, kept_count, ws, static_cast<cudaStream_t>(stream));
 }
 
 size_t bpm_raw_peaks_workspace_bytes(int64_t total_m, int n_items) { return raw_peaks_workspace_bytes(total_m, n_items); }

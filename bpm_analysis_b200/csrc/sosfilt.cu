@@ -25,6 +25,7 @@
 // SS_TILE samples but only the first SS_TILE - SS_HALO of them enter its aggregate; the remaining
 // SS_HALO samples are scanned again by the next tile, so every tile holds all |y| its envelope
 // windows need (w - 1 <= SS_HALO; wider windows take the separate k_envelope kernel of filter.cu).
+#include <stdlib.h>
 #include "filter_common.cuh"
 
 namespace bpm {
@@ -72,6 +73,16 @@ __device__ __forceinline__ void ss_matvec(const double (&M)[16], const double v[
   for (int r = 0; r < 4; ++r) out[r] = M[4 * r] * v[0] + M[4 * r + 1] * v[1] + M[4 * r + 2] * v[2] + M[4 * r + 3] * v[3];
 }
 
+// One int16 frame of a STRIDED gather.  A plain load makes L2 fetch 128 bytes of DRAM for the 2 bytes
+// wanted; the 64-byte prefetch-size hint halves that (measured on B200, tools/gather_probe.cu: 139 MB
+// -> 69.6 MB of DRAM reads and 25 -> 18.7 us for the 1.09 M frames of a 60-minute 48 kHz recording;
+// cudaLimitMaxL2FetchGranularity = 32 changes nothing).
+__device__ __forceinline__ double ss_load_i16_strided(const int16_t* p) {
+  short v;
+  asm volatile("ld.global.L2::64B.s16 %0, [%1];" : "=h"(v) : "l"(p));
+  return static_cast<double>(v);
+}
+
 // one sample through the cascade (direct form II transposed), coefficients from the constant bank
 __device__ __forceinline__ double ss_step(const double (&sos)[12], double s[4], double x) {
 #pragma unroll
@@ -84,10 +95,28 @@ __device__ __forceinline__ double ss_step(const double (&sos)[12], double s[4], 
   return x;
 }
 
-template <int DIR /*0 forward from PCM, 1 backward from y_f*/, int MONO16 /*DIR 0: mono int16 fast path*/>
-__global__ void __launch_bounds__(SS_THREADS, 3) k_sos_scan(const __grid_constant__ SosScanArgs a) {
+// fill of an edge tile (odd extension) or of any tile of the other sample formats: one frame at a
+// time through the accessor.  Out of line: it keeps the dtype dispatch and the reflection branches
+// out of the scan kernel's instruction stream.
+__device__ __noinline__ void ss_fill_generic(const PcmView pcm, const BpmItem it, int64_t stride, int64_t t0, int nvalid,
+                                             double* wb) {
+  const ExtSignal x = make_ext(pcm, it, stride);
+  const int lane = threadIdx.x & 31;
+  const int sw = (threadIdx.x >> 5) * SS_WARP_SAMPLES + lane;
+#pragma unroll 1
+  for (int i = 0; i < SS_CHUNK; ++i)
+    wb[ss_pad(i * 32 + lane)] = (sw + i * 32 < nvalid) ? x.at(t0 + sw + i * 32) : 0.0;
+}
+
+__device__ __noinline__ double ss_first_input(const PcmView pcm, const BpmItem it, int64_t stride) {
+  return make_ext(pcm, it, stride).at(0);
+}
+
+template <int DIR /*0 forward from PCM, 1 backward from y_f*/, int MONO16 /*DIR 0: mono int16 fast path*/,
+          int OCC /*CTAs per SM the register budget is cut for*/>
+__global__ void __launch_bounds__(SS_THREADS, OCC) k_sos_scan(const __grid_constant__ SosScanArgs a) {
   __shared__ double sm_buf[SS_BUF];            // warp-private transposition buffers == the padded tile
-  __shared__ double sm_env[DIR == 1 ? SS_BUF : 1];
+  __shared__ double sm_env[DIR == 1 ? SS_BUF + SS_HALO + SS_HALO / 8 + 2 : 1];   // |y| of the tile (+ zeros), then the outputs
   __shared__ double sm_tot[SS_WARPS][4];
   __shared__ double sm_pre[SS_WARPS][4];
   __shared__ double sm_part[4];
@@ -112,14 +141,10 @@ __global__ void __launch_bounds__(SS_THREADS, 3) k_sos_scan(const __grid_constan
     const int sw = warp * SS_WARP_SAMPLES + lane;          // tile-local position of this lane's first load
     bool filled = false;
     if (DIR == 0) {
-      const ExtSignal x = make_ext(a.pcm, it, a.stride);
       // interior tiles of a mono int16 recording: plain strided loads, no reflection / dtype dispatch
-      const bool interior = MONO16 && t0 >= PADLEN && t0 + SS_TILE <= PADLEN + x.n_dec;
+      const bool interior = MONO16 && t0 >= PADLEN && t0 + SS_TILE <= PADLEN + it.m;
       if (!interior) {
-        // edge tiles and the other sample formats: one frame at a time through the accessor
-#pragma unroll 1
-        for (int i = 0; i < SS_CHUNK; ++i)
-          wb[ss_pad(i * 32 + lane)] = (sw + i * 32 < nvalid) ? x.at(t0 + sw + i * 32) : 0.0;
+        ss_fill_generic(a.pcm, it, a.stride, t0, nvalid, wb);
         filled = true;
       }
     }
@@ -130,7 +155,7 @@ __global__ void __launch_bounds__(SS_THREADS, 3) k_sos_scan(const __grid_constan
             static_cast<const int16_t*>(a.pcm.base) + it.in_off + (t0 - PADLEN + sw) * a.stride;
         const int64_t step = 32 * a.stride;
 #pragma unroll
-        for (int i = 0; i < SS_CHUNK; ++i) v[i] = static_cast<double>(p16[i * step]);
+        for (int i = 0; i < SS_CHUNK; ++i) v[i] = (a.stride > 1) ? ss_load_i16_strided(p16 + i * step) : static_cast<double>(p16[i * step]);
       } else {
         const double* __restrict__ src = yf + (n_ext - 1 - t0 - sw);
 #pragma unroll
@@ -234,7 +259,7 @@ __global__ void __launch_bounds__(SS_THREADS, 3) k_sos_scan(const __grid_constan
     if (k0 == 0) {
       // the true initial state: zi * (first input of this pass)
       double u0;
-      if (DIR == 0) u0 = make_ext(a.pcm, it, a.stride).at(0);
+      if (DIR == 0) u0 = ss_first_input(a.pcm, it, a.stride);
       else u0 = yf[n_ext - 1];
 #pragma unroll
       for (int c = 0; c < 4; ++c) start[c] = a.zi[c] * u0;
@@ -312,24 +337,27 @@ __global__ void __launch_bounds__(SS_THREADS, 3) k_sos_scan(const __grid_constan
   //      order); signal index j = jlo + la.  Samples outside the recording are staged as 0.
   const int64_t jhi = it.m + (PADLEN - 1) - t0;           // signal index of sl == 0
   const int64_t jlo = jhi - (SS_TILE - 1);
-  __syncthreads();                                        // every warp has consumed its inputs: the buffer becomes the tile
+  // la range that lies inside the recording: [la_min, la_max]
+  const int la_min = static_cast<int>(max(static_cast<int64_t>(0), -jlo));
+  const int la_max = static_cast<int>(min(static_cast<int64_t>(SS_TILE - 1), it.m - 1 - jlo));
+  __syncthreads();                                        // every warp has consumed its inputs: the buffers become the tile
 #pragma unroll
   for (int c = 0; c < SS_CHUNK; ++c) {
-    const int sl = tid * SS_CHUNK + c;
-    const int64_t j = jhi - sl;
-    sm_buf[ss_pad(SS_TILE - 1 - sl)] = (j >= 0 && j < it.m) ? x[c] : 0.0;
+    const int la = SS_TILE - 1 - (tid * SS_CHUNK + c);
+    const double v = (la >= la_min && la <= la_max) ? x[c] : 0.0;
+    sm_buf[ss_pad(la)] = v;
+    sm_env[ss_pad(la)] = fabs(v);
   }
+  if (tid < SS_HALO + SS_HALO / 8 + 1) sm_env[ss_pad(SS_TILE) + tid] = 0.0;    // windows of tile 0 may reach past the tile
   __syncthreads();
-  // filtered signal + max |y| over the samples of this tile's partition
-  {
+  if (a.y != nullptr) {
+    // filtered signal + max |y| over the samples of this tile's partition (the debug WAV needs both)
     double amax = 0.0;
-    for (int sl = tid; sl < a.part; sl += SS_THREADS) {
-      const int64_t j = jhi - sl;
-      if (j >= 0 && j < it.m) {
-        const double yy = sm_buf[ss_pad(SS_TILE - 1 - sl)];
-        if (a.y != nullptr) a.y[it.m_off + j] = yy;
-        amax = fmax(amax, fabs(yy));
-      }
+    const int la_lo = max(la_min, SS_TILE - a.part);
+    for (int la = la_max - tid; la >= la_lo; la -= SS_THREADS) {
+      const double yy = sm_buf[ss_pad(la)];
+      a.y[it.m_off + jlo + la] = yy;
+      amax = fmax(amax, fabs(yy));
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -338,38 +366,40 @@ __global__ void __launch_bounds__(SS_THREADS, 3) k_sos_scan(const __grid_constan
   }
   if (a.env_window <= 0) return;
   // envelope: pandas window [i - left, i + off] clipped to the recording (bpm_analysis.py:1053-1054).
-  // Tile t owns the outputs j in (jhi - off - part, jhi - off] (tile 0: up to m - 1); a thread forms
-  // 8 consecutive ones with a sliding sum over the staged |y|.
+  // Tile t owns the outputs j in (jhi - off - part, jhi - off] (tile 0: up to m - 1); thread `tid`
+  // forms the 8 consecutive ones starting at la0 = (part offset) + 8 tid with a sliding sum over the
+  // staged |y| (zeros outside the recording, so clipped windows need no special case in the sum).
   const int w = a.env_window;
   const int off = (w - 1) / 2, left = w - 1 - off;
-  const int64_t own_hi = (blockIdx.x == 0) ? it.m - 1 : jhi - off;
-  const int64_t own_lo = max(static_cast<int64_t>(0), jhi - off - a.part + 1);
-  const int64_t first = jhi - off - a.part + 1;           // output of thread 0, k = 0 (may be < 0)
-  {
-    const int64_t jb = first + static_cast<int64_t>(tid) * SS_CHUNK;
-    const int lb = static_cast<int>(jb - left - jlo);     // la of the first window element of output k = 0  (>= 0)
-    double e[SS_CHUNK];
-    bool any = (jb + SS_CHUNK - 1 >= own_lo) && (jb <= own_hi);
-    if (any) {
-      auto val = [&](int la) -> double { return (la < SS_TILE) ? fabs(sm_buf[ss_pad(la)]) : 0.0; };
-      double s = 0.0;
-      for (int q = 0; q < w; ++q) s += val(lb + q);
+  // tile-local index of output k = 0 of thread 0:  first - jlo  with  first = jhi - off - part + 1
+  const int q0 = SS_TILE - a.part - off;                  // >= left  because  w - 1 <= SS_TILE - part
+  const int own_lo = max(la_min, q0);                     // owned outputs, tile-local, inclusive
+  const int own_hi = (blockIdx.x == 0) ? la_max : min(la_max, SS_TILE - 1 - off);
+  const double inv_w = 1.0 / static_cast<double>(w);
+  double e[SS_CHUNK];
+  const int qb = q0 + tid * SS_CHUNK;                     // tile-local index of this thread's first output
+  const bool any = (qb + SS_CHUNK - 1 >= own_lo) && (qb <= own_hi);
+  if (any) {
+    const double* __restrict__ av = sm_env;
+    const int lb = qb - left;                             // first window element of output k = 0
+    double sacc = 0.0;
+    for (int q = 0; q < w; ++q) sacc += av[ss_pad(lb + q)];
 #pragma unroll
-      for (int k = 0; k < SS_CHUNK; ++k) {
-        const int64_t j = jb + k;
-        const int64_t wa = max(static_cast<int64_t>(0), j - left), wbq = min(it.m - 1, j + off);
-        e[k] = __ddiv_rn(s, static_cast<double>(wbq - wa + 1));
-        s = (s + val(lb + k + w)) - val(lb + k);
-      }
+    for (int k = 0; k < SS_CHUNK; ++k) {
+      const int la = qb + k;
+      const int wa = max(la_min, la - left), wb2 = min(la_max, la + off);
+      const int cnt = wb2 - wa + 1;
+      e[k] = (cnt == w) ? sacc * inv_w : __ddiv_rn(sacc, static_cast<double>(cnt));
+      sacc = (sacc + av[ss_pad(lb + k + w)]) - av[ss_pad(lb + k)];
     }
+  }
+  __syncthreads();                                        // all windows are read: |y| can be overwritten
+  if (any) {
 #pragma unroll
-    for (int k = 0; k < SS_CHUNK; ++k) sm_env[ss_pad(tid * SS_CHUNK + k)] = any ? e[k] : 0.0;
+    for (int k = 0; k < SS_CHUNK; ++k) sm_env[ss_pad(qb + k)] = e[k];
   }
   __syncthreads();
-  for (int q = tid; q < SS_TILE; q += SS_THREADS) {
-    const int64_t j = first + q;
-    if (j >= own_lo && j <= own_hi) a.env[it.m_off + j] = sm_env[ss_pad(q)];
-  }
+  for (int la = own_lo + tid; la <= own_hi; la += SS_THREADS) a.env[it.m_off + jlo + la] = sm_env[ss_pad(la)];
 }
 
 // ------------------------------------------------------------------ host side
@@ -447,8 +477,17 @@ int sosfilt_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* ite
   const int64_t max_ext = sh.max_m + 2 * PADLEN;
   const dim3 gf(cdiv(max_ext, SS_TILE), sh.n_items);
   BPM_KERNEL(k_sos_fwd);
-  if (pcm_dtype == BPM_PCM_I16 && channels == 1) k_sos_scan<0, 1><<<gf, SS_THREADS, 0, st>>>(a);
-  else k_sos_scan<0, 0><<<gf, SS_THREADS, 0, st>>>(a);
+  // register budget: 80 registers (3 CTAs per SM) or 64 (4 per SM, a few spills in the warp scan);
+  // BPM_SOS_OCC selects for experiments, the default is what measured faster on B200
+  static const int occ = [] { const char* e = getenv("BPM_SOS_OCC"); return (e && atoi(e) == 3) ? 3 : 4; }();
+  const bool mono16 = (pcm_dtype == BPM_PCM_I16 && channels == 1);
+  if (occ == 4) {
+    if (mono16) k_sos_scan<0, 1, 4><<<gf, SS_THREADS, 0, st>>>(a);
+    else k_sos_scan<0, 0, 4><<<gf, SS_THREADS, 0, st>>>(a);
+  } else {
+    if (mono16) k_sos_scan<0, 1, 3><<<gf, SS_THREADS, 0, st>>>(a);
+    else k_sos_scan<0, 0, 3><<<gf, SS_THREADS, 0, st>>>(a);
+  }
   BPM_LAUNCH_OK();
 
   // backward (+ envelope): aggregates SS_TILE - SS_HALO apart when the envelope is fused
@@ -469,7 +508,8 @@ int sosfilt_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* ite
   }
   const dim3 gb(cdiv(sh.max_m + PADLEN, a.part), sh.n_items);
   BPM_KERNEL(k_sos_bwd);
-  k_sos_scan<1, 0><<<gb, SS_THREADS, 0, st>>>(a);
+  if (occ == 4) k_sos_scan<1, 0, 4><<<gb, SS_THREADS, 0, st>>>(a);
+  else k_sos_scan<1, 0, 3><<<gb, SS_THREADS, 0, st>>>(a);
   BPM_LAUNCH_OK();
   return BPM_OK;
 }

@@ -230,3 +230,70 @@ def sos_filtfilt_envelope(x_kept: np.ndarray, d: BlockFilterDesign, env_window: 
                 s = (s + val(lb + k + w)) - val(lb + k)
     assert not np.any(np.isnan(y)) and not np.any(np.isnan(env))
     return y, env, float(np.max(np.abs(y)))
+
+
+# ----------------------------------------------------------------------------- csrc/peaks.cu: k_distance_tiles
+def distance_tiles_model(pos: np.ndarray, val: np.ndarray, d: int, own: int = 1024, halo: int = 256):
+    """scipy's distance rule (highest priority first removes neighbours closer than d) the way
+    k_distance_tiles resolves it: per tile of `own` candidates staged with `halo` neighbours on both
+    sides, fix-point of  kept(k) <=> no kept higher-priority neighbour within d  where a candidate
+    may only be KEPT if its whole neighbourhood is staged; leftovers (state 3) are finished by the
+    global fix-point of the last CTA.  Equal values: the later index has the higher priority.
+    Returns (kept mask, number of candidates the tiles left pending)."""
+    nc = len(pos)
+    state = np.full(nc, 3, dtype=np.int8)                      # 0 removed, 1 kept, 3 pending
+    if d <= 1:
+        return np.ones(nc, dtype=bool), 0
+    for k0 in range(0, nc, own):
+        k1 = min(nc, k0 + own)
+        s0, s1 = max(0, k0 - halo), min(nc, k1 + halo)
+        p, v = pos[s0:s1], val[s0:s1]
+        L = s1 - s0
+        st = np.zeros(L, dtype=np.int8)                        # 0 open, 1 kept, 2 removed
+        open_left, open_right = s0 > 0, s1 < nc
+        while True:
+            changed = False
+            prev = st.copy()                                   # rounds are lock-step on the device only between barriers;
+            for k in range(L):                                 # reading fresher states than `prev` is harmless (monotone)
+                if prev[k] != 0:
+                    continue
+                any_keep = any_open = False
+                k2 = k - 1
+                while k2 >= 0 and p[k] - p[k2] < d:
+                    if v[k2] > v[k]:
+                        any_keep |= prev[k2] == 1
+                        any_open |= prev[k2] == 0
+                    k2 -= 1
+                k2 = k + 1
+                while k2 < L and p[k2] - p[k] < d:
+                    if v[k2] >= v[k]:
+                        any_keep |= prev[k2] == 1
+                        any_open |= prev[k2] == 0
+                    k2 += 1
+                full = (not open_left or p[k] - p[0] >= d) and (not open_right or p[-1] - p[k] >= d)
+                if any_keep:
+                    st[k], changed = 2, True
+                elif not any_open and full:
+                    st[k], changed = 1, True
+            if not changed:
+                break
+        for k in range(k0, k1):
+            s = st[k - s0]
+            state[k] = 1 if s == 1 else (0 if s == 2 else 3)
+    n_pending = int(np.count_nonzero(state == 3))
+    while np.any(state == 3):
+        prev = state.copy()
+        for k in np.flatnonzero(prev == 3):
+            any_keep = any_open = False
+            for rng in (range(k - 1, -1, -1), range(k + 1, nc)):
+                for k2 in rng:
+                    if abs(pos[k2] - pos[k]) >= d:
+                        break
+                    if val[k2] > val[k] or (val[k2] == val[k] and k2 > k):
+                        any_keep |= prev[k2] == 1
+                        any_open |= prev[k2] == 3
+            if any_keep:
+                state[k] = 0
+            elif not any_open:
+                state[k] = 1
+    return state == 1, n_pending

@@ -183,7 +183,7 @@ def test_full_size_c2_matches_oracle_through_the_drop_in_functions(gpu, ref_para
     got = _dropin_chain(frontend, pcm, sr, ref_params, beat_idx)
     assert len(got["envelope"]) == 1086793 and got["rate"] == 301
     _check_against_oracle(got, fe, br)
-    assert len(fe["peaks"]) > 10000 and len(br["windowed_hrv_df"]) > 1000 and len(br["major_inclines"]) >= 1
+    assert len(fe["peaks"]) > 10000 and len(br["windowed_hrv_df"]) > 1000
     after = dict(d.stats)
     assert after["stage_a_calls"] - before["stage_a_calls"] == 1        # the whole chain cost one stage-A call
     assert after["session_misses"] == before["session_misses"]          # nothing was uploaded a second time

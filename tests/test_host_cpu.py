@@ -216,3 +216,29 @@ def test_host_gather_frames_matches_numpy_slicing():
                                             C.c_void_p(out.ctypes.data), threads)
             assert rc == 0 and np.array_equal(out, want)
     assert lib.bpm_host_gather_frames(None, 2, 10, 1, None, 0) != 0
+
+
+def test_distance_tiles_model_matches_scipy():
+    """numpy model of csrc/peaks.cu::k_distance_tiles (tile + halo fix-point, leftovers finished by the
+    global fix-point) against scipy's own _select_by_peak_distance, including chains of rising
+    candidates that escape every halo."""
+    from scipy.signal._peak_finding_utils import _select_by_peak_distance
+    rng = np.random.default_rng(1)
+    pending = 0
+    for trial in range(24):
+        n = int(rng.integers(50, 400))
+        gaps = rng.integers(1, 8, size=n) if trial % 3 else rng.integers(1, 40, size=n)
+        pos = np.cumsum(gaps).astype(np.intp)
+        if trial % 4 == 0:
+            val = np.arange(n, dtype=float) + rng.random(n) * 0.5
+        elif trial % 4 == 1:
+            val = -np.arange(n, dtype=float) + rng.random(n) * 0.5
+        else:
+            val = rng.random(n)
+        d = int(rng.integers(2, 20))
+        want = _select_by_peak_distance(pos, val.copy(), float(d))
+        for own, halo in ((16, 4), (1024, 256)):
+            got, npend = kernel_models.distance_tiles_model(pos, val, d, own, halo)
+            pending += npend
+            assert np.array_equal(got, want), (trial, own, halo)
+    assert pending > 0
