@@ -165,6 +165,17 @@ __global__ void __launch_bounds__(PK_THREADS) k_localmax_compact(const double* _
   if (tid == 0 && i0 + PK_TILE >= n) cand_count[item] = s_off + total;
 }
 
+#ifdef BPM_DEBUG_COUNTERS
+// [0] tiles, [1] rounds summed, [2] max rounds of a tile, [3] candidates left pending by the tiles,
+// [4] rounds of the global finish, [5] candidates, [6..8] thread-0 cycles: staging, rounds, write-back
+__device__ unsigned long long g_dbg_pk[16];
+#define PKD_ADD(i, v) atomicAdd(&g_dbg_pk[i], static_cast<unsigned long long>(v))
+#define PKD_MAX(i, v) atomicMax(&g_dbg_pk[i], static_cast<unsigned long long>(v))
+#else
+#define PKD_ADD(i, v)
+#define PKD_MAX(i, v)
+#endif
+
 // ------------------------------------------------------------------ distance
 constexpr int DT_THREADS = 256;
 constexpr int DT_OWN = 1024;                      // candidates a CTA settles per tile
@@ -205,6 +216,10 @@ __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __r
     }
     const int64_t s0 = max(static_cast<int64_t>(0), k0 - DT_HALO), s1 = min(nc, k1 + DT_HALO);
     const int L = static_cast<int>(s1 - s0);
+#ifdef BPM_DEBUG_COUNTERS
+    long long t_dbg = clock64();
+    int rounds_dbg = 0;
+#endif
     __syncthreads();                                              // previous tile's staging is no longer read
     for (int t = tid; t < L; t += DT_THREADS) {
       const int64_t pp = pos[s0 + t];
@@ -217,8 +232,14 @@ __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __r
     // the others can only be removed (by a kept higher-priority neighbour that is staged)
     const int p_first = s_pos[0], p_last = s_pos[L - 1];
     const bool open_left = s0 > 0, open_right = s1 < nc;
+#ifdef BPM_DEBUG_COUNTERS
+    if (tid == 0) { const long long t2 = clock64(); PKD_ADD(6, t2 - t_dbg); t_dbg = t2; }
+#endif
     while (true) {
       int changed = 0;
+#ifdef BPM_DEBUG_COUNTERS
+      ++rounds_dbg;
+#endif
 #pragma unroll 1
       for (int u = 0; u < DT_PER; ++u) {
         const int k = tid + u * DT_THREADS;
@@ -244,12 +265,22 @@ __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __r
       }
       if (!__syncthreads_or(changed)) break;
     }
+#ifdef BPM_DEBUG_COUNTERS
+    if (tid == 0) {
+      const long long t2 = clock64(); PKD_ADD(7, t2 - t_dbg); t_dbg = t2;
+      PKD_ADD(0, 1); PKD_ADD(1, rounds_dbg); PKD_MAX(2, rounds_dbg);
+    }
+#endif
     for (int64_t k = k0 + tid; k < k1; k += DT_THREADS) {
       const unsigned char s = s_st[k - s0];
       st_out[k] = (s == 1) ? DST_KEPT : (s == 2 ? DST_REMOVED : DST_PENDING);
       my_pending += (s == 0) ? 1 : 0;
     }
+#ifdef BPM_DEBUG_COUNTERS
+    if (tid == 0) { const long long t2 = clock64(); PKD_ADD(8, t2 - t_dbg); }
+#endif
   }
+  PKD_ADD(3, my_pending);
   // ---- the last CTA of this recording finishes whatever chains escaped their halo (exact, slow, rare)
   my_pending = __syncthreads_count(my_pending != 0) ? 1 : 0;     // (only "any" matters)
   if (tid == 0) {
@@ -260,10 +291,12 @@ __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __r
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  if (tid == 0) PKD_ADD(5, nc);
   if (atomicAdd(pending + item, 0) == 0) return;
   volatile unsigned char* stt = st_out;
   while (true) {
     int changed = 0;
+    if (tid == 0) PKD_ADD(4, 1);
     for (int64_t k = tid; k < nc; k += DT_THREADS) {
       if (stt[k] != DST_PENDING) continue;
       const int64_t pk = pos[k];
@@ -476,3 +509,12 @@ int find_peaks_run(const double* x, int sign, const double* height, const double
 }
 
 }  // namespace bpm
+
+#ifdef BPM_DEBUG_COUNTERS
+extern "C" int bpm_debug_counters_peaks(unsigned long long* out_host, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out_host, bpm::g_dbg_pk, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(bpm::g_dbg_pk, z, sizeof(z)); }
+  return 0;
+}
+#endif

@@ -111,6 +111,32 @@ def _raw_peaks(envelope: np.ndarray, height_threshold: np.ndarray, sample_rate: 
     return dropin().raw_peaks(env, height, int(sample_rate), params, with_metrics)
 
 
+_sorted_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
+
+
+def _sorted_list(values) -> list:
+    """``sorted(values)`` (bpm_analysis.py:107) -- a list of the array's scalars in ascending order.
+    The trough array we hand out is already ascending, and both classifier constructions get the
+    same array: the list is built once per array (straight iteration when it is sorted already) and
+    every caller receives its own shallow copy."""
+    if not isinstance(values, np.ndarray) or values.ndim != 1:
+        return sorted(values)
+    key = (values.__array_interface__["data"][0], values.size, values.dtype.str)
+    hit = _sorted_cache.get(key)
+    if hit is not None and hit[0]() is values:
+        return list(hit[1])
+    asc = values.size < 2 or bool(np.all(values[:-1] <= values[1:]))
+    lst = list(values) if asc else sorted(values)
+    try:
+        import weakref
+        _sorted_cache[key] = (weakref.ref(values), lst)
+        while len(_sorted_cache) > 4:
+            _sorted_cache.popitem(last=False)
+    except TypeError:
+        pass
+    return list(lst)
+
+
 def _find_raw_peaks(self, height_threshold: np.ndarray) -> np.ndarray:
     """Replacement for ``PeakClassifier._find_raw_peaks`` (bpm_analysis.py:223-229)."""
     peaks, _ = _raw_peaks(self.audio_envelope, height_threshold, self.sample_rate, self.params, False)
@@ -135,7 +161,7 @@ def _initialize_state(self, start_bpm_hint, precomputed_noise_floor, precomputed
     state["candidate_beats"] = []
     state["beat_debug_info"] = {}
     state["long_term_bpm_history"] = []
-    state["sorted_troughs"] = sorted(state["trough_indices"])
+    state["sorted_troughs"] = _sorted_list(state["trough_indices"])
     state["consecutive_rr_rejections"] = 0
     state["loop_idx"] = 0
     return state

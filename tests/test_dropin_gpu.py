@@ -110,8 +110,12 @@ def test_beat_list_reductions_share_one_round_trip(svc, ref_params, synth_inputs
     assert sm.index.equals(o["smoothed_bpm"].index) and rel_err(sm.values, o["smoothed_bpm"].values) < TOL
     assert [(x["start_time"], x["end_time"]) for x in inc] == [(x["start_time"], x["end_time"]) for x in o["major_inclines"]]
     assert [(x["start_time"], x["end_time"]) for x in dec] == [(x["start_time"], x["end_time"]) for x in o["major_declines"]]
-    assert rec["slope_bpm_per_sec"] == o["peak_recovery_stats"]["slope_bpm_per_sec"]
-    assert exe["slope_bpm_per_sec"] == o["peak_exertion_stats"]["slope_bpm_per_sec"]
+    # the reductions of the Series are exact functions of ITS values: compare with the oracle on the same Series
+    o_rec, o_exe = ref_port.find_peak_recovery_rate(sm), ref_port.find_peak_exertion_rate(sm)
+    for got, want in ((rec, o_rec), (exe, o_exe)):
+        assert got["slope_bpm_per_sec"] == want["slope_bpm_per_sec"] and got["duration_sec"] == want["duration_sec"]
+        assert got["start_time"] == want["start_time"] and got["end_time"] == want["end_time"]
+    assert rec["slope_bpm_per_sec"] == pytest.approx(o["peak_recovery_stats"]["slope_bpm_per_sec"], rel=1e-12)
     assert rel_err(hrv.values, o["windowed_hrv_df"].values) < TOL
     # a Series that did not come from calculate_bpm_series (shifted copy) takes the generic kernels
     other = sm * 1.0 + 0.25

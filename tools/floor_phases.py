@@ -19,7 +19,7 @@ DBG = os.path.join(REPO, "bpm_analysis_b200", "libbpm_b200_dbg.so")
 
 def build():
     from bpm_analysis_b200.build import CSRC, NVCC_FLAGS, SOURCES, find_nvcc
-    cmd = [find_nvcc(), *[f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")], "-DBPM_DEBUG_COUNTERS", "-o", DBG,
+    cmd = [find_nvcc(), *[f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")], "-shared", "-DBPM_DEBUG_COUNTERS", "-o", DBG,
            *[os.path.join(CSRC, s) for s in SOURCES]]
     subprocess.run(cmd, check=True)
 
