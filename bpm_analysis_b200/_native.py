@@ -77,6 +77,7 @@ _SIGNATURES = {
     "bpm_steepest_slope_workspace_bytes": (_Z, [_L, _I]),
     "bpm_steepest_slope": (_I, [_P, _P, _P, _P, _P, _I, _I, _D, _P, _P, _Z, _P]),
     "bpm_windowed_hrv": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "bpm_cast_f32": (_I, [_P, _P, _L, _P]),
     "bpm_stage_a_workspace_bytes": (_Z, [_L, _I]),
     "bpm_stage_a": (_I, [_P, _P, _P, _I, _P, _P, _L, C.POINTER(StageAConfig), C.POINTER(StageAOutputs), _P, _Z, _P]),
 }

@@ -504,6 +504,27 @@ __global__ void k_hrv(const int64_t* __restrict__ beats, const BpmItem* __restri
   o[3] = mean_s > 0.0 ? __ddiv_rn(60.0, mean_s) : 0.0;
 }
 
+// ------------------------------------------------------------------ float32 outputs
+// "float32 mode" of the north star: every stage computes in float64 (the filter states and the scan
+// carries need it: a float32 recurrence at these pole radii is off by 1e-3); only the signals handed
+// back to the host are rounded to float32 -- half the read-back bytes, 6e-8 relative error.
+__global__ void k_cast_f32(const double* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  const int64_t T = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += T)
+    dst[i] = static_cast<float>(src[i]);
+}
+
+int cast_f32_run(const double* src, float* dst, int64_t n, cudaStream_t st) {
+  if (!src || !dst || n < 0) return BPM_ERR_ARG;
+  if (n == 0) return BPM_OK;
+  int64_t gx = (n + 1023) / 1024;
+  if (gx > 148 * 8) gx = 148 * 8;
+  BPM_KERNEL(k_cast_f32);
+  k_cast_f32<<<static_cast<unsigned>(gx), 256, 0, st>>>(src, dst, n);
+  BPM_LAUNCH_OK();
+  return BPM_OK;
+}
+
 int hrv_run(const int64_t* beats, const BpmItem* lists, const BatchShape& sh, int rate, int win, int step,
             double* out, int64_t* rows, cudaStream_t st) {
   if (!beats || !lists || !out || !rows || rate <= 0 || win < 2 || step < 1) return BPM_ERR_ARG;

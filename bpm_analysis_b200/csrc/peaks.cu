@@ -9,16 +9,16 @@
 //                         (optionally) at or above its height threshold; the candidates are written
 //                         in order by a SINGLE-PASS compaction (decoupled look-back over tile counts).
 //   k_distance_tiles      scipy's greedy "highest first removes neighbours closer than d" as the
-//                         unique fix-point of  kept(k) <=> no kept higher-priority neighbour within d.
-//                         A CTA owns 1024 consecutive candidates and stages them with a halo of 256 on
-//                         either side; a candidate is settled when its dependency chain (strictly
-//                         rising priority, each hop < d samples) stays inside the staged range, which
-//                         is the case for all but pathological inputs.  Whatever is left is finished
-//                         exactly by the last CTA of the recording over global memory.
-//   k_prominence_compact  prominence >= threshold for every survivor: each lane walks its own peak's
-//                         two sides (most walks end within a few samples: a higher sample stops them,
-//                         a sample low enough passes them); walks still open after 48 samples a side
-//                         are finished warp-cooperatively, 32 samples per step.  The survivors are
+//                         well-founded recursion  kept(k) <=> no kept higher-priority neighbour within d,
+//                         evaluated depth-first per candidate with the results memoised in shared memory
+//                         (no rounds, no barriers).  A CTA owns 1024 consecutive candidates and stages
+//                         them with a halo of 128 on either side; a candidate is settled when its
+//                         dependency chain (strictly rising priority, each hop < d samples) stays inside
+//                         the staged range, which is the case for all but pathological inputs.  Whatever
+//                         is left is finished exactly by the last CTA of the recording over global memory.
+//   k_prominence_compact  prominence >= threshold for every survivor: a warp walks the two sides of
+//                         each of its survivors 32 samples per step with ballot early exit (a higher
+//                         sample stops a side, a sample low enough passes it).  The survivors are
 //                         written in order, again by single-pass compaction.
 // Equal-height candidates within `distance`: the later index wins (what a stable argsort
 // gives scipy); numpy's default sort is unstable, so the reference does not pin this case.
@@ -179,15 +179,24 @@ __device__ unsigned long long g_dbg_pk[16];
 // ------------------------------------------------------------------ distance
 constexpr int DT_THREADS = 256;
 constexpr int DT_OWN = 1024;                      // candidates a CTA settles per tile
-constexpr int DT_HALO = 256;                      // staged on either side of them
+constexpr int DT_HALO = 128;                      // staged on either side of them
 constexpr int DT_STAGE = DT_OWN + 2 * DT_HALO;
-constexpr int DT_PER = DT_STAGE / DT_THREADS;
+constexpr int DT_DEPTH = 24;                      // dependency chains followed this deep, longer ones are left pending
 enum : unsigned char { DST_REMOVED = 0, DST_KEPT = 1, DST_PENDING = 3 };   // global state of a candidate
 
 __device__ __forceinline__ bool higher_priority(double va, int64_t ka, double vb, int64_t kb) {
   return va > vb || (va == vb && ka > kb);
 }
 
+// The rule  kept(k) <=> no kept higher-priority neighbour within d  is a well-founded recursion
+// (priority strictly rises along every dependency), so each thread simply EVALUATES it for its own
+// candidates: scan the higher-priority neighbours; one of them kept -> removed; one still unknown ->
+// evaluate that one first (explicit stack, depth-first), then look again; none left -> kept.
+// Results are memoised in shared memory (a state only ever goes from open to its final value, and
+// every thread would write the same value), so no barriers are needed and threads never wait for
+// each other.  Staged candidates whose neighbourhood is not completely staged cannot be kept here;
+// an owned candidate that depends on one of those -- or on a chain deeper than DT_DEPTH -- is left
+// pending for the exact global finish below (never seen on real envelopes: chains are a few long).
 __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __restrict__ x, int sign,
                                                                const BpmItem* __restrict__ items,
                                                                const int64_t* __restrict__ cand,
@@ -197,7 +206,8 @@ __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __r
                                                                unsigned int* __restrict__ ticket) {
   __shared__ int s_pos[DT_STAGE];
   __shared__ double s_val[DT_STAGE];
-  __shared__ unsigned char s_st[DT_STAGE];        // 0 open, 1 kept, 2 removed
+  __shared__ unsigned char s_st[DT_STAGE];        // 0 open, 1 kept, 2 removed, 3 cannot be settled in this tile
+  __shared__ unsigned short s_stack[DT_DEPTH][DT_THREADS];
   __shared__ int s_last;
   const int item = blockIdx.y;
   const BpmItem it = items[item];
@@ -221,60 +231,85 @@ __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __r
     int rounds_dbg = 0;
 #endif
     __syncthreads();                                              // previous tile's staging is no longer read
-    for (int t = tid; t < L; t += DT_THREADS) {
-      const int64_t pp = pos[s0 + t];
-      s_pos[t] = static_cast<int>(pp);
-      s_val[t] = signed_val(xi[pp], sign);
-      s_st[t] = 0;
+    {
+      int64_t pp[DT_STAGE / DT_THREADS];
+#pragma unroll
+      for (int u = 0; u < DT_STAGE / DT_THREADS; ++u) {
+        const int t = tid + u * DT_THREADS;
+        pp[u] = (t < L) ? pos[s0 + t] : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < DT_STAGE / DT_THREADS; ++u) {
+        const int t = tid + u * DT_THREADS;
+        if (t < L) {
+          s_pos[t] = static_cast<int>(pp[u]);
+          s_val[t] = signed_val(xi[pp[u]], sign);
+          s_st[t] = 0;
+        }
+      }
     }
     __syncthreads();
-    // a candidate whose whole neighbourhood (< d samples either way) is staged may be KEPT here;
-    // the others can only be removed (by a kept higher-priority neighbour that is staged)
     const int p_first = s_pos[0], p_last = s_pos[L - 1];
     const bool open_left = s0 > 0, open_right = s1 < nc;
+    volatile unsigned char* S = s_st;
 #ifdef BPM_DEBUG_COUNTERS
     if (tid == 0) { const long long t2 = clock64(); PKD_ADD(6, t2 - t_dbg); t_dbg = t2; }
 #endif
-    while (true) {
-      int changed = 0;
+    const int own0 = static_cast<int>(k0 - s0), own1 = static_cast<int>(k1 - s0);
+    for (int kk = own0 + tid; kk < own1; kk += DT_THREADS) {
+      int sp = 0, cur = kk;
+      while (true) {
+        if (S[cur] == 0) {
 #ifdef BPM_DEBUG_COUNTERS
-      ++rounds_dbg;
+          ++rounds_dbg;
 #endif
-#pragma unroll 1
-      for (int u = 0; u < DT_PER; ++u) {
-        const int k = tid + u * DT_THREADS;
-        if (k >= L || s_st[k] != 0) continue;
-        const int pk = s_pos[k];
-        const double vk = s_val[k];
-        bool any_keep = false, any_open = false;
-        for (int k2 = k - 1; k2 >= 0 && pk - s_pos[k2] < d; --k2) {
-          if (s_val[k2] > vk) {                                   // equal heights: the later index wins
-            const unsigned char s2 = s_st[k2];
-            any_keep |= (s2 == 1); any_open |= (s2 == 0);
+          const int pk = s_pos[cur];
+          const double vk = s_val[cur];
+          bool any_keep = false, any_unknown = false;
+          int open_j = -1;
+          for (int k2 = cur - 1; k2 >= 0 && pk - s_pos[k2] < d; --k2) {
+            if (s_val[k2] > vk) {                                 // equal heights: the later index wins
+              const unsigned char s2 = S[k2];
+              if (s2 == 1) { any_keep = true; break; }
+              if (s2 == 0) open_j = k2; else if (s2 == 3) any_unknown = true;
+            }
+          }
+          if (!any_keep) {
+            for (int k2 = cur + 1; k2 < L && s_pos[k2] - pk < d; ++k2) {
+              if (s_val[k2] >= vk) {
+                const unsigned char s2 = S[k2];
+                if (s2 == 1) { any_keep = true; break; }
+                if (s2 == 0) open_j = k2; else if (s2 == 3) any_unknown = true;
+              }
+            }
+          }
+          if (any_keep) {
+            S[cur] = 2;
+          } else if (open_j >= 0) {
+            if (sp < DT_DEPTH) { s_stack[sp++][tid] = static_cast<unsigned short>(cur); cur = open_j; continue; }
+            S[cur] = 3;                                           // chain too deep for this tile
+          } else {
+            const bool full = (!open_left || pk - p_first >= d) && (!open_right || p_last - pk >= d);
+            S[cur] = (any_unknown || !full) ? 3 : 1;
           }
         }
-        for (int k2 = k + 1; k2 < L && s_pos[k2] - pk < d; ++k2) {
-          if (s_val[k2] >= vk) {
-            const unsigned char s2 = s_st[k2];
-            any_keep |= (s2 == 1); any_open |= (s2 == 0);
-          }
-        }
-        const bool full = (!open_left || pk - p_first >= d) && (!open_right || p_last - pk >= d);
-        if (any_keep) { s_st[k] = 2; changed = 1; }
-        else if (!any_open && full) { s_st[k] = 1; changed = 1; }
+        if (sp == 0) break;
+        cur = s_stack[--sp][tid];
       }
-      if (!__syncthreads_or(changed)) break;
     }
+    __syncthreads();
 #ifdef BPM_DEBUG_COUNTERS
+    rounds_dbg = __syncthreads_count(rounds_dbg) ? rounds_dbg : 0;
+    PKD_ADD(1, rounds_dbg);
     if (tid == 0) {
       const long long t2 = clock64(); PKD_ADD(7, t2 - t_dbg); t_dbg = t2;
-      PKD_ADD(0, 1); PKD_ADD(1, rounds_dbg); PKD_MAX(2, rounds_dbg);
+      PKD_ADD(0, 1);
     }
 #endif
     for (int64_t k = k0 + tid; k < k1; k += DT_THREADS) {
       const unsigned char s = s_st[k - s0];
       st_out[k] = (s == 1) ? DST_KEPT : (s == 2 ? DST_REMOVED : DST_PENDING);
-      my_pending += (s == 0) ? 1 : 0;
+      my_pending += (s == 3 || s == 0) ? 1 : 0;
     }
 #ifdef BPM_DEBUG_COUNTERS
     if (tid == 0) { const long long t2 = clock64(); PKD_ADD(8, t2 - t_dbg); }
@@ -361,31 +396,7 @@ __device__ bool warp_prominence_ok(const double* __restrict__ xi, int sign, int6
 }
 
 
-// One lane, one peak: 1 = both sides pass, 0 = a side's walk stops first, 2 = still open after
-// `lim` samples on some side (the caller finishes it with warp_prominence_ok).  Same decisions,
-// sample by sample, as the cooperative walk.
-__device__ __forceinline__ int lane_prominence(const double* __restrict__ xi, int sign, int64_t n, int64_t p,
-                                               double thr, int lim) {
-  const double xp = signed_val(xi[p], sign);
-  if (__dsub_rn(xp, xp) >= thr) return 1;
-#pragma unroll 1
-  for (int side = 0; side < 2; ++side) {
-    const int dir = side == 0 ? -1 : +1;
-    bool passed = false;
-    for (int s = 1; s <= lim; ++s) {
-      const int64_t i = p + dir * s;
-      if (i < 0 || i >= n) return 0;
-      const double v = signed_val(xi[i], sign);
-      if (v > xp) return 0;
-      if (__dsub_rn(xp, v) >= thr) { passed = true; break; }
-    }
-    if (!passed) return 2;
-  }
-  return 1;
-}
-
 constexpr int PC_THREADS = 256;                   // candidates per tile of k_prominence_compact
-constexpr int PC_LANE_LIMIT = 48;
 
 __global__ void __launch_bounds__(PC_THREADS) k_prominence_compact(const double* __restrict__ x, int sign,
                                                                    const BpmItem* __restrict__ items,
@@ -414,17 +425,17 @@ __global__ void __launch_bounds__(PC_THREADS) k_prominence_compact(const double*
   bool live = (k < nc) && state[it.m_off + k] == DST_KEPT;
   const int64_t p = (k < nc) ? pos[k] : 0;
   if (prominence != nullptr) {
+    // the warp walks its survivors one after the other, both sides 32 samples per step (a lane-per-peak
+    // walk was measured slower: 410 vs 237 us on the 24-h stream -- the slowest lane sets the pace)
     const double thr = prominence[item];
-    int r = live ? lane_prominence(xi, sign, it.m, p, thr, PC_LANE_LIMIT) : 0;
-    unsigned todo = __ballot_sync(0xffffffffu, r == 2);
+    unsigned todo = __ballot_sync(0xffffffffu, live);
     while (todo) {
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
       const int64_t ps = __shfl_sync(0xffffffffu, p, src);
       const bool ok = warp_prominence_ok(xi, sign, it.m, ps, thr);
-      if (lane == src) r = ok ? 1 : 0;
+      if (lane == src) live = ok;
     }
-    live = live && (r == 1);
   }
   int total;
   const int ex = block_exclusive_scan(live ? 1 : 0, &total, s_scan);

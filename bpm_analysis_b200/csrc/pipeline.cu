@@ -54,6 +54,7 @@ int bpm_series_run(const int64_t* beats, const BpmItem* lists, const BatchShape&
                    cudaStream_t st);
 int steepest_run(const double* smoothed, const int64_t* stamp_us, const int64_t* n_valid, const BpmItem* lists,
                  int n_lists, int64_t max_len, int sign, double window_sec, double* result, cudaStream_t st);
+int cast_f32_run(const double* src, float* dst, int64_t n, cudaStream_t st);
 int hrv_run(const int64_t* beats, const BpmItem* lists, const BatchShape& sh, int rate, int win, int step,
             double* out, int64_t* rows, cudaStream_t st);
 
@@ -450,6 +451,10 @@ int bpm_windowed_hrv(const int64_t* beats, const BpmItem* lists, const BpmItem* 
   if (!lists_host || n_lists <= 0) return BPM_ERR_ARG;
   return hrv_run(beats, lists, batch_shape(lists_host, n_lists), rate, window_beats, step_beats, out, rows,
                  static_cast<cudaStream_t>(stream));
+}
+
+int bpm_cast_f32(const double* src, float* dst, int64_t n, void* stream) {
+  return cast_f32_run(src, dst, n, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------ a1..a4 in one call

@@ -12,6 +12,10 @@ Optional keys this package adds (absent => reference behaviour):
                   envelope rate -- what ``bpm_analysis.py:1031-1045`` does.
                   ``"fullrate"``: band-pass at the original rate (the order
                   ``README.md:6`` documents), then take every ds-th sample.
+``output_dtype``  ``"float64"`` (default) or ``"float32"``: the "float32 mode" of the north star.
+                  All stages compute in float64; the envelope / noise floor / per-peak series
+                  handed back to the host are rounded to float32 (half the read-back bytes;
+                  trough / peak / beat lists are unchanged).
 ``lowcut_hz`` / ``highcut_hz``   band edges, hard-coded 20/150 in
                   ``bpm_analysis.py:1018``; exposed for the C5 sweep.
 """
@@ -105,6 +109,13 @@ def filter_mode(params: Dict) -> str:
     if mode not in ("parity", "fullrate"):
         raise ValueError(f"filter_mode must be 'parity' or 'fullrate', got {mode!r}")
     return mode
+
+
+def output_dtype(params: Dict) -> str:
+    dt = params.get("output_dtype", "float64")
+    if dt not in ("float64", "float32"):
+        raise ValueError(f"output_dtype must be 'float64' or 'float32', got {dt!r}")
+    return dt
 
 
 def effective_decimation(sample_rate: int, params: Dict):

@@ -234,6 +234,12 @@ int bpm_windowed_hrv(const int64_t* beats, const BpmItem* lists, const BpmItem* 
                      int n_lists, int rate, int window_beats, int step_beats,
                      double* out, int64_t* rows, void* stream);
 
+/* ---- float32 outputs (north star: "1e-4 (float32 mode)") ---------------------------------------
+ * dst[i] = (float) src[i].  Every stage computes in float64 -- a float32 filter recurrence at these
+ * pole radii is off by 1e-3 -- and only the signals handed back to the host (envelope, noise
+ * floor, per-peak series) are rounded: half the read-back bytes, 6e-8 relative error. */
+int bpm_cast_f32(const double* src, float* dst, int64_t n, void* stream);
+
 /* ---- a1..a4 chained in one call (what analyze_wav_file does at :1731-1732 + :1635) --- */
 typedef struct {
   int64_t stride, block;          /* filter placement, see bpm_frontend */
