@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __r
   __shared__ double s_val[DT_STAGE];
   __shared__ unsigned char s_st[DT_STAGE];        // 0 open, 1 kept, 2 removed, 3 cannot be settled in this tile
   __shared__ unsigned short s_stack[DT_DEPTH][DT_THREADS];
+  __shared__ unsigned int s_hi[DT_STAGE];         // d <= 32: which of the <= 16 + 16 neighbours within d have the higher priority
   __shared__ int s_last;
   const int item = blockIdx.y;
   const BpmItem it = items[item];
@@ -217,6 +218,11 @@ __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __r
   unsigned char* st_out = state + it.m_off;
   const int tid = threadIdx.x;
   const int d = distance;
+  // Local maxima lie at least 2 samples apart, so at most (d - 1) / 2 <= 15 candidates per side are
+  // within d <= 32: their "has the higher priority" relation fits one word per candidate, computed
+  // once; evaluating a candidate is then a loop over the set bits (a couple of byte loads) instead of
+  // a rescan of positions and values.
+  const bool compact = d <= 32;
   int my_pending = 0;
   for (int64_t k0 = static_cast<int64_t>(blockIdx.x) * DT_OWN; k0 < nc; k0 += static_cast<int64_t>(gridDim.x) * DT_OWN) {
     const int64_t k1 = min(nc, k0 + DT_OWN);
@@ -256,6 +262,54 @@ __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __r
     if (tid == 0) { const long long t2 = clock64(); PKD_ADD(6, t2 - t_dbg); t_dbg = t2; }
 #endif
     const int own0 = static_cast<int>(k0 - s0), own1 = static_cast<int>(k1 - s0);
+    if (compact) {
+      for (int k = tid; k < L; k += DT_THREADS) {
+        const int pk = s_pos[k];
+        const double vk = s_val[k];
+        unsigned int m = 0;
+        for (int b = 0, k2 = k - 1; k2 >= 0 && pk - s_pos[k2] < d; ++b, --k2)
+          if (s_val[k2] > vk) m |= 1u << b;                       // equal heights: the later index wins
+        for (int b = 16, k2 = k + 1; k2 < L && s_pos[k2] - pk < d; ++b, ++k2)
+          if (s_val[k2] >= vk) m |= 1u << b;
+        const bool full = (!open_left || pk - p_first >= d) && (!open_right || p_last - pk >= d);
+        s_hi[k] = m;
+        if (m == 0) s_st[k] = full ? 1 : 3;                       // no higher-priority neighbour at all
+      }
+      __syncthreads();
+      for (int kk = own0 + tid; kk < own1; kk += DT_THREADS) {
+        int sp = 0, cur = kk;
+        while (true) {
+          if (S[cur] == 0) {
+#ifdef BPM_DEBUG_COUNTERS
+            ++rounds_dbg;
+#endif
+            bool any_keep = false, any_unknown = false;
+            int open_j = -1;
+            unsigned int m = s_hi[cur];
+            while (m) {
+              const int b = __ffs(m) - 1;
+              m &= m - 1;
+              const int k2 = (b < 16) ? cur - 1 - b : cur + 1 + (b - 16);
+              const unsigned char s2 = S[k2];
+              if (s2 == 1) { any_keep = true; break; }
+              if (s2 == 0) open_j = k2; else if (s2 == 3) any_unknown = true;
+            }
+            if (any_keep) {
+              S[cur] = 2;
+            } else if (open_j >= 0) {
+              if (sp < DT_DEPTH) { s_stack[sp++][tid] = static_cast<unsigned short>(cur); cur = open_j; continue; }
+              S[cur] = 3;                                         // chain too deep for this tile
+            } else {
+              const int pk = s_pos[cur];
+              const bool full = (!open_left || pk - p_first >= d) && (!open_right || p_last - pk >= d);
+              S[cur] = (any_unknown || !full) ? 3 : 1;
+            }
+          }
+          if (sp == 0) break;
+          cur = s_stack[--sp][tid];
+        }
+      }
+    } else
     for (int kk = own0 + tid; kk < own1; kk += DT_THREADS) {
       int sp = 0, cur = kk;
       while (true) {

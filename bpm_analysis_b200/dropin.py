@@ -38,6 +38,7 @@ import torch
 from . import _native as nat
 from . import runtime as rt
 from .design import PADLEN
+from .params import output_dtype
 
 MAX_SESSIONS = 8
 MAX_RUNNERS = 4
@@ -102,8 +103,7 @@ class _StageARunnerSlot:
         n_stage = A.total_m * channels if sparse else n_in * channels
         self.stage = _pinned(n_stage, rt._torch_dtype(np_dtype))
         self.cap = min(A.total_m, A.total_m // max(int(A.cfg.distance), 1) + 2)    # find_peaks distance bounds the lists
-        self.uses = 0
-        self.graph = None
+        self.f32 = None                               # float32 copies of the signals, allocated on first use
 
 
 def _cfg2(params: Dict, rate: int) -> tuple:
@@ -179,7 +179,7 @@ class DropIn:
         else:
             self.stats["session_hits"] += 1
         if s.env_dev is None:
-            s.env_dev = self._upload(env)
+            s.env_dev = self._upload(env if env.dtype == np.float64 else env.astype(np.float64))
             s.items = rt.make_items([s.m], [s.m])
             s.items_dev = torch.from_numpy(s.items.view(np.int64).reshape(-1, 4).copy()).to(self.device)
         return s
@@ -214,8 +214,12 @@ class DropIn:
     def preprocess(self, pcm: np.ndarray, sample_rate: int, params: Dict, want_debug: bool, want_filtered: bool):
         """K0+K1+K2(+K2b) of one recording, with a2..a4 computed in the same stage-A call.
 
-        Returns (envelope, rate, filtered | None, debug_int16 | None)."""
+        Returns (envelope, rate, filtered | None, debug_int16 | None).  With
+        ``params["output_dtype"] == "float32"`` the envelope, the filtered signal and (later, out of the
+        session) the noise floor and the per-peak series come back as float32."""
         with self.lock:
+            f32 = output_dtype(params) == "float32"
+            sig_dtype = torch.float32 if f32 else torch.float64
             pcm = np.asarray(pcm)
             if pcm.dtype not in nat.PCM_DTYPES:
                 pcm = pcm.astype(np.float64)
@@ -238,13 +242,13 @@ class DropIn:
                     raise RuntimeError(f"bpm_host_gather_frames failed ({rc})")
             else:
                 np.copyto(slot.stage.numpy(), pcm.reshape(-1))
-            out = {"envelope": _pinned(M, torch.float64), "floor": _pinned(M, torch.float64),
+            out = {"envelope": _pinned(M, sig_dtype), "floor": _pinned(M, sig_dtype),
                    "counts": _pinned(4, torch.int64)}
-            lists = {k: _pinned(slot.cap, torch.int64 if k in ("troughs", "peaks") else torch.float64)
+            lists = {k: _pinned(slot.cap, torch.int64 if k in ("troughs", "peaks") else sig_dtype)
                      for k in ("troughs", "peaks", "strength", "deviation", "smoothed_dev")}
             extra = {}
             if want_filtered:
-                extra["filtered"] = _pinned(M, torch.float64)
+                extra["filtered"] = _pinned(M, sig_dtype)
             if want_debug:
                 extra["debug_wav"] = _pinned(M, torch.int16)
             ev_env, ev_all = torch.cuda.Event(), torch.cuda.Event()
@@ -252,17 +256,18 @@ class DropIn:
                 A.ingest(slot.stage)
                 A.launch()
                 self.stats["stage_a_calls"] += 1
-                out["envelope"].copy_(A.out["envelope"], non_blocking=True)
+                src = A.out if not f32 else self._cast_outputs(slot, M, want_filtered)
+                out["envelope"].copy_(src["envelope"][:M], non_blocking=True)
                 for k, h in extra.items():
-                    h.copy_(A.out[k], non_blocking=True)
+                    h.copy_(src[k][:M] if k == "filtered" else A.out[k], non_blocking=True)
                 ev_env.record(self.stream)
-                out["floor"].copy_(A.out["floor"], non_blocking=True)
+                out["floor"].copy_(src["floor"][:M], non_blocking=True)
                 out["counts"][0:1].copy_(A.out["trough_count"], non_blocking=True)
                 out["counts"][1:2].copy_(A.out["peak_count"], non_blocking=True)
                 out["counts"][2:3].copy_(A.out["trough_total"], non_blocking=True)
                 out["counts"][3:4].copy_(A.out["floor_mode"], non_blocking=True)
                 for k, h in lists.items():
-                    h.copy_(A.out[k][:slot.cap], non_blocking=True)
+                    h.copy_(src[k][:slot.cap], non_blocking=True)
                 ev_all.record(self.stream)
             ev_env.synchronize()
             env = out["envelope"].numpy()[:M]
@@ -272,6 +277,22 @@ class DropIn:
             filt = extra["filtered"].numpy()[:M] if want_filtered else None
             dbg = extra["debug_wav"].numpy()[:M] if want_debug else None
             return env, plan.rate, filt, dbg
+
+    def _cast_outputs(self, slot: "_StageARunnerSlot", M: int, want_filtered: bool) -> Dict[str, torch.Tensor]:
+        """float32 copies (bpm_cast_f32) of the signals of the slot's last stage-A call, on our stream."""
+        A = slot.runner
+        if slot.f32 is None:
+            f = dict(dtype=torch.float32, device=self.device)
+            slot.f32 = {"envelope": torch.empty(M, **f), "floor": torch.empty(M, **f), "filtered": torch.empty(M, **f),
+                        "strength": torch.empty(slot.cap, **f), "deviation": torch.empty(slot.cap, **f),
+                        "smoothed_dev": torch.empty(slot.cap, **f)}
+        names = ["envelope", "floor", "strength", "deviation", "smoothed_dev"] + (["filtered"] if want_filtered else [])
+        for k in names:
+            dst = slot.f32[k]
+            nat.check(self.lib.bpm_cast_f32(rt._ptr(A.out[k]), rt._ptr(dst), dst.numel(), self.stream.cuda_stream))
+        out = dict(A.out)
+        out.update({k: slot.f32[k] for k in names})
+        return out
 
     def _settle(self, s: Session) -> None:
         """Turn the read-back a ``preprocess`` call left in flight into session results."""
@@ -351,7 +372,7 @@ class DropIn:
                 if e["floor_dev"] is not None and e["floor_watch"].matches(floor):
                     floor_dev = e["floor_dev"]
             if floor_dev is None:
-                floor_dev = self._upload(floor)
+                floor_dev = self._upload(floor if floor.dtype == np.float64 else floor.astype(np.float64))
             distance, pq, smoothing = cfg
             cap = min(n, n // distance + 2)
             with torch.cuda.stream(self.stream):

@@ -25,7 +25,7 @@ from .dropin import dropin
 from .params import (HR_MIN_CHANGE_BPM, HR_MIN_DURATION_SEC, HR_PROMINENCE, SLOPE_WINDOW_SEC, band_edges,
                      effective_decimation)
 
-__all__ = ["preprocess_audio", "preprocess_pcm", "_calculate_dynamic_noise_floor", "_find_raw_peaks",
+__all__ = ["preprocess_audio", "preprocess_pcm", "read_wav", "_calculate_dynamic_noise_floor", "_find_raw_peaks",
            "_initialize_state", "calculate_bpm_series", "find_peak_recovery_rate", "find_peak_exertion_rate",
            "find_major_hr_inclines", "find_major_hr_declines", "calculate_windowed_hrv", "calculate_hrr",
            "find_recovery_phase", "find_peaks", "peak_trough_noise", "install"]
@@ -50,13 +50,25 @@ def preprocess_pcm(audio_data: np.ndarray, sample_rate: int, params: Dict, want_
     return dropin().preprocess(np.asarray(audio_data), int(sample_rate), params, bool(want_debug), bool(want_filtered))
 
 
+def read_wav(file_path: str):
+    """``wavfile.read`` (bpm_analysis.py:1014) without copying the file: the samples are memory-mapped
+    and the decimate-first ingest (``bpm_host_gather_frames``) then touches one frame in ``ds``
+    straight out of the page cache -- scipy's default read copies all of a 60-minute recording
+    (345 MB, ~150 ms) to hand 2 MB of it to the filter.  Formats scipy cannot map (24-bit PCM) fall
+    back to the copying read; sample rate, dtype, channel layout and errors are scipy's either way."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        try:
+            return wavfile.read(file_path, mmap=True)
+        except ValueError:
+            return wavfile.read(file_path)
+
+
 def preprocess_audio(file_path: str, params: Dict, output_directory: str) -> Tuple[np.ndarray, int]:
     """Reads, filters, and prepares the audio envelope.  Mirrors bpm_analysis.py:1007-1062."""
     save_debug_file = params["save_filtered_wav"]
     _ = params["downsample_factor"]                                 # KeyError like the reference
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        sample_rate, audio_data = wavfile.read(file_path)
+    sample_rate, audio_data = read_wav(file_path)
     envelope, rate, _, debug = preprocess_pcm(audio_data, sample_rate, params, want_debug=bool(save_debug_file),
                                               want_filtered=False)
     if save_debug_file:
@@ -65,6 +77,14 @@ def preprocess_audio(file_path: str, params: Dict, output_directory: str) -> Tup
         base_name = os.path.basename(os.path.splitext(file_path)[0])
         wavfile.write(os.path.join(output_directory, f"{base_name}_filtered_debug.wav"), rate, debug)
     return envelope, rate
+
+
+def _as_signal(a) -> np.ndarray:
+    """A contiguous float array WITHOUT copying what is one already: the session layer recognises the
+    arrays it handed out by their memory (float32 ones included, ``output_dtype="float32"``)."""
+    if isinstance(a, np.ndarray) and a.dtype in (np.float64, np.float32) and a.flags.c_contiguous:
+        return a
+    return np.ascontiguousarray(a, dtype=np.float64)
 
 
 # --------------------------------------------------------------------------- a2
@@ -85,7 +105,7 @@ def _arange_index(n: int) -> pd.Index:
 def _calculate_dynamic_noise_floor(audio_envelope: np.ndarray, sample_rate: int, params: Dict
                                    ) -> Tuple[pd.Series, np.ndarray]:
     """Dynamic noise floor from sanitised troughs.  Mirrors bpm_analysis.py:1064-1117."""
-    env = np.ascontiguousarray(audio_envelope, dtype=np.float64)
+    env = _as_signal(audio_envelope)
     d = dropin()
     floor, troughs, n_all, mode = d.noise_floor(env, int(sample_rate), params)
     if mode == 2:                                                   # :1073-1077
@@ -104,8 +124,7 @@ def _calculate_dynamic_noise_floor(audio_envelope: np.ndarray, sample_rate: int,
 # --------------------------------------------------------------------------- a3 / a4
 def _raw_peaks(envelope: np.ndarray, height_threshold: np.ndarray, sample_rate: int, params: Dict,
                with_metrics: bool):
-    env = np.ascontiguousarray(envelope, dtype=np.float64)
-    height = np.ascontiguousarray(height_threshold, dtype=np.float64)
+    env, height = _as_signal(envelope), _as_signal(height_threshold)
     if height.shape != env.shape:                                   # what scipy's find_peaks raises
         raise ValueError("array size of lower interval border must match x")
     return dropin().raw_peaks(env, height, int(sample_rate), params, with_metrics)
