@@ -19,6 +19,22 @@
 
 namespace bpm {
 
+// Which branch of _calculate_dynamic_noise_floor a recording takes, derived on the device from its
+// trough counts (no separate launch): 2 = fewer than 5 troughs: constant floor (:1073-1077);
+// 1 = at most 2 troughs survive sanitisation: the floor over ALL troughs (:1107-1110); 0 = the
+// regular case.  n_all == nullptr: mode 0 (stand-alone rolling floor).  n_kept == nullptr: the draft
+// stage (only the "< 5" test applies).
+struct FloorModeSrc {
+  const int64_t* n_all;
+  const int64_t* n_kept;
+};
+__device__ __forceinline__ int floor_mode_of(const FloorModeSrc& ms, int item) {
+  if (ms.n_all == nullptr) return 0;
+  if (ms.n_all[item] < 5) return 2;
+  if (ms.n_kept == nullptr) return 0;
+  return ms.n_kept[item] > 2 ? 0 : 1;
+}
+
 struct FloorMeta {
   long long n_knots;
   long long iv0, iv1;     // outputs with >= min_periods observations: [iv0, iv1]; bfill/ffill clamp to it
@@ -43,13 +59,20 @@ __device__ __forceinline__ long long n_obs_at(long long i, long long m, long lon
 // i.e. the floor over ALL troughs, when <= 2 troughs survive sanitisation, :1107-1110).
 __global__ void k_knot_table(const double* __restrict__ env, const int64_t* __restrict__ knots,
                              const int64_t* __restrict__ knot_count, const int64_t* __restrict__ alt_knots,
-                             const int64_t* __restrict__ alt_count, const int* __restrict__ mode,
+                             const int64_t* __restrict__ alt_count, FloorModeSrc ms,
                              const BpmItem* __restrict__ items,
                              int window, int* __restrict__ kt32, double* __restrict__ kv, double* __restrict__ ks,
-                             double* __restrict__ kinv, double* __restrict__ kend, FloorMeta* __restrict__ meta) {
+                             double* __restrict__ kinv, double* __restrict__ kend, FloorMeta* __restrict__ meta,
+                             int64_t* __restrict__ total_out, int64_t* __restrict__ mode_out) {
   const int item = blockIdx.y;
   const BpmItem it = items[item];
-  const bool use_alt = (mode != nullptr && alt_knots != nullptr && mode[item] == 1);
+  const int md_item = floor_mode_of(ms, item);
+  const bool use_alt = (alt_knots != nullptr && md_item == 1);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // what the caller's log lines report (bpm_analysis.py:1074, :1099, :1109)
+    if (total_out && ms.n_all) total_out[item] = ms.n_all[item];
+    if (mode_out) mode_out[item] = md_item;
+  }
   const long long T = use_alt ? alt_count[item] : knot_count[item];
   const int64_t* kt = (use_alt ? alt_knots : knots) + it.m_off;
   const double* e = env + it.m_off;
@@ -472,7 +495,7 @@ __device__ void cached_start(const WinCtx& c, short* cs, int a, int b, int ka, i
 // nan_fill (optional): value written instead of NaN when no output is valid.
 __global__ void __launch_bounds__(RF_THREADS) k_rolling_floor(
     const BpmItem* __restrict__ items, KnotTable kt, const FloorMeta* __restrict__ meta, int window, double q,
-    int run, const int* __restrict__ mode, const double* __restrict__ cval,
+    int run, FloorModeSrc ms, const double* __restrict__ cval,
     const double* __restrict__ nan_fill, double* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char rf_smem[];
   short* cs = reinterpret_cast<short*>(rf_smem) + threadIdx.x;       // [RF_SMAX][RF_THREADS]
@@ -484,7 +507,7 @@ __global__ void __launch_bounds__(RF_THREADS) k_rolling_floor(
   if (first >= m) return;
   const long long last = min(m, first + run);
   double* o = out + it.m_off;
-  const int md = mode ? mode[item] : 0;
+  const int md = floor_mode_of(ms, item);
   const double nanv = nan_fill ? nan_fill[item] : __longlong_as_double(0x7ff8000000000000ll);
   if (md == 2) {
     const double c = cval[item];
@@ -744,7 +767,7 @@ __device__ __forceinline__ bool rb_in(unsigned int j, int a, unsigned int span) 
 
 __global__ void __launch_bounds__(RB_THREADS, 1) k_rolling_floor_blk(
     const BpmItem* __restrict__ items, KnotTable kt, const FloorMeta* __restrict__ meta, int window, double q,
-    int outs, const int* __restrict__ mode, const double* __restrict__ cval,
+    int outs, FloorModeSrc ms, const double* __restrict__ cval,
     const double* __restrict__ nan_fill, double* __restrict__ out, double* __restrict__ sparse_out) {
   extern __shared__ __align__(16) unsigned char rb_raw[];
   RbShared& sh = *reinterpret_cast<RbShared*>(rb_raw);
@@ -756,7 +779,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rolling_floor_blk(
   const long long blk_last = min(m, blk_first + static_cast<long long>(outs));   // exclusive
   double* o = out + it.m_off;
   const int tid = threadIdx.x;
-  const int md = mode ? mode[item] : 0;
+  const int md = floor_mode_of(ms, item);
   const double nanv = nan_fill ? nan_fill[item] : __longlong_as_double(0x7ff8000000000000ll);
   // SPARSE mode (sparse_out != nullptr): outputs are wanted only AT the knots (the draft floor is
   // read nowhere else, :1093) and are written per knot number; tiles without knots do nothing.
@@ -1220,15 +1243,15 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rolling_floor_blk(
 
 // K7: keep trough t iff the draft floor there is not NaN and env[t] <= mult * floor[t]
 // (bpm_analysis.py:1090-1097), written in order by a single-pass compaction (decoupled look-back
-// over tile counts, common.cuh).  keep_all[item] != 0 keeps every trough (the <5 troughs path
-// returns the unsanitised list, :1077).
+// over tile counts, common.cuh).  keep_few: a recording with fewer than 5 troughs keeps them all
+// (the "<5 troughs" path returns the unsanitised list, :1077).
 constexpr int SZ_THREADS = 256;
 constexpr int SZ_PER = 4;
 constexpr int SZ_TILE = SZ_THREADS * SZ_PER;
 
 __global__ void __launch_bounds__(SZ_THREADS) k_sanitize_compact(
     const double* __restrict__ env, const double* __restrict__ draft, const int64_t* __restrict__ troughs,
-    const int64_t* __restrict__ trough_count, const int* __restrict__ keep_all, const BpmItem* __restrict__ items,
+    const int64_t* __restrict__ trough_count, int keep_few, const BpmItem* __restrict__ items,
     double mult, int draft_by_knot, unsigned long long* __restrict__ status, int64_t status_stride,
     int64_t* __restrict__ kept_out, int64_t* __restrict__ kept_count) {
   __shared__ int s_scan[34];
@@ -1241,7 +1264,7 @@ __global__ void __launch_bounds__(SZ_THREADS) k_sanitize_compact(
     if (nt == 0 && blockIdx.x == 0 && threadIdx.x == 0) kept_count[item] = 0;
     return;
   }
-  const bool all = keep_all && keep_all[item];
+  const bool all = keep_few && nt < 5;                       // the "<5 troughs" path returns them all (:1077)
   int64_t t[SZ_PER];
   unsigned mask = 0;
 #pragma unroll
@@ -1271,28 +1294,6 @@ __global__ void __launch_bounds__(SZ_THREADS) k_sanitize_compact(
   if (threadIdx.x == 0 && k0 + SZ_TILE >= nt) kept_count[item] = s_off + total;
 }
 
-// per-item control words of _calculate_dynamic_noise_floor
-//   stage 0 (after the trough search):  few[i] = n_all < 5 ; draft_mode[i] = few ? skip(2 -> constant) : 0
-//   stage 1 (after sanitisation):       final_mode[i] = few ? 2 : (n_kept > 2 ? 0 : 1)
-// total_out / mode_out (optional, stage 1): the trough count before sanitisation and the branch
-// taken, for the caller's log lines (bpm_analysis.py:1074, :1099, :1109)
-__global__ void k_floor_modes(const int64_t* __restrict__ n_all, const int64_t* __restrict__ n_kept, int n_items,
-                              int stage, int* __restrict__ few, int* __restrict__ mode,
-                              int64_t* __restrict__ total_out, int64_t* __restrict__ mode_out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_items) return;
-  if (stage == 0) {
-    const int f = n_all[i] < 5 ? 1 : 0;
-    few[i] = f;
-    mode[i] = f ? 2 : 0;
-  } else {
-    const int md = few[i] ? 2 : (n_kept[i] > 2 ? 0 : 1);
-    mode[i] = md;
-    if (total_out) total_out[i] = n_all[i];
-    if (mode_out) mode_out[i] = md;
-  }
-}
-
 // host launchers of the small kernels above (called from pipeline.cu: every translation unit
 // launches only kernels it defines, so no relocatable device code is needed)
 size_t sanitize_workspace_bytes(int64_t total_m, int n) {
@@ -1302,7 +1303,7 @@ size_t sanitize_workspace_bytes(int64_t total_m, int n) {
 }
 
 int sanitize_run(const double* env, const double* draft, const int64_t* troughs, const int64_t* trough_count,
-                 const int* keep_all, const BpmItem* items, const BatchShape& sh, double mult, int draft_by_knot,
+                 int keep_few, const BpmItem* items, const BatchShape& sh, double mult, int draft_by_knot,
                  int64_t* kept_out, int64_t* kept_count, Workspace& ws, cudaStream_t st) {
   if (!env || !draft || !troughs || !trough_count || !items || !kept_out || !kept_count) return BPM_ERR_ARG;
   const int64_t max_t = sh.max_m / 2 + 2;
@@ -1312,15 +1313,7 @@ int sanitize_run(const double* env, const double* draft, const int64_t* troughs,
   if (cudaMemsetAsync(status, 0, sizeof(unsigned long long) * sh.n_items * stride, st) != cudaSuccess) return BPM_ERR_CUDA;
   BPM_KERNEL(k_sanitize_compact);
   k_sanitize_compact<<<dim3(cdiv(max_t, SZ_TILE), sh.n_items), SZ_THREADS, 0, st>>>(
-      env, draft, troughs, trough_count, keep_all, items, mult, draft_by_knot, status, stride, kept_out, kept_count);
-  BPM_LAUNCH_OK();
-  return BPM_OK;
-}
-
-int floor_modes_run(const int64_t* n_all, const int64_t* n_kept, int n_items, int stage, int* few, int* mode,
-                    int64_t* total_out, int64_t* mode_out, cudaStream_t st) {
-  BPM_KERNEL(k_floor_modes);
-  k_floor_modes<<<cdiv(n_items, 128), 128, 0, st>>>(n_all, n_kept, n_items, stage, few, mode, total_out, mode_out);
+      env, draft, troughs, trough_count, keep_few, items, mult, draft_by_knot, status, stride, kept_out, kept_count);
   BPM_LAUNCH_OK();
   return BPM_OK;
 }
@@ -1353,20 +1346,23 @@ size_t rolling_floor_workspace_bytes(int64_t total_m, int n_items) {
 bool rolling_floor_sparse_ok(int window) { return static_cast<int64_t>(RB_NCAP) - window + 1 >= RB_THREADS; }
 
 // sparse_out != nullptr (only with rolling_floor_sparse_ok): values at the knots, per knot number;
-// `out` is then not written.  alt_knots / alt_count: the list used for items with mode == 1.
+// `out` is then not written.  alt_knots / alt_count: the list used for items whose mode is 1;
+// mode_n_all / mode_n_kept: the trough counts the mode is derived from (floor_mode_of).
 int rolling_floor_run(const double* env, const int64_t* knots, const int64_t* knot_count, const BpmItem* items,
-                      const BatchShape& sh, int window, double q, const int* mode, const int64_t* alt_knots,
-                      const int64_t* alt_count, const double* cval, const double* nan_fill, double* out,
-                      double* sparse_out, Workspace& ws, cudaStream_t st) {
+                      const BatchShape& sh, int window, double q, const int64_t* mode_n_all,
+                      const int64_t* mode_n_kept, const int64_t* alt_knots, const int64_t* alt_count, const double* cval,
+                      const double* nan_fill, int64_t* total_out, int64_t* mode_out, double* out, double* sparse_out,
+                      Workspace& ws, cudaStream_t st) {
   if (!env || !knots || !knot_count || !items || (!out && !sparse_out) || sh.n_items <= 0 || window < 1) return BPM_ERR_ARG;
   if (sparse_out && !rolling_floor_sparse_ok(window)) return BPM_ERR_ARG;
   FloorBuffers b;
   BPM_TRY(carve_floor(ws, sh.total_m, sh.n_items, &b));
   const int64_t max_k = sh.max_m / 2 + 2;
   BPM_KERNEL(k_knot_table);
-  k_knot_table<<<dim3(cdiv(max_k, 256), sh.n_items), 256, 0, st>>>(env, knots, knot_count, alt_knots, alt_count, mode,
+  const FloorModeSrc ms{mode_n_all, mode_n_kept};
+  k_knot_table<<<dim3(cdiv(max_k, 256), sh.n_items), 256, 0, st>>>(env, knots, knot_count, alt_knots, alt_count, ms,
                                                                     items, window, b.kt32, b.kv, b.ks, b.kinv, b.kend,
-                                                                    b.meta);
+                                                                    b.meta, total_out, mode_out);
   BPM_LAUNCH_OK();
   // outputs per thread of the per-thread kernel: long enough to amortise the bisection
   int64_t run = sh.total_m / (148 * 1024);
@@ -1386,7 +1382,7 @@ int rolling_floor_run(const double* env, const int64_t* knots, const int64_t* kn
     cudaFuncSetAttribute(k_rolling_floor_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(RbShared)));
     BPM_KERNEL(k_rolling_floor_blk);
     k_rolling_floor_blk<<<dim3(cdiv(sh.max_m, outs), sh.n_items), RB_THREADS, sizeof(RbShared), st>>>(
-        items, kt, b.meta, window, q, static_cast<int>(outs), mode, cval, nan_fill, out, sparse_out);
+        items, kt, b.meta, window, q, static_cast<int>(outs), ms, cval, nan_fill, out, sparse_out);
     BPM_LAUNCH_OK();
     return BPM_OK;
   }
@@ -1394,7 +1390,7 @@ int rolling_floor_run(const double* env, const int64_t* knots, const int64_t* kn
   cudaFuncSetAttribute(k_rolling_floor, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   BPM_KERNEL(k_rolling_floor);
   k_rolling_floor<<<dim3(cdiv(sh.max_m, RF_THREADS * run), sh.n_items), RF_THREADS, smem, st>>>(
-      items, kt, b.meta, window, q, static_cast<int>(run), mode, cval, nan_fill, out);
+      items, kt, b.meta, window, q, static_cast<int>(run), ms, cval, nan_fill, out);
   BPM_LAUNCH_OK();
   return BPM_OK;
 }

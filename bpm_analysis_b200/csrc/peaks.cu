@@ -11,8 +11,8 @@
 //   k_distance_tiles      scipy's greedy "highest first removes neighbours closer than d" as the
 //                         well-founded recursion  kept(k) <=> no kept higher-priority neighbour within d,
 //                         evaluated depth-first per candidate with the results memoised in shared memory
-//                         (no rounds, no barriers).  A CTA owns 1024 consecutive candidates and stages
-//                         them with a halo of 128 on either side; a candidate is settled when its
+//                         (no rounds, no barriers).  A CTA owns 512 consecutive candidates and stages
+//                         them with a halo of 64 on either side; a candidate is settled when its
 //                         dependency chain (strictly rising priority, each hop < d samples) stays inside
 //                         the staged range, which is the case for all but pathological inputs.  Whatever
 //                         is left is finished exactly by the last CTA of the recording over global memory.
@@ -177,9 +177,9 @@ __device__ unsigned long long g_dbg_pk[16];
 #endif
 
 // ------------------------------------------------------------------ distance
-constexpr int DT_THREADS = 256;
-constexpr int DT_OWN = 1024;                      // candidates a CTA settles per tile
-constexpr int DT_HALO = 128;                      // staged on either side of them
+constexpr int DT_THREADS = 128;
+constexpr int DT_OWN = 512;                       // candidates a CTA settles per tile
+constexpr int DT_HALO = 64;                       // staged on either side of them
 constexpr int DT_STAGE = DT_OWN + 2 * DT_HALO;
 constexpr int DT_DEPTH = 24;                      // dependency chains followed this deep, longer ones are left pending
 enum : unsigned char { DST_REMOVED = 0, DST_KEPT = 1, DST_PENDING = 3 };   // global state of a candidate
@@ -416,17 +416,18 @@ __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __r
 // Warp-cooperative, both sides walked together 32 samples at a time: a side passes as soon as
 // a sample low enough (x[p] - x[i] >= thr) is met before the walk would stop (a sample above
 // the peak, or the end of the signal); it fails when the walk stops first.
-__device__ bool warp_prominence_ok(const double* __restrict__ xi, int sign, int64_t n, int64_t p, double thr) {
+template <class Val>
+__device__ __forceinline__ bool warp_prominence_ok(Val val, int64_t n, int64_t p, double thr) {
   const int lane = threadIdx.x & 31;
-  const double xp = signed_val(xi[p], sign);
+  const double xp = val(p);
   if (__dsub_rn(xp, xp) >= thr) return true;            // the peak itself is the running minimum
   int done_l = 0, done_r = 0;                             // 0 open, 1 passed
   int64_t bl = p - 1, br = p + 1;
   while (true) {
     const int64_t il = bl - lane, ir = br + lane;
     const bool vl = !done_l && il >= 0, vr = !done_r && ir < n;
-    const double xl = vl ? signed_val(xi[il], sign) : 0.0;
-    const double xr = vr ? signed_val(xi[ir], sign) : 0.0;
+    const double xl = vl ? val(il) : 0.0;
+    const double xr = vr ? val(ir) : 0.0;
     if (!done_l) {
       const bool stop = !vl || (xl > xp);
       const bool pass = vl && !(xl > xp) && (__dsub_rn(xp, xl) >= thr);
@@ -449,8 +450,9 @@ __device__ bool warp_prominence_ok(const double* __restrict__ xi, int sign, int6
   }
 }
 
-
 constexpr int PC_THREADS = 256;                   // candidates per tile of k_prominence_compact
+constexpr int PC_WIN = 512;                       // signal samples a warp stages around its 32 candidates
+constexpr int PC_MARGIN = 64;
 
 __global__ void __launch_bounds__(PC_THREADS) k_prominence_compact(const double* __restrict__ x, int sign,
                                                                    const BpmItem* __restrict__ items,
@@ -464,6 +466,7 @@ __global__ void __launch_bounds__(PC_THREADS) k_prominence_compact(const double*
                                                                    int64_t* __restrict__ out_count) {
   __shared__ int s_scan[34];
   __shared__ long long s_off;
+  __shared__ double s_win[PC_THREADS / 32][PC_WIN];
   const int item = blockIdx.y;
   const BpmItem it = items[item];
   const int64_t nc = cand_count[item];
@@ -483,12 +486,27 @@ __global__ void __launch_bounds__(PC_THREADS) k_prominence_compact(const double*
     // walk was measured slower: 410 vs 237 us on the 24-h stream -- the slowest lane sets the pace)
     const double thr = prominence[item];
     unsigned todo = __ballot_sync(0xffffffffu, live);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int64_t ps = __shfl_sync(0xffffffffu, p, src);
-      const bool ok = warp_prominence_ok(xi, sign, it.m, ps, thr);
-      if (lane == src) live = ok;
+    if (todo) {
+      // the signal around this warp's candidates comes into shared memory with ONE round of coalesced
+      // loads; the walks then read it from there (most end inside it) and fall through to global
+      // memory beyond it
+      const int first = __ffs(todo) - 1, last = 31 - __clz(todo);
+      int64_t wlo = __shfl_sync(0xffffffffu, p, first) - PC_MARGIN;
+      if (wlo < 0) wlo = 0;
+      int64_t whi = min(it.m, min(wlo + PC_WIN, __shfl_sync(0xffffffffu, p, last) + PC_MARGIN + 1));
+      double* sw = s_win[tid >> 5];
+      for (int t = lane; t < static_cast<int>(whi - wlo); t += 32) sw[t] = signed_val(xi[wlo + t], sign);
+      __syncwarp();
+      auto val = [&](int64_t i) -> double {
+        return (i >= wlo && i < whi) ? sw[i - wlo] : signed_val(xi[i], sign);
+      };
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int64_t ps = __shfl_sync(0xffffffffu, p, src);
+        const bool ok = warp_prominence_ok(val, it.m, ps, thr);
+        if (lane == src) live = ok;
+      }
     }
   }
   int total;
@@ -557,7 +575,7 @@ int find_peaks_run(const double* x, int sign, const double* height, const double
   const int64_t max_c = sh.max_m / 2 + 1;
   {
     int64_t gx = (max_c + DT_OWN - 1) / DT_OWN;
-    const int64_t cap = (148 * 4 + sh.n_items - 1) / sh.n_items;
+    const int64_t cap = (148 * 12 + sh.n_items - 1) / sh.n_items;
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     BPM_KERNEL(k_distance_tiles);

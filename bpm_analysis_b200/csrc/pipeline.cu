@@ -32,15 +32,14 @@ int find_peaks_run(const double* x, int sign, const double* height, const double
 size_t rolling_floor_workspace_bytes(int64_t total_m, int n_items);
 bool rolling_floor_sparse_ok(int window);
 int rolling_floor_run(const double* env, const int64_t* knots, const int64_t* knot_count, const BpmItem* items,
-                      const BatchShape& sh, int window, double q, const int* mode, const int64_t* alt_knots,
-                      const int64_t* alt_count, const double* cval, const double* nan_fill, double* out,
-                      double* sparse_out, Workspace& ws, cudaStream_t st);
+                      const BatchShape& sh, int window, double q, const int64_t* mode_n_all,
+                      const int64_t* mode_n_kept, const int64_t* alt_knots, const int64_t* alt_count, const double* cval,
+                      const double* nan_fill, int64_t* total_out, int64_t* mode_out, double* out, double* sparse_out,
+                      Workspace& ws, cudaStream_t st);
 size_t sanitize_workspace_bytes(int64_t total_m, int n);
 int sanitize_run(const double* env, const double* draft, const int64_t* troughs, const int64_t* trough_count,
-                 const int* keep_all, const BpmItem* items, const BatchShape& sh, double mult, int draft_by_knot,
+                 int keep_few, const BpmItem* items, const BatchShape& sh, double mult, int draft_by_knot,
                  int64_t* kept_out, int64_t* kept_count, Workspace& ws, cudaStream_t st);
-int floor_modes_run(const int64_t* n_all, const int64_t* n_kept, int n_items, int stage, int* few, int* mode,
-                    int64_t* total_out, int64_t* mode_out, cudaStream_t st);
 // metrics.cu
 int peak_metrics_run(const double* env, const double* floor_, const int64_t* peaks, const int64_t* peak_count,
                      const BpmItem* items, const BatchShape& sh, double factor, double* strength,
@@ -66,8 +65,6 @@ struct NoiseFloorScratch {
   int64_t* all_troughs;
   int64_t* n_all;
   double* draft;
-  int* few;
-  int* mode;
   char* sanitize_ws;
   size_t sanitize_ws_bytes;
   char* select_ws;          // the quantile passes run concurrently with the trough search: own scratch
@@ -81,8 +78,6 @@ static int carve_noise_floor(Workspace& ws, int64_t total_m, int n, NoiseFloorSc
   s->all_troughs = ws.take<int64_t>(total_m);
   s->n_all = ws.take<int64_t>(n);
   s->draft = ws.take<double>(total_m);
-  s->few = ws.take<int>(n);
-  s->mode = ws.take<int>(n);
   s->sanitize_ws_bytes = sanitize_workspace_bytes(total_m, n);
   s->sanitize_ws = ws.take<char>(s->sanitize_ws_bytes);
   s->select_ws_bytes = quantile_workspace_bytes(n);
@@ -149,29 +144,28 @@ int noise_floor_run(const double* env, const BpmItem* items, const BatchShape& s
                            fj.join_event()));                                                        // :1070
     if (fj.active && cudaGetLastError() != cudaSuccess) return BPM_ERR_CUDA;
   }
-  BPM_TRY(floor_modes_run(s.n_all, nullptr, n, 0, s.few, s.mode, nullptr, nullptr, st));
   // draft floor from all troughs (:1081-1086).  It is only ever read AT the troughs (:1093), so it
   // is computed there only (one value per trough) whenever the block-cooperative kernel applies.
   const bool sparse = rolling_floor_sparse_ok(window);
   {
     Workspace w = sub_ws(ws, 0);
-    BPM_TRY(rolling_floor_run(env, s.all_troughs, s.n_all, items, sh, window, floor_q, s.mode, nullptr, nullptr, s.q_nf,
-                              nullptr, sparse ? nullptr : s.draft, sparse ? s.draft : nullptr, w, st));
+    BPM_TRY(rolling_floor_run(env, s.all_troughs, s.n_all, items, sh, window, floor_q, s.n_all, nullptr, nullptr, nullptr,
+                              s.q_nf, nullptr, nullptr, nullptr, sparse ? nullptr : s.draft, sparse ? s.draft : nullptr,
+                              w, st));
   }
   {
     Workspace wz(ws.measuring() ? nullptr : s.sanitize_ws, s.sanitize_ws_bytes);
-    BPM_TRY(sanitize_run(env, s.draft, s.all_troughs, s.n_all, s.few, items, sh, mult, sparse ? 1 : 0, troughs_out,
+    BPM_TRY(sanitize_run(env, s.draft, s.all_troughs, s.n_all, 1, items, sh, mult, sparse ? 1 : 0, troughs_out,
                          trough_count, wz, st));                                                     // :1090-1097
   }
-  BPM_TRY(floor_modes_run(s.n_all, trough_count, n, 1, s.few, s.mode, total_out, mode_out, st));
   {
     // final floor from the kept troughs (:1102-1106); when <= 2 are kept the reference reuses the
     // draft (:1107-1110) = the same rolling quantile over ALL troughs, recomputed here (mode 1
     // makes the knot table take the other list); constant on the "<5" path (:1073-1077), q(0.1)
     // when everything is NaN (:1113-1115)
     Workspace w = sub_ws(ws, 0);
-    BPM_TRY(rolling_floor_run(env, troughs_out, trough_count, items, sh, window, floor_q, s.mode, s.all_troughs,
-                              s.n_all, s.q_nf, q_fb, floor_out, nullptr, w, st));
+    BPM_TRY(rolling_floor_run(env, troughs_out, trough_count, items, sh, window, floor_q, s.n_all, trough_count,
+                              s.all_troughs, s.n_all, s.q_nf, q_fb, total_out, mode_out, floor_out, nullptr, w, st));
   }
   return BPM_OK;
 }
@@ -365,7 +359,7 @@ int bpm_rolling_floor(const double* envelope, const int64_t* knots, const int64_
   if (!workspace || !items_host || n_items <= 0) return BPM_ERR_ARG;
   Workspace ws(workspace, workspace_bytes);
   return rolling_floor_run(envelope, knots, knot_count, items, batch_shape(items_host, n_items), window, q, nullptr,
-                           nullptr, nullptr, nullptr, nullptr, floor_out, nullptr, ws,
+                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, floor_out, nullptr, ws,
                            static_cast<cudaStream_t>(stream));
 }
 
@@ -390,7 +384,7 @@ int bpm_sanitize_troughs(const double* envelope, const double* draft_floor, cons
                          size_t workspace_bytes, void* stream) {
   if (!workspace || !items_host || n_items <= 0) return BPM_ERR_ARG;
   Workspace ws(workspace, workspace_bytes);
-  return sanitize_run(envelope, draft_floor, troughs, trough_count, nullptr, items, batch_shape(items_host, n_items),
+  return sanitize_run(envelope, draft_floor, troughs, trough_count, 0, items, batch_shape(items_host, n_items),
                       rejection_multiplier, 0, kept_out, kept_count, ws, static_cast<cudaStream_t>(stream));
 }
 

@@ -104,30 +104,22 @@ __device__ void sel_advance(const SelState& prev, const unsigned int* __restrict
   __syncthreads();
 }
 
-__global__ void k_select_init(const BpmItem* __restrict__ items, int n_items, SelLevels lv,
-                              SelState* __restrict__ states) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_items) return;
-  const long long n = items[i].m;
-  for (int l = 0; l < lv.nq; ++l) {
-    SelState s;
-    const double v = __dmul_rn(static_cast<double>(n - 1), lv.q[l]);   // (n - 1) * q
-    const double fl = floor(v);
-    s.prefix = 0;
-    s.k = static_cast<long long>(fl);
-    if (s.k > n - 1) s.k = n - 1;
-    if (s.k < 0) s.k = 0;
-    s.rank = s.k;
-    s.below = 0;
-    s.count = n;
-    s.gamma = __dsub_rn(v, fl);
-    s.next_key = ~0ull;
-    s.active = (n > 0 && (lv.cond[l] == nullptr || lv.cond[l][i] != 0)) ? 1 : 0;
-    states[st_idx(0, l, i, n_items)] = s;
-    SelState f = s;                       // final slot: next_key accumulates by atomicMin, active set by k_select_next
-    f.active = 0;
-    states[st_idx(SEL_PASSES, l, i, n_items)] = f;
-  }
+// state before the first digit pass: target rank k = floor((n - 1) q), fraction gamma (numpy's virtual index)
+__device__ __forceinline__ SelState sel_initial(long long n, double q, bool on) {
+  SelState s;
+  const double v = __dmul_rn(static_cast<double>(n - 1), q);     // (n - 1) * q
+  const double fl = floor(v);
+  s.prefix = 0;
+  s.k = static_cast<long long>(fl);
+  if (s.k > n - 1) s.k = n - 1;
+  if (s.k < 0) s.k = 0;
+  s.rank = s.k;
+  s.below = 0;
+  s.count = n;
+  s.gamma = __dsub_rn(v, fl);
+  s.next_key = ~0ull;
+  s.active = (n > 0 && on) ? 1 : 0;
+  return s;
 }
 
 // add 1 to s_hist[bin] for every lane with `on`, one shared-memory atomic per distinct bin per warp
@@ -141,7 +133,7 @@ __device__ __forceinline__ void warp_hist_add(unsigned int* s_hist, bool on, uns
 // pass p: (p > 0) resolve pass p-1, then histogram digit p of the elements under each level's prefix
 __global__ void __launch_bounds__(SEL_THREADS) k_select_pass(const double* __restrict__ x,
                                                              const BpmItem* __restrict__ items, int p, int nq,
-                                                             SelState* __restrict__ states,
+                                                             SelLevels lv, SelState* __restrict__ states,
                                                              unsigned int* __restrict__ hist, int n_items) {
   __shared__ unsigned int s_hist[SEL_MAXQ][SEL_BINS];
   __shared__ SelState s_cur[SEL_MAXQ];
@@ -160,10 +152,14 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_pass(const double* __res
         __syncthreads();
         continue;
       }
-      sel_advance(before, hist + hist_idx(item, l, p - 1), sel_bits(p - 1), &s_cur[l], s_cum);
+      sel_advance(before, hist + hist_idx(item, (p - 1 == 0) ? 0 : l, p - 1), sel_bits(p - 1), &s_cur[l], s_cum);
       if (blockIdx.x == 0 && threadIdx.x == 0) states[st_idx(p, l, item, n_items)] = s_cur[l];
     } else {
-      if (threadIdx.x == 0) s_cur[l] = states[st_idx(0, l, item, n_items)];
+      // first pass: every CTA derives the initial state itself (no separate init launch)
+      if (threadIdx.x == 0) {
+        s_cur[l] = sel_initial(it.m, lv.q[l], lv.cond[l] == nullptr || lv.cond[l][item] != 0);
+        if (blockIdx.x == 0) states[st_idx(0, l, item, n_items)] = s_cur[l];
+      }
       __syncthreads();
     }
     any = any || (s_cur[l].active != 0);
@@ -173,8 +169,11 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_pass(const double* __res
   const int sh = sel_shift(p), bits = sel_bits(p);
   const int up = sh + bits;                       // bits above this digit
   const unsigned int mask = (1u << bits) - 1u;
-  for (int l = 0; l < nq; ++l)
-    if (s_cur[l].active)
+  // in the first pass no digit is resolved yet: ONE histogram of the whole recording serves every level
+  // (sel_advance of the next pass reads it through hist_idx(item, 0, 0))
+  const int nh = (p == 0) ? 1 : nq;
+  for (int l = 0; l < nh; ++l)
+    if (p == 0 || s_cur[l].active)
       for (int t = threadIdx.x; t < (1 << bits); t += SEL_THREADS) s_hist[l][t] = 0;
   __syncthreads();
   const double* __restrict__ xi = x + it.m_off;
@@ -184,15 +183,15 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_pass(const double* __res
     const bool in = i < it.m;
     const unsigned long long key = in ? f64_key(xi[i]) : 0ull;
     const unsigned int bin = static_cast<unsigned int>(key >> sh) & mask;
-    for (int l = 0; l < nq; ++l) {
-      if (!s_cur[l].active) continue;
+    for (int l = 0; l < nh; ++l) {
+      if (p != 0 && !s_cur[l].active) continue;
       const bool match = in && ((up >= 64) ? true : ((key >> up) == s_cur[l].prefix));
       warp_hist_add(s_hist[l], match, bin);
     }
   }
   __syncthreads();
-  for (int l = 0; l < nq; ++l) {
-    if (!s_cur[l].active) continue;
+  for (int l = 0; l < nh; ++l) {
+    if (p != 0 && !s_cur[l].active) continue;
     unsigned int* gh = hist + hist_idx(item, l, p);
     for (int t = threadIdx.x; t < (1 << bits); t += SEL_THREADS) {
       const unsigned int c = s_hist[l][t];
@@ -239,7 +238,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_collect(const double* __
       __syncthreads();
       continue;
     }
-    sel_advance(before, hist + hist_idx(item, l, npre - 1), sel_bits(npre - 1), &s_cur[l], s_cum);
+    sel_advance(before, hist + hist_idx(item, (npre - 1 == 0) ? 0 : l, npre - 1), sel_bits(npre - 1), &s_cur[l], s_cum);
     if (threadIdx.x == 0) s_cur[l].active = (s_cur[l].count <= SEL_CAP) ? 2 : 1;     // 2: collected
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0) states[st_idx(npre, l, item, n_items)] = s_cur[l];
@@ -330,9 +329,10 @@ __global__ void __launch_bounds__(SEL_FIN_THREADS) k_select_finish(const double*
   const int item = blockIdx.x;
   const BpmItem it = items[item];
   const int tid = threadIdx.x;
-  for (int l = 0; l < lv.nq; ++l) {
+  {
+    const int l = blockIdx.y;                               // one CTA per (recording, level)
     const SelState s = states[st_idx(npre, l, item, n_items)];
-    if (s.active == 0) continue;                            // uniform per CTA
+    if (s.active == 0) return;                              // uniform per CTA
     unsigned long long ka, kb;
     if (s.active == 2) {
       const int nc = static_cast<int>(s.count);
@@ -489,13 +489,10 @@ int quantile_multi_run(const double* x, const BpmItem* items, const BatchShape& 
   // digit passes before the bucket is collected: two resolve 22 bits, enough below ~4 M samples; a third
   // (33 bits) keeps the bucket under SEL_CAP for the long streams (24 h at 333 Hz = 28.8 M samples)
   const int npre = sh.max_m > (1ll << 22) ? 3 : 2;
-  BPM_KERNEL(k_select_init);
-  k_select_init<<<cdiv(n, 128), 128, 0, st>>>(items, n, lv, b.states);
-  BPM_LAUNCH_OK();
   const dim3 grid(cdiv(sh.max_m, SEL_TILE), n);
   for (int p = 0; p < npre; ++p) {
     BPM_KERNEL(k_select_pass);
-    k_select_pass<<<grid, SEL_THREADS, 0, st>>>(x, items, p, nq, b.states, b.hist, n);
+    k_select_pass<<<grid, SEL_THREADS, 0, st>>>(x, items, p, nq, lv, b.states, b.hist, n);
     BPM_LAUNCH_OK();
   }
   SelCollect cl{b.buf, b.count, b.next_above, b.next_above + nlv, b.bmax};
@@ -503,7 +500,7 @@ int quantile_multi_run(const double* x, const BpmItem* items, const BatchShape& 
   k_select_collect<<<grid, SEL_THREADS, 0, st>>>(x, items, nq, b.states, b.hist, cl, npre, n);
   BPM_LAUNCH_OK();
   BPM_KERNEL(k_select_finish);
-  k_select_finish<<<n, SEL_FIN_THREADS, 0, st>>>(x, items, lv, b.states, cl, npre, n);
+  k_select_finish<<<dim3(n, nq), SEL_FIN_THREADS, 0, st>>>(x, items, lv, b.states, cl, npre, n);
   BPM_LAUNCH_OK();
   return BPM_OK;
 }
