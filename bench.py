@@ -418,7 +418,9 @@ def run_b200(args):
     lib = _native.load_library()
     params = bench_params(args)
     pcm, sr, beats = make_recording(args, rank)
-    A = StageARunner([len(pcm)], sr, params)
+    # the product path (preprocess_audio -> envelope) never reads the band-passed signal itself: in the
+    # decimate-first order it does not leave the SMs (want_filtered=False); fullrate mode still writes it
+    A = StageARunner([len(pcm)], sr, params, want_filtered=(args.filter_mode != "parity"))
     rate = A.plan.rate
     beat_idx = synth.beats_to_envelope_indices(beats, rate)
     Bn = BeatRunner(len(beat_idx), rate, params, hr_extrema_distance(beat_idx, rate))

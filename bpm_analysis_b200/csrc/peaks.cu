@@ -451,8 +451,6 @@ __device__ __forceinline__ bool warp_prominence_ok(Val val, int64_t n, int64_t p
 }
 
 constexpr int PC_THREADS = 256;                   // candidates per tile of k_prominence_compact
-constexpr int PC_WIN = 512;                       // signal samples a warp stages around its 32 candidates
-constexpr int PC_MARGIN = 64;
 
 __global__ void __launch_bounds__(PC_THREADS) k_prominence_compact(const double* __restrict__ x, int sign,
                                                                    const BpmItem* __restrict__ items,
@@ -466,7 +464,6 @@ __global__ void __launch_bounds__(PC_THREADS) k_prominence_compact(const double*
                                                                    int64_t* __restrict__ out_count) {
   __shared__ int s_scan[34];
   __shared__ long long s_off;
-  __shared__ double s_win[PC_THREADS / 32][PC_WIN];
   const int item = blockIdx.y;
   const BpmItem it = items[item];
   const int64_t nc = cand_count[item];
@@ -486,27 +483,15 @@ __global__ void __launch_bounds__(PC_THREADS) k_prominence_compact(const double*
     // walk was measured slower: 410 vs 237 us on the 24-h stream -- the slowest lane sets the pace)
     const double thr = prominence[item];
     unsigned todo = __ballot_sync(0xffffffffu, live);
-    if (todo) {
-      // the signal around this warp's candidates comes into shared memory with ONE round of coalesced
-      // loads; the walks then read it from there (most end inside it) and fall through to global
-      // memory beyond it
-      const int first = __ffs(todo) - 1, last = 31 - __clz(todo);
-      int64_t wlo = __shfl_sync(0xffffffffu, p, first) - PC_MARGIN;
-      if (wlo < 0) wlo = 0;
-      int64_t whi = min(it.m, min(wlo + PC_WIN, __shfl_sync(0xffffffffu, p, last) + PC_MARGIN + 1));
-      double* sw = s_win[tid >> 5];
-      for (int t = lane; t < static_cast<int>(whi - wlo); t += 32) sw[t] = signed_val(xi[wlo + t], sign);
-      __syncwarp();
-      auto val = [&](int64_t i) -> double {
-        return (i >= wlo && i < whi) ? sw[i - wlo] : signed_val(xi[i], sign);
-      };
-      while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int64_t ps = __shfl_sync(0xffffffffu, p, src);
-        const bool ok = warp_prominence_ok(val, it.m, ps, thr);
-        if (lane == src) live = ok;
-      }
+    // (staging the signal around a warp's candidates in shared memory first was measured slower: 548 vs
+    // 365 us on the 24-h stream -- the walks touch about as many samples as the staging itself)
+    auto val = [&](int64_t i) -> double { return signed_val(xi[i], sign); };
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int64_t ps = __shfl_sync(0xffffffffu, p, src);
+      const bool ok = warp_prominence_ok(val, it.m, ps, thr);
+      if (lane == src) live = ok;
     }
   }
   int total;

@@ -231,7 +231,10 @@ class DropIn:
                 raise ValueError("The length of the input vector x must be greater than padlen, which is 15.")
             frame_bytes = channels * pcm.dtype.itemsize
             sparse = plan.block == 1 and plan.stride > 1 and plan.stride * frame_bytes >= HOST_GATHER_MIN_PITCH_BYTES
-            slot = self._slot(n_in, sample_rate, params, pcm.dtype, channels, want_debug, want_filtered, sparse)
+            # the band-passed signal only stays out of HBM in the decimate-first order with a window the fused
+            # epilogue takes; otherwise the runner writes it and it is simply not read back unless asked for
+            need_filtered = want_filtered or plan.block != 1 or plan.rate // 10 > 65
+            slot = self._slot(n_in, sample_rate, params, pcm.dtype, channels, want_debug, need_filtered, sparse)
             A = slot.runner
             M = A.total_m
             # -- ingest: the kept frames (or the whole recording) -> pinned staging -> device

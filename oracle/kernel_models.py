@@ -208,26 +208,21 @@ def sos_filtfilt_envelope(x_kept: np.ndarray, d: BlockFilterDesign, env_window: 
             if 0 <= j < m:
                 assert np.isnan(y[j])
                 y[j] = tile[SS_TILE - 1 - sl]
-        own_hi = m - 1 if b == 0 else jhi - off
-        own_lo = max(0, jhi - off - part + 1)
-        first = jhi - off - part + 1
-        val = lambda la: abs(tile[la]) if la < SS_TILE else 0.0
-        for t in range(SS_THREADS):
-            jb = first + t * SS_CHUNK
-            if jb + SS_CHUNK - 1 < own_lo or jb > own_hi:
-                continue
-            lb = jb - left - jlo
-            assert lb >= 0
-            s = 0.0
-            for q in range(w):
-                s += val(lb + q)
-            for k in range(SS_CHUNK):
-                j = jb + k
-                if own_lo <= j <= own_hi:
-                    wa, wb = max(0, j - left), min(m - 1, j + off)
-                    assert np.isnan(env[j])
-                    env[j] = s / (wb - wa + 1)
-                s = (s + val(lb + k + w)) - val(lb + k)
+        # envelope of the outputs this tile owns, from an inclusive prefix sum of the staged |y|
+        # (flat beyond the tile): window sum = S[hi] - S[lo - 1]
+        la_min, la_max = max(0, -jlo), min(SS_TILE - 1, m - 1 - jlo)
+        S = np.concatenate([np.cumsum(np.abs(tile)), np.full(SS_HALO + 1, np.sum(np.abs(tile)))])
+        q0 = SS_TILE - part - off
+        own_lo = max(la_min, q0)
+        own_hi = la_max if b == 0 else min(la_max, SS_TILE - 1 - off)
+        for la in range(own_lo, own_hi + 1):
+            lo, hi = la - left, la + off
+            assert lo >= 0
+            total = S[hi] - (S[lo - 1] if lo > 0 else 0.0)
+            cnt = min(la_max, hi) - max(la_min, lo) + 1
+            j = jlo + la
+            assert np.isnan(env[j])
+            env[j] = total * (1.0 / w) if cnt == w else total / cnt
     assert not np.any(np.isnan(y)) and not np.any(np.isnan(env))
     return y, env, float(np.max(np.abs(y)))
 
