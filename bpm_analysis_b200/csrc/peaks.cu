@@ -64,16 +64,25 @@ __device__ __forceinline__ int plateau_test(Val val, int64_t i, int64_t n, doubl
 }
 
 
-// one end of the flat run around p (all samples == c): first index in direction dir that differs
+// one end of the flat run around p (all samples == c): last index in direction dir that still equals c.
+// A warp covers 256 samples per step (8 independent loads per lane): a million-sample run of digital
+// silence is walked in ~4 k steps.
 __device__ int64_t warp_run_edge(const double* __restrict__ xi, int sign, int64_t n, int64_t p, double c, int dir) {
   const int lane = threadIdx.x & 31;
   int64_t e = p;
   while (true) {
-    const int64_t j = e + dir * (1 + lane);
-    const bool eq = (j >= 0 && j <= n - 1) && signed_val(xi[j], sign) == c;
-    const unsigned m = __ballot_sync(0xffffffffu, eq);
-    if (m == 0xffffffffu) { e += dir * 32; continue; }
-    return e + dir * (__ffs(~m) - 1);
+    bool eq[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int64_t j = e + dir * (1 + u * 32 + lane);
+      eq[u] = (j >= 0 && j <= n - 1) && signed_val(xi[j], sign) == c;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const unsigned m = __ballot_sync(0xffffffffu, eq[u]);
+      if (m != 0xffffffffu) return e + dir * (u * 32 + __ffs(~m) - 1);
+    }
+    e += dir * 256;
   }
 }
 

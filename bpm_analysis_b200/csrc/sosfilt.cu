@@ -374,51 +374,28 @@ __global__ void __launch_bounds__(SS_THREADS, OCC) k_sos_scan(const __grid_const
   // tile-local index of output k = 0 of thread 0:  first - jlo  with  first = jhi - off - part + 1
   const int q0 = SS_TILE - a.part - off;                  // >= left  because  w - 1 <= SS_TILE - part
   const double inv_w = 1.0 / static_cast<double>(w);
-  // window sums from an inclusive prefix sum of the staged |y| (block scan: 8 serial adds per thread,
-  // a shuffle scan per warp, one more over the warp totals): S[la] = |y|[0] + .. + |y|[la], so a window
-  // is S[hi] - S[lo - 1].  The partial sums stay below 2048 x max|y|, i.e. the difference carries
-  // ~1e-14 relative error -- five orders of magnitude inside the 1e-9 contract -- and costs two loads
-  // per output instead of re-adding the window.
-  {
-    double run[SS_CHUNK];
-    double acc = 0.0;
-#pragma unroll
-    for (int c = 0; c < SS_CHUNK; ++c) { acc += sm_env[ss_pad(tid * SS_CHUNK + c)]; run[c] = acc; }
-    double inc = acc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double t = shfl_up_f64(inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) sm_tot[warp][0] = inc;
-    __syncthreads();                                       // every thread has read its 8 values; warp totals visible
-    double before = inc - acc;
-    for (int wv = 0; wv < warp; ++wv) before += sm_tot[wv][0];
-#pragma unroll
-    for (int c = 0; c < SS_CHUNK; ++c) sm_env[ss_pad(tid * SS_CHUNK + c)] = before + run[c];
-    if (tid == SS_THREADS - 1) {
-      // indices past the tile (windows of tile 0 reaching beyond the recording): the sum stays flat
-      const double total = before + acc;
-      for (int t = 0; t <= SS_HALO; ++t) sm_env[ss_pad(SS_TILE + t)] = total;
-    }
-  }
-  __syncthreads();
+  // A thread forms its 8 consecutive outputs with a sliding sum that is re-started per thread: the
+  // partial sums never mix magnitudes further apart than 38 samples.  (Window sums as differences of a
+  // tile-wide prefix sum were tried and REJECTED: after a loud passage the differences in a quiet one
+  // -- a dropout decaying to 1e-17 -- are rounding noise of the loud one; the envelope still matched to
+  // 1e-11 of its maximum but the troughs found in the quiet stretch did not.)
   const int own_lo = max(la_min, q0);                     // owned outputs, tile-local, inclusive
   const int own_hi = (blockIdx.x == 0) ? la_max : min(la_max, SS_TILE - 1 - off);
   double e[SS_CHUNK];
   const int qb = q0 + tid * SS_CHUNK;                     // tile-local index of this thread's first output
   const bool any = (qb + SS_CHUNK - 1 >= own_lo) && (qb <= own_hi);
   if (any) {
+    const double* __restrict__ av = sm_env;
+    const int lb = qb - left;                             // first window element of output k = 0
+    double sacc = 0.0;
+    for (int q = 0; q < w; ++q) sacc += av[ss_pad(lb + q)];
 #pragma unroll
     for (int k = 0; k < SS_CHUNK; ++k) {
       const int la = qb + k;
-      const int lo = la - left, hi = la + off;             // lo >= 0; hi may reach into the flat tail
-      const double s_hi = sm_env[ss_pad(hi)];
-      const double s_lo = (lo > 0) ? sm_env[ss_pad(lo - 1)] : 0.0;
-      const int wa = max(la_min, lo), wb2 = min(la_max, hi);
+      const int wa = max(la_min, la - left), wb2 = min(la_max, la + off);
       const int cnt = wb2 - wa + 1;
-      const double sum = s_hi - s_lo;
-      e[k] = (cnt == w) ? sum * inv_w : __ddiv_rn(sum, static_cast<double>(cnt));
+      e[k] = (cnt == w) ? sacc * inv_w : __ddiv_rn(sacc, static_cast<double>(cnt));
+      sacc = (sacc + av[ss_pad(lb + k + w)]) - av[ss_pad(lb + k)];
     }
   }
   __syncthreads();                                        // all windows are read: the sums can be overwritten

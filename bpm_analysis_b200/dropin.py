@@ -27,7 +27,9 @@ bookkeeps.  No CPU fallback: without the libraries or a CUDA device these raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
+import time
 import weakref
 from collections import OrderedDict
 from typing import Dict, Optional, Tuple
@@ -43,6 +45,22 @@ from .params import output_dtype
 MAX_SESSIONS = 8
 MAX_RUNNERS = 4
 HOST_GATHER_MIN_PITCH_BYTES = 32      # below this the whole recording is copied (every cache line is touched anyway)
+
+
+TRACE = os.environ.get("BPM_DROPIN_TRACE", "0") == "1"
+
+
+class _Trace:
+    """Optional host-clock breakdown of the calls (BPM_DROPIN_TRACE=1): name -> accumulated seconds."""
+
+    def __init__(self, sink: Dict[str, float]):
+        self.sink, self.t = sink, time.perf_counter()
+
+    def mark(self, name: str) -> None:
+        if TRACE:
+            now = time.perf_counter()
+            self.sink[name] = self.sink.get(name, 0.0) + (now - self.t)
+            self.t = now
 
 
 def _key(a: np.ndarray) -> Tuple[int, int, str]:
@@ -104,6 +122,8 @@ class _StageARunnerSlot:
         self.stage = _pinned(n_stage, rt._torch_dtype(np_dtype))
         self.cap = min(A.total_m, A.total_m // max(int(A.cfg.distance), 1) + 2)    # find_peaks distance bounds the lists
         self.f32 = None                               # float32 copies of the signals, allocated on first use
+        self.uses = 0
+        self.graph = None                             # CUDA graph of the stage-A launches, captured on the second use
 
 
 def _cfg2(params: Dict, rate: int) -> tuple:
@@ -141,6 +161,7 @@ class DropIn:
         self.series_watch: "OrderedDict[tuple, tuple]" = OrderedDict()
         self.stream = torch.cuda.Stream()
         self.stats = {"session_hits": 0, "session_misses": 0, "stage_a_calls": 0, "beat_hits": 0, "beat_misses": 0}
+        self.trace: Dict[str, float] = {}
 
     def forget(self) -> None:
         """Drop every session and cached result (the preallocated runner buffers stay)."""
@@ -234,9 +255,11 @@ class DropIn:
             # the band-passed signal only stays out of HBM in the decimate-first order with a window the fused
             # epilogue takes; otherwise the runner writes it and it is simply not read back unless asked for
             need_filtered = want_filtered or plan.block != 1 or plan.rate // 10 > 65
+            tr = _Trace(self.trace)
             slot = self._slot(n_in, sample_rate, params, pcm.dtype, channels, want_debug, need_filtered, sparse)
             A = slot.runner
             M = A.total_m
+            tr.mark("pre.plan+slot")
             # -- ingest: the kept frames (or the whole recording) -> pinned staging -> device
             if sparse:
                 rc = self.host.bpm_host_gather_frames(C.c_void_p(pcm.ctypes.data), frame_bytes, n_in, plan.stride,
@@ -245,20 +268,27 @@ class DropIn:
                     raise RuntimeError(f"bpm_host_gather_frames failed ({rc})")
             else:
                 np.copyto(slot.stage.numpy(), pcm.reshape(-1))
-            out = {"envelope": _pinned(M, sig_dtype), "floor": _pinned(M, sig_dtype),
-                   "counts": _pinned(4, torch.int64)}
-            lists = {k: _pinned(slot.cap, torch.int64 if k in ("troughs", "peaks") else sig_dtype)
-                     for k in ("troughs", "peaks", "strength", "deviation", "smoothed_dev")}
-            extra = {}
-            if want_filtered:
-                extra["filtered"] = _pinned(M, sig_dtype)
-            if want_debug:
-                extra["debug_wav"] = _pinned(M, torch.int16)
+            tr.mark("pre.host_gather")
             ev_env, ev_all = torch.cuda.Event(), torch.cuda.Event()
             with torch.cuda.stream(self.stream):
                 A.ingest(slot.stage)
-                A.launch()
+                if slot.graph is not None:
+                    slot.graph.replay()
+                else:
+                    A.launch()
                 self.stats["stage_a_calls"] += 1
+                tr.mark("pre.enqueue_stage_a")
+                # result buffers are allocated while the device is already working
+                out = {"envelope": _pinned(M, sig_dtype), "floor": _pinned(M, sig_dtype),
+                       "counts": _pinned(4, torch.int64)}
+                lists = {k: _pinned(slot.cap, torch.int64 if k in ("troughs", "peaks") else sig_dtype)
+                         for k in ("troughs", "peaks", "strength", "deviation", "smoothed_dev")}
+                extra = {}
+                if want_filtered:
+                    extra["filtered"] = _pinned(M, sig_dtype)
+                if want_debug:
+                    extra["debug_wav"] = _pinned(M, torch.int16)
+                tr.mark("pre.alloc_results")
                 src = A.out if not f32 else self._cast_outputs(slot, M, want_filtered)
                 out["envelope"].copy_(src["envelope"][:M], non_blocking=True)
                 for k, h in extra.items():
@@ -272,13 +302,26 @@ class DropIn:
                 for k, h in lists.items():
                     h.copy_(src[k][:slot.cap], non_blocking=True)
                 ev_all.record(self.stream)
+            tr.mark("pre.enqueue_readback")
             ev_env.synchronize()
+            tr.mark("pre.wait_envelope")
             env = out["envelope"].numpy()[:M]
             s = Session(env, plan.rate)
             s.pending = (ev_all, out, lists, _cfg2(params, plan.rate), _cfg3(params, plan.rate))
             self._remember(s)
             filt = extra["filtered"].numpy()[:M] if want_filtered else None
             dbg = extra["debug_wav"].numpy()[:M] if want_debug else None
+            # a recording shape seen twice gets its stage-A launches captured into a CUDA graph: the next call
+            # replays it (one driver call instead of ~30 launches)
+            slot.uses += 1
+            if slot.uses == 2 and slot.graph is None and not f32 and os.environ.get("BPM_DROPIN_GRAPH", "1") != "0":
+                self.stream.synchronize()
+                with torch.cuda.stream(self.stream):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=self.stream):
+                        A.launch()
+                slot.graph = g
+            tr.mark("pre.session")
             return env, plan.rate, filt, dbg
 
     def _cast_outputs(self, slot: "_StageARunnerSlot", M: int, want_filtered: bool) -> Dict[str, torch.Tensor]:

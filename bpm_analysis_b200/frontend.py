@@ -174,7 +174,7 @@ def _initialize_state(self, start_bpm_hint, precomputed_noise_floor, precomputed
     state["analysis_data"]["dynamic_noise_floor_series"] = state["dynamic_noise_floor"]
     state["analysis_data"]["trough_indices"] = state["trough_indices"]
     deviation_times = (peaks[:-1] + peaks[1:]) / 2 / self.sample_rate
-    state["smoothed_dev_series"] = pd.Series(met["smoothed"], index=deviation_times)
+    state["smoothed_dev_series"] = pd.Series(met["smoothed"].copy(), index=pd.Index(deviation_times, copy=False), copy=False)
     state["analysis_data"]["deviation_series"] = state["smoothed_dev_series"]
     state["long_term_bpm"] = float(start_bpm_hint) if start_bpm_hint else 80.0
     state["candidate_beats"] = []
@@ -257,7 +257,7 @@ def calculate_bpm_series(peaks: np.ndarray, sample_rate: int, params: Dict) -> T
     if not (np.median(inst) > 0):
         return pd.Series(dtype=np.float64), times.copy()
     index = pd.DatetimeIndex((us + _epoch_us()).astype("datetime64[us]"))
-    series = pd.Series(smoothed.copy(), index=index)
+    series = pd.Series(smoothed.copy(), index=index, copy=False)
     _series_results[_series_key(series)] = res
     while len(_series_results) > 16:
         _series_results.popitem(last=False)

@@ -587,58 +587,58 @@ def hr_extrema_distance(beats: np.ndarray, rate: int, min_duration_sec: float = 
 
 
 def beat_chain(owner, beats: np.ndarray, rate: int, window_us: int, win: int, step: int) -> Dict[str, object]:
-    """a5..a8 of one beat list in one device round trip (see dropin.DropIn.beat_metrics)."""
+    """a5..a8 of one beat list in one device round trip (see dropin.DropIn.beat_metrics): ONE upload
+    (beat list + the two list descriptors in one pinned block), the kernels, TWO read-backs (one
+    float64 block, one int64 block), one synchronisation."""
     lib, dev, stream = owner.lib, owner.device, owner.stream
     b = int(beats.size)
     res: Dict[str, object] = {"n_beats": b}
     if b < 2:
         return res
     dist = hr_extrema_distance(beats, rate)
-    items = make_items([b], [b])
     tsec = beats / rate
     n_series = int(np.count_nonzero(np.diff(tsec) > 1e-6))          # == n_valid the device will report (:1468)
     res["n_series"] = n_series
     if n_series == 0:
         return res
-    sitems = make_items([n_series], [n_series])
-    stage = torch.empty(b, dtype=torch.int64, pin_memory=True)
-    stage.numpy()[:] = beats
-    f64 = dict(dtype=torch.float64, device=dev)
-    i64 = dict(dtype=torch.int64, device=dev)
+    items, sitems = make_items([b], [b]), make_items([n_series], [n_series])
+    # int64 block on both sides: [list descriptor 4 | series descriptor 4 | beats b | stamps b | tops b | bottoms b | scalars 4]
+    n_i = 8 + 4 * b + 4
+    stage = torch.empty(8 + b, dtype=torch.int64, pin_memory=True)
+    sn = stage.numpy()
+    sn[0:4] = items.view(np.int64).reshape(-1)
+    sn[4:8] = sitems.view(np.int64).reshape(-1)
+    sn[8:] = beats
     with torch.cuda.stream(stream):
         st = stream.cuda_stream
-        both = np.concatenate([items.view(np.int64).reshape(-1, 4), sitems.view(np.int64).reshape(-1, 4)])
-        desc = torch.from_numpy(both).to(dev, non_blocking=True)
-        items_dev, sitems_dev = desc[0:1], desc[1:2]
-        bd = torch.empty(b, **i64)
-        bd.copy_(stage, non_blocking=True)
-        # one float64 block [inst | smoothed | times | hrv(4b) | slopes(8)] and one int64 block
-        # [stamps | tops | bottoms | n_valid n_tops n_bottoms hrv_rows]: two read-backs in all
-        fblk = torch.empty(7 * b + 8, **f64)
-        iblk = torch.empty(3 * b + 4, **i64)
-        inst, smooth, times, hrv, slopes = fblk[:b], fblk[b:2 * b], fblk[2 * b:3 * b], fblk[3 * b:7 * b], fblk[7 * b:]
-        stamps, tops, bottoms, scal = iblk[:b], iblk[b:2 * b], iblk[2 * b:3 * b], iblk[3 * b:]
-        nat.check(lib.bpm_bpm_series(_ptr(bd), _ptr(items_dev), _host_ptr(items), 1, rate, window_us, _ptr(inst),
-                                     _ptr(smooth), _ptr(times), _ptr(stamps), C.c_void_p(scal.data_ptr()), st))
+        iblk = torch.empty(n_i, dtype=torch.int64, device=dev)
+        fblk = torch.empty(7 * b + 8 + 1, dtype=torch.float64, device=dev)    # [inst | smoothed | times | hrv 4b | slopes 8 | prominence]
+        iblk[:8 + b].copy_(stage, non_blocking=True)
+        ip, fp = iblk.data_ptr(), fblk.data_ptr()
+        P = lambda base, off: C.c_void_p(base + 8 * off)                      # noqa: E731 - element offset -> pointer
+        items_dev, sitems_dev, bd = P(ip, 0), P(ip, 4), P(ip, 8)
+        stamps, tops, bottoms, scal = P(ip, 8 + b), P(ip, 8 + 2 * b), P(ip, 8 + 3 * b), 8 + 4 * b
+        inst, smooth, times, hrv, slopes, prom = P(fp, 0), P(fp, b), P(fp, 2 * b), P(fp, 3 * b), P(fp, 7 * b), P(fp, 7 * b + 8)
+        nat.check(lib.bpm_bpm_series(bd, items_dev, _host_ptr(items), 1, rate, window_us, inst, smooth, times, stamps,
+                                     P(ip, scal), st))
         # the series holds the valid intervals only (dt > 1e-6 s): its length was counted on the host
         # with the same arithmetic, so the follow-up kernels get an exact descriptor
-        ws = torch.empty(max(int(lib.bpm_find_peaks_workspace_bytes(b, 1)), 256), dtype=torch.uint8, device=dev)
-        nat.check(lib.bpm_steepest_slope(_ptr(smooth), _ptr(stamps), C.c_void_p(scal.data_ptr()), _ptr(sitems_dev),
-                                         _host_ptr(sitems), 1, 0, 20.0, _ptr(slopes), _ptr(ws), ws.numel(), st))
+        ws_bytes = max(int(lib.bpm_find_peaks_workspace_bytes(b, 1)), 256)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        nat.check(lib.bpm_steepest_slope(smooth, stamps, P(ip, scal), sitems_dev, _host_ptr(sitems), 1, 0, 20.0, slopes,
+                                         _ptr(ws), ws_bytes, st))
         res["hr_distance"] = dist
         if dist >= 1:
-            prom = torch.full((1,), 5.0, **f64)
+            fblk[7 * b + 8:].fill_(5.0)
             for sign, idx, k in ((+1, tops, 1), (-1, bottoms, 2)):
-                nat.check(lib.bpm_find_peaks(_ptr(smooth), sign, None, _ptr(prom), dist, _ptr(sitems_dev),
-                                             _host_ptr(sitems), 1, _ptr(idx), C.c_void_p(scal.data_ptr() + 8 * k),
-                                             _ptr(ws), ws.numel(), st))
+                nat.check(lib.bpm_find_peaks(smooth, sign, None, prom, dist, sitems_dev, _host_ptr(sitems), 1, idx,
+                                             P(ip, scal + k), _ptr(ws), ws_bytes, st))
         if b >= win:
-            nat.check(lib.bpm_windowed_hrv(_ptr(bd), _ptr(items_dev), _host_ptr(items), 1, rate, win, step, _ptr(hrv),
-                                           C.c_void_p(scal.data_ptr() + 24), st))
-        fh = torch.empty(fblk.numel(), dtype=torch.float64, pin_memory=True)
-        ih = torch.empty(iblk.numel(), dtype=torch.int64, pin_memory=True)
-        fh.copy_(fblk, non_blocking=True)
-        ih.copy_(iblk, non_blocking=True)
+            nat.check(lib.bpm_windowed_hrv(bd, items_dev, _host_ptr(items), 1, rate, win, step, hrv, P(ip, scal + 3), st))
+        fh = torch.empty(7 * b + 8, dtype=torch.float64, pin_memory=True)
+        ih = torch.empty(3 * b + 4, dtype=torch.int64, pin_memory=True)
+        fh.copy_(fblk[:7 * b + 8], non_blocking=True)
+        ih.copy_(iblk[8 + b:], non_blocking=True)
     stream.synchronize()
     f, i = fh.numpy(), ih.numpy()
     nv = int(i[3 * b])

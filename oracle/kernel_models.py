@@ -208,21 +208,30 @@ def sos_filtfilt_envelope(x_kept: np.ndarray, d: BlockFilterDesign, env_window: 
             if 0 <= j < m:
                 assert np.isnan(y[j])
                 y[j] = tile[SS_TILE - 1 - sl]
-        # envelope of the outputs this tile owns, from an inclusive prefix sum of the staged |y|
-        # (flat beyond the tile): window sum = S[hi] - S[lo - 1]
+        # envelope of the outputs this tile owns: per thread a sliding sum over the staged |y| (zeros
+        # outside the recording and beyond the tile), restarted every SS_CHUNK outputs
         la_min, la_max = max(0, -jlo), min(SS_TILE - 1, m - 1 - jlo)
-        S = np.concatenate([np.cumsum(np.abs(tile)), np.full(SS_HALO + 1, np.sum(np.abs(tile)))])
+        av = np.concatenate([np.abs(tile), np.zeros(SS_HALO + 1)])
         q0 = SS_TILE - part - off
         own_lo = max(la_min, q0)
         own_hi = la_max if b == 0 else min(la_max, SS_TILE - 1 - off)
-        for la in range(own_lo, own_hi + 1):
-            lo, hi = la - left, la + off
-            assert lo >= 0
-            total = S[hi] - (S[lo - 1] if lo > 0 else 0.0)
-            cnt = min(la_max, hi) - max(la_min, lo) + 1
-            j = jlo + la
-            assert np.isnan(env[j])
-            env[j] = total * (1.0 / w) if cnt == w else total / cnt
+        for t in range(SS_THREADS):
+            qb = q0 + t * SS_CHUNK
+            if qb + SS_CHUNK - 1 < own_lo or qb > own_hi:
+                continue
+            lb = qb - left
+            assert lb >= 0
+            s = 0.0
+            for q in range(w):
+                s += av[lb + q]
+            for k in range(SS_CHUNK):
+                la = qb + k
+                cnt = min(la_max, la + off) - max(la_min, la - left) + 1
+                if own_lo <= la <= own_hi:
+                    j = jlo + la
+                    assert np.isnan(env[j])
+                    env[j] = s * (1.0 / w) if cnt == w else s / cnt
+                s = (s + av[lb + k + w]) - av[lb + k]
     assert not np.any(np.isnan(y)) and not np.any(np.isnan(env))
     return y, env, float(np.max(np.abs(y)))
 

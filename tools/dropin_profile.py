@@ -12,6 +12,7 @@ import time
 
 import numpy as np
 
+os.environ.setdefault("BPM_DROPIN_TRACE", "1")
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 
@@ -88,6 +89,7 @@ def main():
     out["host_gather_alone_ms"] = round((time.perf_counter() - t0) / reps * 1e3, 4)
     out["host_threads"] = int(lib.bpm_host_threads())
     out["cpu_count"] = os.cpu_count()
+    out["trace_ms_per_step"] = {k: round(v / (reps + 3) * 1e3, 4) for k, v in svc.trace.items()}
     print(json.dumps(out, indent=1))
 
 
