@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libbpm_b200.so")
-SOURCES = ["filter.cu", "sosfilt.cu", "contract.cu", "select.cu", "peaks.cu", "floor.cu", "metrics.cu", "pipeline.cu"]
+SOURCES = ["filter.cu", "sosfilt.cu", "contract.cu", "select.cu", "peaks.cu", "floor.cu", "metrics.cu", "shard.cu", "pipeline.cu"]
 OBJ_DIR = os.path.join(CSRC, "_obj")            # git-ignored (*.o)
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]

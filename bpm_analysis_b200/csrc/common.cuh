@@ -178,6 +178,13 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* smem
   return res;
 }
 
+// A recording that is one TIME CHUNK of a longer stream (see peaks.cu)
+struct ChunkInfo {
+  int64_t core_lo, core_hi;
+  int open_left, open_right;
+  unsigned long long* edge_hits;     // device counter, nullptr: not a chunk
+};
+
 // ------------------------------------------------------------- single-pass ordered compaction
 // Decoupled look-back over per-tile counts: a tile publishes (status | count) as ONE 64-bit word
 // -- status 1: this tile's own count, status 2: inclusive prefix up to and including this tile --

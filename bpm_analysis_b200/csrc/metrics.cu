@@ -143,6 +143,9 @@ __global__ void __launch_bounds__(256) k_dev_smooth_direct(const double* __restr
   }
 }
 
+int deviation_series_run(const double* strength, const int64_t* peak_count, const BpmItem* items, const BatchShape& sh,
+                         double factor, double* deviation, double* smoothed, cudaStream_t st);
+
 int peak_metrics_run(const double* env, const double* floor_, const int64_t* peaks, const int64_t* peak_count,
                      const BpmItem* items, const BatchShape& sh, double factor, double* strength,
                      double* deviation, double* smoothed, cudaStream_t st) {
@@ -155,6 +158,18 @@ int peak_metrics_run(const double* env, const double* floor_, const int64_t* pea
   BPM_KERNEL(k_peak_strength);
   k_peak_strength<<<grid, 256, 0, st>>>(env, floor_, peaks, peak_count, items, strength);
   BPM_LAUNCH_OK();
+  return deviation_series_run(strength, peak_count, items, sh, factor, deviation, smoothed, st);
+}
+
+// deviation[k] and its centred rolling mean from a given strength list (:96-100); `deviation` needs
+// room for 2 P values per recording when the prefix-sum path is taken (see k_dev_prefix)
+int deviation_series_run(const double* strength, const int64_t* peak_count, const BpmItem* items, const BatchShape& sh,
+                         double factor, double* deviation, double* smoothed, cudaStream_t st) {
+  if (!strength || !peak_count || !items || !deviation || !smoothed) return BPM_ERR_ARG;
+  int64_t gx = (sh.max_m / 2 + 2 + 255) / 256;
+  const int64_t cap = (148 * 4 + sh.n_items - 1) / sh.n_items;
+  if (gx > cap) gx = cap;
+  const dim3 grid(static_cast<unsigned>(gx < 1 ? 1 : gx), sh.n_items);
   BPM_KERNEL(k_peak_deviation);
   k_peak_deviation<<<grid, 256, 0, st>>>(strength, peak_count, items, deviation);
   BPM_LAUNCH_OK();

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(PK_THREADS) k_localmax_compact(const double* _
                                                                  unsigned long long* __restrict__ status,
                                                                  int64_t status_stride,
                                                                  int64_t* __restrict__ cand,
-                                                                 int64_t* __restrict__ cand_count) {
+                                                                 int64_t* __restrict__ cand_count, ChunkInfo ci) {
   __shared__ double xs[PK_TILE + 2 + (PK_TILE + 2) / 8 + 1];     // samples i0 - 1 .. i0 + PK_TILE
   __shared__ unsigned char s_mask[PK_THREADS], s_deep[PK_THREADS];
   __shared__ int s_scan[34];
@@ -108,6 +108,18 @@ __global__ void __launch_bounds__(PK_THREADS) k_localmax_compact(const double* _
   if (n == 0) { if (threadIdx.x == 0) cand_count[item] = 0; return; }
   const double* __restrict__ xi = x + it.m_off;
   const int tid = threadIdx.x;
+  if (ci.edge_hits != nullptr && tid < 32 && n >= 2) {
+    // a flat run that starts at an artificial end of a time chunk and reaches its core hides where the
+    // run really begins: plateau midpoints there cannot be decided inside the chunk
+    if (blockIdx.x == 0 && ci.open_left) {
+      const int64_t R = warp_run_edge(xi, sign, n, 0, signed_val(xi[0], sign), +1);
+      if (tid == 0 && R + 1 >= ci.core_lo) atomicAdd(ci.edge_hits, 1ull);
+    }
+    if (i0 + PK_TILE >= n && ci.open_right) {
+      const int64_t L = warp_run_edge(xi, sign, n, n - 1, signed_val(xi[n - 1], sign), -1);
+      if (tid == 0 && L - 1 < ci.core_hi) atomicAdd(ci.edge_hits, 1ull);
+    }
+  }
   for (int e = tid; e < PK_TILE + 2; e += PK_THREADS) {
     const int64_t i = i0 - 1 + e;
     xs[pk_pad(e)] = (i >= 0 && i < n) ? signed_val(xi[i], sign) : 0.0;
@@ -185,6 +197,12 @@ __device__ unsigned long long g_dbg_pk[16];
 #define PKD_MAX(i, v)
 #endif
 
+// A recording that is one TIME CHUNK of a longer stream (bpm_analysis_b200/stream.py): its ends may be
+// artificial.  Decisions for peaks inside [core_lo, core_hi) are final only if no dependency reached
+// an open end; every case where that cannot be proven is counted in *edge_hits (the caller then
+// falls back to the unchunked evaluation): candidates the distance tiles left to the global finish
+// (all other chains are at most DT_DEPTH hops of < d samples long, far inside the halo) and prominence
+// walks of core peaks that stopped at an open end.  Single-recording calls only.
 // ------------------------------------------------------------------ distance
 constexpr int DT_THREADS = 128;
 constexpr int DT_OWN = 512;                       // candidates a CTA settles per tile
@@ -212,7 +230,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __r
                                                                const int64_t* __restrict__ cand_count, int distance,
                                                                unsigned char* __restrict__ state,
                                                                int* __restrict__ pending,
-                                                               unsigned int* __restrict__ ticket) {
+                                                               unsigned int* __restrict__ ticket, ChunkInfo ci) {
   __shared__ int s_pos[DT_STAGE];
   __shared__ double s_val[DT_STAGE];
   __shared__ unsigned char s_st[DT_STAGE];        // 0 open, 1 kept, 2 removed, 3 cannot be settled in this tile
@@ -391,6 +409,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __r
   __threadfence();
   if (tid == 0) PKD_ADD(5, nc);
   if (atomicAdd(pending + item, 0) == 0) return;
+  if (tid == 0 && ci.edge_hits != nullptr) atomicAdd(ci.edge_hits, 1ull);   // a chain longer than the tiles follow
   volatile unsigned char* stt = st_out;
   while (true) {
     int changed = 0;
@@ -425,8 +444,10 @@ __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __r
 // Warp-cooperative, both sides walked together 32 samples at a time: a side passes as soon as
 // a sample low enough (x[p] - x[i] >= thr) is met before the walk would stop (a sample above
 // the peak, or the end of the signal); it fails when the walk stops first.
+// *edge (optional): set to 1 / 2 when the decision was "walk stopped at the left / right END of the
+// array" -- for a time chunk of a longer stream that end is artificial and the decision is not final.
 template <class Val>
-__device__ __forceinline__ bool warp_prominence_ok(Val val, int64_t n, int64_t p, double thr) {
+__device__ __forceinline__ bool warp_prominence_ok(Val val, int64_t n, int64_t p, double thr, int* edge = nullptr) {
   const int lane = threadIdx.x & 31;
   const double xp = val(p);
   if (__dsub_rn(xp, xp) >= thr) return true;            // the peak itself is the running minimum
@@ -443,8 +464,10 @@ __device__ __forceinline__ bool warp_prominence_ok(Val val, int64_t n, int64_t p
       const unsigned bs = __ballot_sync(0xffffffffu, stop), bp = __ballot_sync(0xffffffffu, pass);
       const int fs = bs ? __ffs(bs) : 33, fp = bp ? __ffs(bp) : 33;
       if (fp < fs) done_l = 1;
-      else if (bs) return false;
-      else bl -= 32;
+      else if (bs) {
+        if (edge != nullptr && bl - (fs - 1) < 0) *edge = 1;      // the stopping lane ran off the left end
+        return false;
+      } else bl -= 32;
     }
     if (!done_r) {
       const bool stop = !vr || (xr > xp);
@@ -452,8 +475,10 @@ __device__ __forceinline__ bool warp_prominence_ok(Val val, int64_t n, int64_t p
       const unsigned bs = __ballot_sync(0xffffffffu, stop), bp = __ballot_sync(0xffffffffu, pass);
       const int fs = bs ? __ffs(bs) : 33, fp = bp ? __ffs(bp) : 33;
       if (fp < fs) done_r = 1;
-      else if (bs) return false;
-      else br += 32;
+      else if (bs) {
+        if (edge != nullptr && br + (fs - 1) >= n) *edge = 2;     // ... off the right end
+        return false;
+      } else br += 32;
     }
     if (done_l && done_r) return true;
   }
@@ -470,7 +495,7 @@ __global__ void __launch_bounds__(PC_THREADS) k_prominence_compact(const double*
                                                                    unsigned long long* __restrict__ status,
                                                                    int64_t status_stride,
                                                                    int64_t* __restrict__ out_idx,
-                                                                   int64_t* __restrict__ out_count) {
+                                                                   int64_t* __restrict__ out_count, ChunkInfo ci) {
   __shared__ int s_scan[34];
   __shared__ long long s_off;
   const int item = blockIdx.y;
@@ -499,8 +524,14 @@ __global__ void __launch_bounds__(PC_THREADS) k_prominence_compact(const double*
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
       const int64_t ps = __shfl_sync(0xffffffffu, p, src);
-      const bool ok = warp_prominence_ok(val, it.m, ps, thr);
-      if (lane == src) live = ok;
+      int edge = 0;
+      const bool ok = warp_prominence_ok(val, it.m, ps, thr, ci.edge_hits ? &edge : nullptr);
+      if (lane == src) {
+        live = ok;
+        if (edge != 0 && ps >= ci.core_lo && ps < ci.core_hi &&
+            ((edge == 1 && ci.open_left) || (edge == 2 && ci.open_right)))
+          atomicAdd(ci.edge_hits, 1ull);
+      }
     }
   }
   int total;
@@ -556,14 +587,16 @@ size_t find_peaks_workspace_bytes(int64_t total_m, int n_items) {
 // another stream while the local-maximum / distance steps run here); nullptr = already valid.
 int find_peaks_run(const double* x, int sign, const double* height, const double* prominence, int distance,
                    const BpmItem* items, const BatchShape& sh, int64_t* out_idx, int64_t* out_count,
-                   Workspace& ws, cudaStream_t st, cudaEvent_t prominence_ready) {
+                   Workspace& ws, cudaStream_t st, cudaEvent_t prominence_ready, const ChunkInfo* chunk) {
   if (!x || !items || !out_idx || !out_count || sh.n_items <= 0 || distance < 1) return BPM_ERR_ARG;
+  if (chunk != nullptr && sh.n_items != 1) return BPM_ERR_ARG;
+  const ChunkInfo ci = chunk ? *chunk : ChunkInfo{0, 0, 0, 0, nullptr};
   PeakBuffers b;
   BPM_TRY(carve_peaks(ws, sh.total_m, sh.max_m, sh.n_items, &b));
   if (cudaMemsetAsync(b.status_a, 0, b.zero_bytes, st) != cudaSuccess) return BPM_ERR_CUDA;
   BPM_KERNEL(k_localmax_compact);
   k_localmax_compact<<<dim3(cdiv(sh.max_m > 0 ? sh.max_m : 1, PK_TILE), sh.n_items), PK_THREADS, 0, st>>>(
-      x, sign, height, items, b.status_a, b.stride_a, b.cand, b.cand_count);
+      x, sign, height, items, b.status_a, b.stride_a, b.cand, b.cand_count, ci);
   BPM_LAUNCH_OK();
   // a local maximum needs a lower neighbour on both sides: at most (m - 1) / 2 candidates
   const int64_t max_c = sh.max_m / 2 + 1;
@@ -574,13 +607,13 @@ int find_peaks_run(const double* x, int sign, const double* height, const double
     if (gx < 1) gx = 1;
     BPM_KERNEL(k_distance_tiles);
     k_distance_tiles<<<dim3(static_cast<unsigned>(gx), sh.n_items), DT_THREADS, 0, st>>>(
-        x, sign, items, b.cand, b.cand_count, distance, b.cstate, b.pending, b.ticket);
+        x, sign, items, b.cand, b.cand_count, distance, b.cstate, b.pending, b.ticket, ci);
     BPM_LAUNCH_OK();
   }
   if (prominence_ready && cudaStreamWaitEvent(st, prominence_ready, 0) != cudaSuccess) return BPM_ERR_CUDA;
   BPM_KERNEL(k_prominence_compact);
   k_prominence_compact<<<dim3(cdiv(max_c, PC_THREADS), sh.n_items), PC_THREADS, 0, st>>>(
-      x, sign, items, b.cand, b.cand_count, b.cstate, prominence, b.status_c, b.stride_c, out_idx, out_count);
+      x, sign, items, b.cand, b.cand_count, b.cstate, prominence, b.status_c, b.stride_c, out_idx, out_count, ci);
   BPM_LAUNCH_OK();
   return BPM_OK;
 }

@@ -27,7 +27,8 @@ int quantile_multi_run(const double* x, const BpmItem* items, const BatchShape& 
 size_t find_peaks_workspace_bytes(int64_t total_m, int n_items);
 int find_peaks_run(const double* x, int sign, const double* height, const double* prominence, int distance,
                    const BpmItem* items, const BatchShape& sh, int64_t* out_idx, int64_t* out_count,
-                   Workspace& ws, cudaStream_t st, cudaEvent_t prominence_ready = nullptr);
+                   Workspace& ws, cudaStream_t st, cudaEvent_t prominence_ready = nullptr,
+                   const ChunkInfo* chunk = nullptr);
 // floor.cu
 size_t rolling_floor_workspace_bytes(int64_t total_m, int n_items);
 bool rolling_floor_sparse_ok(int window);
@@ -54,6 +55,8 @@ int bpm_series_run(const int64_t* beats, const BpmItem* lists, const BatchShape&
 int steepest_run(const double* smoothed, const int64_t* stamp_us, const int64_t* n_valid, const BpmItem* lists,
                  int n_lists, int64_t max_len, int sign, double window_sec, double* result, cudaStream_t st);
 int cast_f32_run(const double* src, float* dst, int64_t n, cudaStream_t st);
+int deviation_series_run(const double* strength, const int64_t* peak_count, const BpmItem* items, const BatchShape& sh,
+                         double factor, double* deviation, double* smoothed, cudaStream_t st);
 int hrv_run(const int64_t* beats, const BpmItem* lists, const BatchShape& sh, int rate, int win, int step,
             double* out, int64_t* rows, cudaStream_t st);
 
@@ -166,6 +169,44 @@ int noise_floor_run(const double* env, const BpmItem* items, const BatchShape& s
     Workspace w = sub_ws(ws, 0);
     BPM_TRY(rolling_floor_run(env, troughs_out, trough_count, items, sh, window, floor_q, s.n_all, trough_count,
                               s.all_troughs, s.n_all, s.q_nf, q_fb, total_out, mode_out, floor_out, nullptr, w, st));
+  }
+  return BPM_OK;
+}
+
+// ------------------------------------------------------------------ a2 on one time chunk of a longer stream
+// The stream-wide prominence threshold is GIVEN (it is an order statistic of the whole envelope), and
+// the count-based fall-backs of the reference (<5 troughs, <=2 kept, all-NaN) are NOT applied here:
+// they are decisions on the stream's totals, which the caller takes after gathering the counts.
+int noise_floor_chunk_run(const double* env, const BpmItem* items, const BatchShape& sh, int distance,
+                          const double* q_tp, double floor_q, int window, double mult, const ChunkInfo& ci,
+                          double* floor_out, int64_t* troughs_out, int64_t* trough_count, int64_t* all_troughs_out,
+                          int64_t* all_count, Workspace& ws, cudaStream_t st) {
+  if (!env || !items || !q_tp || !floor_out || !troughs_out || !trough_count || !all_troughs_out || !all_count)
+    return BPM_ERR_ARG;
+  if (distance < 1 || window < MIN_PERIODS || sh.n_items != 1) return BPM_ERR_ARG;
+  double* draft = ws.take<double>(sh.total_m);
+  const size_t zb = sanitize_workspace_bytes(sh.total_m, 1);
+  char* sanitize_ws = ws.take<char>(zb);
+  if (ws.overflow) return BPM_ERR_WORKSPACE;
+  {
+    Workspace w = sub_ws(ws, 0);
+    BPM_TRY(find_peaks_run(env, -1, nullptr, q_tp, distance, items, sh, all_troughs_out, all_count, w, st, nullptr, &ci));
+  }
+  const bool sparse = rolling_floor_sparse_ok(window);
+  {
+    Workspace w = sub_ws(ws, 0);
+    BPM_TRY(rolling_floor_run(env, all_troughs_out, all_count, items, sh, window, floor_q, nullptr, nullptr, nullptr, nullptr,
+                              nullptr, nullptr, nullptr, nullptr, sparse ? nullptr : draft, sparse ? draft : nullptr, w, st));
+  }
+  {
+    Workspace wz(sanitize_ws, zb);
+    BPM_TRY(sanitize_run(env, draft, all_troughs_out, all_count, 0, items, sh, mult, sparse ? 1 : 0, troughs_out,
+                         trough_count, wz, st));
+  }
+  {
+    Workspace w = sub_ws(ws, 0);
+    BPM_TRY(rolling_floor_run(env, troughs_out, trough_count, items, sh, window, floor_q, nullptr, nullptr, nullptr, nullptr,
+                              nullptr, nullptr, nullptr, nullptr, floor_out, nullptr, w, st));
   }
   return BPM_OK;
 }
@@ -445,6 +486,42 @@ int bpm_windowed_hrv(const int64_t* beats, const BpmItem* lists, const BpmItem* 
   if (!lists_host || n_lists <= 0) return BPM_ERR_ARG;
   return hrv_run(beats, lists, batch_shape(lists_host, n_lists), rate, window_beats, step_beats, out, rows,
                  static_cast<cudaStream_t>(stream));
+}
+
+int bpm_find_peaks_chunk(const double* x, int sign, const double* height, const double* prominence, int distance,
+                         const BpmItem* items, const BpmItem* items_host, int64_t core_lo, int64_t core_hi,
+                         int open_left, int open_right, int64_t* out_idx, int64_t* out_count, uint64_t* edge_hits,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (!workspace || !items_host || !edge_hits || (sign != 1 && sign != -1)) return BPM_ERR_ARG;
+  Workspace ws(workspace, workspace_bytes);
+  const ChunkInfo ci{core_lo, core_hi, open_left, open_right, reinterpret_cast<unsigned long long*>(edge_hits)};
+  return find_peaks_run(x, sign, height, prominence, distance, items, batch_shape(items_host, 1), out_idx, out_count,
+                        ws, static_cast<cudaStream_t>(stream), nullptr, &ci);
+}
+
+size_t bpm_noise_floor_chunk_workspace_bytes(int64_t m) {
+  return noise_floor_workspace_bytes(m, 1) + sizeof(double) * static_cast<size_t>(m) + 4096;
+}
+
+int bpm_noise_floor_chunk(const double* envelope, const BpmItem* items, const BpmItem* items_host, int distance,
+                          const double* trough_prominence, double floor_q, int window, double rejection_multiplier,
+                          int64_t core_lo, int64_t core_hi, int open_left, int open_right, double* floor_out,
+                          int64_t* troughs_out, int64_t* trough_count, int64_t* all_troughs_out, int64_t* all_count,
+                          uint64_t* edge_hits, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!workspace || !items_host || !edge_hits) return BPM_ERR_ARG;
+  Workspace ws(workspace, workspace_bytes);
+  const ChunkInfo ci{core_lo, core_hi, open_left, open_right, reinterpret_cast<unsigned long long*>(edge_hits)};
+  return noise_floor_chunk_run(envelope, items, batch_shape(items_host, 1), distance, trough_prominence, floor_q, window,
+                               rejection_multiplier, ci, floor_out, troughs_out, trough_count, all_troughs_out, all_count,
+                               ws, static_cast<cudaStream_t>(stream));
+}
+
+int bpm_deviation_series(const double* strength, const int64_t* peak_count, const BpmItem* items,
+                         const BpmItem* items_host, int n_items, double smoothing_factor, double* deviation,
+                         double* smoothed, void* stream) {
+  if (!items_host || n_items <= 0) return BPM_ERR_ARG;
+  return deviation_series_run(strength, peak_count, items, batch_shape(items_host, n_items), smoothing_factor,
+                              deviation, smoothed, static_cast<cudaStream_t>(stream));
 }
 
 int bpm_cast_f32(const double* src, float* dst, int64_t n, void* stream) {

@@ -591,6 +591,8 @@ def beat_chain(owner, beats: np.ndarray, rate: int, window_us: int, win: int, st
     (beat list + the two list descriptors in one pinned block), the kernels, TWO read-backs (one
     float64 block, one int64 block), one synchronisation."""
     lib, dev, stream = owner.lib, owner.device, owner.stream
+    from .dropin import _Trace
+    tr = _Trace(owner.trace)
     b = int(beats.size)
     res: Dict[str, object] = {"n_beats": b}
     if b < 2:
@@ -609,6 +611,7 @@ def beat_chain(owner, beats: np.ndarray, rate: int, window_us: int, win: int, st
     sn[0:4] = items.view(np.int64).reshape(-1)
     sn[4:8] = sitems.view(np.int64).reshape(-1)
     sn[8:] = beats
+    tr.mark("beat.host_prep")
     with torch.cuda.stream(stream):
         st = stream.cuda_stream
         iblk = torch.empty(n_i, dtype=torch.int64, device=dev)
@@ -639,7 +642,9 @@ def beat_chain(owner, beats: np.ndarray, rate: int, window_us: int, win: int, st
         ih = torch.empty(3 * b + 4, dtype=torch.int64, pin_memory=True)
         fh.copy_(fblk[:7 * b + 8], non_blocking=True)
         ih.copy_(iblk[8 + b:], non_blocking=True)
+    tr.mark("beat.enqueue")
     stream.synchronize()
+    tr.mark("beat.wait")
     f, i = fh.numpy(), ih.numpy()
     nv = int(i[3 * b])
     if nv != n_series:
@@ -651,6 +656,7 @@ def beat_chain(owner, beats: np.ndarray, rate: int, window_us: int, win: int, st
         res["bottoms"] = i[2 * b:2 * b + int(i[3 * b + 2])].copy()
     if b >= win:
         res["hrv"] = f[3 * b:3 * b + 4 * int(i[3 * b + 3])].reshape(-1, 4).copy()
+    tr.mark("beat.unpack")
     return res
 
 

@@ -234,6 +234,51 @@ int bpm_windowed_hrv(const int64_t* beats, const BpmItem* lists, const BpmItem* 
                      int n_lists, int rate, int window_beats, int step_beats,
                      double* out, int64_t* rows, void* stream);
 
+/* ---- ONE long recording as halo-overlapped time chunks over several GPUs ------------------------
+ * (north star: "long single recordings split into halo-overlapped time chunks per GPU, with NCCL
+ * used only to gather per-chunk peak lists and window stats"; host side: stream.ShardedFrontEnd.)
+ * A rank runs every stage on its chunk + halo; the only stream-wide quantities are the np.quantile
+ * thresholds (:1067, :225) -- resolved by bpm_key_histogram / bpm_key_collect with the histograms
+ * summed over the ranks -- and the deviation-smoothing window (:99), which depends on the total peak
+ * count, so bpm_deviation_series runs on the gathered strength list.
+ *
+ * bpm_key_histogram: hist[b] += number of samples whose order-preserving key k has
+ *   (k >> (shift + bits)) == prefix  (every sample when shift + bits == 64)  and  ((k >> shift) & (2^bits - 1)) == b;
+ *   hist: uint64[2^bits], accumulated (zero it first), bits <= 11.
+ * bpm_key_collect: keys with (k >> up_shift) == prefix -> out_keys (first `cap` of them), count_min[0] += their
+ *   number, count_min[1] = min(count_min[1], smallest key above the bucket)  (preset count_min = {0, ~0}).
+ * The key of a double v: bits(v) with the sign bit set for v >= 0, all bits flipped for v < 0. */
+int bpm_key_histogram(const double* x, int64_t n, int shift, int bits, uint64_t prefix, uint64_t* hist, void* stream);
+int bpm_key_collect(const double* x, int64_t n, int up_shift, uint64_t prefix, int64_t cap, uint64_t* out_keys,
+                    uint64_t* count_min, void* stream);
+
+/* find_peaks on a chunk [ext_lo, ext_hi) of a stream (one recording per call).  core_lo / core_hi: the part
+ * of the chunk (chunk-relative indices) whose peaks the caller keeps; open_left / open_right: that end of
+ * the chunk is artificial.  *edge_hits (device, uint64, accumulated) counts every decision about a core
+ * peak that could depend on samples beyond an open end -- a distance chain longer than the kernel
+ * follows, a prominence walk that stopped at the end, a flat run from the end into the core.  0 means
+ * the core's peaks are exactly those of the unchunked evaluation. */
+int bpm_find_peaks_chunk(const double* x, int sign, const double* height, const double* prominence, int distance,
+                         const BpmItem* items, const BpmItem* items_host, int64_t core_lo, int64_t core_hi,
+                         int open_left, int open_right, int64_t* out_idx, int64_t* out_count, uint64_t* edge_hits,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* _calculate_dynamic_noise_floor (:1064-1117) on a chunk with the stream-wide trough prominence threshold
+ * GIVEN (device double[1]) and without the count-based fall-backs (:1073, :1102, :1113: decided on the
+ * stream's totals by the caller).  all_troughs_out / all_count: the troughs before sanitisation. */
+size_t bpm_noise_floor_chunk_workspace_bytes(int64_t m);
+int bpm_noise_floor_chunk(const double* envelope, const BpmItem* items, const BpmItem* items_host, int distance,
+                          const double* trough_prominence, double floor_q, int window, double rejection_multiplier,
+                          int64_t core_lo, int64_t core_hi, int open_left, int open_right, double* floor_out,
+                          int64_t* troughs_out, int64_t* trough_count, int64_t* all_troughs_out, int64_t* all_count,
+                          uint64_t* edge_hits, void* workspace, size_t workspace_bytes, void* stream);
+
+/* deviation / smoothed deviation (:96-100) from a given strength list (laid out like a peak list;
+ * `deviation` needs room for 2 P values per recording). */
+int bpm_deviation_series(const double* strength, const int64_t* peak_count, const BpmItem* items,
+                         const BpmItem* items_host, int n_items, double smoothing_factor, double* deviation,
+                         double* smoothed, void* stream);
+
 /* ---- float32 outputs (north star: "1e-4 (float32 mode)") ---------------------------------------
  * dst[i] = (float) src[i].  Every stage computes in float64 -- a float32 filter recurrence at these
  * pole radii is off by 1e-3 -- and only the signals handed back to the host (envelope, noise
