@@ -80,9 +80,9 @@ _SIGNATURES = {
     "bpm_cast_f32": (_I, [_P, _P, _L, _P]),
     "bpm_key_histogram": (_I, [_P, _L, _I, _I, C.c_uint64, _P, _P]),
     "bpm_key_collect": (_I, [_P, _L, _I, C.c_uint64, _L, _P, _P, _P]),
-    "bpm_find_peaks_chunk": (_I, [_P, _I, _P, _P, _I, _P, _P, _L, _L, _I, _I, _P, _P, _P, _P, _Z, _P]),
+    "bpm_find_peaks_chunk": (_I, [_P, _I, _P, _P, _I, _P, _P, _L, _L, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "bpm_noise_floor_chunk_workspace_bytes": (_Z, [_L]),
-    "bpm_noise_floor_chunk": (_I, [_P, _P, _P, _I, _P, _D, _I, _D, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    "bpm_noise_floor_chunk": (_I, [_P, _P, _P, _I, _P, _D, _I, _D, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "bpm_deviation_series": (_I, [_P, _P, _P, _P, _I, _D, _P, _P, _P]),
     "bpm_stage_a_workspace_bytes": (_Z, [_L, _I]),
     "bpm_stage_a": (_I, [_P, _P, _P, _I, _P, _P, _L, C.POINTER(StageAConfig), C.POINTER(StageAOutputs), _P, _Z, _P]),

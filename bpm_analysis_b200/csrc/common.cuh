@@ -183,6 +183,8 @@ struct ChunkInfo {
   int64_t core_lo, core_hi;
   int open_left, open_right;
   unsigned long long* edge_hits;     // device counter, nullptr: not a chunk
+  long long* anchors;                // [0]: max position <= core_lo, [1]: min position >= core_hi - 1 of a candidate
+                                     // that outranks EVERY candidate within the distance (see k_distance_tiles)
 };
 
 // ------------------------------------------------------------- single-pass ordered compaction

@@ -203,6 +203,14 @@ __device__ unsigned long long g_dbg_pk[16];
 // falls back to the unchunked evaluation): candidates the distance tiles left to the global finish
 // (all other chains are at most DT_DEPTH hops of < d samples long, far inside the halo) and prominence
 // walks of core peaks that stopped at an open end.  Single-recording calls only.
+//
+// Memoised results make the TRUE dependency chain of a decision unbounded in principle (a long ramp of
+// candidates alternates kept / removed all the way), so "not pending" alone proves nothing about how
+// far an open end can reach.  What does: an ANCHOR, a candidate that outranks every candidate within
+// the distance.  It is kept whatever happens elsewhere, it removes every candidate within d of it, and
+// therefore no decision on its far side can depend on anything on its near side.  The kernel reports
+// the anchors nearest to the core (ci.anchors); the caller accepts the core's decisions only if one of
+// them lies between each open end's doubtful zone and the core.
 // ------------------------------------------------------------------ distance
 constexpr int DT_THREADS = 128;
 constexpr int DT_OWN = 512;                       // candidates a CTA settles per tile
@@ -210,6 +218,12 @@ constexpr int DT_HALO = 64;                       // staged on either side of th
 constexpr int DT_STAGE = DT_OWN + 2 * DT_HALO;
 constexpr int DT_DEPTH = 24;                      // dependency chains followed this deep, longer ones are left pending
 enum : unsigned char { DST_REMOVED = 0, DST_KEPT = 1, DST_PENDING = 3 };   // global state of a candidate
+
+__device__ __forceinline__ void note_anchor(const ChunkInfo& ci, int pk) {
+  if (ci.anchors == nullptr) return;
+  if (pk <= ci.core_lo) atomicMax(ci.anchors, static_cast<long long>(pk));
+  if (pk >= ci.core_hi - 1) atomicMin(ci.anchors + 1, static_cast<long long>(pk));
+}
 
 __device__ __forceinline__ bool higher_priority(double va, int64_t ka, double vb, int64_t kb) {
   return va > vb || (va == vb && ka > kb);
@@ -300,7 +314,10 @@ __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __r
           if (s_val[k2] >= vk) m |= 1u << b;
         const bool full = (!open_left || pk - p_first >= d) && (!open_right || p_last - pk >= d);
         s_hi[k] = m;
-        if (m == 0) s_st[k] = full ? 1 : 3;                       // no higher-priority neighbour at all
+        if (m == 0) {                                             // no higher-priority neighbour at all
+          s_st[k] = full ? 1 : 3;
+          if (full) note_anchor(ci, pk);
+        }
       }
       __syncthreads();
       for (int kk = own0 + tid; kk < own1; kk += DT_THREADS) {
@@ -346,10 +363,11 @@ __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __r
 #endif
           const int pk = s_pos[cur];
           const double vk = s_val[cur];
-          bool any_keep = false, any_unknown = false;
+          bool any_keep = false, any_unknown = false, any_hi = false;
           int open_j = -1;
           for (int k2 = cur - 1; k2 >= 0 && pk - s_pos[k2] < d; --k2) {
             if (s_val[k2] > vk) {                                 // equal heights: the later index wins
+              any_hi = true;
               const unsigned char s2 = S[k2];
               if (s2 == 1) { any_keep = true; break; }
               if (s2 == 0) open_j = k2; else if (s2 == 3) any_unknown = true;
@@ -358,6 +376,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __r
           if (!any_keep) {
             for (int k2 = cur + 1; k2 < L && s_pos[k2] - pk < d; ++k2) {
               if (s_val[k2] >= vk) {
+                any_hi = true;
                 const unsigned char s2 = S[k2];
                 if (s2 == 1) { any_keep = true; break; }
                 if (s2 == 0) open_j = k2; else if (s2 == 3) any_unknown = true;
@@ -372,6 +391,7 @@ __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __r
           } else {
             const bool full = (!open_left || pk - p_first >= d) && (!open_right || p_last - pk >= d);
             S[cur] = (any_unknown || !full) ? 3 : 1;
+            if (!any_hi && full) note_anchor(ci, pk);
           }
         }
         if (sp == 0) break;
@@ -590,7 +610,7 @@ int find_peaks_run(const double* x, int sign, const double* height, const double
                    Workspace& ws, cudaStream_t st, cudaEvent_t prominence_ready, const ChunkInfo* chunk) {
   if (!x || !items || !out_idx || !out_count || sh.n_items <= 0 || distance < 1) return BPM_ERR_ARG;
   if (chunk != nullptr && sh.n_items != 1) return BPM_ERR_ARG;
-  const ChunkInfo ci = chunk ? *chunk : ChunkInfo{0, 0, 0, 0, nullptr};
+  const ChunkInfo ci = chunk ? *chunk : ChunkInfo{0, 0, 0, 0, nullptr, nullptr};
   PeakBuffers b;
   BPM_TRY(carve_peaks(ws, sh.total_m, sh.max_m, sh.n_items, &b));
   if (cudaMemsetAsync(b.status_a, 0, b.zero_bytes, st) != cudaSuccess) return BPM_ERR_CUDA;

@@ -491,10 +491,11 @@ int bpm_windowed_hrv(const int64_t* beats, const BpmItem* lists, const BpmItem* 
 int bpm_find_peaks_chunk(const double* x, int sign, const double* height, const double* prominence, int distance,
                          const BpmItem* items, const BpmItem* items_host, int64_t core_lo, int64_t core_hi,
                          int open_left, int open_right, int64_t* out_idx, int64_t* out_count, uint64_t* edge_hits,
-                         void* workspace, size_t workspace_bytes, void* stream) {
-  if (!workspace || !items_host || !edge_hits || (sign != 1 && sign != -1)) return BPM_ERR_ARG;
+                         int64_t* anchors, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!workspace || !items_host || !edge_hits || !anchors || (sign != 1 && sign != -1)) return BPM_ERR_ARG;
   Workspace ws(workspace, workspace_bytes);
-  const ChunkInfo ci{core_lo, core_hi, open_left, open_right, reinterpret_cast<unsigned long long*>(edge_hits)};
+  const ChunkInfo ci{core_lo, core_hi, open_left, open_right, reinterpret_cast<unsigned long long*>(edge_hits),
+                     reinterpret_cast<long long*>(anchors)};
   return find_peaks_run(x, sign, height, prominence, distance, items, batch_shape(items_host, 1), out_idx, out_count,
                         ws, static_cast<cudaStream_t>(stream), nullptr, &ci);
 }
@@ -507,10 +508,11 @@ int bpm_noise_floor_chunk(const double* envelope, const BpmItem* items, const Bp
                           const double* trough_prominence, double floor_q, int window, double rejection_multiplier,
                           int64_t core_lo, int64_t core_hi, int open_left, int open_right, double* floor_out,
                           int64_t* troughs_out, int64_t* trough_count, int64_t* all_troughs_out, int64_t* all_count,
-                          uint64_t* edge_hits, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!workspace || !items_host || !edge_hits) return BPM_ERR_ARG;
+                          uint64_t* edge_hits, int64_t* anchors, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!workspace || !items_host || !edge_hits || !anchors) return BPM_ERR_ARG;
   Workspace ws(workspace, workspace_bytes);
-  const ChunkInfo ci{core_lo, core_hi, open_left, open_right, reinterpret_cast<unsigned long long*>(edge_hits)};
+  const ChunkInfo ci{core_lo, core_hi, open_left, open_right, reinterpret_cast<unsigned long long*>(edge_hits),
+                     reinterpret_cast<long long*>(anchors)};
   return noise_floor_chunk_run(envelope, items, batch_shape(items_host, 1), distance, trough_prominence, floor_q, window,
                                rejection_multiplier, ci, floor_out, troughs_out, trough_count, all_troughs_out, all_count,
                                ws, static_cast<cudaStream_t>(stream));

@@ -6,11 +6,12 @@
 //       rank histograms its own samples, the histograms are summed over NVLink (ncclAllReduce of 2048
 //       counters), all ranks pick the same bucket, and after two or three digits the few keys left in
 //       the bucket are gathered and ordered.  Same order-preserving 64-bit keys as select.cu.
+// The chunk-mode operators themselves live beside their unchunked forms (pipeline.cu, peaks.cu):
 //   bpm_noise_floor_chunk   _calculate_dynamic_noise_floor (:1064-1117) on one chunk + halo with the
 //       stream-wide thresholds GIVEN and without the count-based fall-backs (those are decided on the
 //       stream's totals by the caller).
 //   bpm_find_peaks_chunk    find_peaks on a chunk + halo, reporting every decision that could depend on
-//       samples outside the chunk (edge_hits).
+//       samples outside the chunk (edge_hits, anchors).
 //   bpm_deviation_series    the deviation / smoothed-deviation series (:96-100) from a GIVEN strength list
 //       (the smoothing window is 5 % of the stream's total peak count, so it runs after the gather).
 #include "common.cuh"
@@ -93,8 +94,9 @@ using namespace bpm;
 extern "C" {
 
 int bpm_key_histogram(const double* x, int64_t n, int shift, int bits, uint64_t prefix, uint64_t* hist, void* stream) {
-  if (!x || !hist || n < 0 || bits < 1 || bits > 11 || shift < 0 || shift + bits > 64) return BPM_ERR_ARG;
-  if (n == 0) return BPM_OK;
+  if (!hist || n < 0 || bits < 1 || bits > 11 || shift < 0 || shift + bits > 64) return BPM_ERR_ARG;
+  if (n == 0) return BPM_OK;                      // a rank without samples contributes nothing
+  if (!x) return BPM_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BPM_KERNEL(k_key_hist);
   k_key_hist<<<cdiv(n, KH_THREADS * KH_PER), KH_THREADS, 0, st>>>(x, n, shift, bits, prefix,
@@ -105,8 +107,9 @@ int bpm_key_histogram(const double* x, int64_t n, int shift, int bits, uint64_t 
 
 int bpm_key_collect(const double* x, int64_t n, int up_shift, uint64_t prefix, int64_t cap, uint64_t* out_keys,
                     uint64_t* count_min, void* stream) {
-  if (!x || !out_keys || !count_min || n < 0 || cap < 1 || up_shift < 1 || up_shift > 63) return BPM_ERR_ARG;
+  if (!out_keys || !count_min || n < 0 || cap < 0 || up_shift < 0 || up_shift > 63) return BPM_ERR_ARG;
   if (n == 0) return BPM_OK;
+  if (!x) return BPM_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BPM_KERNEL(k_key_collect);
   k_key_collect<<<cdiv(n, KH_THREADS * KH_PER), KH_THREADS, 0, st>>>(

@@ -133,6 +133,20 @@ class DistComm:
         return [out[r * cap:r * cap + s] for r, s in enumerate(sizes)]
 
 
+    def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            self._dist.all_reduce(t, group=self.group)
+        return t
+
+    def all_gather_rows(self, t: torch.Tensor) -> torch.Tensor:
+        """Equal-size rows, one per rank -> (world, len) tensor."""
+        if self.world == 1:
+            return t[None]
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self._dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
+
 class ThreadComm:
     """``world`` ranks as threads of one process (all on the current device): the exchange is
     a barrier plus a shared slot list.  For tests and for trying a chunking on one GPU."""
@@ -158,6 +172,19 @@ class ThreadComm:
         out = [x.clone() for x in self.shared.slots]
         self.shared.barrier.wait()
         return out
+
+
+def _thread_all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
+    t.copy_(torch.stack(self.all_gather(t)).sum(0))
+    return t
+
+
+def _thread_all_gather_rows(self, t: torch.Tensor) -> torch.Tensor:
+    return torch.stack(self.all_gather(t))
+
+
+ThreadComm.all_reduce_sum = _thread_all_reduce_sum
+ThreadComm.all_gather_rows = _thread_all_gather_rows
 
 
 def run_thread_world(world: int, fn):
@@ -336,6 +363,157 @@ class DeviceEngine:
         return st[:c], dv[:d], sm[:d]
 
 
+    # ---- chunk mode (ShardedFrontEnd): nothing here synchronises the host
+    def key_histogram(self, x: torch.Tensor, shift: int, bits: int, prefix: int) -> torch.Tensor:
+        hist = torch.zeros(1 << bits, dtype=torch.int64, device=self.device)
+        self.nat.check(self.lib.bpm_key_histogram(self.rt._ptr(x), x.numel(), int(shift), int(bits), int(prefix),
+                                                  self.rt._ptr(hist), self.rt._stream_ptr()))
+        return hist
+
+    def key_collect(self, x: torch.Tensor, up_shift: int, prefix: int, cap: int) -> torch.Tensor:
+        """-> int64[cap + 2] (bit patterns of uint64): [count, smallest key above the bucket, keys...]"""
+        out = torch.zeros(cap + 2, dtype=torch.int64, device=self.device)
+        out[1] = -1                                              # ~0 as uint64
+        base = out.data_ptr()
+        self.nat.check(self.lib.bpm_key_collect(self.rt._ptr(x), x.numel(), int(up_shift), int(prefix), int(cap),
+                                                C.c_void_p(base + 16), C.c_void_p(base), self.rt._stream_ptr()))
+        return out
+
+    def chunk_flags(self) -> torch.Tensor:
+        """[edge hits, trough anchors (left, right), peak anchors (left, right)] preset for a chunk call."""
+        big = np.iinfo(np.int64).max
+        return torch.tensor([0, -1, big, -1, big], dtype=torch.int64, device=self.device)
+
+    def noise_floor_chunk(self, env: torch.Tensor, distance: int, q_tp: torch.Tensor, window: int, params: Dict,
+                          core: Tuple[int, int], open_ends: Tuple[bool, bool], flags: torch.Tensor):
+        """-> floor, kept troughs (buffer), all troughs (buffer), counts int64[2] = (kept, all)"""
+        rt, L = self.rt, self.lib
+        n = env.numel()
+        items, items_dev = self._items(n, n)
+        floor = torch.empty(n, dtype=torch.float64, device=self.device)
+        kept = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+        every = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+        cnt = torch.zeros(2, dtype=torch.int64, device=self.device)
+        nb = int(L.bpm_noise_floor_chunk_workspace_bytes(n))
+        ws = self._ws(nb)
+        fb, cb = flags.data_ptr(), cnt.data_ptr()
+        self.nat.check(L.bpm_noise_floor_chunk(rt._ptr(env), rt._ptr(items_dev), rt._host_ptr(items), int(distance),
+                                               rt._ptr(q_tp), float(params["noise_floor_quantile"]), int(window),
+                                               float(params.get("trough_rejection_multiplier", 4.0)),
+                                               int(core[0]), int(core[1]), int(open_ends[0]), int(open_ends[1]),
+                                               rt._ptr(floor), rt._ptr(kept), C.c_void_p(cb), rt._ptr(every),
+                                               C.c_void_p(cb + 8), C.c_void_p(fb), C.c_void_p(fb + 8), rt._ptr(ws), nb,
+                                               rt._stream_ptr()))
+        self._keep_chunk = (ws, items_dev)
+        return floor, kept, every, cnt
+
+    def find_peaks_chunk(self, x: torch.Tensor, sign: int, height: Optional[torch.Tensor], prominence: torch.Tensor,
+                         distance: int, core: Tuple[int, int], open_ends: Tuple[bool, bool], flags: torch.Tensor):
+        rt, L = self.rt, self.lib
+        n = x.numel()
+        items, items_dev = self._items(n, n)
+        idx = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+        cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
+        nb = int(L.bpm_find_peaks_workspace_bytes(n, 1))
+        ws = self._ws(nb)
+        fb = flags.data_ptr()
+        self.nat.check(L.bpm_find_peaks_chunk(rt._ptr(x), int(sign), rt._ptr(height), rt._ptr(prominence), int(distance),
+                                              rt._ptr(items_dev), rt._host_ptr(items), int(core[0]), int(core[1]),
+                                              int(open_ends[0]), int(open_ends[1]), rt._ptr(idx), rt._ptr(cnt),
+                                              C.c_void_p(fb), C.c_void_p(fb + 24), rt._ptr(ws), nb, rt._stream_ptr()))
+        self._keep_peaks = (ws, items_dev)
+        return idx, cnt
+
+    def peak_strength(self, env: torch.Tensor, floor: torch.Tensor, peaks: torch.Tensor, count: torch.Tensor) -> torch.Tensor:
+        """strength of the first ``count`` entries of a peak buffer (:95); no host synchronisation"""
+        rt, L = self.rt, self.lib
+        n = env.numel()
+        items, items_dev = self._items(n, n)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        st, dv, sm = torch.empty(n, **f64), torch.empty(2 * n, **f64), torch.empty(n, **f64)
+        self.nat.check(L.bpm_peak_metrics(rt._ptr(env), rt._ptr(floor), rt._ptr(peaks), rt._ptr(count),
+                                          rt._ptr(items_dev), rt._host_ptr(items), 1, 0.05, rt._ptr(st), rt._ptr(dv),
+                                          rt._ptr(sm), rt._stream_ptr()))
+        self._keep_strength = (items_dev, dv, sm)
+        return st
+
+    def deviation_series(self, strength: torch.Tensor, factor: float):
+        """deviation and its rolling mean (:96-100) of a whole strength list"""
+        rt, L = self.rt, self.lib
+        c = strength.numel()
+        d = max(c - 1, 0)
+        if c < 2:
+            z = torch.zeros(0, dtype=torch.float64, device=self.device)
+            return z, z
+        items, items_dev = self._items(c, c)
+        cnt = torch.tensor([c], dtype=torch.int64, device=self.device)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        dv, sm = torch.empty(2 * c, **f64), torch.empty(c, **f64)
+        self.nat.check(L.bpm_deviation_series(rt._ptr(strength.contiguous()), rt._ptr(cnt), rt._ptr(items_dev),
+                                              rt._host_ptr(items), 1, float(factor), rt._ptr(dv), rt._ptr(sm),
+                                              rt._stream_ptr()))
+        self._keep_dev = (items_dev, cnt)
+        return dv[:d], sm[:d]
+
+
+# --------------------------------------------------------------------------- stream-wide order statistics
+KEY_PASSES = ((53, 11), (42, 11), (31, 11), (20, 11), (9, 11), (0, 9))     # (shift, bits), most significant first
+COLLECT_CAP = 4096
+
+
+def _key_to_f64(k: int) -> float:
+    b = (k & 0x7FFFFFFFFFFFFFFF) if (k >> 63) else (~k & 0xFFFFFFFFFFFFFFFF)
+    return float(np.array([b], dtype=np.uint64).view(np.float64)[0])
+
+
+def _np_lerp(a: float, b: float, t: float) -> float:
+    """numpy's _lerp (lib/_function_base_impl.py) on two scalars, operation for operation."""
+    a, b, t = np.float64(a), np.float64(b), np.float64(t)
+    diff = b - a
+    r = a + diff * t
+    if t >= 0.5:
+        r = b - diff * (np.float64(1.0) - t)
+    return float(r)
+
+
+def stream_quantile(engine, comm, x_core: torch.Tensor, n_total: int, q: float) -> float:
+    """np.quantile(x, q) (linear method) of a series whose samples are spread over the ranks
+    (each rank passes ITS samples, every sample on exactly one rank): a radix descent over the
+    order-preserving 64-bit keys with the per-digit histograms summed over the ranks, then the
+    few keys left in the bucket are gathered and sorted.  Every rank returns the same float."""
+    if n_total < 1:
+        raise ValueError("quantile of an empty stream")
+    v = np.float64(n_total - 1) * np.float64(q)                 # numpy's virtual index
+    k = int(min(max(np.floor(v), 0), n_total - 1))
+    gamma = float(v - np.floor(v))
+    prefix, rank, count, up = 0, k, n_total, 64
+    for shift, bits in KEY_PASSES:
+        hist = comm.all_reduce_sum(engine.key_histogram(x_core, shift, bits, prefix))
+        h = hist.cpu().numpy()
+        c = np.cumsum(h)
+        b = int(np.searchsorted(c, rank, side="right"))
+        rank -= int(c[b - 1]) if b else 0
+        count = int(h[b])
+        prefix = (prefix << bits) | b
+        up = shift
+        if count <= COLLECT_CAP:
+            break
+    # keys in the bucket (all equal when every digit is resolved) and the smallest key above it
+    cap = COLLECT_CAP if up > 0 else 0
+    got = comm.all_gather_rows(engine.key_collect(x_core, up, prefix, cap)).cpu().numpy().view(np.uint64)
+    above = int(got[:, 1].min())
+    if up > 0:
+        keys = np.sort(np.concatenate([row[2:2 + int(row[0])] for row in got]))
+        if len(keys) != count:
+            raise RuntimeError("stream_quantile: bucket size disagrees with its histogram")
+        ka = int(keys[rank])
+        kb = int(keys[rank + 1]) if rank + 1 < count else (above if above != 0xFFFFFFFFFFFFFFFF else ka)
+    else:
+        ka = prefix
+        kb = ka if rank + 1 < count else (above if above != 0xFFFFFFFFFFFFFFFF else ka)
+    return _np_lerp(_key_to_f64(ka), _key_to_f64(kb), gamma)
+
+
 # --------------------------------------------------------------------------- the chunked front end
 class ChunkedFrontEnd:
     """a1..a4 of ONE recording, time-chunked over ``comm.world`` ranks.
@@ -438,4 +616,156 @@ class ChunkedFrontEnd:
         env, filt_core = self.envelope(pcm_slice)
         out = self.analyse(env)
         out["filtered_core"] = filt_core
+        return out
+
+
+# --------------------------------------------------------------------------- every stage sharded
+DISTANCE_MARGIN_HOPS = 32        # samples of margin per unit of `distance` in which an anchor is looked for
+
+
+class ShardedFrontEnd(ChunkedFrontEnd):
+    """a1..a4 of ONE recording with EVERY stage evaluated per time chunk; the ranks exchange digit
+    histograms (the stream-wide np.quantile thresholds), a handful of counters, and at the end the
+    per-chunk trough / peak / strength lists -- never the envelope (``gather_series=False``).
+
+    A rank evaluates its core [c0, c1) on the extended range [c0 - H, c1 + H), H = filter halo +
+    analysis halo, and PROVES afterwards, from what it computed, that nothing it reports can depend on
+    samples it did not see:
+
+      find_peaks     the kernels count every core decision that touched an open end (``edge_hits``:
+                     prominence walks, flat runs, unresolved distance chains) and report the anchors
+                     next to the core (a candidate that outranks everything within ``distance``; no
+                     distance-rule dependency crosses one) -- see bpm_b200.h, bpm_find_peaks_chunk
+      rolling floors the window of an output lies between two knots (troughs) of the part of the
+                     trough list that is itself proven, so the interpolated series under the window
+                     is the stream's (np.interp between the same knots)
+      count rules    :1073 (< 5 troughs), :1102 (<= 2 kept) are decided on the stream's totals
+
+    If any rank cannot prove its chunk (or a count rule fires) ALL ranks fall back to
+    ChunkedFrontEnd (envelope gathered, global steps replicated), which is exact by construction;
+    ``result["sharded"]`` says which path produced the result.
+    """
+
+    def __init__(self, n_frames: int, sample_rate: int, params: Dict, comm, engine, plan=None,
+                 pcm_dtype=np.int16, channels: int = 1, analysis_halo: Optional[int] = None):
+        super().__init__(n_frames, sample_rate, params, comm, engine, plan, pcm_dtype, channels)
+        self.filter_halo = self.chunks.halo
+        self._set_halo(analysis_halo)
+
+    @classmethod
+    def for_envelope(cls, m: int, rate: int, params: Dict, comm, engine,
+                     analysis_halo: Optional[int] = None) -> "ShardedFrontEnd":
+        self = super().for_envelope(m, rate, params, comm, engine)
+        self.filter_halo = 0
+        self._set_halo(analysis_halo)
+        return self
+
+    def _set_halo(self, analysis_halo: Optional[int]) -> None:
+        self.margin = DISTANCE_MARGIN_HOPS * self.distance + 64
+        if analysis_halo is None:
+            # two rolling windows deep (draft floor -> kept troughs -> final floor), each half a window
+            # plus the gap to the next trough (allowed: another half window), and three margins
+            analysis_halo = 2 * self.window + 3 * self.margin
+        self.analysis_halo = int(analysis_halo)
+        ch = self.chunks
+        self.chunks = ChunkPlan(ch.n_frames, ch.m, ch.frames_per_sample, self.filter_halo + self.analysis_halo, ch.world)
+
+    # -- proof obligations, on the host, from the chunk's own lists (indices local to the ext range)
+    def _proven_range(self, knots: np.ndarray, lo: int, hi: int, at_start: bool, at_end: bool, n: int) -> Tuple[int, int]:
+        """Outputs of a rolling quantile over np.interp(knots) that equal the stream's, given that the
+        knot list is the stream's inside [lo, hi)."""
+        off = (self.window - 1) // 2
+        left = self.window - 1 - off
+        k = knots[(knots >= lo) & (knots < hi)]
+        if len(k) == 0:
+            return (0, 0) if not (at_start and at_end) else (0, n)
+        return (0 if at_start else int(k[0]) + left), (n if at_end else int(k[-1]) - off + 1)
+
+    def analyse_sharded(self, env_ext: torch.Tensor) -> Optional[Dict[str, torch.Tensor]]:
+        """Per-chunk evaluation; None if some rank could not prove its chunk."""
+        E, P, ch, comm = self.engine, self.params, self.chunks, self.comm
+        (c0, c1), (e0, e1) = ch.core(comm.rank), ch.ext(comm.rank)
+        n = e1 - e0
+        at_start, at_end = e0 == 0, e1 == ch.m
+        open_ends = (not at_start, not at_end)
+        core = (c0 - e0, c1 - e0)
+        env_core = env_ext[core[0]:core[1]]
+        # stream-wide thresholds (:1067, :225)
+        q_tp = stream_quantile(E, comm, env_core, ch.m, float(P["trough_prominence_quantile"]))
+        q_pp = q_tp if P["peak_prominence_quantile"] == P["trough_prominence_quantile"] else \
+            stream_quantile(E, comm, env_core, ch.m, float(P["peak_prominence_quantile"]))
+        thr = torch.tensor([q_tp, q_pp], dtype=torch.float64, device=env_ext.device)
+        # the whole per-chunk chain, enqueued without a host synchronisation
+        doubt = self.filter_halo + self.margin                   # zone next to an open end nothing is claimed about
+        t_core = (0 if at_start else doubt, n if at_end else n - doubt)
+        flags = E.chunk_flags()
+        floor, kept, every, tcnt = E.noise_floor_chunk(env_ext, self.distance, thr[0:1], self.window, P, t_core,
+                                                       open_ends, flags)
+        peaks, pcnt = E.find_peaks_chunk(env_ext, +1, floor, thr[1:2], self.distance, core, open_ends, flags)
+        strength = E.peak_strength(env_ext, floor, peaks, pcnt)
+        head = torch.cat([flags, tcnt, pcnt]).cpu().numpy()      # the chunk's one wait for the device
+        edge_hits, ta0, ta1, pa0, pa1, n_kept, n_all, n_peaks = (int(v) for v in head)
+        lists = torch.cat([every[:n_all], kept[:n_kept], peaks[:n_peaks]]).cpu().numpy()
+        every_h, kept_h, peaks_h = lists[:n_all], lists[n_all:n_all + n_kept], lists[n_all + n_kept:]
+        d = self.distance
+        ok = edge_hits == 0
+        # trough list proven on t_core: an anchor between each doubtful zone and t_core
+        if d > 1:
+            ok &= at_start or ta0 - d >= self.filter_halo
+            ok &= at_end or ta1 + d <= n - self.filter_halo
+        x2 = self._proven_range(every_h, t_core[0], t_core[1], at_start, at_end, n)       # draft floor
+        x3 = self._proven_range(kept_h, max(x2[0], t_core[0]), min(x2[1], t_core[1]), at_start, at_end, n)  # final floor
+        # peaks: candidates (height = floor) are the stream's on x3; an anchor inside it on each open side
+        ok &= x3[0] <= core[0] and x3[1] >= core[1]
+        if d > 1:
+            ok &= at_start or (pa0 >= 0 and pa0 - d >= x3[0])
+            ok &= at_end or (pa1 < n and pa1 + d < x3[1])
+        lo_a, hi_a = np.searchsorted(every_h, core)
+        lo_k, hi_k = np.searchsorted(kept_h, core)
+        lo_p, hi_p = np.searchsorted(peaks_h, core)
+        mine = torch.tensor([0 if ok else 1, hi_a - lo_a, hi_k - lo_k, hi_p - lo_p], dtype=torch.int64,
+                            device=env_ext.device)
+        table = comm.all_gather_rows(mine).cpu().numpy()
+        self.last_proof = {"ok": bool(ok), "edge_hits": edge_hits, "proven_floor": (x3[0] + e0, x3[1] + e0),
+                           "trough_anchors": (ta0, ta1), "peak_anchors": (pa0, pa1)}
+        if table[:, 0].any() or table[:, 1].sum() < MIN_TROUGHS or table[:, 2].sum() <= MIN_KEPT:
+            return None
+        troughs = torch.cat(comm.all_gather(kept[lo_k:hi_k] + e0, [int(v) for v in table[:, 2]]))
+        sizes_p = [int(v) for v in table[:, 3]]
+        peaks_all = torch.cat(comm.all_gather(peaks[lo_p:hi_p] + e0, sizes_p))
+        strength_all = torch.cat(comm.all_gather(strength[lo_p:hi_p].contiguous(), sizes_p))
+        deviation, smoothed = E.deviation_series(strength_all, float(P["deviation_smoothing_factor"]))
+        return {"troughs": troughs, "peaks": peaks_all, "strength": strength_all, "deviation": deviation,
+                "smoothed_dev": smoothed, "envelope_core": env_core, "floor_core": floor[core[0]:core[1]],
+                "thresholds": thr}
+
+    def analyse_local(self, env_ext: torch.Tensor, gather_series: bool = False) -> Dict[str, torch.Tensor]:
+        ch, comm = self.chunks, self.comm
+        (c0, c1), (e0, _) = ch.core(comm.rank), ch.ext(comm.rank)
+        out = self.analyse_sharded(env_ext)
+        if out is None:                                           # exact by construction, slower
+            env = torch.cat(comm.all_gather(env_ext[c0 - e0:c1 - e0].contiguous(), ch.core_sizes()))
+            out = ChunkedFrontEnd.analyse(self, env)
+            out["envelope_core"], out["floor_core"] = out["envelope"][c0:c1], out["floor"][c0:c1]
+            out["sharded"] = False
+            return out
+        out["sharded"] = True
+        if gather_series:
+            sizes = ch.core_sizes()
+            out["envelope"] = torch.cat(comm.all_gather(out["envelope_core"].contiguous(), sizes))
+            out["floor"] = torch.cat(comm.all_gather(out["floor_core"].contiguous(), sizes))
+        return out
+
+    def analyse(self, env: torch.Tensor, gather_series: bool = True) -> Dict[str, torch.Tensor]:
+        """On an envelope every rank already holds (for_envelope)."""
+        e0, e1 = self.chunks.ext(self.comm.rank)
+        return self.analyse_local(env[e0:e1], gather_series)
+
+    def run(self, pcm_slice, gather_series: bool = False) -> Dict[str, torch.Tensor]:
+        ch, r = self.chunks, self.comm.rank
+        f0, f1 = ch.frames(r)
+        (c0, c1), (e0, _) = ch.core(r), ch.ext(r)
+        filt, env = self.engine.frontend(pcm_slice, f1 - f0, self.plan, self.channels, self.np_dtype)
+        out = self.analyse_local(env, gather_series)
+        out["filtered_core"] = filt[c0 - e0:c1 - e0]
         return out

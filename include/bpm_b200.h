@@ -256,12 +256,18 @@ int bpm_key_collect(const double* x, int64_t n, int up_shift, uint64_t prefix, i
  * of the chunk (chunk-relative indices) whose peaks the caller keeps; open_left / open_right: that end of
  * the chunk is artificial.  *edge_hits (device, uint64, accumulated) counts every decision about a core
  * peak that could depend on samples beyond an open end -- a distance chain longer than the kernel
- * follows, a prominence walk that stopped at the end, a flat run from the end into the core.  0 means
- * the core's peaks are exactly those of the unchunked evaluation. */
+ * follows, a prominence walk that stopped at the end, a flat run from the end into the core.
+ * anchors (device, int64[2], preset {-1, INT64_MAX}): [0] = the largest position <= core_lo, [1] = the
+ * smallest position >= core_hi - 1 of a candidate that outranks every candidate within `distance` of it.
+ * Such a candidate is kept whatever lies beyond it and removes all candidates within the distance, so
+ * no decision on one side of it depends on the other side.  The core's peaks are exactly those of the
+ * unchunked evaluation when *edge_hits == 0 and, towards each open end, an anchor lies between the core
+ * and the zone where the chunk's candidates may differ from the stream's (ShardedFrontEnd checks this
+ * and otherwise falls back to the replicated evaluation). */
 int bpm_find_peaks_chunk(const double* x, int sign, const double* height, const double* prominence, int distance,
                          const BpmItem* items, const BpmItem* items_host, int64_t core_lo, int64_t core_hi,
                          int open_left, int open_right, int64_t* out_idx, int64_t* out_count, uint64_t* edge_hits,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         int64_t* anchors, void* workspace, size_t workspace_bytes, void* stream);
 
 /* _calculate_dynamic_noise_floor (:1064-1117) on a chunk with the stream-wide trough prominence threshold
  * GIVEN (device double[1]) and without the count-based fall-backs (:1073, :1102, :1113: decided on the
@@ -271,7 +277,7 @@ int bpm_noise_floor_chunk(const double* envelope, const BpmItem* items, const Bp
                           const double* trough_prominence, double floor_q, int window, double rejection_multiplier,
                           int64_t core_lo, int64_t core_hi, int open_left, int open_right, double* floor_out,
                           int64_t* troughs_out, int64_t* trough_count, int64_t* all_troughs_out, int64_t* all_count,
-                          uint64_t* edge_hits, void* workspace, size_t workspace_bytes, void* stream);
+                          uint64_t* edge_hits, int64_t* anchors, void* workspace, size_t workspace_bytes, void* stream);
 
 /* deviation / smoothed deviation (:96-100) from a given strength list (laid out like a peak list;
  * `deviation` needs room for 2 P values per recording). */
