@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--duration-sec", type=float, default=3600.0)
     ap.add_argument("--sample-rate", type=int, default=48000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stream", action="store_true", help="skip the `stream` sub-record (one 24-h recording "
+                    "time-chunked over the GPUs of this run)")
+    ap.add_argument("--stream-hours", type=float, default=24.0)
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--no-zero-copy", action="store_true", help="e2e: copy the whole recording to the device first")
@@ -663,6 +666,13 @@ def run_b200(args):
                "sample": f"{reps} x first {sample_sec:g} s of the same recording, a1..a8, one core "
                          f"(the reference is single-threaded); {sum(ts):.2f} s in all"}
 
+    stream_rec = None
+    was_graphed = graphed is not None
+    if not args.no_stream:
+        del A, Bn, graphed
+        torch.cuda.empty_cache()
+        stream_rec = stream_record(args, rank, world, dev, params)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -687,13 +697,139 @@ def run_b200(args):
                         "ingest": (PIPE_INGEST[args.e2e_ingest] + f"{args.e2e_depth}-deep pipeline ingest | compute | "
                                    "read-back over three streams") if zero_copy else
                                   "cudaMemcpyAsync of the whole recording from pinned host memory, serial steps"},
-                "gpu_launches": launches if graphed is None else launches_per_step * args.steps,
-                "launch_mode": "eager" if graphed is None else "cuda-graph replay", "roofline": roofline,
-                "cpu_baseline": cpu, "parity": parity, "kernels": kernels}
+                "gpu_launches": launches_per_step * args.steps if was_graphed else launches,
+                "launch_mode": "cuda-graph replay" if was_graphed else "eager", "roofline": roofline,
+                "cpu_baseline": cpu, "parity": parity, "stream": stream_rec, "kernels": kernels}
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def stream_record(args, rank: int, world: int, dev, params) -> dict:
+    """SURVEY 8e row 2 in front of the driver: ONE long recording (C4, 24 h at 4 kHz) time-chunked
+    over the ranks of this run with every stage evaluated per chunk (stream.ShardedFrontEnd); NCCL
+    carries digit histograms, a table of counters and the chunks' trough / peak / strength lists.
+    Rank 0 also evaluates the whole recording unchunked on its one GPU: that is the parity check
+    (lists exact) and the one-GPU time the chunked step is compared with, measured in this run."""
+    import torch
+    import torch.distributed as dist
+    from bpm_analysis_b200 import _native, stream, synth
+    from bpm_analysis_b200.runtime import StageARunner
+    lib = _native.load_library()
+    sr, dur = 4000, float(args.stream_hours) * 3600.0
+    n = int(dur * sr)
+    pcm = None
+    if rank == 0:
+        pcm = synth.config_c4(seed=4, duration_sec=dur)[0]
+        whole = torch.from_numpy(pcm).to(dev)
+    else:
+        whole = torch.empty(n, dtype=torch.int16, device=dev)
+    if world > 1:
+        dist.broadcast(whole, 0)                      # benchmark set-up only: every rank then keeps its own slice
+    comm, eng = stream.DistComm(), stream.DeviceEngine()
+    fe = stream.ShardedFrontEnd(n, sr, params, comm, eng)
+    f0, f1 = fe.frames()
+    pcm_dev = whole[f0:f1].clone()
+    pcm_pin = torch.empty(f1 - f0, dtype=torch.int16).pin_memory()
+    pcm_pin.copy_(pcm_dev)
+    del whole
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    steps = max(3, min(args.steps, 10))
+    out = None
+    for _ in range(3):
+        out = fe.run(pcm_dev)
+    barrier()
+    l0 = lib.bpm_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = fe.run(pcm_dev)
+    e1.record()
+    barrier()
+    launches = int(lib.bpm_launch_count() - l0)
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / steps)
+    # end to end: this rank's frames from pinned host memory; the gathered lists and this rank's own
+    # envelope / floor chunk back into pinned host memory
+    keys = ("troughs", "peaks", "strength", "smoothed_dev", "envelope_core", "floor_core")
+    host = {}
+
+    def e2e_step():
+        pcm_dev.copy_(pcm_pin, non_blocking=True)
+        o = fe.run(pcm_dev)
+        for k in keys:
+            if k not in host or host[k].numel() < o[k].numel():
+                host[k] = torch.empty(o[k].numel(), dtype=o[k].dtype).pin_memory()
+            host[k][:o[k].numel()].copy_(o[k], non_blocking=True)
+        torch.cuda.synchronize()
+        return o
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+    d2h = int(sum(out[k].numel() * out[k].element_size() for k in keys))
+    sharded = bool(out["sharded"])
+    audio_hours = dur / 3600.0
+    rec = {"workload": f"C4 as ONE stream: synthetic {args.stream_hours:g}-h 4 kHz Holter-style recording, time-chunked "
+                       f"over {world} GPU(s), every stage per chunk + halo (stream.ShardedFrontEnd)",
+           "n_gpus": world, "scaling": "strong", "steps": steps, "ms_per_step": ms_step,
+           "value": audio_hours / (ms_step / 1e3), "unit": UNIT, "chunk_proofs_held": sharded,
+           "raw_samples": n, "envelope_samples": fe.chunks.m, "halo_envelope_samples": fe.chunks.halo,
+           "frames_this_rank": int(f1 - f0), "gpu_launches": launches,
+           "exchange": "all_reduce(2048-bin key histograms) x3 + all_gather(quantile bucket), all_gather(8 counters), "
+                       "all_gather(kept troughs | peaks | strength) -- never the envelope",
+           "e2e": {"value": audio_hours / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": int((f1 - f0) * 2), "d2h_bytes_per_step": d2h},
+           "result": {"troughs": int(out["troughs"].numel()), "peaks": int(out["peaks"].numel())}}
+    # rank 0: the same recording unchunked on one GPU -- parity and the time to beat
+    if rank == 0:
+        A = StageARunner([n], sr, params, want_filtered=False)
+        A.upload([pcm])
+        A.launch()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(3):
+            A.launch()
+        a1.record()
+        torch.cuda.synchronize()
+        one_ms = a0.elapsed_time(a1) / 3
+        nt, npk = int(A.out["trough_count"][0]), int(A.out["peak_count"][0])
+        c0, c1 = fe.chunks.core(0)
+
+        def rel(a, b):
+            return float((a - b).abs().max() / b.abs().max())
+
+        rec["one_gpu_unchunked_ms"] = one_ms
+        rec["speedup_vs_one_gpu_unchunked"] = one_ms / ms_step
+        rec["parity_vs_unchunked"] = {
+            "troughs": "exact" if torch.equal(out["troughs"], A.out["troughs"][:nt]) else "DIFFERENT",
+            "peaks": "exact" if torch.equal(out["peaks"], A.out["peaks"][:npk]) else "DIFFERENT",
+            "strength_rel": rel(out["strength"], A.out["strength"][:npk]) if out["strength"].numel() == npk else None,
+            "smoothed_dev_rel": rel(out["smoothed_dev"], A.out["smoothed_dev"][:max(npk - 1, 0)])
+            if out["smoothed_dev"].numel() == max(npk - 1, 0) else None,
+            "envelope_chunk_rel": rel(out["envelope_core"], A.out["envelope"][c0:c1]),
+            "floor_chunk_rel": rel(out["floor_core"], A.out["floor"][c0:c1])}
+        del A
+    return rec
 
 
 def run_stream(args):

@@ -78,8 +78,11 @@ _SIGNATURES = {
     "bpm_steepest_slope": (_I, [_P, _P, _P, _P, _P, _I, _I, _D, _P, _P, _Z, _P]),
     "bpm_windowed_hrv": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "bpm_cast_f32": (_I, [_P, _P, _L, _P]),
-    "bpm_key_histogram": (_I, [_P, _L, _I, _I, C.c_uint64, _P, _P]),
-    "bpm_key_collect": (_I, [_P, _L, _I, C.c_uint64, _L, _P, _P, _P]),
+    "bpm_key_histogram": (_I, [_P, _L, _I, _I, C.c_uint64, _P, _P, _P]),
+    "bpm_key_collect": (_I, [_P, _L, _I, C.c_uint64, _P, _L, _P, _P, _P]),
+    "bpm_key_pick": (_I, [_P, _I, _P, _P]),
+    "bpm_key_finish": (_I, [_P, _I, _L, _P, _D, _P, _P, _P]),
+    "bpm_chunk_proof": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _I, _I, _L, _I, _I, _P, _P]),
     "bpm_find_peaks_chunk": (_I, [_P, _I, _P, _P, _I, _P, _P, _L, _L, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "bpm_noise_floor_chunk_workspace_bytes": (_Z, [_L]),
     "bpm_noise_floor_chunk": (_I, [_P, _P, _P, _I, _P, _D, _I, _D, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),

@@ -24,8 +24,11 @@ constexpr int KH_MAXBINS = 2048;
 
 // hist[bin] += #{ i : (key(x_i) >> up) == prefix (or any, if up >= 64) and ((key(x_i) >> shift) & mask) == bin }
 __global__ void __launch_bounds__(KH_THREADS) k_key_hist(const double* __restrict__ x, int64_t n, int shift, int bits,
-                                                         unsigned long long prefix, unsigned long long* __restrict__ hist) {
+                                                         unsigned long long prefix,
+                                                         const unsigned long long* __restrict__ state,
+                                                         unsigned long long* __restrict__ hist) {
   __shared__ unsigned int s_hist[KH_MAXBINS];
+  if (state != nullptr) prefix = state[0];                      // the descent's state lives on the device
   const int nb = 1 << bits;
   for (int t = threadIdx.x; t < nb; t += KH_THREADS) s_hist[t] = 0;
   __syncthreads();
@@ -54,13 +57,16 @@ __global__ void __launch_bounds__(KH_THREADS) k_key_hist(const double* __restric
 }
 
 // keys whose leading digits equal `prefix` (key >> up == prefix) -> out_keys[0 .. min(count, cap)), count_min[0] += count,
-// count_min[1] = min(count_min[1], smallest key ABOVE the bucket)
+// count_min[1] = min(count_min[1], smallest key ABOVE the bucket), count_min[2] / [3] = smallest / largest key IN the
+// bucket (a bucket of one repeated value -- digital silence, clipping -- needs no ordering however large it is)
 __global__ void __launch_bounds__(KH_THREADS) k_key_collect(const double* __restrict__ x, int64_t n, int up,
-                                                            unsigned long long prefix, int64_t cap,
+                                                            unsigned long long prefix,
+                                                            const unsigned long long* __restrict__ state, int64_t cap,
                                                             unsigned long long* __restrict__ out_keys,
                                                             unsigned long long* __restrict__ count_min) {
-  __shared__ unsigned long long s_min[KH_THREADS / 32];
-  unsigned long long best = ~0ull;
+  __shared__ unsigned long long s_min[KH_THREADS / 32], s_lo[KH_THREADS / 32], s_hi[KH_THREADS / 32];
+  if (state != nullptr) prefix = state[0];
+  unsigned long long best = ~0ull, lo = ~0ull, hi = 0ull;
   const int64_t i0 = static_cast<int64_t>(blockIdx.x) * KH_THREADS * KH_PER;
   for (int k = 0; k < KH_PER; ++k) {
     const int64_t i = i0 + k * KH_THREADS + threadIdx.x;
@@ -70,6 +76,8 @@ __global__ void __launch_bounds__(KH_THREADS) k_key_collect(const double* __rest
     if (top == prefix) {
       const unsigned long long pos = atomicAdd(count_min, 1ull);
       if (static_cast<int64_t>(pos) < cap) out_keys[pos] = key;
+      lo = key < lo ? key : lo;
+      hi = key > hi ? key : hi;
     } else if (top > prefix && key < best) {
       best = key;
     }
@@ -78,13 +86,202 @@ __global__ void __launch_bounds__(KH_THREADS) k_key_collect(const double* __rest
   for (int o = 16; o; o >>= 1) {
     const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
     best = t < best ? t : best;
+    const unsigned long long tl = __shfl_xor_sync(0xffffffffu, lo, o);
+    lo = tl < lo ? tl : lo;
+    const unsigned long long th = __shfl_xor_sync(0xffffffffu, hi, o);
+    hi = th > hi ? th : hi;
   }
-  if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = best;
+  if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = best; s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < KH_THREADS / 32; ++w) best = s_min[w] < best ? s_min[w] : best;
+    for (int w = 1; w < KH_THREADS / 32; ++w) {
+      best = s_min[w] < best ? s_min[w] : best;
+      lo = s_lo[w] < lo ? s_lo[w] : lo;
+      hi = s_hi[w] > hi ? s_hi[w] : hi;
+    }
     if (best != ~0ull) atomicMin(count_min + 1, best);
+    if (lo != ~0ull) { atomicMin(count_min + 2, lo); atomicMax(count_min + 3, hi); }
   }
+}
+
+// One step of the descent on the device: the bin of the (summed) histogram that holds element `rank`
+// becomes the next digit.  state = {prefix, rank inside the bucket, bucket size}.
+constexpr int KP_THREADS = 256;
+__global__ void __launch_bounds__(KP_THREADS) k_key_pick(const unsigned long long* __restrict__ hist, int bits,
+                                                         unsigned long long* __restrict__ state) {
+  __shared__ unsigned long long s_part[KP_THREADS];
+  const int nb = 1 << bits;
+  const int per = (nb + KP_THREADS - 1) / KP_THREADS;
+  const int b0 = threadIdx.x * per;
+  unsigned long long sum = 0;
+  for (int u = 0; u < per; ++u) sum += (b0 + u < nb) ? hist[b0 + u] : 0ull;
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long run = 0;
+    for (int t = 0; t < KP_THREADS; ++t) { const unsigned long long v = s_part[t]; s_part[t] = run; run += v; }
+  }
+  __syncthreads();
+  const unsigned long long rank = state[1];
+  unsigned long long c = s_part[threadIdx.x];
+  __syncthreads();
+  if (rank >= c && rank < c + sum) {
+    for (int u = 0; u < per && b0 + u < nb; ++u) {
+      const unsigned long long h = hist[b0 + u];
+      if (rank < c + h) {
+        state[0] = (state[0] << bits) | static_cast<unsigned long long>(b0 + u);
+        state[1] = rank - c;
+        state[2] = h;
+        break;
+      }
+      c += h;
+    }
+  }
+}
+
+// The end of the descent: `rows` = per rank {count, smallest key above the bucket, smallest / largest key in it,
+// keys[cap]} (all-gathered);
+// the bucket's keys are ordered and the two order statistics around the virtual index interpolated the
+// way numpy does.  status: 0 fine, 1 = the bucket does not fit (the caller resolves more digits).
+constexpr int KF_THREADS = 512;
+constexpr int KF_CAP = 4096;
+__global__ void __launch_bounds__(KF_THREADS) k_key_finish(const unsigned long long* __restrict__ rows, int world, int64_t cap,
+                                                           const unsigned long long* __restrict__ state, double gamma,
+                                                           double* __restrict__ out, long long* __restrict__ status) {
+  __shared__ unsigned long long s_key[KF_CAP];
+  __shared__ int s_off[65];
+  const int tid = threadIdx.x;
+  const int64_t pitch = cap + 4;
+  unsigned long long above = ~0ull;
+  for (int r = 0; r < world; ++r) above = rows[r * pitch + 1] < above ? rows[r * pitch + 1] : above;
+  if (tid == 0) {
+    unsigned long long total64 = 0, lo = ~0ull, hi = 0ull;
+    for (int r = 0; r < world; ++r) {
+      const unsigned long long* row = rows + r * pitch;
+      total64 += row[0];
+      if (row[0]) { lo = row[2] < lo ? row[2] : lo; hi = row[3] > hi ? row[3] : hi; }
+    }
+    int verdict = 0;                                          // 0: order the bucket, -1: cannot, -2: one repeated value
+    if (total64 == 0 || total64 != state[2]) verdict = -1;
+    else if (lo == hi) {
+      verdict = -2;
+      const unsigned long long kb = (state[1] + 1 < total64) ? lo : (above != ~0ull ? above : lo);
+      s_key[0] = lo; s_key[1] = kb;
+    } else if (total64 > static_cast<unsigned long long>(KF_CAP) || world > 64) verdict = -1;
+    int run = 0;
+    for (int r = 0; r < world && verdict == 0; ++r) {
+      s_off[r] = run;
+      const unsigned long long c = rows[r * pitch];
+      if (c > static_cast<unsigned long long>(cap)) verdict = -1; else run += static_cast<int>(c);
+    }
+    s_off[64] = verdict == 0 ? run : verdict;
+  }
+  __syncthreads();
+  const int total = s_off[64];
+  if (total == -1) { if (tid == 0) *status = 1; return; }
+  if (total == -2) {
+    if (tid == 0) {
+      const double a = key_f64(s_key[0]), b = key_f64(s_key[1]);
+      const double diff = __dsub_rn(b, a);
+      double r = __dadd_rn(a, __dmul_rn(diff, gamma));
+      if (gamma >= 0.5) r = __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, gamma)));
+      *out = r;
+      *status = 0;
+    }
+    return;
+  }
+  for (int r = 0; r < world; ++r) {
+    const unsigned long long* row = rows + r * pitch;
+    const int c = static_cast<int>(row[0]), o = s_off[r];
+    for (int t = tid; t < c; t += KF_THREADS) s_key[o + t] = row[4 + t];
+  }
+  int P = 32;
+  while (P < total) P <<= 1;
+  for (int t = total + tid; t < P; t += KF_THREADS) s_key[t] = ~0ull;
+  __syncthreads();
+  for (int k2 = 2; k2 <= P; k2 <<= 1) {
+    for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+      for (int t = tid; t < P / 2; t += KF_THREADS) {
+        const int lo_i = ((t & ~(j2 - 1)) << 1) | (t & (j2 - 1));
+        const int hi_i = lo_i + j2;
+        const bool upw = ((lo_i & k2) == 0);
+        const unsigned long long a = s_key[lo_i], b = s_key[hi_i];
+        if ((a > b) == upw) { s_key[lo_i] = b; s_key[hi_i] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) {
+    const int rank = static_cast<int>(state[1]);
+    const unsigned long long ka = s_key[rank];
+    const unsigned long long kb = (rank + 1 < total) ? s_key[rank + 1] : (above != ~0ull ? above : ka);
+    const double a = key_f64(ka), b = key_f64(kb);
+    const double diff = __dsub_rn(b, a);
+    double r = __dadd_rn(a, __dmul_rn(diff, gamma));
+    if (gamma >= 0.5) r = __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, gamma)));
+    *out = r;
+    *status = 0;
+  }
+}
+
+// ---------------------------------------------------------------- the chunk's proof, on the device
+// (same obligations as ShardedFrontEnd._prove on the host; see bpm_b200.h)
+struct ProofGeom {
+  long long n, core_lo, core_hi, t_lo, t_hi;
+  int at_start, at_end;
+  long long filter_halo, distance, window;
+};
+
+__device__ long long lower_bound_ll(const int64_t* a, long long n, long long v) {      // first index with a[i] >= v
+  long long lo = 0, hi = n;
+  while (lo < hi) { const long long mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+// outputs rolling-quantile-over-np.interp(knots) that equal the stream's, given that the knot list is the
+// stream's inside [lo, hi)
+__device__ void proven_range(const int64_t* knots, long long count, long long lo, long long hi, const ProofGeom& g,
+                             long long* x_lo, long long* x_hi) {
+  const long long off = (g.window - 1) / 2, left = g.window - 1 - off;
+  const long long i0 = lower_bound_ll(knots, count, lo), i1 = lower_bound_ll(knots, count, hi);
+  if (i1 <= i0) {
+    const bool whole = g.at_start && g.at_end;
+    *x_lo = 0; *x_hi = whole ? g.n : 0;
+    return;
+  }
+  *x_lo = g.at_start ? 0 : knots[i0] + left;
+  *x_hi = g.at_end ? g.n : knots[i1 - 1] - off + 1;
+}
+
+// flags: {edge hits, trough anchors (left, right), peak anchors (left, right)}; counts: {kept, all, peaks}
+// out: {bad, all troughs in core, kept in core, peaks in core, first kept in core, first peak in core, x3 lo, x3 hi}
+__global__ void k_chunk_proof(const int64_t* __restrict__ every, const int64_t* __restrict__ kept,
+                              const int64_t* __restrict__ peaks, const long long* __restrict__ counts,
+                              const long long* __restrict__ flags, const long long* __restrict__ q_status, ProofGeom g,
+                              long long* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const long long n_kept = counts[0], n_all = counts[1], n_peaks = counts[2];
+  const long long d = g.distance;
+  bool ok = flags[0] == 0;
+  if (q_status != nullptr) ok = ok && q_status[0] == 0 && q_status[1] == 0;
+  if (d > 1) {
+    ok = ok && (g.at_start || flags[1] - d >= g.filter_halo);
+    ok = ok && (g.at_end || flags[2] + d <= g.n - g.filter_halo);
+  }
+  long long x2lo, x2hi, x3lo, x3hi;
+  proven_range(every, n_all, g.t_lo, g.t_hi, g, &x2lo, &x2hi);
+  proven_range(kept, n_kept, x2lo > g.t_lo ? x2lo : g.t_lo, x2hi < g.t_hi ? x2hi : g.t_hi, g, &x3lo, &x3hi);
+  ok = ok && x3lo <= g.core_lo && x3hi >= g.core_hi;
+  if (d > 1) {
+    ok = ok && (g.at_start || (flags[3] >= 0 && flags[3] - d >= x3lo));
+    ok = ok && (g.at_end || (flags[4] < g.n && flags[4] + d < x3hi));
+  }
+  const long long la = lower_bound_ll(every, n_all, g.core_lo), ha = lower_bound_ll(every, n_all, g.core_hi);
+  const long long lk = lower_bound_ll(kept, n_kept, g.core_lo), hk = lower_bound_ll(kept, n_kept, g.core_hi);
+  const long long lp = lower_bound_ll(peaks, n_peaks, g.core_lo), hp = lower_bound_ll(peaks, n_peaks, g.core_hi);
+  out[0] = ok ? 0 : 1;
+  out[1] = ha - la; out[2] = hk - lk; out[3] = hp - lp;
+  out[4] = lk; out[5] = lp; out[6] = x3lo; out[7] = x3hi;
 }
 
 }  // namespace bpm
@@ -93,28 +290,68 @@ using namespace bpm;
 
 extern "C" {
 
-int bpm_key_histogram(const double* x, int64_t n, int shift, int bits, uint64_t prefix, uint64_t* hist, void* stream) {
+int bpm_key_histogram(const double* x, int64_t n, int shift, int bits, uint64_t prefix, const uint64_t* state,
+                      uint64_t* hist, void* stream) {
   if (!hist || n < 0 || bits < 1 || bits > 11 || shift < 0 || shift + bits > 64) return BPM_ERR_ARG;
   if (n == 0) return BPM_OK;                      // a rank without samples contributes nothing
   if (!x) return BPM_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BPM_KERNEL(k_key_hist);
-  k_key_hist<<<cdiv(n, KH_THREADS * KH_PER), KH_THREADS, 0, st>>>(x, n, shift, bits, prefix,
-                                                                  reinterpret_cast<unsigned long long*>(hist));
+  k_key_hist<<<cdiv(n, KH_THREADS * KH_PER), KH_THREADS, 0, st>>>(
+      x, n, shift, bits, prefix, reinterpret_cast<const unsigned long long*>(state),
+      reinterpret_cast<unsigned long long*>(hist));
   BPM_LAUNCH_OK();
   return BPM_OK;
 }
 
-int bpm_key_collect(const double* x, int64_t n, int up_shift, uint64_t prefix, int64_t cap, uint64_t* out_keys,
-                    uint64_t* count_min, void* stream) {
+int bpm_key_collect(const double* x, int64_t n, int up_shift, uint64_t prefix, const uint64_t* state, int64_t cap,
+                    uint64_t* out_keys, uint64_t* count_min, void* stream) {
   if (!out_keys || !count_min || n < 0 || cap < 0 || up_shift < 0 || up_shift > 63) return BPM_ERR_ARG;
   if (n == 0) return BPM_OK;
   if (!x) return BPM_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BPM_KERNEL(k_key_collect);
   k_key_collect<<<cdiv(n, KH_THREADS * KH_PER), KH_THREADS, 0, st>>>(
-      x, n, up_shift, prefix, cap, reinterpret_cast<unsigned long long*>(out_keys),
-      reinterpret_cast<unsigned long long*>(count_min));
+      x, n, up_shift, prefix, reinterpret_cast<const unsigned long long*>(state), cap,
+      reinterpret_cast<unsigned long long*>(out_keys), reinterpret_cast<unsigned long long*>(count_min));
+  BPM_LAUNCH_OK();
+  return BPM_OK;
+}
+
+int bpm_key_pick(const uint64_t* hist, int bits, uint64_t* state, void* stream) {
+  if (!hist || !state || bits < 1 || bits > 11) return BPM_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BPM_KERNEL(k_key_pick);
+  k_key_pick<<<1, KP_THREADS, 0, st>>>(
+      reinterpret_cast<const unsigned long long*>(hist), bits, reinterpret_cast<unsigned long long*>(state));
+  BPM_LAUNCH_OK();
+  return BPM_OK;
+}
+
+int bpm_key_finish(const uint64_t* rows, int world, int64_t cap, const uint64_t* state, double gamma, double* out,
+                   int64_t* status, void* stream) {
+  if (!rows || !state || !out || !status || world < 1 || cap < 1) return BPM_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BPM_KERNEL(k_key_finish);
+  k_key_finish<<<1, KF_THREADS, 0, st>>>(
+      reinterpret_cast<const unsigned long long*>(rows), world, cap, reinterpret_cast<const unsigned long long*>(state),
+      gamma, out, reinterpret_cast<long long*>(status));
+  BPM_LAUNCH_OK();
+  return BPM_OK;
+}
+
+int bpm_chunk_proof(const int64_t* all_troughs, const int64_t* kept_troughs, const int64_t* peaks, const int64_t* counts,
+                    const int64_t* flags, const int64_t* quantile_status, int64_t n, int64_t core_lo, int64_t core_hi,
+                    int64_t trough_lo, int64_t trough_hi, int at_start, int at_end, int64_t filter_halo, int distance,
+                    int window, int64_t* out, void* stream) {
+  if (!all_troughs || !kept_troughs || !peaks || !counts || !flags || !out) return BPM_ERR_ARG;
+  const ProofGeom g{n, core_lo, core_hi, trough_lo, trough_hi, at_start, at_end, filter_halo, distance, window};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BPM_KERNEL(k_chunk_proof);
+  k_chunk_proof<<<1, 32, 0, st>>>(
+      all_troughs, kept_troughs, peaks, reinterpret_cast<const long long*>(counts),
+      reinterpret_cast<const long long*>(flags), reinterpret_cast<const long long*>(quantile_status), g,
+      reinterpret_cast<long long*>(out));
   BPM_LAUNCH_OK();
   return BPM_OK;
 }

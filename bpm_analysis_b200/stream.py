@@ -142,9 +142,9 @@ class DistComm:
         """Equal-size rows, one per rank -> (world, len) tensor."""
         if self.world == 1:
             return t[None]
-        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        self._dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
-        return out
+        out = torch.empty(self.world * t.numel(), dtype=t.dtype, device=t.device)
+        self._dist.all_gather_into_tensor(out, t.contiguous().view(-1), group=self.group)
+        return out.view((self.world,) + tuple(t.shape))
 
 
 class ThreadComm:
@@ -223,15 +223,22 @@ class DeviceEngine:
         self.nat, self.rt = nat, runtime
         self.device = runtime.require_cuda()
         self.lib = nat.load_library()
+        self._item_cache: Dict[Tuple[int, int], tuple] = {}
 
     # helpers
     def _ws(self, nbytes: int) -> torch.Tensor:
         return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
 
     def _items(self, n_in: int, m: int):
-        items = self.rt.make_items([n_in], [m])
-        dev = torch.from_numpy(items.view(np.int64).reshape(-1, 4).copy()).to(self.device)
-        return items, dev
+        """(host, device) descriptor of one recording; cached (read-only, a handful of shapes per run)"""
+        got = self._item_cache.get((n_in, m))
+        if got is None:
+            items = self.rt.make_items([n_in], [m])
+            dev = torch.from_numpy(items.view(np.int64).reshape(-1, 4).copy()).to(self.device)
+            if len(self._item_cache) > 256:
+                self._item_cache.clear()
+            got = self._item_cache[(n_in, m)] = (items, dev)
+        return got
 
     def tensor(self, a: np.ndarray) -> torch.Tensor:
         return self.rt.to_device(np.asarray(a))
@@ -364,78 +371,76 @@ class DeviceEngine:
 
 
     # ---- chunk mode (ShardedFrontEnd): nothing here synchronises the host
-    def key_histogram(self, x: torch.Tensor, shift: int, bits: int, prefix: int) -> torch.Tensor:
-        hist = torch.zeros(1 << bits, dtype=torch.int64, device=self.device)
-        self.nat.check(self.lib.bpm_key_histogram(self.rt._ptr(x), x.numel(), int(shift), int(bits), int(prefix),
-                                                  self.rt._ptr(hist), self.rt._stream_ptr()))
-        return hist
+    def key_state(self, n_total: int, k: int) -> torch.Tensor:
+        return torch.tensor([0, int(k), int(n_total)], dtype=torch.int64, device=self.device)
 
-    def key_collect(self, x: torch.Tensor, up_shift: int, prefix: int, cap: int) -> torch.Tensor:
-        """-> int64[cap + 2] (bit patterns of uint64): [count, smallest key above the bucket, keys...]"""
-        out = torch.zeros(cap + 2, dtype=torch.int64, device=self.device)
-        out[1] = -1                                              # ~0 as uint64
+    def key_histogram(self, x: torch.Tensor, shift: int, bits: int, state: torch.Tensor, hist: torch.Tensor) -> None:
+        self.nat.check(self.lib.bpm_key_histogram(self.rt._ptr(x), x.numel(), int(shift), int(bits), 0,
+                                                  self.rt._ptr(state), self.rt._ptr(hist), self.rt._stream_ptr()))
+
+    def key_pick(self, hist: torch.Tensor, bits: int, state: torch.Tensor) -> None:
+        self.nat.check(self.lib.bpm_key_pick(self.rt._ptr(hist), int(bits), self.rt._ptr(state), self.rt._stream_ptr()))
+
+    def key_collect(self, x: torch.Tensor, up_shift: int, state: torch.Tensor, cap: int) -> torch.Tensor:
+        """-> int64[cap + 4] (bit patterns of uint64): [count, smallest key above the bucket, smallest and
+        largest key in it, keys...]"""
+        out = torch.zeros(cap + 4, dtype=torch.int64, device=self.device)
+        out[1:3] = -1                                            # ~0 as uint64
         base = out.data_ptr()
-        self.nat.check(self.lib.bpm_key_collect(self.rt._ptr(x), x.numel(), int(up_shift), int(prefix), int(cap),
-                                                C.c_void_p(base + 16), C.c_void_p(base), self.rt._stream_ptr()))
+        self.nat.check(self.lib.bpm_key_collect(self.rt._ptr(x), x.numel(), int(up_shift), 0, self.rt._ptr(state),
+                                                int(cap), C.c_void_p(base + 32), C.c_void_p(base),
+                                                self.rt._stream_ptr()))
         return out
 
-    def chunk_flags(self) -> torch.Tensor:
-        """[edge hits, trough anchors (left, right), peak anchors (left, right)] preset for a chunk call."""
-        big = np.iinfo(np.int64).max
-        return torch.tensor([0, -1, big, -1, big], dtype=torch.int64, device=self.device)
+    def key_finish(self, rows: torch.Tensor, cap: int, state: torch.Tensor, gamma: float, out: torch.Tensor,
+                   status: torch.Tensor) -> None:
+        self.nat.check(self.lib.bpm_key_finish(self.rt._ptr(rows), int(rows.shape[0]), int(cap), self.rt._ptr(state),
+                                               float(gamma), self.rt._ptr(out), self.rt._ptr(status),
+                                               self.rt._stream_ptr()))
 
-    def noise_floor_chunk(self, env: torch.Tensor, distance: int, q_tp: torch.Tensor, window: int, params: Dict,
-                          core: Tuple[int, int], open_ends: Tuple[bool, bool], flags: torch.Tensor):
-        """-> floor, kept troughs (buffer), all troughs (buffer), counts int64[2] = (kept, all)"""
-        rt, L = self.rt, self.lib
-        n = env.numel()
-        items, items_dev = self._items(n, n)
-        floor = torch.empty(n, dtype=torch.float64, device=self.device)
-        kept = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
-        every = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
-        cnt = torch.zeros(2, dtype=torch.int64, device=self.device)
-        nb = int(L.bpm_noise_floor_chunk_workspace_bytes(n))
-        ws = self._ws(nb)
-        fb, cb = flags.data_ptr(), cnt.data_ptr()
-        self.nat.check(L.bpm_noise_floor_chunk(rt._ptr(env), rt._ptr(items_dev), rt._host_ptr(items), int(distance),
-                                               rt._ptr(q_tp), float(params["noise_floor_quantile"]), int(window),
-                                               float(params.get("trough_rejection_multiplier", 4.0)),
-                                               int(core[0]), int(core[1]), int(open_ends[0]), int(open_ends[1]),
-                                               rt._ptr(floor), rt._ptr(kept), C.c_void_p(cb), rt._ptr(every),
-                                               C.c_void_p(cb + 8), C.c_void_p(fb), C.c_void_p(fb + 8), rt._ptr(ws), nb,
-                                               rt._stream_ptr()))
-        self._keep_chunk = (ws, items_dev)
-        return floor, kept, every, cnt
-
-    def find_peaks_chunk(self, x: torch.Tensor, sign: int, height: Optional[torch.Tensor], prominence: torch.Tensor,
-                         distance: int, core: Tuple[int, int], open_ends: Tuple[bool, bool], flags: torch.Tensor):
-        rt, L = self.rt, self.lib
-        n = x.numel()
-        items, items_dev = self._items(n, n)
-        idx = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
-        cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
-        nb = int(L.bpm_find_peaks_workspace_bytes(n, 1))
-        ws = self._ws(nb)
-        fb = flags.data_ptr()
-        self.nat.check(L.bpm_find_peaks_chunk(rt._ptr(x), int(sign), rt._ptr(height), rt._ptr(prominence), int(distance),
-                                              rt._ptr(items_dev), rt._host_ptr(items), int(core[0]), int(core[1]),
-                                              int(open_ends[0]), int(open_ends[1]), rt._ptr(idx), rt._ptr(cnt),
-                                              C.c_void_p(fb), C.c_void_p(fb + 24), rt._ptr(ws), nb, rt._stream_ptr()))
-        self._keep_peaks = (ws, items_dev)
-        return idx, cnt
-
-    def peak_strength(self, env: torch.Tensor, floor: torch.Tensor, peaks: torch.Tensor, count: torch.Tensor) -> torch.Tensor:
-        """strength of the first ``count`` entries of a peak buffer (:95); no host synchronisation"""
-        rt, L = self.rt, self.lib
+    def chunk_chain(self, env: torch.Tensor, thr: torch.Tensor, qstat: torch.Tensor, geom: "ChunkGeometry",
+                    params: Dict) -> Dict[str, torch.Tensor]:
+        """a2 + a3 + strength (:95) of one chunk + halo and the chunk's proof, enqueued back to back.
+        thr = (trough, peak) prominence thresholds on the device."""
+        rt, L, nat = self.rt, self.lib, self.nat
         n = env.numel()
         items, items_dev = self._items(n, n)
         f64 = dict(dtype=torch.float64, device=self.device)
-        st, dv, sm = torch.empty(n, **f64), torch.empty(2 * n, **f64), torch.empty(n, **f64)
-        self.nat.check(L.bpm_peak_metrics(rt._ptr(env), rt._ptr(floor), rt._ptr(peaks), rt._ptr(count),
-                                          rt._ptr(items_dev), rt._host_ptr(items), 1, 0.05, rt._ptr(st), rt._ptr(dv),
-                                          rt._ptr(sm), rt._stream_ptr()))
-        self._keep_strength = (items_dev, dv, sm)
-        return st
+        i64 = dict(dtype=torch.int64, device=self.device)
+        floor, strength = torch.empty(n, **f64), torch.empty(n, **f64)
+        scratch = torch.empty(3 * n, **f64)                       # deviation (2n) + smoothed (n): not used per chunk
+        kept, every, peaks = torch.empty(n, **i64), torch.empty(n, **i64), torch.empty(n, **i64)
+        big = np.iinfo(np.int64).max
+        # counts {kept, all, peaks} | flags {edge hits, trough anchors l/r, peak anchors l/r} | proof[8]
+        head = torch.tensor([0, 0, 0, 0, -1, big, -1, big, 0, 0, 0, 0, 0, 0, 0, 0], **i64)
+        hb = head.data_ptr()
+        cnt, flg, prf = hb, hb + 24, hb + 64
+        nb = max(int(L.bpm_noise_floor_chunk_workspace_bytes(n)), int(L.bpm_find_peaks_workspace_bytes(n, 1)))
+        ws = self._ws(nb)
+        st = rt._stream_ptr()
+        thr_p = thr.data_ptr()
+        ends = (int(not geom.at_start), int(not geom.at_end))
+        nat.check(L.bpm_noise_floor_chunk(rt._ptr(env), rt._ptr(items_dev), rt._host_ptr(items), int(geom.distance),
+                                          C.c_void_p(thr_p), float(params["noise_floor_quantile"]), int(geom.window),
+                                          float(params.get("trough_rejection_multiplier", 4.0)),
+                                          int(geom.t_lo), int(geom.t_hi), ends[0], ends[1], rt._ptr(floor), rt._ptr(kept),
+                                          C.c_void_p(cnt), rt._ptr(every), C.c_void_p(cnt + 8), C.c_void_p(flg),
+                                          C.c_void_p(flg + 8), rt._ptr(ws), nb, st))
+        nat.check(L.bpm_find_peaks_chunk(rt._ptr(env), 1, rt._ptr(floor), C.c_void_p(thr_p + 8), int(geom.distance),
+                                         rt._ptr(items_dev), rt._host_ptr(items), int(geom.core_lo), int(geom.core_hi),
+                                         ends[0], ends[1], rt._ptr(peaks), C.c_void_p(cnt + 16), C.c_void_p(flg),
+                                         C.c_void_p(flg + 24), rt._ptr(ws), nb, st))
+        sb = scratch.data_ptr()
+        nat.check(L.bpm_peak_metrics(rt._ptr(env), rt._ptr(floor), rt._ptr(peaks), C.c_void_p(cnt + 16),
+                                     rt._ptr(items_dev), rt._host_ptr(items), 1, 0.05, rt._ptr(strength),
+                                     C.c_void_p(sb), C.c_void_p(sb + 16 * n), st))
+        nat.check(L.bpm_chunk_proof(rt._ptr(every), rt._ptr(kept), rt._ptr(peaks), C.c_void_p(cnt), C.c_void_p(flg),
+                                    rt._ptr(qstat), n, int(geom.core_lo), int(geom.core_hi), int(geom.t_lo),
+                                    int(geom.t_hi), int(geom.at_start), int(geom.at_end), int(geom.filter_halo),
+                                    int(geom.distance), int(geom.window), C.c_void_p(prf), st))
+        self._keep_chunk = (ws, items_dev, scratch)
+        return {"floor": floor, "kept": kept, "every": every, "peaks": peaks, "strength": strength,
+                "head": head, "proof": head[8:16]}
 
     def deviation_series(self, strength: torch.Tensor, factor: float):
         """deviation and its rolling mean (:96-100) of a whole strength list"""
@@ -458,60 +463,62 @@ class DeviceEngine:
 
 # --------------------------------------------------------------------------- stream-wide order statistics
 KEY_PASSES = ((53, 11), (42, 11), (31, 11), (20, 11), (9, 11), (0, 9))     # (shift, bits), most significant first
-COLLECT_CAP = 4096
+DESCENT_PASSES = 3               # digits resolved before the bucket is gathered: sign + exponent + 21 mantissa bits
+COLLECT_CAP = 4096               # keys a rank contributes to the final bucket (and the bucket's limit)
 
 
-def _key_to_f64(k: int) -> float:
-    b = (k & 0x7FFFFFFFFFFFFFFF) if (k >> 63) else (~k & 0xFFFFFFFFFFFFFFFF)
-    return float(np.array([b], dtype=np.uint64).view(np.float64)[0])
+def quantile_position(n_total: int, q: float) -> Tuple[int, float]:
+    """numpy's virtual index (linear method): element k and the fraction towards element k + 1."""
+    v = np.float64(n_total - 1) * np.float64(q)
+    k = int(min(max(np.floor(v), 0), n_total - 1))
+    return k, float(v - np.floor(v))
 
 
-def _np_lerp(a: float, b: float, t: float) -> float:
-    """numpy's _lerp (lib/_function_base_impl.py) on two scalars, operation for operation."""
-    a, b, t = np.float64(a), np.float64(b), np.float64(t)
-    diff = b - a
-    r = a + diff * t
-    if t >= 0.5:
-        r = b - diff * (np.float64(1.0) - t)
-    return float(r)
-
-
-def stream_quantile(engine, comm, x_core: torch.Tensor, n_total: int, q: float) -> float:
-    """np.quantile(x, q) (linear method) of a series whose samples are spread over the ranks
-    (each rank passes ITS samples, every sample on exactly one rank): a radix descent over the
-    order-preserving 64-bit keys with the per-digit histograms summed over the ranks, then the
-    few keys left in the bucket are gathered and sorted.  Every rank returns the same float."""
+def stream_quantiles(engine, comm, x_core: torch.Tensor, n_total: int, qs: Sequence[float]):
+    """np.quantile(x, q) (linear method) for each q of a series whose samples are spread over the
+    ranks (each rank passes ITS samples, every sample on exactly one rank): a radix descent over
+    the order-preserving 64-bit keys with the per-digit histograms summed over the ranks, then
+    the few keys left in the bucket are gathered and ordered.  Everything is enqueued -- the
+    descent's state lives on the device -- and every rank ends up with the same values.
+    -> (values float64[len(qs)], status int64[len(qs)]: nonzero = bucket too large, value invalid)"""
     if n_total < 1:
         raise ValueError("quantile of an empty stream")
-    v = np.float64(n_total - 1) * np.float64(q)                 # numpy's virtual index
-    k = int(min(max(np.floor(v), 0), n_total - 1))
-    gamma = float(v - np.floor(v))
-    prefix, rank, count, up = 0, k, n_total, 64
-    for shift, bits in KEY_PASSES:
-        hist = comm.all_reduce_sum(engine.key_histogram(x_core, shift, bits, prefix))
-        h = hist.cpu().numpy()
-        c = np.cumsum(h)
-        b = int(np.searchsorted(c, rank, side="right"))
-        rank -= int(c[b - 1]) if b else 0
-        count = int(h[b])
-        prefix = (prefix << bits) | b
-        up = shift
-        if count <= COLLECT_CAP:
-            break
-    # keys in the bucket (all equal when every digit is resolved) and the smallest key above it
-    cap = COLLECT_CAP if up > 0 else 0
-    got = comm.all_gather_rows(engine.key_collect(x_core, up, prefix, cap)).cpu().numpy().view(np.uint64)
-    above = int(got[:, 1].min())
-    if up > 0:
-        keys = np.sort(np.concatenate([row[2:2 + int(row[0])] for row in got]))
-        if len(keys) != count:
-            raise RuntimeError("stream_quantile: bucket size disagrees with its histogram")
-        ka = int(keys[rank])
-        kb = int(keys[rank + 1]) if rank + 1 < count else (above if above != 0xFFFFFFFFFFFFFFFF else ka)
-    else:
-        ka = prefix
-        kb = ka if rank + 1 < count else (above if above != 0xFFFFFFFFFFFFFFFF else ka)
-    return _np_lerp(_key_to_f64(ka), _key_to_f64(kb), gamma)
+    nq = len(qs)
+    out = torch.zeros(nq, dtype=torch.float64, device=x_core.device)
+    status = torch.ones(nq, dtype=torch.int64, device=x_core.device)
+    pos = [quantile_position(n_total, q) for q in qs]
+    states = [engine.key_state(n_total, k) for k, _ in pos]
+    for p in range(DESCENT_PASSES):
+        shift, bits = KEY_PASSES[p]
+        hist = torch.zeros((nq, 1 << bits), dtype=torch.int64, device=x_core.device)
+        for i in range(nq if p else 1):                          # the first digit's histogram is the same for all
+            engine.key_histogram(x_core, shift, bits, states[i], hist[i])
+        if p == 0 and nq > 1:
+            hist[1:] = hist[0]
+        comm.all_reduce_sum(hist)
+        for i in range(nq):
+            engine.key_pick(hist[i], bits, states[i])
+    up = KEY_PASSES[DESCENT_PASSES - 1][0]
+    mine = torch.stack([engine.key_collect(x_core, up, states[i], COLLECT_CAP) for i in range(nq)])
+    rows = comm.all_gather_rows(mine)                            # (world, nq, cap + 4)
+    for i in range(nq):
+        engine.key_finish(rows[:, i].contiguous(), COLLECT_CAP, states[i], pos[i][1], out[i:i + 1], status[i:i + 1])
+    return out, status
+
+
+@dataclass(frozen=True)
+class ChunkGeometry:
+    """One rank's chunk in indices local to its extended range [0, n)."""
+    n: int
+    core_lo: int
+    core_hi: int
+    t_lo: int            # the range the trough list is claimed on
+    t_hi: int
+    at_start: bool
+    at_end: bool
+    filter_halo: int
+    distance: int
+    window: int
 
 
 # --------------------------------------------------------------------------- the chunked front end
@@ -670,73 +677,52 @@ class ShardedFrontEnd(ChunkedFrontEnd):
         ch = self.chunks
         self.chunks = ChunkPlan(ch.n_frames, ch.m, ch.frames_per_sample, self.filter_halo + self.analysis_halo, ch.world)
 
-    # -- proof obligations, on the host, from the chunk's own lists (indices local to the ext range)
-    def _proven_range(self, knots: np.ndarray, lo: int, hi: int, at_start: bool, at_end: bool, n: int) -> Tuple[int, int]:
-        """Outputs of a rolling quantile over np.interp(knots) that equal the stream's, given that the
-        knot list is the stream's inside [lo, hi)."""
-        off = (self.window - 1) // 2
-        left = self.window - 1 - off
-        k = knots[(knots >= lo) & (knots < hi)]
-        if len(k) == 0:
-            return (0, 0) if not (at_start and at_end) else (0, n)
-        return (0 if at_start else int(k[0]) + left), (n if at_end else int(k[-1]) - off + 1)
-
-    def analyse_sharded(self, env_ext: torch.Tensor) -> Optional[Dict[str, torch.Tensor]]:
-        """Per-chunk evaluation; None if some rank could not prove its chunk."""
-        E, P, ch, comm = self.engine, self.params, self.chunks, self.comm
-        (c0, c1), (e0, e1) = ch.core(comm.rank), ch.ext(comm.rank)
+    def geometry(self) -> ChunkGeometry:
+        ch, r = self.chunks, self.comm.rank
+        (c0, c1), (e0, e1) = ch.core(r), ch.ext(r)
         n = e1 - e0
         at_start, at_end = e0 == 0, e1 == ch.m
-        open_ends = (not at_start, not at_end)
-        core = (c0 - e0, c1 - e0)
-        env_core = env_ext[core[0]:core[1]]
-        # stream-wide thresholds (:1067, :225)
-        q_tp = stream_quantile(E, comm, env_core, ch.m, float(P["trough_prominence_quantile"]))
-        q_pp = q_tp if P["peak_prominence_quantile"] == P["trough_prominence_quantile"] else \
-            stream_quantile(E, comm, env_core, ch.m, float(P["peak_prominence_quantile"]))
-        thr = torch.tensor([q_tp, q_pp], dtype=torch.float64, device=env_ext.device)
-        # the whole per-chunk chain, enqueued without a host synchronisation
         doubt = self.filter_halo + self.margin                   # zone next to an open end nothing is claimed about
-        t_core = (0 if at_start else doubt, n if at_end else n - doubt)
-        flags = E.chunk_flags()
-        floor, kept, every, tcnt = E.noise_floor_chunk(env_ext, self.distance, thr[0:1], self.window, P, t_core,
-                                                       open_ends, flags)
-        peaks, pcnt = E.find_peaks_chunk(env_ext, +1, floor, thr[1:2], self.distance, core, open_ends, flags)
-        strength = E.peak_strength(env_ext, floor, peaks, pcnt)
-        head = torch.cat([flags, tcnt, pcnt]).cpu().numpy()      # the chunk's one wait for the device
-        edge_hits, ta0, ta1, pa0, pa1, n_kept, n_all, n_peaks = (int(v) for v in head)
-        lists = torch.cat([every[:n_all], kept[:n_kept], peaks[:n_peaks]]).cpu().numpy()
-        every_h, kept_h, peaks_h = lists[:n_all], lists[n_all:n_all + n_kept], lists[n_all + n_kept:]
-        d = self.distance
-        ok = edge_hits == 0
-        # trough list proven on t_core: an anchor between each doubtful zone and t_core
-        if d > 1:
-            ok &= at_start or ta0 - d >= self.filter_halo
-            ok &= at_end or ta1 + d <= n - self.filter_halo
-        x2 = self._proven_range(every_h, t_core[0], t_core[1], at_start, at_end, n)       # draft floor
-        x3 = self._proven_range(kept_h, max(x2[0], t_core[0]), min(x2[1], t_core[1]), at_start, at_end, n)  # final floor
-        # peaks: candidates (height = floor) are the stream's on x3; an anchor inside it on each open side
-        ok &= x3[0] <= core[0] and x3[1] >= core[1]
-        if d > 1:
-            ok &= at_start or (pa0 >= 0 and pa0 - d >= x3[0])
-            ok &= at_end or (pa1 < n and pa1 + d < x3[1])
-        lo_a, hi_a = np.searchsorted(every_h, core)
-        lo_k, hi_k = np.searchsorted(kept_h, core)
-        lo_p, hi_p = np.searchsorted(peaks_h, core)
-        mine = torch.tensor([0 if ok else 1, hi_a - lo_a, hi_k - lo_k, hi_p - lo_p], dtype=torch.int64,
-                            device=env_ext.device)
-        table = comm.all_gather_rows(mine).cpu().numpy()
-        self.last_proof = {"ok": bool(ok), "edge_hits": edge_hits, "proven_floor": (x3[0] + e0, x3[1] + e0),
-                           "trough_anchors": (ta0, ta1), "peak_anchors": (pa0, pa1)}
+        return ChunkGeometry(n, c0 - e0, c1 - e0, 0 if at_start else doubt, n if at_end else n - doubt, at_start,
+                             at_end, self.filter_halo, self.distance, self.window)
+
+    def analyse_sharded(self, env_ext: torch.Tensor) -> Optional[Dict[str, torch.Tensor]]:
+        """Per-chunk evaluation; None if some rank could not prove its chunk.  The host waits for the
+        device ONCE (for the table of proofs and list lengths of all ranks)."""
+        E, P, ch, comm = self.engine, self.params, self.chunks, self.comm
+        e0 = ch.ext(comm.rank)[0]
+        g = self.geometry()
+        env_core = env_ext[g.core_lo:g.core_hi]
+        # stream-wide thresholds (:1067, :225)
+        q_t, q_p = float(P["trough_prominence_quantile"]), float(P["peak_prominence_quantile"])
+        if q_t == q_p:
+            one, qstat = stream_quantiles(E, comm, env_core, ch.m, [q_t])
+            thr, qstat = one.repeat(2), qstat.repeat(2)
+        else:
+            thr, qstat = stream_quantiles(E, comm, env_core, ch.m, [q_t, q_p])
+        c = E.chunk_chain(env_ext, thr, qstat, g, P)
+        table = comm.all_gather_rows(c["proof"]).cpu().numpy()    # the chunk's one wait for the device
+        mine = table[comm.rank]
+        self.last_proof = {"ok": not bool(mine[0]), "proven_floor": (int(mine[6]) + e0, int(mine[7]) + e0),
+                           "table": table}
         if table[:, 0].any() or table[:, 1].sum() < MIN_TROUGHS or table[:, 2].sum() <= MIN_KEPT:
             return None
-        troughs = torch.cat(comm.all_gather(kept[lo_k:hi_k] + e0, [int(v) for v in table[:, 2]]))
-        sizes_p = [int(v) for v in table[:, 3]]
-        peaks_all = torch.cat(comm.all_gather(peaks[lo_p:hi_p] + e0, sizes_p))
-        strength_all = torch.cat(comm.all_gather(strength[lo_p:hi_p].contiguous(), sizes_p))
+        # ONE exchange for the three lists: [kept troughs | peaks | strength bits], padded to the longest
+        nk, npk, lk, lp = (int(v) for v in mine[2:6])
+        cap_t, cap_p = int(table[:, 2].max()), int(table[:, 3].max())
+        pack = torch.zeros(cap_t + 2 * cap_p, dtype=torch.int64, device=env_ext.device)
+        pack[:nk] = c["kept"][lk:lk + nk] + e0
+        pack[cap_t:cap_t + npk] = c["peaks"][lp:lp + npk] + e0
+        pack[cap_t + cap_p:cap_t + cap_p + npk] = c["strength"][lp:lp + npk].view(torch.int64)
+        rows = comm.all_gather_rows(pack)
+        world = comm.world
+        troughs = torch.cat([rows[r, :int(table[r, 2])] for r in range(world)])
+        peaks_all = torch.cat([rows[r, cap_t:cap_t + int(table[r, 3])] for r in range(world)])
+        strength_all = torch.cat([rows[r, cap_t + cap_p:cap_t + cap_p + int(table[r, 3])] for r in range(world)]
+                                 ).view(torch.float64)
         deviation, smoothed = E.deviation_series(strength_all, float(P["deviation_smoothing_factor"]))
         return {"troughs": troughs, "peaks": peaks_all, "strength": strength_all, "deviation": deviation,
-                "smoothed_dev": smoothed, "envelope_core": env_core, "floor_core": floor[core[0]:core[1]],
+                "smoothed_dev": smoothed, "envelope_core": env_core, "floor_core": c["floor"][g.core_lo:g.core_hi],
                 "thresholds": thr}
 
     def analyse_local(self, env_ext: torch.Tensor, gather_series: bool = False) -> Dict[str, torch.Tensor]:

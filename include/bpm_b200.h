@@ -246,11 +246,26 @@ int bpm_windowed_hrv(const int64_t* beats, const BpmItem* lists, const BpmItem* 
  *   (k >> (shift + bits)) == prefix  (every sample when shift + bits == 64)  and  ((k >> shift) & (2^bits - 1)) == b;
  *   hist: uint64[2^bits], accumulated (zero it first), bits <= 11.
  * bpm_key_collect: keys with (k >> up_shift) == prefix -> out_keys (first `cap` of them), count_min[0] += their
- *   number, count_min[1] = min(count_min[1], smallest key above the bucket)  (preset count_min = {0, ~0}).
- * The key of a double v: bits(v) with the sign bit set for v >= 0, all bits flipped for v < 0. */
-int bpm_key_histogram(const double* x, int64_t n, int shift, int bits, uint64_t prefix, uint64_t* hist, void* stream);
-int bpm_key_collect(const double* x, int64_t n, int up_shift, uint64_t prefix, int64_t cap, uint64_t* out_keys,
-                    uint64_t* count_min, void* stream);
+ *   number, count_min[1] = min(.., smallest key above the bucket), count_min[2] / [3] = smallest / largest key
+ *   in the bucket  (preset count_min = {0, ~0, ~0, 0}).
+ * The key of a double v: bits(v) with the sign bit set for v >= 0, all bits flipped for v < 0.
+ * `state` (device, uint64[3] = {prefix, rank inside the bucket, bucket size}; may be NULL): when given,
+ * the prefix is read from it instead of the argument, so that a whole descent -- histogram, all-reduce,
+ * bpm_key_pick, ..., bpm_key_collect, all-gather, bpm_key_finish -- is enqueued without the host ever
+ * waiting for the device.  Start it as {0, k, n} with k = floor((n - 1) q).
+ * bpm_key_pick: the bin of the summed histogram that holds element `rank` becomes the next digit.
+ * bpm_key_finish: rows = per rank {count, smallest key above, smallest, largest key in the bucket, keys[cap]}
+ *   (the bpm_key_collect outputs, all-gathered, `cap + 4` words each); orders the bucket and writes numpy's
+ *   linear-method quantile for the fraction gamma = (n - 1) q - k.  A bucket of ONE repeated value (digital
+ *   silence) is resolved whatever its size; *status = 1 if the bucket holds more than 4096 distinct-looking
+ *   keys (resolve another digit first). */
+int bpm_key_histogram(const double* x, int64_t n, int shift, int bits, uint64_t prefix, const uint64_t* state,
+                      uint64_t* hist, void* stream);
+int bpm_key_collect(const double* x, int64_t n, int up_shift, uint64_t prefix, const uint64_t* state, int64_t cap,
+                    uint64_t* out_keys, uint64_t* count_min, void* stream);
+int bpm_key_pick(const uint64_t* hist, int bits, uint64_t* state, void* stream);
+int bpm_key_finish(const uint64_t* rows, int world, int64_t cap, const uint64_t* state, double gamma, double* out,
+                   int64_t* status, void* stream);
 
 /* find_peaks on a chunk [ext_lo, ext_hi) of a stream (one recording per call).  core_lo / core_hi: the part
  * of the chunk (chunk-relative indices) whose peaks the caller keeps; open_left / open_right: that end of
@@ -278,6 +293,18 @@ int bpm_noise_floor_chunk(const double* envelope, const BpmItem* items, const Bp
                           int64_t core_lo, int64_t core_hi, int open_left, int open_right, double* floor_out,
                           int64_t* troughs_out, int64_t* trough_count, int64_t* all_troughs_out, int64_t* all_count,
                           uint64_t* edge_hits, int64_t* anchors, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The chunk's proof obligations evaluated on the device (one thread; the lists stay where they are):
+ * counts = {kept, all, peaks}, flags = {edge hits, trough anchors l/r, peak anchors l/r} as filled by the
+ * two calls above, quantile_status (may be NULL) = the bpm_key_finish status words of the thresholds.
+ * [trough_lo, trough_hi) is the core given to bpm_noise_floor_chunk, [core_lo, core_hi) the chunk's own.
+ * out int64[8] = {bad, all troughs in core, kept troughs in core, peaks in core, index of the first kept
+ * trough in core, index of the first peak in core, proven floor range lo, hi}.  bad = 0 means: every
+ * core output equals the unchunked evaluation's. */
+int bpm_chunk_proof(const int64_t* all_troughs, const int64_t* kept_troughs, const int64_t* peaks, const int64_t* counts,
+                    const int64_t* flags, const int64_t* quantile_status, int64_t n, int64_t core_lo, int64_t core_hi,
+                    int64_t trough_lo, int64_t trough_hi, int at_start, int at_end, int64_t filter_halo, int distance,
+                    int window, int64_t* out, void* stream);
 
 /* deviation / smoothed deviation (:96-100) from a given strength list (laid out like a peak list;
  * `deviation` needs room for 2 P values per recording). */

@@ -142,3 +142,82 @@ def test_gloo_world2_matches_unchunked_oracle():
     ref = _reference(pcm, sr, params)
     for r in range(world):
         _check(got[r], ref)
+
+
+# ----------------------------------------------------------------------------- every stage sharded
+def _sharded(comm, pcm, sr, params, **kw):
+    from _oracle_engine import OracleChunkEngine
+    eng = OracleChunkEngine(sr, params)
+    fe = bstream.ShardedFrontEnd(len(pcm), sr, params, comm, eng, plan=_oracle_plan(sr, params), **kw)
+    f0, f1 = fe.frames()
+    out = fe.run(torch.from_numpy(pcm[f0:f1].copy()), gather_series=True)
+    return {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_stream_quantiles_descent_is_np_quantile(world):
+    """The descent / collect / finish protocol (numpy restatement of the bpm_key_* operators)."""
+    from _oracle_engine import OracleChunkEngine
+    from bpm_analysis_b200.dist import shard_range
+    eng = OracleChunkEngine(8000, _params())
+    rng = np.random.default_rng(1)
+    for x in (np.abs(rng.standard_normal(40001)) * 1e-3, np.round(rng.standard_normal(5000), 1), np.array([2.0, 1.0])):
+        for q in (0.0, 0.1, 0.77, 1.0):
+            def body(comm):
+                lo, hi = shard_range(len(x), comm.world, comm.rank)
+                v, st = bstream.stream_quantiles(eng, comm, torch.from_numpy(x[lo:hi].copy()), len(x), [q, 0.5])
+                return v.numpy(), st.numpy()
+            for v, st in bstream.run_thread_world(world, body):
+                assert st[0] == 0 and v[0] == float(np.quantile(x, q))
+                assert st[1] == 0 and v[1] == float(np.quantile(x, 0.5))
+
+
+@pytest.mark.parametrize("world", [3])
+def test_sharded_thread_world_matches_unchunked_oracle(world):
+    params = _params()
+    pcm, sr, _ = synth.config_c1(seed=3, duration_sec=240.0)
+    ref = _reference(pcm, sr, params)
+    for got in bstream.run_thread_world(world, lambda comm: _sharded(comm, pcm, sr, params)):
+        assert got["sharded"]
+        _check(got, ref)
+        assert np.allclose(got["smoothed_dev"], np.asarray(ref["smoothed_dev_series"]), rtol=1e-9, atol=0)
+
+
+def test_sharded_short_halo_falls_back():
+    params = _params()
+    pcm, sr, _ = synth.config_c1(seed=3, duration_sec=120.0)
+    ref = _reference(pcm, sr, params)
+    for got in bstream.run_thread_world(2, lambda comm: _sharded(comm, pcm, sr, params, analysis_halo=150)):
+        assert not got["sharded"]
+        _check(got, ref)
+
+
+def _gloo_sharded_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        params = _params()
+        pcm, sr, _ = synth.config_c1(seed=5, duration_sec=200.0)
+        got = _sharded(bstream.DistComm(), pcm, sr, params)
+        q.put((rank, {k: got[k] for k in ("troughs", "peaks", "envelope", "floor", "sharded")}))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_sharded_matches_unchunked_oracle():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_sharded_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    params = _params()
+    pcm, sr, _ = synth.config_c1(seed=5, duration_sec=200.0)
+    ref = _reference(pcm, sr, params)
+    for r in range(world):
+        assert got[r]["sharded"]
+        _check(got[r], ref)

@@ -130,10 +130,13 @@ def test_stream_quantile_is_np_quantile(world, engine):
 
             def body(comm):
                 lo, hi = shard_range(len(x), comm.world, comm.rank)
-                return stream.stream_quantile(engine, comm, engine.tensor(x[lo:hi]), len(x), q)
+                mine = engine.tensor(x[lo:hi]) if hi > lo else torch.zeros(0, dtype=torch.float64, device="cuda")
+                val, status = stream.stream_quantiles(engine, comm, mine, len(x), [q, 0.5])
+                return val.cpu().numpy(), status.cpu().numpy()
 
-            for got in stream.run_thread_world(world, body):
-                assert got == want, (len(x), q, got, want)
+            for val, status in stream.run_thread_world(world, body):
+                assert status[0] == 0 and val[0] == want, (len(x), q, val, want)
+                assert status[1] == 0 and val[1] == float(np.quantile(x, 0.5))
 
 
 @pytest.mark.parametrize("mode", ["parity", "fullrate"])
@@ -200,6 +203,7 @@ def test_sharded_long_holter_stream(engine, ref_params):
     pcm, sr, _ = synth.config_c4(seed=4, duration_sec=1500.0)
     ref = ref_port.front_end(pcm, sr, ref_params)
     for got in _run_sharded(4, engine, pcm, sr, ref_params):
+        assert got["sharded"], got["proof"]
         assert np.array_equal(got["troughs"], ref["troughs"])
         assert np.array_equal(got["peaks"], ref["peaks"])
         assert rel_err(got["floor"], np.asarray(ref["floor"])) < TOL
