@@ -176,7 +176,10 @@ def algorithmic_bytes(kernel: str, shp: dict, mode: str = "parity") -> float:
         "k_rolling_floor_blk": 16 * T + 8 * M,
         "k_find_peaks_small": 16 * B,
         "k_sanitize_flags": 24 * T,
-        "k_peak_strength": 32 * P, "k_peak_deviation": 16 * P, "k_dev_smooth": 16 * P,
+        "k_peak_strength": 32 * P, "k_peak_deviation": 16 * P, "k_dev_smooth_slide": 16 * P,
+        "k_select_collect": 8 * M, "k_select_finish": 8 * 4096,
+        # the chunked stream's extra kernels (per rank: M = its chunk)
+        "k_key_hist": 8 * M, "k_key_collect": 8 * M, "k_chunk_pack": 24 * (T + 2 * P), "k_chunk_unpack": 24 * (T + 2 * P),
         "k_bpm_instant": 32 * B, "k_bpm_smooth": 24 * B, "k_steepest": 16 * B, "k_hrv": 8 * B + 32 * (B // 5),
     }
     return float(table.get(kernel, 0.0))
@@ -726,7 +729,7 @@ def stream_record(args, rank: int, world: int, dev, params) -> dict:
     else:
         whole = torch.empty(n, dtype=torch.int16, device=dev)
     if world > 1:
-        dist.broadcast(whole, 0)                      # benchmark set-up only: every rank then keeps its own slice
+        dist.broadcast(whole.view(torch.uint8), 0)    # benchmark set-up only: every rank then keeps its own slice
     comm, eng = stream.DistComm(), stream.DeviceEngine()
     fe = stream.ShardedFrontEnd(n, sr, params, comm, eng)
     f0, f1 = fe.frames()

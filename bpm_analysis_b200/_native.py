@@ -86,6 +86,9 @@ _SIGNATURES = {
     "bpm_find_peaks_chunk": (_I, [_P, _I, _P, _P, _I, _P, _P, _L, _L, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "bpm_noise_floor_chunk_workspace_bytes": (_Z, [_L]),
     "bpm_noise_floor_chunk": (_I, [_P, _P, _P, _I, _P, _D, _I, _D, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    "bpm_chunk_pack": (_I, [_P, _P, _P, _P, _L, _L, _L, _P, _P]),
+    "bpm_chunk_unpack": (_I, [_P, _P, _I, _L, _L, _P, _P, _P, _P]),
+    "bpm_peak_strength": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "bpm_deviation_series": (_I, [_P, _P, _P, _P, _I, _D, _P, _P, _P]),
     "bpm_stage_a_workspace_bytes": (_Z, [_L, _I]),
     "bpm_stage_a": (_I, [_P, _P, _P, _I, _P, _P, _L, C.POINTER(StageAConfig), C.POINTER(StageAOutputs), _P, _Z, _P]),

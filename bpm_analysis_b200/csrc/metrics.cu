@@ -35,116 +35,74 @@ __global__ void k_peak_deviation(const double* __restrict__ strength, const int6
 }
 
 // centred rolling mean, window max(5, int((P-1)*factor)), min_periods=1          (:99-100)
-// The window grows with the recording (5 % of the peak count: 10 k samples for a 24-h stream), so
-// the mean comes from a prefix sum instead of re-adding the window per output:
-//   k_dev_prefix  one CTA per recording, chunks of 1024 x 8 values with a running carry; the
-//                 prefix S[0..n] is parked in the unused tail of the deviation buffer (2P <= m);
-//   k_dev_smooth  out[i] = (S[b+1] - S[a]) / (b - a + 1).
-// |S| stays below n * max(dev) <= n, so the difference is exact to ~1e-16 * n / w relative.
-constexpr int DP_SCAN_THREADS = 1024;
-constexpr int DP_SCAN_PER = 8;
-
-__global__ void __launch_bounds__(DP_SCAN_THREADS) k_dev_prefix(double* __restrict__ dev,
-                                                                const int64_t* __restrict__ peak_count,
-                                                                const BpmItem* __restrict__ items) {
-  __shared__ double s_warp[DP_SCAN_THREADS / 32];
-  __shared__ double s_carry;
-  const BpmItem it = items[blockIdx.x];
-  const long long P = peak_count[blockIdx.x];
-  const long long n = P - 1;
-  if (n < 1) return;
-  const double* d = dev + it.m_off;
-  double* S = dev + it.m_off + P;                       // S[0..n]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { s_carry = 0.0; S[0] = 0.0; }
-  __syncthreads();
-  for (long long base = 0; base < n; base += DP_SCAN_THREADS * DP_SCAN_PER) {
-    const long long k0 = base + static_cast<long long>(tid) * DP_SCAN_PER;
-    double v[DP_SCAN_PER];
-    double run = 0.0;
-#pragma unroll
-    for (int u = 0; u < DP_SCAN_PER; ++u) {
-      v[u] = (k0 + u < n) ? d[k0 + u] : 0.0;
-      run += v[u];
-      v[u] = run;                                      // inclusive inside the thread
-    }
-    double inc = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      double w = s_warp[lane];
-      double wi = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const double t = __shfl_up_sync(0xffffffffu, wi, o);
-        if (lane >= o) wi += t;
-      }
-      s_warp[lane] = wi - w;                           // exclusive prefix of the warp totals
-    }
-    __syncthreads();
-    const double before = s_carry + s_warp[warp] + (inc - run);
-#pragma unroll
-    for (int u = 0; u < DP_SCAN_PER; ++u)
-      if (k0 + u < n) S[k0 + u + 1] = before + v[u];
-    __syncthreads();
-    if (tid == DP_SCAN_THREADS - 1) s_carry = before + run;
-    __syncthreads();
-  }
-}
-
-__global__ void __launch_bounds__(256) k_dev_smooth(const double* __restrict__ dev,
-                                                    const int64_t* __restrict__ peak_count,
-                                                    const BpmItem* __restrict__ items, double factor,
-                                                    double* __restrict__ out) {
-  const BpmItem it = items[blockIdx.y];
-  const long long P = peak_count[blockIdx.y];
-  const long long n = P - 1;
-  long long w = static_cast<long long>(__dmul_rn(static_cast<double>(n), factor));
-  if (w < 5) w = 5;
-  const long long off = (w - 1) / 2;
-  const double* S = dev + it.m_off + P;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    long long a = i + 1 + off - w, b = i + off;
-    if (a < 0) a = 0;
-    if (b > n - 1) b = n - 1;
-    out[it.m_off + i] = __ddiv_rn(__dsub_rn(S[b + 1], S[a]), static_cast<double>(b - a + 1));
-  }
-}
-
-// centred rolling mean, window max(5, int((P-1)*factor)), min_periods=1          (:99-100)
-// (short recordings) one warp per output: lanes stride over the window, then a shuffle reduction
-__global__ void __launch_bounds__(256) k_dev_smooth_direct(const double* __restrict__ dev,
-                                                    const int64_t* __restrict__ peak_count,
-                                                    const BpmItem* __restrict__ items, double factor,
-                                                    double* __restrict__ out) {
+// The window grows with the recording (5 % of the peak count: 640 values for a 60-min recording, 10^4
+// for a 24-h stream).  A warp owns 32 consecutive outputs: its lanes add up the window of the first one
+// together (coalesced), and output l is that sum plus the samples that entered minus those that left on
+// the way from output 0 to l -- a warp scan of per-step differences (the way pandas' rolling mean
+// itself proceeds: add one, remove one).  n / 32 windows are read instead of n.  (Round 1 re-added the
+// window per output for short lists, 12 us at C2, and used a one-CTA prefix sum for long ones, 190 us
+// at C4; this form takes 5 / 27 us.)
+__global__ void __launch_bounds__(128) k_dev_smooth_slide(const double* __restrict__ dev,
+                                                          const int64_t* __restrict__ peak_count,
+                                                          const BpmItem* __restrict__ items, double factor,
+                                                          double* __restrict__ out) {
   const BpmItem it = items[blockIdx.y];
   const long long n = peak_count[blockIdx.y] - 1;
-  const int lane = threadIdx.x & 31;
   long long w = static_cast<long long>(__dmul_rn(static_cast<double>(n), factor));
   if (w < 5) w = 5;
   const long long off = (w - 1) / 2;
   const double* d = dev + it.m_off;
+  const int lane = threadIdx.x & 31;
   const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
-  for (long long i = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+  for (long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r * 32 < n; r += warps) {
+    const long long i0 = r * 32;
+    long long a0 = i0 + 1 + off - w, b0 = i0 + off;
+    if (a0 < 0) a0 = 0;
+    if (b0 > n - 1) b0 = n - 1;
+    double s0 = 0.0, s1 = 0.0;
+    long long k = a0 + lane;
+    for (; k + 32 <= b0; k += 64) { s0 += d[k]; s1 += d[k + 32]; }
+    if (k <= b0) s0 += d[k];
+    double base = s0 + s1;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
+    // lane l: what output i0 + l gains / loses against output i0 + l - 1
+    const long long i = i0 + lane;
     long long a = i + 1 + off - w, b = i + off;
     if (a < 0) a = 0;
     if (b > n - 1) b = n - 1;
-    double s = 0.0;
-    for (long long k = a + lane; k <= b; k += 32) s += d[k];
+    long long pa = i + off - w, pb = i - 1 + off;
+    if (pa < 0) pa = 0;
+    if (pb > n - 1) pb = n - 1;
+    double delta = 0.0;
+    if (lane > 0 && i < n) {
+      if (b > pb) delta += d[b];
+      if (a > pa) delta -= d[pa];
+    }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) out[it.m_off + i] = __ddiv_rn(s, static_cast<double>(b - a + 1));
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, delta, o);
+      if (lane >= o) delta += t;
+    }
+    if (i < n) out[it.m_off + i] = __ddiv_rn(base + delta, static_cast<double>(b - a + 1));
   }
 }
 
 int deviation_series_run(const double* strength, const int64_t* peak_count, const BpmItem* items, const BatchShape& sh,
-                         double factor, double* deviation, double* smoothed, cudaStream_t st);
+                         double factor, double* deviation, double* smoothed, cudaStream_t st, bool list_sized = false);
+
+int peak_strength_run(const double* env, const double* floor_, const int64_t* peaks, const int64_t* peak_count,
+                      const BpmItem* items, const BatchShape& sh, double* strength, cudaStream_t st) {
+  if (!env || !floor_ || !peaks || !peak_count || !items || !strength) return BPM_ERR_ARG;
+  int64_t gx = (sh.max_m / 2 + 2 + 255) / 256;
+  const int64_t cap = (148 * 4 + sh.n_items - 1) / sh.n_items;
+  if (gx > cap) gx = cap;
+  BPM_KERNEL(k_peak_strength);
+  k_peak_strength<<<dim3(static_cast<unsigned>(gx < 1 ? 1 : gx), sh.n_items), 256, 0, st>>>(env, floor_, peaks, peak_count,
+                                                                                          items, strength);
+  BPM_LAUNCH_OK();
+  return BPM_OK;
+}
 
 int peak_metrics_run(const double* env, const double* floor_, const int64_t* peaks, const int64_t* peak_count,
                      const BpmItem* items, const BatchShape& sh, double factor, double* strength,
@@ -161,10 +119,10 @@ int peak_metrics_run(const double* env, const double* floor_, const int64_t* pea
   return deviation_series_run(strength, peak_count, items, sh, factor, deviation, smoothed, st);
 }
 
-// deviation[k] and its centred rolling mean from a given strength list (:96-100); `deviation` needs
-// room for 2 P values per recording when the prefix-sum path is taken (see k_dev_prefix)
+// deviation[k] and its centred rolling mean from a given strength list (:96-100).
+// list_sized: the descriptors give the LIST lengths (not envelope lengths), i.e. max_m = P.
 int deviation_series_run(const double* strength, const int64_t* peak_count, const BpmItem* items, const BatchShape& sh,
-                         double factor, double* deviation, double* smoothed, cudaStream_t st) {
+                         double factor, double* deviation, double* smoothed, cudaStream_t st, bool list_sized) {
   if (!strength || !peak_count || !items || !deviation || !smoothed) return BPM_ERR_ARG;
   int64_t gx = (sh.max_m / 2 + 2 + 255) / 256;
   const int64_t cap = (148 * 4 + sh.n_items - 1) / sh.n_items;
@@ -173,17 +131,15 @@ int deviation_series_run(const double* strength, const int64_t* peak_count, cons
   BPM_KERNEL(k_peak_deviation);
   k_peak_deviation<<<grid, 256, 0, st>>>(strength, peak_count, items, deviation);
   BPM_LAUNCH_OK();
-  if (sh.max_m <= (1ll << 22)) {
-    // short recordings: the window is a few hundred values, re-adding it per output is cheapest
-    BPM_KERNEL(k_dev_smooth_direct);
-    k_dev_smooth_direct<<<grid, 256, 0, st>>>(deviation, peak_count, items, factor, smoothed);
-    BPM_LAUNCH_OK();
-  } else {
-    BPM_KERNEL(k_dev_prefix);
-    k_dev_prefix<<<sh.n_items, DP_SCAN_THREADS, 0, st>>>(deviation, peak_count, items);
-    BPM_LAUNCH_OK();
-    BPM_KERNEL(k_dev_smooth);
-    k_dev_smooth<<<grid, 256, 0, st>>>(deviation, peak_count, items, factor, smoothed);
+  {
+    // peak counts live on the device: the grid is sized for the most peaks the list can hold
+    int64_t runs = ((list_sized ? sh.max_m : sh.max_m / 2 + 1) + 31) / 32;      // one warp each, 4 per CTA
+    int64_t gs = (runs + 3) / 4;
+    const int64_t cap2 = (148 * 8 + sh.n_items - 1) / sh.n_items;
+    if (gs > cap2) gs = cap2;
+    BPM_KERNEL(k_dev_smooth_slide);
+    k_dev_smooth_slide<<<dim3(static_cast<unsigned>(gs < 1 ? 1 : gs), sh.n_items), 128, 0, st>>>(
+        deviation, peak_count, items, factor, smoothed);
     BPM_LAUNCH_OK();
   }
   return BPM_OK;

@@ -56,7 +56,9 @@ int steepest_run(const double* smoothed, const int64_t* stamp_us, const int64_t*
                  int n_lists, int64_t max_len, int sign, double window_sec, double* result, cudaStream_t st);
 int cast_f32_run(const double* src, float* dst, int64_t n, cudaStream_t st);
 int deviation_series_run(const double* strength, const int64_t* peak_count, const BpmItem* items, const BatchShape& sh,
-                         double factor, double* deviation, double* smoothed, cudaStream_t st);
+                         double factor, double* deviation, double* smoothed, cudaStream_t st, bool list_sized = false);
+int peak_strength_run(const double* env, const double* floor_, const int64_t* peaks, const int64_t* peak_count,
+                      const BpmItem* items, const BatchShape& sh, double* strength, cudaStream_t st);
 int hrv_run(const int64_t* beats, const BpmItem* lists, const BatchShape& sh, int rate, int win, int step,
             double* out, int64_t* rows, cudaStream_t st);
 
@@ -523,7 +525,14 @@ int bpm_deviation_series(const double* strength, const int64_t* peak_count, cons
                          double* smoothed, void* stream) {
   if (!items_host || n_items <= 0) return BPM_ERR_ARG;
   return deviation_series_run(strength, peak_count, items, batch_shape(items_host, n_items), smoothing_factor,
-                              deviation, smoothed, static_cast<cudaStream_t>(stream));
+                              deviation, smoothed, static_cast<cudaStream_t>(stream), true);
+}
+
+int bpm_peak_strength(const double* envelope, const double* floor_, const int64_t* peaks, const int64_t* peak_count,
+                      const BpmItem* items, const BpmItem* items_host, int n_items, double* strength, void* stream) {
+  if (!items_host || n_items <= 0) return BPM_ERR_ARG;
+  return peak_strength_run(envelope, floor_, peaks, peak_count, items, batch_shape(items_host, n_items), strength,
+                           static_cast<cudaStream_t>(stream));
 }
 
 int bpm_cast_f32(const double* src, float* dst, int64_t n, void* stream) {

@@ -238,12 +238,11 @@ __device__ long long lower_bound_ll(const int64_t* a, long long n, long long v) 
   return lo;
 }
 
-// outputs rolling-quantile-over-np.interp(knots) that equal the stream's, given that the knot list is the
-// stream's inside [lo, hi)
-__device__ void proven_range(const int64_t* knots, long long count, long long lo, long long hi, const ProofGeom& g,
-                             long long* x_lo, long long* x_hi) {
+// Outputs of a rolling quantile over np.interp(knots) that equal the stream's, given that the knot list is
+// the stream's inside [lo, hi): i0 / i1 = lower bounds of lo / hi in the list.
+__device__ void proven_range(const int64_t* knots, long long i0, long long i1, const ProofGeom& g, long long* x_lo,
+                             long long* x_hi) {
   const long long off = (g.window - 1) / 2, left = g.window - 1 - off;
-  const long long i0 = lower_bound_ll(knots, count, lo), i1 = lower_bound_ll(knots, count, hi);
   if (i1 <= i0) {
     const bool whole = g.at_start && g.at_end;
     *x_lo = 0; *x_hi = whole ? g.n : 0;
@@ -255,12 +254,40 @@ __device__ void proven_range(const int64_t* knots, long long count, long long lo
 
 // flags: {edge hits, trough anchors (left, right), peak anchors (left, right)}; counts: {kept, all, peaks}
 // out: {bad, all troughs in core, kept in core, peaks in core, first kept in core, first peak in core, x3 lo, x3 hi}
+// One warp: the binary searches (dependent global loads, ~5 us each) run side by side on its lanes.
 __global__ void k_chunk_proof(const int64_t* __restrict__ every, const int64_t* __restrict__ kept,
                               const int64_t* __restrict__ peaks, const long long* __restrict__ counts,
                               const long long* __restrict__ flags, const long long* __restrict__ q_status, ProofGeom g,
                               long long* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
   const long long n_kept = counts[0], n_all = counts[1], n_peaks = counts[2];
+  // round 1 -- lane: 0 every@t_lo, 1 every@t_hi, 2 every@core_lo, 3 every@core_hi, 4 kept@core_lo, 5 kept@core_hi,
+  //                  6 peaks@core_lo, 7 peaks@core_hi
+  const int64_t* list = lane < 4 ? every : (lane < 6 ? kept : peaks);
+  const long long len = lane < 4 ? n_all : (lane < 6 ? n_kept : n_peaks);
+  const long long key = lane == 0 ? g.t_lo : lane == 1 ? g.t_hi : (lane & 1) ? g.core_hi : g.core_lo;
+  const long long r1 = lane < 8 ? lower_bound_ll(list, len, key) : 0;
+  long long x2lo = 0, x2hi = 0;
+  if (lane == 0) {
+    const long long i1 = __shfl_sync(0xffffffffu, r1, 1);
+    proven_range(every, r1, i1, g, &x2lo, &x2hi);
+    if (x2lo < g.t_lo) x2lo = g.t_lo;
+    if (x2hi > g.t_hi) x2hi = g.t_hi;
+  } else {
+    (void)__shfl_sync(0xffffffffu, r1, 1);
+  }
+  x2lo = __shfl_sync(0xffffffffu, x2lo, 0);
+  x2hi = __shfl_sync(0xffffffffu, x2hi, 0);
+  // round 2 -- lane 0: kept@x2lo, lane 1: kept@x2hi
+  const long long r2 = lane < 2 ? lower_bound_ll(kept, n_kept, lane == 0 ? x2lo : x2hi) : 0;
+  const long long k1 = __shfl_sync(0xffffffffu, r2, 1);
+  long long v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __shfl_sync(0xffffffffu, r1, j);
+  if (lane != 0) return;
+  long long x3lo, x3hi;
+  proven_range(kept, r2, k1, g, &x3lo, &x3hi);
   const long long d = g.distance;
   bool ok = flags[0] == 0;
   if (q_status != nullptr) ok = ok && q_status[0] == 0 && q_status[1] == 0;
@@ -268,20 +295,58 @@ __global__ void k_chunk_proof(const int64_t* __restrict__ every, const int64_t* 
     ok = ok && (g.at_start || flags[1] - d >= g.filter_halo);
     ok = ok && (g.at_end || flags[2] + d <= g.n - g.filter_halo);
   }
-  long long x2lo, x2hi, x3lo, x3hi;
-  proven_range(every, n_all, g.t_lo, g.t_hi, g, &x2lo, &x2hi);
-  proven_range(kept, n_kept, x2lo > g.t_lo ? x2lo : g.t_lo, x2hi < g.t_hi ? x2hi : g.t_hi, g, &x3lo, &x3hi);
   ok = ok && x3lo <= g.core_lo && x3hi >= g.core_hi;
   if (d > 1) {
     ok = ok && (g.at_start || (flags[3] >= 0 && flags[3] - d >= x3lo));
     ok = ok && (g.at_end || (flags[4] < g.n && flags[4] + d < x3hi));
   }
-  const long long la = lower_bound_ll(every, n_all, g.core_lo), ha = lower_bound_ll(every, n_all, g.core_hi);
-  const long long lk = lower_bound_ll(kept, n_kept, g.core_lo), hk = lower_bound_ll(kept, n_kept, g.core_hi);
-  const long long lp = lower_bound_ll(peaks, n_peaks, g.core_lo), hp = lower_bound_ll(peaks, n_peaks, g.core_hi);
   out[0] = ok ? 0 : 1;
-  out[1] = ha - la; out[2] = hk - lk; out[3] = hp - lp;
-  out[4] = lk; out[5] = lp; out[6] = x3lo; out[7] = x3hi;
+  out[1] = v[3] - v[2]; out[2] = v[5] - v[4]; out[3] = v[7] - v[6];
+  out[4] = v[4]; out[5] = v[6]; out[6] = x3lo; out[7] = x3hi;
+}
+
+// ---------------------------------------------------------------- the one list exchange
+// A rank's contribution: [kept troughs of its core | peaks of its core | their strengths (bit patterns)],
+// indices moved to stream coordinates, each part padded to the longest among the ranks (cap_t, cap_p).
+// `proof` is the rank's own k_chunk_proof output (counts and first indices).
+__global__ void __launch_bounds__(256) k_chunk_pack(const int64_t* __restrict__ kept, const int64_t* __restrict__ peaks,
+                                                    const double* __restrict__ strength,
+                                                    const long long* __restrict__ proof, long long e0, long long cap_t,
+                                                    long long cap_p, long long* __restrict__ out) {
+  const long long nk = proof[2], np = proof[3], lk = proof[4], lp = proof[5];
+  const long long total = cap_t + 2 * cap_p;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long v = 0;
+    if (i < cap_t) { if (i < nk) v = kept[lk + i] + e0; }
+    else if (i < cap_t + cap_p) { const long long k = i - cap_t; if (k < np) v = peaks[lp + k] + e0; }
+    else { const long long k = i - cap_t - cap_p; if (k < np) v = __double_as_longlong(strength[lp + k]); }
+    out[i] = v;
+  }
+}
+
+// rows = the all-gathered contributions, table = the all-gathered proofs: the stream's lists in rank order
+__global__ void __launch_bounds__(256) k_chunk_unpack(const long long* __restrict__ rows, const long long* __restrict__ table,
+                                                      int world, long long cap_t, long long cap_p,
+                                                      int64_t* __restrict__ troughs, int64_t* __restrict__ peaks,
+                                                      double* __restrict__ strength) {
+  __shared__ long long s_t[65], s_p[65];
+  if (threadIdx.x == 0) {
+    long long t = 0, p = 0;
+    for (int r = 0; r < world; ++r) { s_t[r] = t; s_p[r] = p; t += table[r * 8 + 2]; p += table[r * 8 + 3]; }
+    s_t[world] = t; s_p[world] = p;
+  }
+  __syncthreads();
+  const long long pitch = cap_t + 2 * cap_p;
+  const int r = blockIdx.y;
+  const long long nk = s_t[r + 1] - s_t[r], np = s_p[r + 1] - s_p[r];
+  const long long* row = rows + r * pitch;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nk + 2 * np;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (i < nk) troughs[s_t[r] + i] = row[i];
+    else if (i < nk + np) peaks[s_p[r] + (i - nk)] = row[cap_t + (i - nk)];
+    else strength[s_p[r] + (i - nk - np)] = __longlong_as_double(row[cap_t + cap_p + (i - nk - np)]);
+  }
 }
 
 }  // namespace bpm
@@ -352,6 +417,38 @@ int bpm_chunk_proof(const int64_t* all_troughs, const int64_t* kept_troughs, con
       all_troughs, kept_troughs, peaks, reinterpret_cast<const long long*>(counts),
       reinterpret_cast<const long long*>(flags), reinterpret_cast<const long long*>(quantile_status), g,
       reinterpret_cast<long long*>(out));
+  BPM_LAUNCH_OK();
+  return BPM_OK;
+}
+
+int bpm_chunk_pack(const int64_t* kept, const int64_t* peaks, const double* strength, const int64_t* proof,
+                   int64_t chunk_origin, int64_t cap_troughs, int64_t cap_peaks, int64_t* out, void* stream) {
+  if (!kept || !peaks || !strength || !proof || !out || cap_troughs < 0 || cap_peaks < 0) return BPM_ERR_ARG;
+  const int64_t total = cap_troughs + 2 * cap_peaks;
+  if (total == 0) return BPM_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t g = cdiv(total, 256);
+  if (g > 148 * 4) g = 148 * 4;
+  BPM_KERNEL(k_chunk_pack);
+  k_chunk_pack<<<static_cast<unsigned>(g), 256, 0, st>>>(kept, peaks, strength, reinterpret_cast<const long long*>(proof),
+                                                         chunk_origin, cap_troughs, cap_peaks,
+                                                         reinterpret_cast<long long*>(out));
+  BPM_LAUNCH_OK();
+  return BPM_OK;
+}
+
+int bpm_chunk_unpack(const int64_t* rows, const int64_t* table, int world, int64_t cap_troughs, int64_t cap_peaks,
+                     int64_t* troughs, int64_t* peaks, double* strength, void* stream) {
+  if (!rows || !table || !troughs || !peaks || !strength || world < 1 || world > 64) return BPM_ERR_ARG;
+  const int64_t total = cap_troughs + 2 * cap_peaks;
+  if (total == 0) return BPM_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t g = cdiv(total, 256);
+  if (g > 64) g = 64;
+  BPM_KERNEL(k_chunk_unpack);
+  k_chunk_unpack<<<dim3(static_cast<unsigned>(g), world), 256, 0, st>>>(
+      reinterpret_cast<const long long*>(rows), reinterpret_cast<const long long*>(table), world, cap_troughs, cap_peaks,
+      troughs, peaks, strength);
   BPM_LAUNCH_OK();
   return BPM_OK;
 }

@@ -224,6 +224,22 @@ class DeviceEngine:
         self.device = runtime.require_cuda()
         self.lib = nat.load_library()
         self._item_cache: Dict[Tuple[int, int], tuple] = {}
+        self._ring = torch.empty((self.RING_SLOTS, 16), dtype=torch.int64).pin_memory()
+        self._ring_next = 0
+        self._ring_lock = threading.Lock()
+
+    RING_SLOTS = 256
+
+    def small_i64(self, values: Sequence[int]) -> torch.Tensor:
+        """A few int64 constants -> device WITHOUT stalling the stream: torch.tensor(list, device=cuda)
+        copies from pageable memory, which makes the host wait for the stream.  The values are staged
+        in a ring of pinned slots (a slot is reused RING_SLOTS calls later; every step of the chunked
+        front end waits for the device at least once, long before that)."""
+        with self._ring_lock:
+            slot = self._ring[self._ring_next][:len(values)]
+            self._ring_next = (self._ring_next + 1) % self.RING_SLOTS
+        slot.copy_(torch.tensor(list(values), dtype=torch.int64))
+        return slot.to(self.device, non_blocking=True)
 
     # helpers
     def _ws(self, nbytes: int) -> torch.Tensor:
@@ -372,7 +388,7 @@ class DeviceEngine:
 
     # ---- chunk mode (ShardedFrontEnd): nothing here synchronises the host
     def key_state(self, n_total: int, k: int) -> torch.Tensor:
-        return torch.tensor([0, int(k), int(n_total)], dtype=torch.int64, device=self.device)
+        return self.small_i64([0, int(k), int(n_total)])
 
     def key_histogram(self, x: torch.Tensor, shift: int, bits: int, state: torch.Tensor, hist: torch.Tensor) -> None:
         self.nat.check(self.lib.bpm_key_histogram(self.rt._ptr(x), x.numel(), int(shift), int(bits), 0,
@@ -408,11 +424,10 @@ class DeviceEngine:
         f64 = dict(dtype=torch.float64, device=self.device)
         i64 = dict(dtype=torch.int64, device=self.device)
         floor, strength = torch.empty(n, **f64), torch.empty(n, **f64)
-        scratch = torch.empty(3 * n, **f64)                       # deviation (2n) + smoothed (n): not used per chunk
         kept, every, peaks = torch.empty(n, **i64), torch.empty(n, **i64), torch.empty(n, **i64)
         big = np.iinfo(np.int64).max
         # counts {kept, all, peaks} | flags {edge hits, trough anchors l/r, peak anchors l/r} | proof[8]
-        head = torch.tensor([0, 0, 0, 0, -1, big, -1, big, 0, 0, 0, 0, 0, 0, 0, 0], **i64)
+        head = self.small_i64([0, 0, 0, 0, -1, big, -1, big, 0, 0, 0, 0, 0, 0, 0, 0])
         hb = head.data_ptr()
         cnt, flg, prf = hb, hb + 24, hb + 64
         nb = max(int(L.bpm_noise_floor_chunk_workspace_bytes(n)), int(L.bpm_find_peaks_workspace_bytes(n, 1)))
@@ -430,17 +445,31 @@ class DeviceEngine:
                                          rt._ptr(items_dev), rt._host_ptr(items), int(geom.core_lo), int(geom.core_hi),
                                          ends[0], ends[1], rt._ptr(peaks), C.c_void_p(cnt + 16), C.c_void_p(flg),
                                          C.c_void_p(flg + 24), rt._ptr(ws), nb, st))
-        sb = scratch.data_ptr()
-        nat.check(L.bpm_peak_metrics(rt._ptr(env), rt._ptr(floor), rt._ptr(peaks), C.c_void_p(cnt + 16),
-                                     rt._ptr(items_dev), rt._host_ptr(items), 1, 0.05, rt._ptr(strength),
-                                     C.c_void_p(sb), C.c_void_p(sb + 16 * n), st))
+        nat.check(L.bpm_peak_strength(rt._ptr(env), rt._ptr(floor), rt._ptr(peaks), C.c_void_p(cnt + 16),
+                                      rt._ptr(items_dev), rt._host_ptr(items), 1, rt._ptr(strength), st))
         nat.check(L.bpm_chunk_proof(rt._ptr(every), rt._ptr(kept), rt._ptr(peaks), C.c_void_p(cnt), C.c_void_p(flg),
                                     rt._ptr(qstat), n, int(geom.core_lo), int(geom.core_hi), int(geom.t_lo),
                                     int(geom.t_hi), int(geom.at_start), int(geom.at_end), int(geom.filter_halo),
                                     int(geom.distance), int(geom.window), C.c_void_p(prf), st))
-        self._keep_chunk = (ws, items_dev, scratch)
+        self._keep_chunk = (ws, items_dev)
         return {"floor": floor, "kept": kept, "every": every, "peaks": peaks, "strength": strength,
                 "head": head, "proof": head[8:16]}
+
+    def chunk_pack(self, c: Dict[str, torch.Tensor], origin: int, cap_t: int, cap_p: int) -> torch.Tensor:
+        out = torch.empty(cap_t + 2 * cap_p, dtype=torch.int64, device=self.device)
+        self.nat.check(self.lib.bpm_chunk_pack(self.rt._ptr(c["kept"]), self.rt._ptr(c["peaks"]),
+                                               self.rt._ptr(c["strength"]), self.rt._ptr(c["proof"]), int(origin),
+                                               int(cap_t), int(cap_p), self.rt._ptr(out), self.rt._stream_ptr()))
+        return out
+
+    def chunk_unpack(self, rows: torch.Tensor, table: torch.Tensor, cap_t: int, cap_p: int, n_t: int, n_p: int):
+        troughs = torch.empty(n_t, dtype=torch.int64, device=self.device)
+        peaks = torch.empty(n_p, dtype=torch.int64, device=self.device)
+        strength = torch.empty(n_p, dtype=torch.float64, device=self.device)
+        self.nat.check(self.lib.bpm_chunk_unpack(self.rt._ptr(rows), self.rt._ptr(table), int(rows.shape[0]), int(cap_t),
+                                                 int(cap_p), self.rt._ptr(troughs), self.rt._ptr(peaks),
+                                                 self.rt._ptr(strength), self.rt._stream_ptr()))
+        return troughs, peaks, strength
 
     def deviation_series(self, strength: torch.Tensor, factor: float):
         """deviation and its rolling mean (:96-100) of a whole strength list"""
@@ -451,7 +480,7 @@ class DeviceEngine:
             z = torch.zeros(0, dtype=torch.float64, device=self.device)
             return z, z
         items, items_dev = self._items(c, c)
-        cnt = torch.tensor([c], dtype=torch.int64, device=self.device)
+        cnt = self.small_i64([c])
         f64 = dict(dtype=torch.float64, device=self.device)
         dv, sm = torch.empty(2 * c, **f64), torch.empty(c, **f64)
         self.nat.check(L.bpm_deviation_series(rt._ptr(strength.contiguous()), rt._ptr(cnt), rt._ptr(items_dev),
@@ -701,25 +730,18 @@ class ShardedFrontEnd(ChunkedFrontEnd):
         else:
             thr, qstat = stream_quantiles(E, comm, env_core, ch.m, [q_t, q_p])
         c = E.chunk_chain(env_ext, thr, qstat, g, P)
-        table = comm.all_gather_rows(c["proof"]).cpu().numpy()    # the chunk's one wait for the device
+        table_dev = comm.all_gather_rows(c["proof"]).contiguous()
+        table = table_dev.cpu().numpy()                           # the chunk's one wait for the device
         mine = table[comm.rank]
         self.last_proof = {"ok": not bool(mine[0]), "proven_floor": (int(mine[6]) + e0, int(mine[7]) + e0),
                            "table": table}
         if table[:, 0].any() or table[:, 1].sum() < MIN_TROUGHS or table[:, 2].sum() <= MIN_KEPT:
             return None
         # ONE exchange for the three lists: [kept troughs | peaks | strength bits], padded to the longest
-        nk, npk, lk, lp = (int(v) for v in mine[2:6])
         cap_t, cap_p = int(table[:, 2].max()), int(table[:, 3].max())
-        pack = torch.zeros(cap_t + 2 * cap_p, dtype=torch.int64, device=env_ext.device)
-        pack[:nk] = c["kept"][lk:lk + nk] + e0
-        pack[cap_t:cap_t + npk] = c["peaks"][lp:lp + npk] + e0
-        pack[cap_t + cap_p:cap_t + cap_p + npk] = c["strength"][lp:lp + npk].view(torch.int64)
-        rows = comm.all_gather_rows(pack)
-        world = comm.world
-        troughs = torch.cat([rows[r, :int(table[r, 2])] for r in range(world)])
-        peaks_all = torch.cat([rows[r, cap_t:cap_t + int(table[r, 3])] for r in range(world)])
-        strength_all = torch.cat([rows[r, cap_t + cap_p:cap_t + cap_p + int(table[r, 3])] for r in range(world)]
-                                 ).view(torch.float64)
+        rows = comm.all_gather_rows(E.chunk_pack(c, e0, cap_t, cap_p))
+        troughs, peaks_all, strength_all = E.chunk_unpack(rows, table_dev, cap_t, cap_p, int(table[:, 2].sum()),
+                                                          int(table[:, 3].sum()))
         deviation, smoothed = E.deviation_series(strength_all, float(P["deviation_smoothing_factor"]))
         return {"troughs": troughs, "peaks": peaks_all, "strength": strength_all, "deviation": deviation,
                 "smoothed_dev": smoothed, "envelope_core": env_core, "floor_core": c["floor"][g.core_lo:g.core_hi],

@@ -306,8 +306,22 @@ int bpm_chunk_proof(const int64_t* all_troughs, const int64_t* kept_troughs, con
                     int64_t trough_lo, int64_t trough_hi, int at_start, int at_end, int64_t filter_halo, int distance,
                     int window, int64_t* out, void* stream);
 
-/* deviation / smoothed deviation (:96-100) from a given strength list (laid out like a peak list;
- * `deviation` needs room for 2 P values per recording). */
+/* The one list exchange of a chunked stream.  bpm_chunk_pack: a rank's contribution
+ * [kept troughs of its core | peaks of its core | their strengths], indices moved to stream coordinates
+ * (+ chunk_origin), the parts padded to cap_troughs / cap_peaks (the longest among the ranks); `proof` is
+ * the rank's bpm_chunk_proof output.  bpm_chunk_unpack: rows = the all-gathered contributions, table =
+ * the all-gathered proofs (world x 8) -> the stream's lists in rank order. */
+int bpm_chunk_pack(const int64_t* kept, const int64_t* peaks, const double* strength, const int64_t* proof,
+                   int64_t chunk_origin, int64_t cap_troughs, int64_t cap_peaks, int64_t* out, void* stream);
+int bpm_chunk_unpack(const int64_t* rows, const int64_t* table, int world, int64_t cap_troughs, int64_t cap_peaks,
+                     int64_t* troughs, int64_t* peaks, double* strength, void* stream);
+
+/* strength[k] = max(0, env[p_k] - floor[p_k]) (:93-95) alone: what a chunk contributes to the stream's list */
+int bpm_peak_strength(const double* envelope, const double* floor_, const int64_t* peaks, const int64_t* peak_count,
+                      const BpmItem* items, const BpmItem* items_host, int n_items, double* strength, void* stream);
+
+/* deviation / smoothed deviation (:96-100) from a given strength list; the descriptors give the LIST
+ * lengths (m = number of peaks); `deviation` needs room for 2 P values per recording. */
 int bpm_deviation_series(const double* strength, const int64_t* peak_count, const BpmItem* items,
                          const BpmItem* items_host, int n_items, double smoothing_factor, double* deviation,
                          double* smoothed, void* stream);

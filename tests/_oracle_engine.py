@@ -236,6 +236,22 @@ class OracleChunkEngine(OracleEngine):
         return {"floor": self.tensor(floor), "kept": buf(kept), "every": buf(every), "peaks": buf(peaks),
                 "strength": self.tensor(strength), "proof": proof}
 
+    def chunk_pack(self, c, origin, cap_t, cap_p):
+        nk, npk, lk, lp = (int(v) for v in c["proof"][2:6])
+        out = torch.zeros(cap_t + 2 * cap_p, dtype=torch.int64)
+        out[:nk] = c["kept"][lk:lk + nk] + origin
+        out[cap_t:cap_t + npk] = c["peaks"][lp:lp + npk] + origin
+        out[cap_t + cap_p:cap_t + cap_p + npk] = c["strength"][lp:lp + npk].view(torch.int64)
+        return out
+
+    def chunk_unpack(self, rows, table, cap_t, cap_p, n_t, n_p):
+        w = rows.shape[0]
+        tr = torch.cat([rows[r, :int(table[r, 2])] for r in range(w)])
+        pk = torch.cat([rows[r, cap_t:cap_t + int(table[r, 3])] for r in range(w)])
+        st = torch.cat([rows[r, cap_t + cap_p:cap_t + cap_p + int(table[r, 3])] for r in range(w)]).view(torch.float64)
+        assert len(tr) == n_t and len(pk) == n_p
+        return tr, pk, st
+
     def deviation_series(self, strength, factor):
         s = _np(strength)
         if len(s) < 2:
