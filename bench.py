@@ -753,18 +753,26 @@ def stream_record(args, rank: int, world: int, dev, params) -> dict:
         return float(t.item())
 
     steps = max(3, min(args.steps, 10))
-    out = None
-    for _ in range(3):
-        out = fe.run(pcm_dev)
-    barrier()
+    use_graph = not args.no_graph
     l0 = lib.bpm_launch_count()
+    out = fe.run(pcm_dev, want_filtered=False)                   # eager: counts the kernels of a step
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.bpm_launch_count() - l0)
+
+    def step():
+        return fe.run(pcm_dev, want_filtered=False, graph=use_graph)
+
+    for _ in range(3):
+        out = step()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        out = fe.run(pcm_dev)
+        out = step()
     e1.record()
     barrier()
-    launches = int(lib.bpm_launch_count() - l0)
+    launches = launches_per_step * steps
+    graphed = use_graph and fe._graph is not None and not fe._graph.get("failed")
     ms_step = max_over_ranks(e0.elapsed_time(e1) / steps)
     # end to end: this rank's frames from pinned host memory; the gathered lists and this rank's own
     # envelope / floor chunk back into pinned host memory
@@ -773,7 +781,7 @@ def stream_record(args, rank: int, world: int, dev, params) -> dict:
 
     def e2e_step():
         pcm_dev.copy_(pcm_pin, non_blocking=True)
-        o = fe.run(pcm_dev)
+        o = step()
         for k in keys:
             if k not in host or host[k].numel() < o[k].numel():
                 host[k] = torch.empty(o[k].numel(), dtype=o[k].dtype).pin_memory()
@@ -797,6 +805,8 @@ def stream_record(args, rank: int, world: int, dev, params) -> dict:
            "value": audio_hours / (ms_step / 1e3), "unit": UNIT, "chunk_proofs_held": sharded,
            "raw_samples": n, "envelope_samples": fe.chunks.m, "halo_envelope_samples": fe.chunks.halo,
            "frames_this_rank": int(f1 - f0), "gpu_launches": launches,
+           "launch_mode": ("first part (filter .. proofs, NCCL included) as one CUDA graph, list exchange eager"
+                           if graphed else "eager"),
            "exchange": "all_reduce(2048-bin key histograms) x3 + all_gather(quantile bucket), all_gather(8 counters), "
                        "all_gather(kept troughs | peaks | strength) -- never the envelope",
            "e2e": {"value": audio_hours / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,

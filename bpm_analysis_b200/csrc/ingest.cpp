@@ -8,9 +8,12 @@
 // small pool of host threads walks the recording with software prefetch (one cache miss per kept
 // frame, many in flight per core) and packs the frames into a pinned staging buffer; one plain
 // cudaMemcpyAsync of the packed frames (2.2 MB for the recording above) does the rest.
+#include <sched.h>
+
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -20,6 +23,36 @@
 #include "../../include/bpm_host.h"
 
 namespace {
+
+// cores this process may run on (its affinity mask: a container / NUMA binding is respected)
+int usable_cores() {
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+    const int n = CPU_COUNT(&set);
+    if (n > 0) return n;
+  }
+  const unsigned hw = std::thread::hardware_concurrency();
+  return hw == 0 ? 4 : static_cast<int>(hw);
+}
+
+// Threads one call uses when the caller does not say: BPM_HOST_THREADS, else this process's share of the
+// cores -- with one process per GPU (torchrun sets LOCAL_WORLD_SIZE) the ranks of a box divide the cores
+// between them instead of each starting one thread per core (8 ranks x 32 threads on 96 cores ran the
+// gather 6x slower than one rank alone).
+int default_threads() {
+  if (const char* e = std::getenv("BPM_HOST_THREADS")) {
+    const int v = std::atoi(e);
+    if (v > 0) return v;
+  }
+  int ranks = 1;
+  if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) {
+    const int v = std::atoi(e);
+    if (v > 0) ranks = v;
+  }
+  const int n = usable_cores() / ranks;
+  return n < 1 ? 1 : n;
+}
 
 // A fixed pool: the threads are created on first use and sleep on a condition variable between
 // jobs (creating 16 threads per recording would cost more than the gather itself).
@@ -60,8 +93,7 @@ class Pool {
 
  private:
   Pool() {
-    unsigned hw = std::thread::hardware_concurrency();
-    int n = hw == 0 ? 4 : static_cast<int>(hw);
+    int n = usable_cores();
     if (n > 32) n = 32;
     for (int i = 1; i < n; ++i) workers_.emplace_back([this] { loop(); });
     for (auto& t : workers_) t.detach();
@@ -117,7 +149,10 @@ void gather_range(const char* src, int64_t pitch, char* dst, int64_t j0, int64_t
 
 extern "C" {
 
-int bpm_host_threads(void) { return Pool::get().size(); }
+int bpm_host_threads(void) {
+  const int d = default_threads(), p = Pool::get().size();
+  return d < p ? d : p;
+}
 
 int bpm_host_gather_frames(const void* pcm, int64_t frame_bytes, int64_t n_frames, int64_t stride, void* out,
                            int n_threads) {
@@ -127,7 +162,7 @@ int bpm_host_gather_frames(const void* pcm, int64_t frame_bytes, int64_t n_frame
   const char* src = static_cast<const char*>(pcm);
   char* dst = static_cast<char*>(out);
   Pool& pool = Pool::get();
-  int parts = n_threads <= 0 ? pool.size() : n_threads;
+  int parts = n_threads <= 0 ? default_threads() : n_threads;
   if (parts > pool.size()) parts = pool.size();
   if (m < 4096 * static_cast<int64_t>(parts)) parts = static_cast<int>(m / 4096) + 1;   // tiny recordings: fewer threads
   const std::function<void(int, int)> body = [&](int part, int nparts) {

@@ -227,8 +227,14 @@ class DeviceEngine:
         self._ring = torch.empty((self.RING_SLOTS, 16), dtype=torch.int64).pin_memory()
         self._ring_next = 0
         self._ring_lock = threading.Lock()
+        # constants of CAPTURED steps must keep their pinned source for the life of the graph: slots of
+        # this pool are handed out once and never reused
+        self._const_pool = torch.empty((self.CONST_SLOTS, 16), dtype=torch.int64).pin_memory()
+        self._const_next = 0
+        self.capturing = False
 
     RING_SLOTS = 256
+    CONST_SLOTS = 256
 
     def small_i64(self, values: Sequence[int]) -> torch.Tensor:
         """A few int64 constants -> device WITHOUT stalling the stream: torch.tensor(list, device=cuda)
@@ -236,8 +242,14 @@ class DeviceEngine:
         in a ring of pinned slots (a slot is reused RING_SLOTS calls later; every step of the chunked
         front end waits for the device at least once, long before that)."""
         with self._ring_lock:
-            slot = self._ring[self._ring_next][:len(values)]
-            self._ring_next = (self._ring_next + 1) % self.RING_SLOTS
+            if self.capturing:
+                if self._const_next >= self.CONST_SLOTS:
+                    raise RuntimeError("DeviceEngine: out of constant slots for captured steps")
+                slot = self._const_pool[self._const_next][:len(values)]
+                self._const_next += 1
+            else:
+                slot = self._ring[self._ring_next][:len(values)]
+                self._ring_next = (self._ring_next + 1) % self.RING_SLOTS
         slot.copy_(torch.tensor(list(values), dtype=torch.int64))
         return slot.to(self.device, non_blocking=True)
 
@@ -263,13 +275,17 @@ class DeviceEngine:
         return torch.full((n,), float(value), dtype=torch.float64, device=self.device)
 
     # a1 on a slice of the stream
-    def frontend(self, pcm: torch.Tensor, n_in: int, plan, channels: int, np_dtype) -> Tuple[torch.Tensor, torch.Tensor]:
+    def frontend(self, pcm: torch.Tensor, n_in: int, plan, channels: int, np_dtype,
+                 want_filtered: bool = True) -> Tuple[Optional[torch.Tensor], torch.Tensor]:
         rt, nat, L = self.rt, self.nat, self.lib
         m = plan.m(n_in)
         items, items_dev = self._items(n_in, m)
         design, design_host = rt.design_images(plan)
         f64 = dict(dtype=torch.float64, device=self.device)
-        filt, env, amax = torch.empty(m, **f64), torch.empty(m, **f64), torch.empty(1, **f64)
+        env, amax = torch.empty(m, **f64), torch.empty(1, **f64)
+        # the band-passed signal itself is optional when the envelope is fused into the backward pass
+        fused = plan.block == 1 and plan.rate // 10 <= 65
+        filt = torch.empty(m, **f64) if (want_filtered or not fused) else None
         nb = int(L.bpm_frontend_workspace_bytes(m, 1))
         ws = self._ws(nb)
         nat.check(L.bpm_frontend(rt._ptr(pcm), nat.PCM_DTYPES[np.dtype(np_dtype)], channels, rt._ptr(items_dev),
@@ -686,6 +702,7 @@ class ShardedFrontEnd(ChunkedFrontEnd):
                  pcm_dtype=np.int16, channels: int = 1, analysis_halo: Optional[int] = None):
         super().__init__(n_frames, sample_rate, params, comm, engine, plan, pcm_dtype, channels)
         self.filter_halo = self.chunks.halo
+        self._graph = None
         self._set_halo(analysis_halo)
 
     @classmethod
@@ -693,6 +710,7 @@ class ShardedFrontEnd(ChunkedFrontEnd):
                      analysis_halo: Optional[int] = None) -> "ShardedFrontEnd":
         self = super().for_envelope(m, rate, params, comm, engine)
         self.filter_halo = 0
+        self._graph = None
         self._set_halo(analysis_halo)
         return self
 
@@ -715,11 +733,10 @@ class ShardedFrontEnd(ChunkedFrontEnd):
         return ChunkGeometry(n, c0 - e0, c1 - e0, 0 if at_start else doubt, n if at_end else n - doubt, at_start,
                              at_end, self.filter_halo, self.distance, self.window)
 
-    def analyse_sharded(self, env_ext: torch.Tensor) -> Optional[Dict[str, torch.Tensor]]:
-        """Per-chunk evaluation; None if some rank could not prove its chunk.  The host waits for the
-        device ONCE (for the table of proofs and list lengths of all ranks)."""
+    # -- the step in two parts around its one wait for the device
+    def _enqueue(self, env_ext: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Everything up to the all-gathered table of proofs, enqueued (no host synchronisation)."""
         E, P, ch, comm = self.engine, self.params, self.chunks, self.comm
-        e0 = ch.ext(comm.rank)[0]
         g = self.geometry()
         env_core = env_ext[g.core_lo:g.core_hi]
         # stream-wide thresholds (:1067, :225)
@@ -730,8 +747,15 @@ class ShardedFrontEnd(ChunkedFrontEnd):
         else:
             thr, qstat = stream_quantiles(E, comm, env_core, ch.m, [q_t, q_p])
         c = E.chunk_chain(env_ext, thr, qstat, g, P)
-        table_dev = comm.all_gather_rows(c["proof"]).contiguous()
-        table = table_dev.cpu().numpy()                           # the chunk's one wait for the device
+        c.update(env=env_ext, env_core=env_core, thr=thr, table=comm.all_gather_rows(c["proof"]).contiguous())
+        return c
+
+    def _finish(self, c: Dict[str, torch.Tensor]) -> Optional[Dict[str, torch.Tensor]]:
+        """The wait, the verdict of all ranks, the one list exchange, the stream-wide deviation series."""
+        E, P, ch, comm = self.engine, self.params, self.chunks, self.comm
+        e0 = ch.ext(comm.rank)[0]
+        g = self.geometry()
+        table = c["table"].cpu().numpy()                          # the chunk's one wait for the device
         mine = table[comm.rank]
         self.last_proof = {"ok": not bool(mine[0]), "proven_floor": (int(mine[6]) + e0, int(mine[7]) + e0),
                            "table": table}
@@ -740,17 +764,22 @@ class ShardedFrontEnd(ChunkedFrontEnd):
         # ONE exchange for the three lists: [kept troughs | peaks | strength bits], padded to the longest
         cap_t, cap_p = int(table[:, 2].max()), int(table[:, 3].max())
         rows = comm.all_gather_rows(E.chunk_pack(c, e0, cap_t, cap_p))
-        troughs, peaks_all, strength_all = E.chunk_unpack(rows, table_dev, cap_t, cap_p, int(table[:, 2].sum()),
+        troughs, peaks_all, strength_all = E.chunk_unpack(rows, c["table"], cap_t, cap_p, int(table[:, 2].sum()),
                                                           int(table[:, 3].sum()))
         deviation, smoothed = E.deviation_series(strength_all, float(P["deviation_smoothing_factor"]))
         return {"troughs": troughs, "peaks": peaks_all, "strength": strength_all, "deviation": deviation,
-                "smoothed_dev": smoothed, "envelope_core": env_core, "floor_core": c["floor"][g.core_lo:g.core_hi],
-                "thresholds": thr}
+                "smoothed_dev": smoothed, "envelope_core": c["env_core"],
+                "floor_core": c["floor"][g.core_lo:g.core_hi], "thresholds": c["thr"]}
 
-    def analyse_local(self, env_ext: torch.Tensor, gather_series: bool = False) -> Dict[str, torch.Tensor]:
+    def analyse_sharded(self, env_ext: torch.Tensor) -> Optional[Dict[str, torch.Tensor]]:
+        """Per-chunk evaluation; None if some rank could not prove its chunk.  The host waits for the
+        device ONCE (for the table of proofs and list lengths of all ranks)."""
+        return self._finish(self._enqueue(env_ext))
+
+    def _complete(self, out: Optional[Dict[str, torch.Tensor]], env_ext: torch.Tensor,
+                  gather_series: bool) -> Dict[str, torch.Tensor]:
         ch, comm = self.chunks, self.comm
         (c0, c1), (e0, _) = ch.core(comm.rank), ch.ext(comm.rank)
-        out = self.analyse_sharded(env_ext)
         if out is None:                                           # exact by construction, slower
             env = torch.cat(comm.all_gather(env_ext[c0 - e0:c1 - e0].contiguous(), ch.core_sizes()))
             out = ChunkedFrontEnd.analyse(self, env)
@@ -764,16 +793,70 @@ class ShardedFrontEnd(ChunkedFrontEnd):
             out["floor"] = torch.cat(comm.all_gather(out["floor_core"].contiguous(), sizes))
         return out
 
+    def analyse_local(self, env_ext: torch.Tensor, gather_series: bool = False) -> Dict[str, torch.Tensor]:
+        return self._complete(self.analyse_sharded(env_ext), env_ext, gather_series)
+
     def analyse(self, env: torch.Tensor, gather_series: bool = True) -> Dict[str, torch.Tensor]:
         """On an envelope every rank already holds (for_envelope)."""
         e0, e1 = self.chunks.ext(self.comm.rank)
         return self.analyse_local(env[e0:e1], gather_series)
 
-    def run(self, pcm_slice, gather_series: bool = False) -> Dict[str, torch.Tensor]:
+    def _first_part(self, pcm_slice, want_filtered: bool):
+        f0, f1 = self.chunks.frames(self.comm.rank)
+        filt, env = self.engine.frontend(pcm_slice, f1 - f0, self.plan, self.channels, self.np_dtype, want_filtered)
+        c = self._enqueue(env)
+        c["filt"] = filt
+        return c
+
+    def _captured(self, pcm_slice, want_filtered: bool):
+        """The step's first part as ONE CUDA graph (its NCCL collectives included): a replay costs the
+        host ~20 us instead of ~0.7 ms of Python and launches, which is what bounds a step once the
+        chunks are short (8 GPUs: 0.75 ms of kernels per rank).  Captured for one input tensor; a
+        different tensor (or any capture failure) falls back to the eager path."""
+        key = (pcm_slice.data_ptr(), pcm_slice.numel(), bool(want_filtered))
+        st = self._graph
+        if st is not None and st["key"] == key:
+            st["graph"].replay()
+            return st["out"]
+        if st is not None and st.get("failed"):
+            return self._first_part(pcm_slice, want_filtered)
+        E = self.engine
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                        # warm-up: lazy initialisations, NCCL set-up
+                self._first_part(pcm_slice, want_filtered)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            E.capturing = True
+            try:
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    out = self._first_part(pcm_slice, want_filtered)
+            finally:
+                E.capturing = False
+            self._graph = {"key": key, "graph": graph, "out": out}
+            graph.replay()
+            return out
+        except Exception as e:                                   # noqa: BLE001 - the eager path is always valid
+            import warnings
+            warnings.warn(f"ShardedFrontEnd: CUDA-graph capture of the step failed ({e!r}); running eagerly")
+            self._graph = {"key": None, "failed": True}
+            torch.cuda.synchronize()
+            return self._first_part(pcm_slice, want_filtered)
+
+    def run(self, pcm_slice, gather_series: bool = False, want_filtered: bool = True,
+            graph: bool = False) -> Dict[str, torch.Tensor]:
+        """graph=True: replay the captured first part (DistComm / one rank only; the ranks of a thread
+        world synchronise through the host and cannot be captured)."""
         ch, r = self.chunks, self.comm.rank
-        f0, f1 = ch.frames(r)
         (c0, c1), (e0, _) = ch.core(r), ch.ext(r)
-        filt, env = self.engine.frontend(pcm_slice, f1 - f0, self.plan, self.channels, self.np_dtype)
-        out = self.analyse_local(env, gather_series)
-        out["filtered_core"] = filt[c0 - e0:c1 - e0]
+        if graph and isinstance(self.comm, DistComm):
+            c = self._captured(pcm_slice, want_filtered)
+        else:
+            c = self._first_part(pcm_slice, want_filtered)
+        out = self._complete(self._finish(c), c["env"], gather_series)
+        if c["filt"] is not None:
+            out["filtered_core"] = c["filt"][c0 - e0:c1 - e0]
         return out
+

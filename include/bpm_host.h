@@ -196,7 +196,9 @@ int bpm_fix_rhythmic_discontinuities(const int64_t* s1_peaks, int64_t n_s1, cons
  * frame_bytes = channels * sample size, kept in the PCM's own dtype).  `out` is normally a pinned
  * staging buffer that one cudaMemcpyAsync then moves to the device, where bpm_frontend / bpm_stage_a
  * read it with stride 1 -- bit-identical to passing the whole recording with this stride.
- * n_threads <= 0: all threads of the library's pool (bpm_host_threads()). */
+ * n_threads <= 0: bpm_host_threads() threads = $BPM_HOST_THREADS, else this process's share of the cores
+ * it may run on (its affinity mask divided by $LOCAL_WORLD_SIZE, which torchrun sets: the ranks of a
+ * box split the cores instead of oversubscribing them), at most the pool's 32. */
 int bpm_host_threads(void);
 int bpm_host_gather_frames(const void* pcm, int64_t frame_bytes, int64_t n_frames, int64_t stride, void* out,
                            int n_threads);

@@ -23,7 +23,7 @@ class OracleEngine:
     def full(self, n, value):
         return torch.full((n,), float(value), dtype=torch.float64)
 
-    def frontend(self, pcm, n_in, plan, channels, np_dtype):
+    def frontend(self, pcm, n_in, plan, channels, np_dtype, want_filtered=True):
         x = _np(pcm)
         x = x.reshape(n_in, channels) if channels > 1 else x.reshape(n_in)
         env, _, filt = ref_port.preprocess_pcm(x, self.sample_rate, self.params)
