@@ -55,9 +55,10 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--no-zero-copy", action="store_true", help="e2e: copy the whole recording to the device first")
     ap.add_argument("--e2e-depth", type=int, default=3, help="e2e: recordings in flight (1 = strictly serial steps)")
-    ap.add_argument("--e2e-ingest", default="host", choices=["host", "ce", "sm"],
-                    help="e2e: kept frames cross PCIe by a strided copy-engine copy (ce) or by a kernel reading mapped "
-                         "pinned memory (sm)")
+    ap.add_argument("--e2e-ingest", default="auto", choices=["auto", "host", "ce", "sm"],
+                    help="e2e_pipelined: the kept frames are packed by the host cores and copied (host), cross PCIe as a "
+                         "strided copy-engine copy (ce), or are read from mapped pinned memory by a kernel (sm); auto "
+                         "(default) measures the three on this box before the timed region and keeps the fastest")
     ap.add_argument("--dump-kernels", default=None, help="write the per-kernel table to this JSON file")
     ap.add_argument("--workload", default="recordings", choices=["recordings", "stream", "batch", "holter", "sweep"],
                     help="recordings: one C2 recording per GPU (weak scaling, the headline). stream: ONE C2 "
@@ -497,8 +498,17 @@ def run_b200(args):
     if zero_copy:
         from bpm_analysis_b200.runtime import StageAPipeline
         depth = max(1, args.e2e_depth)
-        pipe = StageAPipeline(len(pcm), sr, params, depth=depth,
-                              beat_runner_args=(len(beat_idx), rate, params, hr_extrema_distance(beat_idx, rate)),
+        beat_args = (len(beat_idx), rate, params, hr_extrema_distance(beat_idx, rate))
+        ingest_ms = None
+        if args.e2e_ingest == "auto":
+            # which ingest is fastest is a property of the host (cores per GPU, PCIe root complexes): measured
+            # here, untimed, with all ranks of the run measuring the same candidate at the same time
+            from bpm_analysis_b200.runtime import time_pipeline_ingests
+            ingest_ms = time_pipeline_ingests(len(pcm), sr, params, pcm_pin, beats_pin, beat_args, depth=depth,
+                                              between=barrier)
+            ingest_ms = {k: max_over_ranks(v) for k, v in ingest_ms.items()}
+            args.e2e_ingest = min(ingest_ms, key=ingest_ms.get)
+        pipe = StageAPipeline(len(pcm), sr, params, depth=depth, beat_runner_args=beat_args,
                               use_graph=not args.no_graph, ingest=args.e2e_ingest)
 
         def e2e_run(n_steps):
@@ -684,6 +694,7 @@ def run_b200(args):
                            "raw_samples": len(pcm), "envelope_samples": M, "beats": len(beat_idx),
                            "l2": "inputs larger than L2 (PCM %.1f MB per step)" % (len(pcm) * 2 / 1e6),
                            "parallelism": f"{world} x independent recordings, no collective",
+                           "host_cores": len(os.sched_getaffinity(0)),
                            **({"l2_fetch_granularity": int(l2_fetch)} if l2_fetch else {})},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
@@ -695,6 +706,8 @@ def run_b200(args):
                         "ingest": "bpm_host_gather_frames (host cores pack x[::ds] into pinned staging) + one cudaMemcpyAsync; "
                                   "results come back into pinned host arrays handed to the caller"},
                 "e2e_pipelined": {"value": world * audio_hours / (pipe_ms / 1e3), "unit": UNIT, "ms_per_step": pipe_ms,
+                        "ingest_mode": args.e2e_ingest if zero_copy else "full copy",
+                        "ingest_candidates_ms": ingest_ms if zero_copy else None,
                         "h2d_bytes_per_step": int(pipe_h2d), "d2h_bytes_per_step": int(pipe_d2h),
                         "api": "runtime.StageAPipeline (throughput API: several recordings in flight)",
                         "ingest": (PIPE_INGEST[args.e2e_ingest] + f"{args.e2e_depth}-deep pipeline ingest | compute | "

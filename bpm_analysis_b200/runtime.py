@@ -8,6 +8,7 @@ lengths, filter design tables).
 from __future__ import annotations
 
 import ctypes as C
+import time
 import os
 import threading
 from collections import OrderedDict
@@ -763,6 +764,38 @@ class GraphedStep:
 
     def launch(self) -> None:
         self.graph.replay()
+
+
+def time_pipeline_ingests(n_in: int, sample_rate: int, params: Dict, pcm_pinned: torch.Tensor,
+                          beats_pinned: Optional[torch.Tensor] = None, beat_runner_args=None, depth: int = 2,
+                          candidates: Sequence[str] = ("host", "ce", "sm"), rounds: int = 6, between=None) -> Dict[str, float]:
+    """ms per recording of ``StageAPipeline`` for each ingest, measured on the caller's own recording.
+    Which ingest wins depends on the HOST: packing the kept frames needs cores (a box with 16 cores per
+    GPU packs a 60-min recording in 0.75 ms, one with 4 cores per GPU in 3 ms), the copy-engine and
+    zero-copy forms need PCIe read requests instead (~0.7 G/s per GPU, ~1.9 G/s per root complex).  A
+    service measures once at start-up and keeps the fastest.  ``between``: called between candidates
+    (a barrier when several ranks measure at the same time, so that they contend as they will later)."""
+    out: Dict[str, float] = {}
+    for mode in candidates:
+        if between is not None:
+            between()
+        pipe = StageAPipeline(n_in, sample_rate, params, depth=depth, beat_runner_args=beat_runner_args, ingest=mode)
+
+        def run(n):
+            for k in range(n):
+                if k >= depth:
+                    pipe.wait(k - depth)
+                pipe.submit(k, pcm_pinned, beats_pinned)
+            for k in range(max(0, n - depth), n):
+                pipe.wait(k)
+
+        run(depth + 1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run(rounds)
+        out[mode] = (time.perf_counter() - t0) * 1e3 / rounds
+        del pipe
+    return out
 
 
 class StageAPipeline:
