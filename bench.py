@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--no-stream", action="store_true", help="skip the `stream` sub-record (one 24-h recording "
                     "time-chunked over the GPUs of this run)")
     ap.add_argument("--stream-hours", type=float, default=24.0)
+    ap.add_argument("--no-extras", action="store_true", help="headline only: skip the fullrate / sweep / stream sub-records")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--no-zero-copy", action="store_true", help="e2e: copy the whole recording to the device first")
@@ -679,10 +680,25 @@ def run_b200(args):
                "sample": f"{reps} x first {sample_sec:g} s of the same recording, a1..a8, one core "
                          f"(the reference is single-threaded); {sum(ts):.2f} s in all"}
 
-    stream_rec = None
+    stream_rec, fullrate_rec, sweep_rec = None, None, None
     was_graphed = graphed is not None
-    if not args.no_stream:
+    if not args.no_extras and args.filter_mode == "parity":
         del A, Bn, graphed
+        torch.cuda.empty_cache()
+        fullrate_rec = fullrate_record(args, rank, world, dev, params, pcm, sr, max_over_ranks, barrier)
+        torch.cuda.empty_cache()
+        sw = sweep_record(args, rank, world, params)
+        barrier()
+        sw_ms = max_over_ranks(sw["ms_this_rank"])
+        if rank == 0:
+            hours = sw["settings"] * 0.5
+            sweep_rec = {"workload": "C5: 256 band-pass / noise-floor settings over one synthetic 30-min 48 kHz recording, "
+                                     f"settings sharded over {world} rank(s)", "ms_per_sweep": sw_ms,
+                         "value": hours / (sw_ms / 1e3), "unit": UNIT, "settings": sw["settings"],
+                         "rejected_like_the_reference_rank0": sw["rejected_like_the_reference"],
+                         "timing": "wall clock around the whole sweep (one host synchronisation at its end), max over ranks"}
+        torch.cuda.empty_cache()
+    if not args.no_stream and not args.no_extras:
         torch.cuda.empty_cache()
         stream_rec = stream_record(args, rank, world, dev, params)
 
@@ -715,11 +731,91 @@ def run_b200(args):
                                   "cudaMemcpyAsync of the whole recording from pinned host memory, serial steps"},
                 "gpu_launches": launches_per_step * args.steps if was_graphed else launches,
                 "launch_mode": "cuda-graph replay" if was_graphed else "eager", "roofline": roofline,
-                "cpu_baseline": cpu, "parity": parity, "stream": stream_rec, "kernels": kernels}
+                "cpu_baseline": cpu, "parity": parity, "fullrate": fullrate_rec, "sweep": sweep_rec,
+                "stream": stream_rec, "kernels": kernels}
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def fullrate_record(args, rank: int, world: int, dev, params, pcm, sr, max_over_ranks, barrier) -> dict:
+    """The north star's headline filter ("full-rate Butterworth SOS band-pass", then decimation) on the same
+    recording, device-resident, a1..a4: every one of the N raw samples is read and contracted
+    (k_contract_i16), where the reference's own order (decimate first) reads one frame in `ds`."""
+    import torch
+    from bpm_analysis_b200.runtime import GraphedStep, StageARunner, profile_kernels
+    fp = dict(params, filter_mode="fullrate")
+    A = StageARunner([len(pcm)], sr, fp, want_filtered=True)
+    A.upload([pcm])
+    A.launch()
+    torch.cuda.synchronize()
+    g = None if args.no_graph else GraphedStep(A)
+    step = A.launch if g is None else g.launch
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    rec = {"filter_mode": "fullrate", "scope": "a1..a4, device-resident", "ms_per_step": ms,
+           "value": world * (len(pcm) / sr / 3600.0) / (ms / 1e3), "unit": UNIT, "raw_samples": len(pcm),
+           "envelope_samples": A.total_m}
+    prof = profile_kernels(lambda: [A.launch() for _ in range(5)])
+    torch.cuda.synchronize()
+    peak, peak_src = measured_peak_gbs()
+    shp = {"N": len(pcm), "M": A.total_m, "T": int(A.out["trough_count"][0]), "P": int(A.out["peak_count"][0]), "B": 0}
+    name = "k_contract_i16"
+    if name in prof:
+        cnt, tms = prof[name]
+        us = tms * 1e3 / cnt
+        ab = algorithmic_bytes(name, shp, "fullrate")
+        rec["roofline"] = {"kernel": name, "bound": "hbm", "achieved": round(ab / (us * 1e-6) / 1e9, 1), "peak": peak,
+                           "unit": "GB/s", "frac": round(ab / (us * 1e-6) / 1e9 / peak, 4), "avg_launch_us": round(us, 2),
+                           "alg_bytes": ab, "peak_source": peak_src,
+                           "share_of_step": round(tms / (sum(v[1] for v in prof.values()) or 1.0), 4)}
+    if rank == 0 and not args.no_cpu_baseline:
+        # parity on a bounded sample: scipy's sosfiltfilt at the full rate over the first 5 minutes, compared
+        # on the first 4 (the prefix's own end transient, rho^k < 1e-22 after 4 k samples, is far away)
+        from scipy.signal import butter, sosfiltfilt
+        n5, keep_sec = int(300 * sr), 240
+        nyq = 0.5 * sr
+        sos = butter(2, [float(fp.get("lowcut_hz", 20.0)) / nyq, float(fp.get("highcut_hz", 150.0)) / nyq], btype="band",
+                     output="sos")
+        y = sosfiltfilt(sos, pcm[:n5].astype(np.float64), padlen=15)          # oracle/ref_port.py, 'fullrate'
+        ds = A.plan.stride * A.plan.block
+        k = keep_sec * sr // ds
+        got = A.out["filtered"][:k].cpu().numpy()
+        want = y[::ds][:k]
+        rec["parity_filtered_first_4min"] = {"rel_err": float(np.max(np.abs(got - want)) / np.max(np.abs(want))),
+                                             "against": "scipy.signal.sosfiltfilt at the full rate, then [::ds]",
+                                             "tolerance": 1e-6}
+    del A, g
+    return rec
+
+
+def sweep_record(args, rank: int, world: int, params) -> dict:
+    """BASELINE configs[4] (C5) in front of the driver: 256 band-pass / noise-floor settings over one 30-min
+    recording, sharded over the ranks (no collective); parity of settings against the oracle is the job
+    of `--workload sweep` and tests/test_configs_gpu.py."""
+    import torch
+    from bpm_analysis_b200 import sweep, synth
+    settings = synth.c5_settings()
+    pcm, sr, _ = synth.config_c5(seed=5, duration_sec=1800.0)
+    res = sweep.run_sweep(pcm, sr, params, settings, rank=rank, world=world)
+    torch.cuda.synchronize()
+    n = 2
+    t0 = time.perf_counter()
+    for _ in range(n):
+        res = sweep.run_sweep(pcm, sr, params, settings, rank=rank, world=world)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / n
+    return {"ms_this_rank": ms, "settings_this_rank": len(res), "settings": len(settings),
+            "rejected_like_the_reference": sum(1 for r in res if "error" in r)}
 
 
 def stream_record(args, rank: int, world: int, dev, params) -> dict:
