@@ -777,7 +777,14 @@ def fullrate_record(args, rank: int, world: int, dev, params, pcm, sr, max_over_
         rec["roofline"] = {"kernel": name, "bound": "hbm", "achieved": round(ab / (us * 1e-6) / 1e9, 1), "peak": peak,
                            "unit": "GB/s", "frac": round(ab / (us * 1e-6) / 1e9 / peak, 4), "avg_launch_us": round(us, 2),
                            "alg_bytes": ab, "peak_source": peak_src,
-                           "share_of_step": round(tms / (sum(v[1] for v in prof.values()) or 1.0), 4)}
+                           "share_of_step": round(tms / (sum(v[1] for v in prof.values()) or 1.0), 4),
+                           # the kernel is bound by the FP64 (tensor) pipe, not by HBM: 8 multiply-adds per 2-byte sample
+                           "fp64": {"flops": 16.0 * len(pcm), "achieved_tflops": round(16.0 * len(pcm) / (us * 1e-6) / 1e12, 2),
+                                    "peak_tflops": 37.2, "frac": round(16.0 * len(pcm) / (us * 1e-6) / 37.2e12, 4),
+                                    "peak_source": "148 SMs x 64 FP64 lanes x 2 x 1.965 GHz (ncu: the DMMA sub-pipe's own "
+                                                   "peak is one m8n8k4 per 4.1 cycles per SM)"},
+                           "note": "mma.m8n8k4.f64 on the FP64 tensor pipe (k_contract_i16_mma); the pipe, not HBM, is the "
+                                   "ceiling: 2.76 GFLOP per launch"}
     if rank == 0 and not args.no_cpu_baseline:
         # parity on a bounded sample: scipy's sosfiltfilt at the full rate over the first 5 minutes, compared
         # on the first 4 (the prefix's own end transient, rho^k < 1e-22 after 4 k samples, is far away)

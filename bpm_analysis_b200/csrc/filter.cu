@@ -31,7 +31,8 @@ int sosfilt_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* ite
 size_t sosfilt_workspace_bytes(int64_t total_m, int n_items);
 // contract.cu
 int contract_run(PcmView pv, const BpmItem* items, int n_items, const BatchShape& sh, int64_t stride,
-                 const double* design, int block, double* uf, double* ub0, double* xe, cudaStream_t st);
+                 const double* design, const double* design_host, int block, double* uf, double* ub0, double* xe,
+                 cudaStream_t st);
 
 // ------------------------------------------------------------------ init / tail
 // One warp per recording: the lanes fetch the (strided, possibly reflected) samples with
@@ -556,7 +557,7 @@ int frontend_run(const void* pcm, int pcm_dtype, int channels, const BpmItem* it
   BPM_TRY(carve_frontend(ws, sh.total_m, n_items, block, &b));
   PcmView pv{pcm, pcm_dtype, channels};
 
-  BPM_TRY(contract_run(pv, items, n_items, sh, stride, design, block, b.uf, b.ub0, b.xe, st));
+  BPM_TRY(contract_run(pv, items, n_items, sh, stride, design, design_host, block, b.uf, b.ub0, b.xe, st));
   BPM_KERNEL(k_filter_init);
   k_filter_init<<<cdiv(n_items, FE_WARPS), 32 * FE_WARPS, 0, st>>>(pv, items, n_items, stride, design, b.s0);
   BPM_LAUNCH_OK();
