@@ -1,5 +1,6 @@
 // Shared helpers for libbpm_b200 (sm_100a).  See include/bpm_b200.h for the ABI.
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
@@ -16,9 +17,12 @@ constexpr int SCAN_TILE = SCAN_CHUNK * SCAN_THREADS;
 constexpr int N_POW = 16;
 constexpr int MIN_PERIODS = 3;       // rolling(..., min_periods=3), bpm_analysis.py:1085
 
-extern int64_t g_launches;            // counted by BPM_LAUNCH_OK
-extern const char* g_cur_kernel;      // set by BPM_KERNEL just before a launch
-extern bool g_profiling;              // bpm_profile_begin / bpm_profile_end
+// The library is driven from several host threads (GUI / server workers, the ranks of a thread world):
+// the launch counter is atomic, the "kernel being launched" label is per thread.  The per-kernel event
+// profile (bpm_profile_begin / end) is a single-threaded measuring mode by contract.
+extern std::atomic<int64_t> g_launches;          // counted by BPM_LAUNCH_OK
+extern thread_local const char* g_cur_kernel;    // set by BPM_KERNEL just before a launch
+extern bool g_profiling;                         // bpm_profile_begin / bpm_profile_end
 void profile_mark(const char* name, cudaStream_t st);
 
 // BPM_KERNEL(name); name<<<...>>>(...); BPM_LAUNCH_OK();   -- `st` is the stream in scope
@@ -26,7 +30,7 @@ void profile_mark(const char* name, cudaStream_t st);
 
 #define BPM_LAUNCH_OK()                                                   \
   do {                                                                    \
-    ++::bpm::g_launches;                                                  \
+    ::bpm::g_launches.fetch_add(1, std::memory_order_relaxed);            \
     if (cudaGetLastError() != cudaSuccess) return BPM_ERR_CUDA;           \
     if (::bpm::g_profiling) ::bpm::profile_mark(::bpm::g_cur_kernel, st); \
   } while (0)

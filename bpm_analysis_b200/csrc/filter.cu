@@ -19,8 +19,8 @@
 
 namespace bpm {
 
-int64_t g_launches = 0;
-const char* g_cur_kernel = "?";
+std::atomic<int64_t> g_launches{0};
+thread_local const char* g_cur_kernel = "?";
 bool g_profiling = false;
 
 // sosfilt.cu

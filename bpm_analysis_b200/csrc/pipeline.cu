@@ -289,7 +289,7 @@ const char* bpm_error_string(int code) {
   }
 }
 
-int64_t bpm_launch_count(void) { return g_launches; }
+int64_t bpm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 
 int bpm_profile_begin(void* stream) {
