@@ -587,11 +587,87 @@ def hr_extrema_distance(beats: np.ndarray, rate: int, min_duration_sec: float = 
     return int((min_duration_sec / 2) / mean_gap)
 
 
+class _BeatSlot:
+    """Buffers (and, from the second use on, the CUDA graph) of the a5..a8 chain for ONE shape: number of
+    beats, length of the valid series, extrema distance and the window parameters.  The reference calls
+    the chain with a handful of list lengths per file (preliminary and final beats); a slot turns the
+    ~12 launches, 4 allocations and 3 copies of a call into one graph replay."""
+
+    def __init__(self, owner, b: int, n_series: int, dist: int, rate: int, window_us: int, win: int, step: int):
+        self.key = (b, n_series, dist, rate, window_us, win, step)
+        self.b, self.n_series, self.dist = b, n_series, dist
+        self.rate, self.window_us, self.win, self.step = rate, window_us, win, step
+        self.items, self.sitems = make_items([b], [b]), make_items([n_series], [n_series])
+        dev = owner.device
+        # int64 block on both sides: [list descriptor 4 | series descriptor 4 | beats b | stamps b | tops b | bottoms b | scalars 4]
+        self.stage = torch.empty(8 + b, dtype=torch.int64, pin_memory=True)
+        sn = self.stage.numpy()
+        sn[0:4] = self.items.view(np.int64).reshape(-1)
+        sn[4:8] = self.sitems.view(np.int64).reshape(-1)
+        self.iblk = torch.empty(8 + 4 * b + 4, dtype=torch.int64, device=dev)
+        self.fblk = torch.empty(7 * b + 8 + 1, dtype=torch.float64, device=dev)   # [inst | smoothed | times | hrv 4b | slopes 8 | prominence]
+        self.ws_bytes = max(int(owner.lib.bpm_find_peaks_workspace_bytes(b, 1)), 256)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.fh = torch.empty(7 * b + 8, dtype=torch.float64, pin_memory=True)
+        self.ih = torch.empty(3 * b + 4, dtype=torch.int64, pin_memory=True)
+        self.uses = 0
+        self.graph = None
+
+    def enqueue(self, lib, st: int) -> None:
+        b, items, sitems = self.b, self.items, self.sitems
+        self.iblk[:8 + b].copy_(self.stage, non_blocking=True)
+        ip, fp = self.iblk.data_ptr(), self.fblk.data_ptr()
+        P = lambda base, off: C.c_void_p(base + 8 * off)                      # noqa: E731 - element offset -> pointer
+        items_dev, sitems_dev, bd = P(ip, 0), P(ip, 4), P(ip, 8)
+        stamps, tops, bottoms, scal = P(ip, 8 + b), P(ip, 8 + 2 * b), P(ip, 8 + 3 * b), 8 + 4 * b
+        inst, smooth, times, hrv, slopes, prom = P(fp, 0), P(fp, b), P(fp, 2 * b), P(fp, 3 * b), P(fp, 7 * b), P(fp, 7 * b + 8)
+        nat.check(lib.bpm_bpm_series(bd, items_dev, _host_ptr(items), 1, self.rate, self.window_us, inst, smooth, times,
+                                     stamps, P(ip, scal), st))
+        # the series holds the valid intervals only (dt > 1e-6 s): its length was counted on the host
+        # with the same arithmetic, so the follow-up kernels get an exact descriptor
+        nat.check(lib.bpm_steepest_slope(smooth, stamps, P(ip, scal), sitems_dev, _host_ptr(sitems), 1, 0, 20.0, slopes,
+                                         _ptr(self.ws), self.ws_bytes, st))
+        if self.dist >= 1:
+            self.fblk[7 * b + 8:].fill_(5.0)
+            for sign, idx, k in ((+1, tops, 1), (-1, bottoms, 2)):
+                nat.check(lib.bpm_find_peaks(smooth, sign, None, prom, self.dist, sitems_dev, _host_ptr(sitems), 1, idx,
+                                             P(ip, scal + k), _ptr(self.ws), self.ws_bytes, st))
+        if b >= self.win:
+            nat.check(lib.bpm_windowed_hrv(bd, items_dev, _host_ptr(items), 1, self.rate, self.win, self.step, hrv,
+                                           P(ip, scal + 3), st))
+        self.fh.copy_(self.fblk[:7 * b + 8], non_blocking=True)
+        self.ih.copy_(self.iblk[8 + b:], non_blocking=True)
+
+    def launch(self, owner) -> None:
+        stream = owner.stream
+        self.uses += 1
+        if self.graph is None and self.uses >= 2 and os.environ.get("BPM_DROPIN_GRAPH", "1") != "0":
+            try:
+                stream.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
+                    self.enqueue(owner.lib, torch.cuda.current_stream().cuda_stream)
+                self.graph = g
+            except Exception:                                    # noqa: BLE001 - the eager path is always valid
+                self.graph = False
+                torch.cuda.synchronize()
+        if self.graph:
+            with torch.cuda.stream(stream):
+                self.graph.replay()
+        else:
+            with torch.cuda.stream(stream):
+                self.enqueue(owner.lib, stream.cuda_stream)
+
+
+MAX_BEAT_SLOTS = 8
+
+
 def beat_chain(owner, beats: np.ndarray, rate: int, window_us: int, win: int, step: int) -> Dict[str, object]:
     """a5..a8 of one beat list in one device round trip (see dropin.DropIn.beat_metrics): ONE upload
     (beat list + the two list descriptors in one pinned block), the kernels, TWO read-backs (one
-    float64 block, one int64 block), one synchronisation."""
-    lib, dev, stream = owner.lib, owner.device, owner.stream
+    float64 block, one int64 block), one synchronisation -- replayed as one CUDA graph from the second
+    call with the same shape on."""
+    stream = owner.stream
     from .dropin import _Trace
     tr = _Trace(owner.trace)
     b = int(beats.size)
@@ -604,52 +680,26 @@ def beat_chain(owner, beats: np.ndarray, rate: int, window_us: int, win: int, st
     res["n_series"] = n_series
     if n_series == 0:
         return res
-    items, sitems = make_items([b], [b]), make_items([n_series], [n_series])
-    # int64 block on both sides: [list descriptor 4 | series descriptor 4 | beats b | stamps b | tops b | bottoms b | scalars 4]
-    n_i = 8 + 4 * b + 4
-    stage = torch.empty(8 + b, dtype=torch.int64, pin_memory=True)
-    sn = stage.numpy()
-    sn[0:4] = items.view(np.int64).reshape(-1)
-    sn[4:8] = sitems.view(np.int64).reshape(-1)
-    sn[8:] = beats
+    slots = owner.__dict__.setdefault("beat_slots", OrderedDict())
+    key = (b, n_series, dist, int(rate), int(window_us), int(win), int(step))
+    slot = slots.get(key)
+    if slot is None:
+        slot = slots[key] = _BeatSlot(owner, *key)
+        while len(slots) > MAX_BEAT_SLOTS:
+            slots.popitem(last=False)
+    else:
+        slots.move_to_end(key)
+    slot.stage.numpy()[8:] = beats
     tr.mark("beat.host_prep")
-    with torch.cuda.stream(stream):
-        st = stream.cuda_stream
-        iblk = torch.empty(n_i, dtype=torch.int64, device=dev)
-        fblk = torch.empty(7 * b + 8 + 1, dtype=torch.float64, device=dev)    # [inst | smoothed | times | hrv 4b | slopes 8 | prominence]
-        iblk[:8 + b].copy_(stage, non_blocking=True)
-        ip, fp = iblk.data_ptr(), fblk.data_ptr()
-        P = lambda base, off: C.c_void_p(base + 8 * off)                      # noqa: E731 - element offset -> pointer
-        items_dev, sitems_dev, bd = P(ip, 0), P(ip, 4), P(ip, 8)
-        stamps, tops, bottoms, scal = P(ip, 8 + b), P(ip, 8 + 2 * b), P(ip, 8 + 3 * b), 8 + 4 * b
-        inst, smooth, times, hrv, slopes, prom = P(fp, 0), P(fp, b), P(fp, 2 * b), P(fp, 3 * b), P(fp, 7 * b), P(fp, 7 * b + 8)
-        nat.check(lib.bpm_bpm_series(bd, items_dev, _host_ptr(items), 1, rate, window_us, inst, smooth, times, stamps,
-                                     P(ip, scal), st))
-        # the series holds the valid intervals only (dt > 1e-6 s): its length was counted on the host
-        # with the same arithmetic, so the follow-up kernels get an exact descriptor
-        ws_bytes = max(int(lib.bpm_find_peaks_workspace_bytes(b, 1)), 256)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        nat.check(lib.bpm_steepest_slope(smooth, stamps, P(ip, scal), sitems_dev, _host_ptr(sitems), 1, 0, 20.0, slopes,
-                                         _ptr(ws), ws_bytes, st))
-        res["hr_distance"] = dist
-        if dist >= 1:
-            fblk[7 * b + 8:].fill_(5.0)
-            for sign, idx, k in ((+1, tops, 1), (-1, bottoms, 2)):
-                nat.check(lib.bpm_find_peaks(smooth, sign, None, prom, dist, sitems_dev, _host_ptr(sitems), 1, idx,
-                                             P(ip, scal + k), _ptr(ws), ws_bytes, st))
-        if b >= win:
-            nat.check(lib.bpm_windowed_hrv(bd, items_dev, _host_ptr(items), 1, rate, win, step, hrv, P(ip, scal + 3), st))
-        fh = torch.empty(7 * b + 8, dtype=torch.float64, pin_memory=True)
-        ih = torch.empty(3 * b + 4, dtype=torch.int64, pin_memory=True)
-        fh.copy_(fblk[:7 * b + 8], non_blocking=True)
-        ih.copy_(iblk[8 + b:], non_blocking=True)
+    slot.launch(owner)
     tr.mark("beat.enqueue")
     stream.synchronize()
     tr.mark("beat.wait")
-    f, i = fh.numpy(), ih.numpy()
+    f, i = slot.fh.numpy(), slot.ih.numpy()
     nv = int(i[3 * b])
     if nv != n_series:
         raise RuntimeError(f"beat series length: device {nv}, host {n_series}")
+    res["hr_distance"] = dist
     res.update(n_valid=nv, inst=f[:nv].copy(), smoothed=f[b:b + nv].copy(), times=f[2 * b:2 * b + nv].copy(),
                stamps=i[:nv].copy(), slopes=f[7 * b:7 * b + 8].copy())
     if dist >= 1:
