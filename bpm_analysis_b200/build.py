@@ -94,7 +94,7 @@ def build_native(force: bool = False, verbose: bool = False, extra_flags=()) -> 
 
 
 HOST_LIB_PATH = os.path.join(HERE, "libbpm_host.so")
-HOST_SOURCES = ["classifier.cpp", "corrections.cpp", "ingest.cpp"]
+HOST_SOURCES = ["classifier.cpp", "corrections.cpp", "ingest.cpp", "reports.cpp"]
 # -ffp-contract=off: the classifier's decisions must round exactly like CPython's float arithmetic
 GXX_FLAGS = ["-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-Wall",
              "-Wextra"]

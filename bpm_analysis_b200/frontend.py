@@ -429,7 +429,7 @@ def find_recovery_phase(bpm_series: pd.Series, bpm_times_sec: np.ndarray, params
 
 
 # --------------------------------------------------------------------------- install
-def install(ref_module, classifier: bool = True, corrections: bool = True):
+def install(ref_module, classifier: bool = True, corrections: bool = True, reports: bool = True):
     """Rebind the reference module's front-end names to this package.
 
     ``ref_module`` is an imported reference ``bpm_analysis`` module.  Callers that did
@@ -437,7 +437,8 @@ def install(ref_module, classifier: bool = True, corrections: bool = True):
     resolves these names from the module's globals at call time.  With ``classifier=True``
     (default) ``PeakClassifier.classify_peaks`` is rebound to the compiled sequential loop
     (``classifier.py`` -> libbpm_host.so) as well; with ``corrections=True`` (default) so are
-    ``correct_peaks_by_rhythm`` and ``_fix_rhythmic_discontinuities`` (``corrections.py``).
+    ``correct_peaks_by_rhythm`` and ``_fix_rhythmic_discontinuities`` (``corrections.py``); with
+    ``reports=True`` (default) ``ReportGenerator`` is the index-based writer of ``reports.py`` (same files).
     """
     for name in ("preprocess_audio", "_calculate_dynamic_noise_floor", "calculate_bpm_series",
                  "find_peak_recovery_rate", "find_peak_exertion_rate", "find_major_hr_inclines",
@@ -451,4 +452,7 @@ def install(ref_module, classifier: bool = True, corrections: bool = True):
     if corrections:
         from . import corrections as _corrections
         _corrections.install(ref_module)
+    if reports:
+        from . import reports as _reports
+        _reports.install_reports(ref_module)
     return ref_module

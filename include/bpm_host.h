@@ -203,6 +203,18 @@ int bpm_host_threads(void);
 int bpm_host_gather_frames(const void* pcm, int64_t frame_bytes, int64_t n_frames, int64_t stride, void* out,
                            int n_threads);
 
+/* ---- on-disk outputs ----------------------------------------------
+ * One text table in one call: for every i < n (rows with NaN b[i] left out when skip_nan_b != 0)
+ *     head  format(a[i], ".{prec_a}f")  mid  format(b[i], ".{prec_b}f")  tail
+ * with bpm_host_format_fixed's digits (= Python's).  Replaces the per-row f-strings of the
+ * `_bpm_plot.csv` writer (bpm_analysis.py:466-469: head "", mid ",", tail "\r\n", 3 / 3 digits) and
+ * of the summary's heartbeat table (:979-981: "| ", " | ", " |\n", 2 / 1 digits).
+ * Returns the number of bytes the table takes; if that exceeds `capacity` the contents of `out`
+ * are unspecified and the call is to be repeated with a buffer of that size.  No NUL is appended.
+ * Negative: BPM_HOST_ERR_ARG. */
+int64_t bpm_host_format_rows(const double* a, const double* b, int64_t n, int prec_a, int prec_b, const char* head,
+                             const char* mid, const char* tail, int skip_nan_b, char* out, int64_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

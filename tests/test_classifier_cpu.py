@@ -51,7 +51,7 @@ def test_host_library_exports_header_symbols():
     lib = ctypes.CDLL(classifier.HOST_LIB_PATH)
     header = open(os.path.join(REPO, "include", "bpm_host.h")).read()
     from bpm_analysis_b200 import corrections
-    declared = set(re.findall(r"^\s*(?:int|void)\s+(bpm_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:int|void|int64_t)\s+(bpm_\w+)\s*\(", header, flags=re.M))
     assert declared == set(classifier.EXPORTED_SYMBOLS) | set(corrections.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name

@@ -109,6 +109,22 @@ def test_reference_orchestrator_with_gpu_front_end(case, tmp_path):
     for k in wm["hrv_summary"]:
         assert gm["hrv_summary"][k] == pytest.approx(wm["hrv_summary"][k], rel=1e-9)
 
+    # (1b) the on-disk outputs: the installed module's ReportGenerator is reports.py's;
+    #      its files equal the untouched module's, the time-stamp lines aside
+    import re
+    from bpm_analysis_b200 import reports
+    assert mod.ReportGenerator is reports.ReportGenerator and ref.ReportGenerator is not reports.ReportGenerator
+    stamp = re.compile(rb"(Generated on: |Analysis performed on: )[0-9: -]+")
+    for m_, out_dir, res in ((ref, out_ref, want), (mod, out_gpu, got)):
+        rg = m_.ReportGenerator(path, str(out_dir))
+        rg.save_analysis_summary(res["metrics"])
+        rg.create_chronological_log(want["env"], res["rate"], res["raw"], res["data"], res["metrics"])
+        rg.save_analysis_settings(None)
+    for suffix in ("_Analysis_Summary.md", "_Debug_Log.md", "_Analysis_Settings.json"):
+        a, b = (open(str(d_ / ("rec" + suffix)), "rb").read() for d_ in (out_ref, out_gpu))
+        assert stamp.sub(b"", a) == stamp.sub(b"", b), suffix
+    assert reports.bpm_plot_csv_bytes(got["metrics"]) == reports.bpm_plot_csv_bytes(want["metrics"])
+
     # (2) end to end on the GPU envelope (preprocess -> session -> every later call answered from it):
     #     the same lists come out, and the chain cost ONE stage-A call
     mid = dict(d.stats)
