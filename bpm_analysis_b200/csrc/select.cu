@@ -18,8 +18,6 @@ namespace bpm {
 constexpr int SEL_PASSES = 6;
 constexpr int SEL_BINS = 2048;
 constexpr int SEL_THREADS = 256;
-constexpr int SEL_PER_THREAD = 16;
-constexpr int SEL_TILE = SEL_THREADS * SEL_PER_THREAD;
 constexpr int SEL_MAXQ = 3;
 
 __host__ __device__ __forceinline__ int sel_shift(int p) { return p < 5 ? 53 - 11 * p : 0; }
@@ -51,6 +49,16 @@ __device__ __forceinline__ size_t hist_idx(int item, int lvl, int pass) {
   return ((static_cast<size_t>(item) * SEL_MAXQ + lvl) * SEL_PASSES + pass) * SEL_BINS;
 }
 
+// States and histograms are produced by the previous launch: read around L1 (ld.global.cg).
+__device__ __forceinline__ SelState sel_load_state(const SelState* p) {
+  SelState s;
+  const unsigned long long* w = reinterpret_cast<const unsigned long long*>(p);
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(&s);
+#pragma unroll
+  for (int k = 0; k < static_cast<int>(sizeof(SelState) / 8); ++k) d[k] = __ldcg(w + k);
+  return s;
+}
+
 // state after resolving one pass, from the state before it and that pass's histogram
 // (block-wide; every block computes it redundantly)
 __device__ void sel_advance(const SelState& prev, const unsigned int* __restrict__ hist, int bits, SelState* out_shared,
@@ -59,7 +67,7 @@ __device__ void sel_advance(const SelState& prev, const unsigned int* __restrict
   const int per = (bins + SEL_THREADS - 1) / SEL_THREADS;
   const int b0 = threadIdx.x * per;
   long long local = 0;
-  for (int b = b0; b < min(b0 + per, bins); ++b) local += hist[b];
+  for (int b = b0; b < min(b0 + per, bins); ++b) local += __ldcg(hist + b);
   s_cum[threadIdx.x + 1] = local;
   if (threadIdx.x == 0) s_cum[0] = 0;
   __syncthreads();
@@ -86,7 +94,7 @@ __device__ void sel_advance(const SelState& prev, const unsigned int* __restrict
   if (rank >= lo && rank < hi) {
     long long c = lo;
     for (int b = b0; b < min(b0 + per, bins); ++b) {
-      const long long h = hist[b];
+      const long long h = __ldcg(hist + b);
       if (rank < c + h) {
         out_shared->prefix = (prev.prefix << bits) | static_cast<unsigned long long>(b);
         out_shared->rank = rank - c;
@@ -122,28 +130,77 @@ __device__ __forceinline__ SelState sel_initial(long long n, double q, bool on) 
   return s;
 }
 
-// add 1 to s_hist[bin] for every lane with `on`, one shared-memory atomic per distinct bin per warp
-__device__ __forceinline__ void warp_hist_add(unsigned int* s_hist, bool on, unsigned int bin) {
-  const unsigned act = __ballot_sync(0xffffffffu, on);
-  if (!on) return;
-  const unsigned peers = __match_any_sync(act, bin);
-  if ((threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&s_hist[bin], static_cast<unsigned int>(__popc(peers)));
+// add 1 to s_hist[bin] for every lane with `on`.  Envelope values share their leading digits (a warp's
+// 32 consecutive samples usually fall into ONE bin of the first digit), later digits are close to
+// random: up to two distinct bins per warp are added by one lane each with the group's size, whatever
+// is left goes through plain shared-memory atomics (rarely conflicting).  Called by whole warps.
+__device__ __forceinline__ void warp_hist_add(unsigned int* s_hist, bool on, unsigned int bin, int lane) {
+  unsigned rem = __ballot_sync(0xffffffffu, on);
+  if (rem == 0u) return;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int leader = __ffs(rem) - 1;
+    const unsigned int b = __shfl_sync(0xffffffffu, bin, leader);
+    const unsigned grp = __ballot_sync(0xffffffffu, on && bin == b) & rem;
+    if (lane == leader) atomicAdd(&s_hist[b], static_cast<unsigned int>(__popc(grp)));
+    rem &= ~grp;
+    if (rem == 0u) return;
+  }
+  if ((rem >> lane) & 1u) atomicAdd(&s_hist[bin], 1u);
 }
 
-// pass p: (p > 0) resolve pass p-1, then histogram digit p of the elements under each level's prefix
-__global__ void __launch_bounds__(SEL_THREADS) k_select_pass(const double* __restrict__ x,
-                                                             const BpmItem* __restrict__ items, int p, int nq,
-                                                             SelLevels lv, SelState* __restrict__ states,
-                                                             unsigned int* __restrict__ hist, int n_items) {
-  __shared__ unsigned int s_hist[SEL_MAXQ][SEL_BINS];
-  __shared__ SelState s_cur[SEL_MAXQ];
-  __shared__ long long s_cum[SEL_THREADS + 1];
+// Levels whose resolved prefixes agree look at the same bucket (the default parameters ask for the 0.1
+// quantile twice): they are served by ONE histogram / ONE comparison per sample.  rep[l] = the first
+// active level with level l's prefix (-1: level off); the distinct representatives are the "groups".
+struct SelGroups {
+  int n;
+  int lvl[SEL_MAXQ];     // representative level of group g
+  int of[SEL_MAXQ];      // group of level l (-1: off)
+};
+__device__ __forceinline__ SelGroups sel_groups(const SelState* s_cur, int nq, bool first) {
+  SelGroups g;
+  g.n = 0;
+#pragma unroll
+  for (int l = 0; l < SEL_MAXQ; ++l) {
+    g.of[l] = -1;
+    if (l >= nq || s_cur[l].active == 0) continue;
+#pragma unroll
+    for (int h = 0; h < SEL_MAXQ; ++h)
+      if (h < g.n && g.of[l] < 0 && (first || s_cur[g.lvl[h]].prefix == s_cur[l].prefix)) g.of[l] = h;
+    if (g.of[l] < 0) {
+#pragma unroll
+      for (int h = 0; h < SEL_MAXQ; ++h) if (h == g.n) g.lvl[h] = l;
+      g.of[l] = g.n;
+      ++g.n;
+    }
+  }
+  return g;
+}
+
+// pass p: (p > 0) resolve pass p-1, then histogram digit p of the elements under each level's prefix.
+// A CTA covers per * SEL_THREADS samples (the host picks `per` so that small recordings still fill the
+// GPU and long ones amortise the 2048-bin flush).  HI32: the digit and everything above it lie in the
+// upper half of the key (passes 0 and 1), so only that half of each sample is loaded and converted.
+struct SelShared {
+  unsigned int hist[SEL_MAXQ][SEL_BINS];
+  SelState cur[SEL_MAXQ];
+  long long cum[SEL_THREADS + 1];
+  unsigned long long red_min[SEL_MAXQ][SEL_THREADS / 32], red_lo[SEL_MAXQ][SEL_THREADS / 32],
+      red_hi[SEL_MAXQ][SEL_THREADS / 32];
+};
+
+template <bool HI32>
+__device__ __forceinline__ void sel_pass_body(SelShared& sm, const double* __restrict__ x, const BpmItem* __restrict__ items,
+                                              int p, int nq, const SelLevels& lv, SelState* states, unsigned int* hist,
+                                              int n_items, int per) {
+  unsigned int (*s_hist)[SEL_BINS] = sm.hist;
+  SelState* s_cur = sm.cur;
+  long long* s_cum = sm.cum;
   const int item = blockIdx.y;
   const BpmItem it = items[item];
-  bool any = false;
   for (int l = 0; l < nq; ++l) {
     if (p > 0) {
-      const SelState before = states[st_idx(p - 1, l, item, n_items)];
+      const SelState before = sel_load_state(states + st_idx(p - 1, l, item, n_items));
       if (before.active == 0) {
         if (threadIdx.x == 0) {
           s_cur[l].active = 0;
@@ -162,42 +219,65 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_pass(const double* __res
       }
       __syncthreads();
     }
-    any = any || (s_cur[l].active != 0);
   }
-  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * SEL_TILE;
-  if (!any || i0 >= it.m) return;
+  // in the first pass no digit is resolved yet: ONE histogram of the whole recording serves every level
+  // (sel_advance of the next pass reads it through hist_idx(item, 0, 0))
+  const SelGroups gr = sel_groups(s_cur, nq, p == 0);
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * per * SEL_THREADS;
+  if (gr.n == 0 || i0 >= it.m) return;
   const int sh = sel_shift(p), bits = sel_bits(p);
   const int up = sh + bits;                       // bits above this digit
   const unsigned int mask = (1u << bits) - 1u;
-  // in the first pass no digit is resolved yet: ONE histogram of the whole recording serves every level
-  // (sel_advance of the next pass reads it through hist_idx(item, 0, 0))
-  const int nh = (p == 0) ? 1 : nq;
-  for (int l = 0; l < nh; ++l)
-    if (p == 0 || s_cur[l].active)
-      for (int t = threadIdx.x; t < (1 << bits); t += SEL_THREADS) s_hist[l][t] = 0;
+  unsigned long long pref[SEL_MAXQ];
+#pragma unroll
+  for (int g = 0; g < SEL_MAXQ; ++g) pref[g] = (g < gr.n) ? s_cur[gr.lvl[g]].prefix : 0ull;
+  for (int t = threadIdx.x; t < gr.n * SEL_BINS; t += SEL_THREADS) (&s_hist[0][0])[t] = 0;
   __syncthreads();
   const double* __restrict__ xi = x + it.m_off;
+  const int lane = threadIdx.x & 31;
 #pragma unroll 4
-  for (int k = 0; k < SEL_PER_THREAD; ++k) {
-    const int64_t i = i0 + k * SEL_THREADS + threadIdx.x;
+  for (int k = 0; k < per; ++k) {
+    const int64_t i = i0 + static_cast<int64_t>(k) * SEL_THREADS + threadIdx.x;
     const bool in = i < it.m;
-    const unsigned long long key = in ? f64_key(xi[i]) : 0ull;
-    const unsigned int bin = static_cast<unsigned int>(key >> sh) & mask;
-    for (int l = 0; l < nh; ++l) {
-      if (p != 0 && !s_cur[l].active) continue;
-      const bool match = in && ((up >= 64) ? true : ((key >> up) == s_cur[l].prefix));
-      warp_hist_add(s_hist[l], match, bin);
+    unsigned int bin;
+    unsigned long long top;
+    if (HI32) {
+      const unsigned int hi = in ? __ldg(reinterpret_cast<const unsigned int*>(xi) + 2 * i + 1) : 0u;
+      const unsigned int khi = (hi & 0x80000000u) ? ~hi : (hi | 0x80000000u);      // upper half of f64_key
+      bin = (khi >> (sh - 32)) & mask;
+      top = (up >= 64) ? 0ull : static_cast<unsigned long long>(khi >> (up - 32));
+    } else {
+      const unsigned long long key = in ? f64_key(xi[i]) : 0ull;
+      bin = static_cast<unsigned int>(key >> sh) & mask;
+      top = (up >= 64) ? 0ull : (key >> up);
+    }
+#pragma unroll
+    for (int g = 0; g < SEL_MAXQ; ++g) {
+      if (g >= gr.n) break;
+      warp_hist_add(s_hist[g], in && top == pref[g], bin, lane);      // pass 0: pref = 0 = top
     }
   }
   __syncthreads();
-  for (int l = 0; l < nh; ++l) {
-    if (p != 0 && !s_cur[l].active) continue;
+#pragma unroll
+  for (int l = 0; l < SEL_MAXQ; ++l) {
+    if (l >= ((p == 0) ? 1 : nq)) break;
+    const int g = (p == 0) ? 0 : gr.of[l];
+    if (g < 0) continue;
     unsigned int* gh = hist + hist_idx(item, l, p);
     for (int t = threadIdx.x; t < (1 << bits); t += SEL_THREADS) {
-      const unsigned int c = s_hist[l][t];
+      const unsigned int c = s_hist[g][t];
       if (c) atomicAdd(gh + t, c);
     }
   }
+}
+
+template <bool HI32>
+__global__ void __launch_bounds__(SEL_THREADS) k_select_pass(const double* __restrict__ x,
+                                                             const BpmItem* __restrict__ items, int p, int nq,
+                                                             SelLevels lv, SelState* __restrict__ states,
+                                                             unsigned int* __restrict__ hist, int n_items, int per) {
+  __shared__ SelShared sm;
+  sel_pass_body<HI32>(sm, x, items, p, nq, lv, states, hist, n_items, per);
 }
 
 // ---- after two digit passes (22 bits) the bucket holding the target is almost always tiny:
@@ -216,20 +296,19 @@ struct SelCollect {
   unsigned long long* bmax;         //   equal => the bucket is one value repeated (digital silence, clipping)
 };
 
-__global__ void __launch_bounds__(SEL_THREADS) k_select_collect(const double* __restrict__ x,
-                                                                const BpmItem* __restrict__ items, int nq,
-                                                                SelState* __restrict__ states,
-                                                                const unsigned int* __restrict__ hist, SelCollect cl,
-                                                                int npre, int n_items) {
-  __shared__ SelState s_cur[SEL_MAXQ];
-  __shared__ long long s_cum[SEL_THREADS + 1];
-  __shared__ unsigned long long s_min[SEL_MAXQ][SEL_THREADS / 32];
-  __shared__ unsigned long long s_lo[SEL_MAXQ][SEL_THREADS / 32], s_hi[SEL_MAXQ][SEL_THREADS / 32];
+__device__ __forceinline__ void sel_collect_body(SelShared& sm, const double* __restrict__ x,
+                                                 const BpmItem* __restrict__ items, int nq, SelState* states,
+                                                 const unsigned int* hist, const SelCollect& cl, int npre, int n_items,
+                                                 int per) {
+  SelState* s_cur = sm.cur;
+  long long* s_cum = sm.cum;
+  unsigned long long (*s_min)[SEL_THREADS / 32] = sm.red_min;
+  unsigned long long (*s_lo)[SEL_THREADS / 32] = sm.red_lo;
+  unsigned long long (*s_hi)[SEL_THREADS / 32] = sm.red_hi;
   const int item = blockIdx.y;
   const BpmItem it = items[item];
-  bool any = false;
   for (int l = 0; l < nq; ++l) {
-    const SelState before = states[st_idx(npre - 1, l, item, n_items)];
+    const SelState before = sel_load_state(states + st_idx(npre - 1, l, item, n_items));
     if (before.active == 0) {
       if (threadIdx.x == 0) {
         s_cur[l].active = 0;
@@ -242,63 +321,80 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_collect(const double* __
     if (threadIdx.x == 0) s_cur[l].active = (s_cur[l].count <= SEL_CAP) ? 2 : 1;     // 2: collected
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0) states[st_idx(npre, l, item, n_items)] = s_cur[l];
-    any = any || (s_cur[l].active != 0);
   }
-  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * SEL_TILE;
-  if (!any || i0 >= it.m) return;
+  // levels with the same prefix share a bucket (same count, same mode): one comparison per sample and group
+  const SelGroups gr = sel_groups(s_cur, nq, false);
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * per * SEL_THREADS;
+  if (gr.n == 0 || i0 >= it.m) return;
   const int up = sel_shift(npre - 1);                       // bits below the resolved digits
-  unsigned long long best[SEL_MAXQ], blo[SEL_MAXQ], bhi[SEL_MAXQ];
+  unsigned long long best[SEL_MAXQ], blo[SEL_MAXQ], bhi[SEL_MAXQ], pref[SEL_MAXQ];
+  bool collected[SEL_MAXQ];
 #pragma unroll
-  for (int l = 0; l < SEL_MAXQ; ++l) { best[l] = ~0ull; blo[l] = ~0ull; bhi[l] = 0ull; }
+  for (int g = 0; g < SEL_MAXQ; ++g) {
+    best[g] = ~0ull; blo[g] = ~0ull; bhi[g] = 0ull;
+    pref[g] = (g < gr.n) ? s_cur[gr.lvl[g]].prefix : 0ull;
+    collected[g] = (g < gr.n) && s_cur[gr.lvl[g]].active == 2;
+  }
   const double* __restrict__ xi = x + it.m_off;
-  for (int k = 0; k < SEL_PER_THREAD; ++k) {
-    const int64_t i = i0 + k * SEL_THREADS + threadIdx.x;
-    if (i >= it.m) continue;
+#pragma unroll 4
+  for (int k = 0; k < per; ++k) {
+    const int64_t i = i0 + static_cast<int64_t>(k) * SEL_THREADS + threadIdx.x;
+    if (i >= it.m) break;
     const unsigned long long key = f64_key(xi[i]);
     const unsigned long long top = key >> up;
 #pragma unroll
-    for (int l = 0; l < SEL_MAXQ; ++l) {
-      if (l >= nq || s_cur[l].active == 0) continue;
-      if (top == s_cur[l].prefix) {
-        if (s_cur[l].active == 2) {
-          const unsigned int pos = atomicAdd(cl.count + item * SEL_MAXQ + l, 1u);
-          if (pos < SEL_CAP) cl.buf[(static_cast<size_t>(item) * SEL_MAXQ + l) * SEL_CAP + pos] = key;
+    for (int g = 0; g < SEL_MAXQ; ++g) {
+      if (g >= gr.n) break;
+      if (top == pref[g]) {
+        if (collected[g]) {
+#pragma unroll
+          for (int l = 0; l < SEL_MAXQ; ++l) {              // a few thousand keys per recording at most
+            if (l >= nq || gr.of[l] != g) continue;
+            const unsigned int pos = atomicAdd(cl.count + item * SEL_MAXQ + l, 1u);
+            if (pos < SEL_CAP) cl.buf[(static_cast<size_t>(item) * SEL_MAXQ + l) * SEL_CAP + pos] = key;
+          }
         } else {
-          blo[l] = key < blo[l] ? key : blo[l];
-          bhi[l] = key > bhi[l] ? key : bhi[l];
+          blo[g] = key < blo[g] ? key : blo[g];
+          bhi[g] = key > bhi[g] ? key : bhi[g];
         }
-      } else if (top > s_cur[l].prefix && key < best[l]) {
-        best[l] = key;
+      } else if (top > pref[g] && key < best[g]) {
+        best[g] = key;
       }
     }
   }
 #pragma unroll
-  for (int l = 0; l < SEL_MAXQ; ++l) {
+  for (int g = 0; g < SEL_MAXQ; ++g) {
+    if (g >= gr.n) break;
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
-      const unsigned long long t = __shfl_xor_sync(0xffffffffu, best[l], o);
-      best[l] = t < best[l] ? t : best[l];
+      const unsigned long long t = __shfl_xor_sync(0xffffffffu, best[g], o);
+      best[g] = t < best[g] ? t : best[g];
     }
+    if (!collected[g]) {
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      const unsigned long long a = __shfl_xor_sync(0xffffffffu, blo[l], o), b = __shfl_xor_sync(0xffffffffu, bhi[l], o);
-      blo[l] = a < blo[l] ? a : blo[l];
-      bhi[l] = b > bhi[l] ? b : bhi[l];
+      for (int o = 16; o; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, blo[g], o), b = __shfl_xor_sync(0xffffffffu, bhi[g], o);
+        blo[g] = a < blo[g] ? a : blo[g];
+        bhi[g] = b > bhi[g] ? b : bhi[g];
+      }
     }
     if ((threadIdx.x & 31) == 0) {
-      s_min[l][threadIdx.x >> 5] = best[l];
-      s_lo[l][threadIdx.x >> 5] = blo[l];
-      s_hi[l][threadIdx.x >> 5] = bhi[l];
+      s_min[g][threadIdx.x >> 5] = best[g];
+      s_lo[g][threadIdx.x >> 5] = blo[g];
+      s_hi[g][threadIdx.x >> 5] = bhi[g];
     }
   }
   __syncthreads();
-  if (threadIdx.x < nq && s_cur[threadIdx.x].active != 0) {
-    const int l = threadIdx.x;
-    unsigned long long bm = s_min[l][0], lo = s_lo[l][0], hi = s_hi[l][0];
+  int my_group = -1;
+#pragma unroll
+  for (int l = 0; l < SEL_MAXQ; ++l) if (l == static_cast<int>(threadIdx.x) && l < nq) my_group = gr.of[l];
+  if (my_group >= 0) {
+    const int l = threadIdx.x, g = my_group;
+    unsigned long long bm = s_min[g][0], lo = s_lo[g][0], hi = s_hi[g][0];
     for (int w = 1; w < SEL_THREADS / 32; ++w) {
-      bm = s_min[l][w] < bm ? s_min[l][w] : bm;
-      lo = s_lo[l][w] < lo ? s_lo[l][w] : lo;
-      hi = s_hi[l][w] > hi ? s_hi[l][w] : hi;
+      bm = s_min[g][w] < bm ? s_min[g][w] : bm;
+      lo = s_lo[g][w] < lo ? s_lo[g][w] : lo;
+      hi = s_hi[g][w] > hi ? s_hi[g][w] : hi;
     }
     if (bm != ~0ull) atomicMin(cl.next_above + item * SEL_MAXQ + l, bm);
     if (s_cur[l].active == 1) {
@@ -306,6 +402,15 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_collect(const double* __
       if (hi != 0ull || lo != ~0ull) atomicMax(cl.bmax + item * SEL_MAXQ + l, hi);
     }
   }
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) k_select_collect(const double* __restrict__ x,
+                                                                const BpmItem* __restrict__ items, int nq,
+                                                                SelState* __restrict__ states,
+                                                                const unsigned int* __restrict__ hist, SelCollect cl,
+                                                                int npre, int n_items, int per) {
+  __shared__ SelShared sm;
+  sel_collect_body(sm, x, items, nq, states, hist, cl, npre, n_items, per);
 }
 
 // numpy's quantile from the two neighbouring order statistics (keys) and the fractional index
@@ -489,15 +594,21 @@ int quantile_multi_run(const double* x, const BpmItem* items, const BatchShape& 
   // digit passes before the bucket is collected: two resolve 22 bits, enough below ~4 M samples; a third
   // (33 bits) keeps the bucket under SEL_CAP for the long streams (24 h at 333 Hz = 28.8 M samples)
   const int npre = sh.max_m > (1ll << 22) ? 3 : 2;
-  const dim3 grid(cdiv(sh.max_m, SEL_TILE), n);
+  SelCollect cl{b.buf, b.count, b.next_above, b.next_above + nlv, b.bmax};
+  // samples per thread: every CTA pays for a 2048-bin histogram (zero, flush, the previous pass's scan),
+  // so tiles stay large -- 16 per thread (266 CTAs for a 60-min recording; 4 per thread and 1062 CTAs
+  // measured no faster), up to 64 for long streams and big batches
+  long long per_ll = cdiv(static_cast<long long>(sh.max_m) * n, static_cast<long long>(SEL_THREADS) * 148 * 8);
+  const int per = per_ll < 16 ? 16 : (per_ll > 64 ? 64 : static_cast<int>(per_ll));
+  const dim3 grid(cdiv(sh.max_m, static_cast<long long>(per) * SEL_THREADS), n);
   for (int p = 0; p < npre; ++p) {
     BPM_KERNEL(k_select_pass);
-    k_select_pass<<<grid, SEL_THREADS, 0, st>>>(x, items, p, nq, lv, b.states, b.hist, n);
+    if (sel_shift(p) >= 32) k_select_pass<true><<<grid, SEL_THREADS, 0, st>>>(x, items, p, nq, lv, b.states, b.hist, n, per);
+    else k_select_pass<false><<<grid, SEL_THREADS, 0, st>>>(x, items, p, nq, lv, b.states, b.hist, n, per);
     BPM_LAUNCH_OK();
   }
-  SelCollect cl{b.buf, b.count, b.next_above, b.next_above + nlv, b.bmax};
   BPM_KERNEL(k_select_collect);
-  k_select_collect<<<grid, SEL_THREADS, 0, st>>>(x, items, nq, b.states, b.hist, cl, npre, n);
+  k_select_collect<<<grid, SEL_THREADS, 0, st>>>(x, items, nq, b.states, b.hist, cl, npre, n, per);
   BPM_LAUNCH_OK();
   BPM_KERNEL(k_select_finish);
   k_select_finish<<<dim3(n, nq), SEL_FIN_THREADS, 0, st>>>(x, items, lv, b.states, cl, npre, n);

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Runs the noise-floor stage (a2) a few times on the C2 envelope: a short command for ncu.
+"""Runs stage A a few times on the C2 recording (or, with `holter` as the 4th argument, on a C4-style
+4 kHz Holter recording of the given duration): a short command for ncu.
 
-    python tools/floor_only.py [duration_sec] [repeats]
+    python tools/floor_only.py [duration_sec] [repeats] [parity|fullrate] [holter]
 """
 import os
 import sys
@@ -21,7 +22,10 @@ def main():
     p["save_filtered_wav"] = False
     if len(sys.argv) > 3:
         p["filter_mode"] = sys.argv[3]
-    pcm, sr, _ = synth.config_c2(seed=2, duration_sec=dur)
+    if len(sys.argv) > 4 and sys.argv[4] == "holter":
+        pcm, sr, _ = synth.config_c4(seed=4, duration_sec=dur)
+    else:
+        pcm, sr, _ = synth.config_c2(seed=2, duration_sec=dur)
     A = StageARunner([len(pcm)], sr, p)
     A.upload([pcm])
     for _ in range(reps):
