@@ -200,6 +200,28 @@ __device__ __forceinline__ int knot_at_or_before(const WinCtx& c, int i) {
   return lo;
 }
 
+// first index r in [0, T] with t[r] >= bound (T: none), searched by a whole warp 32 ways per step: a
+// 13 k-knot table is three dependent loads deep instead of fourteen (the CTA waits for this at its start)
+__device__ __forceinline__ int warp_first_knot_ge(const int* __restrict__ t, int T, long long bound) {
+  const int lane = threadIdx.x & 31;
+  int lo = 0, hi = T;                     // t[k] < bound for k < lo;  hi == T or t[hi] >= bound
+  while (hi - lo > 32) {
+    const int step = (hi - lo + 31) / 32;
+    const int idx = lo + lane * step;
+    const bool ge = (idx < hi) ? (static_cast<long long>(t[idx]) >= bound) : true;
+    const unsigned m = __ballot_sync(0xffffffffu, ge);
+    const int f = m ? __ffs(m) - 1 : 32;
+    if (f == 0) return lo;
+    const int nlo = lo + (f - 1) * step + 1, nhi = lo + f * step;
+    lo = nlo;
+    if (nhi < hi) hi = nhi;
+  }
+  const int idx = lo + lane;
+  const bool ge = (idx < hi) ? (static_cast<long long>(t[idx]) >= bound) : true;
+  const unsigned m = __ballot_sync(0xffffffffu, ge);
+  return m ? lo + __ffs(m) - 1 : hi;
+}
+
 // first output of a run: the order statistic `idx` of the window, located by a bracket on
 // the value axis narrowed with counts (secant and bisection steps alternate)
 __device__ double locate_rank(const WinCtx& c, int a, int b, int ka, int kb, int n, int idx) {
@@ -737,6 +759,11 @@ struct RbSlidePhase {
   unsigned short pc[RB_MAXCH + 1][RB_NSUP];       // kept samples with index < c*ch and band <= s
   unsigned char ragged[RB_NSUP][RB_THREADS];      // per-thread band counts of a window's ragged ends (< 2 RB_CH)
 };
+constexpr int RB_KNOT_STAGE = 1280;    // knots of a tile staged in shared memory (min distance 15 => <= 888 for a full tile)
+struct RbKnotStage {
+  double v[RB_KNOT_STAGE], s[RB_KNOT_STAGE];
+  int t[RB_KNOT_STAGE];
+};
 struct RbShared {
   double d[RB_NCAP];
   unsigned short rank[RB_NCAP];        // bucket id while sorting, then position in sorted order
@@ -744,6 +771,7 @@ struct RbShared {
   union {
     RbSortPhase sort;
     RbSlidePhase slide;
+    RbKnotStage knots;
   } u;
   unsigned long long pivot_key;        // max over the probes (order-preserving key of a double)
   int scan_tmp[40];
@@ -821,38 +849,56 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rolling_floor_blk(
   const int n = x1 - x0 + 1;                                  // <= RB_NCAP (host guarantees)
 
   // ---- S1: interpolated samples -> shared memory
-  if (tid == 0) sh.k_lo = knot_at_or_before(c, x0);
-  if (tid == 32) sh.k_hi = knot_at_or_before(c, x1);
-  if (tid == 64 || tid == 96) {
-    // knots whose position lies in this tile's output range: [kf, kl)
-    const long long bound = (tid == 64) ? blk_first : blk_last;
-    int lo = 0, hi = c.T;                                     // first knot with t >= bound
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (c.t[mid] >= bound) hi = mid; else lo = mid + 1;
+  if (tid < 128) {
+    // four warps, one boundary each: the knots around the tile's first / last staged sample (last knot
+    // <= x: one before the first knot >= x + 1; t[0] <= x0 holds) and the knots inside its output range
+    const int w = tid >> 5;
+    const long long bound = (w == 0) ? static_cast<long long>(x0) + 1 : (w == 1) ? static_cast<long long>(x1) + 1
+                                                                      : (w == 2) ? blk_first : blk_last;
+    const int r = warp_first_knot_ge(c.t, c.T, bound);
+    if ((tid & 31) == 0) {
+      if (w == 0) sh.k_lo = r - 1;
+      else if (w == 1) sh.k_hi = r - 1;
+      else if (w == 2) sh.kf = r;
+      else sh.kl = r;
     }
-    if (tid == 64) sh.kf = lo; else sh.kl = lo;
   }
   __syncthreads();
   const int kf = sh.kf, kcnt = sh.kl - sh.kf;
   if (sparse && kcnt <= 0) return;
   {
+    // the tile's knots [k_lo, k_hi + 1] go to shared memory first (the sort phase's area is idle): the
+    // per-thread search and the interpolation then never wait for global memory
+    RbKnotStage& ks = sh.u.knots;
+    const int k_lo = sh.k_lo;
+    const int nkn = min(sh.k_hi + 1, c.T - 1) - k_lo + 1;
+    const bool staged = nkn <= RB_KNOT_STAGE;
+    if (staged) {
+      for (int k = tid; k < nkn; k += RB_THREADS) {
+        ks.t[k] = c.t[k_lo + k];
+        ks.v[k] = c.v[k_lo + k];
+        ks.s[k] = c.s[k_lo + k];
+      }
+      __syncthreads();
+    }
+    WinCtx cs = c;
+    if (staged) { cs.t = ks.t - k_lo; cs.v = ks.v - k_lo; cs.s = ks.s - k_lo; }
     const int per = (n + RB_THREADS - 1) / RB_THREADS;
     const int j0 = tid * per, j1 = min(n, j0 + per);
     if (j0 < j1) {
-      int k = sh.k_lo;
+      int k = k_lo;
       {
         int hi = sh.k_hi;                                     // last knot <= x0 + j0, searched inside the tile's knots
         const int xi = x0 + j0;
         while (k < hi) {
           const int mid = (k + hi + 1) >> 1;
-          if (c.t[mid] <= xi) k = mid; else hi = mid - 1;
+          if (cs.t[mid] <= xi) k = mid; else hi = mid - 1;
         }
       }
       for (int j = j0; j < j1; ++j) {
         const int x = x0 + j;
-        while (k + 1 < c.T && c.t[k + 1] <= x) ++k;
-        sh.d[j] = val_at(c, k, x);
+        while (k + 1 < c.T && cs.t[k + 1] <= x) ++k;
+        sh.d[j] = val_at(cs, k, x);
       }
     }
   }

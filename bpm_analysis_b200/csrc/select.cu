@@ -19,6 +19,7 @@ constexpr int SEL_PASSES = 6;
 constexpr int SEL_BINS = 2048;
 constexpr int SEL_THREADS = 256;
 constexpr int SEL_MAXQ = 3;
+constexpr int SEL_BATCH = 8;                // loads in flight per thread in the sweeps
 
 __host__ __device__ __forceinline__ int sel_shift(int p) { return p < 5 ? 53 - 11 * p : 0; }
 __host__ __device__ __forceinline__ int sel_bits(int p) { return p < 5 ? 11 : 9; }
@@ -49,16 +50,6 @@ __device__ __forceinline__ size_t hist_idx(int item, int lvl, int pass) {
   return ((static_cast<size_t>(item) * SEL_MAXQ + lvl) * SEL_PASSES + pass) * SEL_BINS;
 }
 
-// States and histograms are produced by the previous launch: read around L1 (ld.global.cg).
-__device__ __forceinline__ SelState sel_load_state(const SelState* p) {
-  SelState s;
-  const unsigned long long* w = reinterpret_cast<const unsigned long long*>(p);
-  unsigned long long* d = reinterpret_cast<unsigned long long*>(&s);
-#pragma unroll
-  for (int k = 0; k < static_cast<int>(sizeof(SelState) / 8); ++k) d[k] = __ldcg(w + k);
-  return s;
-}
-
 // state after resolving one pass, from the state before it and that pass's histogram
 // (block-wide; every block computes it redundantly)
 __device__ void sel_advance(const SelState& prev, const unsigned int* __restrict__ hist, int bits, SelState* out_shared,
@@ -67,7 +58,7 @@ __device__ void sel_advance(const SelState& prev, const unsigned int* __restrict
   const int per = (bins + SEL_THREADS - 1) / SEL_THREADS;
   const int b0 = threadIdx.x * per;
   long long local = 0;
-  for (int b = b0; b < min(b0 + per, bins); ++b) local += __ldcg(hist + b);
+  for (int b = b0; b < min(b0 + per, bins); ++b) local += hist[b];
   s_cum[threadIdx.x + 1] = local;
   if (threadIdx.x == 0) s_cum[0] = 0;
   __syncthreads();
@@ -94,7 +85,7 @@ __device__ void sel_advance(const SelState& prev, const unsigned int* __restrict
   if (rank >= lo && rank < hi) {
     long long c = lo;
     for (int b = b0; b < min(b0 + per, bins); ++b) {
-      const long long h = __ldcg(hist + b);
+      const long long h = hist[b];
       if (rank < c + h) {
         out_shared->prefix = (prev.prefix << bits) | static_cast<unsigned long long>(b);
         out_shared->rank = rank - c;
@@ -132,13 +123,15 @@ __device__ __forceinline__ SelState sel_initial(long long n, double q, bool on) 
 
 // add 1 to s_hist[bin] for every lane with `on`.  Envelope values share their leading digits (a warp's
 // 32 consecutive samples usually fall into ONE bin of the first digit), later digits are close to
-// random: up to two distinct bins per warp are added by one lane each with the group's size, whatever
-// is left goes through plain shared-memory atomics (rarely conflicting).  Called by whole warps.
+// random: up to ROUNDS distinct bins per warp (two in the first pass, one later -- enough for a warp of
+// equal samples) are added by one lane each with the group's size, whatever is left goes through plain
+// shared-memory atomics (rarely conflicting).  Called by whole warps.
+template <int ROUNDS>
 __device__ __forceinline__ void warp_hist_add(unsigned int* s_hist, bool on, unsigned int bin, int lane) {
   unsigned rem = __ballot_sync(0xffffffffu, on);
   if (rem == 0u) return;
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     const int leader = __ffs(rem) - 1;
     const unsigned int b = __shfl_sync(0xffffffffu, bin, leader);
     const unsigned grp = __ballot_sync(0xffffffffu, on && bin == b) & rem;
@@ -191,8 +184,8 @@ struct SelShared {
 
 template <bool HI32>
 __device__ __forceinline__ void sel_pass_body(SelShared& sm, const double* __restrict__ x, const BpmItem* __restrict__ items,
-                                              int p, int nq, const SelLevels& lv, SelState* states, unsigned int* hist,
-                                              int n_items, int per) {
+                                              int p, int nq, const SelLevels& lv, SelState* __restrict__ states,
+                                              unsigned int* __restrict__ hist, int n_items, int per) {
   unsigned int (*s_hist)[SEL_BINS] = sm.hist;
   SelState* s_cur = sm.cur;
   long long* s_cum = sm.cum;
@@ -200,7 +193,7 @@ __device__ __forceinline__ void sel_pass_body(SelShared& sm, const double* __res
   const BpmItem it = items[item];
   for (int l = 0; l < nq; ++l) {
     if (p > 0) {
-      const SelState before = sel_load_state(states + st_idx(p - 1, l, item, n_items));
+      const SelState before = states[st_idx(p - 1, l, item, n_items)];
       if (before.active == 0) {
         if (threadIdx.x == 0) {
           s_cur[l].active = 0;
@@ -235,26 +228,39 @@ __device__ __forceinline__ void sel_pass_body(SelShared& sm, const double* __res
   __syncthreads();
   const double* __restrict__ xi = x + it.m_off;
   const int lane = threadIdx.x & 31;
-#pragma unroll 4
-  for (int k = 0; k < per; ++k) {
-    const int64_t i = i0 + static_cast<int64_t>(k) * SEL_THREADS + threadIdx.x;
-    const bool in = i < it.m;
-    unsigned int bin;
-    unsigned long long top;
-    if (HI32) {
-      const unsigned int hi = in ? __ldg(reinterpret_cast<const unsigned int*>(xi) + 2 * i + 1) : 0u;
-      const unsigned int khi = (hi & 0x80000000u) ? ~hi : (hi | 0x80000000u);      // upper half of f64_key
-      bin = (khi >> (sh - 32)) & mask;
-      top = (up >= 64) ? 0ull : static_cast<unsigned long long>(khi >> (up - 32));
-    } else {
-      const unsigned long long key = in ? f64_key(xi[i]) : 0ull;
-      bin = static_cast<unsigned int>(key >> sh) & mask;
-      top = (up >= 64) ? 0ull : (key >> up);
+  // SEL_BATCH independent loads are issued before the first is consumed (`per` is a run-time value: without
+  // the explicit batch every load would wait for the previous sample's histogram update)
+  for (int k0 = 0; k0 < per; k0 += SEL_BATCH) {
+    unsigned int hi32[SEL_BATCH];
+    unsigned long long key64[SEL_BATCH];
+    bool inb[SEL_BATCH];
+#pragma unroll
+    for (int u = 0; u < SEL_BATCH; ++u) {
+      const int64_t i = i0 + static_cast<int64_t>(k0 + u) * SEL_THREADS + threadIdx.x;
+      inb[u] = (k0 + u < per) && i < it.m;
+      if (HI32) hi32[u] = inb[u] ? __ldg(reinterpret_cast<const unsigned int*>(xi) + 2 * i + 1) : 0u;
+      else key64[u] = inb[u] ? f64_key(xi[i]) : 0ull;
     }
 #pragma unroll
-    for (int g = 0; g < SEL_MAXQ; ++g) {
-      if (g >= gr.n) break;
-      warp_hist_add(s_hist[g], in && top == pref[g], bin, lane);      // pass 0: pref = 0 = top
+    for (int u = 0; u < SEL_BATCH; ++u) {
+      const bool in = inb[u];
+      unsigned int bin;
+      unsigned long long top;
+      if (HI32) {
+        const unsigned int hi = hi32[u];
+        const unsigned int khi = (hi & 0x80000000u) ? ~hi : (hi | 0x80000000u);      // upper half of f64_key
+        bin = (khi >> (sh - 32)) & mask;
+        top = (up >= 64) ? 0ull : static_cast<unsigned long long>(khi >> (up - 32));
+      } else {
+        bin = static_cast<unsigned int>(key64[u] >> sh) & mask;
+        top = (up >= 64) ? 0ull : (key64[u] >> up);
+      }
+#pragma unroll
+      for (int g = 0; g < SEL_MAXQ; ++g) {
+        if (g >= gr.n) break;
+        if (p == 0) warp_hist_add<2>(s_hist[g], in, bin, lane);
+        else warp_hist_add<1>(s_hist[g], in && top == pref[g], bin, lane);
+      }
     }
   }
   __syncthreads();
@@ -287,6 +293,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_pass(const double* __res
 // digit passes over the whole recording -- slow, but rare and with no extra launches.
 constexpr int SEL_CAP = 4096;
 constexpr int SEL_FIN_THREADS = 1024;
+constexpr int SEL_RANK_MAX = 384;                 // buckets up to this size are ranked by counting (measured: 2048 doubled the time at ~1.5 k keys), larger ones sorted
 
 struct SelCollect {
   unsigned long long* buf;          // [item][level][SEL_CAP] keys of the bucket
@@ -297,9 +304,9 @@ struct SelCollect {
 };
 
 __device__ __forceinline__ void sel_collect_body(SelShared& sm, const double* __restrict__ x,
-                                                 const BpmItem* __restrict__ items, int nq, SelState* states,
-                                                 const unsigned int* hist, const SelCollect& cl, int npre, int n_items,
-                                                 int per) {
+                                                 const BpmItem* __restrict__ items, int nq, SelState* __restrict__ states,
+                                                 const unsigned int* __restrict__ hist, const SelCollect& cl, int npre,
+                                                 int n_items, int per) {
   SelState* s_cur = sm.cur;
   long long* s_cum = sm.cum;
   unsigned long long (*s_min)[SEL_THREADS / 32] = sm.red_min;
@@ -308,7 +315,7 @@ __device__ __forceinline__ void sel_collect_body(SelShared& sm, const double* __
   const int item = blockIdx.y;
   const BpmItem it = items[item];
   for (int l = 0; l < nq; ++l) {
-    const SelState before = sel_load_state(states + st_idx(npre - 1, l, item, n_items));
+    const SelState before = states[st_idx(npre - 1, l, item, n_items)];
     if (before.active == 0) {
       if (threadIdx.x == 0) {
         s_cur[l].active = 0;
@@ -336,29 +343,38 @@ __device__ __forceinline__ void sel_collect_body(SelShared& sm, const double* __
     collected[g] = (g < gr.n) && s_cur[gr.lvl[g]].active == 2;
   }
   const double* __restrict__ xi = x + it.m_off;
-#pragma unroll 4
-  for (int k = 0; k < per; ++k) {
-    const int64_t i = i0 + static_cast<int64_t>(k) * SEL_THREADS + threadIdx.x;
-    if (i >= it.m) break;
-    const unsigned long long key = f64_key(xi[i]);
-    const unsigned long long top = key >> up;
+  for (int k0 = 0; k0 < per; k0 += SEL_BATCH) {
+    unsigned long long keys[SEL_BATCH];
+    bool inb[SEL_BATCH];
 #pragma unroll
-    for (int g = 0; g < SEL_MAXQ; ++g) {
-      if (g >= gr.n) break;
-      if (top == pref[g]) {
-        if (collected[g]) {
+    for (int u = 0; u < SEL_BATCH; ++u) {                   // independent loads first
+      const int64_t i = i0 + static_cast<int64_t>(k0 + u) * SEL_THREADS + threadIdx.x;
+      inb[u] = (k0 + u < per) && i < it.m;
+      keys[u] = inb[u] ? f64_key(xi[i]) : 0ull;
+    }
 #pragma unroll
-          for (int l = 0; l < SEL_MAXQ; ++l) {              // a few thousand keys per recording at most
-            if (l >= nq || gr.of[l] != g) continue;
-            const unsigned int pos = atomicAdd(cl.count + item * SEL_MAXQ + l, 1u);
-            if (pos < SEL_CAP) cl.buf[(static_cast<size_t>(item) * SEL_MAXQ + l) * SEL_CAP + pos] = key;
+    for (int u = 0; u < SEL_BATCH; ++u) {
+      if (!inb[u]) continue;
+      const unsigned long long key = keys[u];
+      const unsigned long long top = key >> up;
+#pragma unroll
+      for (int g = 0; g < SEL_MAXQ; ++g) {
+        if (g >= gr.n) break;
+        if (top == pref[g]) {
+          if (collected[g]) {
+#pragma unroll
+            for (int l = 0; l < SEL_MAXQ; ++l) {              // a few thousand keys per recording at most
+              if (l >= nq || gr.of[l] != g) continue;
+              const unsigned int pos = atomicAdd(cl.count + item * SEL_MAXQ + l, 1u);
+              if (pos < SEL_CAP) cl.buf[(static_cast<size_t>(item) * SEL_MAXQ + l) * SEL_CAP + pos] = key;
+            }
+          } else {
+            blo[g] = key < blo[g] ? key : blo[g];
+            bhi[g] = key > bhi[g] ? key : bhi[g];
           }
-        } else {
-          blo[g] = key < blo[g] ? key : blo[g];
-          bhi[g] = key > bhi[g] ? key : bhi[g];
+        } else if (top > pref[g] && key < best[g]) {
+          best[g] = key;
         }
-      } else if (top > pref[g] && key < best[g]) {
-        best[g] = key;
       }
     }
   }
@@ -446,6 +462,32 @@ __global__ void __launch_bounds__(SEL_FIN_THREADS) k_select_finish(const double*
       const unsigned long long* src = cl.buf + (static_cast<size_t>(item) * SEL_MAXQ + l) * SEL_CAP;
       for (int t = tid; t < P; t += SEL_FIN_THREADS) s_key[t] = (t < nc) ? src[t] : ~0ull;
       __syncthreads();
+      if (nc <= SEL_RANK_MAX) {
+        // only two order statistics of the bucket are wanted: every thread ranks its own key(s) against the
+        // whole bucket (broadcast shared-memory reads, ties broken by position) instead of a bitonic sort
+        // with ~50 block barriers -- a 60-minute recording leaves a few hundred keys here
+        const int want = static_cast<int>(s.rank);
+        if (tid == 0) { s_red[0] = ~0ull; s_red[1] = ~0ull; }
+        __syncthreads();
+        for (int t = tid; t < nc; t += SEL_FIN_THREADS) {
+          const unsigned long long mine = s_key[t];
+          int before = 0;
+          for (int j = 0; j < nc; ++j) {
+            const unsigned long long o = s_key[j];
+            before += (o < mine || (o == mine && j < t)) ? 1 : 0;
+          }
+          if (before == want) s_red[0] = mine;
+          if (before == want + 1) s_red[1] = mine;
+        }
+        __syncthreads();
+        ka = s_red[0];
+        if (s.rank + 1 < nc) kb = s_red[1];
+        else {
+          const unsigned long long na = cl.next_above[item * SEL_MAXQ + l];
+          kb = (na != ~0ull) ? na : ka;
+        }
+        __syncthreads();
+      } else {
       for (int k2 = 2; k2 <= P; k2 <<= 1) {
         for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
           for (int t = tid; t < P / 2; t += SEL_FIN_THREADS) {
@@ -466,6 +508,7 @@ __global__ void __launch_bounds__(SEL_FIN_THREADS) k_select_finish(const double*
         kb = (na != ~0ull) ? na : ka;
       }
       __syncthreads();
+      }
     } else if (cl.bmin[item * SEL_MAXQ + l] == cl.bmax[item * SEL_MAXQ + l]) {
       // the oversized bucket is ONE value repeated (digital silence, clipping): nothing to resolve
       ka = cl.bmin[item * SEL_MAXQ + l];
