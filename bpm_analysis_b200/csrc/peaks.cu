@@ -212,7 +212,14 @@ __device__ unsigned long long g_dbg_pk[16];
 // the anchors nearest to the core (ci.anchors); the caller accepts the core's decisions only if one of
 // them lies between each open end's doubtful zone and the core.
 // ------------------------------------------------------------------ distance
-constexpr int DT_THREADS = 128;
+// Threads per tile.  A recording of a few M samples has a few hundred tiles: the kernel's time is ONE
+// tile's latency (staging, neighbour masks, evaluation, write-back, each a dependent phase), so every
+// candidate gets its own thread (512: 31 -> 21 us per launch at C2).  Long streams and big batches
+// have thousands of tiles and are throughput-bound: 4 candidates per thread keep more tiles resident
+// (128: 218 us at C4 against 249 with 512).
+constexpr int DT_THREADS_SMALL = 512;
+constexpr int DT_THREADS_LARGE = 128;
+constexpr int64_t DT_LARGE_MIN = 4 << 20;         // total samples from which the throughput form is used
 constexpr int DT_OWN = 512;                       // candidates a CTA settles per tile
 constexpr int DT_HALO = 64;                       // staged on either side of them
 constexpr int DT_STAGE = DT_OWN + 2 * DT_HALO;
@@ -238,6 +245,7 @@ __device__ __forceinline__ bool higher_priority(double va, int64_t ka, double vb
 // each other.  Staged candidates whose neighbourhood is not completely staged cannot be kept here;
 // an owned candidate that depends on one of those -- or on a chain deeper than DT_DEPTH -- is left
 // pending for the exact global finish below (never seen on real envelopes: chains are a few long).
+template <int DT_THREADS>
 __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __restrict__ x, int sign,
                                                                const BpmItem* __restrict__ items,
                                                                const int64_t* __restrict__ cand,
@@ -279,14 +287,15 @@ __global__ void __launch_bounds__(DT_THREADS) k_distance_tiles(const double* __r
 #endif
     __syncthreads();                                              // previous tile's staging is no longer read
     {
-      int64_t pp[DT_STAGE / DT_THREADS];
+      constexpr int DT_PER = (DT_STAGE + DT_THREADS - 1) / DT_THREADS;
+      int64_t pp[DT_PER];
 #pragma unroll
-      for (int u = 0; u < DT_STAGE / DT_THREADS; ++u) {
+      for (int u = 0; u < DT_PER; ++u) {
         const int t = tid + u * DT_THREADS;
         pp[u] = (t < L) ? pos[s0 + t] : 0;
       }
 #pragma unroll
-      for (int u = 0; u < DT_STAGE / DT_THREADS; ++u) {
+      for (int u = 0; u < DT_PER; ++u) {
         const int t = tid + u * DT_THREADS;
         if (t < L) {
           s_pos[t] = static_cast<int>(pp[u]);
@@ -626,8 +635,12 @@ int find_peaks_run(const double* x, int sign, const double* height, const double
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     BPM_KERNEL(k_distance_tiles);
-    k_distance_tiles<<<dim3(static_cast<unsigned>(gx), sh.n_items), DT_THREADS, 0, st>>>(
-        x, sign, items, b.cand, b.cand_count, distance, b.cstate, b.pending, b.ticket, ci);
+    if (sh.total_m >= DT_LARGE_MIN)
+      k_distance_tiles<DT_THREADS_LARGE><<<dim3(static_cast<unsigned>(gx), sh.n_items), DT_THREADS_LARGE, 0, st>>>(
+          x, sign, items, b.cand, b.cand_count, distance, b.cstate, b.pending, b.ticket, ci);
+    else
+      k_distance_tiles<DT_THREADS_SMALL><<<dim3(static_cast<unsigned>(gx), sh.n_items), DT_THREADS_SMALL, 0, st>>>(
+          x, sign, items, b.cand, b.cand_count, distance, b.cstate, b.pending, b.ticket, ci);
     BPM_LAUNCH_OK();
   }
   if (prominence_ready && cudaStreamWaitEvent(st, prominence_ready, 0) != cudaSuccess) return BPM_ERR_CUDA;
