@@ -64,6 +64,31 @@ def test_format_rows_matches_python_formatting():
     assert reports.format_rows(a, b[:7], 1, 1, "", ",", "\n") == "".join(f"{x:.1f},{y:.1f}\n" for x, y in zip(a, b[:7])).encode()
 
 
+def test_format_rows_argument_errors_and_resize():
+    """The C entry never throws: bad arguments come back as BPM_HOST_ERR_ARG (-1), a buffer that is too
+    small as the size to retry with (include/bpm_host.h)."""
+    import ctypes as C
+    from bpm_analysis_b200.classifier import load_host_library
+    lib = load_host_library()
+    a = np.array([1.0, 2.5, 1e300]); b = np.array([3.0, np.nan, 4.0])
+    pa, pb = a.ctypes.data, b.ctypes.data
+    buf = C.create_string_buffer(8)
+    call = lib.bpm_host_format_rows
+    assert call(None, pb, 3, 1, 1, b"", b",", b"\n", 1, C.addressof(buf), 8) == -1
+    assert call(pa, pb, -1, 1, 1, b"", b",", b"\n", 1, C.addressof(buf), 8) == -1
+    assert call(pa, pb, 3, 18, 1, b"", b",", b"\n", 1, C.addressof(buf), 8) == -1
+    assert call(pa, pb, 3, 1, 1, None, b",", b"\n", 1, C.addressof(buf), 8) == -1
+    assert call(pa, pb, 3, 1, 1, b"", b",", b"\n", 1, None, 8) == -1
+    want = "".join(f"{x:.1f},{y:.1f}\n" for x, y in zip(a, b) if not np.isnan(y)).encode()
+    need = call(pa, pb, 3, 1, 1, b"", b",", b"\n", 1, None, 0)            # size query
+    assert need == len(want) > 300                                        # 1e300 prints 301 digits
+    assert call(pa, pb, 3, 1, 1, b"", b",", b"\n", 1, C.addressof(buf), 8) == need
+    big = C.create_string_buffer(need)
+    assert call(pa, pb, 3, 1, 1, b"", b",", b"\n", 1, C.addressof(big), need) == need and big.raw == want
+    assert reports.format_rows(a, b, 1, 1, "", ",", "\n") == want          # the wrapper retries with the size
+    assert call(pa, pb, 0, 1, 1, b"", b",", b"\n", 1, None, 0) == 0
+
+
 def test_empty_and_degenerate_outputs(tmp_path):
     empty = {"smoothed_bpm": pd.Series(dtype=float), "bpm_times": np.array([]), "hrv_summary": {}, "hrr_stats": None,
              "major_inclines": [], "major_declines": [], "peak_recovery_stats": None, "peak_exertion_stats": None,
