@@ -4,9 +4,9 @@
 ``libbpm_host.so``, ``include/bpm_host.h``).
 
 The vectorised numpy calls that produce the thresholds (``np.diff``, ``np.median``,
-``np.percentile``) are made exactly as the reference makes them; the compiled loops return their
-decisions as events, which are applied to the debug-string dict and logged here with the
-reference's own f-strings -- same peaks, same dict, same log lines, same correction count.
+``np.percentile``) are the reference's; the compiled loops return their decisions as events, which
+are applied to the debug-string dict and logged here in the reference's words -- same peaks, same
+dict, same log lines, same correction count.
 """
 from __future__ import annotations
 
@@ -50,63 +50,84 @@ def _lib():
     return lib
 
 
+def _say(text: str) -> None:
+    logging.info(text)
+
+
+def _dbg(text: str) -> None:
+    logging.info("[Correction DEBUG] " + text)
+
+
+def _sec(sample, rate) -> str:
+    return format(sample / rate, ".2f")
+
+
+def _rr(beats, rate) -> np.ndarray:
+    """Intervals between consecutive beats in seconds (the reference's ``np.diff(...) / sample_rate``)."""
+    return np.diff(beats) / rate
+
+
 def correct_peaks_by_rhythm(peaks: np.ndarray, audio_envelope: np.ndarray, sample_rate: int, params: Dict) -> np.ndarray:
-    """Mirrors bpm_analysis.py:1257-1306."""
-    if len(peaks) < 5:
+    """Mirrors bpm_analysis.py:1257-1306: a beat closer to its predecessor than a fraction of the median
+    interval is in conflict with it, the one with the larger envelope amplitude stays."""
+    n_in = len(peaks)
+    if n_in < 5:
         return peaks
-    logging.info(f"--- STAGE 4: Correcting peaks based on rhythm. Initial count: {len(peaks)} ---")
-    rr_intervals_sec = np.diff(peaks) / sample_rate
-    median_rr_sec = np.median(rr_intervals_sec)
-    correction_threshold_sec = median_rr_sec * params.get("rr_correction_threshold_pct", 0.6)
-    logging.info(f"Median R-R: {median_rr_sec:.3f}s. Correction threshold: {correction_threshold_sec:.3f}s.")
+    _say(f"--- STAGE 4: Correcting peaks based on rhythm. Initial count: {n_in} ---")
+    med = np.median(_rr(peaks, sample_rate))
+    limit = med * params.get("rr_correction_threshold_pct", 0.6)
+    _say("Median R-R: {:.3f}s. Correction threshold: {:.3f}s.".format(med, limit))
     pk = np.ascontiguousarray(peaks, dtype=np.int64)
     env = np.ascontiguousarray(audio_envelope, dtype=np.float64)
-    out = np.empty(len(pk), dtype=np.int64)
-    events = (CorrectionEvent * len(pk))()
+    out = np.empty(n_in, dtype=np.int64)
+    events = (CorrectionEvent * n_in)()
     n_out, n_ev = C.c_int64(), C.c_int64()
-    rc = _lib().bpm_correct_peaks_by_rhythm(pk.ctypes.data, len(pk), env.ctypes.data, len(env), float(sample_rate),
-                                            float(correction_threshold_sec), out.ctypes.data, C.byref(n_out), events,
-                                            C.byref(n_ev))
+    rc = _lib().bpm_correct_peaks_by_rhythm(pk.ctypes.data, n_in, env.ctypes.data, len(env), float(sample_rate),
+                                            float(limit), out.ctypes.data, C.byref(n_out), events, C.byref(n_ev))
     if rc != 0:
         raise ValueError(f"bpm_correct_peaks_by_rhythm rejected its arguments (code {rc})")
-    for i in range(n_ev.value):
-        e = events[i]
+    for e in events[:n_ev.value]:
         if e.kind == 1:
-            logging.info(f"Conflict at {e.a/sample_rate:.2f}s. Replaced previous peak at {e.b/sample_rate:.2f}s due to higher amplitude.")
+            _say(f"Conflict at {_sec(e.a, sample_rate)}s. Replaced previous peak at {_sec(e.b, sample_rate)}s "
+                 "due to higher amplitude.")
         else:
-            logging.info(f"Conflict at {e.a/sample_rate:.2f}s. Discarding current peak due to lower amplitude.")
-    final_peak_count = n_out.value
-    if final_peak_count < len(peaks):
-        logging.info(f"Correction complete. Removed {len(peaks) - final_peak_count} peak(s). Final count: {final_peak_count}")
+            _say(f"Conflict at {_sec(e.a, sample_rate)}s. Discarding current peak due to lower amplitude.")
+    kept = n_out.value
+    if kept < n_in:
+        _say(f"Correction complete. Removed {n_in - kept} peak(s). Final count: {kept}")
     else:
-        logging.info("Correction pass complete. No rhythmic conflicts found.")
-    return out[:final_peak_count].copy()
+        _say("Correction pass complete. No rhythmic conflicts found.")
+    return out[:kept].copy()
+
+
+def _discontinuity_thresholds(s1_peaks, sample_rate, params):
+    """(median interval, short limit, long limit) of bpm_analysis.py:1319-1330 -- the median is taken over the
+    intervals inside Tukey's fences -- or None when no interval is."""
+    rr = _rr(s1_peaks, sample_rate)
+    lo_q, hi_q = np.percentile(rr, [25, 75])
+    spread = hi_q - lo_q
+    inside = rr[(rr > (lo_q - 1.5 * spread)) & (rr < (hi_q + 1.5 * spread))]
+    if len(inside) < 1:
+        return None
+    med = np.median(inside)
+    return med, med * params["rr_correction_threshold_pct"], med * params.get("rr_correction_long_interval_pct", 1.7)
 
 
 def _fix_rhythmic_discontinuities(s1_peaks: np.ndarray, all_raw_peaks: np.ndarray, debug_info: Dict,
                                   audio_envelope: np.ndarray, dynamic_noise_floor: pd.Series, params: Dict,
                                   sample_rate: int) -> Tuple[np.ndarray, Dict, int]:
     """Mirrors bpm_analysis.py:1309-1412."""
-    def log_debug(msg):
-        logging.info(f"[Correction DEBUG] {msg}")
-
     margin = 3
-    if len(s1_peaks) < margin * 2:
-        log_debug(f"Skipping correction pass: Not enough S1 peaks ({len(s1_peaks)}) to apply a margin of {margin}.")
+    n_s1 = len(s1_peaks)
+    if n_s1 < margin * 2:
+        _dbg(f"Skipping correction pass: Not enough S1 peaks ({n_s1}) to apply a margin of {margin}.")
         return s1_peaks, debug_info, 0
-    rr_intervals_sec = np.diff(s1_peaks) / sample_rate
-    q1, q3 = np.percentile(rr_intervals_sec, [25, 75])
-    iqr = q3 - q1
-    stable_rr_intervals = rr_intervals_sec[
-        (rr_intervals_sec > (q1 - 1.5 * iqr)) & (rr_intervals_sec < (q3 + 1.5 * iqr))]
-    if len(stable_rr_intervals) < 1:
-        log_debug("Not enough stable R-R intervals to determine median. Skipping correction.")
+    limits = _discontinuity_thresholds(s1_peaks, sample_rate, params)
+    if limits is None:
+        _dbg("Not enough stable R-R intervals to determine median. Skipping correction.")
         return s1_peaks, debug_info, 0
-    median_rr_sec = np.median(stable_rr_intervals)
-    short_conflict_threshold_sec = median_rr_sec * params["rr_correction_threshold_pct"]
-    long_conflict_threshold_sec = median_rr_sec * params.get("rr_correction_long_interval_pct", 1.7)
-    log_debug(
-        f"Median R-R: {median_rr_sec:.3f}s. Short Threshold: < {short_conflict_threshold_sec:.3f}s. Long Threshold: > {long_conflict_threshold_sec:.3f}s.")
+    med, short_limit, long_limit = limits
+    _dbg("Median R-R: {:.3f}s. Short Threshold: < {:.3f}s. Long Threshold: > {:.3f}s.".format(med, short_limit, long_limit))
     waiver_strength, waiver_ratio = params["penalty_waiver_strength_ratio"], params["penalty_waiver_max_s2_s1_ratio"]
 
     s1 = np.ascontiguousarray(s1_peaks, dtype=np.int64)
@@ -121,37 +142,33 @@ def _fix_rhythmic_discontinuities(s1_peaks: np.ndarray, all_raw_peaks: np.ndarra
     n_out, n_ev, n_corr = C.c_int64(), C.c_int64(), C.c_int64()
     rc = _lib().bpm_fix_rhythmic_discontinuities(
         s1.ctypes.data, len(s1), raw.ctypes.data, len(raw), is_noise.ctypes.data, env.ctypes.data, floor.ctypes.data,
-        len(env), float(sample_rate), float(short_conflict_threshold_sec), float(long_conflict_threshold_sec),
-        float(waiver_strength), float(waiver_ratio), out.ctypes.data, C.byref(n_out), events, cap, C.byref(n_ev),
-        C.byref(n_corr))
+        len(env), float(sample_rate), float(short_limit), float(long_limit), float(waiver_strength), float(waiver_ratio),
+        out.ctypes.data, C.byref(n_out), events, cap, C.byref(n_ev), C.byref(n_corr))
     if rc != 0:
         raise ValueError(f"bpm_fix_rhythmic_discontinuities rejected its arguments (code {rc})")
 
-    corrected_debug_info = debug_info.copy()
-    log_debug(f"Checking for long intervals between beat {margin} and beat {len(s1_peaks) - margin}...")
-    short_started = False
-    for i in range(n_ev.value):
-        e = events[i]
-        if e.kind >= 5 and not short_started:
-            log_debug("Starting SHORT interval check...")
-            short_started = True
+    relabelled = dict(debug_info)
+    _dbg(f"Checking for long intervals between beat {margin} and beat {n_s1 - margin}...")
+    short_phase = False
+    for e in events[:n_ev.value]:
+        if e.kind >= 5 and not short_phase:
+            _dbg("Starting SHORT interval check...")
+            short_phase = True
         if e.kind == 3:
-            log_debug(f"Found LONG interval at {e.a / sample_rate:.2f}s. Investigating gap...")
+            _dbg(f"Found LONG interval at {_sec(e.a, sample_rate)}s. Investigating gap...")
         elif e.kind == 4:
-            candidate_s1, candidate_s2 = raw_keys[e.a], raw_keys[e.b]
-            log_debug(f"  - SUCCESS: Re-labeling S1/S2 pair at {candidate_s1 / sample_rate:.2f}s.")
-            original_reason_s1 = corrected_debug_info.get(candidate_s1, "Noise")
-            corrected_debug_info[candidate_s1] = f"{S1_CORRECTED_GAP}§ORIGINAL_REASON§{original_reason_s1}"
-            original_reason_s2 = corrected_debug_info.get(candidate_s2, "Noise")
-            corrected_debug_info[candidate_s2] = f"{S2_CORRECTED_GAP}§ORIGINAL_REASON§{original_reason_s2}"
+            first, second = raw_keys[e.a], raw_keys[e.b]
+            _dbg(f"  - SUCCESS: Re-labeling S1/S2 pair at {_sec(first, sample_rate)}s.")
+            for key, label in ((first, S1_CORRECTED_GAP), (second, S2_CORRECTED_GAP)):
+                relabelled[key] = f"{label}§ORIGINAL_REASON§{relabelled.get(key, 'Noise')}"
         elif e.kind == 5:
-            log_debug(
-                f"Found SHORT interval of {e.x:.3f}s between beats at {e.a / sample_rate:.2f}s and {e.b / sample_rate:.2f}s. Resolving...")
+            _dbg(f"Found SHORT interval of {e.x:.3f}s between beats at {_sec(e.a, sample_rate)}s and "
+                 f"{_sec(e.b, sample_rate)}s. Resolving...")
         elif e.kind == 6:
-            log_debug(f"  - Removing weaker peak at {e.a / sample_rate:.2f}s.")
-    if not short_started:
-        log_debug("Starting SHORT interval check...")
-    return out[:n_out.value].copy(), corrected_debug_info, int(n_corr.value)
+            _dbg(f"  - Removing weaker peak at {_sec(e.a, sample_rate)}s.")
+    if not short_phase:
+        _dbg("Starting SHORT interval check...")
+    return out[:n_out.value].copy(), relabelled, int(n_corr.value)
 
 
 def install(ref_module):
