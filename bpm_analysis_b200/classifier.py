@@ -88,7 +88,8 @@ class Classification(C.Structure):
 
 
 EXPORTED_SYMBOLS = ("bpm_host_abi_version", "bpm_host_format_fixed", "bpm_classify_peaks", "bpm_classify_peaks_batch",
-                    "bpm_classification_free", "bpm_host_threads", "bpm_host_gather_frames", "bpm_host_format_rows")
+                    "bpm_classification_free", "bpm_host_threads", "bpm_host_gather_frames", "bpm_host_gather_s24",
+                    "bpm_host_format_rows")
 
 
 class HostLibraryError(RuntimeError):
@@ -123,6 +124,8 @@ def load_host_library(path: str = HOST_LIB_PATH):
         lib.bpm_host_threads.restype, lib.bpm_host_threads.argtypes = C.c_int, []
         lib.bpm_host_gather_frames.restype = C.c_int
         lib.bpm_host_gather_frames.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int]
+        lib.bpm_host_gather_s24.restype = C.c_int
+        lib.bpm_host_gather_s24.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int]
         lib.bpm_host_format_rows.restype = C.c_int64
         lib.bpm_host_format_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_char_p, C.c_char_p,
                                              C.c_char_p, C.c_int, C.c_void_p, C.c_int64]

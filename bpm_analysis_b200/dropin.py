@@ -241,16 +241,20 @@ class DropIn:
         with self.lock:
             f32 = output_dtype(params) == "float32"
             sig_dtype = torch.float32 if f32 else torch.float64
-            pcm = np.asarray(pcm)
-            if pcm.dtype not in nat.PCM_DTYPES:
-                pcm = pcm.astype(np.float64)
-            pcm = np.ascontiguousarray(pcm)
+            from .wav24 import S24Recording
+            s24 = pcm if isinstance(pcm, S24Recording) else None      # 24-bit file left in its mapping (wav24.py)
+            if s24 is None:
+                pcm = np.asarray(pcm)
+                if pcm.dtype not in nat.PCM_DTYPES:
+                    pcm = pcm.astype(np.float64)
+                pcm = np.ascontiguousarray(pcm)
             channels = 1 if pcm.ndim == 1 else int(pcm.shape[1])
             n_in = int(pcm.shape[0])
             plan = rt.plan_filter(sample_rate, params)
             if plan.n_dec(n_in) <= PADLEN:
                 raise ValueError("The length of the input vector x must be greater than padlen, which is 15.")
-            frame_bytes = channels * pcm.dtype.itemsize
+            # bytes between kept frames IN THE SOURCE (3 per sample for a mapped 24-bit file, staged as int32)
+            frame_bytes = channels * (3 if s24 is not None else pcm.dtype.itemsize)
             sparse = plan.block == 1 and plan.stride > 1 and plan.stride * frame_bytes >= HOST_GATHER_MIN_PITCH_BYTES
             # the band-passed signal only stays out of HBM in the decimate-first order with a window the fused
             # epilogue takes; otherwise the runner writes it and it is simply not read back unless asked for
@@ -261,7 +265,9 @@ class DropIn:
             M = A.total_m
             tr.mark("pre.plan+slot")
             # -- ingest: the kept frames (or the whole recording) -> pinned staging -> device
-            if sparse:
+            if s24 is not None:
+                s24.gather_into(slot.stage.data_ptr(), plan.stride if sparse else 1)
+            elif sparse:
                 rc = self.host.bpm_host_gather_frames(C.c_void_p(pcm.ctypes.data), frame_bytes, n_in, plan.stride,
                                                       C.c_void_p(slot.stage.data_ptr()), 0)
                 if rc != 0:

@@ -47,7 +47,10 @@ def preprocess_pcm(audio_data: np.ndarray, sample_rate: int, params: Dict, want_
         logging.warning(f"Original 'downsample_factor' of {params['downsample_factor']} is too high for a "
                         f"{highcut:g}Hz filter with a {sample_rate}Hz sample rate.")
         logging.warning(f"Adjusting 'downsample_factor' to a safe value of {ds}.")
-    return dropin().preprocess(np.asarray(audio_data), int(sample_rate), params, bool(want_debug), bool(want_filtered))
+    from .wav24 import S24Recording
+    if not isinstance(audio_data, S24Recording):
+        audio_data = np.asarray(audio_data)
+    return dropin().preprocess(audio_data, int(sample_rate), params, bool(want_debug), bool(want_filtered))
 
 
 def read_wav(file_path: str):
@@ -55,13 +58,17 @@ def read_wav(file_path: str):
     and the decimate-first ingest (``bpm_host_gather_frames``) then touches one frame in ``ds``
     straight out of the page cache -- scipy's default read copies all of a 60-minute recording
     (345 MB, ~150 ms) to hand 2 MB of it to the filter.  Formats scipy cannot map (24-bit PCM) fall
-    back to the copying read; sample rate, dtype, channel layout and errors are scipy's either way."""
+    to ``wav24.map_s24`` -- the file mapped as bytes, the kept frames expanded to scipy's int32 by
+    ``bpm_host_gather_s24`` -- and only what that does not recognise to the copying read; sample rate,
+    dtype, channel layout, values and errors are scipy's either way."""
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         try:
             return wavfile.read(file_path, mmap=True)
         except ValueError:
-            return wavfile.read(file_path)
+            from .wav24 import map_s24
+            mapped = map_s24(file_path)
+            return mapped if mapped is not None else wavfile.read(file_path)
 
 
 def preprocess_audio(file_path: str, params: Dict, output_directory: str) -> Tuple[np.ndarray, int]:

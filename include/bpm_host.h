@@ -203,6 +203,13 @@ int bpm_host_threads(void);
 int bpm_host_gather_frames(const void* pcm, int64_t frame_bytes, int64_t n_frames, int64_t stride, void* out,
                            int n_threads);
 
+/* The same for 24-bit PCM (3-byte little-endian samples, `channels` per frame): out[j * channels + c] =
+ * sample c of frame j * stride as int32 with the 24 bits in the upper three bytes -- the array
+ * scipy.io.wavfile.read gives the reference for such a file (bpm_analysis.py:1014), which cannot be
+ * memory-mapped and which scipy expands in full.  stride 1 expands the whole recording. */
+int bpm_host_gather_s24(const void* pcm, int64_t channels, int64_t n_frames, int64_t stride, int32_t* out,
+                        int n_threads);
+
 /* ---- on-disk outputs ----------------------------------------------
  * One text table in one call: for every i < n (rows with NaN b[i] left out when skip_nan_b != 0)
  *     head  format(a[i], ".{prec_a}f")  mid  format(b[i], ".{prec_b}f")  tail

@@ -172,8 +172,8 @@ def test_float32_mode_halves_the_read_back_and_keeps_the_lists(svc, ref_params, 
 
 def test_preprocess_audio_reads_the_wav_through_a_memory_map(svc, ref_params, synth_inputs, tmp_path):
     """File ingest: mono / stereo int16, float32 and uint8 WAVs are mapped, not
-    copied; 24-bit PCM (which scipy cannot map) takes the copying read.  Same envelope as the
-    array-level call on the decoded samples."""
+    copied; 24-bit PCM (which scipy cannot map) is mapped as bytes and only its kept frames are expanded
+    (wav24.py, bpm_host_gather_s24).  Same envelope as the array-level call on the decoded samples."""
     import wave
     from scipy.io import wavfile
     from bpm_analysis_b200 import frontend
@@ -192,8 +192,19 @@ def test_preprocess_audio_reads_the_wav_through_a_memory_map(svc, ref_params, sy
     with wave.open(path24, "wb") as w:
         w.setnchannels(1), w.setsampwidth(3), w.setframerate(sr)
         w.writeframes((pcm.astype(np.int32) << 8).astype("<i4").view(np.uint8).reshape(-1, 4)[:, :3].tobytes())
+    from bpm_analysis_b200 import wav24
     sr24, x24 = frontend.read_wav(path24)
-    assert sr24 == sr and not isinstance(x24, np.memmap)
+    assert sr24 == sr and not isinstance(x24, np.memmap) and isinstance(x24, wav24.S24Recording)
     env24, _ = frontend.preprocess_audio(path24, ref_params, str(tmp_path))
     o24, _, _ = ref_port.preprocess_pcm(wavfile.read(path24)[1], sr, ref_params)
     assert rel_err(env24, o24) < TOL
+    # stereo, and a decimation small enough that the whole recording is expanded (no sparse gather)
+    st, sr_st = synth_inputs["stereo_20s"]
+    path24s = str(tmp_path / "pcm24s.wav")
+    with wave.open(path24s, "wb") as w:
+        w.setnchannels(2), w.setsampwidth(3), w.setframerate(sr_st)
+        w.writeframes((st.astype(np.int32) << 8).astype("<i4").view(np.uint8).reshape(-1, 4)[:, :3].tobytes())
+    for p in (ref_params, dict(ref_params, downsample_factor=2)):
+        env_s, rate_s = frontend.preprocess_audio(path24s, p, str(tmp_path))
+        o_s, o_rate_s, _ = ref_port.preprocess_pcm(wavfile.read(path24s)[1], sr_st, p)
+        assert rate_s == o_rate_s and rel_err(env_s, o_s) < (TOL if rate_s <= 12000 else 1e-6)

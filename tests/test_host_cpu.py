@@ -242,3 +242,65 @@ def test_distance_tiles_model_matches_scipy():
             pending += npend
             assert np.array_equal(got, want), (trial, own, halo)
     assert pending > 0
+
+
+def _write_wav24(path, samples, rate, extensible=False, junk_before_data=b""):
+    """24-bit little-endian PCM WAV from int32 `samples` ([n] or [n, ch], values within 24 bits)."""
+    import struct
+    x = np.asarray(samples, dtype=np.int64)
+    ch = 1 if x.ndim == 1 else x.shape[1]
+    b = (x.reshape(-1) & 0xFFFFFF).astype("<u4").view(np.uint8).reshape(-1, 4)[:, :3].tobytes()
+    if extensible:
+        guid = struct.pack("<H", 1) + bytes.fromhex("000000001000800000AA00389B71")
+        fmt = struct.pack("<HHIIHHHHI", 0xFFFE, ch, rate, rate * ch * 3, ch * 3, 24, 22, 24, (1 << ch) - 1) + guid
+    else:
+        fmt = struct.pack("<HHIIHH", 1, ch, rate, rate * ch * 3, ch * 3, 24)
+    body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt
+    if junk_before_data:
+        body += b"LIST" + struct.pack("<I", len(junk_before_data)) + junk_before_data + (b"\0" if len(junk_before_data) & 1 else b"")
+    body += b"data" + struct.pack("<I", len(b)) + b + (b"\0" if len(b) & 1 else b"")
+    with open(path, "wb") as fh:
+        fh.write(b"RIFF" + struct.pack("<I", len(body)) + body)
+
+
+def test_24_bit_wav_is_mapped_and_gathered_like_scipy_reads_it(tmp_path):
+    """bpm_analysis.py:1014 reads a 24-bit file through scipy (int32, the 24 bits in the upper bytes);
+    wav24.map_s24 + bpm_host_gather_s24 give the same values for the whole file and for every
+    decimation, without expanding the file."""
+    import warnings
+    from scipy.io import wavfile
+    from bpm_analysis_b200 import frontend, wav24
+    rng = np.random.default_rng(24)
+    cases = [("mono", rng.integers(-(1 << 23), 1 << 23, 50001), dict()),
+             ("stereo", rng.integers(-(1 << 23), 1 << 23, (20000, 2)), dict()),
+             ("ext3", rng.integers(-(1 << 23), 1 << 23, (7001, 3)), dict(extensible=True)),
+             ("junk", rng.integers(-(1 << 23), 1 << 23, 12345), dict(junk_before_data=b"INFOsoftware"[:11])),
+             ("edges", np.array([0, 1, -1, (1 << 23) - 1, -(1 << 23), 255, 256, -256] * 40), dict())]
+    for name, x, kw in cases:
+        path = str(tmp_path / f"{name}.wav")
+        _write_wav24(path, x, 8000, **kw)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            rate, want = wavfile.read(path)
+        assert want.dtype == np.int32 and np.array_equal(want >> 8, np.asarray(x).reshape(want.shape)), name
+        got = wav24.map_s24(path)
+        assert got is not None, name
+        assert got[0] == rate and got[1].shape == want.shape and got[1].dtype == want.dtype and len(got[1]) == len(want)
+        assert np.array_equal(np.asarray(got[1]), want), name
+        for stride in (1, 2, 7, 159, len(want) - 1, len(want), len(want) + 5):
+            assert np.array_equal(got[1].decimated(stride), want[::stride]), (name, stride)
+        r2, rec = frontend.read_wav(path)                   # the reference-facing reader takes the mapped route
+        assert r2 == rate and isinstance(rec, wav24.S24Recording)
+    # what the parser does not recognise is scipy's business
+    p16 = str(tmp_path / "p16.wav")
+    wavfile.write(p16, 8000, rng.integers(-30000, 30000, 4000).astype(np.int16))
+    assert wav24.map_s24(p16) is None
+    r16, a16 = frontend.read_wav(p16)
+    assert r16 == 8000 and isinstance(a16, np.ndarray) and a16.dtype == np.int16
+    cut = str(tmp_path / "cut.wav")
+    raw = open(str(tmp_path / "mono.wav"), "rb").read()
+    open(cut, "wb").write(raw[:len(raw) // 2])
+    assert wav24.map_s24(cut) is None
+    assert wav24.map_s24(str(tmp_path / "missing.wav")) is None
+    from bpm_analysis_b200 import classifier
+    assert classifier.load_host_library().bpm_host_gather_s24(None, 1, 10, 1, None, 0) != 0
