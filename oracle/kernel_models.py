@@ -301,3 +301,38 @@ def distance_tiles_model(pos: np.ndarray, val: np.ndarray, d: int, own: int = 10
             elif not any_open:
                 state[k] = 1
     return state == 1, n_pending
+
+
+def warp_first_knot_ge_model(t: np.ndarray, bound: int) -> int:
+    """Serial model of ``warp_first_knot_ge`` (csrc/floor.cu): first index r in [0, T] with t[r] >= bound,
+    narrowed 32 ways per step the way the warp does it (lane l probes lo + l * step; lanes past `hi`
+    count as "reached").  Returns (index, dependent probe rounds)."""
+    T = len(t)
+    lo, hi, rounds = 0, T, 0
+    while hi - lo > 32:
+        rounds += 1
+        step = (hi - lo + 31) // 32
+        ge = [(lo + l * step >= hi) or (int(t[lo + l * step]) >= bound) for l in range(32)]
+        f = ge.index(True) if any(ge) else 32
+        if f == 0:
+            return lo, rounds
+        lo, hi = lo + (f - 1) * step + 1, min(hi, lo + f * step)
+    rounds += 1
+    ge = [(lo + l >= hi) or (int(t[lo + l]) >= bound) for l in range(32)]
+    return (lo + ge.index(True)) if any(ge) else hi, rounds
+
+
+def select_groups_model(prefixes, active, first: bool):
+    """Model of ``sel_groups`` (csrc/select.cu): levels with equal resolved prefixes share one histogram.
+    -> (representative level of every group, group of every level or -1)."""
+    lvl, of = [], []
+    for l, (p, a) in enumerate(zip(prefixes, active)):
+        if not a:
+            of.append(-1)
+            continue
+        g = next((h for h, r in enumerate(lvl) if first or prefixes[r] == p), None)
+        if g is None:
+            lvl.append(l)
+            g = len(lvl) - 1
+        of.append(g)
+    return lvl, of

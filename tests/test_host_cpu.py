@@ -304,3 +304,35 @@ def test_24_bit_wav_is_mapped_and_gathered_like_scipy_reads_it(tmp_path):
     assert wav24.map_s24(str(tmp_path / "missing.wav")) is None
     from bpm_analysis_b200 import classifier
     assert classifier.load_host_library().bpm_host_gather_s24(None, 1, 10, 1, None, 0) != 0
+
+
+def test_warp_knot_search_model_matches_searchsorted():
+    """The 32-ary search the rolling-floor CTAs start with (csrc/floor.cu, warp_first_knot_ge): same
+    index as np.searchsorted(side='left') for every table size and bound, in at most
+    ceil(log32(T)) + 1 dependent rounds (a 13 k-knot table: 3, the bisection it replaced: 14)."""
+    rng = np.random.default_rng(11)
+    for T in (1, 2, 31, 32, 33, 34, 63, 64, 65, 100, 1023, 1024, 1025, 1057, 12856, 40000):
+        t = np.sort(rng.choice(np.arange(0, 40 * T + 50), size=T, replace=False)).astype(np.int32)
+        bounds = list(rng.integers(-5, int(t[-1]) + 10, 60)) + [int(t[0]), int(t[0]) - 1, int(t[-1]), int(t[-1]) + 1]
+        bounds += [int(v) for v in t[rng.integers(0, T, 20)]] + [int(v) + 1 for v in t[rng.integers(0, T, 20)]]
+        worst = 0
+        for b in bounds:
+            got, rounds = kernel_models.warp_first_knot_ge_model(t, int(b))
+            assert got == int(np.searchsorted(t, b, side="left")), (T, b)
+            worst = max(worst, rounds)
+        limit = 1
+        while 32 ** limit < T:
+            limit += 1
+        assert worst <= limit + 1, (T, worst)
+    assert kernel_models.warp_first_knot_ge_model(np.arange(12856, dtype=np.int32) * 85, 500000)[1] <= 3
+
+
+def test_select_level_groups_model():
+    """Levels with the same resolved prefix are served by one histogram (csrc/select.cu, sel_groups)."""
+    g = kernel_models.select_groups_model
+    assert g([0, 0, 0], [True, True, True], first=True) == ([0], [0, 0, 0])
+    assert g([7, 7, 9], [True, True, True], first=False) == ([0, 2], [0, 0, 1])
+    assert g([7, 8, 7], [True, False, True], first=False) == ([0], [0, -1, 0])
+    assert g([1, 2, 3], [True, True, True], first=False) == ([0, 1, 2], [0, 1, 2])
+    assert g([5, 5, 5], [False, False, False], first=False) == ([], [-1, -1, -1])
+    assert g([4, 6, 6], [False, True, True], first=False) == ([1], [-1, 0, 0])
