@@ -43,7 +43,13 @@ def test_golden_files_byte_for_byte(tmp_path):
     assert len(case["files"]["_Debug_Log.md"]) > 100_000
     for s in SUFFIXES:
         assert unstamped(got[s]) == unstamped(case["files"][s]), s
-    # what heartbeat_labeler.py:30-46 reads back: one "## Time" header per logged event
+    # what heartbeat_labeler.py:36-41 reads back: pd.read_csv of the BPM table, by column name
+    table = pd.read_csv(paths["csv"])
+    fm = case["final_metrics"]
+    assert list(table.columns) == ["Time (s)", "Average BPM"] and len(table) == int((~np.isnan(fm["smoothed_bpm"].values)).sum())
+    assert np.allclose(table["Time (s)"].values, fm["bpm_times"], atol=5.1e-4, rtol=0)
+    assert np.allclose(table["Average BPM"].values, fm["smoothed_bpm"].values, atol=5.1e-4, rtol=0)
+    # one "## Time" header per logged event
     n_events = got["_Debug_Log.md"].count(b"## Time: `")
     n_peaks = sum(1 for p in case["raw_peaks"] if case["analysis_data"]["beat_debug_info"].get(p))
     assert n_events == n_peaks + len(case["analysis_data"]["trough_indices"])
